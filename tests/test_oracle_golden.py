@@ -1,0 +1,169 @@
+"""Pin the CPU oracle against golden vectors produced by the LIVE reference functions
+(``oracle/gen_golden.py``).  CPU only; never imports the reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bodies, fast_nn, functions, losses, synth
+from helpers import assert_grad_close, rel_err
+
+T = torch.as_tensor
+
+KL_CASES = ['small_mast3r', 'small_vggt', 'small_mast3r_allkept', 'small_mast3r_allmasked',
+            'small_vggt_allmasked', 'odd_vggt', 'odd_mast3r', 'cfg1_mast3r', 'mid_vggt']
+
+
+def kl_inputs(meta):
+    N, C, seed, var, mode = [int(v) for v in meta]
+    variant = 'mast3r' if var == 0 else 'vggt'
+    mode = ['bernoulli', 'all', 'none'][mode]
+    f1, f2 = synth.features(seed * 16, N, C)
+    t12 = synth.teacher_volume(seed * 16 + 1, N, variant)
+    t21 = synth.teacher_volume(seed * 16 + 2, N, variant)
+    m1 = synth.patch_mask(seed * 16 + 3, N, mode=mode)
+    m2 = synth.patch_mask(seed * 16 + 4, N, mode=mode)
+    return f1, f2, t12, t21, m1, m2, variant
+
+
+@pytest.mark.parametrize('case', KL_CASES)
+def test_cost_kl_oracle(golden, case):
+    g = golden('cost_kl.npz')
+    f1, f2, t12, t21, m1, m2, variant = kl_inputs(g[f'{case}/meta'])
+    f1.requires_grad_(True)
+    f2.requires_grad_(True)
+    loss = bodies.cost_volume_kl(f1, f2, t12, t21, m1, m2, variant)
+    want = float(g[f'{case}/loss'])
+    assert abs(float(loss) - want) <= 1e-5 * max(1.0, abs(want))
+    if loss.requires_grad and (m1.any() or m2.any()):
+        g1, g2 = torch.autograd.grad(loss, [f1, f2])
+        assert_grad_close(g1, T(g[f'{case}/g1']), cos_min=0.99999, name='g1', norm_rtol=1e-3)
+        assert_grad_close(g2, T(g[f'{case}/g2']), cos_min=0.99999, name='g2', norm_rtol=1e-3)
+    else:
+        assert float(np.abs(g[f'{case}/g1']).max()) == 0.0
+
+
+AP_CASES = ['small_mast3r', 'small_vggt', 'small_me', 'k1_mast3r', 'odd_vggt', 'cfg1_mast3r', 'mid_me']
+
+
+@pytest.mark.parametrize('case', AP_CASES)
+def test_smooth_ap_oracle(golden, case):
+    g = golden('smooth_ap.npz')
+    K, C, seed, var = [int(v) for v in g[f'{case}/meta']]
+    variant = ['mast3r', 'vggt', 'me'][var]
+    g1 = T(g[f'{case}/g1']).requires_grad_(True)
+    g2 = T(g[f'{case}/g2']).requires_grad_(True)
+    kp1, kp2 = T(g[f'{case}/kp1']), T(g[f'{case}/kp2'])
+    p1, p2 = T(g[f'{case}/p1']), T(g[f'{case}/p2'])
+    d1 = bodies.sample_tokens(g1[None], 16, 16, kp1[None], normalize=True)[0]
+    d2 = bodies.sample_tokens(g2[None], 16, 16, kp2[None], normalize=True)[0]
+    np.testing.assert_allclose(d1.detach().numpy(), g[f'{case}/d1'], rtol=0, atol=1e-6)
+    loss = bodies.smooth_ap(d1, d2, p1, p2, variant)
+    assert rel_err(loss, g[f'{case}/loss']) <= 1e-5
+    gg1, gg2 = torch.autograd.grad(loss, [g1, g2])
+    assert_grad_close(gg1, T(g[f'{case}/grad_g1']), cos_min=0.9999, name='grad_g1', norm_rtol=1e-2)
+    assert_grad_close(gg2, T(g[f'{case}/grad_g2']), cos_min=0.9999, name='grad_g2', norm_rtol=1e-2)
+
+
+RANK_CASES = ['small', 'novalid', 'cfg1', 'k1', 'notanh']
+
+
+def load_head_case(g, case):
+    K, D, seed, use_tanh = [int(v) for v in g[f'{case}/meta']]
+    head = losses.DepthHead(D, use_tanh=bool(use_tanh))
+    synth.load_head(head, {k: T(g[f'{case}/{k}']) for k in ('W1', 'b1', 'gamma', 'beta', 'w2', 'b2')})
+    kf1 = T(g[f'{case}/kf1']).requires_grad_(True)
+    kf2 = T(g[f'{case}/kf2']).requires_grad_(True)
+    return head, kf1, kf2, T(g[f'{case}/kd1']), T(g[f'{case}/kd2'])
+
+
+@pytest.mark.parametrize('case', RANK_CASES)
+def test_depth_losses_oracle(golden, case):
+    g = golden('ranking.npz')
+    head, kf1, kf2, kd1, kd2 = load_head_case(g, case)
+    params = list(head.fusion_layer.parameters())
+    names = ['kf1', 'kf2', 'W1', 'b1', 'gamma', 'beta', 'w2', 'b2']
+    l1, rank = bodies.depth_losses(head, kf1, kf2, kd1, kd2)
+    hinge = losses.intra_depth_loss(head, kf1, kd1)
+    for tag, val in (('l1', l1), ('rank', rank), ('hinge', hinge)):
+        want = float(g[f'{case}/{tag}/loss'])
+        assert abs(float(val) - want) <= 2e-6 * max(1.0, abs(want)), tag
+        if not val.requires_grad:
+            assert want == 0.0
+            continue
+        grads = torch.autograd.grad(val, [kf1, kf2] + params, allow_unused=True, retain_graph=True)
+        for n_, got in zip(names, grads):
+            ref = T(g[f'{case}/{tag}/grad_{n_}'])
+            got = torch.zeros_like(ref) if got is None else got
+            assert_grad_close(got, ref, cos_min=0.9999, name=f'{tag}/{n_}', norm_rtol=1e-2)
+
+
+def test_helpers_oracle(golden):
+    g = golden('helpers.npz')
+    fmap, pts = T(g['interp/fmap']), T(g['interp/pts'])
+    for nrm in (False, True):
+        out = functions.interpolate_features(fmap, pts, h=9 * 14, w=13 * 14, normalize=nrm)
+        np.testing.assert_allclose(out.numpy(), g[f'interp/out_norm{int(nrm)}'], rtol=0, atol=1e-6)
+    out = functions.interpolate_features(T(g['interp16/fmap']), T(g['interp16/pts']), h=320, w=480,
+                                         normalize=False, patch_size=16, stride=16)
+    np.testing.assert_allclose(out.numpy(), g['interp16/out'], rtol=0, atol=1e-6)
+    out = functions.extract_kp_depth(T(g['kpdepth/depth']), T(g['kpdepth/kp']))
+    np.testing.assert_allclose(out.numpy(), g['kpdepth/out'], rtol=0, atol=1e-6)
+    kp = T(g['kpmask/kp'])
+    assert (functions.get_patch_mask_from_kp_tensor(kp, 168, 224, 14).numpy() == g['kpmask/out']).all()
+    assert (functions.get_patch_mask_from_kp_tensor(kp - 1000, 168, 224, 14).numpy() == g['kpmask/out_empty']).all()
+    xs = T(g['sigmoid/x'])
+    np.testing.assert_allclose(functions.sigmoid(xs, 0.01).numpy(), g['sigmoid/y_t001'], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(functions.sigmoid(xs).numpy(), g['sigmoid/y_t1'], rtol=1e-6, atol=0)
+    cost, m1, m2 = T(g['mpc/cost']), T(g['mpc/m1']), T(g['mpc/m2'])
+    np.testing.assert_allclose(functions.get_masked_patch_cost(cost, m1).numpy(), g['mpc/rownorm'], rtol=1e-6)
+    np.testing.assert_allclose(functions.get_masked_patch_cost(cost, m1, use_softmax=True, temperature=0.5).numpy(),
+                               g['mpc/softmax'], rtol=1e-6)
+    np.testing.assert_allclose(functions.get_masked_patch_cost(cost, m1, m2).numpy(), g['mpc/rownorm_m2'], rtol=1e-6)
+    assert rel_err(losses.kl_divergence_map(T(g['klmap/t']), T(g['klmap/s'])), g['klmap/out']) < 1e-6
+    _, idx = functions.filter_kp_by_conf(T(g['conf/kp']), T(g['conf/mask']))
+    assert (idx.numpy() == g['conf/idx']).all()
+    for mode in ('all', 'proper', 'dual'):
+        got = losses.infonce(T(g['infonce/d1']), T(g['infonce/d2']), T(g['infonce/valid']), mode=mode)
+        assert rel_err(got, g[f'infonce/{mode}']) < 1e-5
+
+
+def test_fast_nn_oracle(golden):
+    g = golden('fast_nn.npz')
+    A, B = T(g['exact/A']), T(g['exact/B'])
+    for tag, kw in (('dot', dict(dist='dot')), ('dot_blk', dict(dist='dot', block_size=128)),
+                    ('l2', dict(dist='l2')), ('l2_blk', dict(dist='l2', block_size=100))):
+        a, b = fast_nn.bruteforce_reciprocal_nns(A, B, device='cpu', **kw)
+        assert a.dtype == np.int64 and b.dtype == np.int64
+        assert (a == g[f'exact/{tag}/nnA']).all(), tag
+        assert (b == g[f'exact/{tag}/nnB']).all(), tag
+    # blocked == single shot on exact inputs (lowest-index ties in both)
+    assert (g['exact/dot/nnA'] == g['exact/dot_blk/nnA']).all()
+    assert (g['exact/dot/nnB'] == g['exact/dot_blk/nnB']).all()
+    with pytest.raises(ValueError):
+        fast_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist='cosine')
+    d1, d2 = T(g['maps/d1']), T(g['maps/d2'])
+    for tag, kw in (('s8', dict(subsample_or_initxy1=8)), ('s4', dict(subsample_or_initxy1=4))):
+        xy1, xy2 = fast_nn.fast_reciprocal_NNs(d1, d2, device='cpu', dist='dot', block_size=2 ** 10, **kw)
+        assert (xy1 == g[f'maps/{tag}/xy1']).all() and (xy2 == g[f'maps/{tag}/xy2']).all()
+        assert xy1.dtype == g[f'maps/{tag}/xy1'].dtype
+    i1, i2 = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=8, ret_xy=False, device='cpu',
+                                         dist='dot', block_size=2 ** 10)
+    assert (i1 == g['maps/s8_idx/i1']).all() and (i2 == g['maps/s8_idx/i2']).all()
+    xy1, xy2 = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=(g['maps/seeds/x'], g['maps/seeds/y']),
+                                           pixel_tol=3, device='cpu', dist='dot', block_size=2 ** 10)
+    assert (xy1 == g['maps/seeds_tol3/xy1']).all() and (xy2 == g['maps/seeds_tol3/xy2']).all()
+    xy1, xy2, basin = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=8, ret_basin=True, device='cpu',
+                                                  dist='dot', block_size=2 ** 10)
+    assert (xy1 == g['maps/basin/xy1']).all() and (basin == g['maps/basin/basin']).all()
+    x1, x2 = fast_nn.merge_corres(g['merge/i1'], g['merge/i2'], (48, 64), (48, 64))
+    assert (x1 == g['merge/xy1']).all() and (x2 == g['merge/xy2']).all()
+    j1, j2, jdx = fast_nn.merge_corres(g['merge/i1'], g['merge/i2'], ret_xy=False, ret_index=True)
+    assert (j1 == g['merge/j1']).all() and (j2 == g['merge/j2']).all() and (jdx == g['merge/jdx']).all()
+    with pytest.raises(AssertionError):
+        fast_nn.merge_corres(g['merge/i1'].astype(np.int64), g['merge/i2'].astype(np.int64))
+    # KDTree branch of the CPU path agrees with brute-force l2 on generic inputs
+    p1 = torch.rand(12, 16, 3, generator=synth._gen(3))
+    p2 = p1 + 0.01 * torch.rand(12, 16, 3, generator=synth._gen(4))
+    a1, a2 = fast_nn.fast_reciprocal_NNs(p1, p2, subsample_or_initxy1=4, device='cpu')
+    b1, b2 = fast_nn.fast_reciprocal_NNs(p1, p2, subsample_or_initxy1=4, device='cpu', dist='l2')
+    assert (a1 == b1).all() and (a2 == b2).all()
