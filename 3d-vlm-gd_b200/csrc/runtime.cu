@@ -1,0 +1,93 @@
+// lib3dgd runtime: error state, driver entry points (TMA descriptor encoding), debug GEMM entry.
+#include "../../include/gd3.h"
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+#include <mutex>
+
+namespace gd3 {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+namespace tc {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // resolved through the runtime so the library does not link libcuda directly
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t k_extent, int64_t rows, int64_t batch,
+                   int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return GD3_ERR_CUDA;
+  }
+  GD3_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  GD3_REQUIRE(row_stride_elems % 8 == 0 && (batch <= 1 || batch_stride_elems % 8 == 0),
+              "TMA strides must be multiples of 16 bytes (row stride %lld, batch stride %lld elements)",
+              (long long)row_stride_elems, (long long)batch_stride_elems);
+  GD3_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+  cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_elems * 2,
+                           (cuuint64_t)(batch > 1 ? batch_stride_elems : row_stride_elems * rows) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (k=%lld rows=%lld batch=%lld ld=%lld)", (int)r,
+              (long long)k_extent, (long long)rows, (long long)batch, (long long)row_stride_elems);
+    return GD3_ERR_CUDA;
+  }
+  return GD3_OK;
+}
+
+}  // namespace tc
+}  // namespace gd3
+
+using namespace gd3;
+
+extern "C" {
+
+int gd3_version(void) { return GD3_VERSION; }
+const char* gd3_last_error(void) { return gd3::last_error(); }
+
+int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
+                        int64_t lda, int64_t ldb, int64_t ldc, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GD3_REQUIRE(A && B && C, "gd3_debug_gemm_bf16: null pointer");
+  GD3_REQUIRE(tile_n == 128 || tile_n == 256, "gd3_debug_gemm_bf16: tile_n must be 128 or 256");
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = tc::make_tmap_bf16(&ta, A, K, M, batch, lda, M * lda, tc::BM))) return rc;
+  if ((rc = tc::make_tmap_bf16(&tb, B, K, N, batch, ldb, N * ldb, tile_n))) return rc;
+  tc::EpiStoreF32::Params ep{C, (int)M, (int)N, ldc, M * ldc, 1.0f};
+  tc::GemmShape s{(int)M, (int)N, (int)K, (int)batch};
+  if (tile_n == 256) return tc::launch_gemm<256, 4, tc::EpiStoreF32>(ta, tb, s, ep, stream);
+  return tc::launch_gemm<128, 8, tc::EpiStoreF32>(ta, tb, s, ep, stream);
+}
+
+}  // extern "C"

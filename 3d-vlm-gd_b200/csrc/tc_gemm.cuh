@@ -1,0 +1,372 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with a pluggable epilogue.
+//
+//   D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]        (both operands K-major bf16, fp32 accumulate)
+//
+// One CTA per SM, static round-robin over (batch, m-tile, n-tile).  Roles:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor.3d -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : MMA issuer    (one thread issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+//                 + owner of the TMEM allocation (2 accumulator buffers of BN columns)
+//   warps 2..   : epilogue      (tcgen05.ld 32x32b -> registers -> Epi functor); the accumulator is
+//                 double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
+// The accumulator never goes to HBM unless the epilogue functor writes it.
+//
+// Descriptor bit layouts follow the PTX ISA "tcgen05 matrix/instruction descriptor" tables (the
+// CuTe headers cute/arch/mma_sm100_desc.hpp document the same fields).
+#pragma once
+
+#include "common.cuh"
+
+namespace gd3 {
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M (rows of A per tile) == TMEM lanes
+constexpr int BK = 64;           // K elements per stage = one 128-byte swizzle atom of bf16
+constexpr int UMMA_K = 16;       // K per tcgen05.mma for 16-bit inputs
+constexpr int PRODUCER_WARPS = 2;  // warp 0 = TMA, warp 1 = MMA
+
+__host__ __device__ constexpr int stage_bytes(int BN) { return (BM + BN) * BK * 2; }
+__host__ __device__ constexpr int num_stages(int BN) { return BN >= 256 ? 4 : (BN >= 128 ? 6 : 8); }
+// dynamic smem: 1024 B alignment slack + ring + epilogue scratch + barriers
+__host__ __device__ constexpr int smem_bytes(int BN, int epi_scratch) {
+  return 1024 + num_stages(BN) * stage_bytes(BN) + epi_scratch + 256;
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x N x 16, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base_lane + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (PTX ISA "shared memory descriptor"):
+//   [0,14)  start address >> 4      [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024)      [46,48) version = 1 (Blackwell)
+//   [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc_k128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: fp32 D, bf16 A/B, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ epilogue context
+struct EpiCtx {
+  int b, m0, n0;        // batch index and tile origin
+  uint32_t tmem;        // TMEM address of this tile's accumulator, lane field already set to the warp's quadrant
+  int row;              // this thread's row inside the tile (0..127) == TMEM lane
+  int col_begin;        // this warp's column range inside the tile [col_begin, col_end)
+  int col_end;
+  int lane;             // lane id
+  int epi_warp;         // 0..EPI_WARPS-1
+  uint8_t* scratch;     // per-CTA epilogue scratch in smem (Epi::kScratchBytes)
+};
+
+// ------------------------------------------------------------------ the kernel
+template <int BN, int EPI_WARPS, class Epi>
+__global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m,
+                   int tiles_n, int batch, int k_blocks, typename Epi::Params ep) {
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS");
+  constexpr int STAGES = num_stages(BN);
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int STAGE_BYTES = stage_bytes(BN);
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* scratch = ring + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + Epi::kScratchBytes);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;    // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = tiles_m * tiles_n * batch;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int b = t / (tiles_m * tiles_n);
+        const int r = t - b * (tiles_m * tiles_n);
+        const int m0 = (r / tiles_n) * BM;
+        const int n0 = (r % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, m0, b);
+          tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, n0, b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc_k128(sa);
+          const uint64_t db = make_smem_desc_k128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);         // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - PRODUCER_WARPS;
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    constexpr int PARTS = EPI_WARPS / 4;             // warps sharing a quadrant split the columns
+    const int part = (PARTS == 1) ? 0 : (ew >> 2);   // ew 0..3 -> part 0, 4..7 -> part 1 (quad = warp & 3 differs per ew)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int b = t / (tiles_m * tiles_n);
+      const int r = t - b * (tiles_m * tiles_n);
+      EpiCtx cx;
+      cx.b = b;
+      cx.m0 = (r / tiles_n) * BM;
+      cx.n0 = (r % tiles_n) * BN;
+      cx.row = quad * 32 + lane;
+      cx.col_begin = part * (BN / PARTS);
+      cx.col_end = cx.col_begin + BN / PARTS;
+      cx.lane = lane;
+      cx.epi_warp = ew;
+      cx.scratch = scratch;
+      cx.tmem = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      Epi::run(ep, cx);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+// 3-D tensor map over a batched K-major bf16 matrix: dims (K, rows, batch), box (64, box_rows, 1),
+// 128-byte swizzle, out-of-bounds elements read as zero (this is what pads ragged N / K).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t k_extent, int64_t rows, int64_t batch,
+                   int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows);
+
+struct GemmShape {
+  int M, N, K, batch;
+};
+
+template <int BN, int EPI_WARPS, class Epi>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
+                const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
+  if (s.M <= 0 || s.N <= 0 || s.batch <= 0) return GD3_OK;
+  GD3_REQUIRE(s.K > 0, "tc_gemm: K must be positive");
+  auto kern = tc_gemm_kernel<BN, EPI_WARPS, Epi>;
+  constexpr int SMEM = smem_bytes(BN, Epi::kScratchBytes);
+  static_assert(SMEM <= 227 * 1024, "tc_gemm shared memory budget");
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    GD3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const int tiles_m = ceil_div(s.M, BM), tiles_n = ceil_div(s.N, BN);
+  const long long total = 1LL * tiles_m * tiles_n * s.batch;
+  int grid = num_sms();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (total < grid) grid = static_cast<int>(total);
+  kern<<<grid, (PRODUCER_WARPS + EPI_WARPS) * 32, SMEM, stream>>>(tmA, tmB, tiles_m, tiles_n, s.batch,
+                                                                ceil_div(s.K, BK), ep);
+  GD3_CHECK_LAUNCH();
+  return GD3_OK;
+}
+
+// ------------------------------------------------------------------ a plain epilogue: store fp32
+// C[b][m][n] = alpha * acc   (row-major, leading dimension ldc, batch stride in elements)
+struct EpiStoreF32 {
+  static constexpr int kScratchBytes = 0;
+  struct Params {
+    float* C;
+    int M, N;
+    int64_t ldc, batch_stride;
+    float alpha;
+  };
+  __device__ static void run(const Params& p, const EpiCtx& cx) {
+    const int m = cx.m0 + cx.row;
+    float* crow = p.C + cx.b * p.batch_stride + static_cast<int64_t>(m) * p.ldc;
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (p.batch_stride % 4 == 0);
+    for (int c = cx.col_begin; c < cx.col_end; c += 32) {
+      float v[32];
+      tmem_ld32(cx.tmem + c, v);       // warp-collective: every lane participates, stores are predicated
+      const int n = cx.n0 + c;
+      if (m < p.M) {
+        if (vec_ok && n + 32 <= p.N) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o = make_float4(v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha, v[4 * q + 2] * p.alpha,
+                                   v[4 * q + 3] * p.alpha);
+            *reinterpret_cast<float4*>(crow + n + 4 * q) = o;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if (n + q < p.N) crow[n + q] = v[q] * p.alpha;
+        }
+      }
+    }
+  }
+};
+
+}  // namespace tc
+}  // namespace gd3

@@ -1,0 +1,123 @@
+"""ctypes binding of lib3dgd.so (the C ABI declared in include/gd3.h).
+
+This file is the reference-side stub INTEGRATION.md describes: plain pointers and sizes in, error
+codes out.  Torch is used only to obtain device pointers, the current stream and workspace memory.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get('GD3_LIB', os.path.join(os.path.dirname(_HERE), 'lib', 'lib3dgd.so'))
+
+# every symbol include/gd3.h declares: name -> (restype, argtypes)
+_c = ctypes
+_i64, _int, _vp, _sz, _f32 = _c.c_int64, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_float
+SYMBOLS = {
+    'gd3_version': (_int, []),
+    'gd3_last_error': (_c.c_char_p, []),
+    'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
+    'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    'gd3_debug_gemm_bf16': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
+}
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+DIST = {'dot': 0, 'l2': 1}
+VARIANT = {'mast3r': 0, 'vggt': 1, 'me': 2}
+
+_lib = None
+
+
+class Gd3Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load lib3dgd.so once.  Raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Gd3Error(f'lib3dgd.so not found at {LIB_PATH}; build it with '
+                           f'`python 3d-vlm-gd_b200/build.py` (there is no CPU / PyTorch fallback)')
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().gd3_last_error().decode(errors='replace')
+        if rc == -1:
+            raise ValueError(msg)
+        raise Gd3Error(f'lib3dgd error {rc}: {msg}')
+
+
+def require_cuda(*tensors):
+    if not torch.cuda.is_available():
+        raise Gd3Error('gd3 needs a CUDA device (sm_100a); there is no CPU fallback')
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ValueError('gd3 ops take CUDA tensors')
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes, device):
+    """Workspace from torch's caching allocator (caller-owned as the C ABI requires)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def dtype_code(t):
+    if t.dtype == torch.float32:
+        return DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    raise ValueError(f'unsupported feature dtype {t.dtype} (float32 or bfloat16)')
+
+
+# ---------------------------------------------------------------------------------------------
+def reciprocal_nn(A, B, dist='dot', want_A=True, want_B=True):
+    """nn_A, nn_B (int64 CUDA tensors or None) for fp32 CUDA descriptors A (nA, D), B (nB, D)."""
+    if dist not in DIST:
+        raise ValueError(f'Unknown {dist=}')
+    require_cuda(A, B)
+    lib = load()
+    A = A.contiguous().float()
+    B = B.contiguous().float()
+    nA, nB = A.shape[0], B.shape[0]
+    if A.shape[1] != B.shape[1]:
+        raise ValueError('descriptor dimensions differ')
+    nn_A = torch.empty(nA, dtype=torch.int64, device=A.device) if want_A else None
+    nn_B = torch.empty(nB, dtype=torch.int64, device=A.device) if want_B else None
+    ws_bytes = lib.gd3_reciprocal_nn_workspace(nA, nB)
+    ws = workspace(ws_bytes, A.device)
+    with torch.cuda.device(A.device):
+        check(lib.gd3_reciprocal_nn(ptr(A), nA, ptr(B), nB, A.shape[1], DIST[dist], ptr(nn_A), ptr(nn_B),
+                                    ptr(ws), ws.numel(), stream_ptr()))
+    return nn_A, nn_B
+
+
+def debug_gemm_bf16(A, B, tile_n=256):
+    """C[b] = A[b] @ B[b].T through the tcgen05 GEMM (A: (b, M, K) bf16, B: (b, N, K) bf16) -> fp32."""
+    require_cuda(A, B)
+    lib = load()
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16 and A.dim() == 3 and B.dim() == 3
+    A = A.contiguous()
+    B = B.contiguous()
+    b, M, K = A.shape
+    N = B.shape[1]
+    C = torch.empty(b, M, N, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.gd3_debug_gemm_bf16(ptr(A), ptr(B), ptr(C), M, N, K, b, K, K, N, tile_n, stream_ptr()))
+    return C

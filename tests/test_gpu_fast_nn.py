@@ -1,0 +1,137 @@
+"""GPU parity: tcgen05 GEMM plumbing and the reciprocal-NN matcher (through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fast_nn as oracle_nn
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def gd3mod():
+    import gd3
+    from gd3 import _lib
+    _lib.load()
+    return gd3
+
+
+@pytest.mark.parametrize('tile_n', [128, 256])
+@pytest.mark.parametrize('shape', [(1, 128, 256, 64), (2, 256, 512, 768), (3, 200, 333, 136), (1, 1369, 1369, 1024)])
+def test_tc_gemm_matches_torch(gd3mod, tile_n, shape):
+    """The hand-written tcgen05/TMA GEMM against a plain fp32 matmul of the same bf16 inputs."""
+    from gd3 import _lib
+    b, M, N, K = shape
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(b, M, K, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(b, N, K, generator=g).to(torch.bfloat16).cuda()
+    C = _lib.debug_gemm_bf16(A, B, tile_n=tile_n)
+    torch.cuda.synchronize()
+    ref = torch.matmul(A.float().cpu(), B.float().cpu().transpose(1, 2))
+    err = (C.cpu() - ref).abs().max().item()
+    assert err <= 1e-3 * (K ** 0.5), f'max abs err {err}'
+
+
+def test_tc_gemm_exact_integers(gd3mod):
+    """Small-integer operands: every partial sum is exact, so the result must be bit-identical."""
+    from gd3 import _lib
+    g = torch.Generator().manual_seed(5)
+    A = torch.randint(-4, 5, (2, 384, 320), generator=g).float()
+    B = torch.randint(-4, 5, (2, 272, 320), generator=g).float()
+    C = _lib.debug_gemm_bf16(A.to(torch.bfloat16).cuda(), B.to(torch.bfloat16).cuda(), tile_n=256)
+    assert torch.equal(C.cpu(), A @ B.transpose(1, 2))
+
+
+@pytest.mark.parametrize('dist', ['dot', 'l2'])
+def test_reciprocal_nn_golden(gd3mod, golden, dist):
+    from gd3.compat import fast_nn
+    g = golden('fast_nn.npz')
+    A, B = g['exact/A'], g['exact/B']
+    for blk in (None, 128 if dist == 'dot' else 100):
+        a, b = fast_nn.bruteforce_reciprocal_nns(A, B, device='cuda', dist=dist, block_size=blk)
+        assert a.dtype == np.int64 and b.dtype == np.int64
+        assert (a == g[f'exact/{dist}/nnA']).all()
+        assert (b == g[f'exact/{dist}/nnB']).all()
+
+
+def test_reciprocal_nn_cfg3_exact_set(gd3mod):
+    """BASELINE.json config 3: 8192 x 8192 x 24, bit-exact indices on the exactly-representable set."""
+    from gd3.compat import fast_nn
+    A = synth.nn_exact_set(301, 8192)
+    B = synth.nn_exact_set(302, 8192)
+    a, b = fast_nn.bruteforce_reciprocal_nns(A, B, device='cuda', dist='dot', block_size=2 ** 13)
+    ra, rb = oracle_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist='dot', block_size=2 ** 13)
+    assert (a == ra).all() and (b == rb).all()
+    # size-independent property: the reported neighbour attains the row / column maximum
+    S = A @ B.T
+    assert torch.equal(S[torch.arange(8192), torch.from_numpy(a)], S.max(dim=1).values)
+    assert torch.equal(S[torch.from_numpy(b), torch.arange(8192)], S.max(dim=0).values)
+
+
+def test_reciprocal_nn_real_set_near_ties_only(gd3mod):
+    """Gaussian unit descriptors: any index mismatch vs the CPU matmul must be a rounding-level near-tie."""
+    from gd3.compat import fast_nn
+    A = synth.nn_real_set(303, 4096)
+    B = synth.nn_real_set(304, 5000)
+    a, b = fast_nn.bruteforce_reciprocal_nns(A, B, device='cuda', dist='dot')
+    ra, rb = oracle_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist='dot')
+    S = (A.double() @ B.double().T)
+    bad = np.nonzero(a != ra)[0]
+    for i in bad:
+        assert abs(S[i, a[i]] - S[i, ra[i]]) < 1e-6
+    bad_b = np.nonzero(b != rb)[0]
+    for j in bad_b:
+        assert abs(S[b[j], j] - S[rb[j], j]) < 1e-6
+    assert len(bad) <= 4 and len(bad_b) <= 4
+
+
+def test_reciprocal_nn_edge_cases(gd3mod):
+    from gd3 import _lib
+    from gd3.compat import fast_nn
+    A = synth.nn_exact_set(1, 37)
+    B = synth.nn_exact_set(2, 5)
+    with pytest.raises(ValueError):
+        fast_nn.bruteforce_reciprocal_nns(A, B, device='cuda', dist='cosine')
+    a, b = fast_nn.bruteforce_reciprocal_nns(A, B, device='cuda', dist='dot')
+    ra, rb = oracle_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist='dot')
+    assert (a == ra).all() and (b == rb).all()
+    # duplicated rows -> ties -> lowest index
+    D = torch.cat([B, B, B])
+    a, _ = fast_nn.bruteforce_reciprocal_nns(B, D, device='cuda', dist='l2')
+    assert (a == np.arange(5)).all()
+    # empty query (cdistMatcher contract, mast3r/fast_nn.py:80-81)
+    m = fast_nn.cdistMatcher(B, device='cuda')
+    assert m.query(torch.empty(0, 24)) == (None, [])
+    with pytest.raises(_lib.Gd3Error):
+        fast_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist='dot')
+
+
+def test_fast_reciprocal_nns_golden(gd3mod, golden):
+    from gd3.compat import fast_nn
+    g = golden('fast_nn.npz')
+    d1, d2 = torch.from_numpy(g['maps/d1']), torch.from_numpy(g['maps/d2'])
+    for tag, kw in (('s8', dict(subsample_or_initxy1=8)), ('s4', dict(subsample_or_initxy1=4))):
+        xy1, xy2 = fast_nn.fast_reciprocal_NNs(d1, d2, device='cuda', dist='dot', block_size=2 ** 10, **kw)
+        assert (xy1 == g[f'maps/{tag}/xy1']).all() and (xy2 == g[f'maps/{tag}/xy2']).all()
+    i1, i2 = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=8, ret_xy=False, device='cuda', dist='dot')
+    assert (i1 == g['maps/s8_idx/i1']).all() and (i2 == g['maps/s8_idx/i2']).all()
+    xy1, xy2 = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=(g['maps/seeds/x'], g['maps/seeds/y']),
+                                           pixel_tol=3, device='cuda', dist='dot')
+    assert (xy1 == g['maps/seeds_tol3/xy1']).all() and (xy2 == g['maps/seeds_tol3/xy2']).all()
+    xy1, xy2, basin = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=8, ret_basin=True, device='cuda',
+                                                  dist='dot')
+    assert (xy1 == g['maps/basin/xy1']).all() and (basin == g['maps/basin/basin']).all()
+
+
+def test_fast_reciprocal_nns_real_shape(gd3mod):
+    """MASt3R-sized maps (384 x 512 x 24, S=16) against the CPU oracle on exactly-representable descriptors."""
+    from gd3.compat import fast_nn
+    d1, d2 = synth.nn_desc_maps(305, 384, 512)
+    d1 = torch.round(d1 * 16) / 8
+    d2 = torch.round(d2 * 16) / 8
+    xy1, xy2 = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=16, device='cuda', dist='dot',
+                                           block_size=2 ** 13)
+    r1, r2 = oracle_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=16, device='cpu', dist='dot',
+                                           block_size=2 ** 13)
+    assert xy1.shape == r1.shape and (xy1 == r1).all() and (xy2 == r2).all()
