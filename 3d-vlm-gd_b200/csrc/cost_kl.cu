@@ -1,0 +1,599 @@
+// K1: dense cost-volume KL distillation loss, forward + backward, batched over image pairs.
+//
+// Replaces the body of calculate_cost_loss (src/finetune_timm_mast3r.py:504-540 "mast3r" variant,
+// src/finetune_timm_vggt.py:488-533 "vggt" variant) together with get_masked_patch_cost
+// (utils/functions.py:402-422) and kl_divergence_map (utils/losses.py:5-15).
+//
+// Math (per pair; a = normalize(f1), b = normalize(f2), z_ij = a_i . b_j in [-1, 1]):
+//   t~12_ij = max(t12_ij / max(R_i, eps), eps) on kept rows (mask1_i), R_i = sum_j t12_ij; same for 21.
+//   KL_12 = (1/N) sum_i m1_i [ A_i - D_i + T_i log L_i ] + (#masked rows) * c_var
+//     A_i = sum_j t~ log t~,  T_i = sum_j t~,  D_i = sum_j t~_ij z_ij,  L_i = sum_j exp(z_ij)
+//     c_var = N eps log(N eps) / N for "mast3r" (masked rows become uniform 1/N), 0 for "vggt".
+//   loss = (KL_12 + KL_21) / 2,  KL_21 the same on columns of z with teacher21 / mask2.
+//   dz_ij = (1/2N) [ (r_i + c_j) exp(z_ij) - W_ij ],  r_i = m1_i T_i / L_i, c_j = m2_j T'_j / L'_j,
+//           W_ij = m1_i t~12_ij + m2_j t~21_ji
+//   df1_i = (sum_j dz_ij b_j - a_i rowdot_i) / |f1_i|,  rowdot_i = sum_j dz_ij z_ij   (normalize backward)
+//   df2_j = (sum_i dz_ij a_i - b_j coldot_j) / |f2_j|.
+// z needs no running max (bounded logits), so row and column softmax statistics come from the same exp.
+//
+// Pipeline per group of pairs (workspace is reused by every group so it stays resident in L2):
+//   1 kl_prep_features  SIMT   normalise rows -> a, b (bf16) and their transposes, 1/|f|
+//   2 kl_teacher_stats  SIMT   R, T, A per teacher row (one read of the teacher)
+//   3 kl_build_w        SIMT   W^T (fp32), the only form in which the teacher is used afterwards
+//   4 tc_gemm<EpiKLStats>      z tiles on tcgen05 -> exp / row+col sums / D in registers; z kept as fp16
+//   5 kl_finalize_stats SIMT   r, c and the T log L terms
+//   6 kl_dz             SIMT   dz, dz^T (bf16) and rowdot / coldot
+//   7 tc_gemm<EpiGradOut> x2   df1 = dz b, df2 = dz^T a with the normalisation backward fused
+// The fp32 N x N cost volume never exists in memory; the fp16 z / bf16 dz staging buffers are sized
+// for one group and live in L2 (see DESIGN.md for the TMEM budget argument against a single kernel).
+#include "../../include/gd3.h"
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace gd3 {
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------
+// 1. feature preparation
+// ------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ float ld_feat(const T* p);
+template <>
+__device__ __forceinline__ float ld_feat<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_feat<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// grid: (ceil(N/32), G, 2 images); block 256.  Writes a (G, N, ldc) bf16, aT (G, C, ldn) bf16, inv (G, N).
+template <class T>
+__global__ void __launch_bounds__(256)
+    kl_prep_features(const T* __restrict__ f1, const T* __restrict__ f2, int64_t s1P, int64_t s1N, int64_t s1C,
+                     int64_t s2P, int64_t s2N, int64_t s2C, int pair0, int N, int C, int ldc, int ldn,
+                     __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ aT,
+                     __nv_bfloat16* __restrict__ bT, float* __restrict__ inv1, float* __restrict__ inv2) {
+  __shared__ float s_inv[32];
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z, g = blockIdx.y, n0 = blockIdx.x * 32;
+  const T* f = (img == 0 ? f1 : f2) + (int64_t)(pair0 + g) * (img == 0 ? s1P : s2P);
+  const int64_t sN = img == 0 ? s1N : s2N, sC = img == 0 ? s1C : s2C;
+  __nv_bfloat16* o = (img == 0 ? a : b) + (int64_t)g * N * ldc;
+  __nv_bfloat16* oT = (img == 0 ? aT : bT);   // transposes are only needed by the backward GEMMs
+  if (oT) oT += (int64_t)g * C * ldn;
+  float* inv = (img == 0 ? inv1 : inv2) + (int64_t)g * N;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool row_major = sC <= sN;   // pick the coalesced direction of the source
+  if (row_major) {
+    for (int r = w; r < 32; r += 8) {
+      const int n = n0 + r;
+      float ss = 0.f;
+      if (n < N)
+        for (int c = lane; c < C; c += 32) { const float v = ld_feat(f + n * sN + c * sC); ss = fmaf(v, v, ss); }
+      ss = warp_sum(ss);
+      if (lane == 0) s_inv[r] = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+  } else {
+    // channel-major view (the MASt3R path hands over N-stride 1, C-stride N): lanes run along n
+    float ss = 0.f;
+    const int n = n0 + lane;
+    if (n < N)
+      for (int c = w; c < C; c += 8) { const float v = ld_feat(f + n * sN + c * sC); ss = fmaf(v, v, ss); }
+    tile[w][lane] = ss;
+    __syncthreads();
+    if (w == 0) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += tile[k][lane];
+      s_inv[lane] = 1.f / fmaxf(sqrtf(t), 1e-12f);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && n0 + threadIdx.x < N) inv[n0 + threadIdx.x] = s_inv[threadIdx.x];
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();
+    // load a 32 (n) x 32 (c) tile in the source's coalesced direction
+    for (int r = w; r < 32; r += 8) {
+      const int n = row_major ? n0 + r : n0 + lane;
+      const int c = row_major ? c0 + lane : c0 + r;
+      float v = 0.f;
+      if (n < N && c < C) v = ld_feat(f + n * sN + c * sC) * s_inv[n - n0];
+      if (row_major) tile[r][lane] = v; else tile[lane][r] = v;
+    }
+    __syncthreads();
+    for (int r = w; r < 32; r += 8) {
+      // a[n][c]: lanes along c
+      if (n0 + r < N && c0 + lane < C) o[(int64_t)(n0 + r) * ldc + c0 + lane] = __float2bfloat16(tile[r][lane]);
+      // aT[c][n]: lanes along n
+      if (oT && c0 + r < C && n0 + lane < N)
+        oT[(int64_t)(c0 + r) * ldn + n0 + lane] = __float2bfloat16(tile[lane][r]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. teacher row statistics: one warp per (direction, pair, row)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    kl_teacher_stats(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+                     int64_t t_row_stride, const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, int pair0,
+                     int G, int N, float eps, float masked_row_const, float* __restrict__ invR /*(2,G,N)*/,
+                     float* __restrict__ epsm /*(2,G,N)*/, float* __restrict__ Tsum /*(2,G,N)*/,
+                     double* __restrict__ loss_acc /*(G)*/) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (int64_t)2 * G * N) return;
+  const int dir = (int)(wid / ((int64_t)G * N));
+  const int rem = (int)(wid - (int64_t)dir * G * N);
+  const int g = rem / N, i = rem - g * N;
+  const uint8_t keep = (dir == 0 ? m1 : m2)[(int64_t)(pair0 + g) * N + i];
+  const int64_t o = ((int64_t)dir * G + g) * N + i;
+  const double scale = 0.5 / (double)N;
+  if (!keep) {
+    if (lane == 0) {
+      invR[o] = 0.f;
+      epsm[o] = 0.f;
+      Tsum[o] = 0.f;
+      if (masked_row_const != 0.f) atomicAdd(&loss_acc[g], scale * (double)masked_row_const);
+    }
+    return;
+  }
+  const float* row = (dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride + (int64_t)i * t_row_stride;
+  float R = 0.f;
+  for (int j = lane; j < N; j += 32) R += __ldg(row + j);
+  R = warp_sum(R);
+  const float ir = 1.f / fmaxf(R, eps);
+  float T = 0.f, A = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const float tt = fmaxf(__ldg(row + j) * ir, eps);
+    T += tt;
+    A = fmaf(tt, __logf(tt), A);
+  }
+  T = warp_sum(T);
+  A = warp_sum(A);
+  if (lane == 0) {
+    invR[o] = ir;
+    epsm[o] = eps;
+    Tsum[o] = T;
+    atomicAdd(&loss_acc[g], scale * (double)A);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. W^T[g][j][i] = m1_i t~12_ij + m2_j t~21_ji      grid (ceil(N/32) i-tiles, ceil(N/32) j-tiles, G)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    kl_build_w(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+               int64_t t_row_stride, int pair0, int G, int N, const float* __restrict__ invR,
+               const float* __restrict__ epsm, float* __restrict__ WT, int ldw) {
+  __shared__ float tile[32][33];
+  const int g = blockIdx.z, i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float* T12 = t12 + (int64_t)(pair0 + g) * t_pair_stride;
+  const float* T21 = t21 + (int64_t)(pair0 + g) * t_pair_stride;
+  const float* ir12 = invR + (int64_t)g * N;
+  const float* ir21 = invR + ((int64_t)G + g) * N;
+  const float* e12 = epsm + (int64_t)g * N;
+  const float* e21 = epsm + ((int64_t)G + g) * N;
+  // t~12 tile read with lanes along j (its contiguous direction), transposed through smem
+  for (int r = w; r < 32; r += 8) {
+    const int i = i0 + r, j = j0 + lane;
+    float v = 0.f;
+    if (i < N && j < N) v = fmaxf(__ldg(T12 + (int64_t)i * t_row_stride + j) * ir12[i], e12[i]);
+    tile[r][lane] = v;
+  }
+  __syncthreads();
+  for (int r = w; r < 32; r += 8) {
+    const int j = j0 + r, i = i0 + lane;
+    if (i < N && j < N) {
+      const float v21 = fmaxf(__ldg(T21 + (int64_t)j * t_row_stride + i) * ir21[j], e21[j]);
+      WT[((int64_t)g * N + j) * ldw + i] = tile[lane][r] + v21;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. pass-1 epilogue: softmax statistics + D term straight from the TMEM accumulator
+// ------------------------------------------------------------------------------------------
+struct EpiKLStats {
+  static constexpr int kScratchBytes = 0;
+  struct Params {
+    int N;
+    const float* WT;   // (G, N, ldw)
+    int ldw;
+    float* Lrow;       // (G, N)  sum_j exp(z_ij)
+    float* Lcol;       // (G, N)  sum_i exp(z_ij)
+    double* loss_acc;  // (G)
+    __half* Z;         // (G, N, ldz) fp16 staging of z for the backward, or nullptr (forward only)
+    int ldz;
+  };
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx) {
+    const int i = cx.m0 + cx.row;
+    const bool row_ok = i < p.N;
+    const float* wt = p.WT + (int64_t)cx.b * p.N * p.ldw + i;
+    float rowsum = 0.f, dsum = 0.f;
+    for (int c = cx.col_begin; c < cx.col_end; c += 32) {
+      const int j0 = cx.n0 + c;
+      if (j0 >= p.N) break;                       // warp-uniform: the rest of the tile is padding
+      float v[32];
+      tc::tmem_ld32(cx.tmem + c, v);
+      if (p.Z && row_ok) {
+        uint4* zrow = reinterpret_cast<uint4*>(p.Z + ((int64_t)cx.b * p.N + i) * p.ldz + j0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (j0 + 8 * q < p.ldz)
+            zrow[q] = make_uint4(pack_f16x2(v[8 * q], v[8 * q + 1]), pack_f16x2(v[8 * q + 2], v[8 * q + 3]),
+                                 pack_f16x2(v[8 * q + 4], v[8 * q + 5]), pack_f16x2(v[8 * q + 6], v[8 * q + 7]));
+      }
+      float e[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const bool ok = row_ok && (j0 + q < p.N);
+        const float w = ok ? __ldg(wt + (int64_t)(j0 + q) * p.ldw) : 0.f;
+        const float ex = ok ? exp2f(v[q] * LOG2E) : 0.f;
+        dsum = fmaf(w, v[q], dsum);
+        rowsum += ex;
+        e[q] = ex;
+      }
+      // transpose-reduce: lane q ends with sum over the warp's 32 rows of column j0 + q
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (cx.lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; ++k) {
+          const float send = up ? e[k] : e[k + off];
+          const float keep = up ? e[k + off] : e[k];
+          e[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      if (j0 + cx.lane < p.N) atomicAdd(p.Lcol + (int64_t)cx.b * p.N + j0 + cx.lane, e[0]);
+    }
+    if (row_ok) atomicAdd(p.Lrow + (int64_t)cx.b * p.N + i, rowsum);
+    dsum = warp_sum(dsum);
+    if (cx.lane == 0 && dsum != 0.f) atomicAdd(p.loss_acc + cx.b, -(0.5 / (double)p.N) * (double)dsum);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// 5. r_i, c_j and the T log L terms.  One thread per (direction, g, i).
+// ------------------------------------------------------------------------------------------
+__global__ void kl_finalize_stats(int G, int N, const float* __restrict__ invR, const float* __restrict__ Tsum,
+                                  const float* __restrict__ Lrow, const float* __restrict__ Lcol,
+                                  float* __restrict__ rc /*(2,G,N): r then c*/, double* __restrict__ loss_acc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double contrib = 0.0;
+  int g = 0;
+  if (idx < (int64_t)2 * G * N) {
+    const int dir = (int)(idx / ((int64_t)G * N));
+    const int rem = (int)(idx - (int64_t)dir * G * N);
+    g = rem / N;
+    const float T = Tsum[idx];
+    const bool keep = invR[idx] != 0.f;
+    const float L = (dir == 0 ? Lrow : Lcol)[rem];
+    rc[idx] = keep ? T / L : 0.f;
+    if (keep) contrib = (0.5 / (double)N) * (double)T * (double)logf(L);
+  }
+  // threads of a warp may straddle two pairs: reduce only when uniform, else add individually
+  const unsigned full = 0xffffffffu;
+  const int g0 = __shfl_sync(full, g, 0);
+  const bool uniform = __all_sync(full, g == g0);
+  if (uniform) {
+    contrib = warp_sum(contrib);
+    if ((threadIdx.x & 31) == 0 && contrib != 0.0) atomicAdd(&loss_acc[g0], contrib);
+  } else if (contrib != 0.0) {
+    atomicAdd(&loss_acc[g], contrib);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 6. dz = s ((r_i + c_j) exp(z) - W), written as dz (row i) and dz^T (row j) in bf16, + row/col dots
+//    grid (ceil(N/64) j-tiles, ceil(N/64) i-tiles, G), block 256
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    kl_dz(int G, int N, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT, int ldw,
+          const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT, int ldd,
+          float* __restrict__ rowdot, float* __restrict__ coldot) {
+  __shared__ float ws[64][65];     // W^T tile, [j][i]
+  __shared__ float ds[64][65];     // dz tile, [i][j]
+  __shared__ float cdot[8][64];
+  const int g = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float* wt = WT + (int64_t)g * N * ldw;
+  for (int r = w; r < 64; r += 8) {
+    const int j = j0 + r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = i0 + lane + 32 * h;
+      ws[r][lane + 32 * h] = (j < N && i < N) ? __ldg(wt + (int64_t)j * ldw + i) : 0.f;
+    }
+  }
+  __syncthreads();
+  const float s = 0.5f / (float)N;
+  const float* rr = rc + (int64_t)g * N;
+  const float* cc = rc + ((int64_t)G + g) * N;
+  const int jl = 2 * lane, j = j0 + jl;
+  const float c0 = (j < N) ? cc[j] : 0.f, c1 = (j + 1 < N) ? cc[j + 1] : 0.f;
+  float cd0 = 0.f, cd1 = 0.f;
+  for (int r = w; r < 64; r += 8) {
+    const int i = i0 + r;
+    float d0 = 0.f, d1 = 0.f, rd = 0.f;
+    if (i < N && j < N) {
+      // ldz is a multiple of 8, so reading the pair (j, j+1) stays inside the row even when j+1 == N
+      const __half2 zz = *reinterpret_cast<const __half2*>(Z + ((int64_t)g * N + i) * ldz + j);
+      const float z0 = __low2float(zz), z1 = (j + 1 < N) ? __high2float(zz) : 0.f;
+      const float ri = rr[i];
+      d0 = s * ((ri + c0) * exp2f(z0 * LOG2E) - ws[jl][r]);
+      d1 = (j + 1 < N) ? s * ((ri + c1) * exp2f(z1 * LOG2E) - ws[jl + 1][r]) : 0.f;
+      *reinterpret_cast<uint32_t*>(dZ + ((int64_t)g * N + i) * ldd + j) = pack_bf16x2(d0, d1);
+      rd = fmaf(d0, z0, d1 * z1);
+      cd0 = fmaf(d0, z0, cd0);
+      cd1 = fmaf(d1, z1, cd1);
+    }
+    ds[r][jl] = d0;
+    ds[r][jl + 1] = d1;
+    rd = warp_sum(rd);
+    if (lane == 0 && i < N) atomicAdd(rowdot + (int64_t)g * N + i, rd);
+  }
+  cdot[w][jl] = cd0;
+  cdot[w][jl + 1] = cd1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += cdot[k][threadIdx.x];
+    if (j0 + threadIdx.x < N) atomicAdd(coldot + (int64_t)g * N + j0 + threadIdx.x, t);
+  }
+  // dz^T rows: lanes along i
+  const int il = 2 * lane, i = i0 + il;
+  for (int r = w; r < 64; r += 8) {
+    const int jj = j0 + r;
+    if (jj < N && i < N)
+      *reinterpret_cast<uint32_t*>(dZT + ((int64_t)g * N + jj) * ldd + i) = pack_bf16x2(ds[il][r], ds[il + 1][r]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 7. gradient GEMM epilogue: df = (acc - x * dot) * inv_norm, x = normalised feature (bf16)
+// ------------------------------------------------------------------------------------------
+template <class OutT>
+struct EpiGradOut {
+  static constexpr int kScratchBytes = 0;
+  struct Params {
+    int N, C;
+    const __nv_bfloat16* X;   // (G, N, ldc) normalised features of the image being differentiated
+    int ldc;
+    const float* dot;         // (G, N)
+    const float* inv;         // (G, N)
+    OutT* out;                // (P, N, C) contiguous, already offset to this group's first pair
+  };
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx) {
+    const int i = cx.m0 + cx.row;
+    const bool row_ok = i < p.N;
+    float dot = 0.f, inv = 0.f;
+    if (row_ok) {
+      dot = p.dot[(int64_t)cx.b * p.N + i];
+      inv = p.inv[(int64_t)cx.b * p.N + i];
+    }
+    const __nv_bfloat16* x = p.X + ((int64_t)cx.b * p.N + i) * p.ldc;
+    OutT* o = p.out + ((int64_t)cx.b * p.N + i) * p.C;
+    const bool vec = (p.C % 8 == 0);
+    for (int c = cx.col_begin; c < cx.col_end; c += 32) {
+      const int c0 = cx.n0 + c;
+      if (c0 >= p.C) break;
+      float v[32];
+      tc::tmem_ld32(cx.tmem + c, v);
+      if (!row_ok) continue;
+      if (vec && c0 + 32 <= p.C) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(x + c0 + 8 * q);   // ldc % 8 == 0
+          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+          float r[8];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            r[2 * h] = (v[8 * q + 2 * h] - bf16_bits_to_float(xs[h] & 0xFFFFu) * dot) * inv;
+            r[2 * h + 1] = (v[8 * q + 2 * h + 1] - bf16_bits_to_float(xs[h] >> 16) * dot) * inv;
+          }
+          if constexpr (sizeof(OutT) == 4) {
+            float4* dst = reinterpret_cast<float4*>(o + c0 + 8 * q);
+            dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+            dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+          } else {
+            *reinterpret_cast<uint4*>(o + c0 + 8 * q) =
+                make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                           pack_bf16x2(r[6], r[7]));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (c0 + q < p.C) {
+            const float r = (v[q] - __bfloat162float(x[c0 + q]) * dot) * inv;
+            if constexpr (sizeof(OutT) == 4) o[c0 + q] = r; else o[c0 + q] = __float2bfloat16(r);
+          }
+      }
+    }
+  }
+};
+
+__global__ void kl_write_loss(const double* __restrict__ acc, float* __restrict__ loss, int G) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) loss[g] = (float)acc[g];
+}
+
+struct KLWorkspace {
+  __nv_bfloat16 *a, *b, *aT, *bT, *dZ, *dZT;
+  __half* Z;
+  float *inv1, *inv2, *invR, *epsm, *Tsum, *WT, *Lrow, *Lcol, *rc, *rowdot, *coldot;
+  double* loss_acc;
+  // the four zero-initialised accumulators are contiguous: [Lrow | Lcol | rowdot | coldot]
+  size_t total;
+  int ldc, ldn, ldw;
+};
+
+KLWorkspace carve_kl(void* base, int64_t G, int64_t N, int64_t C, bool backward) {
+  KLWorkspace w{};
+  Carver c(base);
+  w.ldc = (int)round_up<int64_t>(C, 8);
+  w.ldn = (int)round_up<int64_t>(N, 8);
+  w.ldw = (int)round_up<int64_t>(N, 4);
+  w.a = c.take<__nv_bfloat16>(G * N * w.ldc);
+  w.b = c.take<__nv_bfloat16>(G * N * w.ldc);
+  w.aT = c.take<__nv_bfloat16>(backward ? G * C * w.ldn : 0);
+  w.bT = c.take<__nv_bfloat16>(backward ? G * C * w.ldn : 0);
+  w.inv1 = c.take<float>(G * N);
+  w.inv2 = c.take<float>(G * N);
+  w.invR = c.take<float>(2 * G * N);
+  w.epsm = c.take<float>(2 * G * N);
+  w.Tsum = c.take<float>(2 * G * N);
+  w.WT = c.take<float>(G * N * w.ldw);
+  w.Lrow = c.take<float>(4 * G * N);
+  w.Lcol = w.Lrow + G * N;
+  w.rowdot = w.Lrow + 2 * G * N;
+  w.coldot = w.Lrow + 3 * G * N;
+  w.rc = c.take<float>(2 * G * N);
+  w.loss_acc = c.take<double>(G);
+  w.Z = c.take<__half>(backward ? G * N * w.ldn : 0);
+  w.dZ = c.take<__nv_bfloat16>(backward ? G * N * w.ldn : 0);
+  w.dZT = c.take<__nv_bfloat16>(backward ? G * N * w.ldn : 0);
+  w.total = c.total();
+  return w;
+}
+
+int64_t auto_group(int64_t P, int64_t N, int64_t C) {
+  // keep one group's working set (teacher + W^T + z/dz staging + features) around half of L2
+  const double per_pair = 2.0 * N * N * 4 + N * N * 4.0 + 3.0 * N * N * 2 + 4.0 * N * C * 2 + 2.0 * N * C * 4;
+  int64_t g = (int64_t)(64.0e6 / per_pair);
+  if (g < 1) g = 1;
+  // at least one full wave of 128 x 256 tiles on the pass-1 GEMM
+  const int64_t tiles = ceil_div<int64_t>(N, 128) * ceil_div<int64_t>(N, 256);
+  const int64_t fill = ceil_div<int64_t>(num_sms(), tiles);
+  if (g < fill) g = fill;
+  return g > P ? P : g;
+}
+
+}  // namespace
+}  // namespace gd3
+
+using namespace gd3;
+
+extern "C" {
+
+int64_t gd3_cost_kl_group_size(int64_t P, int64_t N, int64_t C, int64_t pairs_per_group) {
+  if (P <= 0) return 0;
+  if (pairs_per_group > 0) return pairs_per_group > P ? P : pairs_per_group;
+  return auto_group(P, N, C);
+}
+
+size_t gd3_cost_kl_workspace(int64_t P, int64_t N, int64_t C, int64_t pairs_per_group, int with_backward) {
+  if (P <= 0 || N <= 0 || C <= 0) return 0;
+  const int64_t G = gd3_cost_kl_group_size(P, N, C, pairs_per_group);
+  return carve_kl(nullptr, G, N, C, with_backward != 0).total;
+}
+
+int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N, int64_t C, int64_t s1P, int64_t s1N,
+                int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const float* t12, const float* t21,
+                int64_t t_pair_stride, int64_t t_row_stride, const uint8_t* m1, const uint8_t* m2, int variant,
+                float eps, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group, void* workspace,
+                size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (P == 0) return GD3_OK;
+  GD3_REQUIRE(P > 0 && N > 0 && C > 0, "gd3_cost_kl: bad sizes P=%lld N=%lld C=%lld", (long long)P, (long long)N,
+              (long long)C);
+  GD3_REQUIRE(f1 && f2 && t12 && t21 && m1 && m2 && loss, "gd3_cost_kl: null pointer");
+  GD3_REQUIRE(dtype == GD3_DTYPE_F32 || dtype == GD3_DTYPE_BF16, "gd3_cost_kl: bad dtype %d", dtype);
+  GD3_REQUIRE(variant == GD3_VARIANT_MAST3R || variant == GD3_VARIANT_VGGT, "gd3_cost_kl: unknown variant %d",
+              variant);
+  GD3_REQUIRE((grad_f1 == nullptr) == (grad_f2 == nullptr), "gd3_cost_kl: pass both gradients or neither");
+  GD3_REQUIRE(eps > 0.f, "gd3_cost_kl: eps must be positive");
+  const bool backward = grad_f1 != nullptr;
+  const int64_t G = gd3_cost_kl_group_size(P, N, C, pairs_per_group);
+  GD3_REQUIRE(G <= 65535 && ceil_div<int64_t>(N, 32) <= 65535, "gd3_cost_kl: problem too large for one launch grid");
+  KLWorkspace w = carve_kl(workspace, G, N, C, backward);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("gd3_cost_kl: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return GD3_ERR_WORKSPACE;
+  }
+  GD3_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "gd3_cost_kl: workspace must be 256-byte aligned");
+
+  // masked rows: "mast3r" softmaxes a zeroed logit row (uniform 1/N) against a teacher row of eps
+  const double ne = (double)N * (double)eps;
+  const float masked_const = variant == GD3_VARIANT_MAST3R ? (float)(ne * log(ne)) : 0.f;
+
+  CUtensorMap tm_a, tm_b, tm_dz, tm_dzt, tm_at, tm_bt;
+  int rc;
+  if ((rc = tc::make_tmap_bf16(&tm_a, w.a, C, N, G, w.ldc, N * (int64_t)w.ldc, tc::BM))) return rc;
+  if ((rc = tc::make_tmap_bf16(&tm_b, w.b, C, N, G, w.ldc, N * (int64_t)w.ldc, 256))) return rc;
+  if (backward) {
+    if ((rc = tc::make_tmap_bf16(&tm_dz, w.dZ, N, N, G, w.ldn, N * (int64_t)w.ldn, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tm_dzt, w.dZT, N, N, G, w.ldn, N * (int64_t)w.ldn, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tm_at, w.aT, N, C, G, w.ldn, C * (int64_t)w.ldn, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tm_bt, w.bT, N, C, G, w.ldn, C * (int64_t)w.ldn, 256))) return rc;
+  }
+
+  for (int64_t p0 = 0; p0 < P; p0 += G) {
+    const int g = (int)((P - p0) < G ? (P - p0) : G);
+    GD3_CHECK_CUDA(cudaMemsetAsync(w.Lrow, 0, sizeof(float) * 4 * G * N, stream));
+    GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * G, stream));
+    {
+      dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)g, 2);
+      if (dtype == GD3_DTYPE_F32)
+        kl_prep_features<float><<<grid, 256, 0, stream>>>(
+            static_cast<const float*>(f1), static_cast<const float*>(f2), s1P, s1N, s1C, s2P, s2N, s2C, (int)p0,
+            (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, backward ? w.aT : nullptr, backward ? w.bT : nullptr, w.inv1, w.inv2);
+      else
+        kl_prep_features<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(f1), static_cast<const __nv_bfloat16*>(f2), s1P, s1N, s1C, s2P, s2N,
+            s2C, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, backward ? w.aT : nullptr, backward ? w.bT : nullptr,
+            w.inv1, w.inv2);
+      GD3_CHECK_LAUNCH();
+    }
+    {
+      const int64_t warps = 2 * (int64_t)g * N;
+      kl_teacher_stats<<<(unsigned)ceil_div<int64_t>(warps, 8), 256, 0, stream>>>(
+          t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, (int)N, eps, masked_const, w.invR, w.epsm,
+          w.Tsum, w.loss_acc);
+      GD3_CHECK_LAUNCH();
+      dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)ceil_div<int64_t>(N, 32), (unsigned)g);
+      kl_build_w<<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N, w.invR, w.epsm,
+                                           w.WT, w.ldw);
+      GD3_CHECK_LAUNCH();
+    }
+    {
+      EpiKLStats::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, backward ? w.Z : nullptr, w.ldn};
+      tc::GemmShape s{(int)N, (int)N, (int)C, g};
+      if ((rc = tc::launch_gemm<256, 4, EpiKLStats>(tm_a, tm_b, s, ep, stream))) return rc;
+    }
+    {
+      const int64_t n = 2 * (int64_t)g * N;
+      kl_finalize_stats<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(g, (int)N, w.invR, w.Tsum, w.Lrow,
+                                                                               w.Lcol, w.rc, w.loss_acc);
+      GD3_CHECK_LAUNCH();
+      kl_write_loss<<<ceil_div(g, 64), 64, 0, stream>>>(w.loss_acc, loss + p0, g);
+      GD3_CHECK_LAUNCH();
+    }
+    if (backward) {
+      dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
+      kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
+                                      w.coldot);
+      GD3_CHECK_LAUNCH();
+      tc::GemmShape s{(int)N, (int)C, (int)N, g};
+      if (dtype == GD3_DTYPE_F32) {
+        using E = EpiGradOut<float>;
+        E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1, static_cast<float*>(grad_f1) + p0 * N * C};
+        E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2, static_cast<float*>(grad_f2) + p0 * N * C};
+        if ((rc = tc::launch_gemm<256, 4, E>(tm_dz, tm_bt, s, e1, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 4, E>(tm_dzt, tm_at, s, e2, stream))) return rc;
+      } else {
+        using E = EpiGradOut<__nv_bfloat16>;
+        E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1,
+                     static_cast<__nv_bfloat16*>(grad_f1) + p0 * N * C};
+        E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2,
+                     static_cast<__nv_bfloat16*>(grad_f2) + p0 * N * C};
+        if ((rc = tc::launch_gemm<256, 4, E>(tm_dz, tm_bt, s, e1, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 4, E>(tm_dzt, tm_at, s, e2, stream))) return rc;
+      }
+    }
+  }
+  return GD3_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// K3: bilinear sampling of patch-token feature maps at pixel keypoints (+ optional channel L2
+// normalisation and mean over several layers), forward and backward.
+//
+// Replaces interpolate_features (utils/functions.py:55-76) and the glue around it in
+// get_intermediate_feature / get_feature (src/finetune_timm_mast3r.py:271-277, 307-313):
+//   pixel -> grid coords (a*pts + b, patch centres on [-1, 1]) -> grid_sample(align_corners=True,
+//   padding_mode='border') -> optional F.normalize over channels.
+// The arithmetic follows PyTorch's grid_sampler (unnormalise ((g+1)/2)*(size-1), clip to
+// [0, size-1], 4 taps with (1-frac) weights) with the same fp32 operation order; FMA contraction is
+// suppressed on the coordinate path so tap selection is identical.
+// Generic strides let the same kernel read the reference's NCHW maps or token-major ViT outputs.
+#include "../../include/gd3.h"
+#include "common.cuh"
+
+namespace gd3 {
+namespace {
+
+struct SampleGeom {
+  float aw, ah, bw, bh;   // pixel -> normalised grid
+  int ph, pw;             // feature map height / width in patches
+};
+
+struct Taps {
+  int i00, i01, i10, i11;     // token indices (y*pw + x) of nw, ne, sw, se
+  float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ Taps make_taps(const SampleGeom& g, float x, float y) {
+  // keypoints = a * pts + b   (two roundings, like the reference's tensor ops)
+  const float gx = __fadd_rn(__fmul_rn(g.aw, x), g.bw);
+  const float gy = __fadd_rn(__fmul_rn(g.ah, y), g.bh);
+  // grid_sampler_unnormalize, align_corners=True, then clip (padding_mode='border')
+  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(g.pw - 1));
+  float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(g.ph - 1));
+  ix = fminf((float)(g.pw - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(g.ph - 1), fmaxf(iy, 0.f));
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = __fsub_rn(ix, fx), wy1 = __fsub_rn(iy, fy);
+  const float wx0 = __fsub_rn((float)x1, ix), wy0 = __fsub_rn((float)y1, iy);
+  Taps t;
+  const bool xin = x1 < g.pw, yin = y1 < g.ph;   // out-of-range neighbours are skipped (weight is 0 anyway)
+  t.w00 = __fmul_rn(wx0, wy0);
+  t.w01 = xin ? __fmul_rn(wx1, wy0) : 0.f;
+  t.w10 = yin ? __fmul_rn(wx0, wy1) : 0.f;
+  t.w11 = (xin && yin) ? __fmul_rn(wx1, wy1) : 0.f;
+  const int xc = xin ? x1 : x0, yc = yin ? y1 : y0;
+  t.i00 = y0 * g.pw + x0;
+  t.i01 = y0 * g.pw + xc;
+  t.i10 = yc * g.pw + x0;
+  t.i11 = yc * g.pw + xc;
+  return t;
+}
+
+template <class T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// one block per (pair, keypoint); threads stride over channels
+template <class T>
+__global__ void __launch_bounds__(256)
+    sample_fwd_kernel(const T* __restrict__ tok, int L, int64_t sL, int64_t sP, int64_t sN, int64_t sC,
+                      const float* __restrict__ kp, int K, int C, SampleGeom g, int normalize,
+                      float* __restrict__ out, int64_t oP, int64_t oK, int64_t oC, float* __restrict__ inv_norm) {
+  __shared__ float red[32];
+  const int k = blockIdx.x, p = blockIdx.y;
+  const float x = kp[((int64_t)p * K + k) * 2 + 0], y = kp[((int64_t)p * K + k) * 2 + 1];
+  const Taps t = make_taps(g, x, y);
+  const float invL = 1.f / (float)L;
+  float ss = 0.f;
+  float* o = out + p * oP + k * oK;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const T* base = tok + l * sL + p * sP + c * sC;
+      // same accumulation order as grid_sample: nw, ne, sw, se
+      float v = ldf(base + t.i00 * sN) * t.w00;
+      v += ldf(base + t.i01 * sN) * t.w01;
+      v += ldf(base + t.i10 * sN) * t.w10;
+      v += ldf(base + t.i11 * sN) * t.w11;
+      acc += v;
+    }
+    acc = (L > 1) ? acc * invL : acc;
+    o[c * oC] = acc;
+    ss += acc * acc;
+  }
+  if (normalize) {
+    ss = block_sum(ss, red);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize eps
+    if (threadIdx.x == 0 && inv_norm) inv_norm[(int64_t)p * K + k] = inv;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) o[c * oC] *= inv;   // each thread rescales what it wrote
+  }
+}
+
+// grad_tokens (fp32, same strides as tokens, caller-zeroed) += scatter of grad_out through the taps
+__global__ void __launch_bounds__(256)
+    sample_bwd_kernel(const float* __restrict__ gout, int64_t gP, int64_t gK, int64_t gC,
+                      const float* __restrict__ out, int64_t oP, int64_t oK, int64_t oC,
+                      const float* __restrict__ inv_norm, const float* __restrict__ kp, int K, int C, SampleGeom g,
+                      int normalize, int L, float* __restrict__ gtok, int64_t sL, int64_t sP, int64_t sN,
+                      int64_t sC) {
+  __shared__ float red[32];
+  const int k = blockIdx.x, p = blockIdx.y;
+  const float x = kp[((int64_t)p * K + k) * 2 + 0], y = kp[((int64_t)p * K + k) * 2 + 1];
+  const Taps t = make_taps(g, x, y);
+  const float* go = gout + p * gP + k * gK;
+  float dot = 0.f, inv = 1.f;
+  if (normalize) {
+    const float* o = out + p * oP + k * oK;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) dot += o[c * oC] * go[c * gC];
+    dot = block_sum(dot, red);
+    inv = inv_norm[(int64_t)p * K + k];
+  }
+  const float invL = 1.f / (float)L;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float gv = go[c * gC];
+    if (normalize) gv = (gv - out[p * oP + k * oK + c * oC] * dot) * inv;   // d/dx of x / max(|x|, eps)
+    gv *= invL;
+    for (int l = 0; l < L; ++l) {
+      float* base = gtok + l * sL + p * sP + c * sC;
+      atomicAdd(base + t.i00 * sN, gv * t.w00);
+      if (t.w01 != 0.f) atomicAdd(base + t.i01 * sN, gv * t.w01);
+      if (t.w10 != 0.f) atomicAdd(base + t.i10 * sN, gv * t.w10);
+      if (t.w11 != 0.f) atomicAdd(base + t.i11 * sN, gv * t.w11);
+    }
+  }
+}
+
+int make_geom(int64_t ph, int64_t pw, int64_t h, int64_t w, int patch, int stride, SampleGeom* g) {
+  GD3_REQUIRE(ph >= 2 && pw >= 2 && patch >= 1 && stride >= 1, "sample_tokens: feature map must be at least 2 x 2 (got %lld x %lld)",
+              (long long)ph, (long long)pw);
+  GD3_REQUIRE(h - patch >= stride && w - patch >= stride, "sample_tokens: image %lld x %lld too small for patch %d / stride %d",
+              (long long)h, (long long)w, patch, stride);
+  // utils/functions.py:56-63, same operation order in double, then rounded to fp32 like torch.tensor(...).float()
+  const double half = patch / 2.0;
+  const double last_h = (double)(((h - patch) / stride) * stride) + half;
+  const double last_w = (double)(((w - patch) / stride) * stride) + half;
+  const double ah = 2.0 / (last_h - half), aw = 2.0 / (last_w - half);
+  const double bh = 1.0 - last_h * 2.0 / (last_h - half), bw = 1.0 - last_w * 2.0 / (last_w - half);
+  g->aw = (float)aw;
+  g->ah = (float)ah;
+  g->bw = (float)bw;
+  g->bh = (float)bh;
+  g->ph = (int)ph;
+  g->pw = (int)pw;
+  return GD3_OK;
+}
+
+}  // namespace
+}  // namespace gd3
+
+using namespace gd3;
+
+extern "C" {
+
+int gd3_sample_tokens_fwd(const void* tokens, int dtype, int64_t L, int64_t P, int64_t C, int64_t ph, int64_t pw,
+                          int64_t h, int64_t w, int64_t sL, int64_t sP, int64_t sN, int64_t sC, const float* kp,
+                          int64_t K, int patch, int stride, int normalize, float* out, int64_t oP, int64_t oK, int64_t oC,
+                          float* inv_norm, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (P == 0 || K == 0 || C == 0) return GD3_OK;
+  GD3_REQUIRE(tokens && kp && out, "gd3_sample_tokens_fwd: null pointer");
+  GD3_REQUIRE(L >= 1 && P > 0 && K > 0 && C > 0, "gd3_sample_tokens_fwd: bad sizes");
+  GD3_REQUIRE(dtype == GD3_DTYPE_F32 || dtype == GD3_DTYPE_BF16, "gd3_sample_tokens_fwd: bad dtype %d", dtype);
+  GD3_REQUIRE(!normalize || inv_norm, "gd3_sample_tokens_fwd: normalize needs inv_norm");
+  GD3_REQUIRE(P <= 65535, "gd3_sample_tokens_fwd: more than 65535 pairs per call");
+  SampleGeom g;
+  int rc = make_geom(ph, pw, h, w, patch, stride, &g);
+  if (rc) return rc;
+  dim3 grid((unsigned)K, (unsigned)P);
+  const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+  if (dtype == GD3_DTYPE_F32)
+    sample_fwd_kernel<float><<<grid, threads, 0, stream>>>(static_cast<const float*>(tokens), (int)L, sL, sP, sN, sC,
+                                                          kp, (int)K, (int)C, g, normalize, out, oP, oK, oC,
+                                                          inv_norm);
+  else
+    sample_fwd_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(tokens), (int)L,
+                                                                  sL, sP, sN, sC, kp, (int)K, (int)C, g, normalize,
+                                                                  out, oP, oK, oC, inv_norm);
+  GD3_CHECK_LAUNCH();
+  return GD3_OK;
+}
+
+int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t gC, const float* out, int64_t oP,
+                          int64_t oK, int64_t oC, const float* inv_norm, const float* kp, int64_t L, int64_t P,
+                          int64_t K, int64_t C, int64_t ph, int64_t pw, int64_t h, int64_t w, int patch, int stride,
+                          int normalize, float* grad_tokens, int64_t sL, int64_t sP, int64_t sN, int64_t sC, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (P == 0 || K == 0 || C == 0) return GD3_OK;
+  GD3_REQUIRE(grad_out && kp && grad_tokens, "gd3_sample_tokens_bwd: null pointer");
+  GD3_REQUIRE(!normalize || (out && inv_norm), "gd3_sample_tokens_bwd: normalize needs out and inv_norm");
+  GD3_REQUIRE(P <= 65535, "gd3_sample_tokens_bwd: more than 65535 pairs per call");
+  SampleGeom g;
+  int rc = make_geom(ph, pw, h, w, patch, stride, &g);
+  if (rc) return rc;
+  dim3 grid((unsigned)K, (unsigned)P);
+  const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+  sample_bwd_kernel<<<grid, threads, 0, stream>>>(grad_out, gP, gK, gC, out, oP, oK, oC, inv_norm, kp, (int)K, (int)C,
+                                                  g, normalize, (int)L, grad_tokens, sL, sP, sN, sC);
+  GD3_CHECK_LAUNCH();
+  return GD3_OK;
+}
+
+}  // extern "C"

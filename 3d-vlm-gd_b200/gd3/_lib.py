@@ -19,6 +19,14 @@ SYMBOLS = {
     'gd3_last_error': (_c.c_char_p, []),
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    'gd3_cost_kl_group_size': (_i64, [_i64, _i64, _i64, _i64]),
+    'gd3_cost_kl_workspace': (_sz, [_i64, _i64, _i64, _i64, _int]),
+    'gd3_cost_kl': (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64,
+                           _vp, _vp, _int, _f32, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    'gd3_sample_tokens_fwd': (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp,
+                                     _i64, _int, _int, _int, _vp, _i64, _i64, _i64, _vp, _vp]),
+    'gd3_sample_tokens_bwd': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64,
+                                     _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _i64, _i64, _i64, _i64, _vp]),
     'gd3_debug_gemm_bf16': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
 }
 

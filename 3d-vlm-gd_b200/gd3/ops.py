@@ -1,0 +1,183 @@
+"""Fused, batched entry points of the hot path as ``torch.autograd.Function``s.
+
+Each ``forward`` enqueues the fused forward+backward CUDA pipeline once and stashes the
+gradients; ``backward`` only scales them by ``grad_output``.  All
+arithmetic happens inside lib3dgd.so; torch supplies device memory and the stream.
+"""
+import torch
+
+from . import _lib
+from ._lib import VARIANT, check, dtype_code, load, ptr, require_cuda, stream_ptr, workspace
+
+_F32 = torch.float32
+
+
+def _as_mask(m, P, N, device):
+    if m is None:
+        return torch.ones(P, N, dtype=torch.uint8, device=device)
+    m = m.to(device=device)
+    if m.dim() == 1:
+        m = m[None].expand(P, N)
+    return m.to(torch.uint8).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# dense cost-volume KL
+# --------------------------------------------------------------------------------------------
+class _CostVolumeKL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group):
+        require_cuda(f1, f2, teacher12, teacher21)
+        lib = load()
+        if f1.dim() != 3 or f1.shape != f2.shape:
+            raise ValueError(f'cost_volume_kl: f1/f2 must both be (P, N, C), got {tuple(f1.shape)} {tuple(f2.shape)}')
+        if f1.dtype != f2.dtype:
+            raise ValueError('cost_volume_kl: f1 and f2 must share a dtype')
+        P, N, C = f1.shape
+        if teacher12.shape != (P, N, N) or teacher21.shape != (P, N, N):
+            raise ValueError(f'cost_volume_kl: teacher volumes must be (P, N, N) = {(P, N, N)}')
+        if variant not in ('mast3r', 'vggt'):
+            raise ValueError(f'cost_volume_kl: unknown variant {variant!r}')
+        dev = f1.device
+        t12 = teacher12.to(_F32).contiguous()
+        t21 = teacher21.to(_F32).contiguous()
+        m1 = _as_mask(mask1, P, N, dev)
+        m2 = _as_mask(mask2, P, N, dev)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        loss = torch.empty(P, dtype=_F32, device=dev)
+        g1 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
+        g2 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
+        if P == 0:
+            ctx.save_for_backward(g1, g2)
+            return loss
+        ws = workspace(lib.gd3_cost_kl_workspace(P, N, C, pairs_per_group, int(need_grad)), dev)
+        with torch.cuda.device(dev):
+            check(lib.gd3_cost_kl(ptr(f1), ptr(f2), dtype_code(f1), P, N, C,
+                                  f1.stride(0), f1.stride(1), f1.stride(2),
+                                  f2.stride(0), f2.stride(1), f2.stride(2),
+                                  ptr(t12), ptr(t21), N * N, N, ptr(m1), ptr(m2), VARIANT[variant], float(eps),
+                                  ptr(loss), ptr(g1), ptr(g2), int(pairs_per_group), ptr(ws), ws.numel(),
+                                  stream_ptr()))
+        ctx.save_for_backward(g1, g2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        g1, g2 = ctx.saved_tensors
+        if g1 is None:
+            return (None,) * 9
+        s = grad_loss.to(g1.dtype)[:, None, None]
+        return g1 * s, g2 * s, None, None, None, None, None, None, None
+
+
+def cost_volume_kl(f1, f2, teacher12, teacher21, mask1=None, mask2=None, variant='mast3r', eps=1e-8,
+                   pairs_per_group=0):
+    """Dense cost-volume KL loss per pair, ``(P,)``.
+
+    f1, f2: (P, N, C) student patch features (fp32 or bf16, any strides); teacher12 / teacher21:
+    (P, N, N) teacher volumes; mask1 / mask2: (P, N) or (N,) bool patch masks (None = keep all).
+    Equals ``calculate_cost_loss`` of the reference (variant 'mast3r':
+    src/finetune_timm_mast3r.py:504-540, 'vggt': src/finetune_timm_vggt.py:488-533) for each pair.
+    """
+    return _CostVolumeKL.apply(f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group)
+
+
+# --------------------------------------------------------------------------------------------
+# bilinear token sampling
+# --------------------------------------------------------------------------------------------
+def _sample_fwd(tokens, strides, L, P, C, ph, pw, h, w, kp, patch, stride, normalize, out, out_strides):
+    lib = load()
+    K = kp.shape[1]
+    inv = torch.empty(P, K, dtype=_F32, device=tokens.device) if normalize else None
+    with torch.cuda.device(tokens.device):
+        check(lib.gd3_sample_tokens_fwd(ptr(tokens), dtype_code(tokens), L, P, C, ph, pw, h, w, *strides, ptr(kp), K,
+                                        patch, stride, int(normalize), ptr(out), *out_strides, ptr(inv),
+                                        stream_ptr()))
+    return inv
+
+
+class _SampleTokens(torch.autograd.Function):
+    """Strided token tensor -> out (P, K, C) or (P, C, K).
+
+    ``layout`` = (L, P, N, C, strides, grad_strides): element (l, p, n, c) of ``tokens`` lives at
+    ``l*sL + p*sP + n*sN + c*sC``; the gradient is accumulated in a fresh contiguous fp32 tensor of
+    tokens' logical shape, addressed with ``grad_strides`` (autograd accepts any gradient layout).
+    """
+
+    @staticmethod
+    def forward(ctx, tokens, kp, geom, normalize, channels_first_out, layout):
+        require_cuda(tokens, kp)
+        L, P, N, C, strides, _ = layout
+        ph, pw, h, w, patch, stride = geom
+        if N != ph * pw:
+            raise ValueError(f'sample_tokens: {N} tokens do not form a {ph} x {pw} grid')
+        kp = kp.to(_F32).contiguous()
+        if kp.dim() != 3 or kp.shape[0] != P or kp.shape[2] != 2:
+            raise ValueError(f'sample_tokens: keypoints must be (P, K, 2), got {tuple(kp.shape)}')
+        K = kp.shape[1]
+        if channels_first_out:
+            out = torch.empty(P, C, K, dtype=_F32, device=tokens.device)
+            ostr = (C * K, 1, K)          # (oP, oK, oC)
+        else:
+            out = torch.empty(P, K, C, dtype=_F32, device=tokens.device)
+            ostr = (K * C, C, 1)
+        inv = None
+        if P and K:
+            inv = _sample_fwd(tokens, strides, L, P, C, ph, pw, h, w, kp, patch, stride, normalize, out, ostr)
+        ctx.save_for_backward(kp, out if normalize else None, inv)
+        ctx.meta = (tokens.shape, tokens.dtype, layout, geom, normalize, ostr, channels_first_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        kp, out, inv = ctx.saved_tensors
+        shape, dtype, (L, P, N, C, _, gstrides), (ph, pw, h, w, patch, stride), normalize, ostr, cf = ctx.meta
+        lib = load()
+        K = kp.shape[1]
+        gt = torch.zeros(shape, dtype=_F32, device=grad_out.device)
+        if P and K:
+            grad_out = grad_out.to(_F32)
+            if cf:   # (P, C, K)
+                gstr = (grad_out.stride(0), grad_out.stride(2), grad_out.stride(1))
+            else:    # (P, K, C)
+                gstr = (grad_out.stride(0), grad_out.stride(1), grad_out.stride(2))
+            with torch.cuda.device(grad_out.device):
+                check(lib.gd3_sample_tokens_bwd(ptr(grad_out), *gstr, ptr(out), *ostr, ptr(inv), ptr(kp), L, P, K, C,
+                                                ph, pw, h, w, patch, stride, int(normalize), ptr(gt), *gstrides,
+                                                stream_ptr()))
+        return gt.to(dtype), None, None, None, None, None
+
+
+def sample_tokens(tokens, grid, kp, patch_size=14, stride=14, normalize=False, image_hw=None):
+    """Sample token-major ViT features at pixel keypoints: (P, N, C) or (L, P, N, C) -> (P, K, C).
+
+    grid = (ph, pw) patches; kp (P, K, 2) pixel (x, y).  With a leading layer axis the L sampled maps
+    are averaged (the reference samples blocks 4..7 separately and takes the mean,
+    src/finetune_timm_mast3r.py:271-277).  normalize=True applies F.normalize over channels (:312-313).
+    """
+    ph, pw = grid
+    h, w = image_hw if image_hw is not None else (ph * patch_size, pw * patch_size)
+    if tokens.dim() == 3:
+        P, N, C = tokens.shape
+        L = 1
+        strides = (0, tokens.stride(0), tokens.stride(1), tokens.stride(2))
+        gstrides = (0, N * C, C, 1)
+    elif tokens.dim() == 4:
+        L, P, N, C = tokens.shape
+        strides = tuple(tokens.stride())
+        gstrides = (P * N * C, N * C, C, 1)
+    else:
+        raise ValueError('sample_tokens: tokens must be (P, N, C) or (L, P, N, C)')
+    return _SampleTokens.apply(tokens, kp, (ph, pw, h, w, patch_size, stride), normalize, False,
+                               (L, P, N, C, strides, gstrides))
+
+
+def interpolate_nchw(descriptors, pts, h, w, patch_size, stride, normalize):
+    """NCHW flavour behind the ``interpolate_features`` drop-in: (B, C, h', w') -> (B, C, K)."""
+    B, C, fh, fw = descriptors.shape
+    if descriptors.stride(2) != fw * descriptors.stride(3):
+        descriptors = descriptors.contiguous()      # rows of the map must be evenly spaced: n = y*fw + x
+    strides = (0, descriptors.stride(0), descriptors.stride(3), descriptors.stride(1))
+    gstrides = (0, C * fh * fw, 1, fh * fw)
+    return _SampleTokens.apply(descriptors, pts, (fh, fw, h, w, patch_size, stride), normalize, True,
+                               (1, B, fh * fw, C, strides, gstrides))

@@ -63,6 +63,53 @@ int gd3_reciprocal_nn(const float* A, int64_t nA, const float* B, int64_t nB, in
                       int64_t* nn_A, int64_t* nn_B, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Dense cost-volume KL loss, forward + backward, batched over P image pairs.
+ * Replaces the body of calculate_cost_loss (src/finetune_timm_mast3r.py:504-540 for
+ * GD3_VARIANT_MAST3R, src/finetune_timm_vggt.py:488-533 for GD3_VARIANT_VGGT) including
+ * F.normalize + bmm (:524-528), get_masked_patch_cost (utils/functions.py:402-422) and
+ * kl_divergence_map (utils/losses.py:5-15).
+ *   f1, f2   (P, N, C) student patch features, dtype f32 or bf16, arbitrary element strides
+ *            (sP, sN, sC) -- the MASt3R path hands over a channel-major view (sN = 1, sC = N)
+ *   t12, t21 (P, N, N) fp32 teacher volumes, rows of t12 = patches of view 1, rows of t21 =
+ *            patches of view 2; t_row_stride / t_pair_stride in elements
+ *   m1, m2   (P, N) uint8 patch masks (mask_patch_1 of each direction; mask_patch_2 is always
+ *            None in the reference's callers)
+ *   loss     (P) fp32, one value per pair = (KL_12 + KL_21) / 2
+ *   grad_f1/2 (P, N, C) contiguous, same dtype as the features: d loss[p] / d f (NULL, NULL =
+ *            forward only)
+ * pairs_per_group: how many pairs share one pass over the workspace (0 = choose so that a group's
+ * working set stays L2-resident).
+ * ------------------------------------------------------------------------------------------ */
+int64_t gd3_cost_kl_group_size(int64_t P, int64_t N, int64_t C, int64_t pairs_per_group);
+size_t gd3_cost_kl_workspace(int64_t P, int64_t N, int64_t C, int64_t pairs_per_group, int with_backward);
+int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N, int64_t C, int64_t s1P, int64_t s1N,
+                int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const float* t12, const float* t21,
+                int64_t t_pair_stride, int64_t t_row_stride, const uint8_t* m1, const uint8_t* m2, int variant,
+                float eps, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bilinear sampling of patch-token maps at pixel keypoints.  Replaces interpolate_features
+ * (utils/functions.py:55-76) and the glue of get_intermediate_feature / get_feature
+ * (src/finetune_timm_mast3r.py:271-277, 307-313): optional mean over L layers (sampling is linear)
+ * and optional channel L2 normalisation (F.normalize, eps 1e-12).
+ *   tokens  element (l, p, n, c) at tokens[l*sL + p*sP + n*sN + c*sC], n = y*pw + x; f32 or bf16
+ *   ph, pw  feature-map size in patches; h, w the image size in pixels the reference passes
+ *   kp      (P, K, 2) fp32 pixel (x, y)
+ *   out     element (p, k, c) at out[p*oP + k*oK + c*oC], fp32
+ *   inv_norm (P, K) fp32, written when normalize != 0 (needed by the backward)
+ * The backward accumulates into grad_tokens (fp32, same strides as tokens, caller-zeroed).
+ * ------------------------------------------------------------------------------------------ */
+int gd3_sample_tokens_fwd(const void* tokens, int dtype, int64_t L, int64_t P, int64_t C, int64_t ph, int64_t pw,
+                          int64_t h, int64_t w, int64_t sL, int64_t sP, int64_t sN, int64_t sC, const float* kp,
+                          int64_t K, int patch, int stride, int normalize, float* out, int64_t oP, int64_t oK, int64_t oC,
+                          float* inv_norm, void* stream);
+int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t gC, const float* out, int64_t oP,
+                          int64_t oK, int64_t oC, const float* inv_norm, const float* kp, int64_t L, int64_t P,
+                          int64_t K, int64_t C, int64_t ph, int64_t pw, int64_t h, int64_t w, int patch, int stride,
+                          int normalize, float* grad_tokens, int64_t sL, int64_t sP, int64_t sN, int64_t sC, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Debug / self-test: C[b] = A[b] * B[b]^T through the tcgen05 GEMM used by all fused losses.
  * A: (batch, M, lda) bf16, B: (batch, N, ldb) bf16, C: (batch, M, ldc) fp32.  Not a reference
  * interface; used by tests to validate the TMA / UMMA descriptor plumbing in isolation.

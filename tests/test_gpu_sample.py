@@ -1,0 +1,92 @@
+"""GPU parity of the bilinear token sampler (forward + backward) against goldens and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bodies, functions as ofn, synth
+from helpers import assert_grad_close
+
+pytestmark = pytest.mark.gpu
+T = torch.as_tensor
+
+
+def test_interpolate_features_golden(golden):
+    from gd3.compat import functions as fn
+    g = golden('helpers.npz')
+    fmap, pts = T(g['interp/fmap']).cuda(), T(g['interp/pts']).cuda()
+    for nrm in (False, True):
+        out = fn.interpolate_features(fmap, pts, h=9 * 14, w=13 * 14, normalize=nrm)
+        np.testing.assert_allclose(out.cpu().numpy(), g[f'interp/out_norm{int(nrm)}'], rtol=0, atol=2e-6)
+    out = fn.interpolate_features(T(g['interp16/fmap']).cuda(), T(g['interp16/pts']).cuda(), h=320, w=480,
+                                  normalize=False, patch_size=16, stride=16)
+    np.testing.assert_allclose(out.cpu().numpy(), g['interp16/out'], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize('normalize', [False, True])
+def test_interpolate_features_backward(normalize):
+    from gd3.compat import functions as fn
+    gen = synth._gen(9)
+    fmap = torch.randn(2, 40, 7, 11, generator=gen)
+    pts = torch.stack([torch.rand(2, 33, generator=gen) * 11 * 14, torch.rand(2, 33, generator=gen) * 7 * 14], -1)
+    w = torch.randn(2, 40, 33, generator=gen)
+    a = fmap.clone().requires_grad_(True)
+    (ofn.interpolate_features(a, pts, 7 * 14, 11 * 14, normalize=normalize) * w).sum().backward()
+    b = fmap.cuda().requires_grad_(True)
+    out = fn.interpolate_features(b, pts.cuda(), 7 * 14, 11 * 14, normalize=normalize)
+    (out * w.cuda()).sum().backward()
+    assert_grad_close(b.grad, a.grad, cos_min=0.99999, name='fmap', norm_rtol=1e-3)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('layers', [0, 4])
+def test_sample_tokens_vs_oracle(dtype, layers):
+    from gd3 import ops
+    ph, pw, C, K, P = 16, 20, 96, 57, 3
+    gen = synth._gen(31 + layers)
+    shape = (P, ph * pw, C) if layers == 0 else (layers, P, ph * pw, C)
+    tok = synth.bf16_round(torch.randn(*shape, generator=gen))
+    kp = torch.stack([torch.randint(0, pw * 14, (P, K), generator=gen),
+                      torch.randint(0, ph * 14, (P, K), generator=gen)], -1).float()
+    w = torch.randn(P, K, C, generator=gen)
+    for normalize in (False, True):
+        a = tok.clone().requires_grad_(True)
+        if layers == 0:
+            ref = bodies.sample_tokens(a, ph, pw, kp, normalize=False)
+        else:
+            ref = torch.stack([bodies.sample_tokens(a[l], ph, pw, kp, normalize=False) for l in range(layers)]).mean(0)
+        if normalize:
+            ref = torch.nn.functional.normalize(ref, p=2, dim=-1)
+        (ref * w).sum().backward()
+        b = tok.to('cuda', dtype).requires_grad_(True)
+        out = ops.sample_tokens(b, (ph, pw), kp.cuda(), normalize=normalize)
+        (out * w.cuda()).sum().backward()
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=0, atol=3e-6)
+        assert_grad_close(b.grad, a.grad, cos_min=0.9999, name='tokens', norm_rtol=1e-2)
+
+
+def test_sample_tokens_empty():
+    from gd3 import ops
+    tok = torch.randn(2, 16, 8, device='cuda', requires_grad=True)
+    out = ops.sample_tokens(tok, (4, 4), torch.zeros(2, 0, 2, device='cuda'))
+    assert out.shape == (2, 0, 8)
+    out.sum().backward()
+    assert float(tok.grad.abs().max()) == 0.0
+
+
+def test_small_helpers_golden(golden):
+    from gd3.compat import functions as fn
+    g = golden('helpers.npz')
+    out = fn.extract_kp_depth(T(g['kpdepth/depth']).cuda(), T(g['kpdepth/kp']).cuda())
+    np.testing.assert_allclose(out.cpu().numpy(), g['kpdepth/out'], rtol=0, atol=2e-6)
+    kp = T(g['kpmask/kp']).cuda()
+    assert (fn.get_patch_mask_from_kp_tensor(kp, 168, 224, 14).cpu().numpy() == g['kpmask/out']).all()
+    assert (fn.get_patch_mask_from_kp_tensor(kp - 1000, 168, 224, 14).cpu().numpy() == g['kpmask/out_empty']).all()
+    xs = T(g['sigmoid/x']).cuda()
+    np.testing.assert_allclose(fn.sigmoid(xs, 0.01).cpu().numpy(), g['sigmoid/y_t001'], rtol=2e-6, atol=0)
+    cost, m1, m2 = T(g['mpc/cost']).cuda(), T(g['mpc/m1']).cuda(), T(g['mpc/m2']).cuda()
+    np.testing.assert_allclose(fn.get_masked_patch_cost(cost, m1).cpu().numpy(), g['mpc/rownorm'], rtol=1e-6)
+    np.testing.assert_allclose(fn.get_masked_patch_cost(cost, m1, use_softmax=True, temperature=0.5).cpu().numpy(),
+                               g['mpc/softmax'], rtol=1e-6)
+    np.testing.assert_allclose(fn.get_masked_patch_cost(cost, m1, m2).cpu().numpy(), g['mpc/rownorm_m2'], rtol=1e-6)
+    _, idx = fn.filter_kp_by_conf(T(g['conf/kp']).cuda(), T(g['conf/mask']).cuda())
+    assert (idx.cpu().numpy() == g['conf/idx']).all()
