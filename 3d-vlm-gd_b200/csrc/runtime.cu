@@ -84,7 +84,7 @@ int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64
   int rc;
   if ((rc = tc::make_tmap_bf16(&ta, A, K, M, batch, lda, M * lda, tc::BM))) return rc;
   if ((rc = tc::make_tmap_bf16(&tb, B, K, N, batch, ldb, N * ldb, tile_n))) return rc;
-  tc::EpiStoreF32::Params ep{C, (int)M, (int)N, ldc, M * ldc, 1.0f};
+  tc::EpiStoreF32::Params ep{C, (int)M, (int)N, ldc, M * ldc, 1.0f, nullptr};
   tc::GemmShape s{(int)M, (int)N, (int)K, (int)batch};
   if (tile_n == 256) return tc::launch_gemm<256, 4, tc::EpiStoreF32>(ta, tb, s, ep, stream);
   return tc::launch_gemm<128, 8, tc::EpiStoreF32>(ta, tb, s, ep, stream);

@@ -1,0 +1,301 @@
+// K2: Smooth-AP sparse-correspondence loss, forward + backward, batched over image pairs.
+//
+// Replaces the loss bodies of calculate_matching_loss (src/finetune_timm_mast3r.py:557-589 "mast3r",
+// src/finetune_timm_vggt.py:543-574 "vggt") and of FinetuneTIMM.training_step
+// (src/finetune_timm_me.py:196-217 "me"), including torch.cdist, torch.bmm and the clamped
+// temperature sigmoid of utils/functions.py:24-33.
+//
+//   sim = d1 d2^T (K x K);  sig(u) = 1 / (1 + exp(clamp(-u/tau, -50, 50)))
+//   positives q = (s, t): the diagonal (mast3r / vggt) or every pair closer than thr_pos in 3-D (me)
+//   neg_sj = dist(p1_s, p2_j) > thr_neg  (and j != s for mast3r / vggt)
+//   S1 = sum_j neg sig(sim_sj - 1),  S2 = sum_j neg sig(sim_sj - pos),  pos = sim_st
+//   r1 = 1 + sig(pos - 1) (mast3r, me) | 1 + sig(1 - pos) (vggt),  r2 = 1 + sig(1 - pos)
+//   loss = mean_q (1 - (r1/(r1+S1) + r2/(r2+S2)) / 2)
+//
+// tau = 0.01 amplifies similarity error 100x, so the K x K similarity is computed on the tensor
+// cores with a 2-term bf16 split of both operands (hi*hi + hi*lo + lo*hi, three K-concatenated
+// panels in ONE tcgen05 GEMM, ~16 mantissa bits); the gradient GEMMs use plain bf16.
+//   1 ap_prepare       SIMT  split / transpose descriptors
+//   2 tc_gemm<Store>         sim (fp32, K x K per pair: <= 1 MB, L2 resident)
+//   3 ap_rows          SIMT  one block per row: S1, S2, loss, d loss / d sim (bf16, unnormalised)
+//   4 transpose_bf16   SIMT  dsim^T
+//   5 tc_gemm<Store> x2      d d1 = dsim d2 / Q,  d d2 = dsim^T d1 / Q   (Q = number of positives)
+#include "../../include/gd3.h"
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace gd3 {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// 1. operand preparation.  grid (ceil(K/32), P, 2 images), block 256
+//    image 0: A' = [hi | hi | lo] (K x 3 ldc);  image 1: B' = [hi | lo | hi];  XT = hi^T (C x ldk)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    ap_prepare(const float* __restrict__ d1, const float* __restrict__ d2, int K, int C, int ldc, int ldk,
+               __nv_bfloat16* __restrict__ A3, __nv_bfloat16* __restrict__ B3, __nv_bfloat16* __restrict__ d1T,
+               __nv_bfloat16* __restrict__ d2T) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z, p = blockIdx.y, k0 = blockIdx.x * 32;
+  const float* d = (img == 0 ? d1 : d2) + (int64_t)p * K * C;
+  __nv_bfloat16* X3 = (img == 0 ? A3 : B3) + (int64_t)p * K * 3 * ldc;
+  __nv_bfloat16* XT = (img == 0 ? d1T : d2T);
+  if (XT) XT += (int64_t)p * C * ldk;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // which panel holds the low-order term: image 0 -> panel 2, image 1 -> panel 1
+  const int lo_panel = img == 0 ? 2 : 1;
+  for (int c0 = 0; c0 < ldc; c0 += 32) {
+    __syncthreads();
+    for (int r = w; r < 32; r += 8) {
+      const int k = k0 + r, c = c0 + lane;
+      const float v = (k < K && c < C) ? __ldg(d + (int64_t)k * C + c) : 0.f;
+      tile[r][lane] = v;
+      if (k < K && c < ldc) {
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+        __nv_bfloat16* row = X3 + (int64_t)k * 3 * ldc + c;
+        row[0] = hi;
+        row[(3 - lo_panel) * ldc] = hi;      // the other hi panel (1 for image 0, 2 for image 1)
+        row[lo_panel * ldc] = lo;
+      }
+    }
+    __syncthreads();
+    if (XT)
+      for (int r = w; r < 32; r += 8) {
+        const int c = c0 + r, k = k0 + lane;
+        if (c < C && k < K) XT[(int64_t)c * ldk + k] = __float2bfloat16(tile[lane][r]);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. per-row statistics and d loss / d sim.  grid (K, P), block 128, dynamic smem K floats
+// ------------------------------------------------------------------------------------------
+struct SigT {
+  float s, ds;
+};
+__device__ __forceinline__ SigT sig_both(float u, float inv_tau) {
+  const float e = -u * inv_tau;
+  const float ec = fminf(fmaxf(e, -50.f), 50.f);
+  const float s = 1.f / (1.f + expf(ec));
+  SigT r;
+  r.s = s;
+  r.ds = (e >= -50.f && e <= 50.f) ? s * (1.f - s) * inv_tau : 0.f;
+  return r;
+}
+__device__ __forceinline__ float dist3(const float* a, const float* b) {
+  const float dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+  return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+__global__ void __launch_bounds__(128)
+    ap_rows(const float* __restrict__ sim, int lds, const float* __restrict__ p1, const float* __restrict__ p2, int K,
+            int variant, float inv_tau, float thr_neg, float thr_pos, __nv_bfloat16* __restrict__ dS, int ldk,
+            double* __restrict__ loss_acc, int* __restrict__ qcount) {
+  extern __shared__ float rowbuf[];   // K floats: d loss / d sim of this row (sum over the row's positives)
+  __shared__ float red[32];
+  const int s = blockIdx.x, p = blockIdx.y;
+  const float* srow = sim + ((int64_t)p * K + s) * lds;
+  const float* a = p1 + ((int64_t)p * K + s) * 3;
+  const float* P2 = p2 + (int64_t)p * K * 3;
+  const bool me = variant == GD3_VARIANT_ME;
+  const bool want_grad = dS != nullptr;
+
+  // S1 does not depend on the positive
+  float S1 = 0.f;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    rowbuf[j] = 0.f;
+    const bool neg = (dist3(a, P2 + 3 * j) > thr_neg) && (me || j != s);
+    if (neg) S1 += sig_both(srow[j] - 1.f, inv_tau).s;
+  }
+  S1 = block_sum(S1, red);
+
+  int npos = 0;
+  float loss_row = 0.f;
+  const int t_begin = me ? 0 : s, t_end = me ? K : s + 1;
+  for (int t = t_begin; t < t_end; ++t) {
+    if (me && !(dist3(a, P2 + 3 * t) < thr_pos)) continue;   // block-uniform
+    ++npos;
+    const float pos = srow[t];
+    float S2 = 0.f;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+      const bool neg = (dist3(a, P2 + 3 * j) > thr_neg) && (me || j != s);
+      if (neg) S2 += sig_both(srow[j] - pos, inv_tau).s;
+    }
+    S2 = block_sum(S2, red);
+    const SigT q1 = (variant == GD3_VARIANT_VGGT) ? sig_both(1.f - pos, inv_tau) : sig_both(pos - 1.f, inv_tau);
+    const SigT q2 = sig_both(1.f - pos, inv_tau);
+    const float r1 = 1.f + q1.s, r2 = 1.f + q2.s;
+    const float den1 = r1 + S1, den2 = r2 + S2;
+    loss_row += 1.f - 0.5f * (r1 / den1 + r2 / den2);
+    if (!want_grad) continue;
+    const float c1 = r1 / (den1 * den1), c2 = r2 / (den2 * den2);
+    float G2 = 0.f;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+      const bool neg = (dist3(a, P2 + 3 * j) > thr_neg) && (me || j != s);
+      if (neg) {
+        const float sj = srow[j];
+        const float g1 = sig_both(sj - 1.f, inv_tau).ds, g2 = sig_both(sj - pos, inv_tau).ds;
+        rowbuf[j] += 0.5f * (c1 * g1 + c2 * g2);
+        G2 += g2;
+      }
+    }
+    G2 = block_sum(G2, red);
+    if (threadIdx.x == 0) {
+      const float dr1 = (variant == GD3_VARIANT_VGGT) ? -q1.ds : q1.ds;
+      const float dpos = -0.5f * (S1 / (den1 * den1) * dr1 - S2 / (den2 * den2) * q2.ds + c2 * G2);
+      rowbuf[t] += dpos;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && npos > 0) {
+    atomicAdd(loss_acc + p, (double)loss_row);
+    atomicAdd(qcount + p, npos);
+  }
+  if (want_grad) {
+    __syncthreads();
+    __nv_bfloat16* drow = dS + ((int64_t)p * K + s) * ldk;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) drow[j] = __float2bfloat16(rowbuf[j]);
+  }
+}
+
+// loss[p] = acc / Q, scale[p] = 1 / Q  (Q = 0 -> mean of an empty set: NaN like the reference, zero gradient)
+__global__ void ap_finalize(const double* __restrict__ acc, const int* __restrict__ q, float* __restrict__ loss,
+                            float* __restrict__ scale, int P) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) {
+    const int Q = q[p];
+    loss[p] = Q > 0 ? (float)(acc[p] / (double)Q) : __int_as_float(0x7fc00000);
+    scale[p] = Q > 0 ? 1.f / (float)Q : 0.f;
+  }
+}
+
+// 4. batched bf16 transpose of K x K matrices with leading dimension ld.  grid (ceil(K/32), ceil(K/32), P)
+__global__ void __launch_bounds__(256)
+    transpose_bf16(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int K, int ld) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int p = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const __nv_bfloat16* src = in + (int64_t)p * K * ld;
+  __nv_bfloat16* dst = out + (int64_t)p * K * ld;
+  for (int r = w; r < 32; r += 8)
+    tile[r][lane] = (r0 + r < K && c0 + lane < K) ? src[(int64_t)(r0 + r) * ld + c0 + lane] : __float2bfloat16(0.f);
+  __syncthreads();
+  for (int r = w; r < 32; r += 8)
+    if (c0 + r < K && r0 + lane < K) dst[(int64_t)(c0 + r) * ld + r0 + lane] = tile[lane][r];
+}
+
+struct APWorkspace {
+  __nv_bfloat16 *A3, *B3, *d1T, *d2T, *dS, *dST;
+  float *sim, *scale;
+  double* loss_acc;
+  int* qcount;
+  size_t total;
+  int ldc, ldk, lds;
+};
+
+APWorkspace carve_ap(void* base, int64_t P, int64_t K, int64_t C, bool backward) {
+  APWorkspace w{};
+  Carver c(base);
+  w.ldc = (int)round_up<int64_t>(C, 8);
+  w.ldk = (int)round_up<int64_t>(K, 8);
+  w.lds = (int)round_up<int64_t>(K, 4);
+  w.A3 = c.take<__nv_bfloat16>(P * K * 3 * w.ldc);
+  w.B3 = c.take<__nv_bfloat16>(P * K * 3 * w.ldc);
+  w.d1T = c.take<__nv_bfloat16>(backward ? P * C * w.ldk : 0);
+  w.d2T = c.take<__nv_bfloat16>(backward ? P * C * w.ldk : 0);
+  w.dS = c.take<__nv_bfloat16>(backward ? P * K * w.ldk : 0);
+  w.dST = c.take<__nv_bfloat16>(backward ? P * K * w.ldk : 0);
+  w.sim = c.take<float>(P * K * w.lds);
+  w.scale = c.take<float>(P);
+  w.loss_acc = c.take<double>(P);
+  w.qcount = c.take<int>(P);
+  w.total = c.total();
+  return w;
+}
+
+}  // namespace
+}  // namespace gd3
+
+using namespace gd3;
+
+extern "C" {
+
+size_t gd3_smooth_ap_workspace(int64_t P, int64_t K, int64_t C, int with_backward) {
+  if (P <= 0 || K <= 0 || C <= 0) return 0;
+  return carve_ap(nullptr, P, K, C, with_backward != 0).total;
+}
+
+int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const float* pts3d_2, int64_t P, int64_t K,
+                  int64_t C, int variant, float temp, float thr_neg, float thr_pos, float* loss, float* grad_d1,
+                  float* grad_d2, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (P == 0) return GD3_OK;
+  GD3_REQUIRE(P > 0 && K >= 0 && C > 0, "gd3_smooth_ap: bad sizes P=%lld K=%lld C=%lld", (long long)P, (long long)K,
+              (long long)C);
+  GD3_REQUIRE(loss, "gd3_smooth_ap: null loss");
+  GD3_REQUIRE(variant == GD3_VARIANT_MAST3R || variant == GD3_VARIANT_VGGT || variant == GD3_VARIANT_ME,
+              "gd3_smooth_ap: unknown variant %d", variant);
+  GD3_REQUIRE(temp > 0.f, "gd3_smooth_ap: temperature must be positive");
+  GD3_REQUIRE((grad_d1 == nullptr) == (grad_d2 == nullptr), "gd3_smooth_ap: pass both gradients or neither");
+  GD3_REQUIRE(P <= 65535 && K <= 12000, "gd3_smooth_ap: P <= 65535 and K <= 12000 supported");
+  if (K == 0) {
+    // torch.mean over zero positives is NaN in the reference; its callers early-out before (K = 0 => loss 0)
+    GD3_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float) * P, stream));
+    return GD3_OK;
+  }
+  GD3_REQUIRE(d1 && d2 && pts3d_1 && pts3d_2, "gd3_smooth_ap: null input");
+  const bool backward = grad_d1 != nullptr;
+  APWorkspace w = carve_ap(workspace, P, K, C, backward);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("gd3_smooth_ap: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return GD3_ERR_WORKSPACE;
+  }
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * P, stream));
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int) * P, stream));
+  {
+    dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)P, 2);
+    ap_prepare<<<grid, 256, 0, stream>>>(d1, d2, (int)K, (int)C, w.ldc, w.ldk, w.A3, w.B3, backward ? w.d1T : nullptr,
+                                         backward ? w.d2T : nullptr);
+    GD3_CHECK_LAUNCH();
+  }
+  int rc;
+  {
+    CUtensorMap ta, tb;
+    if ((rc = tc::make_tmap_bf16(&ta, w.A3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc,
+                                 tc::BM)))
+      return rc;
+    if ((rc = tc::make_tmap_bf16(&tb, w.B3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 128)))
+      return rc;
+    tc::EpiStoreF32::Params ep{w.sim, (int)K, (int)K, w.lds, K * (int64_t)w.lds, 1.0f, nullptr};
+    tc::GemmShape s{(int)K, (int)K, 3 * w.ldc, (int)P};
+    if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>(ta, tb, s, ep, stream))) return rc;
+  }
+  {
+    dim3 grid((unsigned)K, (unsigned)P);
+    ap_rows<<<grid, 128, sizeof(float) * K, stream>>>(w.sim, w.lds, pts3d_1, pts3d_2, (int)K, variant, 1.f / temp,
+                                                      thr_neg, thr_pos, backward ? w.dS : nullptr, w.ldk, w.loss_acc,
+                                                      w.qcount);
+    GD3_CHECK_LAUNCH();
+    ap_finalize<<<(unsigned)ceil_div<int64_t>(P, 128), 128, 0, stream>>>(w.loss_acc, w.qcount, loss, w.scale, (int)P);
+    GD3_CHECK_LAUNCH();
+  }
+  if (backward) {
+    dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)ceil_div<int64_t>(K, 32), (unsigned)P);
+    transpose_bf16<<<grid, 256, 0, stream>>>(w.dS, w.dST, (int)K, w.ldk);
+    GD3_CHECK_LAUNCH();
+    CUtensorMap t_ds, t_dst, t_d1t, t_d2t;
+    if ((rc = tc::make_tmap_bf16(&t_ds, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_dst, w.dST, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d1t, w.d1T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d2t, w.d2T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
+    tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
+    tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, 1.0f, w.scale};
+    tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, 1.0f, w.scale};
+    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_ds, t_d2t, s, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_dst, t_d1t, s, e2, stream))) return rc;
+  }
+  return GD3_OK;
+}
+
+}  // extern "C"

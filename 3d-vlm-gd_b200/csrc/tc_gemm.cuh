@@ -340,9 +340,11 @@ struct EpiStoreF32 {
     int M, N;
     int64_t ldc, batch_stride;
     float alpha;
+    const float* batch_scale;   // optional per-batch factor read from device memory (nullptr = 1)
   };
   __device__ static void run(const Params& p, const EpiCtx& cx) {
     const int m = cx.m0 + cx.row;
+    const float alpha = p.batch_scale ? p.alpha * __ldg(p.batch_scale + cx.b) : p.alpha;
     float* crow = p.C + cx.b * p.batch_stride + static_cast<int64_t>(m) * p.ldc;
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (p.batch_stride % 4 == 0);
@@ -354,14 +356,13 @@ struct EpiStoreF32 {
         if (vec_ok && n + 32 <= p.N) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha, v[4 * q + 2] * p.alpha,
-                                   v[4 * q + 3] * p.alpha);
+            float4 o = make_float4(v[4 * q] * alpha, v[4 * q + 1] * alpha, v[4 * q + 2] * alpha, v[4 * q + 3] * alpha);
             *reinterpret_cast<float4*>(crow + n + 4 * q) = o;
           }
         } else {
 #pragma unroll
           for (int q = 0; q < 32; ++q)
-            if (n + q < p.N) crow[n + q] = v[q] * p.alpha;
+            if (n + q < p.N) crow[n + q] = v[q] * alpha;
         }
       }
     }

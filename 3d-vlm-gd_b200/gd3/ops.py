@@ -43,7 +43,7 @@ class _CostVolumeKL(torch.autograd.Function):
         t21 = teacher21.to(_F32).contiguous()
         m1 = _as_mask(mask1, P, N, dev)
         m2 = _as_mask(mask2, P, N, dev)
-        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_grad = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         loss = torch.empty(P, dtype=_F32, device=dev)
         g1 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
         g2 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
@@ -80,6 +80,60 @@ def cost_volume_kl(f1, f2, teacher12, teacher21, mask1=None, mask2=None, variant
     src/finetune_timm_mast3r.py:504-540, 'vggt': src/finetune_timm_vggt.py:488-533) for each pair.
     """
     return _CostVolumeKL.apply(f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group)
+
+
+# --------------------------------------------------------------------------------------------
+# Smooth-AP sparse-correspondence loss
+# --------------------------------------------------------------------------------------------
+class _SmoothAP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d1, d2, p1, p2, variant, temp, thr_neg, thr_pos):
+        require_cuda(d1, d2, p1, p2)
+        lib = load()
+        if d1.dim() != 3 or d1.shape != d2.shape:
+            raise ValueError(f'smooth_ap: descriptors must both be (P, K, C), got {tuple(d1.shape)} {tuple(d2.shape)}')
+        if variant not in VARIANT:
+            raise ValueError(f'smooth_ap: unknown variant {variant!r}')
+        P, K, C = d1.shape
+        if p1.shape != (P, K, 3) or p2.shape != (P, K, 3):
+            raise ValueError(f'smooth_ap: 3-D points must be (P, K, 3) = {(P, K, 3)}')
+        dev = d1.device
+        a = d1.to(_F32).contiguous()
+        b = d2.to(_F32).contiguous()
+        q1 = p1.to(_F32).contiguous()
+        q2 = p2.to(_F32).contiguous()
+        need_grad = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        loss = torch.zeros(P, dtype=_F32, device=dev)
+        g1 = torch.zeros(P, K, C, dtype=_F32, device=dev) if need_grad else None
+        g2 = torch.zeros(P, K, C, dtype=_F32, device=dev) if need_grad else None
+        if P and K:
+            ws = workspace(lib.gd3_smooth_ap_workspace(P, K, C, int(need_grad)), dev)
+            with torch.cuda.device(dev):
+                check(lib.gd3_smooth_ap(ptr(a), ptr(b), ptr(q1), ptr(q2), P, K, C, VARIANT[variant], float(temp),
+                                        float(thr_neg), float(thr_pos), ptr(loss), ptr(g1), ptr(g2), ptr(ws),
+                                        ws.numel(), stream_ptr()))
+        ctx.save_for_backward(g1, g2)
+        ctx.in_dtypes = (d1.dtype, d2.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        g1, g2 = ctx.saved_tensors
+        if g1 is None:
+            return (None,) * 8
+        s = grad_loss.to(_F32)[:, None, None]
+        return (g1 * s).to(ctx.in_dtypes[0]), (g2 * s).to(ctx.in_dtypes[1]), None, None, None, None, None, None
+
+
+def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1, thr_pos=5e-3):
+    """Smooth-AP matching loss per pair, ``(P,)``.
+
+    d1, d2: (P, K, C) L2-normalised keypoint descriptors; pts3d_*: (P, K, 3).  Equals the loss body
+    of ``calculate_matching_loss`` (variant 'mast3r': src/finetune_timm_mast3r.py:557-589, 'vggt':
+    src/finetune_timm_vggt.py:543-574) or of src/finetune_timm_me.py:196-217 ('me') for each pair.
+    K = 0 gives loss 0 (the callers' early-out, src/finetune_timm_mast3r.py:604-607).
+    """
+    return _SmoothAP.apply(d1, d2, pts3d_1, pts3d_2, variant, temp, thr_neg, thr_pos)
 
 
 # --------------------------------------------------------------------------------------------

@@ -89,6 +89,21 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
                 size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Smooth-AP sparse-correspondence loss, forward + backward, batched over P pairs.
+ * Replaces the loss bodies of calculate_matching_loss (src/finetune_timm_mast3r.py:557-589,
+ * src/finetune_timm_vggt.py:543-574) and of src/finetune_timm_me.py:196-217, including torch.cdist,
+ * torch.bmm and the clamped sigmoid of utils/functions.py:24-33.
+ *   d1, d2      (P, K, C) fp32 contiguous, L2-normalised keypoint descriptors
+ *   pts3d_1/2   (P, K, 3) fp32 3-D points of the keypoints
+ *   temp 0.01, thr_neg 0.1 (thres3d_neg), thr_pos 5e-3 (thresh3d_pos, GD3_VARIANT_ME only)
+ *   loss        (P) fp32;  grad_d1/2 (P, K, C) fp32 contiguous or NULL, NULL for forward only
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_smooth_ap_workspace(int64_t P, int64_t K, int64_t C, int with_backward);
+int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const float* pts3d_2, int64_t P, int64_t K,
+                  int64_t C, int variant, float temp, float thr_neg, float thr_pos, float* loss, float* grad_d1,
+                  float* grad_d2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Bilinear sampling of patch-token maps at pixel keypoints.  Replaces interpolate_features
  * (utils/functions.py:55-76) and the glue of get_intermediate_feature / get_feature
  * (src/finetune_timm_mast3r.py:271-277, 307-313): optional mean over L layers (sampling is linear)

@@ -1,0 +1,107 @@
+"""GPU parity of the fused Smooth-AP loss (through the C ABI): goldens from the live reference, the CPU
+oracle at full size, and the composition sample_tokens -> normalise -> smooth_ap with gradients
+flowing back to the token maps."""
+import math
+
+import pytest
+import torch
+
+from oracle import bodies, synth
+from helpers import assert_grad_close, rel_err
+from test_oracle_golden import AP_CASES
+
+pytestmark = pytest.mark.gpu
+T = torch.as_tensor
+VARS = ['mast3r', 'vggt', 'me']
+
+
+@pytest.mark.parametrize('case', AP_CASES)
+def test_smooth_ap_golden(golden, case):
+    from gd3 import ops
+    g = golden('smooth_ap.npz')
+    K, C, seed, var = [int(v) for v in g[f'{case}/meta']]
+    d1 = T(g[f'{case}/d1']).cuda()[None].requires_grad_(True)
+    d2 = T(g[f'{case}/d2']).cuda()[None].requires_grad_(True)
+    p1, p2 = T(g[f'{case}/p1']).cuda()[None], T(g[f'{case}/p2']).cuda()[None]
+    loss = ops.smooth_ap(d1, d2, p1, p2, variant=VARS[var])
+    loss.sum().backward()
+    want = float(g[f'{case}/loss'])
+    assert abs(loss[0].item() - want) <= 1e-3 * abs(want) + 1e-7, (loss[0].item(), want)
+    assert_grad_close(d1.grad[0], T(g[f'{case}/grad_d1']), name='grad_d1', norm_rtol=3e-2)
+    assert_grad_close(d2.grad[0], T(g[f'{case}/grad_d2']), name='grad_d2', norm_rtol=3e-2)
+
+
+@pytest.mark.parametrize('case', ['small_mast3r', 'odd_vggt', 'mid_me'])
+def test_sample_then_smooth_ap_golden(golden, case):
+    """Gradients all the way back to the token maps (bilinear scatter + normalise backward)."""
+    from gd3 import ops
+    g = golden('smooth_ap.npz')
+    K, C, seed, var = [int(v) for v in g[f'{case}/meta']]
+    g1 = T(g[f'{case}/g1']).cuda()[None].requires_grad_(True)
+    g2 = T(g[f'{case}/g2']).cuda()[None].requires_grad_(True)
+    kp1, kp2 = T(g[f'{case}/kp1']).cuda()[None], T(g[f'{case}/kp2']).cuda()[None]
+    d1 = ops.sample_tokens(g1, (16, 16), kp1, normalize=True)
+    d2 = ops.sample_tokens(g2, (16, 16), kp2, normalize=True)
+    loss = ops.smooth_ap(d1, d2, T(g[f'{case}/p1']).cuda()[None], T(g[f'{case}/p2']).cuda()[None], variant=VARS[var])
+    loss.sum().backward()
+    assert rel_err(loss[0].item(), g[f'{case}/loss']) <= 1e-3
+    assert_grad_close(g1.grad[0], T(g[f'{case}/grad_g1']), name='grad_g1', norm_rtol=3e-2)
+    assert_grad_close(g2.grad[0], T(g[f'{case}/grad_g2']), name='grad_g2', norm_rtol=3e-2)
+
+
+def make_pair(seed, K, C, N=1024, grid=(32, 32)):
+    ph, pw = grid
+    g1, g2 = synth.ap_token_maps(seed, N, C)
+    kp1 = synth.keypoints(seed + 1, K, pw * 14, ph * 14)
+    kp2 = kp1 + (synth.keypoints(seed + 2, K, 9, 9) - 4.0)
+    kp2[:, 0].clamp_(3, pw * 14 - 4)
+    kp2[:, 1].clamp_(3, ph * 14 - 4)
+    p1, p2 = synth.points3d(seed + 3, K)
+    d1 = bodies.sample_tokens(g1[None], ph, pw, kp1[None], normalize=True)[0]
+    d2 = bodies.sample_tokens(g2[None], ph, pw, kp2[None], normalize=True)[0]
+    return d1, d2, p1, p2
+
+
+@pytest.mark.parametrize('variant,K,C', [('mast3r', 512, 768), ('vggt', 300, 1024)])
+def test_smooth_ap_full_size_batched(variant, K, C):
+    """BASELINE.json sizes (cfg2: K=512,C=768; cfg4: K=300,C=1024), 3 pairs per call vs the CPU oracle."""
+    from gd3 import ops
+    pairs = [make_pair(7000 + 10 * p, K, C) for p in range(3)]
+    want = []
+    for d1, d2, p1, p2 in pairs:
+        a = d1.clone().requires_grad_(True)
+        b = d2.clone().requires_grad_(True)
+        loss = bodies.smooth_ap(a, b, p1, p2, variant)
+        ga, gb = torch.autograd.grad(loss, [a, b])
+        want.append((float(loss), ga, gb))
+    D1, D2, P1, P2 = [torch.stack([q[k] for q in pairs]).cuda() for k in range(4)]
+    D1.requires_grad_(True)
+    D2.requires_grad_(True)
+    loss = ops.smooth_ap(D1, D2, P1, P2, variant=variant)
+    loss.sum().backward()
+    for p in range(3):
+        assert rel_err(loss[p].item(), want[p][0]) <= 1e-3, (p, loss[p].item(), want[p][0])
+        assert_grad_close(D1.grad[p], want[p][1], name=f'd1[{p}]', norm_rtol=3e-2)
+        assert_grad_close(D2.grad[p], want[p][2], name=f'd2[{p}]', norm_rtol=3e-2)
+
+
+def test_smooth_ap_edge_cases():
+    from gd3 import ops
+    # K = 0: the callers' early-out semantics -> loss 0, no kernel
+    z = ops.smooth_ap(torch.zeros(2, 0, 16, device='cuda'), torch.zeros(2, 0, 16, device='cuda'),
+                      torch.zeros(2, 0, 3, device='cuda'), torch.zeros(2, 0, 3, device='cuda'))
+    assert z.shape == (2,) and float(z.abs().max()) == 0.0
+    # 'me' without any positive: mean over an empty set is NaN in the reference
+    d = torch.nn.functional.normalize(torch.randn(1, 8, 16, device='cuda'), dim=-1)
+    p1 = torch.zeros(1, 8, 3, device='cuda')
+    p2 = torch.ones(1, 8, 3, device='cuda')
+    out = ops.smooth_ap(d, d, p1, p2, variant='me')
+    assert math.isnan(out[0].item())
+    with pytest.raises(ValueError):
+        ops.smooth_ap(d, d, p1, p2, variant='nope')
+    # forward only
+    with torch.no_grad():
+        l0 = ops.smooth_ap(d, d, p1, p1 + 0.001, variant='vggt')
+    dd = d.clone().requires_grad_(True)
+    l1 = ops.smooth_ap(dd, d, p1, p1 + 0.001, variant='vggt')
+    assert abs(l0[0].item() - l1[0].item()) < 1e-6
