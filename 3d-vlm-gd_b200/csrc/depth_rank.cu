@@ -1,0 +1,728 @@
+// K4: relative-depth losses on the depth-difference head, forward + backward, batched over keypoint sets.
+//
+// Replaces pairwise_logistic_ranking_loss (utils/losses.py:18-41), intra_depth_loss (utils/losses.py:44-69),
+// the head DepthAwareFeatureFusion.fusion_layer (+tanh) (utils/model.py:100-105,122-127) evaluated on all
+// K^2 feature differences, and the cross-view L1 term of calculate_depth_loss
+// (src/finetune_timm_mast3r.py:489-494).
+//
+// The reference materialises the (K, K, D) difference tensor and runs the MLP on K^2 rows.  The first
+// Linear is linear, so  W1 (f_b - f_a) + b1 = u_b - u_a + b1  with u = f W1^T (K x H, H = hidden = 128):
+// the D-wide GEMM is hoisted out of the pair loop and runs once on the tensor cores (split-bf16, ~fp32
+// accurate); only LayerNorm / GELU / w2 / tanh / loss are evaluated per pair, on chip.
+//
+// For an ordered pair (a -> b):  h = u_b - u_a + b1,  s = [tanh](w2 . GELU(LN(h)) + b2),  D = d_b - d_a
+//   logistic (ranking): valid = |D| > thr,          l = log(1 + exp(-sign(D) s))
+//   hinge (intra_depth): valid = |tanh D| > thr,    l = relu(margin - sign(D) s)      [reference pair (i,j) = (b,a)]
+//   loss = mean over valid pairs (0 without gradient if none)
+// L1 term: pairs keypoint k of set 2p+1 (a) with keypoint k of set 2p (b): mean_k |s - tanh(d_b - d_a)|.
+//
+// Layout of the pair kernel: 16 lanes own one pair, each lane 8 of the 128 hidden units, so LayerNorm / dot
+// reductions are 4 xor-shuffles and a warp works on two pairs at a time.  A CTA owns a 128 x 128 tile of
+// (a, b): every warp keeps the gradient of its b rows in registers and accumulates the a side into a shared
+// tile; the a index is staggered per warp so no two warps touch the same row in the same step.
+#include "../../include/gd3.h"
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace gd3 {
+namespace {
+
+constexpr int H = 128;           // hidden width of fusion_layer (utils/model.py:88)
+constexpr int HPL = 8;           // hidden units per lane
+constexpr int TILE = 128;        // a / b tile edge
+constexpr int WARPS = 16;
+constexpr int B_PER_WARP = TILE / WARPS;   // 8
+
+__device__ __forceinline__ float half_sum(float v) {   // sum over the 16 lanes of a half warp
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// hidden index of this lane's i-th element: two float4 groups, 64 apart -> conflict-free LDS.128
+__device__ __forceinline__ int hidx(int l16, int i) { return (i < 4) ? 4 * l16 + i : 64 + 4 * l16 + (i - 4); }
+
+struct HeadConst {   // per-lane slice of the head parameters
+  float gam[HPL], bet[HPL], w2[HPL];
+  float b2;
+};
+
+struct PairOut {
+  float s;           // head output
+  float rstd;
+  float xh[HPL];     // normalised pre-activation
+  float g[HPL];      // GELU(y)
+  float gp[HPL];     // GELU'(y)
+  float m1, m2;      // mean_h(q), mean_h(q * xh), q = w2 * gam * gp
+};
+
+// Head on one pre-activation difference hc (already mean-free over h).  erf by Abramowitz-Stegun 7.1.26
+// (|err| < 1.5e-7), sharing exp(-y^2/2) between erf and the Gaussian density needed by GELU'.
+template <bool GRAD>
+__device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadConst& hcst, float ln_eps, int use_tanh,
+                                          PairOut& o) {
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) ss = fmaf(hc[i], hc[i], ss);
+  ss = half_sum(ss);
+  o.rstd = rsqrtf(ss * (1.f / H) + ln_eps);
+  float acc = 0.f, m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) {
+    const float xh = hc[i] * o.rstd;
+    const float y = fmaf(xh, hcst.gam[i], hcst.bet[i]);
+    const float z = y * 0.70710678118654752f;
+    const float az = fabsf(z);
+    const float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(t, poly, 1.421413741f);
+    poly = fmaf(t, poly, -0.284496736f);
+    poly = fmaf(t, poly, 0.254829592f);
+    poly *= t;
+    const float e = exp2f(-z * z * 1.4426950408889634f);      // exp(-z^2) = exp(-y^2 / 2)
+    const float erf_abs = fmaf(-poly, e, 1.f);
+    const float phi = fmaf(0.5f, copysignf(erf_abs, z), 0.5f);  // standard normal CDF at y
+    const float g = y * phi;
+    acc = fmaf(hcst.w2[i], g, acc);
+    o.xh[i] = xh;
+    o.g[i] = g;
+    if (GRAD) {
+      const float gp = fmaf(y * e, 0.3989422804014327f, phi);   // Phi(y) + y * pdf(y)
+      const float q = hcst.w2[i] * hcst.gam[i] * gp;
+      o.gp[i] = gp;
+      m1 += q;
+      m2 = fmaf(q, xh, m2);
+    }
+  }
+  acc = half_sum(acc) + hcst.b2;
+  o.s = use_tanh ? tanhf(acc) : acc;
+  if (GRAD) {
+    o.m1 = half_sum(m1) * (1.f / H);
+    o.m2 = half_sum(m2) * (1.f / H);
+  }
+}
+
+struct RankParams {
+  const float* u;        // (S, K, H) fp32: f W1^T
+  const float* depth;    // (S, K)
+  const float* b1;       // (H)
+  const float* gamma;
+  const float* beta;
+  const float* w2;
+  const float* b2;
+  const float* inv_count;  // (S)   1 / #valid pairs (joint or per set), 0 if none
+  const float* w_rank;     // (S) or nullptr
+  int K, S;
+  int mode;              // 0 logistic, 1 hinge
+  int use_tanh;
+  float thr, margin, ln_eps;
+  double* loss_sum;      // (S) sum of pair losses (unnormalised)
+  float* dub_part;       // (S, TA, K, H) partial gradient of u on the b side, per a tile
+  float* dua_part;       // (S, TB, K, H) partial (positive) gradient flowing to -u_a, per b tile
+  float* gparam;         // packed parameter gradients: [W1 (H*D) | b1 | gamma | beta | w2 | b2]
+  int64_t gparam_off;    // offset of b1 inside gparam (= H * D)
+};
+
+// dynamic smem: va[TILE][H] | dua[TILE][H] | da[TILE] | red[3*H + 1]
+template <bool GRAD>
+__global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* va = smem;                       // centred u_a rows of the a tile
+  float* dua = va + TILE * H;             // accumulated d/d(u_a) (sign applied at reduction)
+  float* da = dua + TILE * H;             // depths of the a tile
+  float* red = da + TILE;                 // cross-warp reduction of parameter gradients
+  const int set = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  const int K = p.K;
+  const float* U = p.u + (int64_t)set * K * H;
+  const float* Dp = p.depth + (int64_t)set * K;
+
+  // ---- load and centre the a tile (mean over h of u_a is hoisted out of the pair loop) ----
+  for (int r = warp; r < TILE; r += WARPS) {
+    const int a = ta * TILE + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a < K) v = *reinterpret_cast<const float4*>(U + (int64_t)a * H + 4 * lane);
+    float m = (v.x + v.y) + (v.z + v.w);
+    m = warp_sum(m) * (1.f / H);
+    *reinterpret_cast<float4*>(va + r * H + 4 * lane) = make_float4(v.x - m, v.y - m, v.z - m, v.w - m);
+    if (GRAD) *reinterpret_cast<float4*>(dua + r * H + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane == 0) da[r] = (a < K) ? Dp[a] : 0.f;
+  }
+  HeadConst hc;
+  float bb[HPL];   // b1 - mean(b1)
+  {
+    float bsum = 0.f;
+    for (int h = lane; h < H; h += 32) bsum += p.b1[h];
+    bsum = warp_sum(bsum) * (1.f / H);
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const int h = hidx(l16, i);
+      hc.gam[i] = p.gamma[h];
+      hc.bet[i] = p.beta[h];
+      hc.w2[i] = p.w2[h];
+      bb[i] = p.b1[h] - bsum;
+    }
+    hc.b2 = p.b2[0];
+  }
+  const float inv_cnt = p.inv_count[set] * (p.w_rank ? p.w_rank[set] : 1.f);
+  __syncthreads();
+
+  float dgam[HPL], dbet[HPL], dw2[HPL], db2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) dgam[i] = dbet[i] = dw2[i] = 0.f;
+  float loss_local = 0.f;
+
+  for (int bi = 0; bi < B_PER_WARP; ++bi) {
+    const int b = tb * TILE + warp * B_PER_WARP + bi;
+    const bool b_ok = b < K;     // warp-uniform
+    float vb[HPL], dub[HPL];
+    float d_b = 0.f;
+    {
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < HPL; ++i) {
+        vb[i] = b_ok ? U[(int64_t)b * H + hidx(l16, i)] : 0.f;
+        m += vb[i];
+        dub[i] = 0.f;
+      }
+      m = half_sum(m) * (1.f / H);
+#pragma unroll
+      for (int i = 0; i < HPL; ++i) vb[i] = vb[i] - m + bb[i];
+      if (b_ok) d_b = Dp[b];
+    }
+    for (int t = 0; t < TILE / 2; ++t) {
+      // staggered a index: at any step the 32 half-warps of the CTA work on 32 different rows
+      const int r = 2 * ((t + 4 * warp) & (TILE / 2 - 1)) + half;
+      const int a = ta * TILE + r;
+      bool valid = b_ok && a < K;
+      float dd = 0.f;
+      if (valid) {
+        dd = d_b - da[r];
+        valid = (p.mode == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr);
+      }
+      if (valid) {
+        float hcv[HPL];
+        const float4 a0 = *reinterpret_cast<const float4*>(va + r * H + 4 * l16);
+        const float4 a1 = *reinterpret_cast<const float4*>(va + r * H + 64 + 4 * l16);
+        hcv[0] = vb[0] - a0.x; hcv[1] = vb[1] - a0.y; hcv[2] = vb[2] - a0.z; hcv[3] = vb[3] - a0.w;
+        hcv[4] = vb[4] - a1.x; hcv[5] = vb[5] - a1.y; hcv[6] = vb[6] - a1.z; hcv[7] = vb[7] - a1.w;
+        PairOut o;
+        head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
+        const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
+        float l, dl;
+        if (p.mode == 0) {
+          const float ex = expf(-sg * o.s);
+          l = logf(1.f + ex);
+          dl = -sg * ex / (1.f + ex);
+        } else {
+          const float m = p.margin - sg * o.s;
+          l = fmaxf(m, 0.f);
+          dl = (m > 0.f) ? -sg : 0.f;
+        }
+        if (l16 == 0) loss_local += l;
+        if (GRAD) {
+          const float dout = dl * (p.use_tanh ? (1.f - o.s * o.s) : 1.f) * inv_cnt;   // d total / d (w2.g + b2)
+          db2 += (l16 == 0) ? dout : 0.f;
+          const float coef = dout * o.rstd;
+          float dh[HPL];
+#pragma unroll
+          for (int i = 0; i < HPL; ++i) {
+            const float pg = hc.w2[i] * o.gp[i];
+            dw2[i] = fmaf(dout, o.g[i], dw2[i]);
+            dbet[i] = fmaf(dout, pg, dbet[i]);
+            dgam[i] = fmaf(dout * pg, o.xh[i], dgam[i]);
+            dh[i] = coef * (pg * hc.gam[i] - o.m1 - o.xh[i] * o.m2);
+            dub[i] += dh[i];
+          }
+          float4* q0 = reinterpret_cast<float4*>(dua + r * H + 4 * l16);
+          float4* q1 = reinterpret_cast<float4*>(dua + r * H + 64 + 4 * l16);
+          float4 c0 = *q0, c1 = *q1;
+          c0.x += dh[0]; c0.y += dh[1]; c0.z += dh[2]; c0.w += dh[3];
+          c1.x += dh[4]; c1.y += dh[5]; c1.z += dh[6]; c1.w += dh[7];
+          *q0 = c0;
+          *q1 = c1;
+        }
+      }
+      if (GRAD) __syncthreads();   // keeps the stagger aligned: rows of `dua` are never shared within a step
+    }
+    if (GRAD) {
+      // combine the two half warps and store this b row's partial (over the a tile) gradient
+#pragma unroll
+      for (int i = 0; i < HPL; ++i) dub[i] += __shfl_xor_sync(0xffffffffu, dub[i], 16);
+      if (b_ok && half == 0) {
+        float* dst = p.dub_part + (((int64_t)set * gridDim.x + ta) * K + b) * H;
+        *reinterpret_cast<float4*>(dst + 4 * l16) = make_float4(dub[0], dub[1], dub[2], dub[3]);
+        *reinterpret_cast<float4*>(dst + 64 + 4 * l16) = make_float4(dub[4], dub[5], dub[6], dub[7]);
+      }
+    }
+  }
+  // ---- CTA-level reductions ----
+  loss_local = warp_sum(loss_local);
+  if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_sum + set, (double)loss_local);
+  if (GRAD) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TILE * H; e += blockDim.x) {
+      const int r = e / H, a = ta * TILE + r;
+      if (a < K) p.dua_part[(((int64_t)set * gridDim.y + tb) * K + a) * H + (e - r * H)] = dua[e];
+    }
+    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) red[e] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const float g2 = dgam[i] + __shfl_xor_sync(0xffffffffu, dgam[i], 16);
+      const float b2v = dbet[i] + __shfl_xor_sync(0xffffffffu, dbet[i], 16);
+      const float w2v = dw2[i] + __shfl_xor_sync(0xffffffffu, dw2[i], 16);
+      if (half == 0) {
+        const int h = hidx(l16, i);
+        atomicAdd(red + h, g2);
+        atomicAdd(red + H + h, b2v);
+        atomicAdd(red + 2 * H + h, w2v);
+      }
+    }
+    db2 = warp_sum(db2);
+    if (lane == 0) atomicAdd(red + 3 * H, db2);
+    __syncthreads();
+    float* gp = p.gparam + p.gparam_off;   // [b1 | gamma | beta | w2 | b2]
+    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x)
+      if (red[e] != 0.f) atomicAdd(gp + H + e, red[e]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// number of valid pairs per set -> inv_count (per set, or shared when joint_mean)
+// ------------------------------------------------------------------------------------------
+__global__ void rank_count(const float* __restrict__ depth, int K, int mode, float thr, int* __restrict__ count) {
+  __shared__ int red[32];
+  const int set = blockIdx.y;
+  const float* d = depth + (int64_t)set * K;
+  int c = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)K * K;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(e / K), b = (int)(e - (int64_t)a * K);
+    const float dd = d[b] - d[a];
+    c += (mode == 0) ? (fabsf(dd) > thr) : (fabsf(tanhf(dd)) > thr);
+  }
+  c = block_sum(c, red);
+  if (threadIdx.x == 0 && c) atomicAdd(count + set, c);
+}
+__global__ void rank_inv_count(const int* __restrict__ count, int S, int joint, float* __restrict__ inv) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  long long n = count[s];
+  if (joint) {
+    n = 0;
+    for (int k = 0; k < S; ++k) n += count[k];
+  }
+  inv[s] = n > 0 ? (float)(1.0 / (double)n) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-view L1: pair p couples keypoint k of set 2p+1 (a) with keypoint k of set 2p (b).
+// One half warp per keypoint.  Adds its u-gradient straight into the dub/dua partial slot 0.
+// ------------------------------------------------------------------------------------------
+template <bool GRAD>
+__global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __restrict__ w_l1, double* __restrict__ l1_sum,
+                                              float* __restrict__ du_extra /* (S, K, H) zero-initialised */) {
+  __shared__ float red[3 * H + 1];
+  const int pair = blockIdx.y;
+  const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  const int k = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half;
+  const int K = p.K;
+  const int sb = 2 * pair, sa = 2 * pair + 1;
+  HeadConst hc;
+  float bb[HPL];
+  {
+    float bsum = 0.f;
+    for (int h = lane; h < H; h += 32) bsum += p.b1[h];
+    bsum = warp_sum(bsum) * (1.f / H);
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const int h = hidx(l16, i);
+      hc.gam[i] = p.gamma[h];
+      hc.bet[i] = p.beta[h];
+      hc.w2[i] = p.w2[h];
+      bb[i] = p.b1[h] - bsum;
+    }
+    hc.b2 = p.b2[0];
+  }
+  float dgam[HPL], dbet[HPL], dw2[HPL], db2 = 0.f, loss_local = 0.f;
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) dgam[i] = dbet[i] = dw2[i] = 0.f;
+  const bool ok = k < K;
+  float hcv[HPL];
+  float m = 0.f;
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) {
+    const int h = hidx(l16, i);
+    hcv[i] = ok ? p.u[((int64_t)sb * K + k) * H + h] - p.u[((int64_t)sa * K + k) * H + h] + p.b1[h] : 0.f;
+    m += hcv[i];
+  }
+  m = half_sum(m) * (1.f / H);
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) hcv[i] -= m;
+  (void)bb;
+  PairOut o;
+  head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
+  if (ok) {
+    const float tgt = tanhf(p.depth[(int64_t)sb * K + k] - p.depth[(int64_t)sa * K + k]);
+    const float diff = o.s - tgt;
+    if (l16 == 0) loss_local = fabsf(diff);
+    if (GRAD) {
+      const float sg = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+      const float dout = sg * (p.use_tanh ? (1.f - o.s * o.s) : 1.f) * w_l1[pair] / (float)K;
+      db2 = (l16 == 0) ? dout : 0.f;
+      const float coef = dout * o.rstd;
+#pragma unroll
+      for (int i = 0; i < HPL; ++i) {
+        const int h = hidx(l16, i);
+        const float pg = hc.w2[i] * o.gp[i];
+        dw2[i] = dout * o.g[i];
+        dbet[i] = dout * pg;
+        dgam[i] = dout * pg * o.xh[i];
+        const float dh = coef * (pg * hc.gam[i] - o.m1 - o.xh[i] * o.m2);
+        du_extra[((int64_t)sb * K + k) * H + h] = dh;
+        du_extra[((int64_t)sa * K + k) * H + h] = -dh;
+      }
+    }
+  }
+  loss_local = warp_sum(loss_local);
+  if (lane == 0 && loss_local != 0.f) atomicAdd(l1_sum + pair, (double)loss_local);
+  if (GRAD) {
+    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) red[e] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < HPL; ++i) {
+      const int h = hidx(l16, i);
+      atomicAdd(red + h, dgam[i]);
+      atomicAdd(red + H + h, dbet[i]);
+      atomicAdd(red + 2 * H + h, dw2[i]);
+    }
+    db2 = warp_sum(db2);
+    if (lane == 0) atomicAdd(red + 3 * H, db2);
+    __syncthreads();
+    float* gp = p.gparam + p.gparam_off;
+    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x)
+      if (red[e] != 0.f) atomicAdd(gp + H + e, red[e]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// du = sum_ta dub_part - sum_tb dua_part (+ L1 part); emits bf16 du, du^T and the b1 gradient
+// grid (ceil(K/32), S), block 256 (8 warps x 32 lanes: lane -> 4 h, warp -> rows)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    rank_reduce_du(const float* __restrict__ dub_part, const float* __restrict__ dua_part,
+                   const float* __restrict__ du_extra, int S, int K, int TA, int TB, int ldr,
+                   __nv_bfloat16* __restrict__ du_bf, __nv_bfloat16* __restrict__ duT_bf, float* __restrict__ gb1) {
+  __shared__ float tile[32][H + 1];
+  __shared__ float colsum[8][H];
+  const int set = blockIdx.y, k0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = w; r < 32; r += 8) {
+    const int k = k0 + r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K) {
+      for (int t = 0; t < TA; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(dub_part + (((int64_t)set * TA + t) * K + k) * H + 4 * lane);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      bsum[0] += acc.x; bsum[1] += acc.y; bsum[2] += acc.z; bsum[3] += acc.w;   // d b1 = sum over pairs of dh
+      for (int t = 0; t < TB; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(dua_part + (((int64_t)set * TB + t) * K + k) * H + 4 * lane);
+        acc.x -= v.x; acc.y -= v.y; acc.z -= v.z; acc.w -= v.w;
+      }
+      if (du_extra) {
+        const float4 v = *reinterpret_cast<const float4*>(du_extra + ((int64_t)set * K + k) * H + 4 * lane);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if ((set & 1) == 0) { bsum[0] += v.x; bsum[1] += v.y; bsum[2] += v.z; bsum[3] += v.w; }   // b side of the L1 pair
+      }
+      uint2 pk = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+      *reinterpret_cast<uint2*>(du_bf + ((int64_t)set * K + k) * H + 4 * lane) = pk;
+    }
+    tile[r][4 * lane] = acc.x; tile[r][4 * lane + 1] = acc.y; tile[r][4 * lane + 2] = acc.z; tile[r][4 * lane + 3] = acc.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) colsum[w][4 * lane + i] = bsum[i];
+  __syncthreads();
+  // du^T[h][set*K + k]: lanes along k
+  for (int h = w; h < H; h += 8)
+    if (k0 + lane < K) duT_bf[(int64_t)h * ldr + (int64_t)set * K + k0 + lane] = __float2bfloat16(tile[lane][h]);
+  if (threadIdx.x < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += colsum[i][threadIdx.x];
+    if (t != 0.f) atomicAdd(gb1 + threadIdx.x, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// operand preparation for the GEMMs
+// ------------------------------------------------------------------------------------------
+// split x (R x D fp32) into [hi | second | third] panels (R x 3 ldd) and optionally x^T hi (D x ldr) bf16
+// lo_panel = 2: [hi | hi | lo] (A side); lo_panel = 1: [hi | lo | hi] (B side)
+__global__ void __launch_bounds__(256)
+    split3_bf16(const float* __restrict__ x, int64_t R, int D, int ldd, int lo_panel, __nv_bfloat16* __restrict__ X3,
+                __nv_bfloat16* __restrict__ XT, int64_t ldr) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < ldd; c0 += 32) {
+    __syncthreads();
+    for (int r = w; r < 32; r += 8) {
+      const int64_t row = r0 + r;
+      const int c = c0 + lane;
+      const float v = (row < R && c < D) ? __ldg(x + row * D + c) : 0.f;
+      tile[r][lane] = v;
+      if (row < R && c < ldd) {
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+        __nv_bfloat16* o = X3 + row * 3 * ldd + c;
+        o[0] = hi;
+        o[(3 - lo_panel) * ldd] = hi;
+        o[lo_panel * ldd] = lo;
+      }
+    }
+    __syncthreads();
+    if (XT)
+      for (int r = w; r < 32; r += 8) {
+        const int c = c0 + r;
+        const int64_t row = r0 + lane;
+        if (c < D && row < R) XT[(int64_t)c * ldr + row] = __float2bfloat16(tile[lane][r]);
+      }
+  }
+}
+
+// epilogue: atomically accumulate alpha * acc into a single fp32 matrix shared by all batches (split-K)
+struct EpiAtomicAddF32 {
+  static constexpr int kScratchBytes = 0;
+  struct Params {
+    float* C;
+    int M, N;
+    int64_t ldc;
+  };
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx) {
+    const int m = cx.m0 + cx.row;
+    for (int c = cx.col_begin; c < cx.col_end; c += 32) {
+      const int n = cx.n0 + c;
+      if (n >= p.N) break;
+      float v[32];
+      tc::tmem_ld32(cx.tmem + c, v);
+      if (m < p.M) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if (n + q < p.N && v[q] != 0.f) atomicAdd(p.C + (int64_t)m * p.ldc + n + q, v[q]);
+      }
+    }
+  }
+};
+
+__global__ void rank_finalize(const double* __restrict__ loss_sum, const float* __restrict__ inv_count,
+                              const double* __restrict__ l1_sum, int S, int K, float* __restrict__ loss_rank,
+                              float* __restrict__ loss_l1) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < S) loss_rank[s] = (float)(loss_sum[s] * (double)inv_count[s]);
+  if (loss_l1 && s < S / 2) loss_l1[s] = (float)(l1_sum[s] / (double)K);
+}
+
+struct RankWorkspace {
+  __nv_bfloat16 *F3, *W3, *FT, *W1T, *du_bf, *duT_bf;
+  float *u, *inv_count, *dub_part, *dua_part, *du_extra;
+  double *loss_sum, *l1_sum;
+  int* count;
+  size_t total;
+  int ldd, TA;
+  int64_t ldr;
+};
+
+RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backward, bool l1) {
+  RankWorkspace w{};
+  Carver c(base);
+  const int64_t R = S * K;
+  w.ldd = (int)round_up<int64_t>(D, 8);
+  w.ldr = round_up<int64_t>(R, 8);
+  w.TA = (int)ceil_div<int64_t>(K, TILE);
+  w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
+  w.W3 = c.take<__nv_bfloat16>((int64_t)H * 3 * w.ldd);
+  w.u = c.take<float>(R * H);
+  w.count = c.take<int>(S);
+  w.inv_count = c.take<float>(S);
+  w.loss_sum = c.take<double>(S);
+  w.l1_sum = c.take<double>(S);
+  if (backward) {
+    w.FT = c.take<__nv_bfloat16>(D * w.ldr);
+    w.W1T = c.take<__nv_bfloat16>(D * (int64_t)H);
+    w.du_bf = c.take<__nv_bfloat16>(R * H);
+    w.duT_bf = c.take<__nv_bfloat16>((int64_t)H * w.ldr);
+    w.dub_part = c.take<float>(S * w.TA * K * H);
+    w.dua_part = c.take<float>(S * w.TA * K * H);
+    if (l1) w.du_extra = c.take<float>(R * H);
+  }
+  w.total = c.total();
+  return w;
+}
+
+// W1 (H x D) -> W1^T (D x H) bf16
+__global__ void transpose_w1(const float* __restrict__ W1, int D, __nv_bfloat16* __restrict__ W1T) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < D * H) {
+    const int d = e / H, h = e - d * H;
+    W1T[e] = __float2bfloat16(W1[(int64_t)h * D + d]);
+  }
+}
+
+}  // namespace
+}  // namespace gd3
+
+using namespace gd3;
+
+extern "C" {
+
+size_t gd3_depth_head_loss_workspace(int64_t S, int64_t K, int64_t D, int with_backward, int with_l1) {
+  if (S <= 0 || K <= 0 || D <= 0) return 0;
+  return carve_rank(nullptr, S, K, D, with_backward != 0, with_l1 != 0).total;
+}
+
+int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int64_t K, int64_t D, int64_t hidden,
+                        const float* W1, const float* b1, const float* gamma, const float* beta, const float* w2,
+                        const float* b2, int use_tanh, float ln_eps, int mode, float thr, float margin,
+                        int joint_mean, const float* w_rank, const float* w_l1, float* loss_rank, float* loss_l1,
+                        float* grad_feats, float* grad_params, void* workspace, size_t workspace_bytes,
+                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (S == 0) return GD3_OK;
+  GD3_REQUIRE(S > 0 && K >= 0 && D > 0, "gd3_depth_head_loss: bad sizes S=%lld K=%lld D=%lld", (long long)S,
+              (long long)K, (long long)D);
+  GD3_REQUIRE(hidden == H, "gd3_depth_head_loss: hidden width %lld not supported (fusion_layer uses %d)",
+              (long long)hidden, H);
+  GD3_REQUIRE(mode == 0 || mode == 1, "gd3_depth_head_loss: mode must be 0 (logistic) or 1 (hinge)");
+  GD3_REQUIRE(loss_rank, "gd3_depth_head_loss: null loss output");
+  GD3_REQUIRE((grad_feats == nullptr) == (grad_params == nullptr),
+              "gd3_depth_head_loss: pass both gradient buffers or neither");
+  const bool l1 = w_l1 != nullptr;
+  GD3_REQUIRE(!l1 || (S % 2 == 0 && loss_l1), "gd3_depth_head_loss: the L1 term needs an even number of sets and loss_l1");
+  GD3_REQUIRE(S <= 65535, "gd3_depth_head_loss: at most 65535 sets per call");
+  const bool backward = grad_feats != nullptr;
+  GD3_CHECK_CUDA(cudaMemsetAsync(loss_rank, 0, sizeof(float) * S, stream));
+  if (l1) GD3_CHECK_CUDA(cudaMemsetAsync(loss_l1, 0, sizeof(float) * (S / 2), stream));
+  const int64_t nparam = (int64_t)H * D + 4 * H + 1;
+  if (backward) {
+    GD3_CHECK_CUDA(cudaMemsetAsync(grad_params, 0, sizeof(float) * nparam, stream));
+    GD3_CHECK_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * S * K * D, stream));
+  }
+  if (K == 0) return GD3_OK;
+  GD3_REQUIRE(feats && depths && W1 && b1 && gamma && beta && w2 && b2, "gd3_depth_head_loss: null input");
+  RankWorkspace w = carve_rank(workspace, S, K, D, backward, l1);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("gd3_depth_head_loss: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return GD3_ERR_WORKSPACE;
+  }
+  const int64_t R = S * K;
+  int rc;
+  // ---- u = f W1^T on the tensor cores (split bf16, 3 K-concatenated panels) ----
+  split3_bf16<<<(unsigned)ceil_div<int64_t>(R, 32), 256, 0, stream>>>(feats, R, (int)D, w.ldd, 2, w.F3,
+                                                                     backward ? w.FT : nullptr, w.ldr);
+  GD3_CHECK_LAUNCH();
+  split3_bf16<<<(unsigned)ceil_div<int64_t>(H, 32), 256, 0, stream>>>(W1, H, (int)D, w.ldd, 1, w.W3, nullptr, 0);
+  GD3_CHECK_LAUNCH();
+  {
+    CUtensorMap ta, tb;
+    if ((rc = tc::make_tmap_bf16(&ta, w.F3, 3 * (int64_t)w.ldd, R, 1, 3 * (int64_t)w.ldd, 0, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tb, w.W3, 3 * (int64_t)w.ldd, H, 1, 3 * (int64_t)w.ldd, 0, 128))) return rc;
+    tc::EpiStoreF32::Params ep{w.u, (int)R, H, H, 0, 1.0f, nullptr};
+    tc::GemmShape s{(int)R, H, 3 * w.ldd, 1};
+    if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>(ta, tb, s, ep, stream))) return rc;
+  }
+  // ---- valid-pair counts ----
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * S, stream));
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double) * 2 * S + 256, stream));   // loss_sum and l1_sum
+  {
+    dim3 grid((unsigned)min<int64_t>(64, ceil_div<int64_t>(K * K, 256)), (unsigned)S);
+    rank_count<<<grid, 256, 0, stream>>>(depths, (int)K, mode, thr, w.count);
+    GD3_CHECK_LAUNCH();
+    rank_inv_count<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.count, (int)S, joint_mean, w.inv_count);
+    GD3_CHECK_LAUNCH();
+  }
+  RankParams rp{};
+  rp.u = w.u;
+  rp.depth = depths;
+  rp.b1 = b1;
+  rp.gamma = gamma;
+  rp.beta = beta;
+  rp.w2 = w2;
+  rp.b2 = b2;
+  rp.inv_count = w.inv_count;
+  rp.w_rank = w_rank;
+  rp.K = (int)K;
+  rp.S = (int)S;
+  rp.mode = mode;
+  rp.use_tanh = use_tanh;
+  rp.thr = thr;
+  rp.margin = margin;
+  rp.ln_eps = ln_eps;
+  rp.loss_sum = w.loss_sum;
+  rp.dub_part = w.dub_part;
+  rp.dua_part = w.dua_part;
+  rp.gparam = grad_params;
+  rp.gparam_off = (int64_t)H * D;
+  {
+    const size_t smem = sizeof(float) * (2 * TILE * H + TILE + 3 * H + 1 + 3);
+    dim3 grid((unsigned)w.TA, (unsigned)w.TA, (unsigned)S);
+    if (backward) {
+      static bool cfg = false;
+      if (!cfg) {
+        GD3_CHECK_CUDA(cudaFuncSetAttribute(rank_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = true;
+      }
+      rank_pairs<true><<<grid, WARPS * 32, smem, stream>>>(rp);
+    } else {
+      static bool cfg = false;
+      if (!cfg) {
+        GD3_CHECK_CUDA(cudaFuncSetAttribute(rank_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = true;
+      }
+      rank_pairs<false><<<grid, WARPS * 32, smem, stream>>>(rp);
+    }
+    GD3_CHECK_LAUNCH();
+  }
+  if (l1) {
+    if (backward) GD3_CHECK_CUDA(cudaMemsetAsync(w.du_extra, 0, sizeof(float) * R * H, stream));
+    dim3 grid((unsigned)ceil_div<int64_t>(K, 16), (unsigned)(S / 2));
+    if (backward)
+      rank_l1<true><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, w.du_extra);
+    else
+      rank_l1<false><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, nullptr);
+    GD3_CHECK_LAUNCH();
+  }
+  rank_finalize<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.loss_sum, w.inv_count, w.l1_sum, (int)S,
+                                                                        (int)K, loss_rank, l1 ? loss_l1 : nullptr);
+  GD3_CHECK_LAUNCH();
+  if (!backward) return GD3_OK;
+  // ---- gradients: du, then d feats = du W1 and d W1 = du^T f on the tensor cores ----
+  {
+    dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)S);
+    rank_reduce_du<<<grid, 256, 0, stream>>>(w.dub_part, w.dua_part, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.TA,
+                                             w.TA, (int)w.ldr, w.du_bf, w.duT_bf, grad_params + (int64_t)H * D);
+    GD3_CHECK_LAUNCH();
+    transpose_w1<<<(unsigned)ceil_div<int64_t>(D * H, 256), 256, 0, stream>>>(W1, (int)D, w.W1T);
+    GD3_CHECK_LAUNCH();
+  }
+  {
+    CUtensorMap t_du, t_w1t, t_dut, t_ft;
+    if ((rc = tc::make_tmap_bf16(&t_du, w.du_bf, H, R, 1, H, 0, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_w1t, w.W1T, H, D, 1, H, 0, 256))) return rc;
+    tc::EpiStoreF32::Params e1{grad_feats, (int)R, (int)D, D, 0, 1.0f, nullptr};
+    tc::GemmShape s1{(int)R, (int)D, H, 1};
+    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_du, t_w1t, s1, e1, stream))) return rc;
+    // d W1 (H x D) = sum over sets of du_s^T f_s: one batch entry per set, accumulated atomically (split-K)
+    const int64_t Kp = K;   // batch stride in elements along the row dimension
+    GD3_REQUIRE(Kp % 8 == 0 || S == 1, "gd3_depth_head_loss: K must be a multiple of 8 for the batched d W1 GEMM");
+    if ((rc = tc::make_tmap_bf16(&t_dut, w.duT_bf, K, H, S, w.ldr, Kp, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_ft, w.FT, K, D, S, w.ldr, Kp, 256))) return rc;
+    EpiAtomicAddF32::Params e2{grad_params, H, (int)D, D};
+    tc::GemmShape s2{H, (int)D, (int)K, (int)S};
+    if ((rc = tc::launch_gemm<256, 4, EpiAtomicAddF32>(t_dut, t_ft, s2, e2, stream))) return rc;
+  }
+  return GD3_OK;
+}
+
+}  // extern "C"

@@ -26,7 +26,7 @@ def _as_mask(m, P, N, device):
 # --------------------------------------------------------------------------------------------
 class _CostVolumeKL(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group):
+    def forward(ctx, f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group, grad_mode):
         require_cuda(f1, f2, teacher12, teacher21)
         lib = load()
         if f1.dim() != 3 or f1.shape != f2.shape:
@@ -43,7 +43,7 @@ class _CostVolumeKL(torch.autograd.Function):
         t21 = teacher21.to(_F32).contiguous()
         m1 = _as_mask(mask1, P, N, dev)
         m2 = _as_mask(mask2, P, N, dev)
-        need_grad = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        need_grad = grad_mode and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         loss = torch.empty(P, dtype=_F32, device=dev)
         g1 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
         g2 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
@@ -65,9 +65,9 @@ class _CostVolumeKL(torch.autograd.Function):
     def backward(ctx, grad_loss):
         g1, g2 = ctx.saved_tensors
         if g1 is None:
-            return (None,) * 9
+            return (None,) * 10
         s = grad_loss.to(g1.dtype)[:, None, None]
-        return g1 * s, g2 * s, None, None, None, None, None, None, None
+        return g1 * s, g2 * s, None, None, None, None, None, None, None, None
 
 
 def cost_volume_kl(f1, f2, teacher12, teacher21, mask1=None, mask2=None, variant='mast3r', eps=1e-8,
@@ -79,7 +79,9 @@ def cost_volume_kl(f1, f2, teacher12, teacher21, mask1=None, mask2=None, variant
     Equals ``calculate_cost_loss`` of the reference (variant 'mast3r':
     src/finetune_timm_mast3r.py:504-540, 'vggt': src/finetune_timm_vggt.py:488-533) for each pair.
     """
-    return _CostVolumeKL.apply(f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group)
+    # Function.forward always runs with grad mode off, so the caller's mode is passed in explicitly
+    return _CostVolumeKL.apply(f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group,
+                               torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------------------------
@@ -87,7 +89,7 @@ def cost_volume_kl(f1, f2, teacher12, teacher21, mask1=None, mask2=None, variant
 # --------------------------------------------------------------------------------------------
 class _SmoothAP(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, d1, d2, p1, p2, variant, temp, thr_neg, thr_pos):
+    def forward(ctx, d1, d2, p1, p2, variant, temp, thr_neg, thr_pos, grad_mode):
         require_cuda(d1, d2, p1, p2)
         lib = load()
         if d1.dim() != 3 or d1.shape != d2.shape:
@@ -102,7 +104,7 @@ class _SmoothAP(torch.autograd.Function):
         b = d2.to(_F32).contiguous()
         q1 = p1.to(_F32).contiguous()
         q2 = p2.to(_F32).contiguous()
-        need_grad = torch.is_grad_enabled() and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        need_grad = grad_mode and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         loss = torch.zeros(P, dtype=_F32, device=dev)
         g1 = torch.zeros(P, K, C, dtype=_F32, device=dev) if need_grad else None
         g2 = torch.zeros(P, K, C, dtype=_F32, device=dev) if need_grad else None
@@ -120,9 +122,9 @@ class _SmoothAP(torch.autograd.Function):
     def backward(ctx, grad_loss):
         g1, g2 = ctx.saved_tensors
         if g1 is None:
-            return (None,) * 8
+            return (None,) * 9
         s = grad_loss.to(_F32)[:, None, None]
-        return (g1 * s).to(ctx.in_dtypes[0]), (g2 * s).to(ctx.in_dtypes[1]), None, None, None, None, None, None
+        return (g1 * s).to(ctx.in_dtypes[0]), (g2 * s).to(ctx.in_dtypes[1]), None, None, None, None, None, None, None
 
 
 def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1, thr_pos=5e-3):
@@ -133,7 +135,7 @@ def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1
     src/finetune_timm_vggt.py:543-574) or of src/finetune_timm_me.py:196-217 ('me') for each pair.
     K = 0 gives loss 0 (the callers' early-out, src/finetune_timm_mast3r.py:604-607).
     """
-    return _SmoothAP.apply(d1, d2, pts3d_1, pts3d_2, variant, temp, thr_neg, thr_pos)
+    return _SmoothAP.apply(d1, d2, pts3d_1, pts3d_2, variant, temp, thr_neg, thr_pos, torch.is_grad_enabled())
 
 
 # --------------------------------------------------------------------------------------------
