@@ -33,9 +33,10 @@ constexpr int TILE = 128;        // a / b tile edge
 constexpr int WARPS = 16;
 constexpr int B_PER_WARP = TILE / WARPS;   // 8
 
-__device__ __forceinline__ float half_sum(float v) {   // sum over the 16 lanes of a half warp
+// sum over the 16 lanes of a half warp; `mask` names exactly that half so the two halves may diverge
+__device__ __forceinline__ float half_sum(float v, unsigned mask) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
 // hidden index of this lane's i-th element: two float4 groups, 64 apart -> conflict-free LDS.128
@@ -59,11 +60,11 @@ struct PairOut {
 // (|err| < 1.5e-7), sharing exp(-y^2/2) between erf and the Gaussian density needed by GELU'.
 template <bool GRAD>
 __device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadConst& hcst, float ln_eps, int use_tanh,
-                                          PairOut& o) {
+                                          unsigned mask, PairOut& o) {
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < HPL; ++i) ss = fmaf(hc[i], hc[i], ss);
-  ss = half_sum(ss);
+  ss = half_sum(ss, mask);
   o.rstd = rsqrtf(ss * (1.f / H) + ln_eps);
   float acc = 0.f, m1 = 0.f, m2 = 0.f;
 #pragma unroll
@@ -93,11 +94,11 @@ __device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadCons
       m2 = fmaf(q, xh, m2);
     }
   }
-  acc = half_sum(acc) + hcst.b2;
+  acc = half_sum(acc, mask) + hcst.b2;
   o.s = use_tanh ? tanhf(acc) : acc;
   if (GRAD) {
-    o.m1 = half_sum(m1) * (1.f / H);
-    o.m2 = half_sum(m2) * (1.f / H);
+    o.m1 = half_sum(m1, mask) * (1.f / H);
+    o.m2 = half_sum(m2, mask) * (1.f / H);
   }
 }
 
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
   float* red = da + TILE;                 // cross-warp reduction of parameter gradients
   const int set = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
   const int K = p.K;
   const float* U = p.u + (int64_t)set * K * H;
   const float* Dp = p.depth + (int64_t)set * K;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
         m += vb[i];
         dub[i] = 0.f;
       }
-      m = half_sum(m) * (1.f / H);
+      m = half_sum(m, hmask) * (1.f / H);
 #pragma unroll
       for (int i = 0; i < HPL; ++i) vb[i] = vb[i] - m + bb[i];
       if (b_ok) d_b = Dp[b];
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
         hcv[0] = vb[0] - a0.x; hcv[1] = vb[1] - a0.y; hcv[2] = vb[2] - a0.z; hcv[3] = vb[3] - a0.w;
         hcv[4] = vb[4] - a1.x; hcv[5] = vb[5] - a1.y; hcv[6] = vb[6] - a1.z; hcv[7] = vb[7] - a1.w;
         PairOut o;
-        head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
+        head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, hmask, o);
         const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
         float l, dl;
         if (p.mode == 0) {
@@ -242,7 +244,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
           *q1 = c1;
         }
       }
-      if (GRAD) __syncthreads();   // keeps the stagger aligned: rows of `dua` are never shared within a step
+      // Two half warps collide on a row of `dua` only when their step counters differ by a multiple of 4,
+      // so a CTA barrier every third step is enough to keep the stagger race-free.
+      if (GRAD && ((bi * (TILE / 2) + t) % 3 == 2)) __syncthreads();
     }
     if (GRAD) {
       // combine the two half warps and store this b row's partial (over the a tile) gradient
@@ -326,6 +330,7 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
   const int k = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half;
+  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
   const int K = p.K;
   const int sb = 2 * pair, sa = 2 * pair + 1;
   HeadConst hc;
@@ -356,12 +361,12 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
     hcv[i] = ok ? p.u[((int64_t)sb * K + k) * H + h] - p.u[((int64_t)sa * K + k) * H + h] + p.b1[h] : 0.f;
     m += hcv[i];
   }
-  m = half_sum(m) * (1.f / H);
+  m = half_sum(m, hmask) * (1.f / H);
 #pragma unroll
   for (int i = 0; i < HPL; ++i) hcv[i] -= m;
   (void)bb;
   PairOut o;
-  head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
+  head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, hmask, o);
   if (ok) {
     const float tgt = tanhf(p.depth[(int64_t)sb * K + k] - p.depth[(int64_t)sa * K + k]);
     const float diff = o.s - tgt;
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     rank_reduce_du(const float* __restrict__ dub_part, const float* __restrict__ dua_part,
-                   const float* __restrict__ du_extra, int S, int K, int TA, int TB, int ldr,
+                   const float* __restrict__ du_extra, int S, int K, int TA, int TB, int64_t ldr, int ldk,
                    __nv_bfloat16* __restrict__ du_bf, __nv_bfloat16* __restrict__ duT_bf, float* __restrict__ gb1) {
   __shared__ float tile[32][H + 1];
   __shared__ float colsum[8][H];
@@ -446,7 +451,7 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   // du^T[h][set*K + k]: lanes along k
   for (int h = w; h < H; h += 8)
-    if (k0 + lane < K) duT_bf[(int64_t)h * ldr + (int64_t)set * K + k0 + lane] = __float2bfloat16(tile[lane][h]);
+    if (k0 + lane < K) duT_bf[(int64_t)h * ldr + (int64_t)set * ldk + k0 + lane] = __float2bfloat16(tile[lane][h]);
   if (threadIdx.x < H) {
     float t = 0.f;
 #pragma unroll
@@ -460,9 +465,10 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 // split x (R x D fp32) into [hi | second | third] panels (R x 3 ldd) and optionally x^T hi (D x ldr) bf16
 // lo_panel = 2: [hi | hi | lo] (A side); lo_panel = 1: [hi | lo | hi] (B side)
+// x^T columns are laid out per set with a padded stride: column = (row / K) * ldk + row % K
 __global__ void __launch_bounds__(256)
     split3_bf16(const float* __restrict__ x, int64_t R, int D, int ldd, int lo_panel, __nv_bfloat16* __restrict__ X3,
-                __nv_bfloat16* __restrict__ XT, int64_t ldr) {
+                __nv_bfloat16* __restrict__ XT, int64_t ldr, int K, int ldk) {
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(256)
       for (int r = w; r < 32; r += 8) {
         const int c = c0 + r;
         const int64_t row = r0 + lane;
-        if (c < D && row < R) XT[(int64_t)c * ldr + row] = __float2bfloat16(tile[lane][r]);
+        if (c < D && row < R) XT[(int64_t)c * ldr + (row / K) * ldk + row % K] = __float2bfloat16(tile[lane][r]);
       }
   }
 }
@@ -530,7 +536,7 @@ struct RankWorkspace {
   double *loss_sum, *l1_sum;
   int* count;
   size_t total;
-  int ldd, TA;
+  int ldd, TA, ldk;
   int64_t ldr;
 };
 
@@ -539,7 +545,8 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   Carver c(base);
   const int64_t R = S * K;
   w.ldd = (int)round_up<int64_t>(D, 8);
-  w.ldr = round_up<int64_t>(R, 8);
+  w.ldk = (int)round_up<int64_t>(K, 8);
+  w.ldr = S * (int64_t)w.ldk;
   w.TA = (int)ceil_div<int64_t>(K, TILE);
   w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
   w.W3 = c.take<__nv_bfloat16>((int64_t)H * 3 * w.ldd);
@@ -620,9 +627,9 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   int rc;
   // ---- u = f W1^T on the tensor cores (split bf16, 3 K-concatenated panels) ----
   split3_bf16<<<(unsigned)ceil_div<int64_t>(R, 32), 256, 0, stream>>>(feats, R, (int)D, w.ldd, 2, w.F3,
-                                                                     backward ? w.FT : nullptr, w.ldr);
+                                                                     backward ? w.FT : nullptr, w.ldr, (int)K, w.ldk);
   GD3_CHECK_LAUNCH();
-  split3_bf16<<<(unsigned)ceil_div<int64_t>(H, 32), 256, 0, stream>>>(W1, H, (int)D, w.ldd, 1, w.W3, nullptr, 0);
+  split3_bf16<<<(unsigned)ceil_div<int64_t>(H, 32), 256, 0, stream>>>(W1, H, (int)D, w.ldd, 1, w.W3, nullptr, 0, 1, 1);
   GD3_CHECK_LAUNCH();
   {
     CUtensorMap ta, tb;
@@ -634,9 +641,11 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   }
   // ---- valid-pair counts ----
   GD3_CHECK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * S, stream));
-  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double) * 2 * S + 256, stream));   // loss_sum and l1_sum
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double) * S, stream));
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.l1_sum, 0, sizeof(double) * S, stream));
   {
-    dim3 grid((unsigned)min<int64_t>(64, ceil_div<int64_t>(K * K, 256)), (unsigned)S);
+    const int64_t cnt_blocks = ceil_div<int64_t>(K * K, 256);
+    dim3 grid((unsigned)(cnt_blocks < 64 ? cnt_blocks : 64), (unsigned)S);
     rank_count<<<grid, 256, 0, stream>>>(depths, (int)K, mode, thr, w.count);
     GD3_CHECK_LAUNCH();
     rank_inv_count<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.count, (int)S, joint_mean, w.inv_count);
@@ -701,7 +710,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   {
     dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)S);
     rank_reduce_du<<<grid, 256, 0, stream>>>(w.dub_part, w.dua_part, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.TA,
-                                             w.TA, (int)w.ldr, w.du_bf, w.duT_bf, grad_params + (int64_t)H * D);
+                                             w.TA, w.ldr, w.ldk, w.du_bf, w.duT_bf, grad_params + (int64_t)H * D);
     GD3_CHECK_LAUNCH();
     transpose_w1<<<(unsigned)ceil_div<int64_t>(D * H, 256), 256, 0, stream>>>(W1, (int)D, w.W1T);
     GD3_CHECK_LAUNCH();
@@ -714,10 +723,8 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     tc::GemmShape s1{(int)R, (int)D, H, 1};
     if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_du, t_w1t, s1, e1, stream))) return rc;
     // d W1 (H x D) = sum over sets of du_s^T f_s: one batch entry per set, accumulated atomically (split-K)
-    const int64_t Kp = K;   // batch stride in elements along the row dimension
-    GD3_REQUIRE(Kp % 8 == 0 || S == 1, "gd3_depth_head_loss: K must be a multiple of 8 for the batched d W1 GEMM");
-    if ((rc = tc::make_tmap_bf16(&t_dut, w.duT_bf, K, H, S, w.ldr, Kp, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_ft, w.FT, K, D, S, w.ldr, Kp, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_dut, w.duT_bf, K, H, S, w.ldr, w.ldk, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_ft, w.FT, K, D, S, w.ldr, w.ldk, 256))) return rc;
     EpiAtomicAddF32::Params e2{grad_params, H, (int)D, D};
     tc::GemmShape s2{H, (int)D, (int)K, (int)S};
     if ((rc = tc::launch_gemm<256, 4, EpiAtomicAddF32>(t_dut, t_ft, s2, e2, stream))) return rc;

@@ -139,6 +139,103 @@ def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1
 
 
 # --------------------------------------------------------------------------------------------
+# relative-depth losses on the depth-difference head
+# --------------------------------------------------------------------------------------------
+HIDDEN = 128
+
+
+def head_tensors(head):
+    """(W1, b1, gamma, beta, w2, b2, use_tanh, ln_eps) of a DepthAwareFeatureFusion-shaped module
+    (``fusion_layer = Sequential(Linear, LayerNorm, GELU, Linear)``, utils/model.py:100-105)."""
+    fl = head.fusion_layer
+    lin1, ln, lin2 = fl[0], fl[1], fl[3]
+    if lin1.out_features != HIDDEN or lin2.out_features != 1:
+        raise ValueError(f'depth head must be Linear(D, {HIDDEN}) -> LayerNorm -> GELU -> Linear({HIDDEN}, 1)')
+    act = fl[2]
+    if getattr(act, 'approximate', 'none') != 'none':
+        raise ValueError('depth head must use the exact (erf) GELU')
+    return (lin1.weight, lin1.bias, ln.weight, ln.bias, lin2.weight, lin2.bias,
+            bool(getattr(head, 'use_tanh', True)), float(ln.eps))
+
+
+class _DepthHeadLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, depths, W1, b1, gamma, beta, w2, b2, use_tanh, ln_eps, mode, thr, margin, joint_mean,
+                w_rank, w_l1, grad_mode):
+        require_cuda(feats, depths, W1)
+        lib = load()
+        if feats.dim() != 3 or depths.shape != feats.shape[:2]:
+            raise ValueError(f'depth_head_loss: feats (S, K, D) / depths (S, K) expected, got {tuple(feats.shape)} '
+                             f'{tuple(depths.shape)}')
+        S, K, D = feats.shape
+        if W1.shape != (HIDDEN, D):
+            raise ValueError(f'depth_head_loss: W1 must be ({HIDDEN}, {D}), got {tuple(W1.shape)}')
+        dev = feats.device
+        f = feats.to(_F32).contiguous()
+        d = depths.to(_F32).contiguous()
+        params = [t.detach().to(_F32).contiguous() for t in (W1, b1, gamma, beta, w2.reshape(-1), b2.reshape(-1))]
+        wr = None if w_rank is None else w_rank.to(dev, _F32).contiguous()
+        wl = None if w_l1 is None else w_l1.to(dev, _F32).contiguous()
+        if wl is not None and (S % 2 != 0 or wl.numel() != S // 2):
+            raise ValueError('depth_head_loss: the L1 term couples sets (2p, 2p+1); need an even S and S/2 weights')
+        need_grad = grad_mode and any(ctx.needs_input_grad[:8])
+        loss_rank = torch.zeros(S, dtype=_F32, device=dev)
+        loss_l1 = torch.zeros(S // 2, dtype=_F32, device=dev) if wl is not None else None
+        nparam = HIDDEN * D + 4 * HIDDEN + 1
+        gf = torch.zeros(S, K, D, dtype=_F32, device=dev) if need_grad else None
+        gp = torch.zeros(nparam, dtype=_F32, device=dev) if need_grad else None
+        if S and K:
+            ws = workspace(lib.gd3_depth_head_loss_workspace(S, K, D, int(need_grad), int(wl is not None)), dev)
+            with torch.cuda.device(dev):
+                check(lib.gd3_depth_head_loss(ptr(f), ptr(d), S, K, D, HIDDEN, *[ptr(t) for t in params],
+                                              int(use_tanh), float(ln_eps), int(mode), float(thr), float(margin),
+                                              int(joint_mean), ptr(wr), ptr(wl), ptr(loss_rank), ptr(loss_l1),
+                                              ptr(gf), ptr(gp), ptr(ws), ws.numel(), stream_ptr()))
+        total = (loss_rank * wr).sum() if wr is not None else loss_rank.sum()
+        if wl is not None:
+            total = total + (loss_l1 * wl).sum()
+        ctx.save_for_backward(gf, gp)
+        ctx.meta = (D, feats.dtype, tuple(t.shape for t in (W1, b1, gamma, beta, w2, b2)),
+                    tuple(t.dtype for t in (W1, b1, gamma, beta, w2, b2)))
+        if loss_l1 is None:
+            loss_l1 = torch.zeros(0, dtype=_F32, device=dev)
+        ctx.mark_non_differentiable(loss_rank, loss_l1)
+        return total, loss_rank, loss_l1
+
+    @staticmethod
+    def backward(ctx, g_total, _g_rank, _g_l1):
+        gf, gp = ctx.saved_tensors
+        nin = 17
+        if gf is None:
+            return (None,) * nin
+        D, fdtype, shapes, dtypes = ctx.meta
+        g = g_total.to(_F32)
+        sizes = [HIDDEN * D, HIDDEN, HIDDEN, HIDDEN, HIDDEN, 1]
+        parts = torch.split(gp * g, sizes)
+        grads = [(gf * g).to(fdtype), None] + [p.reshape(s).to(dt) for p, s, dt in zip(parts, shapes, dtypes)]
+        return tuple(grads) + (None,) * (nin - len(grads))
+
+
+def depth_head_loss(head, feats, depths, mode='logistic', depth_threshold=0.05, margin=0.05, joint_mean=False,
+                    w_rank=None, w_l1=None):
+    """Relative-depth losses of ``S`` keypoint sets through the depth-difference head.
+
+    feats (S, K, D), depths (S, K).  Returns ``(total, loss_rank (S,), loss_l1 (S//2,))`` where
+    ``total = sum_s w_rank[s] * loss_rank[s] + sum_p w_l1[p] * loss_l1[p]`` is the differentiable
+    scalar (w.r.t. feats and the six ``fusion_layer`` parameters) and the per-set values are reported
+    without gradient.  mode 'logistic' = ``pairwise_logistic_ranking_loss`` (utils/losses.py:18-41),
+    'hinge' = ``intra_depth_loss`` (:44-69); the L1 term (w_l1 given) couples set 2p with set 2p+1 as in
+    ``calculate_depth_loss`` (src/finetune_timm_mast3r.py:489-494).
+    """
+    if mode not in ('logistic', 'hinge'):
+        raise ValueError(f'depth_head_loss: unknown mode {mode!r}')
+    W1, b1, gamma, beta, w2, b2, use_tanh, ln_eps = head_tensors(head)
+    return _DepthHeadLoss.apply(feats, depths, W1, b1, gamma, beta, w2, b2, use_tanh, ln_eps,
+                                0 if mode == 'logistic' else 1, depth_threshold, margin, joint_mean, w_rank, w_l1,
+                                torch.is_grad_enabled())
+
+
+# --------------------------------------------------------------------------------------------
 # bilinear token sampling
 # --------------------------------------------------------------------------------------------
 def _sample_fwd(tokens, strides, L, P, C, ph, pw, h, w, kp, patch, stride, normalize, out, out_strides):

@@ -104,6 +104,31 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
                   float* grad_d2, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Relative-depth losses on the depth-difference head, forward + backward, batched over S keypoint
+ * sets (one set = the keypoints of one image).  Replaces pairwise_logistic_ranking_loss
+ * (utils/losses.py:18-41, mode 0), intra_depth_loss (utils/losses.py:44-69, mode 1), the head
+ * DepthAwareFeatureFusion.fusion_layer (+ tanh) (utils/model.py:100-105,122-127) applied to all K^2
+ * feature differences, and the cross-view L1 term of calculate_depth_loss
+ * (src/finetune_timm_mast3r.py:489-494).
+ *   feats   (S, K, D) fp32 contiguous keypoint features;  depths (S, K) fp32
+ *   head    W1 (hidden, D), b1, gamma, beta, w2 (hidden), b2 (1), hidden = 128; use_tanh; ln_eps
+ *   thr     depth threshold (0.05 in the callers);  margin: hinge base margin (mode 1)
+ *   joint_mean != 0: one mean over the valid pairs of all sets (the reference's B > 1 semantics)
+ *   w_rank  (S) weights with which each set's loss enters the differentiated total (NULL = 1)
+ *   w_l1    (S/2) weights of the L1 term coupling set 2p (view 1) with set 2p+1 (view 2); NULL = no L1
+ *   loss_rank (S), loss_l1 (S/2): unweighted per-set / per-pair losses
+ *   grad_feats (S, K, D) and grad_params, packed [W1 (hidden*D) | b1 | gamma | beta | w2 | b2]:
+ *           gradient of  sum_s w_rank[s] loss_rank[s] + sum_p w_l1[p] loss_l1[p]   (both NULL = forward only)
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_depth_head_loss_workspace(int64_t S, int64_t K, int64_t D, int with_backward, int with_l1);
+int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int64_t K, int64_t D, int64_t hidden,
+                        const float* W1, const float* b1, const float* gamma, const float* beta, const float* w2,
+                        const float* b2, int use_tanh, float ln_eps, int mode, float thr, float margin,
+                        int joint_mean, const float* w_rank, const float* w_l1, float* loss_rank, float* loss_l1,
+                        float* grad_feats, float* grad_params, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Bilinear sampling of patch-token maps at pixel keypoints.  Replaces interpolate_features
  * (utils/functions.py:55-76) and the glue of get_intermediate_feature / get_feature
  * (src/finetune_timm_mast3r.py:271-277, 307-313): optional mean over L layers (sampling is linear)
