@@ -288,7 +288,7 @@ __global__ void kl_finalize_stats(int G, int N, const float* __restrict__ invR, 
 //    grid (ceil(N/64) j-tiles, ceil(N/64) i-tiles, G), block 256
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    kl_dz(int G, int N, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT, int ldw,
+    kl_dz(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT, int ldw,
           const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT, int ldd,
           float* __restrict__ rowdot, float* __restrict__ coldot) {
   __shared__ float ws[64][65];     // W^T tile, [j][i]
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256)
     }
   }
   __syncthreads();
-  const float s = 0.5f / (float)N;
+  const float s = grad_scale * 0.5f / (float)N;
   const float* rr = rc + (int64_t)g * N;
   const float* cc = rc + ((int64_t)G + g) * N;
   const int jl = 2 * lane, j = j0 + jl;
@@ -492,8 +492,8 @@ size_t gd3_cost_kl_workspace(int64_t P, int64_t N, int64_t C, int64_t pairs_per_
 int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N, int64_t C, int64_t s1P, int64_t s1N,
                 int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const float* t12, const float* t21,
                 int64_t t_pair_stride, int64_t t_row_stride, const uint8_t* m1, const uint8_t* m2, int variant,
-                float eps, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group, void* workspace,
-                size_t workspace_bytes, void* stream_) {
+                float eps, float grad_scale, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group,
+                void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (P == 0) return GD3_OK;
   GD3_REQUIRE(P > 0 && N > 0 && C > 0, "gd3_cost_kl: bad sizes P=%lld N=%lld C=%lld", (long long)P, (long long)N,
@@ -572,7 +572,7 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     }
     if (backward) {
       dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
-      kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
+      kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
                                       w.coldot);
       GD3_CHECK_LAUNCH();
       tc::GemmShape s{(int)N, (int)C, (int)N, g};

@@ -227,8 +227,8 @@ size_t gd3_smooth_ap_workspace(int64_t P, int64_t K, int64_t C, int with_backwar
 }
 
 int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const float* pts3d_2, int64_t P, int64_t K,
-                  int64_t C, int variant, float temp, float thr_neg, float thr_pos, float* loss, float* grad_d1,
-                  float* grad_d2, void* workspace, size_t workspace_bytes, void* stream_) {
+                  int64_t C, int variant, float temp, float thr_neg, float thr_pos, float grad_scale, float* loss,
+                  float* grad_d1, float* grad_d2, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (P == 0) return GD3_OK;
   GD3_REQUIRE(P > 0 && K >= 0 && C > 0, "gd3_smooth_ap: bad sizes P=%lld K=%lld C=%lld", (long long)P, (long long)K,
@@ -290,8 +290,8 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     if ((rc = tc::make_tmap_bf16(&t_d1t, w.d1T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
     if ((rc = tc::make_tmap_bf16(&t_d2t, w.d2T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
     tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
-    tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, 1.0f, w.scale};
-    tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, 1.0f, w.scale};
+    tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, w.scale};
+    tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, w.scale};
     if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_ds, t_d2t, s, e1, stream))) return rc;
     if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_dst, t_d1t, s, e2, stream))) return rc;
   }

@@ -1,15 +1,21 @@
-"""Fused, batched entry points of the hot path as ``torch.autograd.Function``s.
+"""Fused, batched entry points of the hot path.
 
-Each ``forward`` enqueues the fused forward+backward CUDA pipeline once and stashes the
-gradients; ``backward`` only scales them by ``grad_output``.  All
-arithmetic happens inside lib3dgd.so; torch supplies device memory and the stream.
+Two layers:
+  *_raw functions      thin, autograd-free calls into the C ABI (lib3dgd.so): loss values plus eagerly
+                       computed gradients, optionally pre-scaled (``grad_scale`` / weights).  Used by
+                       ``gd3.pipeline`` to run a whole distillation step without autograd overhead.
+  torch.autograd.Function wrappers (``cost_volume_kl``, ``smooth_ap``, ``depth_head_loss``,
+                       ``sample_tokens``): ``forward`` runs the fused forward+backward pipeline once and
+                       stashes the gradients; ``backward`` scales them by ``grad_output``
+                       (SURVEY.md section 8-b).
+All arithmetic happens inside lib3dgd.so; torch supplies device memory and the current stream.
 """
 import torch
 
-from . import _lib
 from ._lib import VARIANT, check, dtype_code, load, ptr, require_cuda, stream_ptr, workspace
 
 _F32 = torch.float32
+HIDDEN = 128
 
 
 def _as_mask(m, P, N, device):
@@ -24,40 +30,46 @@ def _as_mask(m, P, N, device):
 # --------------------------------------------------------------------------------------------
 # dense cost-volume KL
 # --------------------------------------------------------------------------------------------
+def cost_kl_raw(f1, f2, teacher12, teacher21, mask1, mask2, variant='mast3r', eps=1e-8, grad_scale=1.0,
+                want_grad=True, pairs_per_group=0):
+    """-> (loss (P,), grad_f1, grad_f2) with gradients of ``grad_scale * loss[p]`` (None if not wanted)."""
+    require_cuda(f1, f2, teacher12, teacher21)
+    lib = load()
+    if f1.dim() != 3 or f1.shape != f2.shape:
+        raise ValueError(f'cost_volume_kl: f1/f2 must both be (P, N, C), got {tuple(f1.shape)} {tuple(f2.shape)}')
+    if f1.dtype != f2.dtype:
+        raise ValueError('cost_volume_kl: f1 and f2 must share a dtype')
+    P, N, C = f1.shape
+    if tuple(teacher12.shape) != (P, N, N) or tuple(teacher21.shape) != (P, N, N):
+        raise ValueError(f'cost_volume_kl: teacher volumes must be (P, N, N) = {(P, N, N)}')
+    if variant not in ('mast3r', 'vggt'):
+        raise ValueError(f'cost_volume_kl: unknown variant {variant!r}')
+    dev = f1.device
+    t12 = teacher12.to(_F32).contiguous()
+    t21 = teacher21.to(_F32).contiguous()
+    m1 = _as_mask(mask1, P, N, dev)
+    m2 = _as_mask(mask2, P, N, dev)
+    loss = torch.empty(P, dtype=_F32, device=dev)
+    g1 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if want_grad else None
+    g2 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if want_grad else None
+    if P == 0:
+        return loss, g1, g2
+    ws = workspace(lib.gd3_cost_kl_workspace(P, N, C, pairs_per_group, int(want_grad)), dev)
+    with torch.cuda.device(dev):
+        check(lib.gd3_cost_kl(ptr(f1), ptr(f2), dtype_code(f1), P, N, C,
+                              f1.stride(0), f1.stride(1), f1.stride(2), f2.stride(0), f2.stride(1), f2.stride(2),
+                              ptr(t12), ptr(t21), N * N, N, ptr(m1), ptr(m2), VARIANT[variant], float(eps),
+                              float(grad_scale), ptr(loss), ptr(g1), ptr(g2), int(pairs_per_group), ptr(ws),
+                              ws.numel(), stream_ptr()))
+    return loss, g1, g2
+
+
 class _CostVolumeKL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group, grad_mode):
-        require_cuda(f1, f2, teacher12, teacher21)
-        lib = load()
-        if f1.dim() != 3 or f1.shape != f2.shape:
-            raise ValueError(f'cost_volume_kl: f1/f2 must both be (P, N, C), got {tuple(f1.shape)} {tuple(f2.shape)}')
-        if f1.dtype != f2.dtype:
-            raise ValueError('cost_volume_kl: f1 and f2 must share a dtype')
-        P, N, C = f1.shape
-        if teacher12.shape != (P, N, N) or teacher21.shape != (P, N, N):
-            raise ValueError(f'cost_volume_kl: teacher volumes must be (P, N, N) = {(P, N, N)}')
-        if variant not in ('mast3r', 'vggt'):
-            raise ValueError(f'cost_volume_kl: unknown variant {variant!r}')
-        dev = f1.device
-        t12 = teacher12.to(_F32).contiguous()
-        t21 = teacher21.to(_F32).contiguous()
-        m1 = _as_mask(mask1, P, N, dev)
-        m2 = _as_mask(mask2, P, N, dev)
         need_grad = grad_mode and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        loss = torch.empty(P, dtype=_F32, device=dev)
-        g1 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
-        g2 = torch.empty(P, N, C, dtype=f1.dtype, device=dev) if need_grad else None
-        if P == 0:
-            ctx.save_for_backward(g1, g2)
-            return loss
-        ws = workspace(lib.gd3_cost_kl_workspace(P, N, C, pairs_per_group, int(need_grad)), dev)
-        with torch.cuda.device(dev):
-            check(lib.gd3_cost_kl(ptr(f1), ptr(f2), dtype_code(f1), P, N, C,
-                                  f1.stride(0), f1.stride(1), f1.stride(2),
-                                  f2.stride(0), f2.stride(1), f2.stride(2),
-                                  ptr(t12), ptr(t21), N * N, N, ptr(m1), ptr(m2), VARIANT[variant], float(eps),
-                                  ptr(loss), ptr(g1), ptr(g2), int(pairs_per_group), ptr(ws), ws.numel(),
-                                  stream_ptr()))
+        loss, g1, g2 = cost_kl_raw(f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, 1.0, need_grad,
+                                   pairs_per_group)
         ctx.save_for_backward(g1, g2)
         return loss
 
@@ -87,33 +99,40 @@ def cost_volume_kl(f1, f2, teacher12, teacher21, mask1=None, mask2=None, variant
 # --------------------------------------------------------------------------------------------
 # Smooth-AP sparse-correspondence loss
 # --------------------------------------------------------------------------------------------
+def smooth_ap_raw(d1, d2, p1, p2, variant='mast3r', temp=0.01, thr_neg=0.1, thr_pos=5e-3, grad_scale=1.0,
+                  want_grad=True):
+    """-> (loss (P,), grad_d1, grad_d2) fp32, gradients of ``grad_scale * loss[p]``."""
+    require_cuda(d1, d2, p1, p2)
+    lib = load()
+    if d1.dim() != 3 or d1.shape != d2.shape:
+        raise ValueError(f'smooth_ap: descriptors must both be (P, K, C), got {tuple(d1.shape)} {tuple(d2.shape)}')
+    if variant not in VARIANT:
+        raise ValueError(f'smooth_ap: unknown variant {variant!r}')
+    P, K, C = d1.shape
+    if tuple(p1.shape) != (P, K, 3) or tuple(p2.shape) != (P, K, 3):
+        raise ValueError(f'smooth_ap: 3-D points must be (P, K, 3) = {(P, K, 3)}')
+    dev = d1.device
+    a = d1.to(_F32).contiguous()
+    b = d2.to(_F32).contiguous()
+    q1 = p1.to(_F32).contiguous()
+    q2 = p2.to(_F32).contiguous()
+    loss = torch.zeros(P, dtype=_F32, device=dev)
+    g1 = torch.zeros(P, K, C, dtype=_F32, device=dev) if want_grad else None
+    g2 = torch.zeros(P, K, C, dtype=_F32, device=dev) if want_grad else None
+    if P and K:
+        ws = workspace(lib.gd3_smooth_ap_workspace(P, K, C, int(want_grad)), dev)
+        with torch.cuda.device(dev):
+            check(lib.gd3_smooth_ap(ptr(a), ptr(b), ptr(q1), ptr(q2), P, K, C, VARIANT[variant], float(temp),
+                                    float(thr_neg), float(thr_pos), float(grad_scale), ptr(loss), ptr(g1), ptr(g2),
+                                    ptr(ws), ws.numel(), stream_ptr()))
+    return loss, g1, g2
+
+
 class _SmoothAP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, d1, d2, p1, p2, variant, temp, thr_neg, thr_pos, grad_mode):
-        require_cuda(d1, d2, p1, p2)
-        lib = load()
-        if d1.dim() != 3 or d1.shape != d2.shape:
-            raise ValueError(f'smooth_ap: descriptors must both be (P, K, C), got {tuple(d1.shape)} {tuple(d2.shape)}')
-        if variant not in VARIANT:
-            raise ValueError(f'smooth_ap: unknown variant {variant!r}')
-        P, K, C = d1.shape
-        if p1.shape != (P, K, 3) or p2.shape != (P, K, 3):
-            raise ValueError(f'smooth_ap: 3-D points must be (P, K, 3) = {(P, K, 3)}')
-        dev = d1.device
-        a = d1.to(_F32).contiguous()
-        b = d2.to(_F32).contiguous()
-        q1 = p1.to(_F32).contiguous()
-        q2 = p2.to(_F32).contiguous()
         need_grad = grad_mode and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        loss = torch.zeros(P, dtype=_F32, device=dev)
-        g1 = torch.zeros(P, K, C, dtype=_F32, device=dev) if need_grad else None
-        g2 = torch.zeros(P, K, C, dtype=_F32, device=dev) if need_grad else None
-        if P and K:
-            ws = workspace(lib.gd3_smooth_ap_workspace(P, K, C, int(need_grad)), dev)
-            with torch.cuda.device(dev):
-                check(lib.gd3_smooth_ap(ptr(a), ptr(b), ptr(q1), ptr(q2), P, K, C, VARIANT[variant], float(temp),
-                                        float(thr_neg), float(thr_pos), ptr(loss), ptr(g1), ptr(g2), ptr(ws),
-                                        ws.numel(), stream_ptr()))
+        loss, g1, g2 = smooth_ap_raw(d1, d2, p1, p2, variant, temp, thr_neg, thr_pos, 1.0, need_grad)
         ctx.save_for_backward(g1, g2)
         ctx.in_dtypes = (d1.dtype, d2.dtype)
         return loss
@@ -141,9 +160,6 @@ def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1
 # --------------------------------------------------------------------------------------------
 # relative-depth losses on the depth-difference head
 # --------------------------------------------------------------------------------------------
-HIDDEN = 128
-
-
 def head_tensors(head):
     """(W1, b1, gamma, beta, w2, b2, use_tanh, ln_eps) of a DepthAwareFeatureFusion-shaped module
     (``fusion_layer = Sequential(Linear, LayerNorm, GELU, Linear)``, utils/model.py:100-105)."""
@@ -151,54 +167,74 @@ def head_tensors(head):
     lin1, ln, lin2 = fl[0], fl[1], fl[3]
     if lin1.out_features != HIDDEN or lin2.out_features != 1:
         raise ValueError(f'depth head must be Linear(D, {HIDDEN}) -> LayerNorm -> GELU -> Linear({HIDDEN}, 1)')
-    act = fl[2]
-    if getattr(act, 'approximate', 'none') != 'none':
+    if getattr(fl[2], 'approximate', 'none') != 'none':
         raise ValueError('depth head must use the exact (erf) GELU')
     return (lin1.weight, lin1.bias, ln.weight, ln.bias, lin2.weight, lin2.bias,
             bool(getattr(head, 'use_tanh', True)), float(ln.eps))
+
+
+def depth_head_raw(feats, depths, params, use_tanh=True, ln_eps=1e-5, mode=0, thr=0.05, margin=0.05,
+                   joint_mean=False, w_rank=None, w_l1=None, want_grad=True):
+    """-> (loss_rank (S,), loss_l1 (S//2,) or None, grad_feats (S, K, D), grad_params (packed)).
+
+    ``params`` = (W1, b1, gamma, beta, w2, b2); gradients are those of
+    ``sum_s w_rank[s] loss_rank[s] + sum_p w_l1[p] loss_l1[p]``; packed layout
+    [W1 (128*D) | b1 | gamma | beta | w2 | b2].
+    """
+    require_cuda(feats, depths, params[0])
+    lib = load()
+    if feats.dim() != 3 or tuple(depths.shape) != tuple(feats.shape[:2]):
+        raise ValueError(f'depth_head_loss: feats (S, K, D) / depths (S, K) expected, got {tuple(feats.shape)} '
+                         f'{tuple(depths.shape)}')
+    S, K, D = feats.shape
+    if tuple(params[0].shape) != (HIDDEN, D):
+        raise ValueError(f'depth_head_loss: W1 must be ({HIDDEN}, {D}), got {tuple(params[0].shape)}')
+    dev = feats.device
+    f = feats.to(_F32).contiguous()
+    d = depths.to(_F32).contiguous()
+    ps = [t.detach().to(_F32).contiguous().reshape(-1) for t in params]
+    wr = None if w_rank is None else w_rank.to(dev, _F32).contiguous()
+    wl = None if w_l1 is None else w_l1.to(dev, _F32).contiguous()
+    if wl is not None and (S % 2 != 0 or wl.numel() != S // 2):
+        raise ValueError('depth_head_loss: the L1 term couples sets (2p, 2p+1); need an even S and S/2 weights')
+    if wr is not None and wr.numel() != S:
+        raise ValueError('depth_head_loss: w_rank must have one weight per set')
+    loss_rank = torch.zeros(S, dtype=_F32, device=dev)
+    loss_l1 = torch.zeros(S // 2, dtype=_F32, device=dev) if wl is not None else None
+    nparam = HIDDEN * D + 4 * HIDDEN + 1
+    gf = torch.zeros(S, K, D, dtype=_F32, device=dev) if want_grad else None
+    gp = torch.zeros(nparam, dtype=_F32, device=dev) if want_grad else None
+    if S and K:
+        ws = workspace(lib.gd3_depth_head_loss_workspace(S, K, D, int(want_grad), int(wl is not None)), dev)
+        with torch.cuda.device(dev):
+            check(lib.gd3_depth_head_loss(ptr(f), ptr(d), S, K, D, HIDDEN, *[ptr(t) for t in ps], int(use_tanh),
+                                          float(ln_eps), int(mode), float(thr), float(margin), int(joint_mean),
+                                          ptr(wr), ptr(wl), ptr(loss_rank), ptr(loss_l1), ptr(gf), ptr(gp), ptr(ws),
+                                          ws.numel(), stream_ptr()))
+    return loss_rank, loss_l1, gf, gp
+
+
+def split_param_grads(gp, D):
+    """Packed parameter gradient -> (dW1 (128, D), db1, dgamma, dbeta, dw2 (1, 128), db2 (1,))."""
+    parts = torch.split(gp, [HIDDEN * D, HIDDEN, HIDDEN, HIDDEN, HIDDEN, 1])
+    return (parts[0].reshape(HIDDEN, D), parts[1], parts[2], parts[3], parts[4].reshape(1, HIDDEN), parts[5])
 
 
 class _DepthHeadLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, depths, W1, b1, gamma, beta, w2, b2, use_tanh, ln_eps, mode, thr, margin, joint_mean,
                 w_rank, w_l1, grad_mode):
-        require_cuda(feats, depths, W1)
-        lib = load()
-        if feats.dim() != 3 or depths.shape != feats.shape[:2]:
-            raise ValueError(f'depth_head_loss: feats (S, K, D) / depths (S, K) expected, got {tuple(feats.shape)} '
-                             f'{tuple(depths.shape)}')
-        S, K, D = feats.shape
-        if W1.shape != (HIDDEN, D):
-            raise ValueError(f'depth_head_loss: W1 must be ({HIDDEN}, {D}), got {tuple(W1.shape)}')
-        dev = feats.device
-        f = feats.to(_F32).contiguous()
-        d = depths.to(_F32).contiguous()
-        params = [t.detach().to(_F32).contiguous() for t in (W1, b1, gamma, beta, w2.reshape(-1), b2.reshape(-1))]
-        wr = None if w_rank is None else w_rank.to(dev, _F32).contiguous()
-        wl = None if w_l1 is None else w_l1.to(dev, _F32).contiguous()
-        if wl is not None and (S % 2 != 0 or wl.numel() != S // 2):
-            raise ValueError('depth_head_loss: the L1 term couples sets (2p, 2p+1); need an even S and S/2 weights')
         need_grad = grad_mode and any(ctx.needs_input_grad[:8])
-        loss_rank = torch.zeros(S, dtype=_F32, device=dev)
-        loss_l1 = torch.zeros(S // 2, dtype=_F32, device=dev) if wl is not None else None
-        nparam = HIDDEN * D + 4 * HIDDEN + 1
-        gf = torch.zeros(S, K, D, dtype=_F32, device=dev) if need_grad else None
-        gp = torch.zeros(nparam, dtype=_F32, device=dev) if need_grad else None
-        if S and K:
-            ws = workspace(lib.gd3_depth_head_loss_workspace(S, K, D, int(need_grad), int(wl is not None)), dev)
-            with torch.cuda.device(dev):
-                check(lib.gd3_depth_head_loss(ptr(f), ptr(d), S, K, D, HIDDEN, *[ptr(t) for t in params],
-                                              int(use_tanh), float(ln_eps), int(mode), float(thr), float(margin),
-                                              int(joint_mean), ptr(wr), ptr(wl), ptr(loss_rank), ptr(loss_l1),
-                                              ptr(gf), ptr(gp), ptr(ws), ws.numel(), stream_ptr()))
-        total = (loss_rank * wr).sum() if wr is not None else loss_rank.sum()
-        if wl is not None:
-            total = total + (loss_l1 * wl).sum()
+        loss_rank, loss_l1, gf, gp = depth_head_raw(feats, depths, (W1, b1, gamma, beta, w2, b2), use_tanh, ln_eps,
+                                                    mode, thr, margin, joint_mean, w_rank, w_l1, need_grad)
+        total = (loss_rank * w_rank.to(loss_rank)).sum() if w_rank is not None else loss_rank.sum()
+        if loss_l1 is not None:
+            total = total + (loss_l1 * w_l1.to(loss_l1)).sum()
+        else:
+            loss_l1 = torch.zeros(0, dtype=_F32, device=feats.device)
         ctx.save_for_backward(gf, gp)
-        ctx.meta = (D, feats.dtype, tuple(t.shape for t in (W1, b1, gamma, beta, w2, b2)),
-                    tuple(t.dtype for t in (W1, b1, gamma, beta, w2, b2)))
-        if loss_l1 is None:
-            loss_l1 = torch.zeros(0, dtype=_F32, device=dev)
+        ctx.meta = (feats.shape[2], feats.dtype, tuple(t.dtype for t in (W1, b1, gamma, beta, w2, b2)),
+                    tuple(t.shape for t in (W1, b1, gamma, beta, w2, b2)))
         ctx.mark_non_differentiable(loss_rank, loss_l1)
         return total, loss_rank, loss_l1
 
@@ -208,10 +244,9 @@ class _DepthHeadLoss(torch.autograd.Function):
         nin = 17
         if gf is None:
             return (None,) * nin
-        D, fdtype, shapes, dtypes = ctx.meta
+        D, fdtype, dtypes, shapes = ctx.meta
         g = g_total.to(_F32)
-        sizes = [HIDDEN * D, HIDDEN, HIDDEN, HIDDEN, HIDDEN, 1]
-        parts = torch.split(gp * g, sizes)
+        parts = split_param_grads(gp * g, D)
         grads = [(gf * g).to(fdtype), None] + [p.reshape(s).to(dt) for p, s, dt in zip(parts, shapes, dtypes)]
         return tuple(grads) + (None,) * (nin - len(grads))
 
@@ -238,15 +273,42 @@ def depth_head_loss(head, feats, depths, mode='logistic', depth_threshold=0.05, 
 # --------------------------------------------------------------------------------------------
 # bilinear token sampling
 # --------------------------------------------------------------------------------------------
-def _sample_fwd(tokens, strides, L, P, C, ph, pw, h, w, kp, patch, stride, normalize, out, out_strides):
+def sample_fwd_raw(tokens, layout, geom, kp, normalize, channels_first_out=False):
+    """tokens addressed through ``layout`` = (L, P, N, C, (sL, sP, sN, sC)) -> (out, inv_norm, out_strides)."""
     lib = load()
+    L, P, N, C, strides = layout
+    ph, pw, h, w, patch, stride = geom
+    if N != ph * pw:
+        raise ValueError(f'sample_tokens: {N} tokens do not form a {ph} x {pw} grid')
+    if kp.dim() != 3 or kp.shape[0] != P or kp.shape[2] != 2:
+        raise ValueError(f'sample_tokens: keypoints must be (P, K, 2), got {tuple(kp.shape)}')
     K = kp.shape[1]
-    inv = torch.empty(P, K, dtype=_F32, device=tokens.device) if normalize else None
-    with torch.cuda.device(tokens.device):
-        check(lib.gd3_sample_tokens_fwd(ptr(tokens), dtype_code(tokens), L, P, C, ph, pw, h, w, *strides, ptr(kp), K,
-                                        patch, stride, int(normalize), ptr(out), *out_strides, ptr(inv),
-                                        stream_ptr()))
-    return inv
+    dev = tokens.device
+    if channels_first_out:
+        out = torch.empty(P, C, K, dtype=_F32, device=dev)
+        ostr = (C * K, 1, K)          # (oP, oK, oC)
+    else:
+        out = torch.empty(P, K, C, dtype=_F32, device=dev)
+        ostr = (K * C, C, 1)
+    inv = torch.empty(P, K, dtype=_F32, device=dev) if normalize else None
+    if P and K:
+        with torch.cuda.device(dev):
+            check(lib.gd3_sample_tokens_fwd(ptr(tokens), dtype_code(tokens), L, P, C, ph, pw, h, w, *strides, ptr(kp),
+                                            K, patch, stride, int(normalize), ptr(out), *ostr, ptr(inv),
+                                            stream_ptr()))
+    return out, inv, ostr
+
+
+def sample_bwd_raw(grad_out, gstr, out, ostr, inv, kp, dims, geom, normalize, grad_tokens, gstrides):
+    """Scatter ``grad_out`` back through the taps, accumulating into ``grad_tokens`` (fp32)."""
+    lib = load()
+    L, P, K, C = dims
+    ph, pw, h, w, patch, stride = geom
+    if P and K:
+        with torch.cuda.device(grad_out.device):
+            check(lib.gd3_sample_tokens_bwd(ptr(grad_out), *gstr, ptr(out), *ostr, ptr(inv), ptr(kp), L, P, K, C, ph,
+                                            pw, h, w, patch, stride, int(normalize), ptr(grad_tokens), *gstrides,
+                                            stream_ptr()))
 
 
 class _SampleTokens(torch.autograd.Function):
@@ -261,22 +323,8 @@ class _SampleTokens(torch.autograd.Function):
     def forward(ctx, tokens, kp, geom, normalize, channels_first_out, layout):
         require_cuda(tokens, kp)
         L, P, N, C, strides, _ = layout
-        ph, pw, h, w, patch, stride = geom
-        if N != ph * pw:
-            raise ValueError(f'sample_tokens: {N} tokens do not form a {ph} x {pw} grid')
         kp = kp.to(_F32).contiguous()
-        if kp.dim() != 3 or kp.shape[0] != P or kp.shape[2] != 2:
-            raise ValueError(f'sample_tokens: keypoints must be (P, K, 2), got {tuple(kp.shape)}')
-        K = kp.shape[1]
-        if channels_first_out:
-            out = torch.empty(P, C, K, dtype=_F32, device=tokens.device)
-            ostr = (C * K, 1, K)          # (oP, oK, oC)
-        else:
-            out = torch.empty(P, K, C, dtype=_F32, device=tokens.device)
-            ostr = (K * C, C, 1)
-        inv = None
-        if P and K:
-            inv = _sample_fwd(tokens, strides, L, P, C, ph, pw, h, w, kp, patch, stride, normalize, out, ostr)
+        out, inv, ostr = sample_fwd_raw(tokens, (L, P, N, C, strides), geom, kp, normalize, channels_first_out)
         ctx.save_for_backward(kp, out if normalize else None, inv)
         ctx.meta = (tokens.shape, tokens.dtype, layout, geom, normalize, ostr, channels_first_out)
         return out
@@ -284,21 +332,27 @@ class _SampleTokens(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         kp, out, inv = ctx.saved_tensors
-        shape, dtype, (L, P, N, C, _, gstrides), (ph, pw, h, w, patch, stride), normalize, ostr, cf = ctx.meta
-        lib = load()
+        shape, dtype, (L, P, N, C, _, gstrides), geom, normalize, ostr, cf = ctx.meta
         K = kp.shape[1]
         gt = torch.zeros(shape, dtype=_F32, device=grad_out.device)
-        if P and K:
-            grad_out = grad_out.to(_F32)
-            if cf:   # (P, C, K)
-                gstr = (grad_out.stride(0), grad_out.stride(2), grad_out.stride(1))
-            else:    # (P, K, C)
-                gstr = (grad_out.stride(0), grad_out.stride(1), grad_out.stride(2))
-            with torch.cuda.device(grad_out.device):
-                check(lib.gd3_sample_tokens_bwd(ptr(grad_out), *gstr, ptr(out), *ostr, ptr(inv), ptr(kp), L, P, K, C,
-                                                ph, pw, h, w, patch, stride, int(normalize), ptr(gt), *gstrides,
-                                                stream_ptr()))
+        grad_out = grad_out.to(_F32)
+        if cf:   # (P, C, K)
+            gstr = (grad_out.stride(0), grad_out.stride(2), grad_out.stride(1))
+        else:    # (P, K, C)
+            gstr = (grad_out.stride(0), grad_out.stride(1), grad_out.stride(2))
+        sample_bwd_raw(grad_out, gstr, out, ostr, inv, kp, (L, P, K, C), geom, normalize, gt, gstrides)
         return gt.to(dtype), None, None, None, None, None
+
+
+def token_layout(tokens):
+    """(L, P, N, C, strides, contiguous-gradient strides) of a (P, N, C) or (L, P, N, C) token tensor."""
+    if tokens.dim() == 3:
+        P, N, C = tokens.shape
+        return 1, P, N, C, (0, tokens.stride(0), tokens.stride(1), tokens.stride(2)), (0, N * C, C, 1)
+    if tokens.dim() == 4:
+        L, P, N, C = tokens.shape
+        return L, P, N, C, tuple(tokens.stride()), (P * N * C, N * C, C, 1)
+    raise ValueError('sample_tokens: tokens must be (P, N, C) or (L, P, N, C)')
 
 
 def sample_tokens(tokens, grid, kp, patch_size=14, stride=14, normalize=False, image_hw=None):
@@ -310,19 +364,8 @@ def sample_tokens(tokens, grid, kp, patch_size=14, stride=14, normalize=False, i
     """
     ph, pw = grid
     h, w = image_hw if image_hw is not None else (ph * patch_size, pw * patch_size)
-    if tokens.dim() == 3:
-        P, N, C = tokens.shape
-        L = 1
-        strides = (0, tokens.stride(0), tokens.stride(1), tokens.stride(2))
-        gstrides = (0, N * C, C, 1)
-    elif tokens.dim() == 4:
-        L, P, N, C = tokens.shape
-        strides = tuple(tokens.stride())
-        gstrides = (P * N * C, N * C, C, 1)
-    else:
-        raise ValueError('sample_tokens: tokens must be (P, N, C) or (L, P, N, C)')
     return _SampleTokens.apply(tokens, kp, (ph, pw, h, w, patch_size, stride), normalize, False,
-                               (L, P, N, C, strides, gstrides))
+                               token_layout(tokens))
 
 
 def interpolate_nchw(descriptors, pts, h, w, patch_size, stride, normalize):

@@ -1,0 +1,101 @@
+"""One fused geometric-distillation step over a batch of image pairs (product path, no autograd).
+
+Mirrors steps 4-7 of the reference's ``training_step`` (src/finetune_timm_mast3r.py:636-653, vggt
+:614-625): depth losses (cross-view L1 + intra-view ranking), cost-volume KL, Smooth-AP matching and
+their weighted sum, for P pairs at once.  Everything runs through the C ABI of lib3dgd.so; torch is
+used for buffers and the stream only.  The total is the mean over pairs of
+
+    w_ap * ap + w_depth * l1 + w_intra * rank + w_kl * kl
+
+(the reference's per-rank loss with one pair per rank; its DDP then averages gradients over ranks).
+"""
+import torch
+
+from . import ops
+
+_F32 = torch.float32
+
+# constructor defaults of the reference modules: mast3r (src/finetune_timm_mast3r.py:79-84) trains with
+# depth weight 0, vggt (src/finetune_timm_vggt.py:86-89) with all weights 1
+DEFAULT_WEIGHTS = {
+    'mast3r': dict(ap=1.0, depth=0.0, intra=1.0, kl=1.0),
+    'vggt': dict(ap=1.0, depth=1.0, intra=1.0, kl=1.0),
+}
+
+
+def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backward=True, weights=None,
+                      pairs_per_group=0, depth_threshold=0.05, thr_neg=0.1, temp=0.01):
+    """Run the three distillation losses (+ L1) forward and backward for a batch of pairs.
+
+    batch (all CUDA tensors):
+      f1, f2     (P, N, C)  student patch features for the cost volume (fp32 / bf16)
+      t12, t21   (P, N, N)  teacher volumes;  m1, m2 (P, N) bool patch masks
+      g1, g2     (P, N, C)  token maps the keypoint descriptors / depth features are sampled from
+      kp1, kp2   (P, K, 2)  pixel keypoints;  p3d1, p3d2 (P, K, 3);  dep1, dep2 (P, K) keypoint depths
+      head       dict W1, b1, gamma, beta, w2, b2 (+ use_tanh, ln_eps) of the depth-difference head
+    Returns dict: kl, ap, rank, l1 (each (P,)), total (0-d) and, if backward, ``grads`` with f1, f2 (feature
+    dtype), g1, g2 (fp32) and head (packed [W1 | b1 | gamma | beta | w2 | b2]).
+    """
+    w = dict(DEFAULT_WEIGHTS[variant])
+    if weights:
+        w.update(weights)
+    f1, f2 = batch['f1'], batch['f2']
+    P, N, C = f1.shape
+    ph, pw = grid
+    geom = (ph, pw, ph * patch_size, pw * patch_size, patch_size, patch_size)
+    inv_p = 1.0 / max(P, 1)
+    head = batch['head']
+    params = (head['W1'], head['b1'], head['gamma'], head['beta'], head['w2'], head['b2'])
+    dev = f1.device
+    out = {}
+
+    # ---- dense cost-volume KL (K1) ----
+    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, batch['t12'], batch['t21'], batch['m1'], batch['m2'], variant,
+                                   grad_scale=w['kl'] * inv_p, want_grad=backward, pairs_per_group=pairs_per_group)
+
+    # ---- keypoint descriptors / features from the token maps (K3) ----
+    g1, g2 = batch['g1'], batch['g2']
+    kp1 = batch['kp1'].to(_F32).contiguous()
+    kp2 = batch['kp2'].to(_F32).contiguous()
+    K = kp1.shape[1]
+    L1_, P1_, N1_, C1_, str1, gstr1 = ops.token_layout(g1)
+    _, _, _, _, str2, gstr2 = ops.token_layout(g2)
+    lay1, lay2 = (1, P, N, C1_, str1), (1, P, N, C1_, str2)
+    d1, inv1, ostr = ops.sample_fwd_raw(g1, lay1, geom, kp1, True)
+    d2, inv2, _ = ops.sample_fwd_raw(g2, lay2, geom, kp2, True)
+    # depth features of both views interleaved as sets (2p, 2p+1) = (view 1, view 2) of pair p
+    kf = torch.empty(P, 2, K, C1_, dtype=_F32, device=dev)
+    k1, _, _ = ops.sample_fwd_raw(g1, lay1, geom, kp1, False)
+    k2, _, _ = ops.sample_fwd_raw(g2, lay2, geom, kp2, False)
+    kf[:, 0] = k1
+    kf[:, 1] = k2
+    depths = torch.stack([batch['dep1'].to(_F32), batch['dep2'].to(_F32)], dim=1).reshape(2 * P, K)
+
+    # ---- Smooth-AP (K2) ----
+    ap, gd1, gd2 = ops.smooth_ap_raw(d1, d2, batch['p3d1'], batch['p3d2'], variant, temp, thr_neg,
+                                     grad_scale=w['ap'] * inv_p, want_grad=backward)
+
+    # ---- relative depth: ranking on both views + cross-view L1 (K4) ----
+    w_rank = torch.full((2 * P,), 0.5 * w['intra'] * inv_p, dtype=_F32, device=dev)
+    w_l1 = torch.full((P,), w['depth'] * inv_p, dtype=_F32, device=dev)
+    lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, C1_), depths, params,
+                                              head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
+                                              depth_threshold, 0.05, False, w_rank, w_l1, backward)
+    rank = 0.5 * (lr[0::2] + lr[1::2])
+    out.update(kl=kl, ap=ap, rank=rank, l1=l1)
+    out['total'] = (w['ap'] * ap + w['depth'] * l1 + w['intra'] * rank + w['kl'] * kl).mean()
+
+    if backward:
+        # scatter the keypoint gradients back into the token maps (K3 backward)
+        gg1 = torch.zeros(P, N, C1_, dtype=_F32, device=dev)
+        gg2 = torch.zeros(P, N, C1_, dtype=_F32, device=dev)
+        dims = (1, P, K, C1_)
+        cont = (K * C1_, C1_, 1)
+        ops.sample_bwd_raw(gd1, cont, d1, ostr, inv1, kp1, dims, geom, True, gg1, gstr1)
+        ops.sample_bwd_raw(gd2, cont, d2, ostr, inv2, kp2, dims, geom, True, gg2, gstr2)
+        gk = gkf.reshape(P, 2, K, C1_)
+        pstr = (2 * K * C1_, C1_, 1)
+        ops.sample_bwd_raw(gk[:, 0], pstr, None, ostr, None, kp1, dims, geom, False, gg1, gstr1)
+        ops.sample_bwd_raw(gk[:, 1], pstr, None, ostr, None, kp2, dims, geom, False, gg2, gstr2)
+        out['grads'] = dict(f1=gf1, f2=gf2, g1=gg1, g2=gg2, head=gparams)
+    return out

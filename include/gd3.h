@@ -77,6 +77,7 @@ int gd3_reciprocal_nn(const float* A, int64_t nA, const float* B, int64_t nB, in
  *   loss     (P) fp32, one value per pair = (KL_12 + KL_21) / 2
  *   grad_f1/2 (P, N, C) contiguous, same dtype as the features: d loss[p] / d f (NULL, NULL =
  *            forward only)
+ * grad_scale: factor folded into the gradients (e.g. loss weight / P); loss values are unscaled.
  * pairs_per_group: how many pairs share one pass over the workspace (0 = choose so that a group's
  * working set stays L2-resident).
  * ------------------------------------------------------------------------------------------ */
@@ -85,8 +86,8 @@ size_t gd3_cost_kl_workspace(int64_t P, int64_t N, int64_t C, int64_t pairs_per_
 int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N, int64_t C, int64_t s1P, int64_t s1N,
                 int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const float* t12, const float* t21,
                 int64_t t_pair_stride, int64_t t_row_stride, const uint8_t* m1, const uint8_t* m2, int variant,
-                float eps, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group, void* workspace,
-                size_t workspace_bytes, void* stream);
+                float eps, float grad_scale, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group,
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Smooth-AP sparse-correspondence loss, forward + backward, batched over P pairs.
@@ -96,12 +97,12 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
  *   d1, d2      (P, K, C) fp32 contiguous, L2-normalised keypoint descriptors
  *   pts3d_1/2   (P, K, 3) fp32 3-D points of the keypoints
  *   temp 0.01, thr_neg 0.1 (thres3d_neg), thr_pos 5e-3 (thresh3d_pos, GD3_VARIANT_ME only)
- *   loss        (P) fp32;  grad_d1/2 (P, K, C) fp32 contiguous or NULL, NULL for forward only
+ *   loss        (P) fp32;  grad_d1/2 (P, K, C) fp32 contiguous (times grad_scale) or NULL, NULL = forward only
  * ------------------------------------------------------------------------------------------ */
 size_t gd3_smooth_ap_workspace(int64_t P, int64_t K, int64_t C, int with_backward);
 int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const float* pts3d_2, int64_t P, int64_t K,
-                  int64_t C, int variant, float temp, float thr_neg, float thr_pos, float* loss, float* grad_d1,
-                  float* grad_d2, void* workspace, size_t workspace_bytes, void* stream);
+                  int64_t C, int variant, float temp, float thr_neg, float thr_pos, float grad_scale, float* loss,
+                  float* grad_d1, float* grad_d2, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Relative-depth losses on the depth-difference head, forward + backward, batched over S keypoint

@@ -1,0 +1,39 @@
+"""GPU parity of one whole fused distillation step (KL + Smooth-AP + ranking + L1, fwd + bwd, batched)
+against the CPU oracle's per-pair reference flow."""
+import pytest
+import torch
+
+import bench_common
+from helpers import assert_grad_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('variant,cfg', [
+    ('mast3r', dict(N=256, C=384, K=128, grid=(16, 16), P=3)),
+    ('vggt', dict(N=15 * 17, C=200, K=77, grid=(15, 17), P=2)),
+])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_distillation_step_vs_oracle(variant, cfg, dtype):
+    from gd3 import pipeline
+    cfg = dict(cfg, variant=variant)
+    batch = bench_common.make_batch(cfg, cfg_id=1)
+    want = bench_common.oracle_step(batch, cfg)
+    dev = bench_common.to_device(batch, 'cuda', feature_dtype=dtype)
+    out = pipeline.distillation_step(dev, variant=variant, grid=cfg['grid'], backward=True, pairs_per_group=2)
+    torch.cuda.synchronize()
+    for k in ('kl', 'ap', 'rank', 'l1'):
+        got, ref = out[k].float().cpu(), want[k]
+        err = ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
+        assert err <= 1e-3, (k, got, ref)
+    assert abs(out['total'].item() - want['total'].item()) <= 1e-3 * abs(want['total'].item())
+    for k in ('f1', 'f2', 'g1', 'g2', 'head'):
+        assert_grad_close(out['grads'][k], want['grads'][k], name=k, norm_rtol=3e-2)
+    fwd = pipeline.distillation_step(dev, variant=variant, grid=cfg['grid'], backward=False)
+    assert 'grads' not in fwd
+    assert abs(fwd['total'].item() - out['total'].item()) <= 1e-5 * abs(out['total'].item())
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()
