@@ -44,7 +44,24 @@ const char* last_error();
     }                                          \
   } while (0)
 
-#define GD3_CHECK_LAUNCH() GD3_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through GD3_CHECK_LAUNCH: it also feeds gd3_launch_count()
+void count_launch();
+#define GD3_CHECK_LAUNCH()                \
+  do {                                    \
+    ::gd3::count_launch();                \
+    GD3_CHECK_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// Optional per-kernel timing with CUDA events on the launching stream (gd3_profile_enable).  A scope
+// brackets one launch; durations are resolved lazily by gd3_profile_read after a synchronise.
+struct ProfScope {
+  const char* name;
+  cudaStream_t stream;
+  int slot;
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+};
+#define GD3_PROF(name, stream) ::gd3::ProfScope _gd3_prof_scope(name, stream)
 
 inline int num_sms() {
   static int n = 0;

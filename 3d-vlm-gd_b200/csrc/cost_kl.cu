@@ -536,60 +536,81 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     {
       dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)g, 2);
       if (dtype == GD3_DTYPE_F32)
-        kl_prep_features<float><<<grid, 256, 0, stream>>>(
+        {
+          GD3_PROF("kl_prep_features", stream);
+          kl_prep_features<float><<<grid, 256, 0, stream>>>(
             static_cast<const float*>(f1), static_cast<const float*>(f2), s1P, s1N, s1C, s2P, s2N, s2C, (int)p0,
             (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, backward ? w.aT : nullptr, backward ? w.bT : nullptr, w.inv1, w.inv2);
+        }
       else
-        kl_prep_features<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        {
+          GD3_PROF("kl_prep_features", stream);
+          kl_prep_features<__nv_bfloat16><<<grid, 256, 0, stream>>>(
             static_cast<const __nv_bfloat16*>(f1), static_cast<const __nv_bfloat16*>(f2), s1P, s1N, s1C, s2P, s2N,
             s2C, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, backward ? w.aT : nullptr, backward ? w.bT : nullptr,
             w.inv1, w.inv2);
+        }
       GD3_CHECK_LAUNCH();
     }
     {
       const int64_t warps = 2 * (int64_t)g * N;
-      kl_teacher_stats<<<(unsigned)ceil_div<int64_t>(warps, 8), 256, 0, stream>>>(
+      {
+        GD3_PROF("kl_teacher_stats", stream);
+        kl_teacher_stats<<<(unsigned)ceil_div<int64_t>(warps, 8), 256, 0, stream>>>(
           t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, (int)N, eps, masked_const, w.invR, w.epsm,
           w.Tsum, w.loss_acc);
+      }
       GD3_CHECK_LAUNCH();
       dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)ceil_div<int64_t>(N, 32), (unsigned)g);
-      kl_build_w<<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N, w.invR, w.epsm,
+      {
+        GD3_PROF("kl_build_w", stream);
+        kl_build_w<<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N, w.invR, w.epsm,
                                            w.WT, w.ldw);
+      }
       GD3_CHECK_LAUNCH();
     }
     {
       EpiKLStats::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, backward ? w.Z : nullptr, w.ldn};
       tc::GemmShape s{(int)N, (int)N, (int)C, g};
-      if ((rc = tc::launch_gemm<256, 4, EpiKLStats>(tm_a, tm_b, s, ep, stream))) return rc;
+      if ((rc = tc::launch_gemm<256, 4, EpiKLStats>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream))) return rc;
     }
     {
       const int64_t n = 2 * (int64_t)g * N;
-      kl_finalize_stats<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(g, (int)N, w.invR, w.Tsum, w.Lrow,
+      {
+        GD3_PROF("kl_finalize_stats", stream);
+        kl_finalize_stats<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(g, (int)N, w.invR, w.Tsum, w.Lrow,
                                                                                w.Lcol, w.rc, w.loss_acc);
+      }
       GD3_CHECK_LAUNCH();
-      kl_write_loss<<<ceil_div(g, 64), 64, 0, stream>>>(w.loss_acc, loss + p0, g);
+      {
+        GD3_PROF("kl_write_loss", stream);
+        kl_write_loss<<<ceil_div(g, 64), 64, 0, stream>>>(w.loss_acc, loss + p0, g);
+      }
       GD3_CHECK_LAUNCH();
     }
     if (backward) {
       dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
-      kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
+      {
+        GD3_PROF("kl_dz", stream);
+        kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
                                       w.coldot);
+      }
       GD3_CHECK_LAUNCH();
       tc::GemmShape s{(int)N, (int)C, (int)N, g};
       if (dtype == GD3_DTYPE_F32) {
         using E = EpiGradOut<float>;
         E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1, static_cast<float*>(grad_f1) + p0 * N * C};
         E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2, static_cast<float*>(grad_f2) + p0 * N * C};
-        if ((rc = tc::launch_gemm<256, 4, E>(tm_dz, tm_bt, s, e1, stream))) return rc;
-        if ((rc = tc::launch_gemm<256, 4, E>(tm_dzt, tm_at, s, e2, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
       } else {
         using E = EpiGradOut<__nv_bfloat16>;
         E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1,
                      static_cast<__nv_bfloat16*>(grad_f1) + p0 * N * C};
         E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2,
                      static_cast<__nv_bfloat16*>(grad_f2) + p0 * N * C};
-        if ((rc = tc::launch_gemm<256, 4, E>(tm_dz, tm_bt, s, e1, stream))) return rc;
-        if ((rc = tc::launch_gemm<256, 4, E>(tm_dzt, tm_at, s, e2, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
       }
     }
   }

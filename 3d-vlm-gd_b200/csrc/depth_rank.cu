@@ -39,6 +39,18 @@ __device__ __forceinline__ float half_sum(float v, unsigned mask) {
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
+// Transposed operands of the d W1 GEMM.  The contraction runs over keypoints of `gs` consecutive sets and over
+// three precision panels, all contiguous in a row:  column(set, k, panel) = ((set / gs) * 3 + panel) * gl +
+// (set % gs) * ldk + k, gl = gs * ldk.  One GEMM batch entry per group of sets (split-K), so the fp32 atomics
+// of the epilogue are issued once per group instead of once per set.
+struct TLayout {
+  int gs, ldk;
+  int64_t gl, ld;     // group panel length, full row length = groups * 3 * gl
+  __host__ __device__ int64_t col(int set, int k, int panel) const {
+    return ((int64_t)(set / gs) * 3 + panel) * gl + (int64_t)(set % gs) * ldk + k;
+  }
+};
+
 // hidden index of this lane's i-th element: two float4 groups, 64 apart -> conflict-free LDS.128
 __device__ __forceinline__ int hidx(int l16, int i) { return (i < 4) ? 4 * l16 + i : 64 + 4 * l16 + (i - 4); }
 
@@ -416,8 +428,8 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     rank_reduce_du(const float* __restrict__ dub_part, const float* __restrict__ dua_part,
-                   const float* __restrict__ du_extra, int S, int K, int TA, int TB, int64_t ldr, int ldk,
-                   __nv_bfloat16* __restrict__ du_bf, __nv_bfloat16* __restrict__ duT_bf, float* __restrict__ gb1) {
+                   const float* __restrict__ du_extra, int S, int K, int TA, int TB, TLayout tl,
+                   __nv_bfloat16* __restrict__ du_bf, __nv_bfloat16* __restrict__ duT3, float* __restrict__ gb1) {
   __shared__ float tile[32][H + 1];
   __shared__ float colsum[8][H];
   const int set = blockIdx.y, k0 = blockIdx.x * 32;
@@ -449,9 +461,19 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int i = 0; i < 4; ++i) colsum[w][4 * lane + i] = bsum[i];
   __syncthreads();
-  // du^T[h][set*K + k]: lanes along k
-  for (int h = w; h < H; h += 8)
-    if (k0 + lane < K) duT_bf[(int64_t)h * ldr + (int64_t)set * ldk + k0 + lane] = __float2bfloat16(tile[lane][h]);
+  // du^T panels [hi | hi | lo] (A side of the split product), lanes along k; pad columns k in [K, ldk) are zeroed
+  for (int h = w; h < H; h += 8) {
+    const int k = k0 + lane;
+    if (k < tl.ldk) {
+      const float v = (k < K) ? tile[lane][h] : 0.f;
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+      __nv_bfloat16* row = duT3 + (int64_t)h * tl.ld;
+      row[tl.col(set, k, 0)] = hi;
+      row[tl.col(set, k, 1)] = hi;
+      row[tl.col(set, k, 2)] = lo;
+    }
+  }
   if (threadIdx.x < H) {
     float t = 0.f;
 #pragma unroll
@@ -463,12 +485,12 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 // operand preparation for the GEMMs
 // ------------------------------------------------------------------------------------------
-// split x (R x D fp32) into [hi | second | third] panels (R x 3 ldd) and optionally x^T hi (D x ldr) bf16
+// split x (R x D fp32) into [hi | second | third] panels (R x 3 ldd) and optionally x^T as [hi | lo | hi] panels
 // lo_panel = 2: [hi | hi | lo] (A side); lo_panel = 1: [hi | lo | hi] (B side)
-// x^T columns are laid out per set with a padded stride: column = (row / K) * ldk + row % K
+// in the TLayout column order (B side of the d W1 split product)
 __global__ void __launch_bounds__(256)
     split3_bf16(const float* __restrict__ x, int64_t R, int D, int ldd, int lo_panel, __nv_bfloat16* __restrict__ X3,
-                __nv_bfloat16* __restrict__ XT, int64_t ldr, int K, int ldk) {
+                __nv_bfloat16* __restrict__ XT, TLayout tl, int K) {
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -493,7 +515,16 @@ __global__ void __launch_bounds__(256)
       for (int r = w; r < 32; r += 8) {
         const int c = c0 + r;
         const int64_t row = r0 + lane;
-        if (c < D && row < R) XT[(int64_t)c * ldr + (row / K) * ldk + row % K] = __float2bfloat16(tile[lane][r]);
+        if (c < D && row < R) {
+          const float v = tile[lane][r];
+          const __nv_bfloat16 hi = __float2bfloat16(v);
+          const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+          const int set = (int)(row / K), k = (int)(row % K);
+          __nv_bfloat16* o = XT + (int64_t)c * tl.ld;
+          o[tl.col(set, k, 0)] = hi;
+          o[tl.col(set, k, 1)] = lo;
+          o[tl.col(set, k, 2)] = hi;
+        }
       }
   }
 }
@@ -531,13 +562,14 @@ __global__ void rank_finalize(const double* __restrict__ loss_sum, const float* 
 }
 
 struct RankWorkspace {
-  __nv_bfloat16 *F3, *W3, *FT, *W1T, *du_bf, *duT_bf;
+  __nv_bfloat16 *F3, *W3, *FT3, *W1T, *du_bf, *duT3;
   float *u, *inv_count, *dub_part, *dua_part, *du_extra;
   double *loss_sum, *l1_sum;
   int* count;
   size_t total;
-  int ldd, TA, ldk;
-  int64_t ldr;
+  int ldd, TA, groups;
+  TLayout tl;
+  bool t_pads;   // transposed buffers contain columns no writer touches (must be zeroed)
 };
 
 RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backward, bool l1) {
@@ -545,8 +577,13 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   Carver c(base);
   const int64_t R = S * K;
   w.ldd = (int)round_up<int64_t>(D, 8);
-  w.ldk = (int)round_up<int64_t>(K, 8);
-  w.ldr = S * (int64_t)w.ldk;
+  w.tl.ldk = (int)round_up<int64_t>(K, 8);
+  w.groups = (int)(S < 16 ? S : 16);
+  w.tl.gs = (int)ceil_div<int64_t>(S, w.groups);
+  w.groups = (int)ceil_div<int64_t>(S, w.tl.gs);
+  w.tl.gl = (int64_t)w.tl.gs * w.tl.ldk;
+  w.tl.ld = (int64_t)w.groups * 3 * w.tl.gl;
+  w.t_pads = (S % w.tl.gs != 0) || (K != w.tl.ldk);
   w.TA = (int)ceil_div<int64_t>(K, TILE);
   w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
   w.W3 = c.take<__nv_bfloat16>((int64_t)H * 3 * w.ldd);
@@ -556,10 +593,10 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.loss_sum = c.take<double>(S);
   w.l1_sum = c.take<double>(S);
   if (backward) {
-    w.FT = c.take<__nv_bfloat16>(D * w.ldr);
+    w.FT3 = c.take<__nv_bfloat16>(D * w.tl.ld);
     w.W1T = c.take<__nv_bfloat16>(D * (int64_t)H);
     w.du_bf = c.take<__nv_bfloat16>(R * H);
-    w.duT_bf = c.take<__nv_bfloat16>((int64_t)H * w.ldr);
+    w.duT3 = c.take<__nv_bfloat16>((int64_t)H * w.tl.ld);
     w.dub_part = c.take<float>(S * w.TA * K * H);
     w.dua_part = c.take<float>(S * w.TA * K * H);
     if (l1) w.du_extra = c.take<float>(R * H);
@@ -625,11 +662,22 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   }
   const int64_t R = S * K;
   int rc;
+  if (backward && w.t_pads) {
+    // ragged K or a partial last group: columns no writer touches must read as zero in the d W1 contraction
+    GD3_CHECK_CUDA(cudaMemsetAsync(w.FT3, 0, sizeof(__nv_bfloat16) * D * w.tl.ld, stream));
+    GD3_CHECK_CUDA(cudaMemsetAsync(w.duT3, 0, sizeof(__nv_bfloat16) * H * w.tl.ld, stream));
+  }
   // ---- u = f W1^T on the tensor cores (split bf16, 3 K-concatenated panels) ----
-  split3_bf16<<<(unsigned)ceil_div<int64_t>(R, 32), 256, 0, stream>>>(feats, R, (int)D, w.ldd, 2, w.F3,
-                                                                     backward ? w.FT : nullptr, w.ldr, (int)K, w.ldk);
+  {
+    GD3_PROF("split3_bf16", stream);
+    split3_bf16<<<(unsigned)ceil_div<int64_t>(R, 32), 256, 0, stream>>>(feats, R, (int)D, w.ldd, 2, w.F3,
+                                                                     backward ? w.FT3 : nullptr, w.tl, (int)K);
+  }
   GD3_CHECK_LAUNCH();
-  split3_bf16<<<(unsigned)ceil_div<int64_t>(H, 32), 256, 0, stream>>>(W1, H, (int)D, w.ldd, 1, w.W3, nullptr, 0, 1, 1);
+  {
+    GD3_PROF("split3_bf16", stream);
+    split3_bf16<<<(unsigned)ceil_div<int64_t>(H, 32), 256, 0, stream>>>(W1, H, (int)D, w.ldd, 1, w.W3, nullptr, TLayout{}, 1);
+  }
   GD3_CHECK_LAUNCH();
   {
     CUtensorMap ta, tb;
@@ -637,7 +685,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     if ((rc = tc::make_tmap_bf16(&tb, w.W3, 3 * (int64_t)w.ldd, H, 1, 3 * (int64_t)w.ldd, 0, 128))) return rc;
     tc::EpiStoreF32::Params ep{w.u, (int)R, H, H, 0, 1.0f, nullptr};
     tc::GemmShape s{(int)R, H, 3 * w.ldd, 1};
-    if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>(ta, tb, s, ep, stream))) return rc;
+    if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>("rank_u_gemm", ta, tb, s, ep, stream))) return rc;
   }
   // ---- valid-pair counts ----
   GD3_CHECK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * S, stream));
@@ -646,9 +694,15 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   {
     const int64_t cnt_blocks = ceil_div<int64_t>(K * K, 256);
     dim3 grid((unsigned)(cnt_blocks < 64 ? cnt_blocks : 64), (unsigned)S);
-    rank_count<<<grid, 256, 0, stream>>>(depths, (int)K, mode, thr, w.count);
+    {
+      GD3_PROF("rank_count", stream);
+      rank_count<<<grid, 256, 0, stream>>>(depths, (int)K, mode, thr, w.count);
+    }
     GD3_CHECK_LAUNCH();
-    rank_inv_count<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.count, (int)S, joint_mean, w.inv_count);
+    {
+      GD3_PROF("rank_inv_count", stream);
+      rank_inv_count<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.count, (int)S, joint_mean, w.inv_count);
+    }
     GD3_CHECK_LAUNCH();
   }
   RankParams rp{};
@@ -682,14 +736,20 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
         GD3_CHECK_CUDA(cudaFuncSetAttribute(rank_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg = true;
       }
-      rank_pairs<true><<<grid, WARPS * 32, smem, stream>>>(rp);
+      {
+        GD3_PROF("rank_pairs", stream);
+        rank_pairs<true><<<grid, WARPS * 32, smem, stream>>>(rp);
+      }
     } else {
       static bool cfg = false;
       if (!cfg) {
         GD3_CHECK_CUDA(cudaFuncSetAttribute(rank_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg = true;
       }
-      rank_pairs<false><<<grid, WARPS * 32, smem, stream>>>(rp);
+      {
+        GD3_PROF("rank_pairs", stream);
+        rank_pairs<false><<<grid, WARPS * 32, smem, stream>>>(rp);
+      }
     }
     GD3_CHECK_LAUNCH();
   }
@@ -697,22 +757,37 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     if (backward) GD3_CHECK_CUDA(cudaMemsetAsync(w.du_extra, 0, sizeof(float) * R * H, stream));
     dim3 grid((unsigned)ceil_div<int64_t>(K, 16), (unsigned)(S / 2));
     if (backward)
-      rank_l1<true><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, w.du_extra);
+      {
+        GD3_PROF("rank_l1", stream);
+        rank_l1<true><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, w.du_extra);
+      }
     else
-      rank_l1<false><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, nullptr);
+      {
+        GD3_PROF("rank_l1", stream);
+        rank_l1<false><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, nullptr);
+      }
     GD3_CHECK_LAUNCH();
   }
-  rank_finalize<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.loss_sum, w.inv_count, w.l1_sum, (int)S,
+  {
+    GD3_PROF("rank_finalize", stream);
+    rank_finalize<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.loss_sum, w.inv_count, w.l1_sum, (int)S,
                                                                         (int)K, loss_rank, l1 ? loss_l1 : nullptr);
+  }
   GD3_CHECK_LAUNCH();
   if (!backward) return GD3_OK;
   // ---- gradients: du, then d feats = du W1 and d W1 = du^T f on the tensor cores ----
   {
     dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)S);
-    rank_reduce_du<<<grid, 256, 0, stream>>>(w.dub_part, w.dua_part, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.TA,
-                                             w.TA, w.ldr, w.ldk, w.du_bf, w.duT_bf, grad_params + (int64_t)H * D);
+    {
+      GD3_PROF("rank_reduce_du", stream);
+      rank_reduce_du<<<grid, 256, 0, stream>>>(w.dub_part, w.dua_part, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.TA,
+                                             w.TA, w.tl, w.du_bf, w.duT3, grad_params + (int64_t)H * D);
+    }
     GD3_CHECK_LAUNCH();
-    transpose_w1<<<(unsigned)ceil_div<int64_t>(D * H, 256), 256, 0, stream>>>(W1, (int)D, w.W1T);
+    {
+      GD3_PROF("transpose_w1", stream);
+      transpose_w1<<<(unsigned)ceil_div<int64_t>(D * H, 256), 256, 0, stream>>>(W1, (int)D, w.W1T);
+    }
     GD3_CHECK_LAUNCH();
   }
   {
@@ -721,13 +796,13 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     if ((rc = tc::make_tmap_bf16(&t_w1t, w.W1T, H, D, 1, H, 0, 256))) return rc;
     tc::EpiStoreF32::Params e1{grad_feats, (int)R, (int)D, D, 0, 1.0f, nullptr};
     tc::GemmShape s1{(int)R, (int)D, H, 1};
-    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_du, t_w1t, s1, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>("rank_df_gemm", t_du, t_w1t, s1, e1, stream))) return rc;
     // d W1 (H x D) = sum over sets of du_s^T f_s: one batch entry per set, accumulated atomically (split-K)
-    if ((rc = tc::make_tmap_bf16(&t_dut, w.duT_bf, K, H, S, w.ldr, w.ldk, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_ft, w.FT, K, D, S, w.ldr, w.ldk, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_dut, w.duT3, 3 * w.tl.gl, H, w.groups, w.tl.ld, 3 * w.tl.gl, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_ft, w.FT3, 3 * w.tl.gl, D, w.groups, w.tl.ld, 3 * w.tl.gl, 256))) return rc;
     EpiAtomicAddF32::Params e2{grad_params, H, (int)D, D};
-    tc::GemmShape s2{H, (int)D, (int)K, (int)S};
-    if ((rc = tc::launch_gemm<256, 4, EpiAtomicAddF32>(t_dut, t_ft, s2, e2, stream))) return rc;
+    tc::GemmShape s2{H, (int)D, (int)(3 * w.tl.gl), w.groups};
+    if ((rc = tc::launch_gemm<256, 4, EpiAtomicAddF32>("rank_dw1_gemm", t_dut, t_ft, s2, e2, stream))) return rc;
   }
   return GD3_OK;
 }

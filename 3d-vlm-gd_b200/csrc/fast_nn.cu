@@ -150,11 +150,20 @@ int nn_rows(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t D,
   y = ceil_div(db_tiles, tiles_per_cta);
   dim3 grid(q_tiles, y);
   if (dist == 0)
-    nn_rows_kernel<0><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keys);
+    {
+      GD3_PROF("nn_rows_kernel", stream);
+      nn_rows_kernel<0><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keys);
+    }
   else
-    nn_rows_kernel<1><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keys);
+    {
+      GD3_PROF("nn_rows_kernel", stream);
+      nn_rows_kernel<1><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keys);
+    }
   GD3_CHECK_LAUNCH();
-  nn_unpack_kernel<<<(int)ceil_div<int64_t>(nq, 256), 256, 0, stream>>>(keys, out, (int)nq);
+  {
+    GD3_PROF("nn_unpack_kernel", stream);
+    nn_unpack_kernel<<<(int)ceil_div<int64_t>(nq, 256), 256, 0, stream>>>(keys, out, (int)nq);
+  }
   GD3_CHECK_LAUNCH();
   return GD3_OK;
 }

@@ -3,7 +3,13 @@
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
+#include <cstring>
+
+#include <atomic>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace gd3 {
 
@@ -16,6 +22,41 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+}  // namespace
+
+ProfScope::ProfScope(const char* n, cudaStream_t s) : name(n), stream(s), slot(-1) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{n, nullptr, nullptr};
+  if (!g_prof_pool.empty()) {
+    r.a = g_prof_pool.back().first;
+    r.b = g_prof_pool.back().second;
+    g_prof_pool.pop_back();
+  } else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+    return;
+  }
+  cudaEventRecord(r.a, s);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, stream);
+}
 
 namespace tc {
 
@@ -73,6 +114,43 @@ using namespace gd3;
 extern "C" {
 
 int gd3_version(void) { return GD3_VERSION; }
+
+long long gd3_launch_count(void) { return gd3::g_launches.load(); }
+
+void gd3_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(gd3::g_prof_mu);
+  gd3::g_prof_on = on != 0;
+}
+
+// Writes one line per kernel name: "<name> <launches> <total_ms>\n".  Synchronises the device, then
+// (when a buffer is given) clears the records.  Returns the number of bytes needed (excluding the terminator).
+size_t gd3_profile_read(char* buf, size_t buf_bytes) {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(gd3::g_prof_mu);
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : gd3::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += ms;
+    }
+  }
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && buf_bytes) {
+    const size_t n = out.size() < buf_bytes - 1 ? out.size() : buf_bytes - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+    for (auto& r : gd3::g_prof) gd3::g_prof_pool.emplace_back(r.a, r.b);   // recycle the events
+    gd3::g_prof.clear();
+  }
+  return out.size();
+}
 const char* gd3_last_error(void) { return gd3::last_error(); }
 
 int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
@@ -86,8 +164,8 @@ int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64
   if ((rc = tc::make_tmap_bf16(&tb, B, K, N, batch, ldb, N * ldb, tile_n))) return rc;
   tc::EpiStoreF32::Params ep{C, (int)M, (int)N, ldc, M * ldc, 1.0f, nullptr};
   tc::GemmShape s{(int)M, (int)N, (int)K, (int)batch};
-  if (tile_n == 256) return tc::launch_gemm<256, 4, tc::EpiStoreF32>(ta, tb, s, ep, stream);
-  return tc::launch_gemm<128, 8, tc::EpiStoreF32>(ta, tb, s, ep, stream);
+  if (tile_n == 256) return tc::launch_gemm<256, 4, tc::EpiStoreF32>("debug_gemm", ta, tb, s, ep, stream);
+  return tc::launch_gemm<128, 8, tc::EpiStoreF32>("debug_gemm", ta, tb, s, ep, stream);
 }
 
 }  // extern "C"

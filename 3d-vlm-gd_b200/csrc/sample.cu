@@ -174,13 +174,19 @@ int gd3_sample_tokens_fwd(const void* tokens, int dtype, int64_t L, int64_t P, i
   dim3 grid((unsigned)K, (unsigned)P);
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
   if (dtype == GD3_DTYPE_F32)
-    sample_fwd_kernel<float><<<grid, threads, 0, stream>>>(static_cast<const float*>(tokens), (int)L, sL, sP, sN, sC,
+    {
+      GD3_PROF("sample_fwd_kernel", stream);
+      sample_fwd_kernel<float><<<grid, threads, 0, stream>>>(static_cast<const float*>(tokens), (int)L, sL, sP, sN, sC,
                                                           kp, (int)K, (int)C, g, normalize, out, oP, oK, oC,
                                                           inv_norm);
+    }
   else
-    sample_fwd_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(tokens), (int)L,
+    {
+      GD3_PROF("sample_fwd_kernel", stream);
+      sample_fwd_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(tokens), (int)L,
                                                                   sL, sP, sN, sC, kp, (int)K, (int)C, g, normalize,
                                                                   out, oP, oK, oC, inv_norm);
+    }
   GD3_CHECK_LAUNCH();
   return GD3_OK;
 }
@@ -199,8 +205,11 @@ int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t
   if (rc) return rc;
   dim3 grid((unsigned)K, (unsigned)P);
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
-  sample_bwd_kernel<<<grid, threads, 0, stream>>>(grad_out, gP, gK, gC, out, oP, oK, oC, inv_norm, kp, (int)K, (int)C,
+  {
+    GD3_PROF("sample_bwd_kernel", stream);
+    sample_bwd_kernel<<<grid, threads, 0, stream>>>(grad_out, gP, gK, gC, out, oP, oK, oC, inv_norm, kp, (int)K, (int)C,
                                                   g, normalize, (int)L, grad_tokens, sL, sP, sN, sC);
+  }
   GD3_CHECK_LAUNCH();
   return GD3_OK;
 }

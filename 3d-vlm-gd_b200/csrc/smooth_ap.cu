@@ -255,8 +255,11 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
   GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int) * P, stream));
   {
     dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)P, 2);
-    ap_prepare<<<grid, 256, 0, stream>>>(d1, d2, (int)K, (int)C, w.ldc, w.ldk, w.A3, w.B3, backward ? w.d1T : nullptr,
+    {
+      GD3_PROF("ap_prepare", stream);
+      ap_prepare<<<grid, 256, 0, stream>>>(d1, d2, (int)K, (int)C, w.ldc, w.ldk, w.A3, w.B3, backward ? w.d1T : nullptr,
                                          backward ? w.d2T : nullptr);
+    }
     GD3_CHECK_LAUNCH();
   }
   int rc;
@@ -269,20 +272,29 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
       return rc;
     tc::EpiStoreF32::Params ep{w.sim, (int)K, (int)K, w.lds, K * (int64_t)w.lds, 1.0f, nullptr};
     tc::GemmShape s{(int)K, (int)K, 3 * w.ldc, (int)P};
-    if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>(ta, tb, s, ep, stream))) return rc;
+    if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>("ap_sim_gemm", ta, tb, s, ep, stream))) return rc;
   }
   {
     dim3 grid((unsigned)K, (unsigned)P);
-    ap_rows<<<grid, 128, sizeof(float) * K, stream>>>(w.sim, w.lds, pts3d_1, pts3d_2, (int)K, variant, 1.f / temp,
+    {
+      GD3_PROF("ap_rows", stream);
+      ap_rows<<<grid, 128, sizeof(float) * K, stream>>>(w.sim, w.lds, pts3d_1, pts3d_2, (int)K, variant, 1.f / temp,
                                                       thr_neg, thr_pos, backward ? w.dS : nullptr, w.ldk, w.loss_acc,
                                                       w.qcount);
+    }
     GD3_CHECK_LAUNCH();
-    ap_finalize<<<(unsigned)ceil_div<int64_t>(P, 128), 128, 0, stream>>>(w.loss_acc, w.qcount, loss, w.scale, (int)P);
+    {
+      GD3_PROF("ap_finalize", stream);
+      ap_finalize<<<(unsigned)ceil_div<int64_t>(P, 128), 128, 0, stream>>>(w.loss_acc, w.qcount, loss, w.scale, (int)P);
+    }
     GD3_CHECK_LAUNCH();
   }
   if (backward) {
     dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)ceil_div<int64_t>(K, 32), (unsigned)P);
-    transpose_bf16<<<grid, 256, 0, stream>>>(w.dS, w.dST, (int)K, w.ldk);
+    {
+      GD3_PROF("transpose_bf16", stream);
+      transpose_bf16<<<grid, 256, 0, stream>>>(w.dS, w.dST, (int)K, w.ldk);
+    }
     GD3_CHECK_LAUNCH();
     CUtensorMap t_ds, t_dst, t_d1t, t_d2t;
     if ((rc = tc::make_tmap_bf16(&t_ds, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
@@ -292,8 +304,8 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
     tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, w.scale};
     tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, w.scale};
-    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_ds, t_d2t, s, e1, stream))) return rc;
-    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>(t_dst, t_d1t, s, e2, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>("ap_grad_gemm", t_ds, t_d2t, s, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>("ap_grad_gemm", t_dst, t_d1t, s, e2, stream))) return rc;
   }
   return GD3_OK;
 }

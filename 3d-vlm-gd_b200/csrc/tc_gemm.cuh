@@ -308,7 +308,7 @@ struct GemmShape {
 };
 
 template <int BN, int EPI_WARPS, class Epi>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
+int launch_gemm(const char* name, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
                 const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
   if (s.M <= 0 || s.N <= 0 || s.batch <= 0) return GD3_OK;
   GD3_REQUIRE(s.K > 0, "tc_gemm: K must be positive");
@@ -325,8 +325,11 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape&
   int grid = num_sms();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (total < grid) grid = static_cast<int>(total);
-  kern<<<grid, (PRODUCER_WARPS + EPI_WARPS) * 32, SMEM, stream>>>(tmA, tmB, tiles_m, tiles_n, s.batch,
-                                                                ceil_div(s.K, BK), ep);
+  {
+    GD3_PROF(name, stream);
+    kern<<<grid, (PRODUCER_WARPS + EPI_WARPS) * 32, SMEM, stream>>>(tmA, tmB, tiles_m, tiles_n, s.batch,
+                                                                  ceil_div(s.K, BK), ep);
+  }
   GD3_CHECK_LAUNCH();
   return GD3_OK;
 }

@@ -17,6 +17,9 @@ _i64, _int, _vp, _sz, _f32 = _c.c_int64, _c.c_int, _c.c_void_p, _c.c_size_t, _c.
 SYMBOLS = {
     'gd3_version': (_int, []),
     'gd3_last_error': (_c.c_char_p, []),
+    'gd3_launch_count': (_c.c_longlong, []),
+    'gd3_profile_enable': (None, [_int]),
+    'gd3_profile_read': (_sz, [_c.c_char_p, _sz]),
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     'gd3_cost_kl_group_size': (_i64, [_i64, _i64, _i64, _i64]),
@@ -135,3 +138,26 @@ def debug_gemm_bf16(A, B, tile_n=256):
     with torch.cuda.device(A.device):
         check(lib.gd3_debug_gemm_bf16(ptr(A), ptr(B), ptr(C), M, N, K, b, K, K, N, tile_n, stream_ptr()))
     return C
+
+
+def launch_count():
+    """Number of CUDA kernels lib3dgd has launched in this process."""
+    return int(load().gd3_launch_count())
+
+
+def profile_enable(on=True):
+    load().gd3_profile_enable(int(bool(on)))
+
+
+def profile_read():
+    """{kernel name: (launches, total_ms)} since the last read (synchronises the device)."""
+    lib = load()
+    n = lib.gd3_profile_read(None, 0)
+    buf = ctypes.create_string_buffer(int(n) + 64)
+    # records were consumed by the sizing call only if a buffer was given; call again with the buffer
+    lib.gd3_profile_read(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(' ', 2)
+        out[name] = (int(cnt), float(ms))
+    return out

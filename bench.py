@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Headline benchmark: image-pairs/s of the fused geometric-distillation losses, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1]
+
+A step = one pass of the hot path (cost-volume KL + Smooth-AP + depth ranking on both views + cross-view
+L1, incl. bilinear keypoint sampling) over one batch of synthetic pairs.  With
+N GPUs (launched under torchrun, one rank per GPU) every rank processes its own batch: image pairs are
+independent, so there is no data-path collective and the scaling is weak.
+
+Rank 0 prints ONE JSON line (see the contract in the task description):
+  value      pairs/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e        pairs/s through gd3.pipeline.distillation_step from PINNED HOST buffers, H2D copies of all
+             inputs and a D2H read of the losses inside the timed region
+  roofline   the tensor-core GEMM with the largest share of the step (algorithmic FLOPs / event time / peak)
+  cpu_baseline  the CPU oracle (port of the reference's per-pair flow) timed on a bounded sample, rank 0, N = 1
+``--impl reference`` times that CPU port alone (all host threads), one pair per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, '3d-vlm-gd_b200')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = 'image_pairs_per_s_distill_losses_fwd_bwd'
+UNIT = 'pairs/s'
+WORKLOADS = {
+    'cfg1': dict(N=256, C=384, K=128, grid=(16, 16), P=1, variant='mast3r', cfg_id=1,
+                 desc='ViT-S/14 224px (256 tokens x 384), K=128 keypoints, MASt3R-teacher cost volume'),
+    'cfg2': dict(N=1024, C=768, K=512, grid=(32, 32), P=32, variant='mast3r', cfg_id=2,
+                 desc='DINOv2 ViT-B/14 448px (1024 tokens x 768), K=512 keypoints, MASt3R-teacher cost volume'),
+    'cfg4': dict(N=1369, C=1024, K=300, grid=(37, 37), P=64, variant='vggt', cfg_id=4,
+                 desc='ViT-L/14 518px (1369 tokens x 1024), K=300 keypoints, VGGT-teacher cost volume'),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p.get('hbm_gbs'), bf16_tflops=p.get('bf16_tflops'),
+                    bf16_tflops_sustained=p.get('bf16_tflops_sustained'), source='measured')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.Q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def algorithmic_work(cfg):
+    """Per-pair algorithmic work."""
+    N, C, K = cfg['N'], cfg['C'], cfg['K']
+    return dict(k1_flops=6.0 * N * N * C, k2_flops=6.0 * K * K * C,
+                k1_bytes=2.0 * N * N * 4 + 2.0 * N * C * 2 + 2.0 * N * C * 2)
+
+
+# per-launch algorithmic FLOPs of the tensor-core GEMMs, keyed by the library's profile names
+def gemm_flops_per_step(cfg, P):
+    N, C, K = cfg['N'], cfg['C'], cfg['K']
+    return {
+        'kl_pass1_gemm': 2.0 * N * N * C * P,          # z = a b^T, once
+        'kl_grad_gemm': 4.0 * N * N * C * P,           # dz b and dz^T a (two launches per group)
+        'ap_sim_gemm': 2.0 * K * K * C * P,            # algorithmic (the 3-panel split executes 3x)
+        'ap_grad_gemm': 4.0 * K * K * C * P,
+        'rank_u_gemm': 2.0 * (2 * P * K) * C * 128,
+        'rank_df_gemm': 2.0 * (2 * P * K) * C * 128,
+        'rank_dw1_gemm': 2.0 * (2 * P * K) * C * 128,
+    }
+
+
+def run_ours(args):
+    from gd3 import _lib, pipeline
+    import bench_common
+    rank, world, local = dist_setup(args.gpus)
+    cfg = dict(WORKLOADS[args.workload])
+    if args.pairs:
+        cfg['P'] = args.pairs
+    P = cfg['P']
+    dev = torch.device('cuda', local)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    # ---- synthetic inputs: every rank gets its own seeded batch (pair indices rank*P ...) ----
+    host = bench_common.make_batch(cfg, cfg_id=cfg['cfg_id'], pair0=rank * P)
+    host = bench_common.to_device(host, 'cpu', feature_dtype=torch.bfloat16)
+    pinned = {}
+    for k, v in host.items():
+        if torch.is_tensor(v):
+            pinned[k] = v.contiguous().pin_memory()
+    head_dev = {n: (t.to(dev) if torch.is_tensor(t) else t) for n, t in host['head'].items()}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    resident['head'] = head_dev
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    in_bytes_dev = h2d_bytes
+
+    def step(batch):
+        return pipeline.distillation_step(batch, variant=cfg['variant'], grid=cfg['grid'], backward=True,
+                                          pairs_per_group=args.pairs_per_group)
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        out = step(resident)
+    barrier(world)
+
+    # ---- timed region 1: inputs resident in HBM; per-kernel CUDA events on the launching stream ----
+    launches0 = _lib.launch_count()
+    _lib.profile_enable(True)
+    _lib.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier(world)
+        e0.record()
+        for _ in range(args.steps):
+            out = step(resident)
+        e1.record()
+        barrier(world)
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    launches = _lib.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    value = world * P / (ms_step * 1e-3)
+    clocks = clk.summary()
+
+    # ---- timed region 2 (e2e): pinned host -> device copies of every input + D2H of the losses, each step ----
+    def e2e_step():
+        b = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        b['head'] = head_dev
+        o = step(b)
+        res = torch.stack([o['kl'], o['ap'], o['rank'], o['l1']]).cpu()   # D2H, synchronises
+        return res
+    for _ in range(2):
+        res = e2e_step()
+    barrier(world)
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    barrier(world)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / e2e_steps
+    d2h_bytes = res.numel() * res.element_size()
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant tensor-core kernel ----
+    flops = gemm_flops_per_step(cfg, P)
+    tot_prof_ms = sum(ms for _, ms in prof.values()) or 1.0
+    shares = {k: dict(launches=c, ms_per_step=ms / args.steps, share=ms / tot_prof_ms) for k, (c, ms) in prof.items()}
+    gemms = {k: v for k, v in prof.items() if k in flops}
+    top = max(gemms, key=lambda k: gemms[k][1]) if gemms else None
+    roofline = None
+    if top:
+        cnt, ms = gemms[top]
+        per_launch_ms = ms / cnt
+        per_launch_flops = flops[top] * args.steps / cnt
+        achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
+        peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
+        roofline = dict(kernel=top, bound='tensor', achieved=round(achieved, 2), peak=peak, unit='TFLOP/s',
+                        frac=round(achieved / peak, 4), traffic=None, peak_source=peaks['source'] + ' (sustained cuBLAS bf16)',
+                        share_of_step=round(ms / tot_prof_ms, 4), launches=cnt,
+                        us_per_launch=round(per_launch_ms * 1e3, 2))
+    work = algorithmic_work(cfg)
+    step_tflops = (work['k1_flops'] + work['k2_flops']) * P / (ms_step * 1e-3) / 1e12
+    peak_s = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
+
+    # ---- CPU baseline (oracle port of the reference's per-pair flow), bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(cfg, host, sample_pairs=args.cpu_pairs)
+
+    line = dict(
+        metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=round(ms_step, 4), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+        data='synthetic',
+        config=dict(workload=f"{args.workload}: {cfg['desc']}, {P} synthetic pairs per GPU",
+                    pairs_per_gpu=P, tokens=cfg['N'], channels=cfg['C'], keypoints=cfg['K'], variant=cfg['variant'],
+                    parallelism=f'dp{world} (pairs sharded, no data-path collective)',
+                    l2='inputs larger than L2: %.0f MB of teacher volumes + features are read per step' % (in_bytes_dev / 1e6),
+                    losses='cost-volume KL + Smooth-AP + depth ranking (2 views) + cross-view L1, fwd+bwd'),
+        clocks=clocks,
+        e2e=dict(value=round(world * P / (e2e_ms * 1e-3), 2), unit=UNIT, h2d_bytes_per_step=int(h2d_bytes),
+                 d2h_bytes_per_step=int(d2h_bytes), ms_per_step=round(e2e_ms, 3), steps=e2e_steps),
+        gpu_launches=int(launches),
+        roofline=roofline,
+        step_tensor_fraction=dict(algorithmic_tflops=round(step_tflops, 2), peak=peak_s,
+                                  frac=round(step_tflops / peak_s, 4),
+                                  note='(K1 + K2 algorithmic FLOPs of SURVEY 8-d) / whole-step time'),
+        kernels={k: dict(launches=v['launches'], us_per_step=round(v['ms_per_step'] * 1e3, 1), share=round(v['share'], 4))
+                 for k, v in sorted(shares.items(), key=lambda kv: -kv[1]['share'])},
+        cpu_baseline=cpu,
+    )
+    print(json.dumps(line))
+
+
+def cpu_baseline(cfg, host, sample_pairs=2):
+    import bench_common
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    f32 = bench_common.to_device(host, 'cpu', feature_dtype=torch.float32)
+    bench_common.oracle_step(f32, cfg, pairs=1)   # warm-up (allocator, thread pool)
+    t0 = time.perf_counter()
+    bench_common.oracle_step(f32, cfg, pairs=sample_pairs)
+    dt = time.perf_counter() - t0
+    return dict(value=round(sample_pairs / dt, 4), unit=UNIT, cores=torch.get_num_threads(), kind='port',
+                sample=f'{sample_pairs} pairs of the same workload through the CPU oracle (port of the reference '
+                       f'PyTorch flow, fp32, one pair per call), {dt:.1f} s')
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path: Python/PyTorch functions that cannot travel to
+    the GPU box, so the oracle port (validated against the live functions, tests/golden) is timed."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import bench_common
+    cfg = dict(WORKLOADS[args.workload])
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n = max(1, args.warmup + args.steps)
+    pool = min(n, 4)    # a few distinct pairs, cycled
+    host = bench_common.make_batch(cfg, cfg_id=cfg['cfg_id'], pairs=pool)
+
+    def one(i):
+        sl = {k: (v[i % pool:i % pool + 1] if torch.is_tensor(v) else v) for k, v in host.items()}
+        return bench_common.oracle_step(sl, cfg, pairs=1)
+    for i in range(args.warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(args.warmup + i)
+    dt = time.perf_counter() - t0
+    ms_step = dt * 1e3 / args.steps
+    value = 1.0 / (ms_step * 1e-3)
+    line = dict(impl='reference', metric=METRIC, value=round(value, 4), unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(ms_step, 2), higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=f"{args.workload}: {cfg['desc']}; each step = 1 pair (the reference's batch size)",
+                            tokens=cfg['N'], channels=cfg['C'], keypoints=cfg['K'], variant=cfg['variant']),
+                cpu_baseline=dict(value=round(value, 4), unit=UNIT, cores=torch.get_num_threads(), kind='port',
+                                  sample='1 pair per step through the CPU oracle (port of the reference PyTorch flow)'),
+                e2e=dict(value=round(value, 4), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU (default: the workload\'s)')
+    ap.add_argument('--pairs-per-group', type=int, default=0)
+    ap.add_argument('--cpu-pairs', type=int, default=2)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device (there is no CPU fallback for the product path)')
+        run_ours(args)
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -51,6 +51,13 @@ extern "C" {
 int gd3_version(void);
 const char* gd3_last_error(void);
 
+/* Instrumentation (not reference interfaces): number of kernels this library has launched in the
+ * process, and optional per-kernel CUDA-event timing on the launching stream.  gd3_profile_read
+ * synchronises the device and writes "<kernel> <launches> <total_ms>\n" lines, then resets. */
+long long gd3_launch_count(void);
+void gd3_profile_enable(int on);
+size_t gd3_profile_read(char* buf, size_t buf_bytes);
+
 /* ------------------------------------------------------------------------------------------
  * Reciprocal nearest neighbours.  Replaces bruteforce_reciprocal_nns (mast3r/fast_nn.py:16-70):
  * nn_A[i] = argbest_j score(A_i, B_j), nn_B[j] = argbest_i score(A_i, B_j), lowest index on ties.
