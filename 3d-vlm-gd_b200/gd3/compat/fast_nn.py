@@ -20,6 +20,12 @@ def _is_cuda_device(device):
     return isinstance(device, str) and device.startswith('cuda')
 
 
+def _need_gpu(device):
+    if not _is_cuda_device(device):
+        raise _lib.Gd3Error(f'gd3 fast_nn has no CPU path (device={device!r})')
+    _lib.require_cuda()
+
+
 def _to_device(x, device):
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(x)
@@ -35,8 +41,7 @@ def bruteforce_reciprocal_nns(A, B, device='cuda', block_size=None, dist='l2'):
     """
     if dist not in ('l2', 'dot'):
         raise ValueError(f'Unknown {dist=}')
-    if not _is_cuda_device(device):
-        raise _lib.Gd3Error(f'gd3 fast_nn has no CPU path (device={device!r})')
+    _need_gpu(device)
     A = _to_device(A, device)
     B = _to_device(B, device)
     nn_A, nn_B = _lib.reciprocal_nn(A, B, dist=dist)
@@ -47,8 +52,7 @@ class cdistMatcher:
     """Mirror of ``mast3r/fast_nn.py:73-84``: a brute-force 'tree' over device-resident points."""
 
     def __init__(self, db_pts, device='cuda'):
-        if not _is_cuda_device(device):
-            raise _lib.Gd3Error(f'gd3 fast_nn has no CPU path (device={device!r})')
+        _need_gpu(device)
         self.db_pts = db_pts.to(device).contiguous().float()
         self.device = device
 
@@ -100,8 +104,7 @@ def fast_reciprocal_NNs(pts1, pts2, subsample_or_initxy1=8, ret_xy=True, pixel_t
     if not ('dist' in matcher_kw or 'block_size' in matcher_kw or _is_cuda_device(device)):
         raise _lib.Gd3Error('the scipy-KDTree CPU branch of fast_reciprocal_NNs is not provided '
                             '(pass device="cuda" or dist=/block_size=)')
-    if not _is_cuda_device(device):
-        raise _lib.Gd3Error(f'gd3 fast_nn has no CPU path (device={device!r})')
+    _need_gpu(device)
 
     pts1 = _to_device(pts1, device).reshape(-1, DIM1).contiguous().float()
     pts2 = _to_device(pts2, device).reshape(-1, DIM2).contiguous().float()
