@@ -33,7 +33,7 @@ constexpr int TILE = 128;        // a / b tile edge
 constexpr int WARPS = 16;
 constexpr int B_PER_WARP = TILE / WARPS;   // 8
 
-// sum over the 16 lanes of a half warp; `mask` names exactly that half so the two halves may diverge
+// sum over the 16 lanes of a half warp (xor offsets < 16 never cross the halves)
 __device__ __forceinline__ float half_sum(float v, unsigned mask) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
@@ -68,49 +68,74 @@ struct PairOut {
   float m1, m2;      // mean_h(q), mean_h(q * xh), q = w2 * gam * gp
 };
 
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// tanh(x) = 1 - 2 / (1 + e^{2x}); saturates correctly when e^{2x} over/underflows
+__device__ __forceinline__ float fast_tanh(float x) {
+  return 1.f - 2.f * fast_rcp(1.f + fast_ex2(x * (2.f * 1.4426950408889634f)));
+}
+
 // Head on one pre-activation difference hc (already mean-free over h).  erf by Abramowitz-Stegun 7.1.26
 // (|err| < 1.5e-7), sharing exp(-y^2/2) between erf and the Gaussian density needed by GELU'.
+// Both half warps of a warp always execute this together (an invalid pair is masked later), so the
+// xor-shuffles with offsets < 16 use the full mask and stay inside each half.
 template <bool GRAD>
 __device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadConst& hcst, float ln_eps, int use_tanh,
-                                          unsigned mask, PairOut& o) {
+                                          PairOut& o) {
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < HPL; ++i) ss = fmaf(hc[i], hc[i], ss);
-  ss = half_sum(ss, mask);
-  o.rstd = rsqrtf(ss * (1.f / H) + ln_eps);
+  ss = half_sum(ss, 0xffffffffu);
+  o.rstd = rsqrtf(fmaf(ss, 1.f / H, ln_eps));
   float acc = 0.f, m1 = 0.f, m2 = 0.f;
 #pragma unroll
   for (int i = 0; i < HPL; ++i) {
     const float xh = hc[i] * o.rstd;
     const float y = fmaf(xh, hcst.gam[i], hcst.bet[i]);
     const float z = y * 0.70710678118654752f;
-    const float az = fabsf(z);
-    const float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
+    const float t = fast_rcp(fmaf(0.3275911f, fabsf(z), 1.f));
     float poly = fmaf(t, 1.061405429f, -1.453152027f);
     poly = fmaf(t, poly, 1.421413741f);
     poly = fmaf(t, poly, -0.284496736f);
     poly = fmaf(t, poly, 0.254829592f);
     poly *= t;
-    const float e = exp2f(-z * z * 1.4426950408889634f);      // exp(-z^2) = exp(-y^2 / 2)
+    const float e = fast_ex2(z * z * -1.4426950408889634f);      // exp(-z^2) = exp(-y^2 / 2)
     const float erf_abs = fmaf(-poly, e, 1.f);
-    const float phi = fmaf(0.5f, copysignf(erf_abs, z), 0.5f);  // standard normal CDF at y
+    const float phi = fmaf(0.5f, copysignf(erf_abs, z), 0.5f);    // standard normal CDF at y
     const float g = y * phi;
     acc = fmaf(hcst.w2[i], g, acc);
     o.xh[i] = xh;
     o.g[i] = g;
     if (GRAD) {
-      const float gp = fmaf(y * e, 0.3989422804014327f, phi);   // Phi(y) + y * pdf(y)
+      const float gp = fmaf(y * e, 0.3989422804014327f, phi);     // Phi(y) + y * pdf(y)
       const float q = hcst.w2[i] * hcst.gam[i] * gp;
       o.gp[i] = gp;
       m1 += q;
       m2 = fmaf(q, xh, m2);
     }
   }
-  acc = half_sum(acc, mask) + hcst.b2;
-  o.s = use_tanh ? tanhf(acc) : acc;
+  // the three reductions are independent: one shuffle phase with three interleaved chains
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (GRAD) {
+      m1 += __shfl_xor_sync(0xffffffffu, m1, off);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+    }
+  }
+  acc += hcst.b2;
+  o.s = use_tanh ? fast_tanh(acc) : acc;
   if (GRAD) {
-    o.m1 = half_sum(m1, mask) * (1.f / H);
-    o.m2 = half_sum(m2, mask) * (1.f / H);
+    o.m1 = m1 * (1.f / H);
+    o.m2 = m2 * (1.f / H);
   }
 }
 
@@ -145,7 +170,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
   float* red = da + TILE;                 // cross-warp reduction of parameter gradients
   const int set = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
-  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
   const int K = p.K;
   const float* U = p.u + (int64_t)set * K * H;
   const float* Dp = p.depth + (int64_t)set * K;
@@ -198,43 +222,44 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
         m += vb[i];
         dub[i] = 0.f;
       }
-      m = half_sum(m, hmask) * (1.f / H);
+      m = half_sum(m, 0xffffffffu) * (1.f / H);
 #pragma unroll
       for (int i = 0; i < HPL; ++i) vb[i] = vb[i] - m + bb[i];
       if (b_ok) d_b = Dp[b];
     }
+#pragma unroll 1
     for (int t = 0; t < TILE / 2; ++t) {
       // staggered a index: at any step the 32 half-warps of the CTA work on 32 different rows
       const int r = 2 * ((t + 4 * warp) & (TILE / 2 - 1)) + half;
       const int a = ta * TILE + r;
+      const float dd = d_b - da[r];
       bool valid = b_ok && a < K;
-      float dd = 0.f;
-      if (valid) {
-        dd = d_b - da[r];
-        valid = (p.mode == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr);
-      }
-      if (valid) {
+      valid = valid && ((p.mode == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr));
+      // both halves run the same instruction stream (98 % of the pairs are valid); an invalid pair is
+      // masked out of every accumulation below.  Skip only when neither half has work.
+      if (__any_sync(0xffffffffu, valid)) {
         float hcv[HPL];
         const float4 a0 = *reinterpret_cast<const float4*>(va + r * H + 4 * l16);
         const float4 a1 = *reinterpret_cast<const float4*>(va + r * H + 64 + 4 * l16);
         hcv[0] = vb[0] - a0.x; hcv[1] = vb[1] - a0.y; hcv[2] = vb[2] - a0.z; hcv[3] = vb[3] - a0.w;
         hcv[4] = vb[4] - a1.x; hcv[5] = vb[5] - a1.y; hcv[6] = vb[6] - a1.z; hcv[7] = vb[7] - a1.w;
         PairOut o;
-        head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, hmask, o);
+        head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
         const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
         float l, dl;
         if (p.mode == 0) {
-          const float ex = expf(-sg * o.s);
-          l = logf(1.f + ex);
-          dl = -sg * ex / (1.f + ex);
+          const float ex = fast_ex2(-sg * o.s * 1.4426950408889634f);
+          l = __logf(1.f + ex);
+          dl = -sg * ex * fast_rcp(1.f + ex);
         } else {
           const float m = p.margin - sg * o.s;
           l = fmaxf(m, 0.f);
           dl = (m > 0.f) ? -sg : 0.f;
         }
-        if (l16 == 0) loss_local += l;
+        loss_local += (valid && l16 == 0) ? l : 0.f;
         if (GRAD) {
-          const float dout = dl * (p.use_tanh ? (1.f - o.s * o.s) : 1.f) * inv_cnt;   // d total / d (w2.g + b2)
+          // d total / d (w2.g + b2); zero for a masked pair, which zeroes every contribution below
+          const float dout = valid ? dl * (p.use_tanh ? (1.f - o.s * o.s) : 1.f) * inv_cnt : 0.f;
           db2 += (l16 == 0) ? dout : 0.f;
           const float coef = dout * o.rstd;
           float dh[HPL];
@@ -244,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
             dw2[i] = fmaf(dout, o.g[i], dw2[i]);
             dbet[i] = fmaf(dout, pg, dbet[i]);
             dgam[i] = fmaf(dout * pg, o.xh[i], dgam[i]);
-            dh[i] = coef * (pg * hc.gam[i] - o.m1 - o.xh[i] * o.m2);
+            dh[i] = coef * (fmaf(pg, hc.gam[i], -o.m1) - o.xh[i] * o.m2);
             dub[i] += dh[i];
           }
           float4* q0 = reinterpret_cast<float4*>(dua + r * H + 4 * l16);
@@ -342,7 +367,6 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
   const int k = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half;
-  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
   const int K = p.K;
   const int sb = 2 * pair, sa = 2 * pair + 1;
   HeadConst hc;
@@ -373,12 +397,12 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
     hcv[i] = ok ? p.u[((int64_t)sb * K + k) * H + h] - p.u[((int64_t)sa * K + k) * H + h] + p.b1[h] : 0.f;
     m += hcv[i];
   }
-  m = half_sum(m, hmask) * (1.f / H);
+  m = half_sum(m, 0xffffffffu) * (1.f / H);
 #pragma unroll
   for (int i = 0; i < HPL; ++i) hcv[i] -= m;
   (void)bb;
   PairOut o;
-  head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, hmask, o);
+  head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
   if (ok) {
     const float tgt = tanhf(p.depth[(int64_t)sb * K + k] - p.depth[(int64_t)sa * K + k]);
     const float diff = o.s - tgt;
