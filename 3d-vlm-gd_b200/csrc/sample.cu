@@ -130,6 +130,135 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fast path: channel-contiguous tokens (sC == 1, C % 4 == 0, 16-byte aligned rows) and channel-contiguous
+// output.  One warp per keypoint, 8 keypoints per CTA; each lane owns float4 channel groups, keeps the sampled
+// row in registers for the normalisation (C <= 4096) and issues 128-bit loads / stores only.
+// ------------------------------------------------------------------------------------------
+constexpr int FAST_MAX_IT = 32;    // float4 groups per lane: C <= 32 lanes * 4 * 32 = 4096
+
+template <class T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(bf16_bits_to_float(v.x & 0xFFFFu), bf16_bits_to_float(v.x >> 16),
+                     bf16_bits_to_float(v.y & 0xFFFFu), bf16_bits_to_float(v.y >> 16));
+}
+
+template <class T, int NIT>
+__global__ void __launch_bounds__(256)
+    sample_fwd_fast(const T* __restrict__ tok, int L, int64_t sL, int64_t sP, int64_t sN, const float* __restrict__ kp,
+                    int K, int C, SampleGeom g, int normalize, float* __restrict__ out, int64_t oP, int64_t oK,
+                    float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), p = blockIdx.y;
+  if (k >= K) return;
+  const float x = kp[((int64_t)p * K + k) * 2 + 0], y = kp[((int64_t)p * K + k) * 2 + 1];
+  const Taps t = make_taps(g, x, y);
+  const float invL = 1.f / (float)L;
+  float4 acc[NIT];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int c = (it * 32 + lane) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+      for (int l = 0; l < L; ++l) {
+        const T* base = tok + l * sL + p * sP + c;
+        const float4 v00 = ld4(base + t.i00 * sN), v01 = ld4(base + t.i01 * sN);
+        const float4 v10 = ld4(base + t.i10 * sN), v11 = ld4(base + t.i11 * sN);
+        // same accumulation order as grid_sample: nw, ne, sw, se
+        float4 v;
+        v.x = v00.x * t.w00; v.x += v01.x * t.w01; v.x += v10.x * t.w10; v.x += v11.x * t.w11;
+        v.y = v00.y * t.w00; v.y += v01.y * t.w01; v.y += v10.y * t.w10; v.y += v11.y * t.w11;
+        v.z = v00.z * t.w00; v.z += v01.z * t.w01; v.z += v10.z * t.w10; v.z += v11.z * t.w11;
+        v.w = v00.w * t.w00; v.w += v01.w * t.w01; v.w += v10.w * t.w10; v.w += v11.w * t.w11;
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      if (L > 1) { a.x *= invL; a.y *= invL; a.z *= invL; a.w *= invL; }
+      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    acc[it] = a;
+  }
+  float inv = 1.f;
+  if (normalize) {
+    ss = warp_sum(ss);
+    inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[(int64_t)p * K + k] = inv;
+  }
+  float* o = out + p * oP + k * oK;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int c = (it * 32 + lane) * 4;
+    if (c < C)
+      *reinterpret_cast<float4*>(o + c) = make_float4(acc[it].x * inv, acc[it].y * inv, acc[it].z * inv, acc[it].w * inv);
+  }
+}
+
+// backward fast path: gradient rows and token-gradient rows are channel-contiguous fp32
+__global__ void __launch_bounds__(256)
+    sample_bwd_fast(const float* __restrict__ gout, int64_t gP, int64_t gK, const float* __restrict__ out, int64_t oP,
+                    int64_t oK, const float* __restrict__ inv_norm, const float* __restrict__ kp, int K, int C,
+                    SampleGeom g, int normalize, int L, float* __restrict__ gtok, int64_t sL, int64_t sP, int64_t sN) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5), p = blockIdx.y;
+  if (k >= K) return;
+  const float x = kp[((int64_t)p * K + k) * 2 + 0], y = kp[((int64_t)p * K + k) * 2 + 1];
+  const Taps t = make_taps(g, x, y);
+  const float* go = gout + p * gP + k * gK;
+  const float* o = out + p * oP + k * oK;
+  float dot = 0.f, inv = 1.f;
+  if (normalize) {
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(o + c), b = *reinterpret_cast<const float4*>(go + c);
+      dot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    }
+    dot = warp_sum(dot);
+    inv = inv_norm[(int64_t)p * K + k];
+  }
+  const float sc = inv / (float)L;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 gv = *reinterpret_cast<const float4*>(go + c);
+    if (normalize) {
+      const float4 a = *reinterpret_cast<const float4*>(o + c);
+      gv.x -= a.x * dot; gv.y -= a.y * dot; gv.z -= a.z * dot; gv.w -= a.w * dot;
+    }
+    gv.x *= sc; gv.y *= sc; gv.z *= sc; gv.w *= sc;
+    for (int l = 0; l < L; ++l) {
+      float* base = gtok + l * sL + p * sP + c;
+      atomicAdd(reinterpret_cast<float4*>(base + t.i00 * sN), make_float4(gv.x * t.w00, gv.y * t.w00, gv.z * t.w00, gv.w * t.w00));
+      if (t.w01 != 0.f)
+        atomicAdd(reinterpret_cast<float4*>(base + t.i01 * sN), make_float4(gv.x * t.w01, gv.y * t.w01, gv.z * t.w01, gv.w * t.w01));
+      if (t.w10 != 0.f)
+        atomicAdd(reinterpret_cast<float4*>(base + t.i10 * sN), make_float4(gv.x * t.w10, gv.y * t.w10, gv.z * t.w10, gv.w * t.w10));
+      if (t.w11 != 0.f)
+        atomicAdd(reinterpret_cast<float4*>(base + t.i11 * sN), make_float4(gv.x * t.w11, gv.y * t.w11, gv.z * t.w11, gv.w * t.w11));
+    }
+  }
+}
+
+template <class T>
+bool launch_fwd_fast(const T* tok, int L, int64_t sL, int64_t sP, int64_t sN, const float* kp, int K, int P, int C,
+                     const SampleGeom& g, int normalize, float* out, int64_t oP, int64_t oK, float* inv_norm,
+                     cudaStream_t stream) {
+  dim3 grid((unsigned)ceil_div(K, 8), (unsigned)P);
+  const int nit = ceil_div(C, 128);
+#define GD3_FWD_FAST(N)                                                                                           \
+  sample_fwd_fast<T, N><<<grid, 256, 0, stream>>>(tok, L, sL, sP, sN, kp, K, C, g, normalize, out, oP, oK, inv_norm)
+  GD3_PROF("sample_fwd_fast", stream);
+  if (nit <= 2) GD3_FWD_FAST(2);
+  else if (nit <= 4) GD3_FWD_FAST(4);
+  else if (nit <= 8) GD3_FWD_FAST(8);
+  else if (nit <= 16) GD3_FWD_FAST(16);
+  else if (nit <= FAST_MAX_IT) GD3_FWD_FAST(32);
+  else return false;
+#undef GD3_FWD_FAST
+  return true;
+}
+
 int make_geom(int64_t ph, int64_t pw, int64_t h, int64_t w, int patch, int stride, SampleGeom* g) {
   GD3_REQUIRE(ph >= 2 && pw >= 2 && patch >= 1 && stride >= 1, "sample_tokens: feature map must be at least 2 x 2 (got %lld x %lld)",
               (long long)ph, (long long)pw);
@@ -171,6 +300,25 @@ int gd3_sample_tokens_fwd(const void* tokens, int dtype, int64_t L, int64_t P, i
   SampleGeom g;
   int rc = make_geom(ph, pw, h, w, patch, stride, &g);
   if (rc) return rc;
+  {
+    // fast path: channel-contiguous source and destination, rows 16-byte aligned
+    const int esz = dtype == GD3_DTYPE_F32 ? 4 : 2;
+    const bool aligned = sC == 1 && oC == 1 && C % 4 == 0 && C <= 128 * FAST_MAX_IT &&
+                         (reinterpret_cast<uintptr_t>(tokens) % 16 == 0) && (sN * esz) % (4 * esz) == 0 &&
+                         (sN % 4 == 0) && (sP % 4 == 0) && (sL % 4 == 0) &&
+                         (reinterpret_cast<uintptr_t>(out) % 16 == 0) && oK % 4 == 0 && oP % 4 == 0;
+    if (aligned) {
+      bool ok = dtype == GD3_DTYPE_F32
+                    ? launch_fwd_fast(static_cast<const float*>(tokens), (int)L, sL, sP, sN, kp, (int)K, (int)P, (int)C, g,
+                                      normalize, out, oP, oK, inv_norm, stream)
+                    : launch_fwd_fast(static_cast<const __nv_bfloat16*>(tokens), (int)L, sL, sP, sN, kp, (int)K, (int)P,
+                                      (int)C, g, normalize, out, oP, oK, inv_norm, stream);
+      if (ok) {
+        GD3_CHECK_LAUNCH();
+        return GD3_OK;
+      }
+    }
+  }
   dim3 grid((unsigned)K, (unsigned)P);
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
   if (dtype == GD3_DTYPE_F32)
@@ -203,6 +351,23 @@ int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t
   SampleGeom g;
   int rc = make_geom(ph, pw, h, w, patch, stride, &g);
   if (rc) return rc;
+  {
+    const bool aligned = sC == 1 && gC == 1 && (!normalize || oC == 1) && C % 4 == 0 && sN % 4 == 0 && sP % 4 == 0 &&
+                         sL % 4 == 0 && gK % 4 == 0 && gP % 4 == 0 && (!normalize || (oK % 4 == 0 && oP % 4 == 0)) &&
+                         reinterpret_cast<uintptr_t>(grad_tokens) % 16 == 0 &&
+                         reinterpret_cast<uintptr_t>(grad_out) % 16 == 0 &&
+                         (!normalize || reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    if (aligned) {
+      dim3 fgrid((unsigned)ceil_div<int64_t>(K, 8), (unsigned)P);
+      {
+        GD3_PROF("sample_bwd_fast", stream);
+        sample_bwd_fast<<<fgrid, 256, 0, stream>>>(grad_out, gP, gK, out, oP, oK, inv_norm, kp, (int)K, (int)C, g,
+                                                  normalize, (int)L, grad_tokens, sL, sP, sN);
+      }
+      GD3_CHECK_LAUNCH();
+      return GD3_OK;
+    }
+  }
   dim3 grid((unsigned)K, (unsigned)P);
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
   {

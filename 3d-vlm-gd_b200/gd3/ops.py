@@ -273,8 +273,10 @@ def depth_head_loss(head, feats, depths, mode='logistic', depth_threshold=0.05, 
 # --------------------------------------------------------------------------------------------
 # bilinear token sampling
 # --------------------------------------------------------------------------------------------
-def sample_fwd_raw(tokens, layout, geom, kp, normalize, channels_first_out=False):
-    """tokens addressed through ``layout`` = (L, P, N, C, (sL, sP, sN, sC)) -> (out, inv_norm, out_strides)."""
+def sample_fwd_raw(tokens, layout, geom, kp, normalize, channels_first_out=False, out=None, out_strides=None):
+    """tokens addressed through ``layout`` = (L, P, N, C, (sL, sP, sN, sC)) -> (out, inv_norm, out_strides).
+
+    ``out`` / ``out_strides`` = (oP, oK, oC) let the caller place the result inside a larger buffer."""
     lib = load()
     L, P, N, C, strides = layout
     ph, pw, h, w, patch, stride = geom
@@ -284,7 +286,9 @@ def sample_fwd_raw(tokens, layout, geom, kp, normalize, channels_first_out=False
         raise ValueError(f'sample_tokens: keypoints must be (P, K, 2), got {tuple(kp.shape)}')
     K = kp.shape[1]
     dev = tokens.device
-    if channels_first_out:
+    if out is not None:
+        ostr = tuple(out_strides)
+    elif channels_first_out:
         out = torch.empty(P, C, K, dtype=_F32, device=dev)
         ostr = (C * K, 1, K)          # (oP, oK, oC)
     else:

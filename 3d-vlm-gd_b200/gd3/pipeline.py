@@ -65,10 +65,9 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     d2, inv2, _ = ops.sample_fwd_raw(g2, lay2, geom, kp2, True)
     # depth features of both views interleaved as sets (2p, 2p+1) = (view 1, view 2) of pair p
     kf = torch.empty(P, 2, K, C1_, dtype=_F32, device=dev)
-    k1, _, _ = ops.sample_fwd_raw(g1, lay1, geom, kp1, False)
-    k2, _, _ = ops.sample_fwd_raw(g2, lay2, geom, kp2, False)
-    kf[:, 0] = k1
-    kf[:, 1] = k2
+    pstr = (2 * K * C1_, C1_, 1)
+    ops.sample_fwd_raw(g1, lay1, geom, kp1, False, out=kf[:, 0], out_strides=pstr)
+    ops.sample_fwd_raw(g2, lay2, geom, kp2, False, out=kf[:, 1], out_strides=pstr)
     depths = torch.stack([batch['dep1'].to(_F32), batch['dep2'].to(_F32)], dim=1).reshape(2 * P, K)
 
     # ---- Smooth-AP (K2) ----
@@ -94,7 +93,6 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
         ops.sample_bwd_raw(gd1, cont, d1, ostr, inv1, kp1, dims, geom, True, gg1, gstr1)
         ops.sample_bwd_raw(gd2, cont, d2, ostr, inv2, kp2, dims, geom, True, gg2, gstr2)
         gk = gkf.reshape(P, 2, K, C1_)
-        pstr = (2 * K * C1_, C1_, 1)
         ops.sample_bwd_raw(gk[:, 0], pstr, None, ostr, None, kp1, dims, geom, False, gg1, gstr1)
         ops.sample_bwd_raw(gk[:, 1], pstr, None, ostr, None, kp2, dims, geom, False, gg2, gstr2)
         out['grads'] = dict(f1=gf1, f2=gf2, g1=gg1, g2=gg2, head=gparams)
