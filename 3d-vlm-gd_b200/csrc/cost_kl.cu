@@ -459,14 +459,12 @@ KLWorkspace carve_kl(void* base, int64_t G, int64_t N, int64_t C, bool backward)
 }
 
 int64_t auto_group(int64_t P, int64_t N, int64_t C) {
-  // keep one group's working set (teacher + W^T + z/dz staging + features) around half of L2
-  const double per_pair = 2.0 * N * N * 4 + N * N * 4.0 + 3.0 * N * N * 2 + 4.0 * N * C * 2 + 2.0 * N * C * 4;
-  int64_t g = (int64_t)(64.0e6 / per_pair);
+  // Measured on B200 (tools/probe_kl.py): launches that cover many pairs beat small L2-resident groups,
+  // because every kernel of the pipeline then runs several full waves.  So a group is as large as a
+  // ~3 GB workspace allows (W^T fp32 + z fp16 + dz, dz^T bf16 + a, b, aT, bT bf16 per pair).
+  const double per_pair = N * (double)N * (4 + 2 + 2 + 2) + 4.0 * N * C * 2;
+  int64_t g = (int64_t)(3.0e9 / per_pair);
   if (g < 1) g = 1;
-  // at least one full wave of 128 x 256 tiles on the pass-1 GEMM
-  const int64_t tiles = ceil_div<int64_t>(N, 128) * ceil_div<int64_t>(N, 256);
-  const int64_t fill = ceil_div<int64_t>(num_sms(), tiles);
-  if (g < fill) g = fill;
   return g > P ? P : g;
 }
 

@@ -17,7 +17,7 @@ def gd3mod():
     return gd3
 
 
-@pytest.mark.parametrize('tile_n', [128, 256])
+@pytest.mark.parametrize('tile_n', [128, 256, -128, -256])   # negative = 2-CTA (cta_group::2) kernel
 @pytest.mark.parametrize('shape', [(1, 128, 256, 64), (2, 256, 512, 768), (3, 200, 333, 136), (1, 1369, 1369, 1024)])
 def test_tc_gemm_matches_torch(gd3mod, tile_n, shape):
     """The hand-written tcgen05/TMA GEMM against a plain fp32 matmul of the same bf16 inputs."""
@@ -39,8 +39,9 @@ def test_tc_gemm_exact_integers(gd3mod):
     g = torch.Generator().manual_seed(5)
     A = torch.randint(-4, 5, (2, 384, 320), generator=g).float()
     B = torch.randint(-4, 5, (2, 272, 320), generator=g).float()
-    C = _lib.debug_gemm_bf16(A.to(torch.bfloat16).cuda(), B.to(torch.bfloat16).cuda(), tile_n=256)
-    assert torch.equal(C.cpu(), A @ B.transpose(1, 2))
+    for tile_n in (256, -256):
+        C = _lib.debug_gemm_bf16(A.to(torch.bfloat16).cuda(), B.to(torch.bfloat16).cuda(), tile_n=tile_n)
+        assert torch.equal(C.cpu(), A @ B.transpose(1, 2)), tile_n
 
 
 @pytest.mark.parametrize('dist', ['dot', 'l2'])
