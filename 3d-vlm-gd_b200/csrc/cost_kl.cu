@@ -109,6 +109,110 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Fast path of step 1 for channel-contiguous features (sC == 1, C % 8 == 0, 16-byte aligned rows):
+// 64 rows per CTA, 128-bit loads, a and aT written with 128-bit stores through a padded smem transpose.
+template <class T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = bf16_bits_to_float(w[i] & 0xFFFFu);
+    v[2 * i + 1] = bf16_bits_to_float(w[i] >> 16);
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+    kl_prep_fast(const T* __restrict__ f1, const T* __restrict__ f2, int64_t s1P, int64_t s1N, int64_t s2P, int64_t s2N,
+                 int pair0, int N, int C, int ldc, int ldn, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b,
+                 __nv_bfloat16* __restrict__ aT, __nv_bfloat16* __restrict__ bT, float* __restrict__ inv1,
+                 float* __restrict__ inv2) {
+  constexpr int TS = 66;                       // smem row stride in bf16 (33 words: conflict-free column reads)
+  __shared__ __nv_bfloat16 tile[64 * TS];
+  __shared__ float s_inv[64];
+  const int img = blockIdx.z, g = blockIdx.y, n0 = blockIdx.x * 64;
+  const T* f = (img == 0 ? f1 : f2) + (int64_t)(pair0 + g) * (img == 0 ? s1P : s2P);
+  const int64_t sN = img == 0 ? s1N : s2N;
+  __nv_bfloat16* o = (img == 0 ? a : b) + (int64_t)g * N * ldc;
+  __nv_bfloat16* oT = (img == 0 ? aT : bT);
+  if (oT) oT += (int64_t)g * C * ldn;
+  float* inv = (img == 0 ? inv1 : inv2) + (int64_t)g * N;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // ---- row norms: one warp per row, 8 elements per lane and iteration ----
+  for (int r = w; r < 64; r += 8) {
+    const int n = n0 + r;
+    float ss = 0.f;
+    if (n < N)
+      for (int c = lane * 8; c < C; c += 256) {
+        float v[8];
+        ld8(f + n * sN + c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+      }
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      const float iv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      s_inv[r] = iv;
+      if (n < N) inv[n] = iv;
+    }
+  }
+  __syncthreads();
+  // ---- 64 x 64 tiles: normalised rows -> a (row-major) and, through smem, aT ----
+  const int tr = threadIdx.x >> 2, tc = (threadIdx.x & 3) * 16;     // 4 threads per row, 16 channels each
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    {
+      const int n = n0 + tr;
+      const float iv = s_inv[tr];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c = c0 + tc + 8 * hh;
+        float v[8];
+        if (n < N && c < C) ld8(f + n * sN + c, v);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[i] = pack_bf16x2(v[2 * i] * iv, v[2 * i + 1] * iv);
+        if (n < N && c < C) *reinterpret_cast<uint4*>(o + (int64_t)n * ldc + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        uint32_t* trow = reinterpret_cast<uint32_t*>(tile + tr * TS + tc + 8 * hh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) trow[i] = pk[i];
+      }
+    }
+    __syncthreads();
+    if (oT) {
+      const int cc = c0 + tr;          // this thread writes aT row (channel) cc, 16 consecutive tokens
+      if (cc < C) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int nl = tc + 8 * hh;
+          if (n0 + nl < ldn) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint16_t lo = *reinterpret_cast<const uint16_t*>(tile + (nl + 2 * i) * TS + tr);
+              const uint16_t hi = *reinterpret_cast<const uint16_t*>(tile + (nl + 2 * i + 1) * TS + tr);
+              pk[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+            }
+            *reinterpret_cast<uint4*>(oT + (int64_t)cc * ldn + n0 + nl) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // 2. teacher row statistics: one warp per (direction, pair, row)
 // ------------------------------------------------------------------------------------------
@@ -532,22 +636,36 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     GD3_CHECK_CUDA(cudaMemsetAsync(w.Lrow, 0, sizeof(float) * 4 * G * N, stream));
     GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * G, stream));
     {
-      dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)g, 2);
-      if (dtype == GD3_DTYPE_F32)
-        {
-          GD3_PROF("kl_prep_features", stream);
+      const int esz = dtype == GD3_DTYPE_F32 ? 4 : 2;
+      const bool fast = s1C == 1 && s2C == 1 && C % 8 == 0 && (s1N * esz) % 16 == 0 && (s2N * esz) % 16 == 0 &&
+                        (s1P * esz) % 16 == 0 && (s2P * esz) % 16 == 0 &&
+                        reinterpret_cast<uintptr_t>(f1) % 16 == 0 && reinterpret_cast<uintptr_t>(f2) % 16 == 0;
+      __nv_bfloat16* pa = backward ? w.aT : nullptr;
+      __nv_bfloat16* pb = backward ? w.bT : nullptr;
+      if (fast) {
+        dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)g, 2);
+        GD3_PROF("kl_prep_fast", stream);
+        if (dtype == GD3_DTYPE_F32)
+          kl_prep_fast<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(f1), static_cast<const float*>(f2),
+                                                        s1P, s1N, s2P, s2N, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a,
+                                                        w.b, pa, pb, w.inv1, w.inv2);
+        else
+          kl_prep_fast<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+              static_cast<const __nv_bfloat16*>(f1), static_cast<const __nv_bfloat16*>(f2), s1P, s1N, s2P, s2N,
+              (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, pa, pb, w.inv1, w.inv2);
+      } else {
+        // generic strides (e.g. the MASt3R path's channel-major view)
+        dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)g, 2);
+        GD3_PROF("kl_prep_features", stream);
+        if (dtype == GD3_DTYPE_F32)
           kl_prep_features<float><<<grid, 256, 0, stream>>>(
-            static_cast<const float*>(f1), static_cast<const float*>(f2), s1P, s1N, s1C, s2P, s2N, s2C, (int)p0,
-            (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, backward ? w.aT : nullptr, backward ? w.bT : nullptr, w.inv1, w.inv2);
-        }
-      else
-        {
-          GD3_PROF("kl_prep_features", stream);
+              static_cast<const float*>(f1), static_cast<const float*>(f2), s1P, s1N, s1C, s2P, s2N, s2C, (int)p0,
+              (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, pa, pb, w.inv1, w.inv2);
+        else
           kl_prep_features<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(f1), static_cast<const __nv_bfloat16*>(f2), s1P, s1N, s1C, s2P, s2N,
-            s2C, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, backward ? w.aT : nullptr, backward ? w.bT : nullptr,
-            w.inv1, w.inv2);
-        }
+              static_cast<const __nv_bfloat16*>(f1), static_cast<const __nv_bfloat16*>(f2), s1P, s1N, s1C, s2P, s2N,
+              s2C, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, pa, pb, w.inv1, w.inv2);
+      }
       GD3_CHECK_LAUNCH();
     }
     {
