@@ -23,6 +23,7 @@
 #include "../../include/gd3.h"
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "split_bf16.cuh"
 
 namespace gd3 {
 namespace {
@@ -509,50 +510,6 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 // operand preparation for the GEMMs
 // ------------------------------------------------------------------------------------------
-// split x (R x D fp32) into [hi | second | third] panels (R x 3 ldd) and optionally x^T as [hi | lo | hi] panels
-// lo_panel = 2: [hi | hi | lo] (A side); lo_panel = 1: [hi | lo | hi] (B side)
-// in the TLayout column order (B side of the d W1 split product)
-__global__ void __launch_bounds__(256)
-    split3_bf16(const float* __restrict__ x, int64_t R, int D, int ldd, int lo_panel, __nv_bfloat16* __restrict__ X3,
-                __nv_bfloat16* __restrict__ XT, TLayout tl, int K) {
-  __shared__ float tile[32][33];
-  const int64_t r0 = (int64_t)blockIdx.x * 32;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int c0 = 0; c0 < ldd; c0 += 32) {
-    __syncthreads();
-    for (int r = w; r < 32; r += 8) {
-      const int64_t row = r0 + r;
-      const int c = c0 + lane;
-      const float v = (row < R && c < D) ? __ldg(x + row * D + c) : 0.f;
-      tile[r][lane] = v;
-      if (row < R && c < ldd) {
-        const __nv_bfloat16 hi = __float2bfloat16(v);
-        const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-        __nv_bfloat16* o = X3 + row * 3 * ldd + c;
-        o[0] = hi;
-        o[(3 - lo_panel) * ldd] = hi;
-        o[lo_panel * ldd] = lo;
-      }
-    }
-    __syncthreads();
-    if (XT)
-      for (int r = w; r < 32; r += 8) {
-        const int c = c0 + r;
-        const int64_t row = r0 + lane;
-        if (c < D && row < R) {
-          const float v = tile[lane][r];
-          const __nv_bfloat16 hi = __float2bfloat16(v);
-          const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-          const int set = (int)(row / K), k = (int)(row % K);
-          __nv_bfloat16* o = XT + (int64_t)c * tl.ld;
-          o[tl.col(set, k, 0)] = hi;
-          o[tl.col(set, k, 1)] = lo;
-          o[tl.col(set, k, 2)] = hi;
-        }
-      }
-  }
-}
-
 // epilogue: atomically accumulate alpha * acc into a single fp32 matrix shared by all batches (split-K)
 struct EpiAtomicAddF32 {
   static constexpr int kScratchBytes = 0;
@@ -693,16 +650,13 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   }
   // ---- u = f W1^T on the tensor cores (split bf16, 3 K-concatenated panels) ----
   {
-    GD3_PROF("split3_bf16", stream);
-    split3_bf16<<<(unsigned)ceil_div<int64_t>(R, 32), 256, 0, stream>>>(feats, R, (int)D, w.ldd, 2, w.F3,
-                                                                     backward ? w.FT3 : nullptr, w.tl, (int)K);
+    // operands of u = f W1^T (and, for the backward, the transposed panels of f for d W1 = du^T f)
+    XtLayout xf{backward ? 3 : 0, (int)K, w.tl.gs, w.tl.ldk, w.tl.gl, w.tl.ld, 0};
+    if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, backward ? w.FT3 : nullptr, xf, stream)))
+      return rc;
+    XtLayout none{0, 1, 1, 8, 8, 8, 0};
+    if ((rc = launch_split3("split3_w1", W1, H, (int)D, w.ldd, 1, w.W3, nullptr, none, stream))) return rc;
   }
-  GD3_CHECK_LAUNCH();
-  {
-    GD3_PROF("split3_bf16", stream);
-    split3_bf16<<<(unsigned)ceil_div<int64_t>(H, 32), 256, 0, stream>>>(W1, H, (int)D, w.ldd, 1, w.W3, nullptr, TLayout{}, 1);
-  }
-  GD3_CHECK_LAUNCH();
   {
     CUtensorMap ta, tb;
     if ((rc = tc::make_tmap_bf16(&ta, w.F3, 3 * (int64_t)w.ldd, R, 1, 3 * (int64_t)w.ldd, 0, tc::BM))) return rc;

@@ -15,7 +15,7 @@
 // tau = 0.01 amplifies similarity error 100x, so the K x K similarity is computed on the tensor
 // cores with a 2-term bf16 split of both operands (hi*hi + hi*lo + lo*hi, three K-concatenated
 // panels in ONE tcgen05 GEMM, ~16 mantissa bits); the gradient GEMMs use plain bf16.
-//   1 ap_prepare       SIMT  split / transpose descriptors
+//   1 split3 (split_bf16.cuh)  split / transpose descriptors
 //   2 tc_gemm<Store>         sim (fp32, K x K per pair: <= 1 MB, L2 resident)
 //   3 ap_rows          SIMT  one block per row: S1, S2, loss, d loss / d sim (bf16, unnormalised)
 //   4 transpose_bf16   SIMT  dsim^T
@@ -23,50 +23,10 @@
 #include "../../include/gd3.h"
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "split_bf16.cuh"
 
 namespace gd3 {
 namespace {
-
-// ------------------------------------------------------------------------------------------
-// 1. operand preparation.  grid (ceil(K/32), P, 2 images), block 256
-//    image 0: A' = [hi | hi | lo] (K x 3 ldc);  image 1: B' = [hi | lo | hi];  XT = hi^T (C x ldk)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    ap_prepare(const float* __restrict__ d1, const float* __restrict__ d2, int K, int C, int ldc, int ldk,
-               __nv_bfloat16* __restrict__ A3, __nv_bfloat16* __restrict__ B3, __nv_bfloat16* __restrict__ d1T,
-               __nv_bfloat16* __restrict__ d2T) {
-  __shared__ float tile[32][33];
-  const int img = blockIdx.z, p = blockIdx.y, k0 = blockIdx.x * 32;
-  const float* d = (img == 0 ? d1 : d2) + (int64_t)p * K * C;
-  __nv_bfloat16* X3 = (img == 0 ? A3 : B3) + (int64_t)p * K * 3 * ldc;
-  __nv_bfloat16* XT = (img == 0 ? d1T : d2T);
-  if (XT) XT += (int64_t)p * C * ldk;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  // which panel holds the low-order term: image 0 -> panel 2, image 1 -> panel 1
-  const int lo_panel = img == 0 ? 2 : 1;
-  for (int c0 = 0; c0 < ldc; c0 += 32) {
-    __syncthreads();
-    for (int r = w; r < 32; r += 8) {
-      const int k = k0 + r, c = c0 + lane;
-      const float v = (k < K && c < C) ? __ldg(d + (int64_t)k * C + c) : 0.f;
-      tile[r][lane] = v;
-      if (k < K && c < ldc) {
-        const __nv_bfloat16 hi = __float2bfloat16(v);
-        const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-        __nv_bfloat16* row = X3 + (int64_t)k * 3 * ldc + c;
-        row[0] = hi;
-        row[(3 - lo_panel) * ldc] = hi;      // the other hi panel (1 for image 0, 2 for image 1)
-        row[lo_panel * ldc] = lo;
-      }
-    }
-    __syncthreads();
-    if (XT)
-      for (int r = w; r < 32; r += 8) {
-        const int c = c0 + r, k = k0 + lane;
-        if (c < C && k < K) XT[(int64_t)c * ldk + k] = __float2bfloat16(tile[lane][r]);
-      }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // 3. per-row statistics and d loss / d sim.  grid (K, P), block 128, dynamic smem K floats
@@ -253,16 +213,15 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
   }
   GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * P, stream));
   GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int) * P, stream));
-  {
-    dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)P, 2);
-    {
-      GD3_PROF("ap_prepare", stream);
-      ap_prepare<<<grid, 256, 0, stream>>>(d1, d2, (int)K, (int)C, w.ldc, w.ldk, w.A3, w.B3, backward ? w.d1T : nullptr,
-                                         backward ? w.d2T : nullptr);
-    }
-    GD3_CHECK_LAUNCH();
-  }
   int rc;
+  {
+    // [hi | hi | lo] x [hi | lo | hi] panels for the similarity GEMM, hi^T per pair for the gradient GEMMs
+    XtLayout xt{backward ? 1 : 0, (int)K, 1, w.ldk, w.ldk, w.ldk, C * (int64_t)w.ldk};
+    if ((rc = launch_split3("ap_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, backward ? w.d1T : nullptr, xt, stream)))
+      return rc;
+    if ((rc = launch_split3("ap_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, backward ? w.d2T : nullptr, xt, stream)))
+      return rc;
+  }
   {
     CUtensorMap ta, tb;
     if ((rc = tc::make_tmap_bf16(&ta, w.A3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc,
