@@ -55,18 +55,27 @@ struct TLayout {
 // hidden index of this lane's i-th element: two float4 groups, 64 apart -> conflict-free LDS.128
 __device__ __forceinline__ int hidx(int l16, int i) { return (i < 4) ? 4 * l16 + i : 64 + 4 * l16 + (i - 4); }
 
-struct HeadConst {   // per-lane slice of the head parameters
-  float gam[HPL], bet[HPL], w2[HPL];
+// Per-lane slice of the head parameters, pre-scaled so that the pair loop works on ys = c * y with
+// c = sqrt(log2(e) / 2): exp(-y^2 / 2) is then a single ex2(-ys * ys), and all other constants fold.
+constexpr float kC = 0.84932180028801904f;          // sqrt(0.5 * log2(e))
+constexpr float kErfP = 0.3275911f * 0.70710678118654752f / kC;   // A&S p applied to |ys|
+constexpr float kPdf = 0.3989422804014327f / kC;    // y * pdf(y) = ys * e * kPdf
+struct HeadConst {
+  float gs[HPL], bs[HPL];   // gamma * c, beta * c
+  float w2c[HPL];           // w2 / c    (w2 . GELU(y) = sum w2c * (ys * Phi))
+  float w2g[HPL];           // w2 * gamma (d xhat / d out)
   float b2;
+  __device__ __forceinline__ void load(const float* gamma, const float* beta, const float* w2, const float* b2p,
+                                       int l16);
 };
 
 struct PairOut {
   float s;           // head output
   float rstd;
   float xh[HPL];     // normalised pre-activation
-  float g[HPL];      // GELU(y)
+  float g[HPL];      // c * GELU(y)
   float gp[HPL];     // GELU'(y)
-  float m1, m2;      // mean_h(q), mean_h(q * xh), q = w2 * gam * gp
+  float m1, m2;      // mean_h(q), mean_h(q * xh), q = w2 * gamma * gp
 };
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -100,24 +109,23 @@ __device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadCons
 #pragma unroll
   for (int i = 0; i < HPL; ++i) {
     const float xh = hc[i] * o.rstd;
-    const float y = fmaf(xh, hcst.gam[i], hcst.bet[i]);
-    const float z = y * 0.70710678118654752f;
-    const float t = fast_rcp(fmaf(0.3275911f, fabsf(z), 1.f));
+    const float ys = fmaf(xh, hcst.gs[i], hcst.bs[i]);          // c * y
+    const float t = fast_rcp(fmaf(kErfP, fabsf(ys), 1.f));
     float poly = fmaf(t, 1.061405429f, -1.453152027f);
     poly = fmaf(t, poly, 1.421413741f);
     poly = fmaf(t, poly, -0.284496736f);
     poly = fmaf(t, poly, 0.254829592f);
     poly *= t;
-    const float e = fast_ex2(z * z * -1.4426950408889634f);      // exp(-z^2) = exp(-y^2 / 2)
+    const float e = fast_ex2(-ys * ys);                         // exp(-y^2 / 2)
     const float erf_abs = fmaf(-poly, e, 1.f);
-    const float phi = fmaf(0.5f, copysignf(erf_abs, z), 0.5f);    // standard normal CDF at y
-    const float g = y * phi;
-    acc = fmaf(hcst.w2[i], g, acc);
+    const float phi = fmaf(0.5f, copysignf(erf_abs, ys), 0.5f);  // standard normal CDF at y
+    const float g = ys * phi;                                    // c * GELU(y)
+    acc = fmaf(hcst.w2c[i], g, acc);
     o.xh[i] = xh;
     o.g[i] = g;
     if (GRAD) {
-      const float gp = fmaf(y * e, 0.3989422804014327f, phi);     // Phi(y) + y * pdf(y)
-      const float q = hcst.w2[i] * hcst.gam[i] * gp;
+      const float gp = fmaf(ys * e, kPdf, phi);                  // Phi(y) + y * pdf(y)
+      const float q = hcst.w2g[i] * gp;
       o.gp[i] = gp;
       m1 += q;
       m2 = fmaf(q, xh, m2);
@@ -138,6 +146,19 @@ __device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadCons
     o.m1 = m1 * (1.f / H);
     o.m2 = m2 * (1.f / H);
   }
+}
+
+__device__ __forceinline__ void HeadConst::load(const float* gamma, const float* beta, const float* w2,
+                                                const float* b2p, int l16) {
+#pragma unroll
+  for (int i = 0; i < HPL; ++i) {
+    const int h = hidx(l16, i);
+    gs[i] = gamma[h] * kC;
+    bs[i] = beta[h] * kC;
+    w2c[i] = w2[h] * (1.f / kC);
+    w2g[i] = w2[h] * gamma[h];
+  }
+  b2 = b2p[0];
 }
 
 struct RankParams {
@@ -193,14 +214,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
     for (int h = lane; h < H; h += 32) bsum += p.b1[h];
     bsum = warp_sum(bsum) * (1.f / H);
 #pragma unroll
-    for (int i = 0; i < HPL; ++i) {
-      const int h = hidx(l16, i);
-      hc.gam[i] = p.gamma[h];
-      hc.bet[i] = p.beta[h];
-      hc.w2[i] = p.w2[h];
-      bb[i] = p.b1[h] - bsum;
-    }
-    hc.b2 = p.b2[0];
+    for (int i = 0; i < HPL; ++i) bb[i] = p.b1[hidx(l16, i)] - bsum;
+    hc.load(p.gamma, p.beta, p.w2, p.b2, l16);
   }
   const float inv_cnt = p.inv_count[set] * (p.w_rank ? p.w_rank[set] : 1.f);
   __syncthreads();
@@ -266,11 +281,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
           float dh[HPL];
 #pragma unroll
           for (int i = 0; i < HPL; ++i) {
-            const float pg = hc.w2[i] * o.gp[i];
+            // parameter sums are kept unscaled: d w2 = dw2 / c, d beta = w2 * dbet, d gamma = w2 * dgam
+            const float t1 = dout * o.gp[i];
             dw2[i] = fmaf(dout, o.g[i], dw2[i]);
-            dbet[i] = fmaf(dout, pg, dbet[i]);
-            dgam[i] = fmaf(dout * pg, o.xh[i], dgam[i]);
-            dh[i] = coef * (fmaf(pg, hc.gam[i], -o.m1) - o.xh[i] * o.m2);
+            dbet[i] += t1;
+            dgam[i] = fmaf(t1, o.xh[i], dgam[i]);
+            dh[i] = coef * fmaf(-o.xh[i], o.m2, fmaf(hc.w2g[i], o.gp[i], -o.m1));
             dub[i] += dh[i];
           }
           float4* q0 = reinterpret_cast<float4*>(dua + r * H + 4 * l16);
@@ -310,9 +326,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < HPL; ++i) {
-      const float g2 = dgam[i] + __shfl_xor_sync(0xffffffffu, dgam[i], 16);
-      const float b2v = dbet[i] + __shfl_xor_sync(0xffffffffu, dbet[i], 16);
-      const float w2v = dw2[i] + __shfl_xor_sync(0xffffffffu, dw2[i], 16);
+      const float w2h = hc.w2c[i] * kC;
+      const float g2 = (dgam[i] + __shfl_xor_sync(0xffffffffu, dgam[i], 16)) * w2h;
+      const float b2v = (dbet[i] + __shfl_xor_sync(0xffffffffu, dbet[i], 16)) * w2h;
+      const float w2v = (dw2[i] + __shfl_xor_sync(0xffffffffu, dw2[i], 16)) * (1.f / kC);
       if (half == 0) {
         const int h = hidx(l16, i);
         atomicAdd(red + h, g2);
@@ -377,14 +394,8 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
     for (int h = lane; h < H; h += 32) bsum += p.b1[h];
     bsum = warp_sum(bsum) * (1.f / H);
 #pragma unroll
-    for (int i = 0; i < HPL; ++i) {
-      const int h = hidx(l16, i);
-      hc.gam[i] = p.gamma[h];
-      hc.bet[i] = p.beta[h];
-      hc.w2[i] = p.w2[h];
-      bb[i] = p.b1[h] - bsum;
-    }
-    hc.b2 = p.b2[0];
+    for (int i = 0; i < HPL; ++i) bb[i] = p.b1[hidx(l16, i)] - bsum;
+    hc.load(p.gamma, p.beta, p.w2, p.b2, l16);
   }
   float dgam[HPL], dbet[HPL], dw2[HPL], db2 = 0.f, loss_local = 0.f;
 #pragma unroll
@@ -416,11 +427,12 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
 #pragma unroll
       for (int i = 0; i < HPL; ++i) {
         const int h = hidx(l16, i);
-        const float pg = hc.w2[i] * o.gp[i];
-        dw2[i] = dout * o.g[i];
+        const float w2h = hc.w2c[i] * kC;
+        const float pg = w2h * o.gp[i];
+        dw2[i] = dout * o.g[i] * (1.f / kC);
         dbet[i] = dout * pg;
         dgam[i] = dout * pg * o.xh[i];
-        const float dh = coef * (pg * hc.gam[i] - o.m1 - o.xh[i] * o.m2);
+        const float dh = coef * (hc.w2g[i] * o.gp[i] - o.m1 - o.xh[i] * o.m2);
         du_extra[((int64_t)sb * K + k) * H + h] = dh;
         du_extra[((int64_t)sa * K + k) * H + h] = -dh;
       }
