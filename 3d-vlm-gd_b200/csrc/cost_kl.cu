@@ -688,7 +688,7 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     {
       EpiKLStats::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, backward ? w.Z : nullptr, w.ldn};
       tc::GemmShape s{(int)N, (int)N, (int)C, g};
-      if ((rc = tc::launch_gemm<256, 4, EpiKLStats>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream))) return rc;
+      if ((rc = tc::launch_gemm<256, 8, EpiKLStats>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream))) return rc;
     }
     {
       const int64_t n = 2 * (int64_t)g * N;

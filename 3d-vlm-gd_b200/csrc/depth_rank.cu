@@ -55,15 +55,26 @@ struct TLayout {
 // hidden index of this lane's i-th element: two float4 groups, 64 apart -> conflict-free LDS.128
 __device__ __forceinline__ int hidx(int l16, int i) { return (i < 4) ? 4 * l16 + i : 64 + 4 * l16 + (i - 4); }
 
+// ---- packed fp32 arithmetic ------------------------------------------------------------------------------
+// sm_100 has two-wide fp32 instructions (FFMA2 / FMUL2 / FADD2 on 64-bit register pairs).  The pair loop is
+// bound by the instruction issue rate, and every elementwise step acts on 8 independent hidden units per
+// lane, so they are processed as 4 float2 values: half the issue slots for the same IEEE results.
+using F2 = float2;
+constexpr int HP = HPL / 2;
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ F2 add2(F2 a, F2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ F2 bc(float x) { return make_float2(x, x); }
+
 // Per-lane slice of the head parameters, pre-scaled so that the pair loop works on ys = c * y with
 // c = sqrt(log2(e) / 2): exp(-y^2 / 2) is then a single ex2(-ys * ys), and all other constants fold.
 constexpr float kC = 0.84932180028801904f;          // sqrt(0.5 * log2(e))
 constexpr float kErfP = 0.3275911f * 0.70710678118654752f / kC;   // A&S p applied to |ys|
 constexpr float kPdf = 0.3989422804014327f / kC;    // y * pdf(y) = ys * e * kPdf
 struct HeadConst {
-  float gs[HPL], bs[HPL];   // gamma * c, beta * c
-  float w2c[HPL];           // w2 / c    (w2 . GELU(y) = sum w2c * (ys * Phi))
-  float w2g[HPL];           // w2 * gamma (d xhat / d out)
+  F2 gs[HP], bs[HP];   // gamma * c, beta * c
+  F2 w2c[HP];          // w2 / c    (w2 . GELU(y) = sum w2c * (ys * Phi))
+  F2 w2g[HP];          // w2 * gamma (d xhat / d out)
   float b2;
   __device__ __forceinline__ void load(const float* gamma, const float* beta, const float* w2, const float* b2p,
                                        int l16);
@@ -72,9 +83,9 @@ struct HeadConst {
 struct PairOut {
   float s;           // head output
   float rstd;
-  float xh[HPL];     // normalised pre-activation
-  float g[HPL];      // c * GELU(y)
-  float gp[HPL];     // GELU'(y)
+  F2 xh[HP];         // normalised pre-activation
+  F2 g[HP];          // c * GELU(y)
+  F2 gp[HP];         // GELU'(y)
   float m1, m2;      // mean_h(q), mean_h(q * xh), q = w2 * gamma * gp
 };
 
@@ -98,39 +109,44 @@ __device__ __forceinline__ float fast_tanh(float x) {
 // Both half warps of a warp always execute this together (an invalid pair is masked later), so the
 // xor-shuffles with offsets < 16 use the full mask and stay inside each half.
 template <bool GRAD>
-__device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadConst& hcst, float ln_eps, int use_tanh,
+__device__ __forceinline__ void head_eval(const F2 (&hc)[HP], const HeadConst& hcst, float ln_eps, int use_tanh,
                                           PairOut& o) {
-  float ss = 0.f;
+  F2 ss2 = bc(0.f);
 #pragma unroll
-  for (int i = 0; i < HPL; ++i) ss = fmaf(hc[i], hc[i], ss);
-  ss = half_sum(ss, 0xffffffffu);
+  for (int i = 0; i < HP; ++i) ss2 = fma2(hc[i], hc[i], ss2);
+  const float ss = half_sum(ss2.x + ss2.y, 0xffffffffu);
   o.rstd = rsqrtf(fmaf(ss, 1.f / H, ln_eps));
-  float acc = 0.f, m1 = 0.f, m2 = 0.f;
+  const F2 r2 = bc(o.rstd);
+  F2 acc2 = bc(0.f), m1_2 = bc(0.f), m2_2 = bc(0.f);
 #pragma unroll
-  for (int i = 0; i < HPL; ++i) {
-    const float xh = hc[i] * o.rstd;
-    const float ys = fmaf(xh, hcst.gs[i], hcst.bs[i]);          // c * y
-    const float t = fast_rcp(fmaf(kErfP, fabsf(ys), 1.f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    poly *= t;
-    const float e = fast_ex2(-ys * ys);                         // exp(-y^2 / 2)
-    const float erf_abs = fmaf(-poly, e, 1.f);
-    const float phi = fmaf(0.5f, copysignf(erf_abs, ys), 0.5f);  // standard normal CDF at y
-    const float g = ys * phi;                                    // c * GELU(y)
-    acc = fmaf(hcst.w2c[i], g, acc);
+  for (int i = 0; i < HP; ++i) {
+    const F2 xh = mul2(hc[i], r2);
+    const F2 ys = fma2(xh, hcst.gs[i], hcst.bs[i]);               // c * y
+    const F2 ti = fma2(bc(kErfP), make_float2(fabsf(ys.x), fabsf(ys.y)), bc(1.f));
+    const F2 t = make_float2(fast_rcp(ti.x), fast_rcp(ti.y));
+    // -(a1 t + a2 t^2 + ... + a5 t^5): negated so that erf_abs = 1 + npoly * e is a single fma
+    F2 np = fma2(t, bc(-1.061405429f), bc(1.453152027f));
+    np = fma2(t, np, bc(-1.421413741f));
+    np = fma2(t, np, bc(0.284496736f));
+    np = fma2(t, np, bc(-0.254829592f));
+    np = mul2(np, t);
+    const F2 sq = mul2(ys, ys);
+    const F2 e = make_float2(fast_ex2(-sq.x), fast_ex2(-sq.y));   // exp(-y^2 / 2)
+    const F2 ea = fma2(np, e, bc(1.f));                            // erf(|y| / sqrt 2)
+    const F2 phi = fma2(bc(0.5f), make_float2(copysignf(ea.x, ys.x), copysignf(ea.y, ys.y)), bc(0.5f));
+    const F2 g = mul2(ys, phi);                                    // c * GELU(y)
+    acc2 = fma2(hcst.w2c[i], g, acc2);
     o.xh[i] = xh;
     o.g[i] = g;
     if (GRAD) {
-      const float gp = fmaf(ys * e, kPdf, phi);                  // Phi(y) + y * pdf(y)
-      const float q = hcst.w2g[i] * gp;
+      const F2 gp = fma2(mul2(ys, e), bc(kPdf), phi);              // Phi(y) + y * pdf(y)
+      const F2 q = mul2(hcst.w2g[i], gp);
       o.gp[i] = gp;
-      m1 += q;
-      m2 = fmaf(q, xh, m2);
+      m1_2 = add2(m1_2, q);
+      m2_2 = fma2(q, xh, m2_2);
     }
   }
+  float acc = acc2.x + acc2.y, m1 = m1_2.x + m1_2.y, m2 = m2_2.x + m2_2.y;
   // the three reductions are independent: one shuffle phase with three interleaved chains
 #pragma unroll
   for (int off = 8; off > 0; off >>= 1) {
@@ -148,15 +164,16 @@ __device__ __forceinline__ void head_eval(const float (&hc)[HPL], const HeadCons
   }
 }
 
+// element j (0..7) of a lane <-> hidden unit hidx(l16, j); pair i holds elements (2i, 2i+1)
 __device__ __forceinline__ void HeadConst::load(const float* gamma, const float* beta, const float* w2,
                                                 const float* b2p, int l16) {
 #pragma unroll
-  for (int i = 0; i < HPL; ++i) {
-    const int h = hidx(l16, i);
-    gs[i] = gamma[h] * kC;
-    bs[i] = beta[h] * kC;
-    w2c[i] = w2[h] * (1.f / kC);
-    w2g[i] = w2[h] * gamma[h];
+  for (int i = 0; i < HP; ++i) {
+    const int h0 = hidx(l16, 2 * i), h1 = hidx(l16, 2 * i + 1);
+    gs[i] = make_float2(gamma[h0] * kC, gamma[h1] * kC);
+    bs[i] = make_float2(beta[h0] * kC, beta[h1] * kC);
+    w2c[i] = make_float2(w2[h0] * (1.f / kC), w2[h1] * (1.f / kC));
+    w2g[i] = make_float2(w2[h0] * gamma[h0], w2[h1] * gamma[h1]);
   }
   b2 = b2p[0];
 }
@@ -196,52 +213,58 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
   const float* U = p.u + (int64_t)set * K * H;
   const float* Dp = p.depth + (int64_t)set * K;
 
-  // ---- load and centre the a tile (mean over h of u_a is hoisted out of the pair loop) ----
+  // ---- load and centre the a tile; it is stored NEGATED so that hc = vb + va is a plain packed add ----
   for (int r = warp; r < TILE; r += WARPS) {
     const int a = ta * TILE + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < K) v = *reinterpret_cast<const float4*>(U + (int64_t)a * H + 4 * lane);
     float m = (v.x + v.y) + (v.z + v.w);
     m = warp_sum(m) * (1.f / H);
-    *reinterpret_cast<float4*>(va + r * H + 4 * lane) = make_float4(v.x - m, v.y - m, v.z - m, v.w - m);
+    *reinterpret_cast<float4*>(va + r * H + 4 * lane) = make_float4(m - v.x, m - v.y, m - v.z, m - v.w);
     if (GRAD) *reinterpret_cast<float4*>(dua + r * H + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane == 0) da[r] = (a < K) ? Dp[a] : 0.f;
   }
   HeadConst hc;
-  float bb[HPL];   // b1 - mean(b1)
+  F2 bb[HP];   // b1 - mean(b1)
   {
     float bsum = 0.f;
     for (int h = lane; h < H; h += 32) bsum += p.b1[h];
     bsum = warp_sum(bsum) * (1.f / H);
 #pragma unroll
-    for (int i = 0; i < HPL; ++i) bb[i] = p.b1[hidx(l16, i)] - bsum;
+    for (int i = 0; i < HP; ++i)
+      bb[i] = make_float2(p.b1[hidx(l16, 2 * i)] - bsum, p.b1[hidx(l16, 2 * i + 1)] - bsum);
     hc.load(p.gamma, p.beta, p.w2, p.b2, l16);
   }
   const float inv_cnt = p.inv_count[set] * (p.w_rank ? p.w_rank[set] : 1.f);
   __syncthreads();
 
-  float dgam[HPL], dbet[HPL], dw2[HPL], db2 = 0.f;
+  F2 dgam[HP], dbet[HP], dw2[HP];
+  float db2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HPL; ++i) dgam[i] = dbet[i] = dw2[i] = 0.f;
+  for (int i = 0; i < HP; ++i) dgam[i] = dbet[i] = dw2[i] = bc(0.f);
   float loss_local = 0.f;
 
   for (int bi = 0; bi < B_PER_WARP; ++bi) {
     const int b = tb * TILE + warp * B_PER_WARP + bi;
     const bool b_ok = b < K;     // warp-uniform
-    float vb[HPL], dub[HPL];
+    F2 vb[HP], dub[HP];
     float d_b = 0.f;
     {
-      float m = 0.f;
-#pragma unroll
-      for (int i = 0; i < HPL; ++i) {
-        vb[i] = b_ok ? U[(int64_t)b * H + hidx(l16, i)] : 0.f;
-        m += vb[i];
-        dub[i] = 0.f;
+      float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+      if (b_ok) {
+        u0 = *reinterpret_cast<const float4*>(U + (int64_t)b * H + 4 * l16);
+        u1 = *reinterpret_cast<const float4*>(U + (int64_t)b * H + 64 + 4 * l16);
+        d_b = Dp[b];
       }
+      float m = ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w));
       m = half_sum(m, 0xffffffffu) * (1.f / H);
+      const F2 nm = bc(-m);
+      vb[0] = add2(add2(make_float2(u0.x, u0.y), nm), bb[0]);
+      vb[1] = add2(add2(make_float2(u0.z, u0.w), nm), bb[1]);
+      vb[2] = add2(add2(make_float2(u1.x, u1.y), nm), bb[2]);
+      vb[3] = add2(add2(make_float2(u1.z, u1.w), nm), bb[3]);
 #pragma unroll
-      for (int i = 0; i < HPL; ++i) vb[i] = vb[i] - m + bb[i];
-      if (b_ok) d_b = Dp[b];
+      for (int i = 0; i < HP; ++i) dub[i] = bc(0.f);
     }
 #pragma unroll 1
     for (int t = 0; t < TILE / 2; ++t) {
@@ -254,11 +277,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
       // both halves run the same instruction stream (98 % of the pairs are valid); an invalid pair is
       // masked out of every accumulation below.  Skip only when neither half has work.
       if (__any_sync(0xffffffffu, valid)) {
-        float hcv[HPL];
         const float4 a0 = *reinterpret_cast<const float4*>(va + r * H + 4 * l16);
         const float4 a1 = *reinterpret_cast<const float4*>(va + r * H + 64 + 4 * l16);
-        hcv[0] = vb[0] - a0.x; hcv[1] = vb[1] - a0.y; hcv[2] = vb[2] - a0.z; hcv[3] = vb[3] - a0.w;
-        hcv[4] = vb[4] - a1.x; hcv[5] = vb[5] - a1.y; hcv[6] = vb[6] - a1.z; hcv[7] = vb[7] - a1.w;
+        F2 hcv[HP];
+        hcv[0] = add2(vb[0], make_float2(a0.x, a0.y));
+        hcv[1] = add2(vb[1], make_float2(a0.z, a0.w));
+        hcv[2] = add2(vb[2], make_float2(a1.x, a1.y));
+        hcv[3] = add2(vb[3], make_float2(a1.z, a1.w));
         PairOut o;
         head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
         const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
@@ -277,25 +302,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
           // d total / d (w2.g + b2); zero for a masked pair, which zeroes every contribution below
           const float dout = valid ? dl * (p.use_tanh ? (1.f - o.s * o.s) : 1.f) * inv_cnt : 0.f;
           db2 += (l16 == 0) ? dout : 0.f;
-          const float coef = dout * o.rstd;
-          float dh[HPL];
+          const F2 dout2 = bc(dout), coef2 = bc(dout * o.rstd), nm1 = bc(-o.m1), nm2 = bc(-o.m2);
+          F2 dh[HP];
 #pragma unroll
-          for (int i = 0; i < HPL; ++i) {
+          for (int i = 0; i < HP; ++i) {
             // parameter sums are kept unscaled: d w2 = dw2 / c, d beta = w2 * dbet, d gamma = w2 * dgam
-            const float t1 = dout * o.gp[i];
-            dw2[i] = fmaf(dout, o.g[i], dw2[i]);
-            dbet[i] += t1;
-            dgam[i] = fmaf(t1, o.xh[i], dgam[i]);
-            dh[i] = coef * fmaf(-o.xh[i], o.m2, fmaf(hc.w2g[i], o.gp[i], -o.m1));
-            dub[i] += dh[i];
+            const F2 t1 = mul2(dout2, o.gp[i]);
+            dw2[i] = fma2(dout2, o.g[i], dw2[i]);
+            dbet[i] = add2(dbet[i], t1);
+            dgam[i] = fma2(t1, o.xh[i], dgam[i]);
+            dh[i] = mul2(coef2, fma2(o.xh[i], nm2, fma2(hc.w2g[i], o.gp[i], nm1)));
+            dub[i] = add2(dub[i], dh[i]);
           }
           float4* q0 = reinterpret_cast<float4*>(dua + r * H + 4 * l16);
           float4* q1 = reinterpret_cast<float4*>(dua + r * H + 64 + 4 * l16);
-          float4 c0 = *q0, c1 = *q1;
-          c0.x += dh[0]; c0.y += dh[1]; c0.z += dh[2]; c0.w += dh[3];
-          c1.x += dh[4]; c1.y += dh[5]; c1.z += dh[6]; c1.w += dh[7];
-          *q0 = c0;
-          *q1 = c1;
+          const float4 c0 = *q0, c1 = *q1;
+          const F2 s0 = add2(make_float2(c0.x, c0.y), dh[0]), s1 = add2(make_float2(c0.z, c0.w), dh[1]);
+          const F2 s2 = add2(make_float2(c1.x, c1.y), dh[2]), s3 = add2(make_float2(c1.z, c1.w), dh[3]);
+          *q0 = make_float4(s0.x, s0.y, s1.x, s1.y);
+          *q1 = make_float4(s2.x, s2.y, s3.x, s3.y);
         }
       }
       // Two half warps collide on a row of `dua` only when their step counters differ by a multiple of 4,
@@ -305,11 +330,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
     if (GRAD) {
       // combine the two half warps and store this b row's partial (over the a tile) gradient
 #pragma unroll
-      for (int i = 0; i < HPL; ++i) dub[i] += __shfl_xor_sync(0xffffffffu, dub[i], 16);
+      for (int i = 0; i < HP; ++i) {
+        dub[i].x += __shfl_xor_sync(0xffffffffu, dub[i].x, 16);
+        dub[i].y += __shfl_xor_sync(0xffffffffu, dub[i].y, 16);
+      }
       if (b_ok && half == 0) {
         float* dst = p.dub_part + (((int64_t)set * gridDim.x + ta) * K + b) * H;
-        *reinterpret_cast<float4*>(dst + 4 * l16) = make_float4(dub[0], dub[1], dub[2], dub[3]);
-        *reinterpret_cast<float4*>(dst + 64 + 4 * l16) = make_float4(dub[4], dub[5], dub[6], dub[7]);
+        *reinterpret_cast<float4*>(dst + 4 * l16) = make_float4(dub[0].x, dub[0].y, dub[1].x, dub[1].y);
+        *reinterpret_cast<float4*>(dst + 64 + 4 * l16) = make_float4(dub[2].x, dub[2].y, dub[3].x, dub[3].y);
       }
     }
   }
@@ -325,13 +353,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
     for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) red[e] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < HPL; ++i) {
-      const float w2h = hc.w2c[i] * kC;
-      const float g2 = (dgam[i] + __shfl_xor_sync(0xffffffffu, dgam[i], 16)) * w2h;
-      const float b2v = (dbet[i] + __shfl_xor_sync(0xffffffffu, dbet[i], 16)) * w2h;
-      const float w2v = (dw2[i] + __shfl_xor_sync(0xffffffffu, dw2[i], 16)) * (1.f / kC);
+    for (int j = 0; j < HPL; ++j) {
+      const int i = j >> 1;
+      const bool hi = j & 1;
+      const float w2h = (hi ? hc.w2c[i].y : hc.w2c[i].x) * kC;
+      const float vg = hi ? dgam[i].y : dgam[i].x, vb_ = hi ? dbet[i].y : dbet[i].x, vw = hi ? dw2[i].y : dw2[i].x;
+      const float g2 = (vg + __shfl_xor_sync(0xffffffffu, vg, 16)) * w2h;
+      const float b2v = (vb_ + __shfl_xor_sync(0xffffffffu, vb_, 16)) * w2h;
+      const float w2v = (vw + __shfl_xor_sync(0xffffffffu, vw, 16)) * (1.f / kC);
       if (half == 0) {
-        const int h = hidx(l16, i);
+        const int h = hidx(l16, j);
         atomicAdd(red + h, g2);
         atomicAdd(red + H + h, b2v);
         atomicAdd(red + 2 * H + h, w2v);
@@ -388,31 +419,23 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
   const int K = p.K;
   const int sb = 2 * pair, sa = 2 * pair + 1;
   HeadConst hc;
-  float bb[HPL];
-  {
-    float bsum = 0.f;
-    for (int h = lane; h < H; h += 32) bsum += p.b1[h];
-    bsum = warp_sum(bsum) * (1.f / H);
-#pragma unroll
-    for (int i = 0; i < HPL; ++i) bb[i] = p.b1[hidx(l16, i)] - bsum;
-    hc.load(p.gamma, p.beta, p.w2, p.b2, l16);
-  }
+  hc.load(p.gamma, p.beta, p.w2, p.b2, l16);
   float dgam[HPL], dbet[HPL], dw2[HPL], db2 = 0.f, loss_local = 0.f;
 #pragma unroll
   for (int i = 0; i < HPL; ++i) dgam[i] = dbet[i] = dw2[i] = 0.f;
   const bool ok = k < K;
-  float hcv[HPL];
+  float hs[HPL];
   float m = 0.f;
 #pragma unroll
   for (int i = 0; i < HPL; ++i) {
     const int h = hidx(l16, i);
-    hcv[i] = ok ? p.u[((int64_t)sb * K + k) * H + h] - p.u[((int64_t)sa * K + k) * H + h] + p.b1[h] : 0.f;
-    m += hcv[i];
+    hs[i] = ok ? p.u[((int64_t)sb * K + k) * H + h] - p.u[((int64_t)sa * K + k) * H + h] + p.b1[h] : 0.f;
+    m += hs[i];
   }
   m = half_sum(m, 0xffffffffu) * (1.f / H);
+  F2 hcv[HP];
 #pragma unroll
-  for (int i = 0; i < HPL; ++i) hcv[i] -= m;
-  (void)bb;
+  for (int i = 0; i < HP; ++i) hcv[i] = make_float2(hs[2 * i] - m, hs[2 * i + 1] - m);
   PairOut o;
   head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
   if (ok) {
@@ -425,14 +448,17 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
       db2 = (l16 == 0) ? dout : 0.f;
       const float coef = dout * o.rstd;
 #pragma unroll
-      for (int i = 0; i < HPL; ++i) {
-        const int h = hidx(l16, i);
-        const float w2h = hc.w2c[i] * kC;
-        const float pg = w2h * o.gp[i];
-        dw2[i] = dout * o.g[i] * (1.f / kC);
-        dbet[i] = dout * pg;
-        dgam[i] = dout * pg * o.xh[i];
-        const float dh = coef * (hc.w2g[i] * o.gp[i] - o.m1 - o.xh[i] * o.m2);
+      for (int j = 0; j < HPL; ++j) {
+        const int i = j >> 1;
+        const bool hi = j & 1;
+        const int h = hidx(l16, j);
+        const float gp = hi ? o.gp[i].y : o.gp[i].x, gg = hi ? o.g[i].y : o.g[i].x, xh = hi ? o.xh[i].y : o.xh[i].x;
+        const float w2h = (hi ? hc.w2c[i].y : hc.w2c[i].x) * kC, w2g = hi ? hc.w2g[i].y : hc.w2g[i].x;
+        const float pg = w2h * gp;
+        dw2[j] = dout * gg * (1.f / kC);
+        dbet[j] = dout * pg;
+        dgam[j] = dout * pg * xh;
+        const float dh = coef * (w2g * gp - o.m1 - xh * o.m2);
         du_extra[((int64_t)sb * K + k) * H + h] = dh;
         du_extra[((int64_t)sa * K + k) * H + h] = -dh;
       }
