@@ -670,7 +670,8 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   const int64_t nparam = (int64_t)H * D + 4 * H + 1;
   if (backward) {
     GD3_CHECK_CUDA(cudaMemsetAsync(grad_params, 0, sizeof(float) * nparam, stream));
-    GD3_CHECK_CUDA(cudaMemsetAsync(grad_feats, 0, sizeof(float) * S * K * D, stream));
+    // grad_feats is written in full by the d feats GEMM below (K > 0); it only needs clearing for K == 0,
+    // where it is empty anyway
   }
   if (K == 0) return GD3_OK;
   GD3_REQUIRE(feats && depths && W1 && b1 && gamma && beta && w2 && b2, "gd3_depth_head_loss: null input");

@@ -117,8 +117,10 @@ def smooth_ap_raw(d1, d2, p1, p2, variant='mast3r', temp=0.01, thr_neg=0.1, thr_
     q1 = p1.to(_F32).contiguous()
     q2 = p2.to(_F32).contiguous()
     loss = torch.zeros(P, dtype=_F32, device=dev)
-    g1 = torch.zeros(P, K, C, dtype=_F32, device=dev) if want_grad else None
-    g2 = torch.zeros(P, K, C, dtype=_F32, device=dev) if want_grad else None
+    # the gradient GEMM epilogue writes every element; zeros are only needed for the K = 0 early-out
+    alloc = torch.empty if (P and K) else torch.zeros
+    g1 = alloc(P, K, C, dtype=_F32, device=dev) if want_grad else None
+    g2 = alloc(P, K, C, dtype=_F32, device=dev) if want_grad else None
     if P and K:
         ws = workspace(lib.gd3_smooth_ap_workspace(P, K, C, int(want_grad)), dev)
         with torch.cuda.device(dev):
@@ -202,8 +204,10 @@ def depth_head_raw(feats, depths, params, use_tanh=True, ln_eps=1e-5, mode=0, th
     loss_rank = torch.zeros(S, dtype=_F32, device=dev)
     loss_l1 = torch.zeros(S // 2, dtype=_F32, device=dev) if wl is not None else None
     nparam = HIDDEN * D + 4 * HIDDEN + 1
-    gf = torch.zeros(S, K, D, dtype=_F32, device=dev) if want_grad else None
-    gp = torch.zeros(nparam, dtype=_F32, device=dev) if want_grad else None
+    # gd3_depth_head_loss clears its own outputs; zeros only matter for the S = 0 / K = 0 early-outs
+    alloc = torch.empty if (S and K) else torch.zeros
+    gf = alloc(S, K, D, dtype=_F32, device=dev) if want_grad else None
+    gp = alloc(nparam, dtype=_F32, device=dev) if want_grad else None
     if S and K:
         ws = workspace(lib.gd3_depth_head_loss_workspace(S, K, D, int(want_grad), int(wl is not None)), dev)
         with torch.cuda.device(dev):
