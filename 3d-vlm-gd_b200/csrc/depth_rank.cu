@@ -30,9 +30,16 @@ namespace {
 
 constexpr int H = 128;           // hidden width of fusion_layer (utils/model.py:88)
 constexpr int HPL = 8;           // hidden units per lane
-constexpr int TILE = 128;        // a / b tile edge
-constexpr int WARPS = 16;
-constexpr int B_PER_WARP = TILE / WARPS;   // 8
+// CTA tile of the pair kernel: TILE_A rows on the shared (a) side, WARPS * B_PER_WARP rows on the register (b)
+// side.  Two 8-warp CTAs per SM (independent barrier domains) hide latency better than one 16-warp CTA.
+constexpr int TILE_A = 64;
+constexpr int WARPS = 8;
+constexpr int B_PER_WARP = 16;
+constexpr int TILE_B = WARPS * B_PER_WARP;          // 128
+constexpr int CTAS_PER_SM = 2;
+constexpr int SLOTS = TILE_A / 2;                    // ring of row pairs a warp walks through
+constexpr int SPACING = SLOTS / WARPS;               // ring distance between consecutive warps
+static_assert(SLOTS % WARPS == 0 && SPACING >= 2, "stagger needs at least 2 ring slots between warps");
 
 // sum over the 16 lanes of a half warp (xor offsets < 16 never cross the halves)
 __device__ __forceinline__ float half_sum(float v, unsigned mask) {
@@ -199,14 +206,14 @@ struct RankParams {
   int64_t gparam_off;    // offset of b1 inside gparam (= H * D)
 };
 
-// dynamic smem: va[TILE][H] | dua[TILE][H] | da[TILE] | red[3*H + 1]
+// dynamic smem: va[TILE_A][H] | dua[TILE_A][H] | da[TILE_A] | red[3*H + 1]
 template <bool GRAD>
-__global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams p) {
   extern __shared__ __align__(16) float smem[];
   float* va = smem;                       // centred u_a rows of the a tile
-  float* dua = va + TILE * H;             // accumulated d/d(u_a) (sign applied at reduction)
-  float* da = dua + TILE * H;             // depths of the a tile
-  float* red = da + TILE;                 // cross-warp reduction of parameter gradients
+  float* dua = va + TILE_A * H;           // accumulated d/d(u_a) (sign applied at reduction)
+  float* da = dua + TILE_A * H;           // depths of the a tile
+  float* red = da + TILE_A;                 // cross-warp reduction of parameter gradients
   const int set = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
   const int K = p.K;
@@ -214,8 +221,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
   const float* Dp = p.depth + (int64_t)set * K;
 
   // ---- load and centre the a tile; it is stored NEGATED so that hc = vb + va is a plain packed add ----
-  for (int r = warp; r < TILE; r += WARPS) {
-    const int a = ta * TILE + r;
+  for (int r = warp; r < TILE_A; r += WARPS) {
+    const int a = ta * TILE_A + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < K) v = *reinterpret_cast<const float4*>(U + (int64_t)a * H + 4 * lane);
     float m = (v.x + v.y) + (v.z + v.w);
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
   float loss_local = 0.f;
 
   for (int bi = 0; bi < B_PER_WARP; ++bi) {
-    const int b = tb * TILE + warp * B_PER_WARP + bi;
+    const int b = tb * TILE_B + warp * B_PER_WARP + bi;
     const bool b_ok = b < K;     // warp-uniform
     F2 vb[HP], dub[HP];
     float d_b = 0.f;
@@ -267,10 +274,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
       for (int i = 0; i < HP; ++i) dub[i] = bc(0.f);
     }
 #pragma unroll 1
-    for (int t = 0; t < TILE / 2; ++t) {
-      // staggered a index: at any step the 32 half-warps of the CTA work on 32 different rows
-      const int r = 2 * ((t + 4 * warp) & (TILE / 2 - 1)) + half;
-      const int a = ta * TILE + r;
+    for (int t = 0; t < SLOTS; ++t) {
+      // staggered a index: at any step the half-warps of the CTA work on different rows
+      const int r = 2 * ((t + SPACING * warp) % SLOTS) + half;
+      const int a = ta * TILE_A + r;
       const float dd = d_b - da[r];
       bool valid = b_ok && a < K;
       valid = valid && ((p.mode == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr));
@@ -323,9 +330,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
           *q1 = make_float4(s2.x, s2.y, s3.x, s3.y);
         }
       }
-      // Two half warps collide on a row of `dua` only when their step counters differ by a multiple of 4,
-      // so a CTA barrier every third step is enough to keep the stagger race-free.
-      if (GRAD && ((bi * (TILE / 2) + t) % 3 == 2)) __syncthreads();
+      // Two half warps collide on a row of `dua` only when their step counters differ by a multiple of
+      // SPACING, so a CTA barrier every (SPACING - 1) steps keeps the stagger race-free.
+      if (GRAD && ((bi * SLOTS + t) % (SPACING - 1) == SPACING - 2)) __syncthreads();
     }
     if (GRAD) {
       // combine the two half warps and store this b row's partial (over the a tile) gradient
@@ -346,8 +353,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rank_pairs(RankParams p) {
   if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_sum + set, (double)loss_local);
   if (GRAD) {
     __syncthreads();
-    for (int e = threadIdx.x; e < TILE * H; e += blockDim.x) {
-      const int r = e / H, a = ta * TILE + r;
+    for (int e = threadIdx.x; e < TILE_A * H; e += blockDim.x) {
+      const int r = e / H, a = ta * TILE_A + r;
       if (a < K) p.dua_part[(((int64_t)set * gridDim.y + tb) * K + a) * H + (e - r * H)] = dua[e];
     }
     for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) red[e] = 0.f;
@@ -586,7 +593,7 @@ struct RankWorkspace {
   double *loss_sum, *l1_sum;
   int* count;
   size_t total;
-  int ldd, TA, groups;
+  int ldd, TA, TB, groups;
   TLayout tl;
   bool t_pads;   // transposed buffers contain columns no writer touches (must be zeroed)
 };
@@ -603,7 +610,8 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.tl.gl = (int64_t)w.tl.gs * w.tl.ldk;
   w.tl.ld = (int64_t)w.groups * 3 * w.tl.gl;
   w.t_pads = (S % w.tl.gs != 0) || (K != w.tl.ldk);
-  w.TA = (int)ceil_div<int64_t>(K, TILE);
+  w.TA = (int)ceil_div<int64_t>(K, TILE_A);
+  w.TB = (int)ceil_div<int64_t>(K, TILE_B);
   w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
   w.W3 = c.take<__nv_bfloat16>((int64_t)H * 3 * w.ldd);
   w.u = c.take<float>(R * H);
@@ -617,7 +625,7 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
     w.du_bf = c.take<__nv_bfloat16>(R * H);
     w.duT3 = c.take<__nv_bfloat16>((int64_t)H * w.tl.ld);
     w.dub_part = c.take<float>(S * w.TA * K * H);
-    w.dua_part = c.take<float>(S * w.TA * K * H);
+    w.dua_part = c.take<float>(S * w.TB * K * H);
     if (l1) w.du_extra = c.take<float>(R * H);
   }
   w.total = c.total();
@@ -745,8 +753,8 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.gparam = grad_params;
   rp.gparam_off = (int64_t)H * D;
   {
-    const size_t smem = sizeof(float) * (2 * TILE * H + TILE + 3 * H + 1 + 3);
-    dim3 grid((unsigned)w.TA, (unsigned)w.TA, (unsigned)S);
+    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 1 + 3);
+    dim3 grid((unsigned)w.TA, (unsigned)w.TB, (unsigned)S);
     if (backward) {
       static bool cfg = false;
       if (!cfg) {
@@ -798,7 +806,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     {
       GD3_PROF("rank_reduce_du", stream);
       rank_reduce_du<<<grid, 256, 0, stream>>>(w.dub_part, w.dua_part, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.TA,
-                                             w.TA, w.tl, w.du_bf, w.duT3, grad_params + (int64_t)H * D);
+                                             w.TB, w.tl, w.du_bf, w.duT3, grad_params + (int64_t)H * D);
     }
     GD3_CHECK_LAUNCH();
     {
