@@ -54,47 +54,56 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+    """Samples nvidia-smi clocks / throttle reasons (loop mode, 20 ms period) while the timed region runs."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
-        self.stop = threading.Event()
-        self.th = None
-
-    def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.Q}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(',')])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        self.proc = None
+        self.lines = []
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)      # let the first samples arrive before the region starts
+        except Exception:
+            self.proc = None
+        self.t0 = time.time()
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        self.th.join(timeout=6)
+        self.t1 = time.time()
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ''
+            self.lines = [ln for ln in out.splitlines() if ln.strip()]
 
     def summary(self):
+        import datetime
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for ln in self.lines:
+            r = [c.strip() for c in ln.split(',')]
+            if len(r) < 8:
+                continue
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                ts = datetime.datetime.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                if ts < self.t0 - 0.02 or ts > self.t1 + 0.02:
+                    continue
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
             except Exception:
                 continue
-            for n, v in zip(names, r[3:7]):
+            for n, v in zip(names, r[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(n)
         sm.sort()
@@ -329,7 +338,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
