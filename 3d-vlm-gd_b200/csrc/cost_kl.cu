@@ -309,7 +309,9 @@ struct EpiKLStats {
     __half* Z;         // (G, N, ldz) fp16 staging of z for the backward, or nullptr (forward only)
     int ldz;
   };
-  __device__ static void run(const Params& p, const tc::EpiCtx& cx) {
+  struct Pre {};
+  __device__ static void pre(const Params&, const tc::EpiCtx&, Pre&) {}
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre&) {
     const int i = cx.m0 + cx.row;
     const bool row_ok = i < p.N;
     const float* wt = p.WT + (int64_t)cx.b * p.N * p.ldw + i;
@@ -468,28 +470,50 @@ struct EpiGradOut {
     const float* inv;         // (G, N)
     OutT* out;                // (P, N, C) contiguous, already offset to this group's first pair
   };
-  __device__ static void run(const Params& p, const tc::EpiCtx& cx) {
+  // x (the normalised feature row of this thread) does not depend on the accumulator: the loads for the
+  // first 32 columns are issued before the tile's MMAs are awaited, the following ones one chunk ahead.
+  struct Pre {
+    uint4 x[4];
+    float dot, inv;
+  };
+  __device__ static __forceinline__ void load_x(const Params& p, const tc::EpiCtx& cx, int i, int c0, uint4 (&x)[4]) {
+    const __nv_bfloat16* xr = p.X + ((int64_t)cx.b * p.N + i) * p.ldc + c0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const uint4*>(xr + 8 * q));
+  }
+  __device__ static void pre(const Params& p, const tc::EpiCtx& cx, Pre& pr) {
+    const int i = cx.m0 + cx.row;
+    pr.dot = 0.f;
+    pr.inv = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pr.x[q] = make_uint4(0, 0, 0, 0);
+    if (i < p.N) {
+      pr.dot = p.dot[(int64_t)cx.b * p.N + i];
+      pr.inv = p.inv[(int64_t)cx.b * p.N + i];
+      const int c0 = cx.n0 + cx.col_begin;
+      if ((p.C % 8 == 0) && c0 + 32 <= p.C) load_x(p, cx, i, c0, pr.x);
+    }
+  }
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre& pr) {
     const int i = cx.m0 + cx.row;
     const bool row_ok = i < p.N;
-    float dot = 0.f, inv = 0.f;
-    if (row_ok) {
-      dot = p.dot[(int64_t)cx.b * p.N + i];
-      inv = p.inv[(int64_t)cx.b * p.N + i];
-    }
+    const float dot = pr.dot, inv = pr.inv;
     const __nv_bfloat16* x = p.X + ((int64_t)cx.b * p.N + i) * p.ldc;
     OutT* o = p.out + ((int64_t)cx.b * p.N + i) * p.C;
     const bool vec = (p.C % 8 == 0);
+    uint4 xn[4] = {pr.x[0], pr.x[1], pr.x[2], pr.x[3]};
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
       const int c0 = cx.n0 + c;
       if (c0 >= p.C) break;
+      uint4 xc[4] = {xn[0], xn[1], xn[2], xn[3]};
+      if (row_ok && vec && c + 32 < cx.col_end && c0 + 64 <= p.C) load_x(p, cx, i, c0 + 32, xn);   // next chunk
       float v[32];
       tc::tmem_ld32(cx.tmem + c, v);
       if (!row_ok) continue;
       if (vec && c0 + 32 <= p.C) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(x + c0 + 8 * q);   // ldc % 8 == 0
-          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+          const uint32_t xs[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
           float r[8];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -717,16 +741,16 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         using E = EpiGradOut<float>;
         E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1, static_cast<float*>(grad_f1) + p0 * N * C};
         E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2, static_cast<float*>(grad_f2) + p0 * N * C};
-        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
-        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
       } else {
         using E = EpiGradOut<__nv_bfloat16>;
         E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1,
                      static_cast<__nv_bfloat16*>(grad_f1) + p0 * N * C};
         E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2,
                      static_cast<__nv_bfloat16*>(grad_f2) + p0 * N * C};
-        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
-        if ((rc = tc::launch_gemm<256, 4, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
+        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
       }
     }
   }

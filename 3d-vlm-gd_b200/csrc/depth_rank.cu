@@ -563,7 +563,9 @@ struct EpiAtomicAddF32 {
     int M, N;
     int64_t ldc;
   };
-  __device__ static void run(const Params& p, const tc::EpiCtx& cx) {
+  struct Pre {};
+  __device__ static void pre(const Params&, const tc::EpiCtx&, Pre&) {}
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre&) {
     const int m = cx.m0 + cx.row;
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
       const int n = cx.n0 + c;

@@ -8,6 +8,8 @@
 //                 + owner of the TMEM allocation (2 accumulator buffers of BN columns)
 //   warps 2..   : epilogue      (tcgen05.ld 32x32b -> registers -> Epi functor); the accumulator is
 //                 double-buffered in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
+//                 Epi::pre() runs before the accumulator is awaited (prefetch of epilogue operands),
+//                 Epi::run() after.
 // The accumulator never goes to HBM unless the epilogue functor writes it.
 //
 // Descriptor bit layouts follow the PTX ISA "tcgen05 matrix/instruction descriptor" tables (the
@@ -279,9 +281,11 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
       cx.epi_warp = ew;
       cx.scratch = scratch;
       cx.tmem = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      typename Epi::Pre pre;
+      Epi::pre(ep, cx, pre);            // global loads that do not depend on the accumulator start here
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      Epi::run(ep, cx);
+      Epi::run(ep, cx, pre);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -484,9 +488,11 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
       cx.epi_warp = ew;
       cx.scratch = scratch;
       cx.tmem = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      typename Epi::Pre pre;
+      Epi::pre(ep, cx, pre);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      Epi::run(ep, cx);
+      Epi::run(ep, cx, pre);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -589,7 +595,9 @@ struct EpiStoreF32 {
     float alpha;
     const float* batch_scale;   // optional per-batch factor read from device memory (nullptr = 1)
   };
-  __device__ static void run(const Params& p, const EpiCtx& cx) {
+  struct Pre {};
+  __device__ static void pre(const Params&, const EpiCtx&, Pre&) {}
+  __device__ static void run(const Params& p, const EpiCtx& cx, const Pre&) {
     const int m = cx.m0 + cx.row;
     const float alpha = p.batch_scale ? p.alpha * __ldg(p.batch_scale + cx.b) : p.alpha;
     float* crow = p.C + cx.b * p.batch_stride + static_cast<int64_t>(m) * p.ldc;
