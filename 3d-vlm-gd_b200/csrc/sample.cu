@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256)
                       const float* __restrict__ out, int64_t oP, int64_t oK, int64_t oC,
                       const float* __restrict__ inv_norm, const float* __restrict__ kp, int K, int C, SampleGeom g,
                       int normalize, int L, float* __restrict__ gtok, int64_t sL, int64_t sP, int64_t sN,
-                      int64_t sC) {
+                      int64_t sC, const float* __restrict__ gextra, int64_t eP, int64_t eK, int64_t eC) {
   __shared__ float red[32];
   const int k = blockIdx.x, p = blockIdx.y;
   const float x = kp[((int64_t)p * K + k) * 2 + 0], y = kp[((int64_t)p * K + k) * 2 + 1];
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float gv = go[c * gC];
     if (normalize) gv = (gv - out[p * oP + k * oK + c * oC] * dot) * inv;   // d/dx of x / max(|x|, eps)
+    if (gextra) gv += gextra[p * eP + k * eK + c * eC];   // gradient w.r.t. the un-normalised sample
     gv *= invL;
     for (int l = 0; l < L; ++l) {
       float* base = gtok + l * sL + p * sP + c * sC;
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     sample_bwd_fast(const float* __restrict__ gout, int64_t gP, int64_t gK, const float* __restrict__ out, int64_t oP,
                     int64_t oK, const float* __restrict__ inv_norm, const float* __restrict__ kp, int K, int C,
-                    SampleGeom g, int normalize, int L, float* __restrict__ gtok, int64_t sL, int64_t sP, int64_t sN) {
+                    SampleGeom g, int normalize, int L, float* __restrict__ gtok, int64_t sL, int64_t sP, int64_t sN,
+                    const float* __restrict__ gextra, int64_t eP, int64_t eK) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5), p = blockIdx.y;
   if (k >= K) return;
@@ -219,14 +221,20 @@ __global__ void __launch_bounds__(256)
     dot = warp_sum(dot);
     inv = inv_norm[(int64_t)p * K + k];
   }
-  const float sc = inv / (float)L;
+  const float invL = 1.f / (float)L;
+  const float* ge = gextra ? gextra + p * eP + k * eK : nullptr;
   for (int c = lane * 4; c < C; c += 128) {
     float4 gv = *reinterpret_cast<const float4*>(go + c);
     if (normalize) {
       const float4 a = *reinterpret_cast<const float4*>(o + c);
-      gv.x -= a.x * dot; gv.y -= a.y * dot; gv.z -= a.z * dot; gv.w -= a.w * dot;
+      gv.x = (gv.x - a.x * dot) * inv; gv.y = (gv.y - a.y * dot) * inv;
+      gv.z = (gv.z - a.z * dot) * inv; gv.w = (gv.w - a.w * dot) * inv;
     }
-    gv.x *= sc; gv.y *= sc; gv.z *= sc; gv.w *= sc;
+    if (ge) {   // gradient w.r.t. the un-normalised sample of the same keypoint (e.g. the depth features)
+      const float4 e = *reinterpret_cast<const float4*>(ge + c);
+      gv.x += e.x; gv.y += e.y; gv.z += e.z; gv.w += e.w;
+    }
+    gv.x *= invL; gv.y *= invL; gv.z *= invL; gv.w *= invL;
     for (int l = 0; l < L; ++l) {
       float* base = gtok + l * sL + p * sP + c;
       atomicAdd(reinterpret_cast<float4*>(base + t.i00 * sN), make_float4(gv.x * t.w00, gv.y * t.w00, gv.z * t.w00, gv.w * t.w00));
@@ -342,7 +350,8 @@ int gd3_sample_tokens_fwd(const void* tokens, int dtype, int64_t L, int64_t P, i
 int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t gC, const float* out, int64_t oP,
                           int64_t oK, int64_t oC, const float* inv_norm, const float* kp, int64_t L, int64_t P,
                           int64_t K, int64_t C, int64_t ph, int64_t pw, int64_t h, int64_t w, int patch, int stride,
-                          int normalize, float* grad_tokens, int64_t sL, int64_t sP, int64_t sN, int64_t sC, void* stream_) {
+                          int normalize, float* grad_tokens, int64_t sL, int64_t sP, int64_t sN, int64_t sC,
+                          const float* grad_extra, int64_t eP, int64_t eK, int64_t eC, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (P == 0 || K == 0 || C == 0) return GD3_OK;
   GD3_REQUIRE(grad_out && kp && grad_tokens, "gd3_sample_tokens_bwd: null pointer");
@@ -356,13 +365,15 @@ int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t
                          sL % 4 == 0 && gK % 4 == 0 && gP % 4 == 0 && (!normalize || (oK % 4 == 0 && oP % 4 == 0)) &&
                          reinterpret_cast<uintptr_t>(grad_tokens) % 16 == 0 &&
                          reinterpret_cast<uintptr_t>(grad_out) % 16 == 0 &&
-                         (!normalize || reinterpret_cast<uintptr_t>(out) % 16 == 0);
+                         (!normalize || reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                         (!grad_extra || (eC == 1 && eK % 4 == 0 && eP % 4 == 0 &&
+                                          reinterpret_cast<uintptr_t>(grad_extra) % 16 == 0));
     if (aligned) {
       dim3 fgrid((unsigned)ceil_div<int64_t>(K, 8), (unsigned)P);
       {
         GD3_PROF("sample_bwd_fast", stream);
         sample_bwd_fast<<<fgrid, 256, 0, stream>>>(grad_out, gP, gK, out, oP, oK, inv_norm, kp, (int)K, (int)C, g,
-                                                  normalize, (int)L, grad_tokens, sL, sP, sN);
+                                                  normalize, (int)L, grad_tokens, sL, sP, sN, grad_extra, eP, eK);
       }
       GD3_CHECK_LAUNCH();
       return GD3_OK;
@@ -373,7 +384,7 @@ int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t
   {
     GD3_PROF("sample_bwd_kernel", stream);
     sample_bwd_kernel<<<grid, threads, 0, stream>>>(grad_out, gP, gK, gC, out, oP, oK, oC, inv_norm, kp, (int)K, (int)C,
-                                                  g, normalize, (int)L, grad_tokens, sL, sP, sN, sC);
+                                                  g, normalize, (int)L, grad_tokens, sL, sP, sN, sC, grad_extra, eP, eK, eC);
   }
   GD3_CHECK_LAUNCH();
   return GD3_OK;

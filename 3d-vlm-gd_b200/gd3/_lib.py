@@ -35,7 +35,8 @@ SYMBOLS = {
     'gd3_sample_tokens_fwd': (_int, [_vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp,
                                      _i64, _int, _int, _int, _vp, _i64, _i64, _i64, _vp, _vp]),
     'gd3_sample_tokens_bwd': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64,
-                                     _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _i64, _i64, _i64, _i64, _vp]),
+                                     _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _i64, _i64, _i64, _i64, _vp, _i64,
+                                     _i64, _i64, _vp]),
     'gd3_debug_gemm_bf16': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
 }
 

@@ -307,8 +307,12 @@ def sample_fwd_raw(tokens, layout, geom, kp, normalize, channels_first_out=False
     return out, inv, ostr
 
 
-def sample_bwd_raw(grad_out, gstr, out, ostr, inv, kp, dims, geom, normalize, grad_tokens, gstrides):
-    """Scatter ``grad_out`` back through the taps, accumulating into ``grad_tokens`` (fp32)."""
+def sample_bwd_raw(grad_out, gstr, out, ostr, inv, kp, dims, geom, normalize, grad_tokens, gstrides, grad_extra=None,
+                   estr=(0, 0, 0)):
+    """Scatter ``grad_out`` back through the taps, accumulating into ``grad_tokens`` (fp32).
+
+    ``grad_extra`` (strides ``estr``) is an additional gradient w.r.t. the un-normalised sample of the same
+    keypoints; it shares the scatter."""
     lib = load()
     L, P, K, C = dims
     ph, pw, h, w, patch, stride = geom
@@ -316,7 +320,7 @@ def sample_bwd_raw(grad_out, gstr, out, ostr, inv, kp, dims, geom, normalize, gr
         with torch.cuda.device(grad_out.device):
             check(lib.gd3_sample_tokens_bwd(ptr(grad_out), *gstr, ptr(out), *ostr, ptr(inv), ptr(kp), L, P, K, C, ph,
                                             pw, h, w, patch, stride, int(normalize), ptr(grad_tokens), *gstrides,
-                                            stream_ptr()))
+                                            ptr(grad_extra), *estr, stream_ptr()))
 
 
 class _SampleTokens(torch.autograd.Function):

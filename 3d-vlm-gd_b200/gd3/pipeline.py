@@ -90,10 +90,9 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
         gg2 = torch.zeros(P, N, C1_, dtype=_F32, device=dev)
         dims = (1, P, K, C1_)
         cont = (K * C1_, C1_, 1)
-        ops.sample_bwd_raw(gd1, cont, d1, ostr, inv1, kp1, dims, geom, True, gg1, gstr1)
-        ops.sample_bwd_raw(gd2, cont, d2, ostr, inv2, kp2, dims, geom, True, gg2, gstr2)
+        # descriptor gradients (through the normalisation) and depth-feature gradients share one scatter per view
         gk = gkf.reshape(P, 2, K, C1_)
-        ops.sample_bwd_raw(gk[:, 0], pstr, None, ostr, None, kp1, dims, geom, False, gg1, gstr1)
-        ops.sample_bwd_raw(gk[:, 1], pstr, None, ostr, None, kp2, dims, geom, False, gg2, gstr2)
+        ops.sample_bwd_raw(gd1, cont, d1, ostr, inv1, kp1, dims, geom, True, gg1, gstr1, gk[:, 0], pstr)
+        ops.sample_bwd_raw(gd2, cont, d2, ostr, inv2, kp2, dims, geom, True, gg2, gstr2, gk[:, 1], pstr)
         out['grads'] = dict(f1=gf1, f2=gf2, g1=gg1, g2=gg2, head=gparams)
     return out

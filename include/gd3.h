@@ -146,7 +146,9 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
  *   kp      (P, K, 2) fp32 pixel (x, y)
  *   out     element (p, k, c) at out[p*oP + k*oK + c*oC], fp32
  *   inv_norm (P, K) fp32, written when normalize != 0 (needed by the backward)
- * The backward accumulates into grad_tokens (fp32, same strides as tokens, caller-zeroed).
+ * The backward accumulates into grad_tokens (fp32, same strides as tokens, caller-zeroed).  grad_extra
+ * (optional, element (p, k, c) at p*eP + k*eK + c*eC) is a second gradient w.r.t. the UN-normalised sample of
+ * the same keypoints; it is added after the normalisation backward so both share one scatter.
  * ------------------------------------------------------------------------------------------ */
 int gd3_sample_tokens_fwd(const void* tokens, int dtype, int64_t L, int64_t P, int64_t C, int64_t ph, int64_t pw,
                           int64_t h, int64_t w, int64_t sL, int64_t sP, int64_t sN, int64_t sC, const float* kp,
@@ -155,7 +157,8 @@ int gd3_sample_tokens_fwd(const void* tokens, int dtype, int64_t L, int64_t P, i
 int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t gC, const float* out, int64_t oP,
                           int64_t oK, int64_t oC, const float* inv_norm, const float* kp, int64_t L, int64_t P,
                           int64_t K, int64_t C, int64_t ph, int64_t pw, int64_t h, int64_t w, int patch, int stride,
-                          int normalize, float* grad_tokens, int64_t sL, int64_t sP, int64_t sN, int64_t sC, void* stream);
+                          int normalize, float* grad_tokens, int64_t sL, int64_t sP, int64_t sN, int64_t sC,
+                          const float* grad_extra, int64_t eP, int64_t eK, int64_t eC, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Debug / self-test: C[b] = A[b] * B[b]^T through the tcgen05 GEMM used by all fused losses.
