@@ -96,3 +96,54 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
         ops.sample_bwd_raw(gd2, cont, d2, ostr, inv2, kp2, dims, geom, True, gg2, gstr2, gk[:, 1], pstr)
         out['grads'] = dict(f1=gf1, f2=gf2, g1=gg1, g2=gg2, head=gparams)
     return out
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device staging for batches that live in pinned host memory.
+
+    ``for dev_batch in DevicePrefetcher(batches, device): ...`` uploads batch i+1 on a side stream while
+    the caller's stream works on batch i, so a step costs max(copy, compute) instead of their sum.  Every
+    tensor of every batch is still copied exactly once (non-tensor entries such as the head parameters
+    are passed through).  The consumer stream waits on the copy event before it touches a batch, and the
+    copy stream waits until the consumer has finished with the buffer it is about to overwrite.
+    """
+
+    def __init__(self, batches, device, depth=2):
+        self.batches = iter(batches)
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self.queue = []          # [(device batch, ready event)]
+        self.done_events = []    # consumer-side events guarding buffer reuse
+
+    def _enqueue(self):
+        try:
+            host = next(self.batches)
+        except StopIteration:
+            return False
+        with torch.cuda.stream(self.copy_stream):
+            if len(self.done_events) >= self.depth:
+                self.copy_stream.wait_event(self.done_events.pop(0))
+            dev = {}
+            for k, v in host.items():
+                dev[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.queue.append((dev, ev))
+        return True
+
+    def __iter__(self):
+        for _ in range(self.depth):
+            self._enqueue()
+        while self.queue:
+            dev, ev = self.queue.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for v in dev.values():
+                if torch.is_tensor(v):
+                    v.record_stream(cur)
+            yield dev
+            done = torch.cuda.Event()
+            done.record(cur)
+            self.done_events.append(done)
+            self._enqueue()
