@@ -457,6 +457,141 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------
+// Vectorised variants of steps 3 and 6 for N % 8 == 0 with 16-byte aligned teacher rows:
+// 64 x 64 tiles, 128-bit global accesses, padded shared-memory transposes.
+// ------------------------------------------------------------------------------------------
+// grid (N/64 i-tiles, N/64 j-tiles, G), block 256: thread = (row tr of a 16-row pass, float4 column tc)
+__global__ void __launch_bounds__(256)
+    kl_build_w_fast(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+                    int64_t t_row_stride, int pair0, int G, int N, const float* __restrict__ invR,
+                    const float* __restrict__ epsm, float* __restrict__ WT, int ldw) {
+  __shared__ float tile[64][65];     // t~12 tile, transposed: [j][i]
+  const int g = blockIdx.z, i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+  const float* T12 = t12 + (int64_t)(pair0 + g) * t_pair_stride;
+  const float* T21 = t21 + (int64_t)(pair0 + g) * t_pair_stride;
+  const float* ir12 = invR + (int64_t)g * N;
+  const float* ir21 = invR + ((int64_t)G + g) * N;
+  const float* e12 = epsm + (int64_t)g * N;
+  const float* e21 = epsm + ((int64_t)G + g) * N;
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int r = ps * 16 + tr, i = i0 + r, j = j0 + tc;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < N && j < N) {
+      v = __ldg(reinterpret_cast<const float4*>(T12 + (int64_t)i * t_row_stride + j));
+      const float ir = ir12[i], ee = e12[i];
+      v.x = fmaxf(v.x * ir, ee); v.y = fmaxf(v.y * ir, ee); v.z = fmaxf(v.z * ir, ee); v.w = fmaxf(v.w * ir, ee);
+    }
+    tile[tc][r] = v.x; tile[tc + 1][r] = v.y; tile[tc + 2][r] = v.z; tile[tc + 3][r] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int r = ps * 16 + tr, j = j0 + r, i = i0 + tc;
+    if (j < N && i < N) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(T21 + (int64_t)j * t_row_stride + i));
+      const float ir = ir21[j], ee = e21[j];
+      v.x = fmaxf(v.x * ir, ee) + tile[r][tc];
+      v.y = fmaxf(v.y * ir, ee) + tile[r][tc + 1];
+      v.z = fmaxf(v.z * ir, ee) + tile[r][tc + 2];
+      v.w = fmaxf(v.w * ir, ee) + tile[r][tc + 3];
+      *reinterpret_cast<float4*>(WT + ((int64_t)g * N + j) * ldw + i) = v;
+    }
+  }
+}
+
+// grid (N/64 j-tiles, N/64 i-tiles, G), block 256
+__global__ void __launch_bounds__(256)
+    kl_dz_fast(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT,
+               int ldw, const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT,
+               int ldd, float* __restrict__ rowdot, float* __restrict__ coldot) {
+  __shared__ float ws[64][65];      // W^T tile [j][i]; later reused as dz [i][j]
+  __shared__ float cdot[32][65];
+  const int g = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const float* wt = WT + (int64_t)g * N * ldw;
+  {
+    const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+      const int r = ps * 16 + tr, j = j0 + r, i = i0 + tc;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < N && i < N) v = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)j * ldw + i));
+      ws[r][tc] = v.x; ws[r][tc + 1] = v.y; ws[r][tc + 2] = v.z; ws[r][tc + 3] = v.w;
+    }
+  }
+  __syncthreads();
+  const float s = grad_scale * 0.5f / (float)N;
+  const float* rr = rc + (int64_t)g * N;
+  const float* cc = rc + ((int64_t)G + g) * N;
+  // thread = (row tr8 of a 32-row pass, 8 consecutive columns at jc)
+  const int tr8 = threadIdx.x >> 3, jc = (threadIdx.x & 7) * 8;
+  float cj[8], cdp[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    cj[q] = (j0 + jc + q < N) ? cc[j0 + jc + q] : 0.f;
+    cdp[q] = 0.f;
+  }
+  float dzv[2][8];
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int r = ps * 32 + tr8, i = i0 + r;
+    float rd = 0.f;
+    float d[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d[q] = 0.f;
+    if (i < N && j0 + jc < N) {
+      const uint4 zz = __ldg(reinterpret_cast<const uint4*>(Z + ((int64_t)g * N + i) * ldz + j0 + jc));
+      const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
+      const float ri = rr[i];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const __half hv = __ushort_as_half((unsigned short)((q & 1) ? (zw[q >> 1] >> 16) : (zw[q >> 1] & 0xFFFFu)));
+        const float z = (j0 + jc + q < N) ? __half2float(hv) : 0.f;
+        const float v = (j0 + jc + q < N) ? s * ((ri + cj[q]) * exp2f(z * LOG2E) - ws[jc + q][r]) : 0.f;
+        d[q] = v;
+        rd = fmaf(v, z, rd);
+        cdp[q] = fmaf(v, z, cdp[q]);
+      }
+      *reinterpret_cast<uint4*>(dZ + ((int64_t)g * N + i) * ldd + j0 + jc) =
+          make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+    }
+    // row dot: the 8 threads of a row are consecutive lanes
+    rd += __shfl_xor_sync(0xffffffffu, rd, 1);
+    rd += __shfl_xor_sync(0xffffffffu, rd, 2);
+    rd += __shfl_xor_sync(0xffffffffu, rd, 4);
+    if ((threadIdx.x & 7) == 0 && i < N) atomicAdd(rowdot + (int64_t)g * N + i, rd);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dzv[ps][q] = d[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) cdot[tr8][jc + q] = cdp[q];
+  __syncthreads();                   // all reads of ws (as W^T) are done
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ws[ps * 32 + tr8][jc + q] = dzv[ps][q];     // now dz [i][j]
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) t += cdot[k][threadIdx.x];
+    if (j0 + threadIdx.x < N) atomicAdd(coldot + (int64_t)g * N + j0 + threadIdx.x, t);
+  }
+  __syncthreads();
+  // dz^T rows: thread = (row j of a 32-row pass, 8 consecutive i)
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int r = ps * 32 + tr8, j = j0 + r, ic = jc;
+    if (j < N && i0 + ic < N) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pk[q] = pack_bf16x2(ws[ic + 2 * q][r], ws[ic + 2 * q + 1][r]);
+      *reinterpret_cast<uint4*>(dZT + ((int64_t)g * N + j) * ldd + i0 + ic) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 7. gradient GEMM epilogue: df = (acc - x * dot) * inv_norm, x = normalised feature (bf16)
 // ------------------------------------------------------------------------------------------
 template <class OutT>
@@ -701,8 +836,15 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
           w.Tsum, w.loss_acc);
       }
       GD3_CHECK_LAUNCH();
-      dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)ceil_div<int64_t>(N, 32), (unsigned)g);
-      {
+      const bool vec_ok = N % 8 == 0 && t_row_stride % 4 == 0 && t_pair_stride % 4 == 0 &&
+                          reinterpret_cast<uintptr_t>(t12) % 16 == 0 && reinterpret_cast<uintptr_t>(t21) % 16 == 0;
+      if (vec_ok) {
+        dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
+        GD3_PROF("kl_build_w_fast", stream);
+        kl_build_w_fast<<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N, w.invR,
+                                                  w.epsm, w.WT, w.ldw);
+      } else {
+        dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)ceil_div<int64_t>(N, 32), (unsigned)g);
         GD3_PROF("kl_build_w", stream);
         kl_build_w<<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N, w.invR, w.epsm,
                                            w.WT, w.ldw);
@@ -730,7 +872,11 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     }
     if (backward) {
       dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
-      {
+      if (N % 8 == 0) {
+        GD3_PROF("kl_dz_fast", stream);
+        kl_dz_fast<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn,
+                                             w.rowdot, w.coldot);
+      } else {
         GD3_PROF("kl_dz", stream);
         kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
                                       w.coldot);
