@@ -822,13 +822,13 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     if ((rc = tc::make_tmap_bf16(&t_w1t, w.W1T, H, D, 1, H, 0, 256))) return rc;
     tc::EpiStoreF32::Params e1{grad_feats, (int)R, (int)D, D, 0, 1.0f, nullptr};
     tc::GemmShape s1{(int)R, (int)D, H, 1};
-    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>("rank_df_gemm", t_du, t_w1t, s1, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("rank_df_gemm", t_du, t_w1t, s1, e1, stream))) return rc;
     // d W1 (H x D) = sum over sets of du_s^T f_s: one batch entry per set, accumulated atomically (split-K)
     if ((rc = tc::make_tmap_bf16(&t_dut, w.duT3, 3 * w.tl.gl, H, w.groups, w.tl.ld, 3 * w.tl.gl, tc::BM))) return rc;
     if ((rc = tc::make_tmap_bf16(&t_ft, w.FT3, 3 * w.tl.gl, D, w.groups, w.tl.ld, 3 * w.tl.gl, 256))) return rc;
     EpiAtomicAddF32::Params e2{grad_params, H, (int)D, D};
     tc::GemmShape s2{H, (int)D, (int)(3 * w.tl.gl), w.groups};
-    if ((rc = tc::launch_gemm<256, 4, EpiAtomicAddF32>("rank_dw1_gemm", t_dut, t_ft, s2, e2, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, EpiAtomicAddF32>("rank_dw1_gemm", t_dut, t_ft, s2, e2, stream))) return rc;
   }
   return GD3_OK;
 }

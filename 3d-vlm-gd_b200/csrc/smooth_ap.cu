@@ -263,8 +263,8 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
     tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, w.scale};
     tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, w.scale};
-    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>("ap_grad_gemm", t_ds, t_d2t, s, e1, stream))) return rc;
-    if ((rc = tc::launch_gemm<256, 4, tc::EpiStoreF32>("ap_grad_gemm", t_dst, t_d1t, s, e2, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("ap_grad_gemm", t_ds, t_d2t, s, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("ap_grad_gemm", t_dst, t_d1t, s, e2, stream))) return rc;
   }
   return GD3_OK;
 }
