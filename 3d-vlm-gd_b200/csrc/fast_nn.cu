@@ -6,8 +6,9 @@
 // the column index into a 64-bit key and reduced with max():
 //     key = orderable(score) << 32 | (0xFFFFFFFF - index)   ->   max score, lowest index on ties,
 // which is exactly torch.max / torch.min semantics (and the strict '<' block merge at :60-61).
-// The column direction (nn_B) is the same kernel with A and B swapped; a*b is commutative in fp32 so
-// both directions see bit-identical scores.
+// The column direction (nn_B) is reduced from the very same accumulators in the same pass, so both directions
+// see bit-identical scores.  The query tile stays resident in shared memory and DB tiles are double-buffered
+// with cp.async.
 #include "../../include/gd3.h"
 #include "common.cuh"
 
@@ -15,7 +16,7 @@ namespace gd3 {
 namespace {
 
 constexpr int TILE = 128;      // rows of Q and rows of DB per tile
-constexpr int KC = 32;         // k-chunk held in shared memory
+constexpr int KC = 24;         // k-chunk held in shared memory (MASt3R descriptors are 24-d: one chunk)
 constexpr int THREADS = 256;   // 16 x 16 threads, 8 x 8 scores each
 
 __device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx) {
@@ -24,21 +25,45 @@ __device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   return (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - idx);
 }
+__device__ __forceinline__ unsigned long long kmax(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// (row, k) panel of X starting at row0 -> smem [k][row]; rows past n are zero
+__device__ __forceinline__ void load_panel_async(float (*dst)[TILE], const float* __restrict__ X, int n, int row0, int D,
+                                                 int k0, int kc) {
+  for (int e = threadIdx.x; e < TILE * kc; e += THREADS) {
+    const int row = e / kc, k = e - row * kc;
+    const int g = row0 + row;
+    if (g < n) cp_async4(&dst[k][row], X + (size_t)g * D + k0 + k);
+    else dst[k][row] = 0.f;
+  }
+}
 
 // Q: (nq, D) queries, DB: (ndb, D).  Each CTA: one 128-row query tile x `tiles_per_cta` DB tiles.
 // MODE 0: score = q.d ; MODE 1: score = -sqrt(max(|q|^2 + |d|^2 - 2 q.d, 0))
-template <int MODE>
+// BOTH: also reduce every tile over its rows -> arg-best query for each DB row (the nn_B direction), from the
+// very same accumulators, so both directions see bit-identical scores in a single pass.
+template <int MODE, bool BOTH>
 __global__ void __launch_bounds__(THREADS, 2)
-    nn_rows_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, int ndb, int D,
-                   int tiles_per_cta, unsigned long long* __restrict__ keys) {
+    nn_tile_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, int ndb, int D, int tiles_per_cta,
+                   unsigned long long* __restrict__ keysQ, unsigned long long* __restrict__ keysDB) {
   __shared__ __align__(16) float sq[KC][TILE];
-  __shared__ __align__(16) float sd[KC][TILE];
+  __shared__ __align__(16) float sd[2][KC][TILE];
   __shared__ float nq2[TILE], nd2[TILE];
+  __shared__ unsigned long long colbest[BOTH ? 8 : 1][TILE];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int q0 = blockIdx.x * TILE;
   const int ndb_tiles = ceil_div(ndb, TILE);
   const int t_begin = blockIdx.y * tiles_per_cta;
   const int t_end = min(t_begin + tiles_per_cta, ndb_tiles);
+  const bool one_chunk = D <= KC;      // whole descriptor in one chunk: Q stays resident, DB tiles are double-buffered
 
   unsigned long long best[8];
 #pragma unroll
@@ -54,9 +79,15 @@ __global__ void __launch_bounds__(THREADS, 2)
       nq2[threadIdx.x] = s;
     }
   }
+  if (one_chunk && t_begin < t_end) {
+    load_panel_async(sq, Q, nq, q0, D, 0, D);
+    load_panel_async(sd[0], DB, ndb, t_begin * TILE, D, 0, D);
+    cp_async_commit();
+  }
 
   for (int t = t_begin; t < t_end; ++t) {
     const int d0 = t * TILE;
+    const int buf = one_chunk ? ((t - t_begin) & 1) : 0;
     float acc[8][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -76,32 +107,40 @@ __global__ void __launch_bounds__(THREADS, 2)
 
     for (int k0 = 0; k0 < D; k0 += KC) {
       const int kc = min(KC, D - k0);
-      __syncthreads();
-      // coalesced global reads of the (row, k) panel, transposed into smem [k][row]
-      for (int e = threadIdx.x; e < TILE * kc; e += THREADS) {
-        const int row = e / kc, k = e - row * kc;
-        const int q = q0 + row, d = d0 + row;
-        sq[k][row] = (q < nq) ? Q[(size_t)q * D + k0 + k] : 0.f;
-        sd[k][row] = (d < ndb) ? DB[(size_t)d * D + k0 + k] : 0.f;
+      if (one_chunk) {
+        // prefetch the next DB tile into the other buffer, then wait for the current one
+        if (t + 1 < t_end) load_panel_async(sd[buf ^ 1], DB, ndb, (t + 1) * TILE, D, 0, D);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+      } else {
+        __syncthreads();
+        load_panel_async(sq, Q, nq, q0, D, k0, kc);
+        load_panel_async(sd[0], DB, ndb, d0, D, k0, kc);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
       }
-      __syncthreads();
       for (int k = 0; k < kc; ++k) {
         const float4 a0 = *reinterpret_cast<const float4*>(&sq[k][ty * 8]);
         const float4 a1 = *reinterpret_cast<const float4*>(&sq[k][ty * 8 + 4]);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         float b[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) b[c] = sd[k][c * 16 + tx];
+        for (int c = 0; c < 8; ++c) b[c] = sd[buf][k][c * 16 + tx];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);   // fixed k order: tiling-independent
       }
     }
-    // fold this tile into the running per-row best; columns visited in increasing index order
+    // fold this tile into the running per-row best (columns in increasing index order) and, for BOTH,
+    // into the per-column best of this tile
+    unsigned long long cb[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int d = d0 + c * 16 + tx;
+      cb[c] = 0ull;
       if (d < ndb) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -110,23 +149,43 @@ __global__ void __launch_bounds__(THREADS, 2)
             const float d2 = (nq2[ty * 8 + r] + nd2[c * 16 + tx]) - 2.0f * s;
             s = -sqrtf(fmaxf(d2, 0.f));
           }
-          const unsigned long long key = pack_key(s, (uint32_t)d);
-          best[r] = key > best[r] ? key : best[r];
+          best[r] = kmax(best[r], pack_key(s, (uint32_t)d));
+          if (BOTH) {
+            const int q = q0 + ty * 8 + r;
+            if (q < nq) cb[c] = kmax(cb[c], pack_key(s, (uint32_t)q));
+          }
         }
       }
     }
+    if (BOTH) {
+      // the two ty groups of a warp first, then the 8 warps through shared memory, then one atomic per DB row
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cb[c] = kmax(cb[c], __shfl_xor_sync(0xffffffffu, cb[c], 16));
+      const int warp = threadIdx.x >> 5;
+      if ((threadIdx.x & 16) == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) colbest[warp][c * 16 + tx] = cb[c];
+      }
+      __syncthreads();
+      if (threadIdx.x < TILE) {
+        unsigned long long k = colbest[0][threadIdx.x];
+#pragma unroll
+        for (int w2 = 1; w2 < 8; ++w2) k = kmax(k, colbest[w2][threadIdx.x]);
+        const int d = d0 + threadIdx.x;
+        if (d < ndb && k != 0ull) atomicMax(&keysDB[d], k);
+      }
+    }
+    if (one_chunk) __syncthreads();   // everyone is done with sd[buf] before the next prefetch overwrites it
   }
+  cp_async_wait<0>();
   // reduce across the 16 threads that share a row group (same ty -> a half warp), then one atomic per row
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     unsigned long long k = best[r];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
-      k = other > k ? other : k;
-    }
+    for (int o = 8; o > 0; o >>= 1) k = kmax(k, __shfl_xor_sync(0xffffffffu, k, o));
     const int q = q0 + ty * 8 + r;
-    if (tx == 0 && q < nq && k != 0ull) atomicMax(&keys[q], k);
+    if (tx == 0 && q < nq && k != 0ull) atomicMax(&keysQ[q], k);
   }
 }
 
@@ -138,9 +197,12 @@ __global__ void nn_unpack_kernel(const unsigned long long* __restrict__ keys, in
   }
 }
 
-int nn_rows(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t D, int dist,
-            unsigned long long* keys, int64_t* out, cudaStream_t stream) {
-  GD3_CHECK_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * nq, stream));
+// arg-best DB row for every Q row (outQ) and, when keysDB / outDB are given, arg-best Q row for every DB row
+int nn_search(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t D, int dist, unsigned long long* keysQ,
+              int64_t* outQ, unsigned long long* keysDB, int64_t* outDB, cudaStream_t stream) {
+  const bool both = outDB != nullptr;
+  GD3_CHECK_CUDA(cudaMemsetAsync(keysQ, 0, sizeof(unsigned long long) * nq, stream));
+  if (both) GD3_CHECK_CUDA(cudaMemsetAsync(keysDB, 0, sizeof(unsigned long long) * ndb, stream));
   const int q_tiles = (int)ceil_div<int64_t>(nq, TILE);
   const int db_tiles = (int)ceil_div<int64_t>(ndb, TILE);
   // aim at ~4 CTAs per SM over the whole grid so that short query sets still fill the chip
@@ -149,22 +211,28 @@ int nn_rows(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t D,
   const int tiles_per_cta = ceil_div(db_tiles, y);
   y = ceil_div(db_tiles, tiles_per_cta);
   dim3 grid(q_tiles, y);
-  if (dist == 0)
-    {
-      GD3_PROF("nn_rows_kernel", stream);
-      nn_rows_kernel<0><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keys);
-    }
-  else
-    {
-      GD3_PROF("nn_rows_kernel", stream);
-      nn_rows_kernel<1><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keys);
-    }
+  {
+    GD3_PROF("nn_tile_kernel", stream);
+    if (dist == 0 && both)
+      nn_tile_kernel<0, true><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+    else if (dist == 0)
+      nn_tile_kernel<0, false><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+    else if (both)
+      nn_tile_kernel<1, true><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+    else
+      nn_tile_kernel<1, false><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+  }
   GD3_CHECK_LAUNCH();
   {
     GD3_PROF("nn_unpack_kernel", stream);
-    nn_unpack_kernel<<<(int)ceil_div<int64_t>(nq, 256), 256, 0, stream>>>(keys, out, (int)nq);
+    nn_unpack_kernel<<<(int)ceil_div<int64_t>(nq, 256), 256, 0, stream>>>(keysQ, outQ, (int)nq);
   }
   GD3_CHECK_LAUNCH();
+  if (both) {
+    GD3_PROF("nn_unpack_kernel", stream);
+    nn_unpack_kernel<<<(int)ceil_div<int64_t>(ndb, 256), 256, 0, stream>>>(keysDB, outDB, (int)ndb);
+    GD3_CHECK_LAUNCH();
+  }
   return GD3_OK;
 }
 
@@ -205,10 +273,8 @@ int gd3_reciprocal_nn(const float* A, int64_t nA, const float* B, int64_t nB, in
   Carver c(workspace);
   unsigned long long* kA = c.take<unsigned long long>(nA);
   unsigned long long* kB = c.take<unsigned long long>(nB);
-  int rc = GD3_OK;
-  if (nn_A && (rc = nn_rows(A, nA, B, nB, dim, dist, kA, nn_A, stream))) return rc;
-  if (nn_B && (rc = nn_rows(B, nB, A, nA, dim, dist, kB, nn_B, stream))) return rc;
-  return GD3_OK;
+  if (nn_A) return nn_search(A, nA, B, nB, dim, dist, kA, nn_A, nn_B ? kB : nullptr, nn_B, stream);
+  return nn_search(B, nB, A, nA, dim, dist, kB, nn_B, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

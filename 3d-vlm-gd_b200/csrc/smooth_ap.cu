@@ -145,10 +145,121 @@ __global__ void __launch_bounds__(256)
     if (c0 + r < K && r0 + lane < K) dst[(int64_t)(c0 + r) * ld + r0 + lane] = tile[lane][r];
 }
 
+// ------------------------------------------------------------------------------------------
+// InfoNCE (upstream MASt3R softmax-CE correspondence loss, mast3r/losses.py:237-272): kernels on the K x K
+// similarity produced by the same split-bf16 GEMM.  E = exp(sim / T) (NaN -> 0), positives on the diagonal.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nce_exp(float sim, float inv_t) {
+  const float v = sim * inv_t;
+  return (v != v) ? 0.f : expf(v);     // sim[sim.isnan()] = -inf  ->  exp = 0
+}
+// grid (K, P): row sums (and the grand total for mode 'all')
+__global__ void __launch_bounds__(128)
+    nce_rowsums(const float* __restrict__ sim, int lds, int K, float inv_t, float* __restrict__ rowsum,
+                double* __restrict__ tot) {
+  __shared__ float red[32];
+  const int i = blockIdx.x, p = blockIdx.y;
+  const float* srow = sim + ((int64_t)p * K + i) * lds;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) s += nce_exp(srow[j], inv_t);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    rowsum[(int64_t)p * K + i] = s;
+    atomicAdd(tot + p, (double)s);
+  }
+}
+// grid (ceil(K/32), P), block 256: column sums, 32 columns per CTA, rows split over 8 warps
+__global__ void __launch_bounds__(256)
+    nce_colsums(const float* __restrict__ sim, int lds, int K, float inv_t, float* __restrict__ colsum) {
+  __shared__ float part[8][32];
+  const int p = blockIdx.y, j = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+  const float* S = sim + (int64_t)p * K * lds;
+  float s = 0.f;
+  if (j < K)
+    for (int i = w; i < K; i += 8) s += nce_exp(S[(int64_t)i * lds + j], inv_t);
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (threadIdx.x < 32 && j < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+    colsum[(int64_t)p * K + j] = t;
+  }
+}
+// grid (K, P), block 128: per-row loss and d loss / d sim (row i), unnormalised by the number of valid rows.
+// mode 0 'all', 1 'proper', 2 'dual'.  va / vc: this row's / each column's "term is active and valid" weight.
+__global__ void __launch_bounds__(128)
+    nce_rows(const float* __restrict__ sim, int lds, int K, float inv_t, float eps, int mode,
+             const uint8_t* __restrict__ valid, const float* __restrict__ rowsum, const float* __restrict__ colsum,
+             const double* __restrict__ tot, float* __restrict__ row_loss, __nv_bfloat16* __restrict__ dS, int ldk,
+             double* __restrict__ loss_acc, int* __restrict__ qcount) {
+  const int i = blockIdx.x, p = blockIdx.y;
+  const float* srow = sim + ((int64_t)p * K + i) * lds;
+  const float* rs = rowsum + (int64_t)p * K;
+  const float* cs = colsum + (int64_t)p * K;
+  const uint8_t* vm = valid ? valid + (int64_t)p * K : nullptr;
+  const float total = (float)tot[p];
+  // weight of row r's loss and which of its log terms is not clipped
+  auto terms = [&](int r, float& w_row, float& w_col) {
+    const bool v = vm ? vm[r] != 0 : true;
+    const float pos = nce_exp(sim[((int64_t)p * K + r) * lds + r], inv_t);
+    w_row = 0.f; w_col = 0.f;
+    if (!v) return;
+    if (mode == 0) { w_row = (pos / total >= eps) ? 1.f : 0.f; }
+    else if (mode == 1) { w_row = (pos / rs[r] >= eps) ? 1.f : 0.f; w_col = (pos / cs[r] >= eps) ? 1.f : 0.f; }
+    else { const float a = (pos * pos / rs[r] / cs[r] >= eps) ? 1.f : 0.f; w_row = a; w_col = a; }
+  };
+  float wr_i, wc_i;
+  terms(i, wr_i, wc_i);
+  float nact = 0.f;       // mode 'all': number of valid rows of this pair whose log term is not clipped
+  if (mode == 0 && dS) {
+    __shared__ float red[32];
+    float c = 0.f;
+    for (int r = threadIdx.x; r < K; r += blockDim.x) {
+      float a, b;
+      terms(r, a, b);
+      c += a;
+    }
+    nact = block_sum(c, red);
+  }
+  if (threadIdx.x == 0) {
+    const bool v = vm ? vm[i] != 0 : true;
+    const float pos = nce_exp(srow[i], inv_t);
+    float l = 0.f;
+    if (mode == 0) l = -logf(fmaxf(pos / total, eps));
+    else if (mode == 1) l = -(logf(fmaxf(pos / cs[i], eps)) + logf(fmaxf(pos / rs[i], eps)));
+    else l = -logf(fmaxf(pos * pos / rs[i] / cs[i], eps));
+    row_loss[(int64_t)p * K + i] = v ? l : 0.f;
+    if (v) {
+      atomicAdd(loss_acc, (double)l);
+      atomicAdd(qcount, 1);
+    }
+  }
+  if (!dS) return;
+  __nv_bfloat16* drow = dS + ((int64_t)p * K + i) * ldk;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) {
+    const float e = nce_exp(srow[j], inv_t);
+    float g;
+    if (mode == 0) {
+      // d/ds_ij of sum_k w_k (-s_kk + log total) = n_active * E_ij / total - delta_ij w_i
+      g = nact * e / total;
+      if (j == i) g -= wr_i;
+    } else {
+      float wr_j, wc_j;
+      terms(j, wr_j, wc_j);
+      g = wr_i * e / rs[i] + wc_j * e / cs[j];
+      if (j == i) g -= (wr_i + wc_i);
+    }
+    drow[j] = __float2bfloat16(g * inv_t);
+  }
+}
+
 struct APWorkspace {
   __nv_bfloat16 *A3, *B3, *d1T, *d2T, *dS, *dST;
   float *sim, *scale;
+  float *rowsum, *colsum;     // InfoNCE: (P, K) each
   double* loss_acc;
+  double* tot;                // InfoNCE 'all': (P) sum of all exp
   int* qcount;
   size_t total;
   int ldc, ldk, lds;
@@ -168,7 +279,10 @@ APWorkspace carve_ap(void* base, int64_t P, int64_t K, int64_t C, bool backward)
   w.dST = c.take<__nv_bfloat16>(backward ? P * K * w.ldk : 0);
   w.sim = c.take<float>(P * K * w.lds);
   w.scale = c.take<float>(P);
+  w.rowsum = c.take<float>(P * K);
+  w.colsum = c.take<float>(P * K);
   w.loss_acc = c.take<double>(P);
+  w.tot = c.take<double>(P);
   w.qcount = c.take<int>(P);
   w.total = c.total();
   return w;
@@ -265,6 +379,100 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, w.scale};
     if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("ap_grad_gemm", t_ds, t_d2t, s, e1, stream))) return rc;
     if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("ap_grad_gemm", t_dst, t_d1t, s, e2, stream))) return rc;
+  }
+  return GD3_OK;
+}
+
+size_t gd3_infonce_workspace(int64_t P, int64_t K, int64_t C, int with_backward) {
+  return gd3_smooth_ap_workspace(P, K, C, with_backward);
+}
+
+int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t P, int64_t K, int64_t C, int mode,
+                float temperature, float eps, float grad_scale, float* loss_mean, float* row_loss, float* grad_d1,
+                float* grad_d2, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GD3_REQUIRE(P > 0 && K > 0 && C > 0, "gd3_infonce: bad sizes P=%lld K=%lld C=%lld", (long long)P, (long long)K,
+              (long long)C);
+  GD3_REQUIRE(d1 && d2 && loss_mean && row_loss, "gd3_infonce: null pointer");
+  GD3_REQUIRE(mode >= 0 && mode <= 2, "gd3_infonce: mode must be 0 (all), 1 (proper) or 2 (dual)");
+  GD3_REQUIRE(temperature > 0.f, "gd3_infonce: temperature must be positive");
+  GD3_REQUIRE((grad_d1 == nullptr) == (grad_d2 == nullptr), "gd3_infonce: pass both gradients or neither");
+  GD3_REQUIRE(P <= 65535 && K <= 65535, "gd3_infonce: P, K <= 65535 supported");
+  const bool backward = grad_d1 != nullptr;
+  APWorkspace w = carve_ap(workspace, P, K, C, backward);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("gd3_infonce: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return GD3_ERR_WORKSPACE;
+  }
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double), stream));
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.tot, 0, sizeof(double) * P, stream));
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int), stream));
+  int rc;
+  {
+    XtLayout xt{backward ? 1 : 0, (int)K, 1, w.ldk, w.ldk, w.ldk, C * (int64_t)w.ldk};
+    if ((rc = launch_split3("nce_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, backward ? w.d1T : nullptr, xt, stream)))
+      return rc;
+    if ((rc = launch_split3("nce_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, backward ? w.d2T : nullptr, xt, stream)))
+      return rc;
+    CUtensorMap ta, tb;
+    if ((rc = tc::make_tmap_bf16(&ta, w.A3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc,
+                                 tc::BM)))
+      return rc;
+    if ((rc = tc::make_tmap_bf16(&tb, w.B3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 128)))
+      return rc;
+    tc::EpiStoreF32::Params ep{w.sim, (int)K, (int)K, w.lds, K * (int64_t)w.lds, 1.0f, nullptr};
+    tc::GemmShape s{(int)K, (int)K, 3 * w.ldc, (int)P};
+    if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>("nce_sim_gemm", ta, tb, s, ep, stream))) return rc;
+  }
+  const float inv_t = 1.f / temperature;
+  {
+    dim3 grid((unsigned)K, (unsigned)P);
+    {
+      GD3_PROF("nce_rowsums", stream);
+      nce_rowsums<<<grid, 128, 0, stream>>>(w.sim, w.lds, (int)K, inv_t, w.rowsum, w.tot);
+    }
+    GD3_CHECK_LAUNCH();
+    dim3 gridc((unsigned)ceil_div<int64_t>(K, 32), (unsigned)P);
+    {
+      GD3_PROF("nce_colsums", stream);
+      nce_colsums<<<gridc, 256, 0, stream>>>(w.sim, w.lds, (int)K, inv_t, w.colsum);
+    }
+    GD3_CHECK_LAUNCH();
+    {
+      GD3_PROF("nce_rows", stream);
+      nce_rows<<<grid, 128, 0, stream>>>(w.sim, w.lds, (int)K, inv_t, eps, mode, valid, w.rowsum, w.colsum, w.tot,
+                                         row_loss, backward ? w.dS : nullptr, w.ldk, w.loss_acc, w.qcount);
+    }
+    GD3_CHECK_LAUNCH();
+    // one mean over every valid row of the batch: loss_acc[0] / qcount[0] (ap_finalize with P = 1)
+    {
+      GD3_PROF("ap_finalize", stream);
+      ap_finalize<<<1, 32, 0, stream>>>(w.loss_acc, w.qcount, loss_mean, w.scale, 1);
+    }
+    GD3_CHECK_LAUNCH();
+  }
+  if (backward) {
+    dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)ceil_div<int64_t>(K, 32), (unsigned)P);
+    {
+      GD3_PROF("transpose_bf16", stream);
+      transpose_bf16<<<grid, 256, 0, stream>>>(w.dS, w.dST, (int)K, w.ldk);
+    }
+    GD3_CHECK_LAUNCH();
+    CUtensorMap t_ds, t_dst, t_d1t, t_d2t;
+    if ((rc = tc::make_tmap_bf16(&t_ds, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_dst, w.dST, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d1t, w.d1T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d2t, w.d2T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
+    tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
+    // every batch entry is scaled by the same 1 / n_valid (scale[0]); stride-0 read via a per-batch pointer of 1 entry
+    tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, nullptr};
+    tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, nullptr};
+    e1.batch_scale = w.scale;
+    e2.batch_scale = w.scale;
+    e1.batch_scale_stride0 = 1;
+    e2.batch_scale_stride0 = 1;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("nce_grad_gemm", t_ds, t_d2t, s, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("nce_grad_gemm", t_dst, t_d1t, s, e2, stream))) return rc;
   }
   return GD3_OK;
 }

@@ -594,12 +594,13 @@ struct EpiStoreF32 {
     int64_t ldc, batch_stride;
     float alpha;
     const float* batch_scale;   // optional per-batch factor read from device memory (nullptr = 1)
+    int batch_scale_stride0 = 0;   // 1: every batch entry uses batch_scale[0]
   };
   struct Pre {};
   __device__ static void pre(const Params&, const EpiCtx&, Pre&) {}
   __device__ static void run(const Params& p, const EpiCtx& cx, const Pre&) {
     const int m = cx.m0 + cx.row;
-    const float alpha = p.batch_scale ? p.alpha * __ldg(p.batch_scale + cx.b) : p.alpha;
+    const float alpha = p.batch_scale ? p.alpha * __ldg(p.batch_scale + (p.batch_scale_stride0 ? 0 : cx.b)) : p.alpha;
     float* crow = p.C + cx.b * p.batch_stride + static_cast<int64_t>(m) * p.ldc;
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         (p.batch_stride % 4 == 0);

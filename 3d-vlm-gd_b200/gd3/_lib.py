@@ -29,6 +29,8 @@ SYMBOLS = {
     'gd3_smooth_ap_workspace': (_sz, [_i64, _i64, _i64, _int]),
     'gd3_smooth_ap': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp,
                              _sz, _vp]),
+    'gd3_infonce_workspace': (_sz, [_i64, _i64, _i64, _int]),
+    'gd3_infonce': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd3_depth_head_loss_workspace': (_sz, [_i64, _i64, _i64, _int, _int]),
     'gd3_depth_head_loss': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _int,
                                    _f32, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -159,6 +159,59 @@ def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1
     return _SmoothAP.apply(d1, d2, pts3d_1, pts3d_2, variant, temp, thr_neg, thr_pos, torch.is_grad_enabled())
 
 
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d1, d2, valid, mode, temperature, eps, grad_mode):
+        require_cuda(d1, d2)
+        lib = load()
+        if d1.dim() != 3 or d1.shape != d2.shape:
+            raise ValueError(f'infonce: descriptors must both be (B, N, D), got {tuple(d1.shape)} {tuple(d2.shape)}')
+        P, K, C = d1.shape
+        dev = d1.device
+        a = d1.to(_F32).contiguous()
+        b = d2.to(_F32).contiguous()
+        vm = None
+        if valid is not None:
+            if tuple(valid.shape) != (P, K):
+                raise ValueError(f'infonce: valid_matches must be (B, N) = {(P, K)}')
+            vm = valid.to(dev).to(torch.uint8).contiguous()
+        need_grad = grad_mode and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        loss = torch.zeros(1, dtype=_F32, device=dev)
+        rows = torch.zeros(P, K, dtype=_F32, device=dev)
+        g1 = torch.empty(P, K, C, dtype=_F32, device=dev) if need_grad else None
+        g2 = torch.empty(P, K, C, dtype=_F32, device=dev) if need_grad else None
+        if P and K:
+            ws = workspace(lib.gd3_infonce_workspace(P, K, C, int(need_grad)), dev)
+            with torch.cuda.device(dev):
+                check(lib.gd3_infonce(ptr(a), ptr(b), ptr(vm), P, K, C, {'all': 0, 'proper': 1, 'dual': 2}[mode],
+                                      float(temperature), float(eps), 1.0, ptr(loss), ptr(rows), ptr(g1), ptr(g2),
+                                      ptr(ws), ws.numel(), stream_ptr()))
+        ctx.save_for_backward(g1, g2)
+        ctx.in_dtypes = (d1.dtype, d2.dtype)
+        ctx.mark_non_differentiable(rows)
+        return loss[0], rows
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_rows):
+        g1, g2 = ctx.saved_tensors
+        if g1 is None:
+            return (None,) * 7
+        s = g_loss.to(_F32)
+        return (g1 * s).to(ctx.in_dtypes[0]), (g2 * s).to(ctx.in_dtypes[1]), None, None, None, None, None
+
+
+def infonce(desc1, desc2, valid_matches=None, temperature=0.07, eps=1e-8, mode='all'):
+    """Upstream MASt3R InfoNCE (softmax-CE correspondence loss) with the 'mean' reduction.
+
+    desc1, desc2: (B, N, D); positives on the diagonal; mode 'all' | 'proper' | 'dual'
+    (mast3r/losses.py:237-272).  Returns ``(loss, row_losses (B, N))``; ``loss`` is the mean over the valid rows
+    and carries the gradient.  No fine-tune script of the reference uses it.
+    """
+    if mode not in ('all', 'proper', 'dual'):
+        raise ValueError(f'infonce: unknown mode {mode!r}')
+    return _InfoNCE.apply(desc1, desc2, valid_matches, mode, temperature, eps, torch.is_grad_enabled())
+
+
 # --------------------------------------------------------------------------------------------
 # relative-depth losses on the depth-difference head
 # --------------------------------------------------------------------------------------------

@@ -112,6 +112,21 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
                   float* grad_d1, float* grad_d2, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * InfoNCE softmax-CE correspondence loss (upstream MASt3R criterion, mast3r/losses.py:237-272 with
+ * get_similarities :202-209 and the 'mean' reduction of MatchingCriterion.forward :217-231).  No src/ script of
+ * the reference calls it; it is provided because the task statement words the correspondence loss as
+ * "softmax-CE" (SURVEY.md section 8, row a3b).  Shares the split-bf16 similarity GEMM with gd3_smooth_ap.
+ *   d1, d2  (P, K, C) fp32 contiguous descriptors; valid (P, K) uint8 or NULL (all valid)
+ *   mode    0 'all', 1 'proper', 2 'dual';  temperature 0.07, eps 1e-8 in the reference
+ *   loss_mean (1): mean over all valid rows of the batch;  row_loss (P, K): per-row values (0 where invalid)
+ *   grad_d1/2 (P, K, C) fp32: gradient of grad_scale * loss_mean (both NULL = forward only)
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_infonce_workspace(int64_t P, int64_t K, int64_t C, int with_backward);
+int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t P, int64_t K, int64_t C, int mode,
+                float temperature, float eps, float grad_scale, float* loss_mean, float* row_loss, float* grad_d1,
+                float* grad_d2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Relative-depth losses on the depth-difference head, forward + backward, batched over S keypoint
  * sets (one set = the keypoints of one image).  Replaces pairwise_logistic_ranking_loss
  * (utils/losses.py:18-41, mode 0), intra_depth_loss (utils/losses.py:44-69, mode 1), the head

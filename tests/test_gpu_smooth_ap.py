@@ -105,3 +105,30 @@ def test_smooth_ap_edge_cases():
     dd = d.clone().requires_grad_(True)
     l1 = ops.smooth_ap(dd, d, p1, p1 + 0.001, variant='vggt')
     assert abs(l0[0].item() - l1[0].item()) < 1e-6
+
+
+@pytest.mark.parametrize('mode', ['all', 'proper', 'dual'])
+def test_infonce_golden_and_gradients(golden, mode):
+    """Upstream MASt3R InfoNCE: forward against the live reference's values, gradients against the oracle."""
+    from gd3 import ops
+    from oracle import losses as olosses
+    g = golden('helpers.npz')
+    d1, d2, vm = T(g['infonce/d1']), T(g['infonce/d2']), T(g['infonce/valid'])
+    a = d1.cuda().requires_grad_(True)
+    b = d2.cuda().requires_grad_(True)
+    loss, rows = ops.infonce(a, b, vm.cuda(), mode=mode)
+    assert rel_err(loss.item(), g[f'infonce/{mode}']) <= 1e-4
+    loss.backward()
+    ra = d1.clone().requires_grad_(True)
+    rb = d2.clone().requires_grad_(True)
+    olosses.infonce(ra, rb, vm, mode=mode).backward()
+    assert_grad_close(a.grad, ra.grad, name='d1', norm_rtol=3e-2)
+    assert_grad_close(b.grad, rb.grad, name='d2', norm_rtol=3e-2)
+    # larger, all valid, descriptor size of MASt3R (24) and of the student (768)
+    for K, D in ((300, 24), (512, 768)):
+        gen = synth._gen(K + D)
+        x = torch.nn.functional.normalize(torch.randn(2, K, D, generator=gen), dim=-1)
+        y = torch.nn.functional.normalize(x + 0.2 * torch.randn(2, K, D, generator=gen), dim=-1)
+        want = olosses.infonce(x, y, None, mode=mode)
+        got, _ = ops.infonce(x.cuda(), y.cuda(), None, mode=mode)
+        assert rel_err(got.item(), float(want)) <= 1e-3, (K, D, got.item(), float(want))
