@@ -780,6 +780,7 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
   const float masked_const = variant == GD3_VARIANT_MAST3R ? (float)(ne * log(ne)) : 0.f;
 
   CUtensorMap tm_a, tm_b, tm_dz, tm_dzt, tm_at, tm_bt;
+  int tmap_bn = 256;   // box rows of tm_at / tm_bt
   int rc;
   if ((rc = tc::make_tmap_bf16(&tm_a, w.a, C, N, G, w.ldc, N * (int64_t)w.ldc, tc::BM))) return rc;
   if ((rc = tc::make_tmap_bf16(&tm_b, w.b, C, N, G, w.ldc, N * (int64_t)w.ldc, 256))) return rc;
@@ -883,21 +884,32 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       }
       GD3_CHECK_LAUNCH();
       tc::GemmShape s{(int)N, (int)C, (int)N, g};
-      if (dtype == GD3_DTYPE_F32) {
-        using E = EpiGradOut<float>;
-        E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1, static_cast<float*>(grad_f1) + p0 * N * C};
-        E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2, static_cast<float*>(grad_f2) + p0 * N * C};
-        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
-        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
-      } else {
-        using E = EpiGradOut<__nv_bfloat16>;
-        E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1,
-                     static_cast<__nv_bfloat16*>(grad_f1) + p0 * N * C};
-        E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2,
-                     static_cast<__nv_bfloat16*>(grad_f2) + p0 * N * C};
-        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return rc;
-        if ((rc = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream))) return rc;
+      const int bn = tc::pick_tile_n(s);
+      // B operands (bT, aT) need a TMA box of `bn` rows
+      if (bn != tmap_bn) {
+        if ((rc = tc::make_tmap_bf16(&tm_at, w.aT, N, C, G, w.ldn, C * (int64_t)w.ldn, bn))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tm_bt, w.bT, N, C, G, w.ldn, C * (int64_t)w.ldn, bn))) return rc;
+        tmap_bn = bn;
       }
+      auto run_grad = [&](auto tag) -> int {
+        using E = EpiGradOut<decltype(tag)>;
+        using OutT = decltype(tag);
+        typename E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1, static_cast<OutT*>(grad_f1) + p0 * N * C};
+        typename E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2, static_cast<OutT*>(grad_f2) + p0 * N * C};
+        int r;
+        if (bn == 256) {
+          if ((r = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;
+          return tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);
+        } else if (bn == 192) {
+          if ((r = tc::launch_gemm<192, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;
+          return tc::launch_gemm<192, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);
+        }
+        if ((r = tc::launch_gemm<128, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;
+        return tc::launch_gemm<128, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);
+      };
+      if (dtype == GD3_DTYPE_F32) rc = run_grad(float{});
+      else rc = run_grad(__nv_bfloat16{});
+      if (rc) return rc;
     }
   }
   return GD3_OK;

@@ -27,7 +27,7 @@ constexpr int UMMA_K = 16;       // K per tcgen05.mma for 16-bit inputs
 constexpr int PRODUCER_WARPS = 2;  // warp 0 = TMA, warp 1 = MMA
 
 __host__ __device__ constexpr int stage_bytes(int BN) { return (BM + BN) * BK * 2; }
-__host__ __device__ constexpr int num_stages(int BN) { return BN >= 256 ? 4 : (BN >= 128 ? 6 : 8); }
+__host__ __device__ constexpr int num_stages(int BN) { return BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8)); }
 // dynamic smem: 1024 B alignment slack + ring + epilogue scratch + barriers
 __host__ __device__ constexpr int smem_bytes(int BN, int epi_scratch) {
   return 1024 + num_stages(BN) * stage_bytes(BN) + epi_scratch + 256;
@@ -517,6 +517,24 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t k_extent, int64_t
 struct GemmShape {
   int M, N, K, batch;
 };
+
+// Tile width with the least wave-quantisation loss: a persistent launch runs ceil(tiles / SMs) rounds whose cost is
+// proportional to the tile width.  Candidates 256 / 192 / 128 (wider tiles reuse A better, so they win ties).
+inline int pick_tile_n(const GemmShape& s) {
+  const int cand[3] = {256, 192, 128};
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn : cand) {
+    const long long tiles = 1LL * ceil_div(s.M, BM) * ceil_div(s.N, bn) * s.batch;
+    const double rounds = (double)ceil_div<long long>(tiles, num_sms());
+    const double cost = rounds * bn * (1.0 + 0.02 * (256 - bn) / 64.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
 
 template <int BN, int EPI_WARPS, class Epi>
 int launch_gemm(const char* name, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
