@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 template <class OutT>
 struct EpiGradOut {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = tc::kMaxEpiWarps * tc::kWarpTileBytes;
   struct Params {
     int N, C;
     const __nv_bfloat16* X;   // (G, N, ldc) normalised features of the image being differentiated
@@ -607,6 +607,7 @@ struct EpiGradOut {
   };
   // x (the normalised feature row of this thread) does not depend on the accumulator: the loads for the
   // first 32 columns are issued before the tile's MMAs are awaited, the following ones one chunk ahead.
+  // df goes out through the per-warp shared-memory transposition so that stores cover whole row segments.
   struct Pre {
     uint4 x[4];
     float dot, inv;
@@ -630,11 +631,14 @@ struct EpiGradOut {
     }
   }
   __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre& pr) {
+    float* t = reinterpret_cast<float*>(cx.scratch) + cx.epi_warp * tc::kWarpTileFloats;
     const int i = cx.m0 + cx.row;
     const bool row_ok = i < p.N;
+    const int m_warp = cx.m0 + (cx.row & ~31);
+    const int rows = p.N - m_warp;
     const float dot = pr.dot, inv = pr.inv;
     const __nv_bfloat16* x = p.X + ((int64_t)cx.b * p.N + i) * p.ldc;
-    OutT* o = p.out + ((int64_t)cx.b * p.N + i) * p.C;
+    OutT* oslab = p.out + ((int64_t)cx.b * p.N + m_warp) * p.C;
     const bool vec = (p.C % 8 == 0);
     uint4 xn[4] = {pr.x[0], pr.x[1], pr.x[2], pr.x[3]};
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
@@ -644,35 +648,25 @@ struct EpiGradOut {
       if (row_ok && vec && c + 32 < cx.col_end && c0 + 64 <= p.C) load_x(p, cx, i, c0 + 32, xn);   // next chunk
       float v[32];
       tc::tmem_ld32(cx.tmem + c, v);
-      if (!row_ok) continue;
+      if (rows <= 0) continue;
       if (vec && c0 + 32 <= p.C) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t xs[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
-          float r[8];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            r[2 * h] = (v[8 * q + 2 * h] - bf16_bits_to_float(xs[h] & 0xFFFFu) * dot) * inv;
-            r[2 * h + 1] = (v[8 * q + 2 * h + 1] - bf16_bits_to_float(xs[h] >> 16) * dot) * inv;
-          }
-          if constexpr (sizeof(OutT) == 4) {
-            float4* dst = reinterpret_cast<float4*>(o + c0 + 8 * q);
-            dst[0] = make_float4(r[0], r[1], r[2], r[3]);
-            dst[1] = make_float4(r[4], r[5], r[6], r[7]);
-          } else {
-            *reinterpret_cast<uint4*>(o + c0 + 8 * q) =
-                make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                           pack_bf16x2(r[6], r[7]));
+            v[8 * q + 2 * h] = (v[8 * q + 2 * h] - bf16_bits_to_float(xs[h] & 0xFFFFu) * dot) * inv;
+            v[8 * q + 2 * h + 1] = (v[8 * q + 2 * h + 1] - bf16_bits_to_float(xs[h] >> 16) * dot) * inv;
           }
         }
       } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (c0 + q < p.C) {
-            const float r = (v[q] - __bfloat162float(x[c0 + q]) * dot) * inv;
-            if constexpr (sizeof(OutT) == 4) o[c0 + q] = r; else o[c0 + q] = __float2bfloat16(r);
-          }
+        for (int q = 0; q < 32; ++q) {
+          const float xv = (row_ok && c0 + q < p.C) ? __bfloat162float(x[c0 + q]) : 0.f;
+          v[q] = (v[q] - xv * dot) * inv;
+        }
       }
+      tc::warp_store_rows<OutT>(t, v, oslab + c0, p.C, rows, p.C - c0, cx.lane);
     }
   }
 };
@@ -780,7 +774,7 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
   const float masked_const = variant == GD3_VARIANT_MAST3R ? (float)(ne * log(ne)) : 0.f;
 
   CUtensorMap tm_a, tm_b, tm_dz, tm_dzt, tm_at, tm_bt;
-  int tmap_bn = 256;   // box rows of tm_at / tm_bt
+  int tmap_bn = 256;   // box rows of tm_at / tm_bt (half a tile in the 2-CTA kernels)
   int rc;
   if ((rc = tc::make_tmap_bf16(&tm_a, w.a, C, N, G, w.ldc, N * (int64_t)w.ldc, tc::BM))) return rc;
   if ((rc = tc::make_tmap_bf16(&tm_b, w.b, C, N, G, w.ldc, N * (int64_t)w.ldc, 256))) return rc;
@@ -884,12 +878,15 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       }
       GD3_CHECK_LAUNCH();
       tc::GemmShape s{(int)N, (int)C, (int)N, g};
-      const int bn = tc::pick_tile_n(s);
-      // B operands (bT, aT) need a TMA box of `bn` rows
-      if (bn != tmap_bn) {
-        if ((rc = tc::make_tmap_bf16(&tm_at, w.aT, N, C, G, w.ldn, C * (int64_t)w.ldn, bn))) return rc;
-        if ((rc = tc::make_tmap_bf16(&tm_bt, w.bT, N, C, G, w.ldn, C * (int64_t)w.ldn, bn))) return rc;
-        tmap_bn = bn;
+      // 128 x bn single-CTA tiles by default; GD3_KL_GRAD_2SM=1 selects the 2-CTA kernel (256 x bn per CTA pair, each
+      // CTA staging half of the B tile) for A/B measurements - at these shapes it is within 5% of the 1-CTA kernel
+      static const bool one_sm = [] { const char* e = getenv("GD3_KL_GRAD_2SM"); return !(e && e[0] == '1'); }();
+      const int bn = tc::pick_tile_n(s, one_sm ? 1 : 2);
+      const int box = one_sm ? bn : bn / 2;
+      if (box != tmap_bn) {
+        if ((rc = tc::make_tmap_bf16(&tm_at, w.aT, N, C, G, w.ldn, C * (int64_t)w.ldn, box))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tm_bt, w.bT, N, C, G, w.ldn, C * (int64_t)w.ldn, box))) return rc;
+        tmap_bn = box;
       }
       auto run_grad = [&](auto tag) -> int {
         using E = EpiGradOut<decltype(tag)>;
@@ -897,15 +894,19 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         typename E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1, static_cast<OutT*>(grad_f1) + p0 * N * C};
         typename E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2, static_cast<OutT*>(grad_f2) + p0 * N * C};
         int r;
-        if (bn == 256) {
-          if ((r = tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;
-          return tc::launch_gemm<256, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);
-        } else if (bn == 192) {
-          if ((r = tc::launch_gemm<192, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;
-          return tc::launch_gemm<192, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);
-        }
-        if ((r = tc::launch_gemm<128, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;
-        return tc::launch_gemm<128, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);
+#define GD3_KL_GRAD(BN)                                                                                   \
+  do {                                                                                                    \
+    if (one_sm) {                                                                                         \
+      if ((r = tc::launch_gemm<BN, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;         \
+      return tc::launch_gemm<BN, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);                     \
+    }                                                                                                     \
+    if ((r = tc::launch_gemm_2sm<BN, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;       \
+    return tc::launch_gemm_2sm<BN, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);                   \
+  } while (0)
+        if (bn == 256) GD3_KL_GRAD(256);
+        if (bn == 192) GD3_KL_GRAD(192);
+        GD3_KL_GRAD(128);
+#undef GD3_KL_GRAD
       };
       if (dtype == GD3_DTYPE_F32) rc = run_grad(float{});
       else rc = run_grad(__nv_bfloat16{});

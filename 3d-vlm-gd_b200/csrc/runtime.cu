@@ -157,25 +157,23 @@ int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64
                         int64_t lda, int64_t ldb, int64_t ldc, int tile_n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GD3_REQUIRE(A && B && C, "gd3_debug_gemm_bf16: null pointer");
-  GD3_REQUIRE(tile_n == 128 || tile_n == 256 || tile_n == -256 || tile_n == -128,
-              "gd3_debug_gemm_bf16: tile_n must be 128 or 256 (negative = 2-CTA kernel)");
+  const int bn = tile_n < 0 ? -tile_n : tile_n;
+  GD3_REQUIRE(bn == 128 || bn == 192 || bn == 256, "gd3_debug_gemm_bf16: tile_n must be +-128, +-192 or +-256");
   CUtensorMap ta, tb;
   int rc;
-  if (tile_n < 0) {
-    // 2-CTA (cta_group::2) kernel: 256 x |tile_n| tiles, each CTA loads half of the B tile
-    const int bn = -tile_n;
-    if ((rc = tc::make_tmap_bf16(&ta, A, K, M, batch, lda, M * lda, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&tb, B, K, N, batch, ldb, N * ldb, bn / 2))) return rc;
-    tc::EpiStoreF32::Params ep2{C, (int)M, (int)N, ldc, M * ldc, 1.0f, nullptr};
-    tc::GemmShape s2{(int)M, (int)N, (int)K, (int)batch};
-    if (bn == 256) return tc::launch_gemm_2sm<256, 4, tc::EpiStoreF32>("debug_gemm_2sm", ta, tb, s2, ep2, stream);
-    return tc::launch_gemm_2sm<128, 8, tc::EpiStoreF32>("debug_gemm_2sm", ta, tb, s2, ep2, stream);
-  }
-  if ((rc = tc::make_tmap_bf16(&ta, A, K, M, batch, lda, M * lda, tc::BM))) return rc;
-  if ((rc = tc::make_tmap_bf16(&tb, B, K, N, batch, ldb, N * ldb, tile_n))) return rc;
   tc::EpiStoreF32::Params ep{C, (int)M, (int)N, ldc, M * ldc, 1.0f, nullptr};
   tc::GemmShape s{(int)M, (int)N, (int)K, (int)batch};
-  if (tile_n == 256) return tc::launch_gemm<256, 4, tc::EpiStoreF32>("debug_gemm", ta, tb, s, ep, stream);
+  if ((rc = tc::make_tmap_bf16(&ta, A, K, M, batch, lda, M * lda, tc::BM))) return rc;
+  if (tile_n < 0) {
+    // 2-CTA (cta_group::2) kernel: 256 x bn tiles, each CTA loads half of the B tile
+    if ((rc = tc::make_tmap_bf16(&tb, B, K, N, batch, ldb, N * ldb, bn / 2))) return rc;
+    if (bn == 256) return tc::launch_gemm_2sm<256, 8, tc::EpiStoreF32>("debug_gemm_2sm", ta, tb, s, ep, stream);
+    if (bn == 192) return tc::launch_gemm_2sm<192, 8, tc::EpiStoreF32>("debug_gemm_2sm", ta, tb, s, ep, stream);
+    return tc::launch_gemm_2sm<128, 8, tc::EpiStoreF32>("debug_gemm_2sm", ta, tb, s, ep, stream);
+  }
+  if ((rc = tc::make_tmap_bf16(&tb, B, K, N, batch, ldb, N * ldb, bn))) return rc;
+  if (bn == 256) return tc::launch_gemm<256, 8, tc::EpiStoreF32>("debug_gemm", ta, tb, s, ep, stream);
+  if (bn == 192) return tc::launch_gemm<192, 8, tc::EpiStoreF32>("debug_gemm", ta, tb, s, ep, stream);
   return tc::launch_gemm<128, 8, tc::EpiStoreF32>("debug_gemm", ta, tb, s, ep, stream);
 }
 

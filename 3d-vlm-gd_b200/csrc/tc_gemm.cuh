@@ -27,10 +27,14 @@ constexpr int UMMA_K = 16;       // K per tcgen05.mma for 16-bit inputs
 constexpr int PRODUCER_WARPS = 2;  // warp 0 = TMA, warp 1 = MMA
 
 __host__ __device__ constexpr int stage_bytes(int BN) { return (BM + BN) * BK * 2; }
-__host__ __device__ constexpr int num_stages(int BN) { return BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8)); }
-// dynamic smem: 1024 B alignment slack + ring + epilogue scratch + barriers
+constexpr int kSmemBudget = 227 * 1024;
+// as many stages as fit next to the epilogue scratch (at most 8): 1024 B alignment slack + ring + scratch + barriers
+__host__ __device__ constexpr int num_stages(int BN, int epi_scratch = 0) {
+  const int fit = (kSmemBudget - 1024 - 256 - epi_scratch) / stage_bytes(BN);
+  return fit > 8 ? 8 : fit;
+}
 __host__ __device__ constexpr int smem_bytes(int BN, int epi_scratch) {
-  return 1024 + num_stages(BN) * stage_bytes(BN) + epi_scratch + 256;
+  return 1024 + num_stages(BN, epi_scratch) * stage_bytes(BN) + epi_scratch + 256;
 }
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -168,13 +172,15 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
                    int tiles_n, int batch, int k_blocks, typename Epi::Params ep) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS");
-  constexpr int STAGES = num_stages(BN);
+  constexpr int STAGES = num_stages(BN, Epi::kScratchBytes);
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int STAGE_BYTES = stage_bytes(BN);
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ symbol (not a uintptr_t round trip) keeps the address space visible to the
+  // compiler, so epilogue scratch accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
   uint8_t* scratch = ring + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + Epi::kScratchBytes);
@@ -362,9 +368,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 }
 
 __host__ __device__ constexpr int stage_bytes_2sm(int BN) { return (BM + BN / 2) * BK * 2; }
-__host__ __device__ constexpr int num_stages_2sm(int BN) { return BN >= 256 ? 6 : 8; }
+__host__ __device__ constexpr int num_stages_2sm(int BN, int epi_scratch = 0) {
+  const int fit = (kSmemBudget - 1024 - 256 - epi_scratch) / stage_bytes_2sm(BN);
+  return fit > 8 ? 8 : fit;
+}
 __host__ __device__ constexpr int smem_bytes_2sm(int BN, int epi_scratch) {
-  return 1024 + num_stages_2sm(BN) * stage_bytes_2sm(BN) + epi_scratch + 256;
+  return 1024 + num_stages_2sm(BN, epi_scratch) * stage_bytes_2sm(BN) + epi_scratch + 256;
 }
 
 template <int BN, int EPI_WARPS, class Epi>
@@ -373,13 +382,15 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
                     int tiles_n, int batch, int k_blocks, typename Epi::Params ep) {
   static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN");
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS");
-  constexpr int STAGES = num_stages_2sm(BN);
+  constexpr int STAGES = num_stages_2sm(BN, Epi::kScratchBytes);
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int STAGE_BYTES = stage_bytes_2sm(BN);
   constexpr uint32_t TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ symbol (not a uintptr_t round trip) keeps the address space visible to the
+  // compiler, so epilogue scratch accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
   uint8_t* scratch = ring + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + Epi::kScratchBytes);
@@ -520,13 +531,13 @@ struct GemmShape {
 
 // Tile width with the least wave-quantisation loss: a persistent launch runs ceil(tiles / SMs) rounds whose cost is
 // proportional to the tile width.  Candidates 256 / 192 / 128 (wider tiles reuse A better, so they win ties).
-inline int pick_tile_n(const GemmShape& s) {
+inline int pick_tile_n(const GemmShape& s, int ctas_per_tile = 1) {
   const int cand[3] = {256, 192, 128};
   int best = 256;
   double best_cost = 1e30;
   for (int bn : cand) {
-    const long long tiles = 1LL * ceil_div(s.M, BM) * ceil_div(s.N, bn) * s.batch;
-    const double rounds = (double)ceil_div<long long>(tiles, num_sms());
+    const long long tiles = 1LL * ceil_div(s.M, BM * ctas_per_tile) * ceil_div(s.N, bn) * s.batch;
+    const double rounds = (double)ceil_div<long long>(tiles, num_sms() / ctas_per_tile);
     const double cost = rounds * bn * (1.0 + 0.02 * (256 - bn) / 64.0);
     if (cost < best_cost - 1e-9) {
       best_cost = cost;
@@ -602,10 +613,90 @@ int launch_gemm_2sm(const char* name, const CUtensorMap& tmA, const CUtensorMap&
   return GD3_OK;
 }
 
+// ------------------------------------------------------------------ coalesced epilogue I/O
+// After tcgen05.ld a thread owns one ROW of the tile (32 consecutive columns per chunk), so a direct global
+// access touches 32 different rows per warp instruction.  These helpers bounce a 32 x 32 chunk through a padded
+// per-warp shared-memory tile so that every global instruction covers whole contiguous row segments instead.
+constexpr int kWarpTileFloats = 32 * 33;
+constexpr int kWarpTileBytes = kWarpTileFloats * 4;
+constexpr int kMaxEpiWarps = 8;
+
+// thread `lane` holds row `lane` of the chunk in v[32]; writes rows [0, rows) x cols [0, cols) to dst (row stride ld)
+template <class OutT>
+__device__ __forceinline__ void warp_store_rows(float* t, const float (&v)[32], OutT* dst, int64_t ld, int rows,
+                                                int cols, int lane) {
+#pragma unroll
+  for (int q = 0; q < 32; ++q) t[lane * 33 + q] = v[q];
+  __syncwarp();
+  if constexpr (sizeof(OutT) == 4) {
+    // one row per instruction: 32 lanes x 4 B = one 128-byte line
+    const bool c_ok = lane < cols;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float x = t[r * 33 + lane];
+      if (r < rows && c_ok) dst[r * ld + lane] = x;
+    }
+  } else {
+    // two rows per instruction: 16 lanes x (2 x bf16) = 64 contiguous bytes per row
+    const int half = lane >> 4, c2 = 2 * (lane & 15);
+    const bool pair_ok = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
+#pragma unroll
+    for (int r = 0; r < 32; r += 2) {
+      const int rr = r + half;
+      const float x0 = t[rr * 33 + c2], x1 = t[rr * 33 + c2 + 1];
+      const bool r_ok = rr < rows;
+      if (pair_ok) {
+        if (r_ok && c2 + 1 < cols) *reinterpret_cast<uint32_t*>(dst + rr * ld + c2) = pack_bf16x2(x0, x1);
+        else if (r_ok && c2 < cols) dst[rr * ld + c2] = __float2bfloat16(x0);
+      } else {
+        if (r_ok && c2 < cols) dst[rr * ld + c2] = __float2bfloat16(x0);
+        if (r_ok && c2 + 1 < cols) dst[rr * ld + c2 + 1] = __float2bfloat16(x1);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// issue the coalesced loads of a 32 x 32 bf16 chunk (two rows per instruction); raw[i] holds row 2i + half
+__device__ __forceinline__ void warp_load_rows_issue(const __nv_bfloat16* src, int64_t ld, int rows, int cols, int lane,
+                                                     uint32_t (&raw)[16]) {
+  const int half = lane >> 4, c2 = 2 * (lane & 15);
+  const bool pair_ok = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int rr = 2 * i + half;
+    uint32_t w = 0;
+    if (rr < rows) {
+      if (pair_ok && c2 + 1 < cols) {
+        w = __ldg(reinterpret_cast<const uint32_t*>(src + rr * ld + c2));
+      } else {
+        const uint32_t lo = (c2 < cols) ? (uint32_t)__bfloat16_as_ushort(src[rr * ld + c2]) : 0u;
+        const uint32_t hi = (c2 + 1 < cols) ? (uint32_t)__bfloat16_as_ushort(src[rr * ld + c2 + 1]) : 0u;
+        w = lo | (hi << 16);
+      }
+    }
+    raw[i] = w;
+  }
+}
+// scatter the loaded chunk into the warp tile and read back this thread's row as floats
+__device__ __forceinline__ void warp_load_rows_finish(float* t, const uint32_t (&raw)[16], int lane, float (&x)[32]) {
+  const int half = lane >> 4, c2 = 2 * (lane & 15);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int rr = 2 * i + half;
+    t[rr * 33 + c2] = bf16_bits_to_float(raw[i] & 0xFFFFu);
+    t[rr * 33 + c2 + 1] = bf16_bits_to_float(raw[i] >> 16);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 32; ++q) x[q] = t[lane * 33 + q];
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------ a plain epilogue: store fp32
 // C[b][m][n] = alpha * acc   (row-major, leading dimension ldc, batch stride in elements)
 struct EpiStoreF32 {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = kMaxEpiWarps * kWarpTileBytes;
   struct Params {
     float* C;
     int M, N;
@@ -617,28 +708,20 @@ struct EpiStoreF32 {
   struct Pre {};
   __device__ static void pre(const Params&, const EpiCtx&, Pre&) {}
   __device__ static void run(const Params& p, const EpiCtx& cx, const Pre&) {
-    const int m = cx.m0 + cx.row;
     const float alpha = p.batch_scale ? p.alpha * __ldg(p.batch_scale + (p.batch_scale_stride0 ? 0 : cx.b)) : p.alpha;
-    float* crow = p.C + cx.b * p.batch_stride + static_cast<int64_t>(m) * p.ldc;
-    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        (p.batch_stride % 4 == 0);
+    float* t = reinterpret_cast<float*>(cx.scratch) + cx.epi_warp * kWarpTileFloats;
+    const int m_warp = cx.m0 + (cx.row & ~31);            // first row of this warp's 32-row slab
+    const int rows = p.M - m_warp;                         // valid rows in the slab (may be <= 0)
+    float* cslab = p.C + cx.b * p.batch_stride + static_cast<int64_t>(m_warp) * p.ldc;
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
-      float v[32];
-      tmem_ld32(cx.tmem + c, v);       // warp-collective: every lane participates, stores are predicated
       const int n = cx.n0 + c;
-      if (m < p.M) {
-        if (vec_ok && n + 32 <= p.N) {
+      if (n >= p.N) break;
+      float v[32];
+      tmem_ld32(cx.tmem + c, v);       // warp-collective: every lane participates
+      if (rows <= 0) continue;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 o = make_float4(v[4 * q] * alpha, v[4 * q + 1] * alpha, v[4 * q + 2] * alpha, v[4 * q + 3] * alpha);
-            *reinterpret_cast<float4*>(crow + n + 4 * q) = o;
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (n + q < p.N) crow[n + q] = v[q] * alpha;
-        }
-      }
+      for (int q = 0; q < 32; ++q) v[q] *= alpha;
+      warp_store_rows<float>(t, v, cslab + n, p.ldc, rows, p.N - n, cx.lane);
     }
   }
 };

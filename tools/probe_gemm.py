@@ -31,3 +31,22 @@ if __name__ == '__main__':
     for _ in range(5): A @ B.t()
     e1.record(); torch.cuda.synchronize()
     print(f'cuBLAS 8192^3: {2*8192**3/(e0.elapsed_time(e1)/5)/1e9:.0f} TFLOP/s')
+
+
+def cublas_bmm(b, M, N, K, iters=20):
+    A = torch.randn(b, M, K, device='cuda').to(torch.bfloat16)
+    B = torch.randn(b, N, K, device='cuda').to(torch.bfloat16)
+    for _ in range(3): torch.bmm(A, B.transpose(1, 2))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): torch.bmm(A, B.transpose(1, 2))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f'cuBLAS bmm b={b} M={M} N={N} K={K}: {ms*1e3:.1f} us  {2.0*b*M*N*K/ms/1e9:.0f} TFLOP/s (bf16 out)', flush=True)
+
+
+if __name__ == '__main__':
+    cublas_bmm(32, 1024, 768, 1024)
+    cublas_bmm(32, 1024, 1024, 768)
+    cublas_bmm(64, 1369, 1024, 1369)
