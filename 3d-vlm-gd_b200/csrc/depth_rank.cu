@@ -115,14 +115,17 @@ __device__ __forceinline__ float fast_tanh(float x) {
 // (|err| <= 2.5e-5), sharing exp(-y^2/2) between erf and the Gaussian density needed by GELU'.
 // Both half warps of a warp always execute this together (an invalid pair is masked later), so the
 // xor-shuffles with offsets < 16 use the full mask and stay inside each half.
-template <bool GRAD>
+// HOIST: o.rstd was filled by the caller (read from the rank_rstd_gemm output) and the sum of squares is skipped.
+template <bool GRAD, bool HOIST = false>
 __device__ __forceinline__ void head_eval(const F2 (&hc)[HP], const HeadConst& hcst, float ln_eps, int use_tanh,
                                           PairOut& o) {
-  F2 ss2 = bc(0.f);
+  if (!HOIST) {
+    F2 ss2 = bc(0.f);
 #pragma unroll
-  for (int i = 0; i < HP; ++i) ss2 = fma2(hc[i], hc[i], ss2);
-  const float ss = half_sum(ss2.x + ss2.y, 0xffffffffu);
-  o.rstd = rsqrtf(fmaf(ss, 1.f / H, ln_eps));
+    for (int i = 0; i < HP; ++i) ss2 = fma2(hc[i], hc[i], ss2);
+    const float ss = half_sum(ss2.x + ss2.y, 0xffffffffu);
+    o.rstd = rsqrtf(fmaf(ss, 1.f / H, ln_eps));
+  }
   const F2 r2 = bc(o.rstd);
   F2 acc2 = bc(0.f), m1_2 = bc(0.f), m2_2 = bc(0.f);
 #pragma unroll
@@ -192,6 +195,7 @@ struct RankParams {
   const float* beta;
   const float* w2;
   const float* b2;
+  const float* rstd;     // (S, K, K) [set][b][a]: LayerNorm 1 / sigma of every ordered pair (rank_rstd_gemm)
   const float* inv_count;  // (S)   1 / #valid pairs (joint or per set), 0 if none
   const float* w_rank;     // (S) or nullptr
   int K, S;
@@ -250,6 +254,17 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   for (int i = 0; i < HP; ++i) dgam[i] = dbet[i] = dw2[i] = bc(0.f);
   float loss_local = 0.f;
 
+  // rstd of one b row against the 64 rows of the a tile: the 16 lanes of a half hold ring slots l16 and l16 + 16
+  // (a = 2 * slot + half), i.e. two fully coalesced 128-byte loads per warp and b row
+  static_assert(SLOTS == 32, "rstd registers cover 2 x 16 ring slots");
+  auto load_rstd = [&](int b_, float& x0, float& x1) {
+    const float* rrow = p.rstd + ((int64_t)set * K + b_) * K + ta * TILE_A + half;
+    const int a0 = ta * TILE_A + 2 * l16 + half, a1 = a0 + 32;
+    x0 = (b_ < K && a0 < K) ? __ldg(rrow + 2 * l16) : 1.f;
+    x1 = (b_ < K && a1 < K) ? __ldg(rrow + 2 * l16 + 32) : 1.f;
+  };
+  float rs0_next, rs1_next;
+  load_rstd(tb * TILE_B + warp * B_PER_WARP, rs0_next, rs1_next);
   for (int bi = 0; bi < B_PER_WARP; ++bi) {
     const int b = tb * TILE_B + warp * B_PER_WARP + bi;
     const bool b_ok = b < K;     // warp-uniform
@@ -272,11 +287,17 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
 #pragma unroll
       for (int i = 0; i < HP; ++i) dub[i] = bc(0.f);
     }
+    // 1 / sigma of this b row's pairs: taken from the registers loaded during the previous row, and the next
+    // row's values are requested now
+    const float rs0 = rs0_next, rs1 = rs1_next;
+    if (bi + 1 < B_PER_WARP) load_rstd(b + 1, rs0_next, rs1_next);
 #pragma unroll 1
     for (int t = 0; t < SLOTS; ++t) {
       // staggered a index: at any step the half-warps of the CTA work on different rows
-      const int r = 2 * ((t + SPACING * warp) % SLOTS) + half;
+      const int slot = (t + SPACING * warp) % SLOTS;
+      const int r = 2 * slot + half;
       const int a = ta * TILE_A + r;
+      const float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, (lane & 16) | (slot & 15));
       const float dd = d_b - da[r];
       bool valid = b_ok && a < K;
       valid = valid && ((p.mode == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr));
@@ -291,7 +312,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
         hcv[2] = add2(vb[2], make_float2(a1.x, a1.y));
         hcv[3] = add2(vb[3], make_float2(a1.z, a1.w));
         PairOut o;
-        head_eval<GRAD>(hcv, hc, p.ln_eps, p.use_tanh, o);
+        o.rstd = rs;
+        head_eval<GRAD, true>(hcv, hc, p.ln_eps, p.use_tanh, o);
         const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
         float l, dl;
         if (p.mode == 0) {
@@ -382,6 +404,96 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
       if (red[e] != 0.f) atomicAdd(gp + H + e, red[e]);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm statistics of all K^2 pairs, hoisted onto the tensor cores.
+//   h_c(a -> b) = w_b - v_a,  v = u - mean_h(u),  w = v + (b1 - mean(b1))        (mean-free over h)
+//   sum_h h_c^2 = |w_b|^2 + |v_a|^2 - 2 w_b . v_a
+// The Gram term is one split-bf16 GEMM per set ([hi|hi|lo] x [hi|lo|hi] panels, ~16 mantissa bits on the
+// products, the same accuracy class as u itself); its epilogue writes rstd = rsqrt(ss / H + eps) for every pair.
+// This removes the sum of squares, its 4 shuffle rounds and the rsqrt from the head of every pair step.
+// ------------------------------------------------------------------------------------------
+// one warp per row of u: centre, add the centred bias on the b side, split into bf16 panels, squared norms
+__global__ void __launch_bounds__(256) rank_gram_prep(const float* __restrict__ u, const float* __restrict__ b1, int64_t R,
+                                                      __nv_bfloat16* __restrict__ Wb3, __nv_bfloat16* __restrict__ Va3,
+                                                      float* __restrict__ nb, float* __restrict__ na) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float4 bv = make_float4(b1[4 * lane], b1[4 * lane + 1], b1[4 * lane + 2], b1[4 * lane + 3]);   // no alignment assumed
+  const float bm = warp_sum((bv.x + bv.y) + (bv.z + bv.w)) * (1.f / H);
+  const float4 uv = *reinterpret_cast<const float4*>(u + r * H + 4 * lane);
+  const float m = warp_sum((uv.x + uv.y) + (uv.z + uv.w)) * (1.f / H);
+  const float v[4] = {uv.x - m, uv.y - m, uv.z - m, uv.w - m};
+  const float w[4] = {v[0] + (bv.x - bm), v[1] + (bv.y - bm), v[2] + (bv.z - bm), v[3] + (bv.w - bm)};
+  float sv = 0.f, sw = 0.f;
+  uint16_t vh[4], vl[4], wh[4], wl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sv = fmaf(v[i], v[i], sv);
+    sw = fmaf(w[i], w[i], sw);
+    split_detail::hi_lo(v[i], vh[i], vl[i]);
+    split_detail::hi_lo(w[i], wh[i], wl[i]);
+  }
+  sv = warp_sum(sv);
+  sw = warp_sum(sw);
+  auto pk = [](const uint16_t (&x)[4]) {
+    return make_uint2((uint32_t)x[0] | ((uint32_t)x[1] << 16), (uint32_t)x[2] | ((uint32_t)x[3] << 16));
+  };
+  uint2* wo = reinterpret_cast<uint2*>(Wb3 + r * 3 * H) + lane;     // [hi | hi | lo]
+  wo[0] = pk(wh);
+  wo[H / 4] = pk(wh);
+  wo[2 * (H / 4)] = pk(wl);
+  uint2* vo = reinterpret_cast<uint2*>(Va3 + r * 3 * H) + lane;     // [hi | lo | hi]
+  vo[0] = pk(vh);
+  vo[H / 4] = pk(vl);
+  vo[2 * (H / 4)] = pk(vh);
+  if (lane == 0) {
+    nb[r] = sw;
+    na[r] = sv;
+  }
+}
+
+// rstd[set][b][a] = rsqrt(max(|w_b|^2 + |v_a|^2 - 2 acc, 0) / H + eps)
+struct EpiRstd {
+  static constexpr int kScratchBytes = tc::kMaxEpiWarps * tc::kWarpTileBytes;
+  struct Params {
+    float* out;          // (S, K, K)
+    int K;
+    const float* nb;     // (S, K)
+    const float* na;     // (S, K)
+    float eps;
+  };
+  struct Pre {
+    float nb;
+  };
+  __device__ static void pre(const Params& p, const tc::EpiCtx& cx, Pre& pr) {
+    const int b = cx.m0 + cx.row;
+    pr.nb = (b < p.K) ? p.nb[(int64_t)cx.b * p.K + b] : 0.f;
+  }
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre& pr) {
+    float* t = reinterpret_cast<float*>(cx.scratch) + cx.epi_warp * tc::kWarpTileFloats;
+    const int m_warp = cx.m0 + (cx.row & ~31);
+    const int rows = p.K - m_warp;
+    float* oslab = p.out + ((int64_t)cx.b * p.K + m_warp) * p.K;
+    const float* na = p.na + (int64_t)cx.b * p.K;
+    for (int c = cx.col_begin; c < cx.col_end; c += 32) {
+      const int n = cx.n0 + c;
+      if (n >= p.K) break;
+      // |v_a|^2 of this chunk's 32 columns: one coalesced load, handed out by shuffle
+      const float na_l = (n + cx.lane < p.K) ? __ldg(na + n + cx.lane) : 0.f;
+      float v[32];
+      tc::tmem_ld32(cx.tmem + c, v);
+      if (rows <= 0) continue;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const float ss = fmaxf(fmaf(-2.f, v[q], pr.nb + __shfl_sync(0xffffffffu, na_l, q)), 0.f);
+        v[q] = rsqrtf(fmaf(ss, 1.f / H, p.eps));
+      }
+      tc::warp_store_rows<float>(t, v, oslab + n, p.K, rows, p.K - n, cx.lane);
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // number of valid pairs per set -> inv_count (per set, or shared when joint_mean)
@@ -590,7 +702,8 @@ __global__ void rank_finalize(const double* __restrict__ loss_sum, const float* 
 
 struct RankWorkspace {
   __nv_bfloat16 *F3, *W3, *FT3, *W1T, *du_bf, *duT3;
-  float *u, *inv_count, *dub_part, *dua_part, *du_extra;
+  __nv_bfloat16 *Wb3, *Va3;
+  float *u, *inv_count, *dub_part, *dua_part, *du_extra, *nb, *na, *rstd;
   double *loss_sum, *l1_sum;
   int* count;
   size_t total;
@@ -616,6 +729,11 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
   w.W3 = c.take<__nv_bfloat16>((int64_t)H * 3 * w.ldd);
   w.u = c.take<float>(R * H);
+  w.Wb3 = c.take<__nv_bfloat16>(R * 3 * H);
+  w.Va3 = c.take<__nv_bfloat16>(R * 3 * H);
+  w.nb = c.take<float>(R);
+  w.na = c.take<float>(R);
+  w.rstd = c.take<float>(R * K);
   w.count = c.take<int>(S);
   w.inv_count = c.take<float>(S);
   w.loss_sum = c.take<double>(S);
@@ -713,6 +831,24 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     tc::GemmShape s{(int)R, H, 3 * w.ldd, 1};
     if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>("rank_u_gemm", ta, tb, s, ep, stream))) return rc;
   }
+  // ---- LayerNorm 1 / sigma of every ordered pair (Gram matrix of the centred rows, per set) ----
+  {
+    {
+      GD3_PROF("rank_gram_prep", stream);
+      rank_gram_prep<<<(unsigned)ceil_div<int64_t>(R, 8), 256, 0, stream>>>(w.u, b1, R, w.Wb3, w.Va3, w.nb, w.na);
+    }
+    GD3_CHECK_LAUNCH();
+    tc::GemmShape s{(int)K, (int)K, 3 * H, (int)S};
+    const int bn = tc::pick_tile_n(s);
+    CUtensorMap ta, tb;
+    if ((rc = tc::make_tmap_bf16(&ta, w.Wb3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tb, w.Va3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, bn))) return rc;
+    EpiRstd::Params ep{w.rstd, (int)K, w.nb, w.na, ln_eps};
+    if (bn == 256) rc = tc::launch_gemm<256, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
+    else if (bn == 192) rc = tc::launch_gemm<192, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
+    else rc = tc::launch_gemm<128, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
+    if (rc) return rc;
+  }
   // ---- valid-pair counts ----
   GD3_CHECK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * S, stream));
   GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double) * S, stream));
@@ -739,6 +875,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.beta = beta;
   rp.w2 = w2;
   rp.b2 = b2;
+  rp.rstd = w.rstd;
   rp.inv_count = w.inv_count;
   rp.w_rank = w_rank;
   rp.K = (int)K;
