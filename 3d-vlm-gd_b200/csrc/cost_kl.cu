@@ -297,6 +297,9 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 // 4. pass-1 epilogue: softmax statistics + D term straight from the TMEM accumulator
 // ------------------------------------------------------------------------------------------
+// WITH_D: also accumulate the D term  -1/(2N) sum_ij W_ij z_ij  (forward-only calls).  When the backward runs, kl_dz
+// reads W and z anyway and takes the term over, so this epilogue issues no global loads at all.
+template <bool WITH_D>
 struct EpiKLStats {
   static constexpr int kScratchBytes = 0;
   struct Params {
@@ -333,9 +336,11 @@ struct EpiKLStats {
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         const bool ok = row_ok && (j0 + q < p.N);
-        const float w = ok ? __ldg(wt + (int64_t)(j0 + q) * p.ldw) : 0.f;
         const float ex = ok ? exp2f(v[q] * LOG2E) : 0.f;
-        dsum = fmaf(w, v[q], dsum);
+        if (WITH_D) {
+          const float w = ok ? __ldg(wt + (int64_t)(j0 + q) * p.ldw) : 0.f;
+          dsum = fmaf(w, v[q], dsum);
+        }
         rowsum += ex;
         e[q] = ex;
       }
@@ -353,8 +358,10 @@ struct EpiKLStats {
       if (j0 + cx.lane < p.N) atomicAdd(p.Lcol + (int64_t)cx.b * p.N + j0 + cx.lane, e[0]);
     }
     if (row_ok) atomicAdd(p.Lrow + (int64_t)cx.b * p.N + i, rowsum);
-    dsum = warp_sum(dsum);
-    if (cx.lane == 0 && dsum != 0.f) atomicAdd(p.loss_acc + cx.b, -(0.5 / (double)p.N) * (double)dsum);
+    if (WITH_D) {
+      dsum = warp_sum(dsum);
+      if (cx.lane == 0 && dsum != 0.f) atomicAdd(p.loss_acc + cx.b, -(0.5 / (double)p.N) * (double)dsum);
+    }
   }
 };
 
@@ -396,10 +403,12 @@ __global__ void kl_finalize_stats(int G, int N, const float* __restrict__ invR, 
 __global__ void __launch_bounds__(256)
     kl_dz(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT, int ldw,
           const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT, int ldd,
-          float* __restrict__ rowdot, float* __restrict__ coldot) {
+          float* __restrict__ rowdot, float* __restrict__ coldot, double* __restrict__ loss_acc) {
   __shared__ float ws[64][65];     // W^T tile, [j][i]
   __shared__ float ds[64][65];     // dz tile, [i][j]
   __shared__ float cdot[8][64];
+  __shared__ float red[32];
+  float wz = 0.f;                  // sum W z of this tile (the D term of the loss)
   const int g = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const float* wt = WT + (int64_t)g * N * ldw;
@@ -428,6 +437,8 @@ __global__ void __launch_bounds__(256)
       const float ri = rr[i];
       d0 = s * ((ri + c0) * exp2f(z0 * LOG2E) - ws[jl][r]);
       d1 = (j + 1 < N) ? s * ((ri + c1) * exp2f(z1 * LOG2E) - ws[jl + 1][r]) : 0.f;
+      wz = fmaf(ws[jl][r], z0, wz);
+      if (j + 1 < N) wz = fmaf(ws[jl + 1][r], z1, wz);
       *reinterpret_cast<uint32_t*>(dZ + ((int64_t)g * N + i) * ldd + j) = pack_bf16x2(d0, d1);
       rd = fmaf(d0, z0, d1 * z1);
       cd0 = fmaf(d0, z0, cd0);
@@ -454,6 +465,8 @@ __global__ void __launch_bounds__(256)
     if (jj < N && i < N)
       *reinterpret_cast<uint32_t*>(dZT + ((int64_t)g * N + jj) * ldd + i) = pack_bf16x2(ds[il][r], ds[il + 1][r]);
   }
+  wz = block_sum(wz, red);
+  if (threadIdx.x == 0 && wz != 0.f) atomicAdd(loss_acc + g, -(0.5 / (double)N) * (double)wz);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -505,9 +518,11 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     kl_dz_fast(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT,
                int ldw, const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT,
-               int ldd, float* __restrict__ rowdot, float* __restrict__ coldot) {
+               int ldd, float* __restrict__ rowdot, float* __restrict__ coldot, double* __restrict__ loss_acc) {
   __shared__ float ws[64][65];      // W^T tile [j][i]; later reused as dz [i][j]
   __shared__ float cdot[32][65];
+  __shared__ float red[32];
+  float wz = 0.f;                   // sum W z of this tile (the D term of the loss)
   const int g = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   const float* wt = WT + (int64_t)g * N * ldw;
   {
@@ -548,7 +563,9 @@ __global__ void __launch_bounds__(256)
       for (int q = 0; q < 8; ++q) {
         const __half hv = __ushort_as_half((unsigned short)((q & 1) ? (zw[q >> 1] >> 16) : (zw[q >> 1] & 0xFFFFu)));
         const float z = (j0 + jc + q < N) ? __half2float(hv) : 0.f;
-        const float v = (j0 + jc + q < N) ? s * ((ri + cj[q]) * exp2f(z * LOG2E) - ws[jc + q][r]) : 0.f;
+        const float wv = ws[jc + q][r];
+        const float v = (j0 + jc + q < N) ? s * ((ri + cj[q]) * exp2f(z * LOG2E) - wv) : 0.f;
+        wz = fmaf(wv, z, wz);
         d[q] = v;
         rd = fmaf(v, z, rd);
         cdp[q] = fmaf(v, z, cdp[q]);
@@ -589,6 +606,8 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<uint4*>(dZT + ((int64_t)g * N + j) * ldd + i0 + ic) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
+  wz = block_sum(wz, red);
+  if (threadIdx.x == 0 && wz != 0.f) atomicAdd(loss_acc + g, -(0.5 / (double)N) * (double)wz);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -847,9 +866,16 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       GD3_CHECK_LAUNCH();
     }
     {
-      EpiKLStats::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, backward ? w.Z : nullptr, w.ldn};
       tc::GemmShape s{(int)N, (int)N, (int)C, g};
-      if ((rc = tc::launch_gemm<256, 8, EpiKLStats>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream))) return rc;
+      if (backward) {
+        // the D term is taken over by kl_dz, which reads W and z anyway
+        EpiKLStats<false>::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, w.Z, w.ldn};
+        rc = tc::launch_gemm<256, 8, EpiKLStats<false>>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream);
+      } else {
+        EpiKLStats<true>::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, nullptr, w.ldn};
+        rc = tc::launch_gemm<256, 8, EpiKLStats<true>>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream);
+      }
+      if (rc) return rc;
     }
     {
       const int64_t n = 2 * (int64_t)g * N;
@@ -859,10 +885,10 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
                                                                                w.Lcol, w.rc, w.loss_acc);
       }
       GD3_CHECK_LAUNCH();
-      {
-        GD3_PROF("kl_write_loss", stream);
-        kl_write_loss<<<ceil_div(g, 64), 64, 0, stream>>>(w.loss_acc, loss + p0, g);
-      }
+    }
+    if (!backward) {
+      GD3_PROF("kl_write_loss", stream);
+      kl_write_loss<<<ceil_div(g, 64), 64, 0, stream>>>(w.loss_acc, loss + p0, g);
       GD3_CHECK_LAUNCH();
     }
     if (backward) {
@@ -870,11 +896,16 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       if (N % 8 == 0) {
         GD3_PROF("kl_dz_fast", stream);
         kl_dz_fast<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn,
-                                             w.rowdot, w.coldot);
+                                             w.rowdot, w.coldot, w.loss_acc);
       } else {
         GD3_PROF("kl_dz", stream);
         kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
-                                      w.coldot);
+                                      w.coldot, w.loss_acc);
+      }
+      GD3_CHECK_LAUNCH();
+      {
+        GD3_PROF("kl_write_loss", stream);
+        kl_write_loss<<<ceil_div(g, 64), 64, 0, stream>>>(w.loss_acc, loss + p0, g);
       }
       GD3_CHECK_LAUNCH();
       tc::GemmShape s{(int)N, (int)C, (int)N, g};

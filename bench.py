@@ -161,6 +161,23 @@ def gemm_flops_per_step(cfg, P):
     }
 
 
+# fp32 operations of the restated math per ordered keypoint pair and hidden unit, forward + backward:
+# LayerNorm scale/affine 4, erf (A&S 7.1.25) + Phi + GELU 15, w2 dot 2, GELU' 3, LayerNorm backward means 4,
+# parameter gradients 6, d h 5, the two u-gradient accumulations 2.  MUFU (rcp, ex2) counted as 1 each.
+RANK_FLOPS_PER_UNIT = 41
+
+
+def ncu_traffic(kernel, workload):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    capture of this kernel on this workload (profiles/traffic.json), or None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            t = json.load(f)
+        return t.get(workload, {}).get(kernel, {}).get('dram_bytes_per_launch')
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args):
     from gd3 import _lib, pipeline
     import bench_common
@@ -258,9 +275,28 @@ def run_ours(args):
         achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
         peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
         roofline = dict(kernel=top, bound='tensor', achieved=round(achieved, 2), peak=peak, unit='TFLOP/s',
-                        frac=round(achieved / peak, 4), traffic=None, peak_source=peaks['source'] + ' (sustained cuBLAS bf16)',
+                        frac=round(achieved / peak, 4), traffic=ncu_traffic(top, args.workload),
+                        peak_source=peaks['source'] + ' (sustained cuBLAS bf16)',
                         share_of_step=round(ms / tot_prof_ms, 4), launches=cnt,
                         us_per_launch=round(per_launch_ms * 1e3, 2))
+    # ---- the kernel with the largest share of the step is the pair kernel of the depth-ranking loss: fp32 SIMT
+    #      work (LayerNorm / GELU / logistic per hidden unit of every ordered keypoint pair), neither HBM- nor
+    #      tensor-bound, so it is reported against the fp32 FMA peak at the measured SM clock ----
+    simt = None
+    if 'rank_pairs' in prof:
+        cnt, ms = prof['rank_pairs']
+        K = cfg['K']
+        flops_launch = RANK_FLOPS_PER_UNIT * 128.0 * K * K * (2 * P) * args.steps / cnt
+        sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+        peak32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        ach = flops_launch / (ms / cnt * 1e-3) / 1e12
+        simt = dict(kernel='rank_pairs', bound='fp32 FMA pipe', achieved=round(ach, 2), peak=round(peak32, 1),
+                    unit='TFLOP/s', frac=round(ach / peak32, 4), share_of_step=round(ms / tot_prof_ms, 4),
+                    us_per_launch=round(ms / cnt * 1e3, 1),
+                    flops_per_pair_and_hidden_unit=RANK_FLOPS_PER_UNIT,
+                    traffic=ncu_traffic('rank_pairs', args.workload),
+                    note='algorithmic fp32 flops (DESIGN.md, K4) per ordered pair and hidden unit, fwd+bwd; '
+                         'peak = 148 SMs x 128 lanes x 2 flop x SM clock')
     work = algorithmic_work(cfg)
     step_tflops = (work['k1_flops'] + work['k2_flops']) * P / (ms_step * 1e-3) / 1e12
     peak_s = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
@@ -284,6 +320,7 @@ def run_ours(args):
                  d2h_bytes_per_step=int(d2h_bytes), ms_per_step=round(e2e_ms, 3), steps=e2e_steps),
         gpu_launches=int(launches),
         roofline=roofline,
+        roofline_simt=simt,
         step_tensor_fraction=dict(algorithmic_tflops=round(step_tflops, 2), peak=peak_s,
                                   frac=round(step_tflops / peak_s, 4),
                                   note='(K1 + K2 algorithmic FLOPs of SURVEY 8-d) / whole-step time'),
