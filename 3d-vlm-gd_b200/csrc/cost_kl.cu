@@ -34,6 +34,12 @@ namespace gd3 {
 namespace {
 
 constexpr float LOG2E = 1.4426950408889634f;
+// Every loss term of a pair is accumulated with double atomics.  Thousands of them on ONE address serialise in
+// L2 (~35 ns each), so each pair owns kLossSlots accumulators and kl_write_loss adds them up.
+constexpr int kLossSlots = 64;
+__device__ __forceinline__ void loss_add(double* loss_acc, int g, unsigned slot, double v) {
+  atomicAdd(loss_acc + (int64_t)g * kLossSlots + (slot & (kLossSlots - 1)), v);
+}
 
 // ------------------------------------------------------------------------------------------
 // 1. feature preparation
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(256)
       invR[o] = 0.f;
       epsm[o] = 0.f;
       Tsum[o] = 0.f;
-      if (masked_row_const != 0.f) atomicAdd(&loss_acc[g], scale * (double)masked_row_const);
+      if (masked_row_const != 0.f) loss_add(loss_acc, g, i, scale * (double)masked_row_const);
     }
     return;
   }
@@ -257,7 +263,70 @@ __global__ void __launch_bounds__(256)
     invR[o] = ir;
     epsm[o] = eps;
     Tsum[o] = T;
-    atomicAdd(&loss_acc[g], scale * (double)A);
+    loss_add(loss_acc, g, i, scale * (double)A);
+  }
+}
+
+// Single-read variant for N <= 128 * NV, N % 4 == 0 and 16-byte aligned rows: the whole row sits in registers
+// (NV float4 per lane), all loads of a row are in flight at once.
+template <int NV>
+__global__ void __launch_bounds__(256)
+    kl_teacher_stats_vec(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+                         int64_t t_row_stride, const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, int pair0,
+                         int G, int N, float eps, float masked_row_const, float* __restrict__ invR,
+                         float* __restrict__ epsm, float* __restrict__ Tsum, double* __restrict__ loss_acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (int64_t)2 * G * N) return;
+  const int dir = (int)(wid / ((int64_t)G * N));
+  const int rem = (int)(wid - (int64_t)dir * G * N);
+  const int g = rem / N, i = rem - g * N;
+  const uint8_t keep = (dir == 0 ? m1 : m2)[(int64_t)(pair0 + g) * N + i];
+  const int64_t o = ((int64_t)dir * G + g) * N + i;
+  const double scale = 0.5 / (double)N;
+  if (!keep) {
+    if (lane == 0) {
+      invR[o] = 0.f;
+      epsm[o] = 0.f;
+      Tsum[o] = 0.f;
+      if (masked_row_const != 0.f) loss_add(loss_acc, g, i, scale * (double)masked_row_const);
+    }
+    return;
+  }
+  const float4* row = reinterpret_cast<const float4*>((dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride +
+                                                      (int64_t)i * t_row_stride);
+  const int nv = N >> 2;
+  float4 v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int j = lane + 32 * k;
+    v[k] = (j < nv) ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float R = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) R += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  R = warp_sum(R);
+  const float ir = 1.f / fmaxf(R, eps);
+  float T = 0.f, A = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    if (lane + 32 * k < nv) {
+      const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float tt = fmaxf(e[q] * ir, eps);
+        T += tt;
+        A = fmaf(tt, __logf(tt), A);
+      }
+    }
+  }
+  T = warp_sum(T);
+  A = warp_sum(A);
+  if (lane == 0) {
+    invR[o] = ir;
+    epsm[o] = eps;
+    Tsum[o] = T;
+    loss_add(loss_acc, g, i, scale * (double)A);
   }
 }
 
@@ -360,7 +429,7 @@ struct EpiKLStats {
     if (row_ok) atomicAdd(p.Lrow + (int64_t)cx.b * p.N + i, rowsum);
     if (WITH_D) {
       dsum = warp_sum(dsum);
-      if (cx.lane == 0 && dsum != 0.f) atomicAdd(p.loss_acc + cx.b, -(0.5 / (double)p.N) * (double)dsum);
+      if (cx.lane == 0 && dsum != 0.f) loss_add(p.loss_acc, cx.b, (unsigned)i >> 5, -(0.5 / (double)p.N) * (double)dsum);
     }
   }
 };
@@ -390,9 +459,9 @@ __global__ void kl_finalize_stats(int G, int N, const float* __restrict__ invR, 
   const bool uniform = __all_sync(full, g == g0);
   if (uniform) {
     contrib = warp_sum(contrib);
-    if ((threadIdx.x & 31) == 0 && contrib != 0.0) atomicAdd(&loss_acc[g0], contrib);
+    if ((threadIdx.x & 31) == 0 && contrib != 0.0) loss_add(loss_acc, g0, (unsigned)(idx >> 5), contrib);
   } else if (contrib != 0.0) {
-    atomicAdd(&loss_acc[g], contrib);
+    loss_add(loss_acc, g, (unsigned)idx, contrib);
   }
 }
 
@@ -466,7 +535,7 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<uint32_t*>(dZT + ((int64_t)g * N + jj) * ldd + i) = pack_bf16x2(ds[il][r], ds[il + 1][r]);
   }
   wz = block_sum(wz, red);
-  if (threadIdx.x == 0 && wz != 0.f) atomicAdd(loss_acc + g, -(0.5 / (double)N) * (double)wz);
+  if (threadIdx.x == 0 && wz != 0.f) loss_add(loss_acc, g, blockIdx.x + blockIdx.y * 7u, -(0.5 / (double)N) * (double)wz);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -607,7 +676,7 @@ __global__ void __launch_bounds__(256)
     }
   }
   wz = block_sum(wz, red);
-  if (threadIdx.x == 0 && wz != 0.f) atomicAdd(loss_acc + g, -(0.5 / (double)N) * (double)wz);
+  if (threadIdx.x == 0 && wz != 0.f) loss_add(loss_acc, g, blockIdx.x + blockIdx.y * 7u, -(0.5 / (double)N) * (double)wz);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -692,7 +761,12 @@ struct EpiGradOut {
 
 __global__ void kl_write_loss(const double* __restrict__ acc, float* __restrict__ loss, int G) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < G) loss[g] = (float)acc[g];
+  if (g < G) {
+    double t = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < kLossSlots; ++k) t += acc[(int64_t)g * kLossSlots + k];
+    loss[g] = (float)t;
+  }
 }
 
 struct KLWorkspace {
@@ -726,7 +800,7 @@ KLWorkspace carve_kl(void* base, int64_t G, int64_t N, int64_t C, bool backward)
   w.rowdot = w.Lrow + 2 * G * N;
   w.coldot = w.Lrow + 3 * G * N;
   w.rc = c.take<float>(2 * G * N);
-  w.loss_acc = c.take<double>(G);
+  w.loss_acc = c.take<double>(G * kLossSlots);
   w.Z = c.take<__half>(backward ? G * N * w.ldn : 0);
   w.dZ = c.take<__nv_bfloat16>(backward ? G * N * w.ldn : 0);
   w.dZT = c.take<__nv_bfloat16>(backward ? G * N * w.ldn : 0);
@@ -807,7 +881,7 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
   for (int64_t p0 = 0; p0 < P; p0 += G) {
     const int g = (int)((P - p0) < G ? (P - p0) : G);
     GD3_CHECK_CUDA(cudaMemsetAsync(w.Lrow, 0, sizeof(float) * 4 * G * N, stream));
-    GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * G, stream));
+    GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * G * kLossSlots, stream));
     {
       const int esz = dtype == GD3_DTYPE_F32 ? 4 : 2;
       const bool fast = s1C == 1 && s2C == 1 && C % 8 == 0 && (s1N * esz) % 16 == 0 && (s2N * esz) % 16 == 0 &&
@@ -843,15 +917,24 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     }
     {
       const int64_t warps = 2 * (int64_t)g * N;
+      const bool rows_aligned = t_row_stride % 4 == 0 && t_pair_stride % 4 == 0 &&
+                                reinterpret_cast<uintptr_t>(t12) % 16 == 0 && reinterpret_cast<uintptr_t>(t21) % 16 == 0;
       {
         GD3_PROF("kl_teacher_stats", stream);
-        kl_teacher_stats<<<(unsigned)ceil_div<int64_t>(warps, 8), 256, 0, stream>>>(
-          t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, (int)N, eps, masked_const, w.invR, w.epsm,
-          w.Tsum, w.loss_acc);
+        const unsigned blocks = (unsigned)ceil_div<int64_t>(warps, 8);
+#define GD3_TSTATS(NV)                                                                                             \
+  kl_teacher_stats_vec<NV><<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g,  \
+                                                       (int)N, eps, masked_const, w.invR, w.epsm, w.Tsum, w.loss_acc)
+        if (rows_aligned && N % 4 == 0 && N <= 512) GD3_TSTATS(4);
+        else if (rows_aligned && N % 4 == 0 && N <= 1024) GD3_TSTATS(8);
+        else if (rows_aligned && N % 4 == 0 && N <= 2048) GD3_TSTATS(16);
+        else
+          kl_teacher_stats<<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, (int)N,
+                                                       eps, masked_const, w.invR, w.epsm, w.Tsum, w.loss_acc);
+#undef GD3_TSTATS
       }
       GD3_CHECK_LAUNCH();
-      const bool vec_ok = N % 8 == 0 && t_row_stride % 4 == 0 && t_pair_stride % 4 == 0 &&
-                          reinterpret_cast<uintptr_t>(t12) % 16 == 0 && reinterpret_cast<uintptr_t>(t21) % 16 == 0;
+      const bool vec_ok = N % 8 == 0 && rows_aligned;
       if (vec_ok) {
         dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
         GD3_PROF("kl_build_w_fast", stream);

@@ -119,6 +119,81 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// One warp per row for the single-positive variants (mast3r / vggt: the positive of row s is column s) and
+// K <= 32 * NE: the row, its negative mask and both sigmoid derivatives stay in registers, one pass over the row,
+// shuffle reductions only, one loss atomic per block of 8 rows.  Same formulas as ap_rows.
+template <int NE>
+__global__ void __launch_bounds__(256)
+    ap_rows_warp(const float* __restrict__ sim, int lds, const float* __restrict__ p1, const float* __restrict__ p2,
+                 int K, int variant, float inv_tau, float thr_neg, __nv_bfloat16* __restrict__ dS, int ldk,
+                 double* __restrict__ loss_acc, int* __restrict__ qcount) {
+  __shared__ float s_loss[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int s = blockIdx.x * 8 + wid, p = blockIdx.y;
+  const bool row_ok = s < K;
+  float loss_row = 0.f;
+  if (row_ok) {
+    const float* srow = sim + ((int64_t)p * K + s) * lds;
+    const float* a = p1 + ((int64_t)p * K + s) * 3;
+    const float* P2 = p2 + (int64_t)p * K * 3;
+    const float ax = a[0], ay = a[1], az = a[2];
+    const float pos = srow[s];
+    float g1[NE], g2[NE];
+    float S1 = 0.f, S2 = 0.f, G2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int j = lane + 32 * e;
+      g1[e] = 0.f;
+      g2[e] = 0.f;
+      if (j < K) {
+        const float dx = ax - P2[3 * j], dy = ay - P2[3 * j + 1], dz = az - P2[3 * j + 2];
+        const bool neg = (sqrtf(dx * dx + dy * dy + dz * dz) > thr_neg) && (j != s);
+        if (neg) {
+          const float sj = srow[j];
+          const SigT q1 = sig_both(sj - 1.f, inv_tau), q2 = sig_both(sj - pos, inv_tau);
+          S1 += q1.s;
+          S2 += q2.s;
+          G2 += q2.ds;
+          g1[e] = q1.ds;
+          g2[e] = q2.ds;
+        }
+      }
+    }
+    S1 = warp_sum(S1);
+    S2 = warp_sum(S2);
+    G2 = warp_sum(G2);
+    const SigT q1 = (variant == GD3_VARIANT_VGGT) ? sig_both(1.f - pos, inv_tau) : sig_both(pos - 1.f, inv_tau);
+    const SigT q2 = sig_both(1.f - pos, inv_tau);
+    const float r1 = 1.f + q1.s, r2 = 1.f + q2.s;
+    const float den1 = r1 + S1, den2 = r2 + S2;
+    loss_row = 1.f - 0.5f * (r1 / den1 + r2 / den2);
+    if (dS) {
+      const float c1 = r1 / (den1 * den1), c2 = r2 / (den2 * den2);
+      const float dr1 = (variant == GD3_VARIANT_VGGT) ? -q1.ds : q1.ds;
+      const float dpos = -0.5f * (S1 / (den1 * den1) * dr1 - S2 / (den2 * den2) * q2.ds + c2 * G2);
+      __nv_bfloat16* drow = dS + ((int64_t)p * K + s) * ldk;
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int j = lane + 32 * e;
+        if (j < K) drow[j] = __float2bfloat16(j == s ? dpos : 0.5f * (c1 * g1[e] + c2 * g2[e]));
+      }
+    }
+  }
+  if (lane == 0) s_loss[wid] = loss_row;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    int n = 0;
+    for (int k = 0; k < 8; ++k)
+      if (blockIdx.x * 8 + k < K) {
+        t += s_loss[k];
+        ++n;
+      }
+    atomicAdd(loss_acc + p, (double)t);
+    atomicAdd(qcount + p, n);
+  }
+}
+
 // loss[p] = acc / Q, scale[p] = 1 / Q  (Q = 0 -> mean of an empty set: NaN like the reference, zero gradient)
 __global__ void ap_finalize(const double* __restrict__ acc, const int* __restrict__ q, float* __restrict__ loss,
                             float* __restrict__ scale, int P) {
@@ -351,9 +426,19 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     dim3 grid((unsigned)K, (unsigned)P);
     {
       GD3_PROF("ap_rows", stream);
-      ap_rows<<<grid, 128, sizeof(float) * K, stream>>>(w.sim, w.lds, pts3d_1, pts3d_2, (int)K, variant, 1.f / temp,
-                                                      thr_neg, thr_pos, backward ? w.dS : nullptr, w.ldk, w.loss_acc,
-                                                      w.qcount);
+      __nv_bfloat16* ds = backward ? w.dS : nullptr;
+      dim3 wgrid((unsigned)ceil_div<int64_t>(K, 8), (unsigned)P);
+#define GD3_AP_WARP(NE)                                                                                           \
+  ap_rows_warp<NE><<<wgrid, 256, 0, stream>>>(w.sim, w.lds, pts3d_1, pts3d_2, (int)K, variant, 1.f / temp, thr_neg, \
+                                              ds, w.ldk, w.loss_acc, w.qcount)
+      if (variant != GD3_VARIANT_ME && K <= 128) GD3_AP_WARP(4);
+      else if (variant != GD3_VARIANT_ME && K <= 256) GD3_AP_WARP(8);
+      else if (variant != GD3_VARIANT_ME && K <= 512) GD3_AP_WARP(16);
+      else if (variant != GD3_VARIANT_ME && K <= 1024) GD3_AP_WARP(32);
+      else
+        ap_rows<<<grid, 128, sizeof(float) * K, stream>>>(w.sim, w.lds, pts3d_1, pts3d_2, (int)K, variant, 1.f / temp,
+                                                        thr_neg, thr_pos, ds, w.ldk, w.loss_acc, w.qcount);
+#undef GD3_AP_WARP
     }
     GD3_CHECK_LAUNCH();
     {
