@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     // row's values are requested now
     const float rs0 = rs0_next, rs1 = rs1_next;
     if (bi + 1 < B_PER_WARP) load_rstd(b + 1, rs0_next, rs1_next);
-#pragma unroll 1
+#pragma unroll 2
     for (int t = 0; t < SLOTS; ++t) {
       // staggered a index: at any step the half-warps of the CTA work on different rows
       const int slot = (t + SPACING * warp) % SLOTS;
@@ -353,7 +353,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
       }
       // Two half warps collide on a row of `dua` only when their step counters differ by a multiple of
       // SPACING, so a CTA barrier every (SPACING - 1) steps keeps the stagger race-free.
-      if (GRAD && ((bi * SLOTS + t) % (SPACING - 1) == SPACING - 2)) __syncthreads();
+      // (barrier every 2 steps <= SPACING - 1; the pair of steps in between is unrolled so that their shuffle / MUFU
+      // latencies overlap)
+      static_assert(SPACING - 1 >= 2 && SLOTS % 2 == 0, "barrier period");
+      if (GRAD && (t & 1)) __syncthreads();
     }
     if (GRAD) {
       // combine the two half warps and store this b row's partial (over the a tile) gradient
