@@ -18,6 +18,14 @@ namespace {
 constexpr int TILE = 128;      // rows of Q and rows of DB per tile
 constexpr int KC = 24;         // k-chunk held in shared memory (MASt3R descriptors are 24-d: one chunk)
 constexpr int THREADS = 256;   // 16 x 16 threads, 8 x 8 scores each
+// Shared-memory panels (no [k][row] transposition: that made every 4-byte cp.async a 32-way bank conflict):
+//   Q  panel  sq[row][k]              row stride KSQ = 28 floats: the 8 lanes of an LDS.128 wavefront that read
+//                                     different rows fall into disjoint groups of 4 banks
+//   DB panel  sd[row / 2][2 k + row % 2]   two adjacent DB rows interleaved, so that one LDS.128 yields the (k, k+1)
+//                                     values of a COLUMN PAIR as two register pairs -> FFMA2 on two scores at once;
+//                                     pair-row stride KSD = 52 floats (same bank argument)
+constexpr int KSQ = KC + 4;
+constexpr int KSD = 2 * KC + 4;
 
 __device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx) {
   score = score + 0.0f;        // -0 -> +0 so that signed zeros tie like torch.max
@@ -31,43 +39,93 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// (row, k) panel of X starting at row0 -> smem [k][row]; rows past n are zero
-__device__ __forceinline__ void load_panel_async(float (*dst)[TILE], const float* __restrict__ X, int n, int row0, int D,
-                                                 int k0, int kc) {
-  for (int e = threadIdx.x; e < TILE * kc; e += THREADS) {
-    const int row = e / kc, k = e - row * kc;
-    const int g = row0 + row;
-    if (g < n) cp_async4(&dst[k][row], X + (size_t)g * D + k0 + k);
-    else dst[k][row] = 0.f;
+// Q panel: rows [row0, row0 + TILE) x columns [k0, k0 + kc) -> sq[row][k]; rows past n and columns up to the next
+// multiple of 4 are zero.  16-byte copies when the rows are 16-byte aligned (vec).
+__device__ __forceinline__ void load_q_async(float (*dst)[KSQ], const float* __restrict__ X, int n, int row0, int D, int k0,
+                                             int kc, bool vec) {
+  const int kc4 = (kc + 3) >> 2;
+  if (vec) {
+    for (int e = threadIdx.x; e < TILE * kc4; e += THREADS) {
+      const int row = e / kc4, j = e - row * kc4;
+      const int g = row0 + row;
+      if (g < n) cp_async16(&dst[row][4 * j], X + (size_t)g * D + k0 + 4 * j);
+      else *reinterpret_cast<float4*>(&dst[row][4 * j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    for (int e = threadIdx.x; e < TILE * 4 * kc4; e += THREADS) {
+      const int row = e / (4 * kc4), k = e - row * (4 * kc4);
+      const int g = row0 + row;
+      if (g < n && k < kc) cp_async4(&dst[row][k], X + (size_t)g * D + k0 + k);
+      else dst[row][k] = 0.f;
+    }
   }
+}
+// DB panel, interleaved by row pairs: element (row, k) -> sd[row / 2][2 k + row % 2]
+__device__ __forceinline__ void load_db_async(float (*dst)[KSD], const float* __restrict__ X, int n, int row0, int D,
+                                              int k0, int kc) {
+  const int kp = ((kc + 3) >> 2) << 2;
+  for (int e = threadIdx.x; e < TILE * kp; e += THREADS) {
+    const int row = e / kp, k = e - row * kp;
+    const int g = row0 + row;
+    float* d = &dst[row >> 1][2 * k + (row & 1)];
+    if (g < n && k < kc) cp_async4(d, X + (size_t)g * D + k0 + k);
+    else *d = 0.f;
+  }
+}
+
+// dynamic shared memory: sq | sd0 | sd1 | nq2 | nd2 | colbest[8][TILE] (BOTH only)
+inline size_t nn_smem_bytes(bool both) {
+  return sizeof(float) * (TILE * KSQ + 2 * (TILE / 2) * KSD + 2 * TILE) + (both ? sizeof(unsigned long long) * 8 * TILE : 0);
 }
 
 // Q: (nq, D) queries, DB: (ndb, D).  Each CTA: one 128-row query tile x `tiles_per_cta` DB tiles.
 // MODE 0: score = q.d ; MODE 1: score = -sqrt(max(|q|^2 + |d|^2 - 2 q.d, 0))
 // BOTH: also reduce every tile over its rows -> arg-best query for each DB row (the nn_B direction), from the
 // very same accumulators, so both directions see bit-identical scores in a single pass.
+// Thread (ty, tx) owns query rows ty * 8 + [0, 8) and the four DB column pairs 2 * (cp * 16 + tx) + {0, 1}.
 template <int MODE, bool BOTH>
 __global__ void __launch_bounds__(THREADS, 2)
     nn_tile_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, int ndb, int D, int tiles_per_cta,
-                   unsigned long long* __restrict__ keysQ, unsigned long long* __restrict__ keysDB) {
-  __shared__ __align__(16) float sq[KC][TILE];
-  __shared__ __align__(16) float sd[2][KC][TILE];
-  __shared__ float nq2[TILE], nd2[TILE];
-  __shared__ unsigned long long colbest[BOTH ? 8 : 1][TILE];
+                   unsigned long long* __restrict__ keysQ, unsigned long long* __restrict__ keysDB,
+                   const int* __restrict__ nq_dev = nullptr, int nq_min = 0) {
+  extern __shared__ __align__(16) unsigned char nn_smem[];
+  if (nq_dev) {
+    // device-resident loops (gd3_fast_reciprocal_nn): the number of live queries is only known on the device; the
+    // grid is sized for the maximum and surplus CTAs leave.  Below nq_min the streaming kernel takes the query.
+    nq = *nq_dev;
+    if (nq < nq_min || (int)(blockIdx.x * TILE) >= nq) return;
+  }
+  float (*sq)[KSQ] = reinterpret_cast<float (*)[KSQ]>(nn_smem);
+  float (*sd0)[KSD] = reinterpret_cast<float (*)[KSD]>(sq + TILE);
+  float (*sd1)[KSD] = sd0 + TILE / 2;
+  float* nq2 = reinterpret_cast<float*>(sd1 + TILE / 2);
+  float* nd2 = nq2 + TILE;
+  unsigned long long (*colbest)[TILE] = reinterpret_cast<unsigned long long (*)[TILE]>(nd2 + TILE);   // [8][TILE] if BOTH
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int q0 = blockIdx.x * TILE;
   const int ndb_tiles = ceil_div(ndb, TILE);
   const int t_begin = blockIdx.y * tiles_per_cta;
   const int t_end = min(t_begin + tiles_per_cta, ndb_tiles);
   const bool one_chunk = D <= KC;      // whole descriptor in one chunk: Q stays resident, DB tiles are double-buffered
+  const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(Q) % 16 == 0);
 
-  unsigned long long best[8];
+  // running per-row best as (value, index): a thread visits its columns in increasing index order, so a strict
+  // '>' keeps the lowest index on ties; keys are only packed for the cross-thread reductions
+  float bestv[8];
+  uint32_t besti[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) best[r] = 0ull;
+  for (int r = 0; r < 8; ++r) {
+    bestv[r] = -INFINITY;
+    besti[r] = 0xFFFFFFFFu;      // "no candidate yet"
+  }
 
   if (MODE == 1) {
     // squared norms of this CTA's query rows (sequential k order, one thread per row)
@@ -80,19 +138,19 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
   }
   if (one_chunk && t_begin < t_end) {
-    load_panel_async(sq, Q, nq, q0, D, 0, D);
-    load_panel_async(sd[0], DB, ndb, t_begin * TILE, D, 0, D);
+    load_q_async(sq, Q, nq, q0, D, 0, D, vec);
+    load_db_async(sd0, DB, ndb, t_begin * TILE, D, 0, D);
     cp_async_commit();
   }
 
   for (int t = t_begin; t < t_end; ++t) {
     const int d0 = t * TILE;
     const int buf = one_chunk ? ((t - t_begin) & 1) : 0;
-    float acc[8][8];
+    float2 acc[8][4];            // [query row][column pair]
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+      for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
 
     if (MODE == 1) {
       __syncthreads();
@@ -109,52 +167,103 @@ __global__ void __launch_bounds__(THREADS, 2)
       const int kc = min(KC, D - k0);
       if (one_chunk) {
         // prefetch the next DB tile into the other buffer, then wait for the current one
-        if (t + 1 < t_end) load_panel_async(sd[buf ^ 1], DB, ndb, (t + 1) * TILE, D, 0, D);
+        if (t + 1 < t_end) load_db_async(buf ? sd0 : sd1, DB, ndb, (t + 1) * TILE, D, 0, D);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
       } else {
         __syncthreads();
-        load_panel_async(sq, Q, nq, q0, D, k0, kc);
-        load_panel_async(sd[0], DB, ndb, d0, D, k0, kc);
+        load_q_async(sq, Q, nq, q0, D, k0, kc, vec);
+        load_db_async(sd0, DB, ndb, d0, D, k0, kc);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
       }
-      for (int k = 0; k < kc; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&sq[k][ty * 8]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&sq[k][ty * 8 + 4]);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        float b[8];
+      float (*sdb)[KSD] = buf ? sd1 : sd0;
+      // 2 k at a time (columns past kc are zero: fma(0, 0, acc) leaves acc unchanged).  Per score the FFMA chain runs
+      // over k in increasing order, so the result does not depend on the tiling; FFMA2 works on the two scores of
+      // a column pair with the query value broadcast.
+      for (int k = 0; k < kc; k += 2) {
+        float2 a[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) b[c] = sd[buf][k][c * 16 + tx];
+        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&sq[ty * 8 + r][k]);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int c = 0; c < 4; ++c) {
+          const float4 b = *reinterpret_cast<const float4*>(&sdb[c * 16 + tx][2 * k]);   // (c0 k, c1 k, c0 k+1, c1 k+1)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);   // fixed k order: tiling-independent
-      }
-    }
-    // fold this tile into the running per-row best (columns in increasing index order) and, for BOTH,
-    // into the per-column best of this tile
-    unsigned long long cb[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int d = d0 + c * 16 + tx;
-      cb[c] = 0ull;
-      if (d < ndb) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          float s = acc[r][c];
-          if (MODE == 1) {
-            const float d2 = (nq2[ty * 8 + r] + nd2[c * 16 + tx]) - 2.0f * s;
-            s = -sqrtf(fmaxf(d2, 0.f));
-          }
-          best[r] = kmax(best[r], pack_key(s, (uint32_t)d));
-          if (BOTH) {
-            const int q = q0 + ty * 8 + r;
-            if (q < nq) cb[c] = kmax(cb[c], pack_key(s, (uint32_t)q));
+          for (int r = 0; r < 8; ++r) {
+            float2 v = acc[r][c];
+            v = __ffma2_rn(make_float2(a[r].x, a[r].x), make_float2(b.x, b.y), v);
+            v = __ffma2_rn(make_float2(a[r].y, a[r].y), make_float2(b.z, b.w), v);
+            acc[r][c] = v;
           }
         }
+      }
+    }
+    // ---- fold this tile into the running per-row best and, for BOTH, into the per-column best of this tile ----
+    // Two stages per row / column: the maximum VALUE first (one FMNMX per score), then the lowest index that
+    // attains it (compare + select per score, under a branch for the rows: the running best rarely improves).
+    // This replaced a (value, index) update per score, which cost twice the FFMA work of a 24-d descriptor.
+    float sc[8][8];              // [query row][column c8]; column inside the tile: lc(c8) = 2 * ((c8 >> 1) * 16 + tx) + (c8 & 1)
+    const bool partial = (d0 + TILE > ndb) || (q0 + TILE > nq);      // CTA-uniform
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float v = (c & 1) ? acc[r][c >> 1].y : acc[r][c >> 1].x;
+        if (MODE == 1) {
+          const float d2 = (nq2[ty * 8 + r] + nd2[2 * ((c >> 1) * 16 + tx) + (c & 1)]) - 2.0f * v;
+          v = -sqrtf(fmaxf(d2, 0.f));
+        }
+        sc[r][c] = v;
+      }
+    if (partial) {
+      // rows / columns outside the problem never win: -inf (and they are never reported, see the guards below)
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const bool ok = (d0 + 2 * ((c >> 1) * 16 + tx) + (c & 1) < ndb) && (q0 + ty * 8 + r < nq);
+          sc[r][c] = ok ? sc[r][c] : -INFINITY;
+        }
+    }
+    if (t == t_begin) {
+      // first candidate of every row: with it in place a strict '>' implements "first maximum" even for -inf scores
+      const int d = d0 + 2 * tx;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (d < ndb) {
+          bestv[r] = sc[r][0];
+          besti[r] = (uint32_t)d;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float m = sc[r][0];
+#pragma unroll
+      for (int c = 1; c < 8; ++c) m = fmaxf(m, sc[r][c]);
+      if (m > bestv[r]) {
+        int ci = 7;
+#pragma unroll
+        for (int c = 6; c >= 0; --c) ci = (sc[r][c] == m) ? c : ci;
+        bestv[r] = m;
+        besti[r] = (uint32_t)(d0 + 2 * ((ci >> 1) * 16 + tx) + (ci & 1));
+      }
+    }
+    unsigned long long cb[8];
+    if (BOTH) {
+      const bool rows_ok = q0 + ty * 8 < nq;       // valid rows are a prefix of the thread's 8 rows
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float m = sc[0][c];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) m = fmaxf(m, sc[r][c]);
+        int ri = 0;
+#pragma unroll
+        for (int r = 7; r >= 1; --r) ri = (sc[r][c] == m) ? r : ri;
+        ri = (sc[0][c] == m) ? 0 : ri;
+        const bool col_ok = d0 + 2 * ((c >> 1) * 16 + tx) + (c & 1) < ndb;
+        cb[c] = (rows_ok && col_ok) ? pack_key(m, (uint32_t)(q0 + ty * 8 + ri)) : 0ull;
       }
     }
     if (BOTH) {
@@ -164,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, 2)
       const int warp = threadIdx.x >> 5;
       if ((threadIdx.x & 16) == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) colbest[warp][c * 16 + tx] = cb[c];
+        for (int c = 0; c < 8; ++c) colbest[warp][2 * ((c >> 1) * 16 + tx) + (c & 1)] = cb[c];
       }
       __syncthreads();
       if (threadIdx.x < TILE) {
@@ -175,13 +284,13 @@ __global__ void __launch_bounds__(THREADS, 2)
         if (d < ndb && k != 0ull) atomicMax(&keysDB[d], k);
       }
     }
-    if (one_chunk) __syncthreads();   // everyone is done with sd[buf] before the next prefetch overwrites it
+    if (one_chunk) __syncthreads();   // everyone is done with this DB buffer before the next prefetch overwrites it
   }
   cp_async_wait<0>();
   // reduce across the 16 threads that share a row group (same ty -> a half warp), then one atomic per row
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    unsigned long long k = best[r];
+    unsigned long long k = (besti[r] != 0xFFFFFFFFu) ? pack_key(bestv[r], besti[r]) : 0ull;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) k = kmax(k, __shfl_xor_sync(0xffffffffu, k, o));
     const int q = q0 + ty * 8 + r;
@@ -189,19 +298,237 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
 }
 
-__global__ void nn_unpack_kernel(const unsigned long long* __restrict__ keys, int64_t* __restrict__ out, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const unsigned long long k = keys[i];
-    out[i] = (k == 0ull) ? int64_t(-1) : int64_t(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+// ------------------------------------------------------------------------------------------
+// Few queries against a large DB (the late ping-pong iterations of fast_reciprocal_NNs have a handful of live
+// seeds against 196,608 points): one DB row per thread, all queries in shared memory (broadcast reads), per query
+// a warp-wide arg-max by two REDUX (max of the orderable score, then min index among the lanes that attain it).
+// The FFMA chain per score runs over k in increasing order exactly like the tile kernel: bit-identical scores.
+// ------------------------------------------------------------------------------------------
+constexpr int STREAM_MAX_D = 128;
+__device__ __forceinline__ uint32_t orderable(float score) {
+  score = score + 0.0f;
+  const uint32_t u = __float_as_uint(score);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+template <int MODE, int NQ>
+__global__ void __launch_bounds__(256)
+    nn_stream_kernel(const float* __restrict__ Q, int nq, const int* __restrict__ nq_dev, int nq_min,
+                     const float* __restrict__ DB, int ndb, int D, unsigned long long* __restrict__ keysQ) {
+  extern __shared__ __align__(16) float sQ[];     // [D][NQ], zero padded, then |q|^2 [NQ]
+  if (nq_dev) nq = *nq_dev;
+  if (nq < nq_min || nq <= 0 || nq > NQ) return;
+  float* qn2 = sQ + D * NQ;
+  for (int e = threadIdx.x; e < D * NQ; e += blockDim.x) {
+    const int k = e / NQ, j = e - k * NQ;
+    sQ[e] = (j < nq) ? Q[(size_t)j * D + k] : 0.f;
+  }
+  if (MODE == 1 && threadIdx.x < NQ) {
+    float s2 = 0.f;
+    if (threadIdx.x < nq)
+      for (int k = 0; k < D; ++k) { const float v = Q[(size_t)threadIdx.x * D + k]; s2 = fmaf(v, v, s2); }
+    qn2[threadIdx.x] = s2;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(DB) % 16 == 0);
+  constexpr int OWN = (NQ + 31) / 32;
+  unsigned long long best[OWN];
+#pragma unroll
+  for (int o = 0; o < OWN; ++o) best[o] = 0ull;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < ndb; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t d = base + threadIdx.x;
+    const bool ok = d < ndb;
+    const float* row = DB + (size_t)(ok ? d : 0) * D;
+    float acc[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) acc[j] = 0.f;
+    float dn2 = 0.f;
+    for (int k = 0; k < D; k += 4) {
+      float dv[4];
+      if (vec) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(row + k));
+        dv[0] = t4.x; dv[1] = t4.y; dv[2] = t4.z; dv[3] = t4.w;
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dv[kk] = (k + kk < D) ? __ldg(row + k + kk) : 0.f;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (k + kk < D) {
+          if (MODE == 1) dn2 = fmaf(dv[kk], dv[kk], dn2);
+          const float4* qk = reinterpret_cast<const float4*>(sQ + (k + kk) * NQ);
+#pragma unroll
+          for (int j = 0; j < NQ; j += 4) {
+            const float4 q4 = qk[j >> 2];
+            acc[j] = fmaf(q4.x, dv[kk], acc[j]);
+            acc[j + 1] = fmaf(q4.y, dv[kk], acc[j + 1]);
+            acc[j + 2] = fmaf(q4.z, dv[kk], acc[j + 2]);
+            acc[j + 3] = fmaf(q4.w, dv[kk], acc[j + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      if (j < nq) {                     // uniform
+        float sc = acc[j];
+        if (MODE == 1) sc = -sqrtf(fmaxf((qn2[j] + dn2) - 2.0f * sc, 0.f));
+        const uint32_t u = ok ? orderable(sc) : 0u;
+        const uint32_t umax = __reduce_max_sync(0xffffffffu, u);
+        const uint32_t cand = (ok && u == umax) ? (uint32_t)d : 0xFFFFFFFFu;
+        const uint32_t imin = __reduce_min_sync(0xffffffffu, cand);
+        if (imin != 0xFFFFFFFFu && lane == (j & 31)) {
+          const unsigned long long key = ((unsigned long long)umax << 32) | (unsigned long long)(0xFFFFFFFFu - imin);
+          best[j >> 5] = kmax(best[j >> 5], key);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < OWN; ++o) {
+    const int j = lane + 32 * o;
+    if (j < nq && best[o] != 0ull) atomicMax(&keysQ[j], best[o]);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Device-resident ping-pong of fast_reciprocal_NNs (mast3r/fast_nn.py:147-170): the seed state never leaves the
+// GPU and no iteration synchronises with the host.  frn_step (one block) applies the result of the previous query,
+// optionally rolls the "old" arrays, compacts the live seeds (in increasing seed order) and gathers their
+// descriptors into a dense query buffer for the next nearest-neighbour search.
+// ------------------------------------------------------------------------------------------
+struct FrnState {
+  int32_t *xy1, *xy2, *old1, *old2;
+  uint8_t* notyet;
+  int32_t* list;              // live seeds of the current query
+  int* n_live;
+  unsigned long long* keys;   // (n_seeds) result keys of the current query
+  float* qbuf;                // (n_seeds, D) gathered query descriptors
+  int n_seeds, D;
+};
+
+__global__ void frn_init(FrnState st, const int32_t* __restrict__ seeds) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < st.n_seeds) {
+    st.xy1[s] = seeds[s];
+    st.old1[s] = seeds[s];
+    st.xy2[s] = -1;
+    st.old2[s] = -1;
+    st.notyet[s] = 1;
+  }
+  if (s == 0) *st.n_live = 0;
+}
+
+// apply: 0 nothing, 1 previous query answered xy2 (its "old" array is old2), 2 previous query answered xy1
+// gather_from: 0 no new query (final call), 1 next query uses pts[xy1] (pts = pts1), 2 next query uses pts[xy2]
+__global__ void __launch_bounds__(1024)
+    frn_step(FrnState st, int apply, int roll, int gather_from, const float* __restrict__ pts, uint8_t* converged) {
+  __shared__ int warp_tot[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = st.n_seeds;
+  if (apply) {
+    int32_t* dst = (apply == 1) ? st.xy2 : st.xy1;
+    const int32_t* old = (apply == 1) ? st.old2 : st.old1;
+    const int n_prev = *st.n_live;
+    for (int i = tid; i < n_prev; i += blockDim.x) {
+      const int s = st.list[i];
+      const unsigned long long k = st.keys[i];
+      const int32_t nn = (k == 0ull) ? -1 : (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+      dst[s] = nn;
+      if (old[s] == nn) st.notyet[s] = 0;     // converged: the neighbour did not change (fast_nn.py:157,164)
+    }
+    __syncthreads();
+  }
+  if (roll) {
+    for (int s = tid; s < n; s += blockDim.x) {
+      st.old1[s] = st.xy1[s];
+      st.old2[s] = st.xy2[s];
+    }
+    __syncthreads();
+  }
+  if (converged)
+    for (int s = tid; s < n; s += blockDim.x) converged[s] = st.notyet[s] ? 0 : 1;
+  if (!gather_from) return;
+  // ordered compaction of the live seeds
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < n; s0 += blockDim.x) {
+    const int s = s0 + tid;
+    const int live = (s < n && st.notyet[s]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < wid; ++w) before += warp_tot[w];
+    if (live) st.list[before + __popc(bal & ((1u << lane) - 1u))] = s;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += warp_tot[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  const int n_live = s_base;
+  if (tid == 0) *st.n_live = n_live;
+  const int32_t* src = (gather_from == 1) ? st.xy1 : st.xy2;
+  for (int e = tid; e < n_live * st.D; e += blockDim.x) {
+    const int i = e / st.D, k = e - i * st.D;
+    st.qbuf[e] = pts[(size_t)src[st.list[i]] * st.D + k];
+  }
+  for (int i = tid; i < n; i += blockDim.x) st.keys[i] = 0ull;
+}
+
+// keys -> indices for both directions in one launch (outB may be null)
+__global__ void nn_unpack_kernel(const unsigned long long* __restrict__ keysA, int64_t* __restrict__ outA, int nA,
+                                 const unsigned long long* __restrict__ keysB, int64_t* __restrict__ outB, int nB) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long* keys = keysA;
+  int64_t* out = outA;
+  if (i >= nA) {
+    i -= nA;
+    keys = keysB;
+    out = outB;
+    if (!out || i >= nB) return;
+  }
+  const unsigned long long k = keys[i];
+  out[i] = (k == 0ull) ? int64_t(-1) : int64_t(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+}
+
+constexpr int STREAM_SMALL = 16, STREAM_BIG = 64;      // query-count classes of the streaming kernel
+
+template <int NQ>
+int launch_stream(const float* Q, int nq, const int* nq_dev, int nq_min, const float* DB, int64_t ndb, int64_t D, int dist,
+                  unsigned long long* keysQ, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * ((size_t)D * NQ + NQ);
+  int blocks = (int)ceil_div<int64_t>(ndb, 256);
+  const int cap = 8 * num_sms();
+  blocks = blocks > cap ? cap : blocks;
+  GD3_PROF("nn_stream_kernel", stream);
+  if (dist == 0) nn_stream_kernel<0, NQ><<<blocks, 256, smem, stream>>>(Q, nq, nq_dev, nq_min, DB, (int)ndb, (int)D, keysQ);
+  else nn_stream_kernel<1, NQ><<<blocks, 256, smem, stream>>>(Q, nq, nq_dev, nq_min, DB, (int)ndb, (int)D, keysQ);
+  GD3_CHECK_LAUNCH();
+  return GD3_OK;
+}
+inline bool stream_ok(int64_t D) { return D <= STREAM_MAX_D; }
 
 // arg-best DB row for every Q row (outQ) and, when keysDB / outDB are given, arg-best Q row for every DB row
 int nn_search(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t D, int dist, unsigned long long* keysQ,
               int64_t* outQ, unsigned long long* keysDB, int64_t* outDB, cudaStream_t stream) {
   const bool both = outDB != nullptr;
   GD3_CHECK_CUDA(cudaMemsetAsync(keysQ, 0, sizeof(unsigned long long) * nq, stream));
+  if (!both && nq <= STREAM_BIG && stream_ok(D) && ndb >= 4096) {
+    // a handful of queries against a large DB: streaming kernel (see nn_stream_kernel)
+    int rc = (nq <= STREAM_SMALL)
+                 ? launch_stream<STREAM_SMALL>(Q, (int)nq, nullptr, 1, DB, ndb, D, dist, keysQ, stream)
+                 : launch_stream<STREAM_BIG>(Q, (int)nq, nullptr, 1, DB, ndb, D, dist, keysQ, stream);
+    if (rc) return rc;
+    GD3_PROF("nn_unpack_kernel", stream);
+    nn_unpack_kernel<<<(int)ceil_div<int64_t>(nq, 256), 256, 0, stream>>>(keysQ, outQ, (int)nq, nullptr, nullptr, 0);
+    GD3_CHECK_LAUNCH();
+    return GD3_OK;
+  }
   if (both) GD3_CHECK_CUDA(cudaMemsetAsync(keysDB, 0, sizeof(unsigned long long) * ndb, stream));
   const int q_tiles = (int)ceil_div<int64_t>(nq, TILE);
   const int db_tiles = (int)ceil_div<int64_t>(ndb, TILE);
@@ -211,29 +538,102 @@ int nn_search(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t 
   const int tiles_per_cta = ceil_div(db_tiles, y);
   y = ceil_div(db_tiles, tiles_per_cta);
   dim3 grid(q_tiles, y);
+  const size_t smem = nn_smem_bytes(both);
+  {
+    static bool configured = false;
+    if (!configured) {
+      const int big = (int)nn_smem_bytes(true), small = (int)nn_smem_bytes(false);
+      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
+      configured = true;
+    }
+  }
   {
     GD3_PROF("nn_tile_kernel", stream);
     if (dist == 0 && both)
-      nn_tile_kernel<0, true><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+      nn_tile_kernel<0, true><<<grid, THREADS, smem, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
     else if (dist == 0)
-      nn_tile_kernel<0, false><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+      nn_tile_kernel<0, false><<<grid, THREADS, smem, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
     else if (both)
-      nn_tile_kernel<1, true><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+      nn_tile_kernel<1, true><<<grid, THREADS, smem, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
     else
-      nn_tile_kernel<1, false><<<grid, THREADS, 0, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
+      nn_tile_kernel<1, false><<<grid, THREADS, smem, stream>>>(Q, (int)nq, DB, (int)ndb, (int)D, tiles_per_cta, keysQ, keysDB);
   }
   GD3_CHECK_LAUNCH();
   {
     GD3_PROF("nn_unpack_kernel", stream);
-    nn_unpack_kernel<<<(int)ceil_div<int64_t>(nq, 256), 256, 0, stream>>>(keysQ, outQ, (int)nq);
+    const int64_t n = nq + (both ? ndb : 0);
+    nn_unpack_kernel<<<(int)ceil_div<int64_t>(n, 256), 256, 0, stream>>>(keysQ, outQ, (int)nq, keysDB, outDB,
+                                                                       both ? (int)ndb : 0);
   }
   GD3_CHECK_LAUNCH();
-  if (both) {
-    GD3_PROF("nn_unpack_kernel", stream);
-    nn_unpack_kernel<<<(int)ceil_div<int64_t>(ndb, 256), 256, 0, stream>>>(keysDB, outDB, (int)ndb);
+  return GD3_OK;
+}
+
+// arg-best DB row for each of the first *nq_dev rows of Q (at most nq_max); keys must be zero on entry.  Every
+// kernel class is launched and the ones whose query-count range does not contain *nq_dev return at once.
+// The host only knows bounds nq_lo <= *nq_dev <= nq_max; classes outside the bounds are not launched at all.
+int nn_query_dev(const float* Q, int nq_lo, int nq_max, const int* nq_dev, const float* DB, int64_t ndb, int64_t D,
+                 int dist, unsigned long long* keys, cudaStream_t stream) {
+  int rc;
+  int tile_min = 1;
+  if (stream_ok(D)) {
+    if (nq_lo <= STREAM_SMALL)
+      if ((rc = launch_stream<STREAM_SMALL>(Q, 0, nq_dev, 1, DB, ndb, D, dist, keys, stream))) return rc;
+    tile_min = STREAM_SMALL + 1;
+    if (nq_max > STREAM_SMALL) {
+      if (nq_lo <= STREAM_BIG)
+        if ((rc = launch_stream<STREAM_BIG>(Q, 0, nq_dev, STREAM_SMALL + 1, DB, ndb, D, dist, keys, stream))) return rc;
+      tile_min = STREAM_BIG + 1;
+    }
+  }
+  if (nq_max >= tile_min) {
+    const int q_tiles = ceil_div(nq_max, TILE);
+    const int db_tiles = (int)ceil_div<int64_t>(ndb, TILE);
+    int y = (int)ceil_div<int64_t>(4 * num_sms(), q_tiles);
+    y = y < 1 ? 1 : (y > db_tiles ? db_tiles : y);
+    const int tiles_per_cta = ceil_div(db_tiles, y);
+    y = ceil_div(db_tiles, tiles_per_cta);
+    dim3 grid(q_tiles, y);
+    const size_t smem = nn_smem_bytes(false);
+    static bool configured = false;
+    if (!configured) {
+      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    GD3_PROF("nn_tile_kernel", stream);
+    if (dist == 0)
+      nn_tile_kernel<0, false><<<grid, THREADS, smem, stream>>>(Q, 0, DB, (int)ndb, (int)D, tiles_per_cta, keys, nullptr,
+                                                              nq_dev, tile_min);
+    else
+      nn_tile_kernel<1, false><<<grid, THREADS, smem, stream>>>(Q, 0, DB, (int)ndb, (int)D, tiles_per_cta, keys, nullptr,
+                                                              nq_dev, tile_min);
     GD3_CHECK_LAUNCH();
   }
   return GD3_OK;
+}
+
+struct FrnWorkspace {
+  FrnState st;
+  size_t total;
+};
+FrnWorkspace carve_frn(void* base, int64_t n_seeds, int64_t D) {
+  FrnWorkspace w{};
+  Carver c(base);
+  w.st.old1 = c.take<int32_t>(n_seeds);
+  w.st.old2 = c.take<int32_t>(n_seeds);
+  w.st.notyet = c.take<uint8_t>(n_seeds);
+  w.st.list = c.take<int32_t>(n_seeds);
+  w.st.n_live = c.take<int>(1);
+  w.st.keys = c.take<unsigned long long>(n_seeds);
+  w.st.qbuf = c.take<float>(n_seeds * D);
+  w.st.n_seeds = (int)n_seeds;
+  w.st.D = (int)D;
+  w.total = c.total();
+  return w;
 }
 
 }  // namespace
@@ -275,6 +675,79 @@ int gd3_reciprocal_nn(const float* A, int64_t nA, const float* B, int64_t nB, in
   unsigned long long* kB = c.take<unsigned long long>(nB);
   if (nn_A) return nn_search(A, nA, B, nB, dim, dist, kA, nn_A, nn_B ? kB : nullptr, nn_B, stream);
   return nn_search(B, nB, A, nA, dim, dist, kB, nn_B, nullptr, nullptr, stream);
+}
+
+size_t gd3_fast_reciprocal_nn_workspace(int64_t n_seeds, int64_t dim) {
+  if (n_seeds <= 0 || dim <= 0) return 0;
+  return carve_frn(nullptr, n_seeds, dim).total;
+}
+
+int gd3_fast_reciprocal_nn(const float* pts1, int64_t n1, const float* pts2, int64_t n2, int64_t dim, int dist,
+                           const int32_t* seeds, int64_t n_seeds, int max_iter, int host_poll, int32_t* xy1,
+                           int32_t* xy2, uint8_t* converged, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GD3_REQUIRE(dist == GD3_DIST_DOT || dist == GD3_DIST_L2, "Unknown dist=%d", dist);
+  GD3_REQUIRE(n1 > 0 && n2 > 0 && dim > 0 && n_seeds >= 0 && max_iter >= 1,
+              "gd3_fast_reciprocal_nn: bad sizes n1=%lld n2=%lld dim=%lld seeds=%lld max_iter=%d", (long long)n1,
+              (long long)n2, (long long)dim, (long long)n_seeds, max_iter);
+  GD3_REQUIRE(n1 < (1ll << 31) && n2 < (1ll << 31) && n_seeds < (1ll << 31), "gd3_fast_reciprocal_nn: more than 2^31 rows");
+  if (n_seeds == 0) return GD3_OK;
+  GD3_REQUIRE(pts1 && pts2 && seeds && xy1 && xy2 && converged, "gd3_fast_reciprocal_nn: null argument");
+  FrnWorkspace w = carve_frn(workspace, n_seeds, dim);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("gd3_fast_reciprocal_nn: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return GD3_ERR_WORKSPACE;
+  }
+  FrnState st = w.st;
+  st.xy1 = xy1;
+  st.xy2 = xy2;
+  int rc;
+  {
+    GD3_PROF("frn_init", stream);
+    frn_init<<<(unsigned)ceil_div<int64_t>(n_seeds, 256), 256, 0, stream>>>(st, seeds);
+  }
+  GD3_CHECK_LAUNCH();
+  {
+    GD3_PROF("frn_step", stream);
+    frn_step<<<1, 1024, 0, stream>>>(st, 0, 0, 1, pts1, nullptr);      // live list + queries of the first 1 -> 2 search
+  }
+  GD3_CHECK_LAUNCH();
+  int n_upper = (int)n_seeds;      // upper bound of the live seeds (refreshed by the host poll)
+  for (int it = 0; it < max_iter; ++it) {
+    const bool last = it + 1 == max_iter;
+    // 1 -> 2: query tree2 with pts1[xy1[live]]
+    // (in the first round every seed is live in both searches: old_xy2 is -1, so the 1 -> 2 answer retires nobody)
+    const int n_lower = it == 0 ? n_upper : 0;
+    if ((rc = nn_query_dev(st.qbuf, n_lower, n_upper, st.n_live, pts2, n2, dim, dist, st.keys, stream))) return rc;
+    {
+      GD3_PROF("frn_step", stream);
+      frn_step<<<1, 1024, 0, stream>>>(st, 1, 0, 2, pts2, nullptr);
+    }
+    GD3_CHECK_LAUNCH();
+    // 2 -> 1: query tree1 with pts2[xy2[live]]
+    if ((rc = nn_query_dev(st.qbuf, n_lower, n_upper, st.n_live, pts1, n1, dim, dist, st.keys, stream))) return rc;
+    // apply, and unless this was the last round roll the "old" arrays (fast_nn.py:166-170) and prepare the next search
+    {
+      GD3_PROF("frn_step", stream);
+      frn_step<<<1, 1024, 0, stream>>>(st, 2, last ? 0 : 1, last ? 0 : 1, pts1, last ? converged : nullptr);
+    }
+    GD3_CHECK_LAUNCH();
+    if (!last && host_poll && it >= 1) {
+      // nothing can converge before the second round; from then on ask the device how many seeds are still live
+      // (4 bytes + one stream synchronisation per round) instead of launching rounds that have nothing to do
+      int h_live = 0;
+      GD3_CHECK_CUDA(cudaMemcpyAsync(&h_live, st.n_live, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      GD3_CHECK_CUDA(cudaStreamSynchronize(stream));
+      if (h_live == 0) {
+        GD3_PROF("frn_step", stream);
+        frn_step<<<1, 1024, 0, stream>>>(st, 0, 0, 0, nullptr, converged);
+        GD3_CHECK_LAUNCH();
+        break;
+      }
+      n_upper = h_live;
+    }
+  }
+  return GD3_OK;
 }
 
 }  // extern "C"

@@ -22,6 +22,8 @@ SYMBOLS = {
     'gd3_profile_read': (_sz, [_c.c_char_p, _sz]),
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    'gd3_fast_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
+    'gd3_fast_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd3_cost_kl_group_size': (_i64, [_i64, _i64, _i64, _i64]),
     'gd3_cost_kl_workspace': (_sz, [_i64, _i64, _i64, _i64, _int]),
     'gd3_cost_kl': (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64,
@@ -126,6 +128,32 @@ def reciprocal_nn(A, B, dist='dot', want_A=True, want_B=True):
         check(lib.gd3_reciprocal_nn(ptr(A), nA, ptr(B), nB, A.shape[1], DIST[dist], ptr(nn_A), ptr(nn_B),
                                     ptr(ws), ws.numel(), stream_ptr()))
     return nn_A, nn_B
+
+
+def fast_reciprocal_nn(pts1, pts2, seeds, max_iter=10, dist='dot', host_poll=True):
+    """Device-resident reciprocal-NN ping-pong.  pts1 (n1, D), pts2 (n2, D) fp32 CUDA, seeds (S,) int32 CUDA flat
+    indices into pts1 -> (xy1, xy2) int32 CUDA and converged (S,) bool CUDA.  host_poll=False never synchronises;
+    host_poll=True reads the live-seed count back once per round (from the second on) to stop early."""
+    if dist not in DIST:
+        raise ValueError(f'Unknown {dist=}')
+    require_cuda(pts1, pts2, seeds)
+    lib = load()
+    pts1 = pts1.contiguous().float()
+    pts2 = pts2.contiguous().float()
+    seeds = seeds.contiguous().to(torch.int32)
+    if pts1.shape[1] != pts2.shape[1]:
+        raise ValueError('descriptor dimensions differ')
+    S = seeds.numel()
+    xy1 = torch.empty(S, dtype=torch.int32, device=pts1.device)
+    xy2 = torch.empty(S, dtype=torch.int32, device=pts1.device)
+    conv = torch.empty(S, dtype=torch.uint8, device=pts1.device)
+    ws = workspace(lib.gd3_fast_reciprocal_nn_workspace(S, pts1.shape[1]), pts1.device)
+    with torch.cuda.device(pts1.device):
+        check(lib.gd3_fast_reciprocal_nn(ptr(pts1), pts1.shape[0], ptr(pts2), pts2.shape[0], pts1.shape[1], DIST[dist],
+                                         ptr(seeds), S, int(max_iter), int(bool(host_poll)), ptr(xy1), ptr(xy2), ptr(conv),
+                                         ptr(ws),
+                                         ws.numel(), stream_ptr()))
+    return xy1, xy2, conv.bool()
 
 
 def debug_gemm_bf16(A, B, tile_n=256):

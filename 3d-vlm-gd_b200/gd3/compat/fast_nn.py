@@ -122,6 +122,23 @@ def fast_reciprocal_NNs(pts1, pts2, subsample_or_initxy1=8, ret_xy=True, pixel_t
         max_iter = 1
 
     xy1 = np.int32(np.unique(x1 + W1 * y1))
+    dist = matcher_kw.get('dist', 'l2')
+    unknown = set(matcher_kw) - {'dist', 'block_size'}
+    if unknown:
+        raise TypeError(f'unexpected matcher arguments {sorted(unknown)}')
+    if dist not in ('l2', 'dot'):
+        raise ValueError(f'Unknown {dist=}')
+    if pixel_tol == 0 and not ret_basin:
+        # the whole ping-pong runs on the device (gd3_fast_reciprocal_nn): one copy back at the end instead of
+        # one per query; ret_basin / pixel_tol keep the reference's host bookkeeping below
+        if len(xy1) == 0:
+            empty = np.zeros(0, dtype=np.int32)
+            return merge_corres(empty, empty, (H1, W1), (H2, W2), ret_xy=ret_xy)
+        seeds = torch.from_numpy(xy1).to(pts1.device)
+        d1, d2, conv = _lib.fast_reciprocal_nn(pts1, pts2, seeds, max_iter=max_iter, dist=dist)
+        keep = conv.nonzero().squeeze(1)
+        out = torch.stack([d1[keep], d2[keep]]).cpu().numpy()
+        return merge_corres(out[0], out[1], (H1, W1), (H2, W2), ret_xy=ret_xy)
     xy2 = np.full_like(xy1, -1)
     old_xy1 = xy1.copy()
     old_xy2 = xy2.copy()

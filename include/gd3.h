@@ -70,6 +70,27 @@ int gd3_reciprocal_nn(const float* A, int64_t nA, const float* B, int64_t nB, in
                       int64_t* nn_A, int64_t* nn_B, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Device-resident ping-pong of fast_reciprocal_NNs (mast3r/fast_nn.py:109-188, the loop at :147-170
+ * for ret_basin=False, pixel_tol=0): starting from `seeds` (unique, sorted flat indices into pts1,
+ * :130-131), alternately replace every live seed's partner by its nearest neighbour in the other
+ * image (1 -> 2, then 2 -> 1), retiring a seed as soon as a partner repeats (:157,164), for at
+ * most max_iter rounds (10 for grid seeds, 1 for explicit seeds, :121-128).  No host
+ * synchronisation inside; the reference copies indices to the host after every 8192-block.
+ *   pts1 (n1, dim), pts2 (n2, dim) fp32 descriptors; dist as for gd3_reciprocal_nn
+ *   xy1, xy2  (n_seeds) int32 out: final flat indices (:182 keeps the converged ones)
+ *   converged (n_seeds) uint8 out: ~notyet of the reference
+ * host_poll = 0: never synchronises (all max_iter rounds are enqueued; rounds without live seeds are
+ *   cheap no-ops), usable under stream capture.  host_poll = 1: from the second round on, reads the
+ *   number of live seeds back after each round (4 bytes + a stream synchronisation) and stops early,
+ *   like the reference's `while notyet.any()`.
+ * The unique + sort of merge_corres (:87-106) stays with the caller.
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_fast_reciprocal_nn_workspace(int64_t n_seeds, int64_t dim);
+int gd3_fast_reciprocal_nn(const float* pts1, int64_t n1, const float* pts2, int64_t n2, int64_t dim, int dist,
+                           const int32_t* seeds, int64_t n_seeds, int max_iter, int host_poll, int32_t* xy1,
+                           int32_t* xy2, uint8_t* converged, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dense cost-volume KL loss, forward + backward, batched over P image pairs.
  * Replaces the body of calculate_cost_loss (src/finetune_timm_mast3r.py:504-540 for
  * GD3_VARIANT_MAST3R, src/finetune_timm_vggt.py:488-533 for GD3_VARIANT_VGGT) including

@@ -136,3 +136,53 @@ def test_fast_reciprocal_nns_real_shape(gd3mod):
     r1, r2 = oracle_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=16, device='cpu', dist='dot',
                                            block_size=2 ** 13)
     assert xy1.shape == r1.shape and (xy1 == r1).all() and (xy2 == r2).all()
+
+
+@pytest.mark.parametrize('dist', ['dot', 'l2'])
+@pytest.mark.parametrize('nq,dim', [(1, 24), (7, 24), (16, 24), (17, 24), (64, 24), (5, 3), (33, 10), (12, 128)])
+def test_few_queries_streaming_kernel(gd3mod, dist, nq, dim):
+    """A handful of queries against a large DB takes the streaming kernel: same answers (lowest-index ties) as the
+    oracle, and as the tile kernel on the same data (bit-identical scores)."""
+    from gd3 import _lib
+    g = torch.Generator().manual_seed(nq * 131 + dim)
+    DB = torch.randint(-8, 9, (6000, dim), generator=g).float() / 8          # exactly representable, many ties
+    DB[4000:4100] = DB[100:200]                                               # duplicated rows
+    Q = DB[torch.randint(0, 6000, (nq,), generator=g)] + (torch.randint(-1, 2, (nq, dim), generator=g).float() / 8)
+    ref, _ = oracle_nn.bruteforce_reciprocal_nns(Q, DB, device='cpu', dist=dist)
+    got, _ = _lib.reciprocal_nn(Q.cuda(), DB.cuda(), dist=dist, want_B=False)        # streaming kernel (nq <= 64)
+    assert (got.cpu().numpy() == ref).all()
+    both, _ = _lib.reciprocal_nn(Q.cuda(), DB.cuda(), dist=dist, want_B=True)        # tile kernel
+    assert torch.equal(both, got)
+
+
+@pytest.mark.parametrize('dist', ['dot', 'l2'])
+def test_device_resident_ping_pong(gd3mod, dist):
+    """gd3_fast_reciprocal_nn against the reference loop (oracle) for both distances, grid and explicit seeds."""
+    from gd3.compat import fast_nn
+    d1, d2 = synth.nn_desc_maps(77, 96, 128)
+    d1 = torch.round(d1 * 16) / 8
+    d2 = torch.round(d2 * 16) / 8
+    for S in (16, 8, 3):
+        xy1, xy2 = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=S, device='cuda', dist=dist)
+        r1, r2 = oracle_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=S, device='cpu', dist=dist, block_size=2 ** 13)
+        assert xy1.shape == r1.shape and (xy1 == r1).all() and (xy2 == r2).all(), S
+    # explicit seeds: a single round (mast3r/fast_nn.py:122-128)
+    ys, xs = np.mgrid[2:96:7, 3:128:5].reshape(2, -1)
+    xy1, xy2 = fast_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=(xs, ys), device='cuda', dist=dist)
+    r1, r2 = oracle_nn.fast_reciprocal_NNs(d1, d2, subsample_or_initxy1=(xs, ys), device='cpu', dist=dist,
+                                           block_size=2 ** 13)
+    assert xy1.shape == r1.shape and (xy1 == r1).all() and (xy2 == r2).all()
+
+
+def test_device_ping_pong_poll_modes_agree(gd3mod):
+    """host_poll only decides when to stop launching rounds: both modes return identical arrays."""
+    from gd3 import _lib
+    d1, d2 = synth.nn_desc_maps(78, 64, 96)
+    p1 = (torch.round(d1 * 16) / 8).reshape(-1, 24).cuda()
+    p2 = (torch.round(d2 * 16) / 8).reshape(-1, 24).cuda()
+    seeds = torch.arange(5, 64 * 96, 37, dtype=torch.int32).cuda()
+    a = _lib.fast_reciprocal_nn(p1, p2, seeds, max_iter=10, dist='dot', host_poll=True)
+    b = _lib.fast_reciprocal_nn(p1, p2, seeds, max_iter=10, dist='dot', host_poll=False)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert a[2].any()
