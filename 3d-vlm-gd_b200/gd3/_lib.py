@@ -22,6 +22,8 @@ SYMBOLS = {
     'gd3_profile_read': (_sz, [_c.c_char_p, _sz]),
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    'gd3_semantic_argmax_workspace': (_sz, [_i64, _i64, _i64]),
+    'gd3_semantic_argmax': (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     'gd3_fast_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_fast_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd3_cost_kl_group_size': (_i64, [_i64, _i64, _i64, _i64]),
@@ -154,6 +156,38 @@ def fast_reciprocal_nn(pts1, pts2, seeds, max_iter=10, dist='dot', host_poll=Tru
                                          ptr(ws),
                                          ws.numel(), stream_ptr()))
     return xy1, xy2, conv.bool()
+
+
+def semantic_argmax(kp_desc, desc2, img_size, patch_size=14, stride=14, want_val=False):
+    """Arg-max pixel (y * img_size + x) of image 2 for every keypoint descriptor of image 1.
+
+    kp_desc: (K, C) or the reference's (1, C, K) fp32 CUDA (any strides); desc2: (1, C, ph, pw) or (C, ph, pw) fp32 CUDA.
+    Returns int64 (K,) [and the similarity attained]."""
+    require_cuda(kp_desc, desc2)
+    lib = load()
+    if kp_desc.dim() == 3:                      # (1, C, K) as produced by interpolate_features
+        assert kp_desc.shape[0] == 1
+        kd = kp_desc[0].float()
+        sk, sc = kd.stride(1), kd.stride(0)
+        K, C = kd.shape[1], kd.shape[0]
+    else:
+        kd = kp_desc.float()
+        sk, sc = kd.stride(0), kd.stride(1)
+        K, C = kd.shape
+    d2 = desc2.float()
+    if d2.dim() == 4:
+        assert d2.shape[0] == 1
+        d2 = d2[0]
+    d2 = d2.contiguous()
+    assert d2.shape[0] == C
+    ph, pw = d2.shape[1], d2.shape[2]
+    idx = torch.empty(K, dtype=torch.int64, device=d2.device)
+    val = torch.empty(K, dtype=torch.float32, device=d2.device) if want_val else None
+    ws = workspace(lib.gd3_semantic_argmax_workspace(K, ph, pw), d2.device)
+    with torch.cuda.device(d2.device):
+        check(lib.gd3_semantic_argmax(ptr(kd), sk, sc, ptr(d2), K, C, ph, pw, int(img_size), int(patch_size), int(stride),
+                                      ptr(idx), ptr(val), ptr(ws), ws.numel(), stream_ptr()))
+    return (idx, val) if want_val else idx
 
 
 def debug_gemm_bf16(A, B, tile_n=256):

@@ -197,6 +197,24 @@ int gd3_sample_tokens_bwd(const float* grad_out, int64_t gP, int64_t gK, int64_t
                           const float* grad_extra, int64_t eP, int64_t eK, int64_t eC, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Keypoint -> best-matching pixel of the other image.  Replaces the inline block
+ * src/evaluate_timm.py:532-547: F.interpolate(img2_desc, (ds, ds), bilinear, align_corners=True)
+ * with ds = (img - patch) // stride * stride + 1, VF.pad(..., padding_mode='edge') to img x img,
+ * einsum('nfk,nif->nki') against the K keypoint descriptors and argmax over the img^2 pixels --
+ * without materialising the upsampled (1, C, img, img) map (the interpolation is applied to the
+ * K x (ph pw) low-resolution similarity instead; it is linear).
+ *   kp_desc  element (k, c) at kp_desc[k * kd_stride_k + c * kd_stride_c] fp32 (the reference's
+ *            interpolate_features output (1, C, K): stride_k = 1, stride_c = K)
+ *   desc2    (C, ph, pw) fp32 contiguous patch descriptors of image 2
+ *   nn_idx   (K) int64: y * img + x of the arg-max pixel, lowest index on ties (:543-545)
+ *   nn_val   (K) fp32 or NULL: the similarity attained
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_semantic_argmax_workspace(int64_t K, int64_t ph, int64_t pw);
+int gd3_semantic_argmax(const float* kp_desc, int64_t kd_stride_k, int64_t kd_stride_c, const float* desc2, int64_t K,
+                        int64_t C, int64_t ph, int64_t pw, int64_t img_size, int64_t patch_size, int64_t stride,
+                        int64_t* nn_idx, float* nn_val, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Debug / self-test: C[b] = A[b] * B[b]^T through the tcgen05 GEMM used by all fused losses.
  * A: (batch, M, lda) bf16, B: (batch, N, ldb) bf16, C: (batch, M, ldc) fp32.  Not a reference
  * interface; used by tests to validate the TMA / UMMA descriptor plumbing in isolation.
