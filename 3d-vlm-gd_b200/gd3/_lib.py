@@ -22,6 +22,8 @@ SYMBOLS = {
     'gd3_profile_read': (_sz, [_c.c_char_p, _sz]),
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    'gd3_teacher_volume_workspace': (_sz, [_i64, _i64, _i64]),
+    'gd3_teacher_volume': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _sz, _vp]),
     'gd3_semantic_argmax_workspace': (_sz, [_i64, _i64, _i64]),
     'gd3_semantic_argmax': (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     'gd3_fast_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
@@ -156,6 +158,26 @@ def fast_reciprocal_nn(pts1, pts2, seeds, max_iter=10, dist='dot', host_poll=Tru
                                          ptr(ws),
                                          ws.numel(), stream_ptr()))
     return xy1, xy2, conv.bool()
+
+
+def teacher_volume(tgt_camap, src_camap=None, temperature=3.0, reciprocity=True):
+    """tgt_attn_map (B, N, N) from the per-layer cross-attention logits (lists of (B, H, N, N) fp32 CUDA tensors)."""
+    import ctypes
+    lib = load()
+    tgt = [t.contiguous().float() for t in tgt_camap]
+    require_cuda(*tgt)
+    src = [t.contiguous().float() for t in src_camap] if reciprocity else []
+    L = len(tgt)
+    B, H, N, N2 = tgt[0].shape
+    assert N == N2 and all(t.shape == tgt[0].shape for t in tgt + src) and (not reciprocity or len(src) == L)
+    arr_t = (ctypes.c_void_p * L)(*[t.data_ptr() for t in tgt])
+    arr_s = (ctypes.c_void_p * L)(*[t.data_ptr() for t in src]) if reciprocity else None
+    out = torch.empty(B, N, N, dtype=torch.float32, device=tgt[0].device)
+    ws = workspace(lib.gd3_teacher_volume_workspace(L, B, N), out.device)
+    with torch.cuda.device(out.device):
+        check(lib.gd3_teacher_volume(arr_t, arr_s, L, B, H, N, float(temperature), int(bool(reciprocity)), ptr(out),
+                                     ptr(ws), ws.numel(), stream_ptr()))
+    return out
 
 
 def semantic_argmax(kp_desc, desc2, img_size, patch_size=14, stride=14, want_val=False):

@@ -215,6 +215,21 @@ int gd3_semantic_argmax(const float* kp_desc, int64_t kd_stride_k, int64_t kd_st
                         int64_t* nn_idx, float* nn_val, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * MASt3R teacher cost-volume post-processing, fused.  Replaces
+ * dust3r/dust3r/model.py:346-366: per decoder layer, head-mean of both branches' pre-softmax
+ * cross-attention logits (dust3r/croco/models/blocks.py:163-164), symmetrisation with the
+ * transposed other branch, softmax(./temperature), column 0 := global minimum of the layer
+ * (:353-354), then the mean over layers (:363).  reciprocity = 0 follows :355-359 (head-mean only).
+ *   tgt_layers, src_layers  HOST arrays of L DEVICE pointers, each (B, H, N, N) fp32 contiguous
+ *   out                     (B, N, N) fp32 = tgt_attn_map
+ * Every logit is read once; workspace holds the per-layer maps (L B N^2 fp32).
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_teacher_volume_workspace(int64_t L, int64_t B, int64_t N);
+int gd3_teacher_volume(const float* const* tgt_layers, const float* const* src_layers, int64_t L, int64_t B, int64_t H,
+                       int64_t N, float temperature, int reciprocity, float* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Debug / self-test: C[b] = A[b] * B[b]^T through the tcgen05 GEMM used by all fused losses.
  * A: (batch, M, lda) bf16, B: (batch, N, ldb) bf16, C: (batch, M, ldc) fp32.  Not a reference
  * interface; used by tests to validate the TMA / UMMA descriptor plumbing in isolation.
