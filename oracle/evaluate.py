@@ -1,6 +1,9 @@
 """Oracle restatement of the keypoint-transfer block of the reference's evaluation.
 
 Test infrastructure only (see ``oracle/__init__.py``).  Plain PyTorch on CPU.
+
+**Parity unpinned**: the block is inline in the evaluation loop of ``src/evaluate_timm.py`` (which needs timm, the datasets and a checkpoint), so no golden vector could be
+produced by the live reference; the restatement re-types those lines around the same torch ops.
 """
 import torch
 import torch.nn.functional as F

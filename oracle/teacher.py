@@ -1,6 +1,9 @@
 """Oracle restatement of the MASt3R teacher's cost-volume post-processing.
 
 Test infrastructure only (see ``oracle/__init__.py``).  Plain PyTorch on CPU.
+
+**Parity unpinned**: the block sits inside ``AsymmetricCroCo3DStereo.forward`` and cannot be called without the teacher model and its weights, so no golden vector could be
+produced by the live reference; the restatement re-types those lines around the same torch ops.
 """
 import torch
 
