@@ -330,38 +330,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// 3. W^T[g][j][i] = m1_i t~12_ij + m2_j t~21_ji      grid (ceil(N/32) i-tiles, ceil(N/32) j-tiles, G)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    kl_build_w(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
-               int64_t t_row_stride, int pair0, int G, int N, const float* __restrict__ invR,
-               const float* __restrict__ epsm, float* __restrict__ WT, int ldw) {
-  __shared__ float tile[32][33];
-  const int g = blockIdx.z, i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const float* T12 = t12 + (int64_t)(pair0 + g) * t_pair_stride;
-  const float* T21 = t21 + (int64_t)(pair0 + g) * t_pair_stride;
-  const float* ir12 = invR + (int64_t)g * N;
-  const float* ir21 = invR + ((int64_t)G + g) * N;
-  const float* e12 = epsm + (int64_t)g * N;
-  const float* e21 = epsm + ((int64_t)G + g) * N;
-  // t~12 tile read with lanes along j (its contiguous direction), transposed through smem
-  for (int r = w; r < 32; r += 8) {
-    const int i = i0 + r, j = j0 + lane;
-    float v = 0.f;
-    if (i < N && j < N) v = fmaxf(__ldg(T12 + (int64_t)i * t_row_stride + j) * ir12[i], e12[i]);
-    tile[r][lane] = v;
-  }
-  __syncthreads();
-  for (int r = w; r < 32; r += 8) {
-    const int j = j0 + r, i = i0 + lane;
-    if (i < N && j < N) {
-      const float v21 = fmaxf(__ldg(T21 + (int64_t)j * t_row_stride + i) * ir21[j], e21[j]);
-      WT[((int64_t)g * N + j) * ldw + i] = tile[lane][r] + v21;
-    }
-  }
-}
+// (step 3, W^T[g][j][i] = m1_i t~12_ij + m2_j t~21_ji, is kl_build_w_fast below)
 
 // ------------------------------------------------------------------------------------------
 // 4. pass-1 epilogue: softmax statistics + D term straight from the TMEM accumulator
@@ -466,83 +435,16 @@ __global__ void kl_finalize_stats(int G, int N, const float* __restrict__ invR, 
 }
 
 // ------------------------------------------------------------------------------------------
-// 6. dz = s ((r_i + c_j) exp(z) - W), written as dz (row i) and dz^T (row j) in bf16, + row/col dots
-//    grid (ceil(N/64) j-tiles, ceil(N/64) i-tiles, G), block 256
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    kl_dz(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT, int ldw,
-          const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT, int ldd,
-          float* __restrict__ rowdot, float* __restrict__ coldot, double* __restrict__ loss_acc) {
-  __shared__ float ws[64][65];     // W^T tile, [j][i]
-  __shared__ float ds[64][65];     // dz tile, [i][j]
-  __shared__ float cdot[8][64];
-  __shared__ float red[32];
-  float wz = 0.f;                  // sum W z of this tile (the D term of the loss)
-  const int g = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const float* wt = WT + (int64_t)g * N * ldw;
-  for (int r = w; r < 64; r += 8) {
-    const int j = j0 + r;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = i0 + lane + 32 * h;
-      ws[r][lane + 32 * h] = (j < N && i < N) ? __ldg(wt + (int64_t)j * ldw + i) : 0.f;
-    }
-  }
-  __syncthreads();
-  const float s = grad_scale * 0.5f / (float)N;
-  const float* rr = rc + (int64_t)g * N;
-  const float* cc = rc + ((int64_t)G + g) * N;
-  const int jl = 2 * lane, j = j0 + jl;
-  const float c0 = (j < N) ? cc[j] : 0.f, c1 = (j + 1 < N) ? cc[j + 1] : 0.f;
-  float cd0 = 0.f, cd1 = 0.f;
-  for (int r = w; r < 64; r += 8) {
-    const int i = i0 + r;
-    float d0 = 0.f, d1 = 0.f, rd = 0.f;
-    if (i < N && j < N) {
-      // ldz is a multiple of 8, so reading the pair (j, j+1) stays inside the row even when j+1 == N
-      const __half2 zz = *reinterpret_cast<const __half2*>(Z + ((int64_t)g * N + i) * ldz + j);
-      const float z0 = __low2float(zz), z1 = (j + 1 < N) ? __high2float(zz) : 0.f;
-      const float ri = rr[i];
-      d0 = s * ((ri + c0) * exp2f(z0 * LOG2E) - ws[jl][r]);
-      d1 = (j + 1 < N) ? s * ((ri + c1) * exp2f(z1 * LOG2E) - ws[jl + 1][r]) : 0.f;
-      wz = fmaf(ws[jl][r], z0, wz);
-      if (j + 1 < N) wz = fmaf(ws[jl + 1][r], z1, wz);
-      *reinterpret_cast<uint32_t*>(dZ + ((int64_t)g * N + i) * ldd + j) = pack_bf16x2(d0, d1);
-      rd = fmaf(d0, z0, d1 * z1);
-      cd0 = fmaf(d0, z0, cd0);
-      cd1 = fmaf(d1, z1, cd1);
-    }
-    ds[r][jl] = d0;
-    ds[r][jl + 1] = d1;
-    rd = warp_sum(rd);
-    if (lane == 0 && i < N) atomicAdd(rowdot + (int64_t)g * N + i, rd);
-  }
-  cdot[w][jl] = cd0;
-  cdot[w][jl + 1] = cd1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += cdot[k][threadIdx.x];
-    if (j0 + threadIdx.x < N) atomicAdd(coldot + (int64_t)g * N + j0 + threadIdx.x, t);
-  }
-  // dz^T rows: lanes along i
-  const int il = 2 * lane, i = i0 + il;
-  for (int r = w; r < 64; r += 8) {
-    const int jj = j0 + r;
-    if (jj < N && i < N)
-      *reinterpret_cast<uint32_t*>(dZT + ((int64_t)g * N + jj) * ldd + i) = pack_bf16x2(ds[il][r], ds[il + 1][r]);
-  }
-  wz = block_sum(wz, red);
-  if (threadIdx.x == 0 && wz != 0.f) loss_add(loss_acc, g, blockIdx.x + blockIdx.y * 7u, -(0.5 / (double)N) * (double)wz);
-}
-
-// ------------------------------------------------------------------------------------------
-// Vectorised variants of steps 3 and 6 for N % 8 == 0 with 16-byte aligned teacher rows:
-// 64 x 64 tiles, 128-bit global accesses, padded shared-memory transposes.
+// Steps 3 and 6: 64 x 64 tiles, 128-bit global accesses wherever rows are 16-byte aligned (always for the padded
+// workspace buffers), padded shared-memory transposes.
+//   3. W^T[g][j][i] = m1_i t~12_ij + m2_j t~21_ji
+//   6. dz = s ((r_i + c_j) exp(z) - W), written as dz (row i) and dz^T (row j) in bf16, + row / col dots + sum W z
 // ------------------------------------------------------------------------------------------
 // grid (N/64 i-tiles, N/64 j-tiles, G), block 256: thread = (row tr of a 16-row pass, float4 column tc)
+// VEC: teacher rows are 16-byte aligned (128-bit loads); otherwise four scalar loads per thread (ragged N such as 37^2:
+// still 64 x 64 tiles, 256 contiguous bytes per 16 threads).  W^T rows are padded to a multiple of 4 floats, so its
+// stores are always 128-bit (elements in the padding are never read).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
     kl_build_w_fast(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
                     int64_t t_row_stride, int pair0, int G, int N, const float* __restrict__ invR,
@@ -561,7 +463,15 @@ __global__ void __launch_bounds__(256)
     const int r = ps * 16 + tr, i = i0 + r, j = j0 + tc;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < N && j < N) {
-      v = __ldg(reinterpret_cast<const float4*>(T12 + (int64_t)i * t_row_stride + j));
+      const float* src = T12 + (int64_t)i * t_row_stride + j;
+      if (VEC) {
+        v = __ldg(reinterpret_cast<const float4*>(src));
+      } else {
+        v.x = __ldg(src);
+        v.y = (j + 1 < N) ? __ldg(src + 1) : 0.f;
+        v.z = (j + 2 < N) ? __ldg(src + 2) : 0.f;
+        v.w = (j + 3 < N) ? __ldg(src + 3) : 0.f;
+      }
       const float ir = ir12[i], ee = e12[i];
       v.x = fmaxf(v.x * ir, ee); v.y = fmaxf(v.y * ir, ee); v.z = fmaxf(v.z * ir, ee); v.w = fmaxf(v.w * ir, ee);
     }
@@ -572,7 +482,16 @@ __global__ void __launch_bounds__(256)
   for (int ps = 0; ps < 4; ++ps) {
     const int r = ps * 16 + tr, j = j0 + r, i = i0 + tc;
     if (j < N && i < N) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(T21 + (int64_t)j * t_row_stride + i));
+      const float* src = T21 + (int64_t)j * t_row_stride + i;
+      float4 v;
+      if (VEC) {
+        v = __ldg(reinterpret_cast<const float4*>(src));
+      } else {
+        v.x = __ldg(src);
+        v.y = (i + 1 < N) ? __ldg(src + 1) : 0.f;
+        v.z = (i + 2 < N) ? __ldg(src + 2) : 0.f;
+        v.w = (i + 3 < N) ? __ldg(src + 3) : 0.f;
+      }
       const float ir = ir21[j], ee = e21[j];
       v.x = fmaxf(v.x * ir, ee) + tile[r][tc];
       v.y = fmaxf(v.y * ir, ee) + tile[r][tc + 1];
@@ -935,16 +854,15 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       }
       GD3_CHECK_LAUNCH();
       const bool vec_ok = N % 8 == 0 && rows_aligned;
-      if (vec_ok) {
+      {
         dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
         GD3_PROF("kl_build_w_fast", stream);
-        kl_build_w_fast<<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N, w.invR,
-                                                  w.epsm, w.WT, w.ldw);
-      } else {
-        dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)ceil_div<int64_t>(N, 32), (unsigned)g);
-        GD3_PROF("kl_build_w", stream);
-        kl_build_w<<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N, w.invR, w.epsm,
-                                           w.WT, w.ldw);
+        if (vec_ok)
+          kl_build_w_fast<true><<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N,
+                                                          w.invR, w.epsm, w.WT, w.ldw);
+        else
+          kl_build_w_fast<false><<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N,
+                                                           w.invR, w.epsm, w.WT, w.ldw);
       }
       GD3_CHECK_LAUNCH();
     }
@@ -976,14 +894,12 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     }
     if (backward) {
       dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
-      if (N % 8 == 0) {
+      {
+        // workspace rows are padded to a multiple of 8 elements, so the 128-bit kernel also serves ragged N (elements in
+        // the padding are masked on read and never consumed: the TMA extents of the gradient GEMMs stop at N)
         GD3_PROF("kl_dz_fast", stream);
         kl_dz_fast<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn,
                                              w.rowdot, w.coldot, w.loss_acc);
-      } else {
-        GD3_PROF("kl_dz", stream);
-        kl_dz<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn, w.rowdot,
-                                      w.coldot, w.loss_acc);
       }
       GD3_CHECK_LAUNCH();
       {

@@ -81,24 +81,30 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
-// fast kernel: 64 rows x 64 channels per iteration, 256 threads, thread = (row tr, 16 channels at tc)
+// fast kernel: 64 rows x 64 channels per iteration, 256 threads, thread = (row tr, 16 channels at tc).
+// With a transposed output a CTA's 64 rows belong to ONE set (tiles_per_set CTAs per set), so that an aligned group
+// of 8 rows never straddles two sets whatever K is; the rows past the end of the set are zeros (padding up to ldk).
 static __global__ void __launch_bounds__(256)
     split_fast(const float* __restrict__ x, int64_t R, int D, int ldd, int lo_panel, __nv_bfloat16* __restrict__ X3,
-               __nv_bfloat16* __restrict__ XT, XtLayout xl) {
+               __nv_bfloat16* __restrict__ XT, XtLayout xl, int tiles_per_set) {
   constexpr int TS = 66;
   __shared__ uint16_t t_hi[64 * TS];
   __shared__ uint16_t t_lo[64 * TS];
-  const int64_t r0 = (int64_t)blockIdx.x * 64;
-  const int tr = threadIdx.x >> 2, tc = (threadIdx.x & 3) * 16;
   const bool want_t = XT != nullptr && xl.panels != 0;
+  const int set = want_t ? blockIdx.x / tiles_per_set : 0;
+  const int k0 = want_t ? (blockIdx.x - set * tiles_per_set) * 64 : 0;
+  const int64_t r0 = want_t ? (int64_t)set * xl.K + k0 : (int64_t)blockIdx.x * 64;
+  const int64_t r_end = want_t ? (int64_t)set * xl.K + xl.K : R;       // rows of this CTA stop at the end of its set
+  const int tr = threadIdx.x >> 2, tc = (threadIdx.x & 3) * 16;
   for (int c0 = 0; c0 < D; c0 += 64) {
     {
       const int64_t row = r0 + tr;
+      const bool row_ok = row < r_end && row < R;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int c = c0 + tc + 8 * hh;
         float v[8];
-        if (row < R && c < D) {
+        if (row_ok && c < D) {
           const float4 a = __ldg(reinterpret_cast<const float4*>(x + row * D + c));
           const float4 b = __ldg(reinterpret_cast<const float4*>(x + row * D + c) + 1);
           v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -115,7 +121,7 @@ static __global__ void __launch_bounds__(256)
           ph[i] = (uint32_t)h[2 * i] | ((uint32_t)h[2 * i + 1] << 16);
           pl[i] = (uint32_t)l[2 * i] | ((uint32_t)l[2 * i + 1] << 16);
         }
-        if (row < R && c < D) {
+        if (row_ok && c < D) {
           __nv_bfloat16* o = X3 + row * 3 * ldd + c;
           const uint4 vh = make_uint4(ph[0], ph[1], ph[2], ph[3]), vl = make_uint4(pl[0], pl[1], pl[2], pl[3]);
           *reinterpret_cast<uint4*>(o) = vh;
@@ -138,15 +144,14 @@ static __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int nl = tc + 8 * hh;
-          const int64_t row = r0 + nl;
-          if (row < R) {                // K % 8 == 0: an aligned group of 8 rows never straddles two sets
+          if (k0 + nl < xl.K) {         // groups of 8 are aligned inside the set; rows past K in the group are zeros
             uint32_t ph[4], pl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               ph[i] = (uint32_t)t_hi[(nl + 2 * i) * TS + tr] | ((uint32_t)t_hi[(nl + 2 * i + 1) * TS + tr] << 16);
               pl[i] = (uint32_t)t_lo[(nl + 2 * i) * TS + tr] | ((uint32_t)t_lo[(nl + 2 * i + 1) * TS + tr] << 16);
             }
-            const int set = (int)(row / xl.K), k = (int)(row % xl.K);
+            const int k = k0 + nl;
             const uint4 vh = make_uint4(ph[0], ph[1], ph[2], ph[3]), vl = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             *reinterpret_cast<uint4*>(XT + xl.off(c, set, k, 0)) = vh;
             if (xl.panels == 3) {
@@ -168,15 +173,18 @@ static __global__ void __launch_bounds__(256)
 inline int launch_split3(const char* name, const float* x, int64_t R, int D, int ldd, int lo_panel,
                          __nv_bfloat16* X3, __nv_bfloat16* XT, const XtLayout& xl, cudaStream_t stream) {
   if (R <= 0) return GD3_OK;
-  const bool t_ok = XT == nullptr || xl.panels == 0 ||
-                    (xl.K % 8 == 0 && xl.ld % 8 == 0 && xl.ldk % 8 == 0 && xl.group_len % 8 == 0 &&
-                     xl.set_stride % 8 == 0 && reinterpret_cast<uintptr_t>(XT) % 16 == 0);
+  const bool want_t = XT != nullptr && xl.panels != 0;
+  const bool t_ok = !want_t || (xl.ld % 8 == 0 && xl.ldk % 8 == 0 && xl.ldk >= round_up(xl.K, 8) && xl.group_len % 8 == 0 &&
+                                xl.set_stride % 8 == 0 && R % xl.K == 0 && reinterpret_cast<uintptr_t>(XT) % 16 == 0);
   const bool fast = D % 8 == 0 && ldd == D && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(X3) % 16 == 0 && t_ok;
   {
     GD3_PROF(name, stream);
-    if (fast)
-      split_detail::split_fast<<<(unsigned)ceil_div<int64_t>(R, 64), 256, 0, stream>>>(x, R, D, ldd, lo_panel, X3, XT, xl);
+    if (fast) {
+      const int tps = want_t ? ceil_div(xl.K, 64) : 1;
+      const int64_t blocks = want_t ? (R / xl.K) * tps : ceil_div<int64_t>(R, 64);
+      split_detail::split_fast<<<(unsigned)blocks, 256, 0, stream>>>(x, R, D, ldd, lo_panel, X3, XT, xl, tps);
+    }
     else
       split_detail::split_scalar<<<(unsigned)ceil_div<int64_t>(R, 32), 256, 0, stream>>>(x, R, D, ldd, lo_panel, X3, XT,
                                                                                          xl);
