@@ -11,7 +11,9 @@
 //                   column strip (128-byte segments) meet in a shared 32 x N tile, row softmax, P_l written once,
 //                   layer minimum by an ordered-uint atomicMin.
 //   tv_mean_layers  out = mean_l P_l with column 0 taken from the layer minima.
-// reciprocity = 0 (:355-359): P_l = mean_h tgt_l without softmax; same column-0 rule.
+// mode GD3_TV_HEAD_MEAN (reciprocity off, :355-359): P_l = mean_h tgt_l without softmax; same column-0 rule.
+// mode GD3_TV_PLAIN_MEAN: mean over layers and heads only -- the VGGT teacher's aggregation of its per-block
+// attention maps (vggt/models/aggregator.py:273 followed by src/finetune_timm_vggt.py:390-392).
 #include "../../include/gd3.h"
 #include "common.cuh"
 
@@ -154,10 +156,10 @@ __global__ void __launch_bounds__(TV_THREADS)
 }
 
 __global__ void tv_mean_layers(const float* __restrict__ P, const uint32_t* __restrict__ layer_min, int L, int64_t BNN, int N,
-                               float* __restrict__ out) {
+                               int col0_rule, float* __restrict__ out) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= BNN) return;
-  const bool col0 = (e % N) == 0;
+  const bool col0 = col0_rule && (e % N) == 0;
   float a = 0.f;
   for (int l = 0; l < L; ++l) a += col0 ? tv_from_orderable(layer_min[l]) : P[(int64_t)l * BNN + e];
   out[e] = a / (float)L;
@@ -190,9 +192,12 @@ size_t gd3_teacher_volume_workspace(int64_t L, int64_t B, int64_t N) {
 }
 
 int gd3_teacher_volume(const float* const* tgt_layers, const float* const* src_layers, int64_t L, int64_t B, int64_t H,
-                       int64_t N, float temperature, int reciprocity, float* out, void* workspace,
+                       int64_t N, float temperature, int mode, float* out, void* workspace,
                        size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GD3_REQUIRE(mode == GD3_TV_RECIPROCAL || mode == GD3_TV_HEAD_MEAN || mode == GD3_TV_PLAIN_MEAN,
+              "gd3_teacher_volume: unknown mode %d", mode);
+  const int reciprocity = mode == GD3_TV_RECIPROCAL;
   GD3_REQUIRE(L > 0 && L <= TV_MAX_LAYERS && B > 0 && H > 0 && N > 0,
               "gd3_teacher_volume: bad sizes L=%lld B=%lld H=%lld N=%lld (at most %d layers)", (long long)L, (long long)B,
               (long long)H, (long long)N, TV_MAX_LAYERS);
@@ -238,7 +243,8 @@ int gd3_teacher_volume(const float* const* tgt_layers, const float* const* src_l
   {
     const int64_t BNN = B * N * N;
     GD3_PROF("tv_mean_layers", stream);
-    tv_mean_layers<<<(unsigned)ceil_div<int64_t>(BNN, 256), 256, 0, stream>>>(w.P, w.layer_min, (int)L, BNN, (int)N, out);
+    tv_mean_layers<<<(unsigned)ceil_div<int64_t>(BNN, 256), 256, 0, stream>>>(w.P, w.layer_min, (int)L, BNN, (int)N,
+                                                                              mode != GD3_TV_PLAIN_MEAN, out);
   }
   GD3_CHECK_LAUNCH();
   return GD3_OK;

@@ -160,8 +160,10 @@ def fast_reciprocal_nn(pts1, pts2, seeds, max_iter=10, dist='dot', host_poll=Tru
     return xy1, xy2, conv.bool()
 
 
-def teacher_volume(tgt_camap, src_camap=None, temperature=3.0, reciprocity=True):
-    """tgt_attn_map (B, N, N) from the per-layer cross-attention logits (lists of (B, H, N, N) fp32 CUDA tensors)."""
+def teacher_volume(tgt_camap, src_camap=None, temperature=3.0, reciprocity=True, plain_mean=False):
+    """tgt_attn_map (B, N, N) from the per-layer cross-attention logits (lists of (B, H, N, N) fp32 CUDA tensors).
+    plain_mean=True: mean over layers and heads only (the VGGT teacher's aggregation)."""
+    reciprocity = bool(reciprocity) and not plain_mean
     import ctypes
     lib = load()
     tgt = [t.contiguous().float() for t in tgt_camap]
@@ -175,7 +177,7 @@ def teacher_volume(tgt_camap, src_camap=None, temperature=3.0, reciprocity=True)
     out = torch.empty(B, N, N, dtype=torch.float32, device=tgt[0].device)
     ws = workspace(lib.gd3_teacher_volume_workspace(L, B, N), out.device)
     with torch.cuda.device(out.device):
-        check(lib.gd3_teacher_volume(arr_t, arr_s, L, B, H, N, float(temperature), int(bool(reciprocity)), ptr(out),
+        check(lib.gd3_teacher_volume(arr_t, arr_s, L, B, H, N, float(temperature), 2 if plain_mean else int(reciprocity), ptr(out),
                                      ptr(ws), ws.numel(), stream_ptr()))
     return out
 

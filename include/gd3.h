@@ -219,14 +219,21 @@ int gd3_semantic_argmax(const float* kp_desc, int64_t kd_stride_k, int64_t kd_st
  * dust3r/dust3r/model.py:346-366: per decoder layer, head-mean of both branches' pre-softmax
  * cross-attention logits (dust3r/croco/models/blocks.py:163-164), symmetrisation with the
  * transposed other branch, softmax(./temperature), column 0 := global minimum of the layer
- * (:353-354), then the mean over layers (:363).  reciprocity = 0 follows :355-359 (head-mean only).
+ * (:353-354), then the mean over layers (:363).
+ *   mode  GD3_TV_RECIPROCAL  the above (self.reciprocity = True, the configuration the fine-tuning uses)
+ *         GD3_TV_HEAD_MEAN   :355-359: head-mean, column-0 rule, layer mean (src_layers unused)
+ *         GD3_TV_PLAIN_MEAN  mean over layers and heads only: the VGGT teacher's aggregation of its
+ *                            per-block maps, vggt/models/aggregator.py:273 + src/finetune_timm_vggt.py:390-392
  *   tgt_layers, src_layers  HOST arrays of L DEVICE pointers, each (B, H, N, N) fp32 contiguous
  *   out                     (B, N, N) fp32 = tgt_attn_map
  * Every logit is read once; workspace holds the per-layer maps (L B N^2 fp32).
  * ------------------------------------------------------------------------------------------ */
+#define GD3_TV_HEAD_MEAN 0
+#define GD3_TV_RECIPROCAL 1
+#define GD3_TV_PLAIN_MEAN 2
 size_t gd3_teacher_volume_workspace(int64_t L, int64_t B, int64_t N);
 int gd3_teacher_volume(const float* const* tgt_layers, const float* const* src_layers, int64_t L, int64_t B, int64_t H,
-                       int64_t N, float temperature, int reciprocity, float* out, void* workspace,
+                       int64_t N, float temperature, int mode, float* out, void* workspace,
                        size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

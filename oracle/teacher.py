@@ -27,3 +27,11 @@ def teacher_volume(tgt_camap, src_camap, temperature=3.0, reciprocity=True):
         for i in range(len(tgt)):
             tgt[i][:, :, 0] = tgt[i].min()
     return torch.stack(tgt, dim=1).mean(dim=1)
+
+
+def vggt_cost_volumes(attn_list):
+    """Follows ``vggt/models/aggregator.py:273`` and ``src/finetune_timm_vggt.py:390-392``: mean over the
+    global blocks, split into the two directions, mean over heads.  attn_list: list of (2B, heads, n, n)."""
+    attn = torch.mean(torch.stack(attn_list), dim=0)
+    cost_1, cost_2 = attn.chunk(2, dim=0)
+    return cost_1.mean(dim=1), cost_2.mean(dim=1)

@@ -45,3 +45,12 @@ def test_teacher_volume_feeds_cost_kl():
     m = torch.ones(1, N, dtype=torch.bool).cuda()
     loss = ops.cost_volume_kl(f1, f2, t12, t21, m, m, variant='mast3r')
     assert torch.isfinite(loss).all() and (loss > 0).all()
+
+
+def test_vggt_plain_mean_matches_oracle():
+    from gd3.compat import teacher
+    g = torch.Generator().manual_seed(4)
+    maps = [torch.softmax(2 * torch.randn(2, 5, 120, 120, generator=g), -1) for _ in range(6)]
+    r1, r2 = oracle_teacher.vggt_cost_volumes(maps)
+    c1, c2 = teacher.vggt_cost_volumes([m.cuda() for m in maps])
+    assert torch.allclose(c1.cpu(), r1, rtol=2e-5, atol=1e-8) and torch.allclose(c2.cpu(), r2, rtol=2e-5, atol=1e-8)
