@@ -501,16 +501,24 @@ struct EpiRstd {
 // ------------------------------------------------------------------------------------------
 // number of valid pairs per set -> inv_count (per set, or shared when joint_mean)
 // ------------------------------------------------------------------------------------------
-__global__ void rank_count(const float* __restrict__ depth, int K, int mode, float thr, int* __restrict__ count) {
+// grid (ceil(K / 256), S), block 256: thread = one a, loop over all b with the set's depths in shared memory
+__global__ void __launch_bounds__(256) rank_count(const float* __restrict__ depth, int K, int mode, float thr,
+                                                  int* __restrict__ count) {
+  extern __shared__ float sdep[];     // K depths of this set
   __shared__ int red[32];
   const int set = blockIdx.y;
   const float* d = depth + (int64_t)set * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sdep[k] = d[k];
+  __syncthreads();
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
   int c = 0;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)K * K;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const int a = (int)(e / K), b = (int)(e - (int64_t)a * K);
-    const float dd = d[b] - d[a];
-    c += (mode == 0) ? (fabsf(dd) > thr) : (fabsf(tanhf(dd)) > thr);
+  if (a < K) {
+    const float da = sdep[a];
+    if (mode == 0) {
+      for (int b = 0; b < K; ++b) c += (fabsf(sdep[b] - da) > thr) ? 1 : 0;
+    } else {
+      for (int b = 0; b < K; ++b) c += (fabsf(tanhf(sdep[b] - da)) > thr) ? 1 : 0;
+    }
   }
   c = block_sum(c, red);
   if (threadIdx.x == 0 && c) atomicAdd(count + set, c);
@@ -794,6 +802,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   const bool l1 = w_l1 != nullptr;
   GD3_REQUIRE(!l1 || (S % 2 == 0 && loss_l1), "gd3_depth_head_loss: the L1 term needs an even number of sets and loss_l1");
   GD3_REQUIRE(S <= 65535, "gd3_depth_head_loss: at most 65535 sets per call");
+  GD3_REQUIRE(K <= 12288, "gd3_depth_head_loss: at most 12288 keypoints per set (K^2 pairs are evaluated)");
   const bool backward = grad_feats != nullptr;
   GD3_CHECK_CUDA(cudaMemsetAsync(loss_rank, 0, sizeof(float) * S, stream));
   if (l1) GD3_CHECK_CUDA(cudaMemsetAsync(loss_l1, 0, sizeof(float) * (S / 2), stream));
@@ -857,11 +866,10 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double) * S, stream));
   GD3_CHECK_CUDA(cudaMemsetAsync(w.l1_sum, 0, sizeof(double) * S, stream));
   {
-    const int64_t cnt_blocks = ceil_div<int64_t>(K * K, 256);
-    dim3 grid((unsigned)(cnt_blocks < 64 ? cnt_blocks : 64), (unsigned)S);
+    dim3 grid((unsigned)ceil_div<int64_t>(K, 256), (unsigned)S);
     {
       GD3_PROF("rank_count", stream);
-      rank_count<<<grid, 256, 0, stream>>>(depths, (int)K, mode, thr, w.count);
+      rank_count<<<grid, 256, sizeof(float) * K, stream>>>(depths, (int)K, mode, thr, w.count);
     }
     GD3_CHECK_LAUNCH();
     {
