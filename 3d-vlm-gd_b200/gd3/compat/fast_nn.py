@@ -1,17 +1,22 @@
-"""CUDA drop-in for the reference's ``mast3r/fast_nn.py`` (same names, arguments and errors).
+"""CUDA drop-in for the reference's ``mast3r/fast_nn.py``: same public names, arguments, return types and errors.
 
-The score matrix is never materialised: ``gd3_reciprocal_nn`` fuses the dot / l2 scores with the
-row and column arg-best (lowest index on ties, like ``torch.max`` / ``torch.min``).  Host-side
-bookkeeping (seed grid, convergence masks, unique + sort) stays in numpy exactly as in the
-reference, but one query costs a single small device->host copy instead of one per 8192-block.
+What runs where
+* every nearest-neighbour search is ``gd3_reciprocal_nn`` (fused scores + row / column arg-best, lowest index on ties
+  like ``torch.max`` / ``torch.min``; the score matrix is never materialised);
+* the seed ping-pong of ``fast_reciprocal_NNs`` (``mast3r/fast_nn.py:147-170``) is ``gd3_fast_reciprocal_nn``: the seed
+  state stays on the GPU for all rounds and comes back once;
+* only ``ret_basin=True`` keeps a host loop, because the basin table is host bookkeeping in the reference as well
+  (``:172-176``); unique + sort (``merge_corres``) is numpy as in the reference.
 
-Not provided: the scipy-KDTree branch the reference takes for CPU devices without ``dist`` /
-``block_size`` (``mast3r/fast_nn.py:142-145``) -- there is no CPU path in this library.
+Not provided: the scipy-KDTree branch the reference takes for CPU devices without ``dist`` / ``block_size``
+(``mast3r/fast_nn.py:142-145``) -- there is no CPU path in this library.
 """
 import numpy as np
 import torch
 
 from .. import _lib
+
+_DISTS = ('l2', 'dot')
 
 
 def _is_cuda_device(device):
@@ -26,192 +31,183 @@ def _need_gpu(device):
     _lib.require_cuda()
 
 
-def _to_device(x, device):
-    if isinstance(x, np.ndarray):
-        x = torch.from_numpy(x)
-    return x.to(device)
+def _on_device(x, device):
+    return (torch.from_numpy(x) if isinstance(x, np.ndarray) else x).to(device)
+
+
+def _matcher_options(kw):
+    """Validate the reference's ``**matcher_kw`` (dist / block_size) and return the distance name."""
+    extra = set(kw) - {'dist', 'block_size'}
+    if extra:
+        raise TypeError(f'unexpected matcher arguments {sorted(extra)}')
+    dist = kw.get('dist', 'l2')
+    if dist not in _DISTS:
+        raise ValueError(f'Unknown {dist=}')
+    return dist
 
 
 @torch.no_grad()
 def bruteforce_reciprocal_nns(A, B, device='cuda', block_size=None, dist='l2'):
-    """Mirror of ``mast3r/fast_nn.py:16-70``.  Returns (nn_A, nn_B) as int64 numpy arrays.
+    """``mast3r/fast_nn.py:16-70``: (nn_A, nn_B) int64 numpy arrays.
 
-    ``block_size`` is accepted for signature compatibility; it only bounded the reference's
-    temporary and never changed the result (the fused kernel has no temporary).
+    ``block_size`` only bounded the reference's temporary and never changed the result; the fused kernel has no
+    temporary, so the argument is accepted and ignored.
     """
-    if dist not in ('l2', 'dot'):
+    if dist not in _DISTS:
         raise ValueError(f'Unknown {dist=}')
     _need_gpu(device)
-    A = _to_device(A, device)
-    B = _to_device(B, device)
-    nn_A, nn_B = _lib.reciprocal_nn(A, B, dist=dist)
+    nn_A, nn_B = _lib.reciprocal_nn(_on_device(A, device), _on_device(B, device), dist=dist)
     return nn_A.cpu().numpy(), nn_B.cpu().numpy()
 
 
 class cdistMatcher:
-    """Mirror of ``mast3r/fast_nn.py:73-84``: a brute-force 'tree' over device-resident points."""
+    """``mast3r/fast_nn.py:73-84``: a brute-force "tree" over device-resident points; ``query`` returns (None, nn)."""
 
     def __init__(self, db_pts, device='cuda'):
         _need_gpu(device)
-        self.db_pts = db_pts.to(device).contiguous().float()
         self.device = device
+        self.db_pts = db_pts.to(device).contiguous().float()
 
     def query(self, queries, k=1, **kw):
         assert k == 1
         if queries.numel() == 0:
             return None, []
-        dist = kw.get('dist', 'l2')
-        unknown = set(kw) - {'dist', 'block_size'}
-        if unknown:
-            raise TypeError(f'unexpected matcher arguments {sorted(unknown)}')
-        if dist not in ('l2', 'dot'):
-            raise ValueError(f'Unknown {dist=}')
-        nn_A, _ = _lib.reciprocal_nn(_to_device(queries, self.device), self.db_pts, dist=dist, want_B=False)
-        return None, nn_A.cpu().numpy()
+        dist = _matcher_options(kw)
+        nn, _ = _lib.reciprocal_nn(_on_device(queries, self.device), self.db_pts, dist=dist, want_B=False)
+        return None, nn.cpu().numpy()
 
 
 def merge_corres(idx1, idx2, shape1=None, shape2=None, ret_xy=True, ret_index=False):
-    """Mirror of ``mast3r/fast_nn.py:87-106``: unique pairs sorted by idx1 then idx2."""
+    """``mast3r/fast_nn.py:87-106``: unique (idx1, idx2) pairs ordered by idx1 then idx2, optionally as pixel (x, y)."""
     assert idx1.dtype == idx2.dtype == np.int32
-    packed = (idx1.astype(np.int64) << 32) | (idx2.astype(np.int64) & 0xFFFFFFFF)
+    key = (idx1.astype(np.int64) << 32) | (idx2.astype(np.int64) & 0xFFFFFFFF)     # sorts like the pair
     if ret_index:
-        packed, indices = np.unique(packed, return_index=True)
+        key, first = np.unique(key, return_index=True)
     else:
-        packed = np.unique(packed)
-    xy1 = (packed >> 32).astype(np.int32)
-    xy2 = (packed & 0xFFFFFFFF).astype(np.int32)
+        key = np.unique(key)
+    xy1 = (key >> 32).astype(np.int32)
+    xy2 = (key & 0xFFFFFFFF).astype(np.int32)
     if ret_xy:
         assert shape1 and shape2
-        yx1 = np.unravel_index(xy1, shape1)
-        yx2 = np.unravel_index(xy2, shape2)
+        rc1 = np.unravel_index(xy1, shape1)
+        rc2 = np.unravel_index(xy2, shape2)
         if ret_xy == 'y_x':
-            xy1, xy2 = yx1, yx2
+            xy1, xy2 = rc1, rc2
         else:
-            xy1 = np.stack(yx1[::-1], axis=-1)
-            xy2 = np.stack(yx2[::-1], axis=-1)
-    if ret_index:
-        return xy1, xy2, indices
-    return xy1, xy2
+            xy1 = np.stack((rc1[1], rc1[0]), axis=-1)
+            xy2 = np.stack((rc2[1], rc2[0]), axis=-1)
+    return (xy1, xy2, first) if ret_index else (xy1, xy2)
+
+
+def _seed_indices(spec, H1, W1, grid_mode):
+    """Flat, unique, sorted int32 seed indices into image 1 (``:116-131``)."""
+    if grid_mode:
+        ys, xs = np.mgrid[spec // 2:H1:spec, spec // 2:W1:spec].reshape(2, -1)
+    else:
+        xs, ys = spec
+        xs = xs.cpu().numpy() if isinstance(xs, torch.Tensor) else xs
+        ys = ys.cpu().numpy() if isinstance(ys, torch.Tensor) else ys
+    return np.int32(np.unique(xs + W1 * ys))
+
+
+def _basin_walk(pts1, pts2, seeds, H1, W1, rounds, dist):
+    """The ``ret_basin=True`` variant of the ping-pong (``:147-176``): seeds are not retired on the 1 -> 2 leg and every
+    round records where each live seed of image 1 moved to.  Host loop (the basin table is host data)."""
+    cur1, cur2 = seeds.copy(), np.full_like(seeds, -1)
+    prev1 = cur1.copy()
+    live = np.ones(len(seeds), dtype=bool)
+    basin = np.full((H1 * W1 + 1,), -1, dtype=np.int32)
+
+    def nearest(queries, db):
+        nn, _ = _lib.reciprocal_nn(queries, db, dist=dist, want_B=False)
+        return nn.cpu().numpy()
+
+    def rows(pts, idx):
+        return pts[torch.from_numpy(idx.astype(np.int64)).to(pts.device)]
+
+    for r in range(rounds):
+        if not live.any():
+            break
+        cur2[live] = nearest(rows(pts1, cur1[live]), pts2)
+        cur1[live] = nearest(rows(pts2, cur2[live]), pts1)
+        basin[prev1[live]] = cur1[live]
+        live &= prev1 != cur1
+        if r + 1 < rounds:
+            prev1[:] = cur1
+    return cur1, cur2, ~live, basin
 
 
 def fast_reciprocal_NNs(pts1, pts2, subsample_or_initxy1=8, ret_xy=True, pixel_tol=0, ret_basin=False,
                         device='cuda', **matcher_kw):
-    """Mirror of ``mast3r/fast_nn.py:109-188`` (iterative reciprocal NN from a sparse seed grid)."""
+    """``mast3r/fast_nn.py:109-188``: iterative reciprocal nearest neighbours from a sparse seed grid (10 rounds) or from
+    explicit seeds (one round)."""
     H1, W1, DIM1 = pts1.shape
     H2, W2, DIM2 = pts2.shape
     assert DIM1 == DIM2
-
     if not ('dist' in matcher_kw or 'block_size' in matcher_kw or _is_cuda_device(device)):
         raise _lib.Gd3Error('the scipy-KDTree CPU branch of fast_reciprocal_NNs is not provided '
                             '(pass device="cuda" or dist=/block_size=)')
     _need_gpu(device)
+    dist = _matcher_options(matcher_kw)
+    flat1 = _on_device(pts1, device).reshape(-1, DIM1).contiguous().float()
+    flat2 = _on_device(pts2, device).reshape(-1, DIM2).contiguous().float()
 
-    pts1 = _to_device(pts1, device).reshape(-1, DIM1).contiguous().float()
-    pts2 = _to_device(pts2, device).reshape(-1, DIM2).contiguous().float()
+    grid_mode = isinstance(subsample_or_initxy1, int) and pixel_tol == 0
+    rounds = 10 if grid_mode else 1
+    seeds = _seed_indices(subsample_or_initxy1, H1, W1, grid_mode)
 
-    if isinstance(subsample_or_initxy1, int) and pixel_tol == 0:
-        S = subsample_or_initxy1
-        y1, x1 = np.mgrid[S // 2:H1:S, S // 2:W1:S].reshape(2, -1)
-        max_iter = 10
+    if ret_basin:
+        xy1, xy2, converged, basin = _basin_walk(flat1, flat2, seeds, H1, W1, rounds, dist)
     else:
-        x1, y1 = subsample_or_initxy1
-        if isinstance(x1, torch.Tensor):
-            x1 = x1.cpu().numpy()
-        if isinstance(y1, torch.Tensor):
-            y1 = y1.cpu().numpy()
-        max_iter = 1
-
-    xy1 = np.int32(np.unique(x1 + W1 * y1))
-    dist = matcher_kw.get('dist', 'l2')
-    unknown = set(matcher_kw) - {'dist', 'block_size'}
-    if unknown:
-        raise TypeError(f'unexpected matcher arguments {sorted(unknown)}')
-    if dist not in ('l2', 'dot'):
-        raise ValueError(f'Unknown {dist=}')
-    if pixel_tol == 0 and not ret_basin:
-        # the whole ping-pong runs on the device (gd3_fast_reciprocal_nn): one copy back at the end instead of
-        # one per query; ret_basin / pixel_tol keep the reference's host bookkeeping below
-        if len(xy1) == 0:
-            empty = np.zeros(0, dtype=np.int32)
-            return merge_corres(empty, empty, (H1, W1), (H2, W2), ret_xy=ret_xy)
-        seeds = torch.from_numpy(xy1).to(pts1.device)
-        d1, d2, conv = _lib.fast_reciprocal_nn(pts1, pts2, seeds, max_iter=max_iter, dist=dist)
-        keep = conv.nonzero().squeeze(1)
-        out = torch.stack([d1[keep], d2[keep]]).cpu().numpy()
-        return merge_corres(out[0], out[1], (H1, W1), (H2, W2), ret_xy=ret_xy)
-    xy2 = np.full_like(xy1, -1)
-    old_xy1 = xy1.copy()
-    old_xy2 = xy2.copy()
-
-    tree1 = cdistMatcher(pts1, device=device)
-    tree2 = cdistMatcher(pts2, device=device)
-
-    def gather(pts, idx):
-        return pts[torch.from_numpy(idx.astype(np.int64)).to(pts.device)]
-
-    notyet = np.ones(len(xy1), dtype=bool)
-    basin = np.full((H1 * W1 + 1,), -1, dtype=np.int32) if ret_basin else None
-
-    niter = 0
-    while notyet.any():
-        _, nn = tree2.query(gather(pts1, xy1[notyet]), **matcher_kw)
-        xy2[notyet] = nn
-        if not ret_basin:
-            notyet &= (old_xy2 != xy2)
-        _, nn = tree1.query(gather(pts2, xy2[notyet]), **matcher_kw)
-        xy1[notyet] = nn
-        if ret_basin:
-            basin[old_xy1[notyet]] = xy1[notyet]
-        notyet &= (old_xy1 != xy1)
-        niter += 1
-        if niter >= max_iter:
-            break
-        old_xy2[:] = xy2
-        old_xy1[:] = xy1
+        basin = None
+        if len(seeds) == 0:
+            xy1 = xy2 = np.zeros(0, dtype=np.int32)
+            converged = np.zeros(0, dtype=bool)
+        else:
+            d1, d2, conv = _lib.fast_reciprocal_nn(flat1, flat2, torch.from_numpy(seeds).to(flat1.device),
+                                                   max_iter=rounds, dist=dist)
+            packed = torch.stack([d1, d2, conv.to(torch.int32)]).cpu().numpy()      # the only copy back
+            xy1, xy2, converged = packed[0], packed[1], packed[2].astype(bool)
 
     if pixel_tol > 0:
-        old_yx1 = np.stack(np.unravel_index(old_xy1, (H1, W1)), axis=-1)
-        new_yx1 = np.stack(np.unravel_index(xy1, (H1, W1)), axis=-1)
-        converged = np.linalg.norm(old_yx1 - new_yx1, axis=-1) < pixel_tol
+        # explicit seeds, one round: a seed counts as converged when it came back within pixel_tol of where it
+        # started, and the reported position in image 1 is the seed itself (:172-180)
+        start = np.stack(np.unravel_index(seeds, (H1, W1)), axis=-1)
+        back = np.stack(np.unravel_index(xy1, (H1, W1)), axis=-1)
+        converged = np.linalg.norm(start - back, axis=-1) < pixel_tol
         if not isinstance(subsample_or_initxy1, int):
-            xy1 = old_xy1
-    else:
-        converged = ~notyet
+            xy1 = seeds
 
-    xy1, xy2 = merge_corres(xy1[converged], xy2[converged], (H1, W1), (H2, W2), ret_xy=ret_xy)
-    if ret_basin:
-        return xy1, xy2, basin
-    return xy1, xy2
+    out = merge_corres(xy1[converged], xy2[converged], (H1, W1), (H2, W2), ret_xy=ret_xy)
+    return out + (basin,) if ret_basin else out
 
 
 def extract_correspondences_nonsym(A, B, confA, confB, subsample=8, device=None, ptmap_key='pred_desc',
                                    pixel_tol=0):
-    """Mirror of ``mast3r/fast_nn.py:191-223`` for descriptor maps (``'3d' in ptmap_key`` is the
-    reference's CPU KDTree configuration and is not provided)."""
+    """``mast3r/fast_nn.py:191-223`` for descriptor maps: matches found from both sides are merged and carry the smaller
+    of the two confidences.  (``'3d' in ptmap_key`` is the reference's CPU KDTree configuration: not provided.)"""
     if '3d' in ptmap_key:
         raise _lib.Gd3Error('extract_correspondences_nonsym on 3-D point maps uses the CPU KDTree branch, '
                             'which gd3 does not provide')
-    opt = dict(device=device, dist='dot', block_size=2 ** 13)
-    HA, WA = A.shape[:2]
-    HB, WB = B.shape[:2]
-    if pixel_tol == 0:
-        nn1to2 = fast_reciprocal_NNs(A, B, subsample_or_initxy1=subsample, ret_xy=False, **opt)
-        nn2to1 = fast_reciprocal_NNs(B, A, subsample_or_initxy1=subsample, ret_xy=False, **opt)
-    else:
-        S = subsample
-        yA, xA = np.mgrid[S // 2:HA:S, S // 2:WA:S].reshape(2, -1)
-        yB, xB = np.mgrid[S // 2:HB:S, S // 2:WB:S].reshape(2, -1)
-        nn1to2 = fast_reciprocal_NNs(A, B, subsample_or_initxy1=(xA, yA), ret_xy=False, pixel_tol=pixel_tol, **opt)
-        nn2to1 = fast_reciprocal_NNs(B, A, subsample_or_initxy1=(xB, yB), ret_xy=False, pixel_tol=pixel_tol, **opt)
+    search = dict(device=device, dist='dot', block_size=2 ** 13, ret_xy=False)
+    shapeA, shapeB = A.shape[:2], B.shape[:2]
 
-    idx1 = np.r_[nn1to2[0], nn2to1[1]]
-    idx2 = np.r_[nn1to2[1], nn2to1[0]]
-    confA = confA.detach().cpu().numpy() if torch.is_tensor(confA) else np.asarray(confA)
-    confB = confB.detach().cpu().numpy() if torch.is_tensor(confB) else np.asarray(confB)
-    c1 = confA.ravel()[idx1]
-    c2 = confB.ravel()[idx2]
-    xy1, xy2, idx = merge_corres(idx1, idx2, (HA, WA), (HB, WB), ret_xy=True, ret_index=True)
-    conf = np.minimum(c1[idx], c2[idx])
-    out = (xy1.copy(), xy2.copy(), conf)
-    # the reference ends with dust3r's todevice(corres, device): numpy -> torch, then .to(device)
-    return tuple(torch.from_numpy(np.ascontiguousarray(x)).to(device) for x in out)
+    def seeds_of(shape):
+        if pixel_tol == 0:
+            return subsample
+        ys, xs = np.mgrid[subsample // 2:shape[0]:subsample, subsample // 2:shape[1]:subsample].reshape(2, -1)
+        return xs, ys
+
+    a_from_a, b_from_a = fast_reciprocal_NNs(A, B, subsample_or_initxy1=seeds_of(shapeA), pixel_tol=pixel_tol, **search)
+    b_from_b, a_from_b = fast_reciprocal_NNs(B, A, subsample_or_initxy1=seeds_of(shapeB), pixel_tol=pixel_tol, **search)
+    idxA = np.r_[a_from_a, a_from_b]
+    idxB = np.r_[b_from_a, b_from_b]
+
+    def flat_conf(c):
+        return (c.detach().cpu().numpy() if torch.is_tensor(c) else np.asarray(c)).ravel()
+
+    cA, cB = flat_conf(confA)[idxA], flat_conf(confB)[idxB]
+    xyA, xyB, first = merge_corres(idxA, idxB, shapeA, shapeB, ret_xy=True, ret_index=True)
+    conf = np.minimum(cA[first], cB[first])
+    # the reference finishes with dust3r's todevice(corres, device): numpy -> torch -> device
+    return tuple(torch.from_numpy(np.ascontiguousarray(v)).to(device) for v in (xyA.copy(), xyB.copy(), conf))

@@ -171,3 +171,32 @@ def fast_reciprocal_NNs(pts1, pts2, subsample_or_initxy1=8, ret_xy=True, pixel_t
     if ret_basin:
         return out1, out2, basin
     return out1, out2
+
+
+def extract_correspondences_nonsym(A, B, confA, confB, subsample=8, device='cpu', ptmap_key='pred_desc', pixel_tol=0):
+    """Matches searched from both images, merged, with min(confA, confB) per match.
+
+    Follows ``mast3r/fast_nn.py:191-223``.  Returns (xy1, xy2, conf) as torch tensors like the
+    reference's ``todevice``.
+    """
+    if '3d' in ptmap_key:
+        opt = dict(device='cpu', workers=32)
+    else:
+        opt = dict(device=device, dist='dot', block_size=2 ** 13)
+    HA, WA = A.shape[:2]
+    HB, WB = B.shape[:2]
+    if pixel_tol == 0:
+        ab = fast_reciprocal_NNs(A, B, subsample_or_initxy1=subsample, ret_xy=False, **opt)
+        ba = fast_reciprocal_NNs(B, A, subsample_or_initxy1=subsample, ret_xy=False, **opt)
+    else:
+        yA, xA = np.mgrid[subsample // 2:HA:subsample, subsample // 2:WA:subsample].reshape(2, -1)
+        yB, xB = np.mgrid[subsample // 2:HB:subsample, subsample // 2:WB:subsample].reshape(2, -1)
+        ab = fast_reciprocal_NNs(A, B, subsample_or_initxy1=(xA, yA), ret_xy=False, pixel_tol=pixel_tol, **opt)
+        ba = fast_reciprocal_NNs(B, A, subsample_or_initxy1=(xB, yB), ret_xy=False, pixel_tol=pixel_tol, **opt)
+    idx1 = np.r_[ab[0], ba[1]]
+    idx2 = np.r_[ab[1], ba[0]]
+    c1 = np.asarray(confA).ravel()[idx1]
+    c2 = np.asarray(confB).ravel()[idx2]
+    xy1, xy2, first = merge_corres(idx1, idx2, (HA, WA), (HB, WB), ret_xy=True, ret_index=True)
+    conf = np.minimum(c1[first], c2[first])
+    return tuple(torch.from_numpy(np.ascontiguousarray(v)) for v in (xy1.copy(), xy2.copy(), conf))

@@ -337,5 +337,29 @@ def main():
     print('fast_nn done')
 
 
+def fast_nn_extra():
+    """``extract_correspondences_nonsym`` (``mast3r/fast_nn.py:191-223``) from the live reference ->
+    ``tests/golden/fast_nn_extra.npz``.  Separate file so that the other golden files stay byte-identical."""
+    from oracle import synth
+    _, _, _, RN = import_reference()
+    out = {}
+    d1, d2 = synth.nn_desc_maps(61, 40, 56)
+    d1 = torch.round(d1 * 16) / 8
+    d2 = torch.round(d2 * 16) / 8
+    g = torch.Generator().manual_seed(62)
+    cA = torch.rand(40, 56, generator=g) + 1.0
+    cB = torch.rand(40, 56, generator=g) + 1.0
+    out['d1'], out['d2'], out['cA'], out['cB'] = _np(d1), _np(d2), _np(cA), _np(cB)
+    for tag, tol in (('tol0', 0), ('tol2', 2)):
+        xy1, xy2, conf = RN.extract_correspondences_nonsym(d1, d2, cA.numpy(), cB.numpy(), subsample=8, device='cpu',
+                                                           pixel_tol=tol)
+        out[f'{tag}/xy1'], out[f'{tag}/xy2'], out[f'{tag}/conf'] = _np(xy1), _np(xy2), _np(conf)
+        print('extract_correspondences_nonsym', tag, tuple(xy1.shape))
+    np.savez_compressed(os.path.join(OUT, 'fast_nn_extra.npz'), **out)
+
+
 if __name__ == '__main__':
-    main()
+    if '--fast-nn-extra' in sys.argv:
+        fast_nn_extra()
+    else:
+        main()

@@ -186,3 +186,16 @@ def test_device_ping_pong_poll_modes_agree(gd3mod):
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     assert a[2].any()
+
+
+def test_extract_correspondences_nonsym_golden(gd3mod, golden):
+    """Both-sided matching with confidences (mast3r/fast_nn.py:191-223) against the live reference's output."""
+    from gd3.compat import fast_nn
+    g = golden('fast_nn_extra.npz')
+    d1, d2 = torch.from_numpy(g['d1']), torch.from_numpy(g['d2'])
+    for tag, tol in (('tol0', 0), ('tol2', 2)):
+        xy1, xy2, conf = fast_nn.extract_correspondences_nonsym(d1, d2, torch.from_numpy(g['cA']), g['cB'], subsample=8,
+                                                                device='cuda', pixel_tol=tol)
+        assert xy1.is_cuda and conf.is_cuda
+        assert (xy1.cpu().numpy() == g[f'{tag}/xy1']).all() and (xy2.cpu().numpy() == g[f'{tag}/xy2']).all()
+        assert np.array_equal(conf.cpu().numpy(), g[f'{tag}/conf'])

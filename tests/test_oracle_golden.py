@@ -167,3 +167,15 @@ def test_fast_nn_oracle(golden):
     a1, a2 = fast_nn.fast_reciprocal_NNs(p1, p2, subsample_or_initxy1=4, device='cpu')
     b1, b2 = fast_nn.fast_reciprocal_NNs(p1, p2, subsample_or_initxy1=4, device='cpu', dist='l2')
     assert (a1 == b1).all() and (a2 == b2).all()
+
+
+def test_extract_correspondences_nonsym_golden(golden):
+    """``mast3r/fast_nn.py:191-223`` run by the live reference (oracle/gen_golden.py --fast-nn-extra)."""
+    from oracle import fast_nn
+    g = golden('fast_nn_extra.npz')
+    d1, d2 = torch.from_numpy(g['d1']), torch.from_numpy(g['d2'])
+    for tag, tol in (('tol0', 0), ('tol2', 2)):
+        xy1, xy2, conf = fast_nn.extract_correspondences_nonsym(d1, d2, g['cA'], g['cB'], subsample=8, device='cpu',
+                                                                pixel_tol=tol)
+        assert (xy1.numpy() == g[f'{tag}/xy1']).all() and (xy2.numpy() == g[f'{tag}/xy2']).all()
+        assert np.array_equal(conf.numpy(), g[f'{tag}/conf'])
