@@ -267,9 +267,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Single-read variant for N <= 128 * NV, N % 4 == 0 and 16-byte aligned rows: the whole row sits in registers
-// (NV float4 per lane), all loads of a row are in flight at once.
-template <int NV>
+// Single-read variant for N <= 128 * NV: the whole row sits in registers (4 NV floats per lane) and all loads of a
+// row are in flight at once.  VEC: N % 4 == 0 and 16-byte aligned rows (128-bit loads); otherwise scalar loads
+// (ragged N such as 37^2, whose rows are not 16-byte aligned).
+template <int NV, bool VEC>
 __global__ void __launch_bounds__(256)
     kl_teacher_stats_vec(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
                          int64_t t_row_stride, const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, int pair0,
@@ -293,31 +294,37 @@ __global__ void __launch_bounds__(256)
     }
     return;
   }
-  const float4* row = reinterpret_cast<const float4*>((dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride +
-                                                      (int64_t)i * t_row_stride);
-  const int nv = N >> 2;
-  float4 v[NV];
+  const float* rowp = (dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride + (int64_t)i * t_row_stride;
+  float v[4 * NV];       // VEC: element 4 * (lane + 32 k) + q at v[4 k + q]; scalar: element lane + 32 k at v[k]
+  if (VEC) {
+    const float4* row = reinterpret_cast<const float4*>(rowp);
+    const int nv = N >> 2;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int j = lane + 32 * k;
-    v[k] = (j < nv) ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < NV; ++k) {
+      const int j = lane + 32 * k;
+      const float4 t4 = (j < nv) ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * k] = t4.x; v[4 * k + 1] = t4.y; v[4 * k + 2] = t4.z; v[4 * k + 3] = t4.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4 * NV; ++k) {
+      const int j = lane + 32 * k;
+      v[k] = (j < N) ? __ldg(rowp + j) : 0.f;
+    }
   }
   float R = 0.f;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) R += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  for (int k = 0; k < NV; ++k) R += (v[4 * k] + v[4 * k + 1]) + (v[4 * k + 2] + v[4 * k + 3]);
   R = warp_sum(R);
   const float ir = 1.f / fmaxf(R, eps);
   float T = 0.f, A = 0.f;
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    if (lane + 32 * k < nv) {
-      const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float tt = fmaxf(e[q] * ir, eps);
-        T += tt;
-        A = fmaf(tt, __logf(tt), A);
-      }
+  for (int k = 0; k < 4 * NV; ++k) {
+    const bool in_row = VEC ? (4 * (lane + 32 * (k >> 2)) < N) : (lane + 32 * k < N);
+    if (in_row) {
+      const float tt = fmaxf(v[k] * ir, eps);
+      T += tt;
+      A = fmaf(tt, __logf(tt), A);
     }
   }
   T = warp_sum(T);
@@ -841,12 +848,16 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       {
         GD3_PROF("kl_teacher_stats", stream);
         const unsigned blocks = (unsigned)ceil_div<int64_t>(warps, 8);
-#define GD3_TSTATS(NV)                                                                                             \
-  kl_teacher_stats_vec<NV><<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g,  \
-                                                       (int)N, eps, masked_const, w.invR, w.epsm, w.Tsum, w.loss_acc)
-        if (rows_aligned && N % 4 == 0 && N <= 512) GD3_TSTATS(4);
-        else if (rows_aligned && N % 4 == 0 && N <= 1024) GD3_TSTATS(8);
-        else if (rows_aligned && N % 4 == 0 && N <= 2048) GD3_TSTATS(16);
+#define GD3_TSTATS(NV, VEC)                                                                                          \
+  kl_teacher_stats_vec<NV, VEC><<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, \
+                                                            (int)N, eps, masked_const, w.invR, w.epsm, w.Tsum,          \
+                                                            w.loss_acc)
+        // (the scalar-load instantiation of the register-resident kernel measured slower than the two-pass kernel on
+        // unaligned rows -- 345 vs 185 us at N = 37^2 -- so ragged N keeps the two-pass kernel)
+        const bool v4 = rows_aligned && N % 4 == 0;
+        if (v4 && N <= 512) GD3_TSTATS(4, true);
+        else if (v4 && N <= 1024) GD3_TSTATS(8, true);
+        else if (v4 && N <= 2048) GD3_TSTATS(16, true);
         else
           kl_teacher_stats<<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, (int)N,
                                                        eps, masked_const, w.invR, w.epsm, w.Tsum, w.loss_acc);
