@@ -56,16 +56,14 @@ template <class T>
 __global__ void __launch_bounds__(256)
     kl_prep_features(const T* __restrict__ f1, const T* __restrict__ f2, int64_t s1P, int64_t s1N, int64_t s1C,
                      int64_t s2P, int64_t s2N, int64_t s2C, int pair0, int N, int C, int ldc, int ldn,
-                     __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ aT,
-                     __nv_bfloat16* __restrict__ bT, float* __restrict__ inv1, float* __restrict__ inv2) {
+                     __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b, float* __restrict__ inv1,
+                     float* __restrict__ inv2) {
   __shared__ float s_inv[32];
   __shared__ float tile[32][33];
   const int img = blockIdx.z, g = blockIdx.y, n0 = blockIdx.x * 32;
   const T* f = (img == 0 ? f1 : f2) + (int64_t)(pair0 + g) * (img == 0 ? s1P : s2P);
   const int64_t sN = img == 0 ? s1N : s2N, sC = img == 0 ? s1C : s2C;
   __nv_bfloat16* o = (img == 0 ? a : b) + (int64_t)g * N * ldc;
-  __nv_bfloat16* oT = (img == 0 ? aT : bT);   // transposes are only needed by the backward GEMMs
-  if (oT) oT += (int64_t)g * C * ldn;
   float* inv = (img == 0 ? inv1 : inv2) + (int64_t)g * N;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool row_major = sC <= sN;   // pick the coalesced direction of the source
@@ -108,9 +106,6 @@ __global__ void __launch_bounds__(256)
     for (int r = w; r < 32; r += 8) {
       // a[n][c]: lanes along c
       if (n0 + r < N && c0 + lane < C) o[(int64_t)(n0 + r) * ldc + c0 + lane] = __float2bfloat16(tile[r][lane]);
-      // aT[c][n]: lanes along n
-      if (oT && c0 + r < C && n0 + lane < N)
-        oT[(int64_t)(c0 + r) * ldn + n0 + lane] = __float2bfloat16(tile[lane][r]);
     }
   }
 }
@@ -135,87 +130,52 @@ __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float
   }
 }
 
-template <class T>
+// One warp per token row, 8 rows per CTA; a row of up to 256 * NIT channels is read once into registers
+// (128-bit loads), normalised and written back as bf16 (128-bit stores).  Longer rows are read a second time.
+template <class T, int NIT>
 __global__ void __launch_bounds__(256)
     kl_prep_fast(const T* __restrict__ f1, const T* __restrict__ f2, int64_t s1P, int64_t s1N, int64_t s2P, int64_t s2N,
-                 int pair0, int N, int C, int ldc, int ldn, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b,
-                 __nv_bfloat16* __restrict__ aT, __nv_bfloat16* __restrict__ bT, float* __restrict__ inv1,
-                 float* __restrict__ inv2) {
-  constexpr int TS = 66;                       // smem row stride in bf16 (33 words: conflict-free column reads)
-  __shared__ __nv_bfloat16 tile[64 * TS];
-  __shared__ float s_inv[64];
-  const int img = blockIdx.z, g = blockIdx.y, n0 = blockIdx.x * 64;
-  const T* f = (img == 0 ? f1 : f2) + (int64_t)(pair0 + g) * (img == 0 ? s1P : s2P);
-  const int64_t sN = img == 0 ? s1N : s2N;
-  __nv_bfloat16* o = (img == 0 ? a : b) + (int64_t)g * N * ldc;
-  __nv_bfloat16* oT = (img == 0 ? aT : bT);
-  if (oT) oT += (int64_t)g * C * ldn;
-  float* inv = (img == 0 ? inv1 : inv2) + (int64_t)g * N;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  // ---- row norms: one warp per row, 8 elements per lane and iteration ----
-  for (int r = w; r < 64; r += 8) {
-    const int n = n0 + r;
-    float ss = 0.f;
-    if (n < N)
-      for (int c = lane * 8; c < C; c += 256) {
-        float v[8];
-        ld8(f + n * sN + c, v);
+                 int pair0, int N, int C, int ldc, __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b,
+                 float* __restrict__ inv1, float* __restrict__ inv2) {
+  const int img = blockIdx.z, g = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const T* row = (img == 0 ? f1 : f2) + (int64_t)(pair0 + g) * (img == 0 ? s1P : s2P) + (int64_t)n * (img == 0 ? s1N : s2N);
+  __nv_bfloat16* o = (img == 0 ? a : b) + ((int64_t)g * N + n) * ldc;
+  float v[NIT][8];
+  float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
-      }
-    ss = warp_sum(ss);
-    if (lane == 0) {
-      const float iv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-      s_inv[r] = iv;
-      if (n < N) inv[n] = iv;
+  for (int it = 0; it < NIT; ++it) {
+    const int c = lane * 8 + 256 * it;
+    if (c < C) {
+      ld8(row + c, v[it]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss = fmaf(v[it][i], v[it][i], ss);
     }
   }
-  __syncthreads();
-  // ---- 64 x 64 tiles: normalised rows -> a (row-major) and, through smem, aT ----
-  const int tr = threadIdx.x >> 2, tc = (threadIdx.x & 3) * 16;     // 4 threads per row, 16 channels each
-  for (int c0 = 0; c0 < C; c0 += 64) {
-    {
-      const int n = n0 + tr;
-      const float iv = s_inv[tr];
+  for (int c = lane * 8 + 256 * NIT; c < C; c += 256) {       // rows longer than the register budget
+    float t[8];
+    ld8(row + c, t);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int c = c0 + tc + 8 * hh;
-        float v[8];
-        if (n < N && c < C) ld8(f + n * sN + c, v);
-        else {
+    for (int i = 0; i < 8; ++i) ss = fmaf(t[i], t[i], ss);
+  }
+  ss = warp_sum(ss);
+  const float iv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0) (img == 0 ? inv1 : inv2)[(int64_t)g * N + n] = iv;
+  auto store8 = [&](int c, const float (&x)[8]) {
+    *reinterpret_cast<uint4*>(o + c) = make_uint4(pack_bf16x2(x[0] * iv, x[1] * iv), pack_bf16x2(x[2] * iv, x[3] * iv),
+                                                  pack_bf16x2(x[4] * iv, x[5] * iv), pack_bf16x2(x[6] * iv, x[7] * iv));
+  };
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pk[i] = pack_bf16x2(v[2 * i] * iv, v[2 * i + 1] * iv);
-        if (n < N && c < C) *reinterpret_cast<uint4*>(o + (int64_t)n * ldc + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        uint32_t* trow = reinterpret_cast<uint32_t*>(tile + tr * TS + tc + 8 * hh);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) trow[i] = pk[i];
-      }
-    }
-    __syncthreads();
-    if (oT) {
-      const int cc = c0 + tr;          // this thread writes aT row (channel) cc, 16 consecutive tokens
-      if (cc < C) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int nl = tc + 8 * hh;
-          if (n0 + nl < ldn) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint16_t lo = *reinterpret_cast<const uint16_t*>(tile + (nl + 2 * i) * TS + tr);
-              const uint16_t hi = *reinterpret_cast<const uint16_t*>(tile + (nl + 2 * i + 1) * TS + tr);
-              pk[i] = (uint32_t)lo | ((uint32_t)hi << 16);
-            }
-            *reinterpret_cast<uint4*>(oT + (int64_t)cc * ldn + n0 + nl) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
-        }
-      }
-    }
-    __syncthreads();
+  for (int it = 0; it < NIT; ++it) {
+    const int c = lane * 8 + 256 * it;
+    if (c < C) store8(c, v[it]);
+  }
+  for (int c = lane * 8 + 256 * NIT; c < C; c += 256) {
+    float t[8];
+    ld8(row + c, t);
+    store8(c, t);
   }
 }
 
@@ -512,9 +472,9 @@ __global__ void __launch_bounds__(256)
 // grid (N/64 j-tiles, N/64 i-tiles, G), block 256
 __global__ void __launch_bounds__(256)
     kl_dz_fast(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT,
-               int ldw, const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, __nv_bfloat16* __restrict__ dZT,
-               int ldd, float* __restrict__ rowdot, float* __restrict__ coldot, double* __restrict__ loss_acc) {
-  __shared__ float ws[64][65];      // W^T tile [j][i]; later reused as dz [i][j]
+               int ldw, const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, int ldd,
+               float* __restrict__ rowdot, float* __restrict__ coldot, double* __restrict__ loss_acc) {
+  __shared__ float ws[64][65];      // W^T tile [j][i]
   __shared__ float cdot[32][65];
   __shared__ float red[32];
   float wz = 0.f;                   // sum W z of this tile (the D term of the loss)
@@ -542,7 +502,6 @@ __global__ void __launch_bounds__(256)
     cj[q] = (j0 + jc + q < N) ? cc[j0 + jc + q] : 0.f;
     cdp[q] = 0.f;
   }
-  float dzv[2][8];
 #pragma unroll
   for (int ps = 0; ps < 2; ++ps) {
     const int r = ps * 32 + tr8, i = i0 + r;
@@ -573,33 +532,15 @@ __global__ void __launch_bounds__(256)
     rd += __shfl_xor_sync(0xffffffffu, rd, 2);
     rd += __shfl_xor_sync(0xffffffffu, rd, 4);
     if ((threadIdx.x & 7) == 0 && i < N) atomicAdd(rowdot + (int64_t)g * N + i, rd);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) dzv[ps][q] = d[q];
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) cdot[tr8][jc + q] = cdp[q];
-  __syncthreads();                   // all reads of ws (as W^T) are done
-#pragma unroll
-  for (int ps = 0; ps < 2; ++ps)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) ws[ps * 32 + tr8][jc + q] = dzv[ps][q];     // now dz [i][j]
+  __syncthreads();
   if (threadIdx.x < 64) {
     float t = 0.f;
 #pragma unroll 8
     for (int k = 0; k < 32; ++k) t += cdot[k][threadIdx.x];
     if (j0 + threadIdx.x < N) atomicAdd(coldot + (int64_t)g * N + j0 + threadIdx.x, t);
-  }
-  __syncthreads();
-  // dz^T rows: thread = (row j of a 32-row pass, 8 consecutive i)
-#pragma unroll
-  for (int ps = 0; ps < 2; ++ps) {
-    const int r = ps * 32 + tr8, j = j0 + r, ic = jc;
-    if (j < N && i0 + ic < N) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) pk[q] = pack_bf16x2(ws[ic + 2 * q][r], ws[ic + 2 * q + 1][r]);
-      *reinterpret_cast<uint4*>(dZT + ((int64_t)g * N + j) * ldd + i0 + ic) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
   }
   wz = block_sum(wz, red);
   if (threadIdx.x == 0 && wz != 0.f) loss_add(loss_acc, g, blockIdx.x + blockIdx.y * 7u, -(0.5 / (double)N) * (double)wz);
@@ -696,7 +637,7 @@ __global__ void kl_write_loss(const double* __restrict__ acc, float* __restrict_
 }
 
 struct KLWorkspace {
-  __nv_bfloat16 *a, *b, *aT, *bT, *dZ, *dZT;
+  __nv_bfloat16 *a, *b, *dZ;
   __half* Z;
   float *inv1, *inv2, *invR, *epsm, *Tsum, *WT, *Lrow, *Lcol, *rc, *rowdot, *coldot;
   double* loss_acc;
@@ -713,8 +654,6 @@ KLWorkspace carve_kl(void* base, int64_t G, int64_t N, int64_t C, bool backward)
   w.ldw = (int)round_up<int64_t>(N, 4);
   w.a = c.take<__nv_bfloat16>(G * N * w.ldc);
   w.b = c.take<__nv_bfloat16>(G * N * w.ldc);
-  w.aT = c.take<__nv_bfloat16>(backward ? G * C * w.ldn : 0);
-  w.bT = c.take<__nv_bfloat16>(backward ? G * C * w.ldn : 0);
   w.inv1 = c.take<float>(G * N);
   w.inv2 = c.take<float>(G * N);
   w.invR = c.take<float>(2 * G * N);
@@ -729,7 +668,6 @@ KLWorkspace carve_kl(void* base, int64_t G, int64_t N, int64_t C, bool backward)
   w.loss_acc = c.take<double>(G * kLossSlots);
   w.Z = c.take<__half>(backward ? G * N * w.ldn : 0);
   w.dZ = c.take<__nv_bfloat16>(backward ? G * N * w.ldn : 0);
-  w.dZT = c.take<__nv_bfloat16>(backward ? G * N * w.ldn : 0);
   w.total = c.total();
   return w;
 }
@@ -792,16 +730,19 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
   const double ne = (double)N * (double)eps;
   const float masked_const = variant == GD3_VARIANT_MAST3R ? (float)(ne * log(ne)) : 0.f;
 
-  CUtensorMap tm_a, tm_b, tm_dz, tm_dzt, tm_at, tm_bt;
-  int tmap_bn = 256;   // box rows of tm_at / tm_bt (half a tile in the 2-CTA kernels)
+  // K-major maps for z = a b^T; for the gradient GEMMs the SAME buffers are read MN-major (tc_gemm.cuh):
+  //   df1 = dz b      A = dz  (K-major: rows i, contiguous j)   B = b  as [k = j][mn = c]
+  //   df2 = dz^T a    A = dz  as [k = i][mn = j]               B = a  as [k = i][mn = c]
+  // so neither a^T / b^T nor dz^T is ever written.
+  CUtensorMap tm_a, tm_b, tm_dz, tm_dz_mn, tm_a_mn, tm_b_mn;
   int rc;
   if ((rc = tc::make_tmap_bf16(&tm_a, w.a, C, N, G, w.ldc, N * (int64_t)w.ldc, tc::BM))) return rc;
   if ((rc = tc::make_tmap_bf16(&tm_b, w.b, C, N, G, w.ldc, N * (int64_t)w.ldc, 256))) return rc;
   if (backward) {
     if ((rc = tc::make_tmap_bf16(&tm_dz, w.dZ, N, N, G, w.ldn, N * (int64_t)w.ldn, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&tm_dzt, w.dZT, N, N, G, w.ldn, N * (int64_t)w.ldn, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&tm_at, w.aT, N, C, G, w.ldn, C * (int64_t)w.ldn, 256))) return rc;
-    if ((rc = tc::make_tmap_bf16(&tm_bt, w.bT, N, C, G, w.ldn, C * (int64_t)w.ldn, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tm_dz_mn, w.dZ, N, N, G, w.ldn, N * (int64_t)w.ldn, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tm_a_mn, w.a, C, N, G, w.ldc, N * (int64_t)w.ldc, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&tm_b_mn, w.b, C, N, G, w.ldc, N * (int64_t)w.ldc, 64))) return rc;
   }
 
   for (int64_t p0 = 0; p0 < P; p0 += G) {
@@ -813,19 +754,20 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       const bool fast = s1C == 1 && s2C == 1 && C % 8 == 0 && (s1N * esz) % 16 == 0 && (s2N * esz) % 16 == 0 &&
                         (s1P * esz) % 16 == 0 && (s2P * esz) % 16 == 0 &&
                         reinterpret_cast<uintptr_t>(f1) % 16 == 0 && reinterpret_cast<uintptr_t>(f2) % 16 == 0;
-      __nv_bfloat16* pa = backward ? w.aT : nullptr;
-      __nv_bfloat16* pb = backward ? w.bT : nullptr;
       if (fast) {
-        dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)g, 2);
+        dim3 grid((unsigned)ceil_div<int64_t>(N, 8), (unsigned)g, 2);
         GD3_PROF("kl_prep_fast", stream);
-        if (dtype == GD3_DTYPE_F32)
-          kl_prep_fast<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(f1), static_cast<const float*>(f2),
-                                                        s1P, s1N, s2P, s2N, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a,
-                                                        w.b, pa, pb, w.inv1, w.inv2);
-        else
-          kl_prep_fast<__nv_bfloat16><<<grid, 256, 0, stream>>>(
-              static_cast<const __nv_bfloat16*>(f1), static_cast<const __nv_bfloat16*>(f2), s1P, s1N, s2P, s2N,
-              (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, pa, pb, w.inv1, w.inv2);
+#define GD3_KL_PREP(T, NIT)                                                                                         \
+  kl_prep_fast<T, NIT><<<grid, 256, 0, stream>>>(static_cast<const T*>(f1), static_cast<const T*>(f2), s1P, s1N, s2P, \
+                                                 s2N, (int)p0, (int)N, (int)C, w.ldc, w.a, w.b, w.inv1, w.inv2)
+        if (dtype == GD3_DTYPE_F32) {
+          if (C <= 512) GD3_KL_PREP(float, 2);
+          else GD3_KL_PREP(float, 4);
+        } else {
+          if (C <= 512) GD3_KL_PREP(__nv_bfloat16, 2);
+          else GD3_KL_PREP(__nv_bfloat16, 4);
+        }
+#undef GD3_KL_PREP
       } else {
         // generic strides (e.g. the MASt3R path's channel-major view)
         dim3 grid((unsigned)ceil_div<int64_t>(N, 32), (unsigned)g, 2);
@@ -833,11 +775,11 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         if (dtype == GD3_DTYPE_F32)
           kl_prep_features<float><<<grid, 256, 0, stream>>>(
               static_cast<const float*>(f1), static_cast<const float*>(f2), s1P, s1N, s1C, s2P, s2N, s2C, (int)p0,
-              (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, pa, pb, w.inv1, w.inv2);
+              (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, w.inv1, w.inv2);
         else
           kl_prep_features<__nv_bfloat16><<<grid, 256, 0, stream>>>(
               static_cast<const __nv_bfloat16*>(f1), static_cast<const __nv_bfloat16*>(f2), s1P, s1N, s1C, s2P, s2N,
-              s2C, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, pa, pb, w.inv1, w.inv2);
+              s2C, (int)p0, (int)N, (int)C, w.ldc, w.ldn, w.a, w.b, w.inv1, w.inv2);
       }
       GD3_CHECK_LAUNCH();
     }
@@ -909,8 +851,8 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         // workspace rows are padded to a multiple of 8 elements, so the 128-bit kernel also serves ragged N (elements in
         // the padding are masked on read and never consumed: the TMA extents of the gradient GEMMs stop at N)
         GD3_PROF("kl_dz_fast", stream);
-        kl_dz_fast<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.dZT, w.ldn,
-                                             w.rowdot, w.coldot, w.loss_acc);
+        kl_dz_fast<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.ldn, w.rowdot,
+                                             w.coldot, w.loss_acc);
       }
       GD3_CHECK_LAUNCH();
       {
@@ -919,30 +861,17 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       }
       GD3_CHECK_LAUNCH();
       tc::GemmShape s{(int)N, (int)C, (int)N, g};
-      // 128 x bn single-CTA tiles by default; GD3_KL_GRAD_2SM=1 selects the 2-CTA kernel (256 x bn per CTA pair, each
-      // CTA staging half of the B tile) for A/B measurements - at these shapes it is within 5% of the 1-CTA kernel
-      static const bool one_sm = [] { const char* e = getenv("GD3_KL_GRAD_2SM"); return !(e && e[0] == '1'); }();
-      const int bn = tc::pick_tile_n(s, one_sm ? 1 : 2);
-      const int box = one_sm ? bn : bn / 2;
-      if (box != tmap_bn) {
-        if ((rc = tc::make_tmap_bf16(&tm_at, w.aT, N, C, G, w.ldn, C * (int64_t)w.ldn, box))) return rc;
-        if ((rc = tc::make_tmap_bf16(&tm_bt, w.bT, N, C, G, w.ldn, C * (int64_t)w.ldn, box))) return rc;
-        tmap_bn = box;
-      }
+      const int bn = tc::pick_tile_n(s);
       auto run_grad = [&](auto tag) -> int {
         using E = EpiGradOut<decltype(tag)>;
         using OutT = decltype(tag);
         typename E::Params e1{(int)N, (int)C, w.a, w.ldc, w.rowdot, w.inv1, static_cast<OutT*>(grad_f1) + p0 * N * C};
         typename E::Params e2{(int)N, (int)C, w.b, w.ldc, w.coldot, w.inv2, static_cast<OutT*>(grad_f2) + p0 * N * C};
         int r;
-#define GD3_KL_GRAD(BN)                                                                                   \
-  do {                                                                                                    \
-    if (one_sm) {                                                                                         \
-      if ((r = tc::launch_gemm<BN, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;         \
-      return tc::launch_gemm<BN, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);                     \
-    }                                                                                                     \
-    if ((r = tc::launch_gemm_2sm<BN, 8, E>("kl_grad_gemm", tm_dz, tm_bt, s, e1, stream))) return r;       \
-    return tc::launch_gemm_2sm<BN, 8, E>("kl_grad_gemm", tm_dzt, tm_at, s, e2, stream);                   \
+#define GD3_KL_GRAD(BN)                                                                                             \
+  do {                                                                                                              \
+    if ((r = tc::launch_gemm<BN, 8, E, false, true>("kl_grad_gemm", tm_dz, tm_b_mn, s, e1, stream))) return r;      \
+    return tc::launch_gemm<BN, 8, E, true, true>("kl_grad_gemm", tm_dz_mn, tm_a_mn, s, e2, stream);                 \
   } while (0)
         if (bn == 256) GD3_KL_GRAD(256);
         if (bn == 192) GD3_KL_GRAD(192);

@@ -177,4 +177,35 @@ int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64
   return tc::launch_gemm<128, 8, tc::EpiStoreF32>("debug_gemm", ta, tb, s, ep, stream);
 }
 
+// Same GEMM with MN-major operands: a_mn -> A is given as (batch, K, M) (M contiguous), b_mn -> B as (batch, K, N).
+int gd3_debug_gemm_bf16_mn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
+                           int a_mn, int b_mn, int tile_n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GD3_REQUIRE(A && B && C, "gd3_debug_gemm_bf16_mn: null pointer");
+  GD3_REQUIRE(tile_n == 128 || tile_n == 192 || tile_n == 256, "gd3_debug_gemm_bf16_mn: tile_n must be 128, 192 or 256");
+  GD3_REQUIRE((!a_mn || M % 8 == 0) && (!b_mn || N % 8 == 0) && ((a_mn && b_mn) || K % 8 == 0),
+              "gd3_debug_gemm_bf16_mn: contiguous dimensions must be multiples of 8 (16-byte TMA strides)");
+  CUtensorMap ta, tb;
+  int rc;
+  tc::EpiStoreF32::Params ep{C, (int)M, (int)N, N, M * N, 1.0f, nullptr};
+  tc::GemmShape s{(int)M, (int)N, (int)K, (int)batch};
+  if (a_mn) rc = tc::make_tmap_bf16(&ta, A, M, K, batch, M, K * M, 64);
+  else rc = tc::make_tmap_bf16(&ta, A, K, M, batch, K, M * K, tc::BM);
+  if (rc) return rc;
+  if (b_mn) rc = tc::make_tmap_bf16(&tb, B, N, K, batch, N, K * N, 64);
+  else rc = tc::make_tmap_bf16(&tb, B, K, N, batch, K, N * K, tile_n);
+  if (rc) return rc;
+#define GD3_DBG_MN(BN)                                                                                                  \
+  do {                                                                                                                  \
+    if (a_mn && b_mn) return tc::launch_gemm<BN, 8, tc::EpiStoreF32, true, true>("debug_gemm_mn", ta, tb, s, ep, stream); \
+    if (a_mn) return tc::launch_gemm<BN, 8, tc::EpiStoreF32, true, false>("debug_gemm_mn", ta, tb, s, ep, stream);       \
+    if (b_mn) return tc::launch_gemm<BN, 8, tc::EpiStoreF32, false, true>("debug_gemm_mn", ta, tb, s, ep, stream);       \
+    return tc::launch_gemm<BN, 8, tc::EpiStoreF32>("debug_gemm_mn", ta, tb, s, ep, stream);                              \
+  } while (0)
+  if (tile_n == 256) GD3_DBG_MN(256);
+  if (tile_n == 192) GD3_DBG_MN(192);
+  GD3_DBG_MN(128);
+#undef GD3_DBG_MN
+}
+
 }  // extern "C"

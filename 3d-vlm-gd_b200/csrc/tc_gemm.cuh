@@ -147,10 +147,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// kind::f16 instruction descriptor: fp32 D, bf16 A/B, both K-major, dense
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
+// MN-major, 128B-swizzled operand: the tile sits in shared memory as [k rows][64 MN elements] blocks (128-byte rows,
+// exactly how TMA delivers a box of a matrix whose MN dimension is the contiguous one), one 8 KB block per 64 MN
+// elements.  Canonical layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units: LBO = distance between 64-element MN
+// blocks (64 k rows x 128 B = 8192), SBO = distance between groups of 8 k rows (1024).  One MMA consumes 16 k rows:
+// the start address advances by 2048 bytes per UMMA_K step.
+__device__ __forceinline__ uint64_t make_smem_desc_mn128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: fp32 D, bf16 A/B, dense; bit 15 / 16 = A / B is MN-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ epilogue context
@@ -166,11 +180,14 @@ struct EpiCtx {
 };
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int EPI_WARPS, class Epi>
+// A_MN / B_MN: the operand's MN dimension is the contiguous one in global memory (its tensor map has inner extent =
+// MN size, rows = K extent, box 64 x 64); no transposed copy of the operand is needed.
+template <int BN, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m,
                    int tiles_n, int batch, int k_blocks, typename Epi::Params ep) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(!B_MN || BN % 64 == 0, "MN-major B needs BN to be a multiple of 64");
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS");
   constexpr int STAGES = num_stages(BN, Epi::kScratchBytes);
   constexpr int A_BYTES = BM * BK * 2;
@@ -228,8 +245,18 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
           uint8_t* sa = ring + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, m0, b);
-          tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, n0, b);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, kb * BK, b);
+          } else {
+            tma_load_3d(sa, &tmA, &full_bar[stage], kb * BK, m0, b);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * 8192, &tmB, &full_bar[stage], n0 + c * 64, kb * BK, b);
+          } else {
+            tma_load_3d(sb, &tmB, &full_bar[stage], kb * BK, n0, b);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -237,7 +264,10 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      // per UMMA_K step: K-major operands advance 32 bytes inside the 128-byte swizzle atom, MN-major operands advance
+      // 16 k rows = 2048 bytes (descriptor addresses are in 16-byte units)
+      constexpr uint64_t STEP_A = A_MN ? (2048 >> 4) : 2, STEP_B = B_MN ? (2048 >> 4) : 2;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -250,13 +280,11 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * STAGE_BYTES);
-          const uint64_t da = make_smem_desc_k128(sa);
-          const uint64_t db = make_smem_desc_k128(sa + A_BYTES);
+          const uint64_t da = A_MN ? make_smem_desc_mn128(sa) : make_smem_desc_k128(sa);
+          const uint64_t db = B_MN ? make_smem_desc_mn128(sa + A_BYTES) : make_smem_desc_k128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, da + STEP_A * k, db + STEP_B * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -547,12 +575,14 @@ inline int pick_tile_n(const GemmShape& s, int ctas_per_tile = 1) {
   return best;
 }
 
-template <int BN, int EPI_WARPS, class Epi>
+// For an MN-major operand build its tensor map with make_tmap_bf16(&tm, base, MN extent, K extent, batch, row stride,
+// batch stride, 64): the inner (contiguous) dimension is MN, the rows run along K.
+template <int BN, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
 int launch_gemm(const char* name, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
                 const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
   if (s.M <= 0 || s.N <= 0 || s.batch <= 0) return GD3_OK;
   GD3_REQUIRE(s.K > 0, "tc_gemm: K must be positive");
-  auto kern = tc_gemm_kernel<BN, EPI_WARPS, Epi>;
+  auto kern = tc_gemm_kernel<BN, EPI_WARPS, Epi, A_MN, B_MN>;
   constexpr int SMEM = smem_bytes(BN, Epi::kScratchBytes);
   static_assert(SMEM <= 227 * 1024, "tc_gemm shared memory budget");
   static bool configured = false;   // per instantiation

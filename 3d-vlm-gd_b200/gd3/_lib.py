@@ -46,6 +46,7 @@ SYMBOLS = {
                                      _i64, _i64, _i64, _i64, _int, _int, _int, _vp, _i64, _i64, _i64, _i64, _vp, _i64,
                                      _i64, _i64, _vp]),
     'gd3_debug_gemm_bf16': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _vp]),
+    'gd3_debug_gemm_bf16_mn': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp]),
 }
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
@@ -226,6 +227,21 @@ def debug_gemm_bf16(A, B, tile_n=256):
     C = torch.empty(b, M, N, dtype=torch.float32, device=A.device)
     with torch.cuda.device(A.device):
         check(lib.gd3_debug_gemm_bf16(ptr(A), ptr(B), ptr(C), M, N, K, b, K, K, N, tile_n, stream_ptr()))
+    return C
+
+
+def debug_gemm_bf16_mn(A, B, a_mn=False, b_mn=False, tile_n=256):
+    """C[b] = op(A[b]) @ op(B[b]).T with MN-major operands: a_mn -> A is (b, K, M), b_mn -> B is (b, K, N)."""
+    require_cuda(A, B)
+    lib = load()
+    A = A.contiguous()
+    B = B.contiguous()
+    b = A.shape[0]
+    K, M = (A.shape[1], A.shape[2]) if a_mn else (A.shape[2], A.shape[1])
+    N = B.shape[2] if b_mn else B.shape[1]
+    C = torch.empty(b, M, N, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.gd3_debug_gemm_bf16_mn(ptr(A), ptr(B), ptr(C), M, N, K, b, int(a_mn), int(b_mn), tile_n, stream_ptr()))
     return C
 
 

@@ -243,6 +243,10 @@ int gd3_teacher_volume(const float* const* tgt_layers, const float* const* src_l
  * ------------------------------------------------------------------------------------------ */
 int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
                         int64_t lda, int64_t ldb, int64_t ldc, int tile_n, void* stream);
+/* The same with MN-major operands (no transposed copies): a_mn -> A is (batch, K, M) with M contiguous,
+ * b_mn -> B is (batch, K, N) with N contiguous; C (batch, M, N) fp32 contiguous. */
+int gd3_debug_gemm_bf16_mn(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
+                           int a_mn, int b_mn, int tile_n, void* stream);
 
 #ifdef __cplusplus
 }

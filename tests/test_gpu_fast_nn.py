@@ -33,6 +33,27 @@ def test_tc_gemm_matches_torch(gd3mod, tile_n, shape):
     assert err <= 1e-3 * (K ** 0.5), f'max abs err {err}'
 
 
+@pytest.mark.parametrize('a_mn,b_mn', [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize('tile_n', [128, 192, 256])
+@pytest.mark.parametrize('shape', [(1, 128, 256, 64), (2, 256, 512, 768), (3, 200, 336, 136), (1, 1376, 1024, 1369)])
+def test_tc_gemm_mn_major_operands(gd3mod, a_mn, b_mn, tile_n, shape):
+    """MN-major UMMA descriptors (operands used without a transposed copy) against a plain fp32 matmul."""
+    from gd3 import _lib
+    b, M, N, K = shape
+    g = torch.Generator().manual_seed(M + 3 * N + 5 * K)
+    A = torch.randn(b, M, K, generator=g).to(torch.bfloat16)
+    B = torch.randn(b, N, K, generator=g).to(torch.bfloat16)
+    Ain = A.transpose(1, 2).contiguous() if a_mn else A
+    Bin = B.transpose(1, 2).contiguous() if b_mn else B
+    if (not (a_mn and b_mn)) and K % 8:
+        pytest.skip('K-major operand needs K % 8 == 0')
+    C = _lib.debug_gemm_bf16_mn(Ain.cuda(), Bin.cuda(), a_mn=a_mn, b_mn=b_mn, tile_n=tile_n)
+    torch.cuda.synchronize()
+    ref = torch.matmul(A.float(), B.float().transpose(1, 2))
+    err = (C.cpu() - ref).abs().max().item()
+    assert err <= 1e-3 * (K ** 0.5), f'max abs err {err}'
+
+
 def test_tc_gemm_exact_integers(gd3mod):
     """Small-integer operands: every partial sum is exact, so the result must be bit-identical."""
     from gd3 import _lib
