@@ -15,11 +15,11 @@
 // tau = 0.01 amplifies similarity error 100x, so the K x K similarity is computed on the tensor
 // cores with a 2-term bf16 split of both operands (hi*hi + hi*lo + lo*hi, three K-concatenated
 // panels in ONE tcgen05 GEMM, ~16 mantissa bits); the gradient GEMMs use plain bf16.
-//   1 split3 (split_bf16.cuh)  split / transpose descriptors
+//   1 split3 (split_bf16.cuh)  split descriptors into bf16 hi / lo panels
 //   2 tc_gemm<Store>         sim (fp32, K x K per pair: <= 1 MB, L2 resident)
 //   3 ap_rows          SIMT  one block per row: S1, S2, loss, d loss / d sim (bf16, unnormalised)
-//   4 transpose_bf16   SIMT  dsim^T
-//   5 tc_gemm<Store> x2      d d1 = dsim d2 / Q,  d d2 = dsim^T d1 / Q   (Q = number of positives)
+//   4 tc_gemm<Store> x2      d d1 = dsim d2 / Q,  d d2 = dsim^T d1 / Q   (Q = number of positives); dsim and the
+//                            descriptors are read in place through MN-major operand descriptors (no transposes)
 #include "../../include/gd3.h"
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -205,21 +205,6 @@ __global__ void ap_finalize(const double* __restrict__ acc, const int* __restric
   }
 }
 
-// 4. batched bf16 transpose of K x K matrices with leading dimension ld.  grid (ceil(K/32), ceil(K/32), P)
-__global__ void __launch_bounds__(256)
-    transpose_bf16(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int K, int ld) {
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int p = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const __nv_bfloat16* src = in + (int64_t)p * K * ld;
-  __nv_bfloat16* dst = out + (int64_t)p * K * ld;
-  for (int r = w; r < 32; r += 8)
-    tile[r][lane] = (r0 + r < K && c0 + lane < K) ? src[(int64_t)(r0 + r) * ld + c0 + lane] : __float2bfloat16(0.f);
-  __syncthreads();
-  for (int r = w; r < 32; r += 8)
-    if (c0 + r < K && r0 + lane < K) dst[(int64_t)(c0 + r) * ld + r0 + lane] = tile[lane][r];
-}
-
 // ------------------------------------------------------------------------------------------
 // InfoNCE (upstream MASt3R softmax-CE correspondence loss, mast3r/losses.py:237-272): kernels on the K x K
 // similarity produced by the same split-bf16 GEMM.  E = exp(sim / T) (NaN -> 0), positives on the diagonal.
@@ -330,7 +315,7 @@ __global__ void __launch_bounds__(128)
 }
 
 struct APWorkspace {
-  __nv_bfloat16 *A3, *B3, *d1T, *d2T, *dS, *dST;
+  __nv_bfloat16 *A3, *B3, *dS;
   float *sim, *scale;
   float *rowsum, *colsum;     // InfoNCE: (P, K) each
   double* loss_acc;
@@ -348,10 +333,7 @@ APWorkspace carve_ap(void* base, int64_t P, int64_t K, int64_t C, bool backward)
   w.lds = (int)round_up<int64_t>(K, 4);
   w.A3 = c.take<__nv_bfloat16>(P * K * 3 * w.ldc);
   w.B3 = c.take<__nv_bfloat16>(P * K * 3 * w.ldc);
-  w.d1T = c.take<__nv_bfloat16>(backward ? P * C * w.ldk : 0);
-  w.d2T = c.take<__nv_bfloat16>(backward ? P * C * w.ldk : 0);
   w.dS = c.take<__nv_bfloat16>(backward ? P * K * w.ldk : 0);
-  w.dST = c.take<__nv_bfloat16>(backward ? P * K * w.ldk : 0);
   w.sim = c.take<float>(P * K * w.lds);
   w.scale = c.take<float>(P);
   w.rowsum = c.take<float>(P * K);
@@ -404,12 +386,11 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
   GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int) * P, stream));
   int rc;
   {
-    // [hi | hi | lo] x [hi | lo | hi] panels for the similarity GEMM, hi^T per pair for the gradient GEMMs
-    XtLayout xt{backward ? 1 : 0, (int)K, 1, w.ldk, w.ldk, w.ldk, C * (int64_t)w.ldk};
-    if ((rc = launch_split3("ap_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, backward ? w.d1T : nullptr, xt, stream)))
-      return rc;
-    if ((rc = launch_split3("ap_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, backward ? w.d2T : nullptr, xt, stream)))
-      return rc;
+    // [hi | hi | lo] x [hi | lo | hi] panels for the similarity GEMM; the gradient GEMMs read the hi panels (panel 0 of
+    // either buffer) MN-major, so no transposed copy is made
+    XtLayout none{0, 1, 1, 8, 8, 8, 0};
+    if ((rc = launch_split3("ap_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, nullptr, none, stream))) return rc;
+    if ((rc = launch_split3("ap_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, nullptr, none, stream))) return rc;
   }
   {
     CUtensorMap ta, tb;
@@ -448,22 +429,18 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     GD3_CHECK_LAUNCH();
   }
   if (backward) {
-    dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)ceil_div<int64_t>(K, 32), (unsigned)P);
-    {
-      GD3_PROF("transpose_bf16", stream);
-      transpose_bf16<<<grid, 256, 0, stream>>>(w.dS, w.dST, (int)K, w.ldk);
-    }
-    GD3_CHECK_LAUNCH();
-    CUtensorMap t_ds, t_dst, t_d1t, t_d2t;
+    // d D1 = dS D2 and d D2 = dS^T D1: dS is read K-major for the first and MN-major for the second product, the
+    // descriptors D1 / D2 (hi panels) MN-major in both -- no transposed copies
+    CUtensorMap t_ds, t_ds_mn, t_d1_mn, t_d2_mn;
     if ((rc = tc::make_tmap_bf16(&t_ds, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_dst, w.dST, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_d1t, w.d1T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_d2t, w.d2T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_ds_mn, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d1_mn, w.A3, C, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d2_mn, w.B3, C, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 64))) return rc;
     tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
     tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, w.scale};
     tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, w.scale};
-    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("ap_grad_gemm", t_ds, t_d2t, s, e1, stream))) return rc;
-    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("ap_grad_gemm", t_dst, t_d1t, s, e2, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, false, true>("ap_grad_gemm", t_ds, t_d2_mn, s, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, true, true>("ap_grad_gemm", t_ds_mn, t_d1_mn, s, e2, stream))) return rc;
   }
   return GD3_OK;
 }
@@ -494,11 +471,9 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
   GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int), stream));
   int rc;
   {
-    XtLayout xt{backward ? 1 : 0, (int)K, 1, w.ldk, w.ldk, w.ldk, C * (int64_t)w.ldk};
-    if ((rc = launch_split3("nce_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, backward ? w.d1T : nullptr, xt, stream)))
-      return rc;
-    if ((rc = launch_split3("nce_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, backward ? w.d2T : nullptr, xt, stream)))
-      return rc;
+    XtLayout none{0, 1, 1, 8, 8, 8, 0};
+    if ((rc = launch_split3("nce_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, nullptr, none, stream))) return rc;
+    if ((rc = launch_split3("nce_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, nullptr, none, stream))) return rc;
     CUtensorMap ta, tb;
     if ((rc = tc::make_tmap_bf16(&ta, w.A3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc,
                                  tc::BM)))
@@ -537,17 +512,13 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
     GD3_CHECK_LAUNCH();
   }
   if (backward) {
-    dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)ceil_div<int64_t>(K, 32), (unsigned)P);
-    {
-      GD3_PROF("transpose_bf16", stream);
-      transpose_bf16<<<grid, 256, 0, stream>>>(w.dS, w.dST, (int)K, w.ldk);
-    }
-    GD3_CHECK_LAUNCH();
-    CUtensorMap t_ds, t_dst, t_d1t, t_d2t;
+    // d D1 = dS D2 and d D2 = dS^T D1: dS is read K-major for the first and MN-major for the second product, the
+    // descriptors D1 / D2 (hi panels) MN-major in both -- no transposed copies
+    CUtensorMap t_ds, t_ds_mn, t_d1_mn, t_d2_mn;
     if ((rc = tc::make_tmap_bf16(&t_ds, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_dst, w.dST, K, K, P, w.ldk, K * (int64_t)w.ldk, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_d1t, w.d1T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_d2t, w.d2T, K, C, P, w.ldk, C * (int64_t)w.ldk, 256))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_ds_mn, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d1_mn, w.A3, C, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_d2_mn, w.B3, C, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 64))) return rc;
     tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
     // every batch entry is scaled by the same 1 / n_valid (scale[0]); stride-0 read via a per-batch pointer of 1 entry
     tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, nullptr};
@@ -556,8 +527,8 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
     e2.batch_scale = w.scale;
     e1.batch_scale_stride0 = 1;
     e2.batch_scale_stride0 = 1;
-    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("nce_grad_gemm", t_ds, t_d2t, s, e1, stream))) return rc;
-    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("nce_grad_gemm", t_dst, t_d1t, s, e2, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, false, true>("nce_grad_gemm", t_ds, t_d2_mn, s, e1, stream))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, true, true>("nce_grad_gemm", t_ds_mn, t_d1_mn, s, e2, stream))) return rc;
   }
   return GD3_OK;
 }
