@@ -47,18 +47,6 @@ __device__ __forceinline__ float half_sum(float v, unsigned mask) {
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
   return v;
 }
-// Transposed operands of the d W1 GEMM.  The contraction runs over keypoints of `gs` consecutive sets and over
-// three precision panels, all contiguous in a row:  column(set, k, panel) = ((set / gs) * 3 + panel) * gl +
-// (set % gs) * ldk + k, gl = gs * ldk.  One GEMM batch entry per group of sets (split-K), so the fp32 atomics
-// of the epilogue are issued once per group instead of once per set.
-struct TLayout {
-  int gs, ldk;
-  int64_t gl, ld;     // group panel length, full row length = groups * 3 * gl
-  __host__ __device__ int64_t col(int set, int k, int panel) const {
-    return ((int64_t)(set / gs) * 3 + panel) * gl + (int64_t)(set % gs) * ldk + k;
-  }
-};
-
 // hidden index of this lane's i-th element: two float4 groups, 64 apart -> conflict-free LDS.128
 __device__ __forceinline__ int hidx(int l16, int i) { return (i < 4) ? 4 * l16 + i : 64 + 4 * l16 + (i - 4); }
 
@@ -615,14 +603,13 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// du = sum_ta dub_part - sum_tb dua_part (+ L1 part); emits bf16 du, du^T and the b1 gradient
+// du = sum_ta dub_part - sum_tb dua_part (+ L1 part); emits the bf16 hi / lo panels of du and the b1 gradient
 // grid (ceil(K/32), S), block 256 (8 warps x 32 lanes: lane -> 4 h, warp -> rows)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     rank_reduce_du(const float* __restrict__ dub_part, const float* __restrict__ dua_part,
-                   const float* __restrict__ du_extra, int S, int K, int TA, int TB, TLayout tl,
-                   __nv_bfloat16* __restrict__ du_bf, __nv_bfloat16* __restrict__ duT3, float* __restrict__ gb1) {
-  __shared__ float tile[32][H + 1];
+                   const float* __restrict__ du_extra, int S, int K, int TA, int TB,
+                   __nv_bfloat16* __restrict__ du2 /* (S K, 2 H): [hi | lo] */, float* __restrict__ gb1) {
   __shared__ float colsum[8][H];
   const int set = blockIdx.y, k0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -645,27 +632,20 @@ __global__ void __launch_bounds__(256)
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         if ((set & 1) == 0) { bsum[0] += v.x; bsum[1] += v.y; bsum[2] += v.z; bsum[3] += v.w; }   // b side of the L1 pair
       }
-      uint2 pk = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
-      *reinterpret_cast<uint2*>(du_bf + ((int64_t)set * K + k) * H + 4 * lane) = pk;
+      // bf16 hi / lo split of du, row-major: the d feats GEMM reads the hi panel K-major, the d W1 GEMM reads both
+      // panels MN-major (tc_gemm.cuh), so no transposed copy is written
+      const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      uint16_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_detail::hi_lo(v[i], hi[i], lo[i]);
+      __nv_bfloat16* row = du2 + ((int64_t)set * K + k) * 2 * H + 4 * lane;
+      *reinterpret_cast<uint2*>(row) = make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
+      *reinterpret_cast<uint2*>(row + H) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
     }
-    tile[r][4 * lane] = acc.x; tile[r][4 * lane + 1] = acc.y; tile[r][4 * lane + 2] = acc.z; tile[r][4 * lane + 3] = acc.w;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) colsum[w][4 * lane + i] = bsum[i];
   __syncthreads();
-  // du^T panels [hi | hi | lo] (A side of the split product), lanes along k; pad columns k in [K, ldk) are zeroed
-  for (int h = w; h < H; h += 8) {
-    const int k = k0 + lane;
-    if (k < tl.ldk) {
-      const float v = (k < K) ? tile[lane][h] : 0.f;
-      const __nv_bfloat16 hi = __float2bfloat16(v);
-      const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-      __nv_bfloat16* row = duT3 + (int64_t)h * tl.ld;
-      row[tl.col(set, k, 0)] = hi;
-      row[tl.col(set, k, 1)] = hi;
-      row[tl.col(set, k, 2)] = lo;
-    }
-  }
   if (threadIdx.x < H) {
     float t = 0.f;
 #pragma unroll
@@ -712,15 +692,14 @@ __global__ void rank_finalize(const double* __restrict__ loss_sum, const float* 
 }
 
 struct RankWorkspace {
-  __nv_bfloat16 *F3, *W3, *FT3, *W1T, *du_bf, *duT3;
+  __nv_bfloat16 *F3, *W3, *du2;
   __nv_bfloat16 *Wb3, *Va3;
   float *u, *inv_count, *dub_part, *dua_part, *du_extra, *nb, *na, *rstd;
   double *loss_sum, *l1_sum;
   int* count;
   size_t total;
   int ldd, TA, TB, groups;
-  TLayout tl;
-  bool t_pads;   // transposed buffers contain columns no writer touches (must be zeroed)
+  int gs;        // sets per split-K group of the d W1 contraction
 };
 
 RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backward, bool l1) {
@@ -728,13 +707,11 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   Carver c(base);
   const int64_t R = S * K;
   w.ldd = (int)round_up<int64_t>(D, 8);
-  w.tl.ldk = (int)round_up<int64_t>(K, 8);
-  w.groups = (int)(S < 16 ? S : 16);
-  w.tl.gs = (int)ceil_div<int64_t>(S, w.groups);
-  w.groups = (int)ceil_div<int64_t>(S, w.tl.gs);
-  w.tl.gl = (int64_t)w.tl.gs * w.tl.ldk;
-  w.tl.ld = (int64_t)w.groups * 3 * w.tl.gl;
-  w.t_pads = (S % w.tl.gs != 0) || (K != w.tl.ldk);
+  // d W1 sums over all S K keypoints: split-K into at most 48 groups of sets (one GEMM batch entry each), so that
+  // (groups x D / BN) tiles fill the SMs while the fp32 atomics of the epilogue are issued once per group
+  w.groups = (int)(S < 48 ? S : 48);
+  w.gs = (int)ceil_div<int64_t>(S, w.groups);
+  w.groups = (int)ceil_div<int64_t>(S, w.gs);
   w.TA = (int)ceil_div<int64_t>(K, TILE_A);
   w.TB = (int)ceil_div<int64_t>(K, TILE_B);
   w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
@@ -750,25 +727,13 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.loss_sum = c.take<double>(S);
   w.l1_sum = c.take<double>(S);
   if (backward) {
-    w.FT3 = c.take<__nv_bfloat16>(D * w.tl.ld);
-    w.W1T = c.take<__nv_bfloat16>(D * (int64_t)H);
-    w.du_bf = c.take<__nv_bfloat16>(R * H);
-    w.duT3 = c.take<__nv_bfloat16>((int64_t)H * w.tl.ld);
+    w.du2 = c.take<__nv_bfloat16>(R * 2 * H);
     w.dub_part = c.take<float>(S * w.TA * K * H);
     w.dua_part = c.take<float>(S * w.TB * K * H);
     if (l1) w.du_extra = c.take<float>(R * H);
   }
   w.total = c.total();
   return w;
-}
-
-// W1 (H x D) -> W1^T (D x H) bf16
-__global__ void transpose_w1(const float* __restrict__ W1, int D, __nv_bfloat16* __restrict__ W1T) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < D * H) {
-    const int d = e / H, h = e - d * H;
-    W1T[e] = __float2bfloat16(W1[(int64_t)h * D + d]);
-  }
 }
 
 }  // namespace
@@ -821,18 +786,11 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   }
   const int64_t R = S * K;
   int rc;
-  if (backward && w.t_pads) {
-    // ragged K or a partial last group: columns no writer touches must read as zero in the d W1 contraction
-    GD3_CHECK_CUDA(cudaMemsetAsync(w.FT3, 0, sizeof(__nv_bfloat16) * D * w.tl.ld, stream));
-    GD3_CHECK_CUDA(cudaMemsetAsync(w.duT3, 0, sizeof(__nv_bfloat16) * H * w.tl.ld, stream));
-  }
   // ---- u = f W1^T on the tensor cores (split bf16, 3 K-concatenated panels) ----
   {
-    // operands of u = f W1^T (and, for the backward, the transposed panels of f for d W1 = du^T f)
-    XtLayout xf{backward ? 3 : 0, (int)K, w.tl.gs, w.tl.ldk, w.tl.gl, w.tl.ld, 0};
-    if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, backward ? w.FT3 : nullptr, xf, stream)))
-      return rc;
+    // operands of u = f W1^T; the backward GEMMs read the same panels MN-major (no transposed copies)
     XtLayout none{0, 1, 1, 8, 8, 8, 0};
+    if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, nullptr, none, stream))) return rc;
     if ((rc = launch_split3("split3_w1", W1, H, (int)D, w.ldd, 1, w.W3, nullptr, none, stream))) return rc;
   }
   {
@@ -955,28 +913,35 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     {
       GD3_PROF("rank_reduce_du", stream);
       rank_reduce_du<<<grid, 256, 0, stream>>>(w.dub_part, w.dua_part, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.TA,
-                                             w.TB, w.tl, w.du_bf, w.duT3, grad_params + (int64_t)H * D);
-    }
-    GD3_CHECK_LAUNCH();
-    {
-      GD3_PROF("transpose_w1", stream);
-      transpose_w1<<<(unsigned)ceil_div<int64_t>(D * H, 256), 256, 0, stream>>>(W1, (int)D, w.W1T);
+                                             w.TB, w.du2, grad_params + (int64_t)H * D);
     }
     GD3_CHECK_LAUNCH();
   }
   {
-    CUtensorMap t_du, t_w1t, t_dut, t_ft;
-    if ((rc = tc::make_tmap_bf16(&t_du, w.du_bf, H, R, 1, H, 0, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_w1t, w.W1T, H, D, 1, H, 0, 256))) return rc;
+    // d feats = du W1: A = du hi panel (K-major, row stride 2 H), B = W1 hi panel of W3 read MN-major ([k = h][mn = d])
+    CUtensorMap t_du, t_w1;
+    if ((rc = tc::make_tmap_bf16(&t_du, w.du2, H, R, 1, 2 * H, 0, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_w1, w.W3, D, H, 1, 3 * (int64_t)w.ldd, 0, 64))) return rc;
     tc::EpiStoreF32::Params e1{grad_feats, (int)R, (int)D, D, 0, 1.0f, nullptr};
     tc::GemmShape s1{(int)R, (int)D, H, 1};
-    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32>("rank_df_gemm", t_du, t_w1t, s1, e1, stream))) return rc;
-    // d W1 (H x D) = sum over sets of du_s^T f_s: one batch entry per set, accumulated atomically (split-K)
-    if ((rc = tc::make_tmap_bf16(&t_dut, w.duT3, 3 * w.tl.gl, H, w.groups, w.tl.ld, 3 * w.tl.gl, tc::BM))) return rc;
-    if ((rc = tc::make_tmap_bf16(&t_ft, w.FT3, 3 * w.tl.gl, D, w.groups, w.tl.ld, 3 * w.tl.gl, 256))) return rc;
+    if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, false, true>("rank_df_gemm", t_du, t_w1, s1, e1, stream))) return rc;
+    // d W1 (H x D) = sum over sets of du_s^T f_s with the 3-term bf16 split  hi^T hi + lo^T hi + hi^T lo: a grouped
+    // contraction over (term, set of the group, 64-keypoint block), both operands read MN-major from their row-major
+    // panels (du2 = [hi | lo], F3 = [hi | hi | lo]); one GEMM batch entry per group, fp32 atomic accumulation
+    CUtensorMap t_dum, t_fm;
+    if ((rc = tc::make_tmap_bf16(&t_dum, w.du2, 2 * H, K, S, 2 * H, K * 2 * (int64_t)H, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_fm, w.F3, 3 * (int64_t)w.ldd, K, S, 3 * (int64_t)w.ldd, K * 3 * (int64_t)w.ldd, 64)))
+      return rc;
+    tc::GroupedK gk;
+    gk.panels = 3;
+    gk.sets_per_group = w.gs;
+    gk.row_blocks = (int)ceil_div<int64_t>(K, tc::BK);
+    gk.a_off[0] = 0; gk.a_off[1] = H; gk.a_off[2] = 0;
+    gk.b_off[0] = 0; gk.b_off[1] = 0; gk.b_off[2] = 2 * w.ldd;
     EpiAtomicAddF32::Params e2{grad_params, H, (int)D, D};
-    tc::GemmShape s2{H, (int)D, (int)(3 * w.tl.gl), w.groups};
-    if ((rc = tc::launch_gemm<256, 8, EpiAtomicAddF32>("rank_dw1_gemm", t_dut, t_ft, s2, e2, stream))) return rc;
+    tc::GemmShape s2{H, (int)D, gk.panels * gk.sets_per_group * gk.row_blocks * tc::BK, w.groups};
+    if ((rc = tc::launch_gemm<256, 8, EpiAtomicAddF32, true, true, true>("rank_dw1_gemm", t_dum, t_fm, s2, e2, stream, 0, gk)))
+      return rc;
   }
   return GD3_OK;
 }

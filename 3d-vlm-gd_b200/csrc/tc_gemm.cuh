@@ -167,6 +167,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn =
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ grouped contraction (split-K over sets)
+// For C[g] = sum over the sets s of group g and over `panels` precision panels of A_s^T B_s, where A_s / B_s are
+// row-major (rows = contraction index, i.e. both operands MN-major).  The k-blocks of a tile enumerate
+// (panel, set in group, 64-row block of the set); the tensor maps are (inner = all panels side by side, rows of one
+// set, sets), so rows past the end of a set and sets past the last one read as zeros.
+struct GroupedK {
+  int panels = 0;            // 0 = plain contraction
+  int sets_per_group = 1;
+  int row_blocks = 1;        // ceil(rows per set / 64)
+  int a_off[3] = {0, 0, 0};  // inner-coordinate offset of the A panel used by term p
+  int b_off[3] = {0, 0, 0};
+};
+
 // ------------------------------------------------------------------ epilogue context
 struct EpiCtx {
   int b, m0, n0;        // batch index and tile origin
@@ -182,11 +195,12 @@ struct EpiCtx {
 // ------------------------------------------------------------------ the kernel
 // A_MN / B_MN: the operand's MN dimension is the contiguous one in global memory (its tensor map has inner extent =
 // MN size, rows = K extent, box 64 x 64); no transposed copy of the operand is needed.
-template <int BN, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
+template <int BN, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, bool GROUPED = false>
 __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m,
-                   int tiles_n, int batch, int k_blocks, typename Epi::Params ep) {
+                   int tiles_n, int batch, int k_blocks, typename Epi::Params ep, GroupedK gk) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  static_assert(!GROUPED || (A_MN && B_MN), "the grouped contraction reads both operands MN-major");
   static_assert(!B_MN || BN % 64 == 0, "MN-major B needs BN to be a multiple of 64");
   static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "EPI_WARPS");
   constexpr int STAGES = num_stages(BN, Epi::kScratchBytes);
@@ -245,6 +259,19 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
           uint8_t* sa = ring + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (GROUPED) {
+            const int per_panel = gk.sets_per_group * gk.row_blocks;
+            const int pnl = kb / per_panel, rem = kb - pnl * per_panel;
+            const int set = b * gk.sets_per_group + rem / gk.row_blocks, row = (rem % gk.row_blocks) * BK;
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_3d(sa + c * 8192, &tmA, &full_bar[stage], gk.a_off[pnl] + m0 + c * 64, row, set);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_3d(sb + c * 8192, &tmB, &full_bar[stage], gk.b_off[pnl] + n0 + c * 64, row, set);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, &full_bar[stage], m0 + c * 64, kb * BK, b);
@@ -577,12 +604,13 @@ inline int pick_tile_n(const GemmShape& s, int ctas_per_tile = 1) {
 
 // For an MN-major operand build its tensor map with make_tmap_bf16(&tm, base, MN extent, K extent, batch, row stride,
 // batch stride, 64): the inner (contiguous) dimension is MN, the rows run along K.
-template <int BN, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false>
+template <int BN, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, bool GROUPED = false>
 int launch_gemm(const char* name, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
-                const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0) {
+                const typename Epi::Params& ep, cudaStream_t stream, int max_ctas = 0, const GroupedK& gk = GroupedK{}) {
   if (s.M <= 0 || s.N <= 0 || s.batch <= 0) return GD3_OK;
   GD3_REQUIRE(s.K > 0, "tc_gemm: K must be positive");
-  auto kern = tc_gemm_kernel<BN, EPI_WARPS, Epi, A_MN, B_MN>;
+  GD3_REQUIRE(GROUPED == (gk.panels > 0), "tc_gemm: grouped-K description does not match the kernel variant");
+  auto kern = tc_gemm_kernel<BN, EPI_WARPS, Epi, A_MN, B_MN, GROUPED>;
   constexpr int SMEM = smem_bytes(BN, Epi::kScratchBytes);
   static_assert(SMEM <= 227 * 1024, "tc_gemm shared memory budget");
   static bool configured = false;   // per instantiation
@@ -597,8 +625,8 @@ int launch_gemm(const char* name, const CUtensorMap& tmA, const CUtensorMap& tmB
   if (total < grid) grid = static_cast<int>(total);
   {
     GD3_PROF(name, stream);
-    kern<<<grid, (PRODUCER_WARPS + EPI_WARPS) * 32, SMEM, stream>>>(tmA, tmB, tiles_m, tiles_n, s.batch,
-                                                                  ceil_div(s.K, BK), ep);
+    const int k_blocks = GROUPED ? gk.panels * gk.sets_per_group * gk.row_blocks : ceil_div(s.K, BK);
+    kern<<<grid, (PRODUCER_WARPS + EPI_WARPS) * 32, SMEM, stream>>>(tmA, tmB, tiles_m, tiles_n, s.batch, k_blocks, ep, gk);
   }
   GD3_CHECK_LAUNCH();
   return GD3_OK;
