@@ -408,89 +408,105 @@ __global__ void kl_finalize_stats(int G, int N, const float* __restrict__ invR, 
 //   6. dz = s ((r_i + c_j) exp(z) - W), written as dz (row i) and dz^T (row j) in bf16, + row / col dots + sum W z
 // ------------------------------------------------------------------------------------------
 // grid (N/64 i-tiles, N/64 j-tiles, G), block 256: thread = (row tr of a 16-row pass, float4 column tc)
-// VEC: teacher rows are 16-byte aligned (128-bit loads); otherwise four scalar loads per thread (ragged N such as 37^2:
-// still 64 x 64 tiles, 256 contiguous bytes per 16 threads).  W^T rows are padded to a multiple of 4 floats, so its
-// stores are always 128-bit (elements in the padding are never read).
+// W^T tile [j][i] (64 x 64, row stride 65) of pair g into shared memory: t~12 read with lanes along j (its contiguous
+// direction) and transposed on the way in, t~21 read with lanes along i and added.  256 threads; ends with a barrier.
+// VEC: teacher rows are 16-byte aligned (128-bit loads); otherwise four scalar loads per thread (ragged N such as
+// 37^2: still 256 contiguous bytes per 16 threads).
+struct TeacherView {
+  const float *t12, *t21;           // already offset to the pair
+  int64_t row_stride;
+  const float *ir12, *ir21;         // 1 / row sum (0 for masked rows), already offset to the pair
+  const float *e12, *e21;           // eps of kept rows (0 for masked rows)
+};
 template <bool VEC>
-__global__ void __launch_bounds__(256)
-    kl_build_w_fast(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
-                    int64_t t_row_stride, int pair0, int G, int N, const float* __restrict__ invR,
-                    const float* __restrict__ epsm, float* __restrict__ WT, int ldw) {
-  __shared__ float tile[64][65];     // t~12 tile, transposed: [j][i]
-  const int g = blockIdx.z, i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+__device__ __forceinline__ float4 teacher_ld4(const float* src, int col, int N) {
+  if (VEC) return __ldg(reinterpret_cast<const float4*>(src));
+  float4 v;
+  v.x = __ldg(src);
+  v.y = (col + 1 < N) ? __ldg(src + 1) : 0.f;
+  v.z = (col + 2 < N) ? __ldg(src + 2) : 0.f;
+  v.w = (col + 3 < N) ? __ldg(src + 3) : 0.f;
+  return v;
+}
+template <bool VEC>
+__device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& tv, int N, int i0, int j0) {
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
-  const float* T12 = t12 + (int64_t)(pair0 + g) * t_pair_stride;
-  const float* T21 = t21 + (int64_t)(pair0 + g) * t_pair_stride;
-  const float* ir12 = invR + (int64_t)g * N;
-  const float* ir21 = invR + ((int64_t)G + g) * N;
-  const float* e12 = epsm + (int64_t)g * N;
-  const float* e21 = epsm + ((int64_t)G + g) * N;
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int r = ps * 16 + tr, i = i0 + r, j = j0 + tc;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < N && j < N) {
-      const float* src = T12 + (int64_t)i * t_row_stride + j;
-      if (VEC) {
-        v = __ldg(reinterpret_cast<const float4*>(src));
-      } else {
-        v.x = __ldg(src);
-        v.y = (j + 1 < N) ? __ldg(src + 1) : 0.f;
-        v.z = (j + 2 < N) ? __ldg(src + 2) : 0.f;
-        v.w = (j + 3 < N) ? __ldg(src + 3) : 0.f;
-      }
-      const float ir = ir12[i], ee = e12[i];
+      v = teacher_ld4<VEC>(tv.t12 + (int64_t)i * tv.row_stride + j, j, N);
+      const float ir = tv.ir12[i], ee = tv.e12[i];
       v.x = fmaxf(v.x * ir, ee); v.y = fmaxf(v.y * ir, ee); v.z = fmaxf(v.z * ir, ee); v.w = fmaxf(v.w * ir, ee);
     }
-    tile[tc][r] = v.x; tile[tc + 1][r] = v.y; tile[tc + 2][r] = v.z; tile[tc + 3][r] = v.w;
+    ws[tc][r] = v.x; ws[tc + 1][r] = v.y; ws[tc + 2][r] = v.z; ws[tc + 3][r] = v.w;
   }
   __syncthreads();
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int r = ps * 16 + tr, j = j0 + r, i = i0 + tc;
     if (j < N && i < N) {
-      const float* src = T21 + (int64_t)j * t_row_stride + i;
-      float4 v;
-      if (VEC) {
-        v = __ldg(reinterpret_cast<const float4*>(src));
-      } else {
-        v.x = __ldg(src);
-        v.y = (i + 1 < N) ? __ldg(src + 1) : 0.f;
-        v.z = (i + 2 < N) ? __ldg(src + 2) : 0.f;
-        v.w = (i + 3 < N) ? __ldg(src + 3) : 0.f;
-      }
-      const float ir = ir21[j], ee = e21[j];
-      v.x = fmaxf(v.x * ir, ee) + tile[r][tc];
-      v.y = fmaxf(v.y * ir, ee) + tile[r][tc + 1];
-      v.z = fmaxf(v.z * ir, ee) + tile[r][tc + 2];
-      v.w = fmaxf(v.w * ir, ee) + tile[r][tc + 3];
-      *reinterpret_cast<float4*>(WT + ((int64_t)g * N + j) * ldw + i) = v;
+      float4 v = teacher_ld4<VEC>(tv.t21 + (int64_t)j * tv.row_stride + i, i, N);
+      const float ir = tv.ir21[j], ee = tv.e21[j];
+      ws[r][tc] += fmaxf(v.x * ir, ee);
+      ws[r][tc + 1] += fmaxf(v.y * ir, ee);
+      ws[r][tc + 2] += fmaxf(v.z * ir, ee);
+      ws[r][tc + 3] += fmaxf(v.w * ir, ee);
     }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ TeacherView teacher_view(const float* t12, const float* t21, int64_t t_pair_stride,
+                                                    int64_t t_row_stride, int pair, int g, int G, int N, const float* invR,
+                                                    const float* epsm) {
+  TeacherView tv;
+  tv.t12 = t12 + (int64_t)pair * t_pair_stride;
+  tv.t21 = t21 + (int64_t)pair * t_pair_stride;
+  tv.row_stride = t_row_stride;
+  tv.ir12 = invR + (int64_t)g * N;
+  tv.ir21 = invR + ((int64_t)G + g) * N;
+  tv.e12 = epsm + (int64_t)g * N;
+  tv.e21 = epsm + ((int64_t)G + g) * N;
+  return tv;
+}
+
+// Step 3 as a kernel of its own is only needed by forward-only calls (the pass-1 epilogue then reads W^T for the D
+// term); with a backward, kl_dz_fast builds the tile itself and W^T is never written.
+// grid (N/64 i-tiles, N/64 j-tiles, G), block 256.  W^T rows are padded to a multiple of 4 floats: 128-bit stores.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+    kl_build_w_fast(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+                    int64_t t_row_stride, int pair0, int G, int N, const float* __restrict__ invR,
+                    const float* __restrict__ epsm, float* __restrict__ WT, int ldw) {
+  __shared__ float ws[64][65];
+  const int g = blockIdx.z, i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  load_w_tile<VEC>(ws, teacher_view(t12, t21, t_pair_stride, t_row_stride, pair0 + g, g, G, N, invR, epsm), N, i0, j0);
+  const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int r = ps * 16 + tr, j = j0 + r, i = i0 + tc;
+    if (j < N && i < N)
+      *reinterpret_cast<float4*>(WT + ((int64_t)g * N + j) * ldw + i) =
+          make_float4(ws[r][tc], ws[r][tc + 1], ws[r][tc + 2], ws[r][tc + 3]);
   }
 }
 
-// grid (N/64 j-tiles, N/64 i-tiles, G), block 256
+// grid (N/64 j-tiles, N/64 i-tiles, G), block 256.  The W^T tile comes straight from the teacher volumes (no W^T
+// buffer in the backward path).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
-    kl_dz_fast(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ WT,
-               int ldw, const float* __restrict__ rc, __nv_bfloat16* __restrict__ dZ, int ldd,
-               float* __restrict__ rowdot, float* __restrict__ coldot, double* __restrict__ loss_acc) {
+    kl_dz_fast(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ t12,
+               const float* __restrict__ t21, int64_t t_pair_stride, int64_t t_row_stride, int pair0,
+               const float* __restrict__ invR, const float* __restrict__ epsm, const float* __restrict__ rc,
+               __nv_bfloat16* __restrict__ dZ, int ldd, float* __restrict__ rowdot, float* __restrict__ coldot,
+               double* __restrict__ loss_acc) {
   __shared__ float ws[64][65];      // W^T tile [j][i]
   __shared__ float cdot[32][65];
   __shared__ float red[32];
   float wz = 0.f;                   // sum W z of this tile (the D term of the loss)
   const int g = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-  const float* wt = WT + (int64_t)g * N * ldw;
-  {
-    const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
-#pragma unroll
-    for (int ps = 0; ps < 4; ++ps) {
-      const int r = ps * 16 + tr, j = j0 + r, i = i0 + tc;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < N && i < N) v = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)j * ldw + i));
-      ws[r][tc] = v.x; ws[r][tc + 1] = v.y; ws[r][tc + 2] = v.z; ws[r][tc + 3] = v.w;
-    }
-  }
-  __syncthreads();
+  load_w_tile<VEC>(ws, teacher_view(t12, t21, t_pair_stride, t_row_stride, pair0 + g, g, G, N, invR, epsm), N, i0, j0);
   const float s = grad_scale * 0.5f / (float)N;
   const float* rr = rc + (int64_t)g * N;
   const float* cc = rc + ((int64_t)G + g) * N;
@@ -659,7 +675,7 @@ KLWorkspace carve_kl(void* base, int64_t G, int64_t N, int64_t C, bool backward)
   w.invR = c.take<float>(2 * G * N);
   w.epsm = c.take<float>(2 * G * N);
   w.Tsum = c.take<float>(2 * G * N);
-  w.WT = c.take<float>(G * N * w.ldw);
+  w.WT = c.take<float>(backward ? 0 : G * N * w.ldw);      // only the forward-only pass-1 epilogue reads W^T
   w.Lrow = c.take<float>(4 * G * N);
   w.Lcol = w.Lrow + G * N;
   w.rowdot = w.Lrow + 2 * G * N;
@@ -749,6 +765,7 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
     const int g = (int)((P - p0) < G ? (P - p0) : G);
     GD3_CHECK_CUDA(cudaMemsetAsync(w.Lrow, 0, sizeof(float) * 4 * G * N, stream));
     GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * G * kLossSlots, stream));
+    bool vec_ok = false;     // teacher rows allow 128-bit loads
     {
       const int esz = dtype == GD3_DTYPE_F32 ? 4 : 2;
       const bool fast = s1C == 1 && s2C == 1 && C % 8 == 0 && (s1N * esz) % 16 == 0 && (s2N * esz) % 16 == 0 &&
@@ -806,8 +823,9 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
 #undef GD3_TSTATS
       }
       GD3_CHECK_LAUNCH();
-      const bool vec_ok = N % 8 == 0 && rows_aligned;
-      {
+      vec_ok = N % 4 == 0 && rows_aligned;
+      if (!backward) {
+        // forward only: the pass-1 epilogue needs W^T for the D term
         dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
         GD3_PROF("kl_build_w_fast", stream);
         if (vec_ok)
@@ -816,8 +834,8 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         else
           kl_build_w_fast<false><<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N,
                                                            w.invR, w.epsm, w.WT, w.ldw);
+        GD3_CHECK_LAUNCH();
       }
-      GD3_CHECK_LAUNCH();
     }
     {
       tc::GemmShape s{(int)N, (int)N, (int)C, g};
@@ -851,8 +869,14 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         // workspace rows are padded to a multiple of 8 elements, so the 128-bit kernel also serves ragged N (elements in
         // the padding are masked on read and never consumed: the TMA extents of the gradient GEMMs stop at N)
         GD3_PROF("kl_dz_fast", stream);
-        kl_dz_fast<<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, w.WT, w.ldw, w.rc, w.dZ, w.ldn, w.rowdot,
-                                             w.coldot, w.loss_acc);
+        if (vec_ok)
+          kl_dz_fast<true><<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, t12, t21, t_pair_stride, t_row_stride,
+                                                     (int)p0, w.invR, w.epsm, w.rc, w.dZ, w.ldn, w.rowdot, w.coldot,
+                                                     w.loss_acc);
+        else
+          kl_dz_fast<false><<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, t12, t21, t_pair_stride, t_row_stride,
+                                                      (int)p0, w.invR, w.epsm, w.rc, w.dZ, w.ldn, w.rowdot, w.coldot,
+                                                      w.loss_acc);
       }
       GD3_CHECK_LAUNCH();
       {
