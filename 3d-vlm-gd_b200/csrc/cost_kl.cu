@@ -16,16 +16,18 @@
 //   df2_j = (sum_i dz_ij a_i - b_j coldot_j) / |f2_j|.
 // z needs no running max (bounded logits), so row and column softmax statistics come from the same exp.
 //
-// Pipeline per group of pairs (workspace is reused by every group so it stays resident in L2):
-//   1 kl_prep_features  SIMT   normalise rows -> a, b (bf16) and their transposes, 1/|f|
-//   2 kl_teacher_stats  SIMT   R, T, A per teacher row (one read of the teacher)
-//   3 kl_build_w        SIMT   W^T (fp32), the only form in which the teacher is used afterwards
-//   4 tc_gemm<EpiKLStats>      z tiles on tcgen05 -> exp / row+col sums / D in registers; z kept as fp16
-//   5 kl_finalize_stats SIMT   r, c and the T log L terms
-//   6 kl_dz             SIMT   dz, dz^T (bf16) and rowdot / coldot
-//   7 tc_gemm<EpiGradOut> x2   df1 = dz b, df2 = dz^T a with the normalisation backward fused
-// The fp32 N x N cost volume never exists in memory; the fp16 z / bf16 dz staging buffers are sized
-// for one group and live in L2 (see DESIGN.md for the TMEM budget argument against a single kernel).
+// Pipeline per group of pairs (forward + backward):
+//   1 kl_prep            SIMT   normalise rows -> a, b (bf16), 1/|f|
+//   2 kl_teacher_stats   SIMT   R, T, A per teacher row (first read of the teacher)
+//   3 tc_gemm<EpiKLStats>       z tiles on tcgen05 -> exp / row + col sums in registers; z kept as fp16
+//   4 kl_finalize_stats  SIMT   r, c and the T log L terms
+//   5 kl_dz              SIMT   builds the W tile from the teacher (second and last read), dz (bf16), rowdot /
+//                               coldot and the D = sum W z term of the loss
+//   6 tc_gemm<EpiGradOut> x2    df1 = dz b, df2 = dz^T a with the normalisation backward fused; a, b and dz are read
+//                               in place through MN-major operand descriptors (no a^T / b^T / dz^T copies)
+// Forward-only calls have no step 5: kl_build_w materialises W^T and the pass-1 epilogue accumulates D from it.
+// The fp32 N x N cost volume never exists in memory; only fp16 z / bf16 dz are staged for the gradient GEMMs (see
+// DESIGN.md for the TMEM budget argument against a single kernel).
 #include "../../include/gd3.h"
 #include "common.cuh"
 #include "tc_gemm.cuh"

@@ -252,9 +252,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     x1 = (b_ < K && a1 < K) ? __ldg(rrow + 2 * l16 + 32) : 1.f;
   };
   float rs0_next, rs1_next;
-  load_rstd(tb * TILE_B + warp * B_PER_WARP, rs0_next, rs1_next);
+  // b rows are dealt round-robin to the warps (row bi * WARPS + warp of the tile), so that a partial last tile
+  // (K = 300: 44 of 128 rows) still keeps all 8 warps busy and the CTA stops as soon as the rows run out
+  load_rstd(tb * TILE_B + warp, rs0_next, rs1_next);
   for (int bi = 0; bi < B_PER_WARP; ++bi) {
-    const int b = tb * TILE_B + warp * B_PER_WARP + bi;
+    if (tb * TILE_B + bi * WARPS >= K) break;       // CTA-uniform: no row left for any warp
+    const int b = tb * TILE_B + bi * WARPS + warp;
     const bool b_ok = b < K;     // warp-uniform
     F2 vb[HP], dub[HP];
     float d_b = 0.f;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     // 1 / sigma of this b row's pairs: taken from the registers loaded during the previous row, and the next
     // row's values are requested now
     const float rs0 = rs0_next, rs1 = rs1_next;
-    if (bi + 1 < B_PER_WARP) load_rstd(b + 1, rs0_next, rs1_next);
+    if (bi + 1 < B_PER_WARP) load_rstd(b + WARPS, rs0_next, rs1_next);
 #pragma unroll 2
     for (int t = 0; t < SLOTS; ++t) {
       // staggered a index: at any step the half-warps of the CTA work on different rows
