@@ -20,6 +20,8 @@
 // reductions are 4 xor-shuffles and a warp works on two pairs at a time.  A CTA owns a 128 x 128 tile of
 // (a, b): every warp keeps the gradient of its b rows in registers and accumulates the a side into a shared
 // tile; the a index is staggered per warp so no two warps touch the same row in the same step.
+#include <type_traits>
+
 #include "../../include/gd3.h"
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -281,7 +283,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     // 1 / sigma of this b row's pairs: taken from the registers loaded during the previous row, and the next
     // row's values are requested now
     const float rs0 = rs0_next, rs1 = rs1_next;
+    // does any pair of this b row carry the "recompute directly" flag of the Gram epilogue?  (warp-uniform, rare)
+    const bool row_flagged = __any_sync(0xffffffffu, rs0 < 0.f || rs1 < 0.f);
     if (bi + 1 < B_PER_WARP) load_rstd(b + WARPS, rs0_next, rs1_next);
+    // The walk over the a tile exists twice: the common one trusts the Gram rstd, the rare one (a flagged pair in
+    // this b row) re-derives 1 / sigma from the pair itself where the flag is set.  Same barrier pattern in both.
+    auto walk_a_tile = [&](auto check_tag) {
+    constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll 2
     for (int t = 0; t < SLOTS; ++t) {
       // staggered a index: at any step the half-warps of the CTA work on different rows
@@ -304,6 +312,14 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
         hcv[3] = add2(vb[3], make_float2(a1.z, a1.w));
         PairOut o;
         o.rstd = rs;
+        if (CHECK) {
+          // flagged by the Gram epilogue (near-duplicate rows): sum of squares of this pair's h_c directly
+          F2 ss2 = bc(0.f);
+#pragma unroll
+          for (int i = 0; i < HP; ++i) ss2 = fma2(hcv[i], hcv[i], ss2);
+          const float ss = half_sum(ss2.x + ss2.y, 0xffffffffu);
+          if (rs < 0.f) o.rstd = rsqrtf(fmaf(ss, 1.f / H, p.ln_eps));
+        }
         head_eval<GRAD, true>(hcv, hc, p.ln_eps, p.use_tanh, o);
         const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
         float l, dl;
@@ -349,6 +365,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
       static_assert(SPACING - 1 >= 2 && SLOTS % 2 == 0, "barrier period");
       if (GRAD && (t & 1)) __syncthreads();
     }
+    };
+    if (row_flagged) walk_a_tile(std::true_type{});
+    else walk_a_tile(std::false_type{});
     if (GRAD) {
       // combine the two half warps and store this b row's partial (over the a tile) gradient
 #pragma unroll
@@ -407,6 +426,35 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
 // products, the same accuracy class as u itself); its epilogue writes rstd = rsqrt(ss / H + eps) for every pair.
 // This removes the sum of squares, its 4 shuffle rounds and the rsqrt from the head of every pair step.
 // ------------------------------------------------------------------------------------------
+// mean keypoint feature of every centring group (one set, or the two sets of an image pair when the cross-view L1
+// term couples them).  Every loss term depends on feature DIFFERENCES inside a group only, and sum_k d loss / d u_k = 0
+// over a group, so u = (f - mu) W1^T gives the same losses and gradients as u = f W1^T -- while the bf16 split of
+// the GEMM operands (and the Gram matrix of 4.3) resolves the deviations instead of the component all keypoints of
+// an image share (real ViT tokens: the common component is 10-1000x the differences).
+// grid (groups, ceil(D / 64)), block 1024 = 16 row slices x 64 channels
+__global__ void __launch_bounds__(1024) rank_group_mean(const float* __restrict__ f, int rows, int D, float* __restrict__ mu) {
+  __shared__ float part[16][64];
+  const int g = blockIdx.x, cl = threadIdx.x & 63, c = blockIdx.y * 64 + cl, slice = threadIdx.x >> 6;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < D) {
+    const float* col = f + (int64_t)g * rows * D + c;
+    int r = slice;
+    for (; r + 16 < rows; r += 32) {      // two independent chains
+      s0 += __ldg(col + (int64_t)r * D);
+      s1 += __ldg(col + (int64_t)(r + 16) * D);
+    }
+    if (r < rows) s0 += __ldg(col + (int64_t)r * D);
+  }
+  part[slice][cl] = s0 + s1;
+  __syncthreads();
+  if (slice == 0 && c < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += part[k][cl];
+    mu[(int64_t)g * D + c] = t / (float)rows;
+  }
+}
+
 // one warp per row of u: centre, add the centred bias on the b side, split into bf16 panels, squared norms
 __global__ void __launch_bounds__(256) rank_gram_prep(const float* __restrict__ u, const float* __restrict__ b1, int64_t R,
                                                       __nv_bfloat16* __restrict__ Wb3, __nv_bfloat16* __restrict__ Va3,
@@ -448,7 +496,8 @@ __global__ void __launch_bounds__(256) rank_gram_prep(const float* __restrict__ 
   }
 }
 
-// rstd[set][b][a] = rsqrt(max(|w_b|^2 + |v_a|^2 - 2 acc, 0) / H + eps)
+// rstd[set][b][a] = rsqrt(max(|w_b|^2 + |v_a|^2 - 2 acc, 0) / H + eps), or -1 where the Gram form is too inaccurate
+constexpr float kGramMinRatio = 1.f / 64.f;      // ss / (|w|^2 + |v|^2) below which the pair is recomputed directly
 struct EpiRstd {
   static constexpr int kScratchBytes = tc::kMaxEpiWarps * tc::kWarpTileBytes;
   struct Params {
@@ -481,8 +530,11 @@ struct EpiRstd {
       if (rows <= 0) continue;
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
-        const float ss = fmaxf(fmaf(-2.f, v[q], pr.nb + __shfl_sync(0xffffffffu, na_l, q)), 0.f);
-        v[q] = rsqrtf(fmaf(ss, 1.f / H, p.eps));
+        const float nsum = pr.nb + __shfl_sync(0xffffffffu, na_l, q);
+        const float ss = fmaxf(fmaf(-2.f, v[q], nsum), 0.f);
+        // the difference of nearly identical rows cancels in |w|^2 + |v|^2 - 2 w.v (split-bf16 products carry ~2^-16 of
+        // |w| |v|): flag such pairs (negative value) and let the pair kernel sum the squares directly
+        v[q] = (ss < kGramMinRatio * nsum) ? -1.f : rsqrtf(fmaf(ss, 1.f / H, p.eps));
       }
       tc::warp_store_rows<float>(t, v, oslab + n, p.K, rows, p.K - n, cx.lane);
     }
@@ -697,7 +749,7 @@ __global__ void rank_finalize(const double* __restrict__ loss_sum, const float* 
 struct RankWorkspace {
   __nv_bfloat16 *F3, *W3, *du2;
   __nv_bfloat16 *Wb3, *Va3;
-  float *u, *inv_count, *dub_part, *dua_part, *du_extra, *nb, *na, *rstd;
+  float *u, *inv_count, *dub_part, *dua_part, *du_extra, *nb, *na, *rstd, *mu;
   double *loss_sum, *l1_sum;
   int* count;
   size_t total;
@@ -720,6 +772,7 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
   w.W3 = c.take<__nv_bfloat16>((int64_t)H * 3 * w.ldd);
   w.u = c.take<float>(R * H);
+  w.mu = c.take<float>(S * D);
   w.Wb3 = c.take<__nv_bfloat16>(R * 3 * H);
   w.Va3 = c.take<__nv_bfloat16>(R * 3 * H);
   w.nb = c.take<float>(R);
@@ -793,7 +846,16 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   {
     // operands of u = f W1^T; the backward GEMMs read the same panels MN-major (no transposed copies)
     XtLayout none{0, 1, 1, 8, 8, 8, 0};
-    if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, nullptr, none, stream))) return rc;
+    // centring group: the two sets of an image pair when the L1 term couples them, else one set (rank_group_mean)
+    const int group_rows = (int)((l1 ? 2 : 1) * K);
+    {
+      dim3 grid((unsigned)(R / group_rows), (unsigned)ceil_div<int64_t>(D, 64));
+      GD3_PROF("rank_group_mean", stream);
+      rank_group_mean<<<grid, 1024, 0, stream>>>(feats, group_rows, (int)D, w.mu);
+    }
+    GD3_CHECK_LAUNCH();
+    if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, nullptr, none, stream, w.mu, group_rows)))
+      return rc;
     if ((rc = launch_split3("split3_w1", W1, H, (int)D, w.ldd, 1, w.W3, nullptr, none, stream))) return rc;
   }
   {

@@ -41,7 +41,7 @@ __device__ __forceinline__ void hi_lo(float v, uint16_t& hi, uint16_t& lo) {
 // generic scalar kernel: 32 x 32 tiles
 static __global__ void __launch_bounds__(256)
     split_scalar(const float* __restrict__ x, int64_t R, int D, int ldd, int lo_panel, __nv_bfloat16* __restrict__ X3,
-                 __nv_bfloat16* __restrict__ XT, XtLayout xl) {
+                 __nv_bfloat16* __restrict__ XT, XtLayout xl, const float* __restrict__ mu, int mu_rows) {
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -50,7 +50,8 @@ static __global__ void __launch_bounds__(256)
     for (int r = w; r < 32; r += 8) {
       const int64_t row = r0 + r;
       const int c = c0 + lane;
-      const float v = (row < R && c < D) ? __ldg(x + row * D + c) : 0.f;
+      float v = (row < R && c < D) ? __ldg(x + row * D + c) : 0.f;
+      if (mu && row < R && c < D) v -= __ldg(mu + (row / mu_rows) * D + c);
       tile[r][lane] = v;
       if (row < R && c < ldd) {
         uint16_t hi, lo;
@@ -86,7 +87,8 @@ static __global__ void __launch_bounds__(256)
 // of 8 rows never straddles two sets whatever K is; the rows past the end of the set are zeros (padding up to ldk).
 static __global__ void __launch_bounds__(256)
     split_fast(const float* __restrict__ x, int64_t R, int D, int ldd, int lo_panel, __nv_bfloat16* __restrict__ X3,
-               __nv_bfloat16* __restrict__ XT, XtLayout xl, int tiles_per_set) {
+               __nv_bfloat16* __restrict__ XT, XtLayout xl, int tiles_per_set, const float* __restrict__ mu,
+               int mu_rows) {
   constexpr int TS = 66;
   __shared__ uint16_t t_hi[64 * TS];
   __shared__ uint16_t t_lo[64 * TS];
@@ -108,6 +110,11 @@ static __global__ void __launch_bounds__(256)
           const float4 a = __ldg(reinterpret_cast<const float4*>(x + row * D + c));
           const float4 b = __ldg(reinterpret_cast<const float4*>(x + row * D + c) + 1);
           v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          if (mu) {
+            const float* m = mu + (row / mu_rows) * D + c;
+            const float4 ma = __ldg(reinterpret_cast<const float4*>(m)), mb = __ldg(reinterpret_cast<const float4*>(m) + 1);
+            v[0] -= ma.x; v[1] -= ma.y; v[2] -= ma.z; v[3] -= ma.w; v[4] -= mb.x; v[5] -= mb.y; v[6] -= mb.z; v[7] -= mb.w;
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -170,24 +177,27 @@ static __global__ void __launch_bounds__(256)
 
 // rows beyond R inside the last aligned group of 8 are written as zeros by the fast path only when they exist
 // in the tile; callers that rely on zero padding clear the buffers themselves.
+// mu (optional): (R / mu_rows, D) fp32 row-group means that are subtracted before the split (x - mu[row / mu_rows]),
+// so that the bf16 panels resolve the deviations and not a large component shared by the whole group.
 inline int launch_split3(const char* name, const float* x, int64_t R, int D, int ldd, int lo_panel,
-                         __nv_bfloat16* X3, __nv_bfloat16* XT, const XtLayout& xl, cudaStream_t stream) {
+                         __nv_bfloat16* X3, __nv_bfloat16* XT, const XtLayout& xl, cudaStream_t stream,
+                         const float* mu = nullptr, int mu_rows = 1) {
   if (R <= 0) return GD3_OK;
   const bool want_t = XT != nullptr && xl.panels != 0;
   const bool t_ok = !want_t || (xl.ld % 8 == 0 && xl.ldk % 8 == 0 && xl.ldk >= round_up(xl.K, 8) && xl.group_len % 8 == 0 &&
                                 xl.set_stride % 8 == 0 && R % xl.K == 0 && reinterpret_cast<uintptr_t>(XT) % 16 == 0);
   const bool fast = D % 8 == 0 && ldd == D && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
-                    reinterpret_cast<uintptr_t>(X3) % 16 == 0 && t_ok;
+                    reinterpret_cast<uintptr_t>(X3) % 16 == 0 && reinterpret_cast<uintptr_t>(mu) % 16 == 0 && t_ok;
   {
     GD3_PROF(name, stream);
     if (fast) {
       const int tps = want_t ? ceil_div(xl.K, 64) : 1;
       const int64_t blocks = want_t ? (R / xl.K) * tps : ceil_div<int64_t>(R, 64);
-      split_detail::split_fast<<<(unsigned)blocks, 256, 0, stream>>>(x, R, D, ldd, lo_panel, X3, XT, xl, tps);
+      split_detail::split_fast<<<(unsigned)blocks, 256, 0, stream>>>(x, R, D, ldd, lo_panel, X3, XT, xl, tps, mu, mu_rows);
     }
     else
       split_detail::split_scalar<<<(unsigned)ceil_div<int64_t>(R, 32), 256, 0, stream>>>(x, R, D, ldd, lo_panel, X3, XT,
-                                                                                         xl);
+                                                                                         xl, mu, mu_rows);
   }
   GD3_CHECK_LAUNCH();
   return GD3_OK;

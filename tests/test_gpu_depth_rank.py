@@ -142,3 +142,28 @@ def test_depth_losses_edge_cases():
     want = olosses.pairwise_logistic_ranking_loss(hc, feats, depths, 0.05)
     got = losses.pairwise_logistic_ranking_loss(cuda_head(hc), feats.cuda(), depths.cuda(), 0.05)
     assert rel_err(got.item(), float(want)) <= 1e-3
+
+
+@pytest.mark.parametrize('spread', [1.0, 0.1, 0.01, 0.001])
+def test_ranking_correlated_keypoint_features(spread):
+    """Keypoint features that share a large common component (real ViT tokens of one image do): the LayerNorm
+    statistics of the pair differences come from a Gram matrix, which must not lose the small differences."""
+    from gd3.compat import losses
+    torch.manual_seed(11)
+    K, D = 96, 64
+    head = olosses.DepthHead(D)
+    with torch.no_grad():
+        head.fusion_layer[0].bias.mul_(0.05)          # small bias: the pair statistics are dominated by f_j - f_i
+    base = torch.randn(1, 1, D) * 3.0
+    feats = base + spread * torch.randn(1, K, D)
+    feats[0, 5] = feats[0, 4] + 1e-4 * spread * torch.randn(D)        # a near-duplicate pair on top
+    depths = torch.rand(1, K) * 4.5 + 0.5
+    ref_in = feats.clone().requires_grad_(True)
+    want = olosses.pairwise_logistic_ranking_loss(head, ref_in, depths, depth_threshold=0.05)
+    want.backward()
+    h = cuda_head(head)
+    x = feats.cuda().requires_grad_(True)
+    got = losses.pairwise_logistic_ranking_loss(h, x, depths.cuda(), depth_threshold=0.05)
+    got.backward()
+    assert rel_err(got.item(), want.item()) <= 1e-3, (spread, got.item(), want.item())
+    assert_grad_close(x.grad, ref_in.grad, name=f'feats/spread={spread}', norm_rtol=3e-2)
