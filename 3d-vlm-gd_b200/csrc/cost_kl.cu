@@ -53,7 +53,7 @@ __device__ __forceinline__ float ld_feat<float>(const float* p) { return __ldg(p
 template <>
 __device__ __forceinline__ float ld_feat<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
-// grid: (ceil(N/32), G, 2 images); block 256.  Writes a (G, N, ldc) bf16, aT (G, C, ldn) bf16, inv (G, N).
+// grid: (ceil(N/32), G, 2 images); block 256.  Writes a (G, N, ldc) bf16 and inv (G, N); any element strides.
 template <class T>
 __global__ void __launch_bounds__(256)
     kl_prep_features(const T* __restrict__ f1, const T* __restrict__ f2, int64_t s1P, int64_t s1N, int64_t s1C,
@@ -112,8 +112,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Fast path of step 1 for channel-contiguous features (sC == 1, C % 8 == 0, 16-byte aligned rows):
-// 64 rows per CTA, 128-bit loads, a and aT written with 128-bit stores through a padded smem transpose.
+// Fast path of step 1 for channel-contiguous features (sC == 1, C % 8 == 0, 16-byte aligned rows): 128-bit accesses.
 template <class T>
 __device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
 template <>
@@ -693,8 +692,8 @@ KLWorkspace carve_kl(void* base, int64_t G, int64_t N, int64_t C, bool backward)
 int64_t auto_group(int64_t P, int64_t N, int64_t C) {
   // Measured on B200 (tools/probe_kl.py): launches that cover many pairs beat small L2-resident groups,
   // because every kernel of the pipeline then runs several full waves.  So a group is as large as a
-  // ~3 GB workspace allows (W^T fp32 + z fp16 + dz, dz^T bf16 + a, b, aT, bT bf16 per pair).
-  const double per_pair = N * (double)N * (4 + 2 + 2 + 2) + 4.0 * N * C * 2;
+  // ~3 GB workspace allows (per pair: z fp16 + dz bf16, or W^T fp32 for forward-only calls, + a, b bf16).
+  const double per_pair = N * (double)N * 4 + 2.0 * N * C * 2;
   int64_t g = (int64_t)(3.0e9 / per_pair);
   if (g < 1) g = 1;
   return g > P ? P : g;

@@ -845,7 +845,6 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   // ---- u = f W1^T on the tensor cores (split bf16, 3 K-concatenated panels) ----
   {
     // operands of u = f W1^T; the backward GEMMs read the same panels MN-major (no transposed copies)
-    XtLayout none{0, 1, 1, 8, 8, 8, 0};
     // centring group: the two sets of an image pair when the L1 term couples them, else one set (rank_group_mean)
     const int group_rows = (int)((l1 ? 2 : 1) * K);
     {
@@ -854,9 +853,9 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
       rank_group_mean<<<grid, 1024, 0, stream>>>(feats, group_rows, (int)D, w.mu);
     }
     GD3_CHECK_LAUNCH();
-    if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, nullptr, none, stream, w.mu, group_rows)))
+    if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, stream, w.mu, group_rows)))
       return rc;
-    if ((rc = launch_split3("split3_w1", W1, H, (int)D, w.ldd, 1, w.W3, nullptr, none, stream))) return rc;
+    if ((rc = launch_split3("split3_w1", W1, H, (int)D, w.ldd, 1, w.W3, stream))) return rc;
   }
   {
     CUtensorMap ta, tb;

@@ -388,9 +388,8 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
   {
     // [hi | hi | lo] x [hi | lo | hi] panels for the similarity GEMM; the gradient GEMMs read the hi panels (panel 0 of
     // either buffer) MN-major, so no transposed copy is made
-    XtLayout none{0, 1, 1, 8, 8, 8, 0};
-    if ((rc = launch_split3("ap_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, nullptr, none, stream))) return rc;
-    if ((rc = launch_split3("ap_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, nullptr, none, stream))) return rc;
+    if ((rc = launch_split3("ap_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, stream))) return rc;
+    if ((rc = launch_split3("ap_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, stream))) return rc;
   }
   {
     CUtensorMap ta, tb;
@@ -471,9 +470,8 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
   GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int), stream));
   int rc;
   {
-    XtLayout none{0, 1, 1, 8, 8, 8, 0};
-    if ((rc = launch_split3("nce_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, nullptr, none, stream))) return rc;
-    if ((rc = launch_split3("nce_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, nullptr, none, stream))) return rc;
+    if ((rc = launch_split3("nce_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, stream))) return rc;
+    if ((rc = launch_split3("nce_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, stream))) return rc;
     CUtensorMap ta, tb;
     if ((rc = tc::make_tmap_bf16(&ta, w.A3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc,
                                  tc::BM)))
