@@ -37,7 +37,9 @@ struct SigT {
 __device__ __forceinline__ SigT sig_both(float u, float inv_tau) {
   const float e = -u * inv_tau;
   const float ec = fminf(fmaxf(e, -50.f), 50.f);
-  const float s = 1.f / (1.f + expf(ec));
+  // ex2-based exponential and approximate division: relative error ~1e-6 (<= 1e-5 at the +-50 clamp, where the
+  // sigmoid is saturated), far inside the 1e-3 loss bar; the precise versions made this kernel 1.5x slower
+  const float s = __fdividef(1.f, 1.f + __expf(ec));
   SigT r;
   r.s = s;
   r.ds = (e >= -50.f && e <= 50.f) ? s * (1.f - s) * inv_tau : 0.f;
@@ -140,24 +142,28 @@ __global__ void __launch_bounds__(256)
     const float pos = srow[s];
     float g1[NE], g2[NE];
     float S1 = 0.f, S2 = 0.f, G2 = 0.f;
+    // all loads of the row first (independent, coalesced), then the arithmetic: the negative mask lives in a bit field
+    float sj[NE];
+    unsigned negmask = 0u;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const int j = lane + 32 * e;
-      g1[e] = 0.f;
-      g2[e] = 0.f;
+      sj[e] = 0.f;
       if (j < K) {
+        sj[e] = srow[j];
         const float dx = ax - P2[3 * j], dy = ay - P2[3 * j + 1], dz = az - P2[3 * j + 2];
-        const bool neg = (sqrtf(dx * dx + dy * dy + dz * dz) > thr_neg) && (j != s);
-        if (neg) {
-          const float sj = srow[j];
-          const SigT q1 = sig_both(sj - 1.f, inv_tau), q2 = sig_both(sj - pos, inv_tau);
-          S1 += q1.s;
-          S2 += q2.s;
-          G2 += q2.ds;
-          g1[e] = q1.ds;
-          g2[e] = q2.ds;
-        }
+        if ((sqrtf(dx * dx + dy * dy + dz * dz) > thr_neg) && (j != s)) negmask |= 1u << e;
       }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const SigT q1 = sig_both(sj[e] - 1.f, inv_tau), q2 = sig_both(sj[e] - pos, inv_tau);
+      const bool neg = (negmask >> e) & 1u;
+      S1 += neg ? q1.s : 0.f;
+      S2 += neg ? q2.s : 0.f;
+      G2 += neg ? q2.ds : 0.f;
+      g1[e] = neg ? q1.ds : 0.f;
+      g2[e] = neg ? q2.ds : 0.f;
     }
     S1 = warp_sum(S1);
     S2 = warp_sum(S2);
