@@ -20,6 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-I', INCLUDE, '-I', CSRC]
+FLAGS += os.environ.get('GD3_NVCC_EXTRA', '').split()      # e.g. -DGD3_MAX_STAGES=3 for pipeline experiments
 
 
 def _digest(paths):

@@ -31,7 +31,11 @@ constexpr int kSmemBudget = 227 * 1024;
 // as many stages as fit next to the epilogue scratch (at most 8): 1024 B alignment slack + ring + scratch + barriers
 __host__ __device__ constexpr int num_stages(int BN, int epi_scratch = 0) {
   const int fit = (kSmemBudget - 1024 - 256 - epi_scratch) / stage_bytes(BN);
+#ifdef GD3_MAX_STAGES
+  return fit > GD3_MAX_STAGES ? GD3_MAX_STAGES : fit;      // experiment knob: pipeline-depth sensitivity
+#else
   return fit > 8 ? 8 : fit;
+#endif
 }
 __host__ __device__ constexpr int smem_bytes(int BN, int epi_scratch) {
   return 1024 + num_stages(BN, epi_scratch) * stage_bytes(BN) + epi_scratch + 256;
