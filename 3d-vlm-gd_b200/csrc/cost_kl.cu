@@ -432,29 +432,41 @@ __device__ __forceinline__ float4 teacher_ld4(const float* src, int col, int N) 
 template <bool VEC>
 __device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& tv, int N, int i0, int j0) {
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+  // all eight teacher loads of a thread (and their row factors) are issued before the first use
+  float4 v12[4], v21[4];
+  float ir12[4], ee12[4], ir21[4], ee21[4];
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
-    const int r = ps * 16 + tr, i = i0 + r, j = j0 + tc;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < N && j < N) {
-      v = teacher_ld4<VEC>(tv.t12 + (int64_t)i * tv.row_stride + j, j, N);
-      const float ir = tv.ir12[i], ee = tv.e12[i];
-      v.x = fmaxf(v.x * ir, ee); v.y = fmaxf(v.y * ir, ee); v.z = fmaxf(v.z * ir, ee); v.w = fmaxf(v.w * ir, ee);
-    }
-    ws[tc][r] = v.x; ws[tc + 1][r] = v.y; ws[tc + 2][r] = v.z; ws[tc + 3][r] = v.w;
+    const int r = ps * 16 + tr;
+    const int i = i0 + r, j = j0 + tc;
+    const bool ok12 = i < N && j < N;
+    v12[ps] = ok12 ? teacher_ld4<VEC>(tv.t12 + (int64_t)i * tv.row_stride + j, j, N) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ir12[ps] = ok12 ? tv.ir12[i] : 0.f;
+    ee12[ps] = ok12 ? tv.e12[i] : 0.f;
+    const int jj = j0 + r, ii = i0 + tc;
+    const bool ok21 = jj < N && ii < N;
+    v21[ps] = ok21 ? teacher_ld4<VEC>(tv.t21 + (int64_t)jj * tv.row_stride + ii, ii, N) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ir21[ps] = ok21 ? tv.ir21[jj] : 0.f;
+    ee21[ps] = ok21 ? tv.e21[jj] : 0.f;
+  }
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int r = ps * 16 + tr;
+    const float ir = ir12[ps], ee = ee12[ps];
+    ws[tc][r] = fmaxf(v12[ps].x * ir, ee);
+    ws[tc + 1][r] = fmaxf(v12[ps].y * ir, ee);
+    ws[tc + 2][r] = fmaxf(v12[ps].z * ir, ee);
+    ws[tc + 3][r] = fmaxf(v12[ps].w * ir, ee);
   }
   __syncthreads();
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
-    const int r = ps * 16 + tr, j = j0 + r, i = i0 + tc;
-    if (j < N && i < N) {
-      float4 v = teacher_ld4<VEC>(tv.t21 + (int64_t)j * tv.row_stride + i, i, N);
-      const float ir = tv.ir21[j], ee = tv.e21[j];
-      ws[r][tc] += fmaxf(v.x * ir, ee);
-      ws[r][tc + 1] += fmaxf(v.y * ir, ee);
-      ws[r][tc + 2] += fmaxf(v.z * ir, ee);
-      ws[r][tc + 3] += fmaxf(v.w * ir, ee);
-    }
+    const int r = ps * 16 + tr;
+    const float ir = ir21[ps], ee = ee21[ps];
+    ws[r][tc] += fmaxf(v21[ps].x * ir, ee);
+    ws[r][tc + 1] += fmaxf(v21[ps].y * ir, ee);
+    ws[r][tc + 2] += fmaxf(v21[ps].z * ir, ee);
+    ws[r][tc + 3] += fmaxf(v21[ps].w * ir, ee);
   }
   __syncthreads();
 }
@@ -507,12 +519,20 @@ __global__ void __launch_bounds__(256)
   __shared__ float red[32];
   float wz = 0.f;                   // sum W z of this tile (the D term of the loss)
   const int g = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  // thread = (row tr8 of a 32-row pass, 8 consecutive columns at jc); its two z vectors are requested before the W tile
+  // is built so that their latency hides behind it
+  const int tr8 = threadIdx.x >> 3, jc = (threadIdx.x & 7) * 8;
+  uint4 zpre[2];
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int i = i0 + ps * 32 + tr8;
+    zpre[ps] = (i < N && j0 + jc < N) ? __ldg(reinterpret_cast<const uint4*>(Z + ((int64_t)g * N + i) * ldz + j0 + jc))
+                                      : make_uint4(0u, 0u, 0u, 0u);
+  }
   load_w_tile<VEC>(ws, teacher_view(t12, t21, t_pair_stride, t_row_stride, pair0 + g, g, G, N, invR, epsm), N, i0, j0);
   const float s = grad_scale * 0.5f / (float)N;
   const float* rr = rc + (int64_t)g * N;
   const float* cc = rc + ((int64_t)G + g) * N;
-  // thread = (row tr8 of a 32-row pass, 8 consecutive columns at jc)
-  const int tr8 = threadIdx.x >> 3, jc = (threadIdx.x & 7) * 8;
   float cj[8], cdp[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int q = 0; q < 8; ++q) d[q] = 0.f;
     if (i < N && j0 + jc < N) {
-      const uint4 zz = __ldg(reinterpret_cast<const uint4*>(Z + ((int64_t)g * N + i) * ldz + j0 + jc));
+      const uint4 zz = zpre[ps];
       const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
       const float ri = rr[i];
 #pragma unroll
