@@ -190,6 +190,9 @@ def run_ours(args):
     lib = _lib.load()
     peaks = load_peaks()
 
+    if world > 1:
+        # every rank builds its own batch on the host: share the cores instead of oversubscribing them
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     # ---- synthetic inputs: every rank gets its own seeded batch (pair indices rank*P ...) ----
     host = bench_common.make_batch(cfg, cfg_id=cfg['cfg_id'], pair0=rank * P)
     host = bench_common.to_device(host, 'cpu', feature_dtype=torch.bfloat16)
