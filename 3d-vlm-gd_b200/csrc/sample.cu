@@ -138,22 +138,32 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_MAX_IT = 32;    // float4 groups per lane: C <= 32 lanes * 4 * 32 = 4096
 
-template <class T>
-__device__ __forceinline__ float4 ld4(const T* p);
-template <>
-__device__ __forceinline__ float4 ld4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-template <>
-__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
-  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-  return make_float4(bf16_bits_to_float(v.x & 0xFFFFu), bf16_bits_to_float(v.x >> 16),
-                     bf16_bits_to_float(v.y & 0xFFFFu), bf16_bits_to_float(v.y >> 16));
-}
+// raw 4-channel load (8 bytes of bf16 or 16 bytes of fp32) and its conversion, so that many loads can be in flight
+// before the first conversion
+template <class T> struct Raw4;
+template <> struct Raw4<float> {
+  using type = float4;
+  static __device__ __forceinline__ type ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ float4 cvt(const type& v) { return v; }
+};
+template <> struct Raw4<__nv_bfloat16> {
+  using type = uint2;
+  static __device__ __forceinline__ type ld(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  static __device__ __forceinline__ float4 cvt(const type& v) {
+    return make_float4(bf16_bits_to_float(v.x & 0xFFFFu), bf16_bits_to_float(v.x >> 16),
+                       bf16_bits_to_float(v.y & 0xFFFFu), bf16_bits_to_float(v.y >> 16));
+  }
+};
 
+// The 4 taps of GRP channel groups are requested together before the first conversion (the loop over the layers has a
+// runtime trip count, so the compiler cannot hoist them itself): 150 -> 107 us per step at cfg2.
 template <class T, int NIT>
 __global__ void __launch_bounds__(256)
     sample_fwd_fast(const T* __restrict__ tok, int L, int64_t sL, int64_t sP, int64_t sN, const float* __restrict__ kp,
                     int K, int C, SampleGeom g, int normalize, float* __restrict__ out, int64_t oP, int64_t oK,
                     float* __restrict__ inv_norm) {
+  using R = Raw4<T>;
+  constexpr int GRP = (sizeof(typename R::type) == 8) ? 4 : 2;      // iterations whose 4 taps are loaded together
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5), p = blockIdx.y;
   if (k >= K) return;
@@ -161,28 +171,47 @@ __global__ void __launch_bounds__(256)
   const Taps t = make_taps(g, x, y);
   const float invL = 1.f / (float)L;
   float4 acc[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const T* lbase = tok + l * sL + p * sP;
+#pragma unroll
+    for (int g0 = 0; g0 < NIT; g0 += GRP) {
+      typename R::type raw[GRP][4];
+#pragma unroll
+      for (int q = 0; q < GRP; ++q) {
+        const int c = ((g0 + q) * 32 + lane) * 4;
+        if (g0 + q < NIT && c < C) {
+          const T* base = lbase + c;
+          raw[q][0] = R::ld(base + t.i00 * sN);
+          raw[q][1] = R::ld(base + t.i01 * sN);
+          raw[q][2] = R::ld(base + t.i10 * sN);
+          raw[q][3] = R::ld(base + t.i11 * sN);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < GRP; ++q) {
+        const int c = ((g0 + q) * 32 + lane) * 4;
+        if (g0 + q < NIT && c < C) {
+          const float4 v00 = R::cvt(raw[q][0]), v01 = R::cvt(raw[q][1]), v10 = R::cvt(raw[q][2]), v11 = R::cvt(raw[q][3]);
+          // same accumulation order as grid_sample: nw, ne, sw, se
+          float4 v;
+          v.x = v00.x * t.w00; v.x += v01.x * t.w01; v.x += v10.x * t.w10; v.x += v11.x * t.w11;
+          v.y = v00.y * t.w00; v.y += v01.y * t.w01; v.y += v10.y * t.w10; v.y += v11.y * t.w11;
+          v.z = v00.z * t.w00; v.z += v01.z * t.w01; v.z += v10.z * t.w10; v.z += v11.z * t.w11;
+          v.w = v00.w * t.w00; v.w += v01.w * t.w01; v.w += v10.w * t.w10; v.w += v11.w * t.w11;
+          float4& a = acc[g0 + q];
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+      }
+    }
+  }
   float ss = 0.f;
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
-    const int c = (it * 32 + lane) * 4;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < C) {
-      for (int l = 0; l < L; ++l) {
-        const T* base = tok + l * sL + p * sP + c;
-        const float4 v00 = ld4(base + t.i00 * sN), v01 = ld4(base + t.i01 * sN);
-        const float4 v10 = ld4(base + t.i10 * sN), v11 = ld4(base + t.i11 * sN);
-        // same accumulation order as grid_sample: nw, ne, sw, se
-        float4 v;
-        v.x = v00.x * t.w00; v.x += v01.x * t.w01; v.x += v10.x * t.w10; v.x += v11.x * t.w11;
-        v.y = v00.y * t.w00; v.y += v01.y * t.w01; v.y += v10.y * t.w10; v.y += v11.y * t.w11;
-        v.z = v00.z * t.w00; v.z += v01.z * t.w01; v.z += v10.z * t.w10; v.z += v11.z * t.w11;
-        v.w = v00.w * t.w00; v.w += v01.w * t.w01; v.w += v10.w * t.w10; v.w += v11.w * t.w11;
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-      }
-      if (L > 1) { a.x *= invL; a.y *= invL; a.z *= invL; a.w *= invL; }
-      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-    }
-    acc[it] = a;
+    float4& a = acc[it];
+    if (L > 1) { a.x *= invL; a.y *= invL; a.z *= invL; a.w *= invL; }
+    ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
   }
   float inv = 1.f;
   if (normalize) {
@@ -259,6 +288,7 @@ bool launch_fwd_fast(const T* tok, int L, int64_t sL, int64_t sP, int64_t sN, co
   GD3_PROF("sample_fwd_fast", stream);
   if (nit <= 2) GD3_FWD_FAST(2);
   else if (nit <= 4) GD3_FWD_FAST(4);
+  else if (nit <= 6) GD3_FWD_FAST(6);
   else if (nit <= 8) GD3_FWD_FAST(8);
   else if (nit <= 16) GD3_FWD_FAST(16);
   else if (nit <= FAST_MAX_IT) GD3_FWD_FAST(32);
