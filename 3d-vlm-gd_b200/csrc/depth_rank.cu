@@ -673,13 +673,15 @@ __global__ void __launch_bounds__(256)
     const int k = k0 + r;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < K) {
+#pragma unroll 4
       for (int t = 0; t < TA; ++t) {
-        const float4 v = *reinterpret_cast<const float4*>(dub_part + (((int64_t)set * TA + t) * K + k) * H + 4 * lane);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dub_part + (((int64_t)set * TA + t) * K + k) * H + 4 * lane));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
       bsum[0] += acc.x; bsum[1] += acc.y; bsum[2] += acc.z; bsum[3] += acc.w;   // d b1 = sum over pairs of dh
+#pragma unroll 4
       for (int t = 0; t < TB; ++t) {
-        const float4 v = *reinterpret_cast<const float4*>(dua_part + (((int64_t)set * TB + t) * K + k) * H + 4 * lane);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dua_part + (((int64_t)set * TB + t) * K + k) * H + 4 * lane));
         acc.x -= v.x; acc.y -= v.y; acc.z -= v.z; acc.w -= v.w;
       }
       if (du_extra) {
