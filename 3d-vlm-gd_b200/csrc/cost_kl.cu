@@ -285,9 +285,10 @@ __global__ void __launch_bounds__(256)
     if (in_row) {
       const float tt = fmaxf(v[k] * ir, eps);
       T += tt;
-      A = fmaf(tt, __logf(tt), A);
+      A = fmaf(tt, __log2f(tt), A);      // in bits; converted to nats once per row below
     }
   }
+  A *= 0.69314718055994531f;
   T = warp_sum(T);
   A = warp_sum(A);
   if (lane == 0) {
