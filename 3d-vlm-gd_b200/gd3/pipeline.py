@@ -98,6 +98,34 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     return out
 
 
+class GraphedStep:
+    """CUDA-graph replay of ``distillation_step`` for a batch that lives in fixed device buffers.
+
+    The step is ~35 kernel launches and a dozen small torch fills / memsets; captured once, a replay issues them as
+    one graph launch (no per-launch gaps, no Python between kernels).  ``step = GraphedStep(batch, variant=...,
+    grid=...)``, then refresh the contents of ``batch``'s tensors in place and call ``step()``: it returns the same
+    dict of (static) output tensors every time.  Capture allocates the outputs and workspaces from the graph's
+    private pool, so the addresses baked into the TMA descriptors stay valid for every replay.
+    """
+
+    def __init__(self, batch, **step_kwargs):
+        self.batch = batch
+        self.kwargs = step_kwargs
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):      # lazy one-time settings (kernel attributes, allocator pools) happen outside the capture
+                distillation_step(batch, **step_kwargs)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = distillation_step(batch, **step_kwargs)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
 class DevicePrefetcher:
     """Double-buffered host -> device staging for batches that live in pinned host memory.
 

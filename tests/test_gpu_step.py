@@ -37,3 +37,30 @@ def test_distillation_step_vs_oracle(variant, cfg, dtype):
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_graphed_step_matches_eager():
+    """CUDA-graph replay of the fused step: same losses and gradients as the eager call, also after the inputs change."""
+    import bench_common
+    from gd3 import pipeline
+    cfg = dict(N=256, C=384, K=128, P=3, grid=(16, 16), variant='mast3r')
+    batch = bench_common.to_device(bench_common.make_batch(cfg, cfg_id=1), 'cuda', feature_dtype=torch.bfloat16)
+    eager = pipeline.distillation_step(batch, variant='mast3r', grid=cfg['grid'])
+    step = pipeline.GraphedStep(batch, variant='mast3r', grid=cfg['grid'])
+    out = step()
+    torch.cuda.synchronize()
+    for k in ('kl', 'ap', 'rank', 'l1'):
+        assert torch.allclose(out[k], eager[k], rtol=1e-5, atol=1e-7), k
+    for k in ('f1', 'g1', 'head'):
+        a, b = out['grads'][k].float(), eager['grads'][k].float()
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-6 * float(b.abs().max())), k
+    # new contents in the same buffers -> new results from the same graph
+    other = bench_common.to_device(bench_common.make_batch(cfg, cfg_id=1, pair0=7), 'cuda', feature_dtype=torch.bfloat16)
+    for k, v in other.items():
+        if torch.is_tensor(v):
+            batch[k].copy_(v)
+    want = pipeline.distillation_step(other, variant='mast3r', grid=cfg['grid'])
+    got = step()
+    torch.cuda.synchronize()
+    assert torch.allclose(got['kl'], want['kl'], rtol=1e-5) and torch.allclose(got['rank'], want['rank'], rtol=1e-5)
+    assert not torch.allclose(got['kl'], eager['kl'], rtol=1e-3)
