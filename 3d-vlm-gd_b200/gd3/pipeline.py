@@ -49,10 +49,6 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     dev = f1.device
     out = {}
 
-    # ---- dense cost-volume KL (K1) ----
-    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, batch['t12'], batch['t21'], batch['m1'], batch['m2'], variant,
-                                   grad_scale=w['kl'] * inv_p, want_grad=backward, pairs_per_group=pairs_per_group)
-
     # ---- keypoint descriptors / features from the token maps (K3) ----
     g1, g2 = batch['g1'], batch['g2']
     kp1 = batch['kp1'].to(_F32).contiguous()
@@ -70,16 +66,21 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     ops.sample_fwd_raw(g2, lay2, geom, kp2, False, out=kf[:, 1], out_strides=pstr)
     depths = torch.stack([batch['dep1'].to(_F32), batch['dep2'].to(_F32)], dim=1).reshape(2 * P, K)
 
-    # ---- Smooth-AP (K2) ----
-    ap, gd1, gd2 = ops.smooth_ap_raw(d1, d2, batch['p3d1'], batch['p3d2'], variant, temp, thr_neg,
-                                     grad_scale=w['ap'] * inv_p, want_grad=backward)
-
-    # ---- relative depth: ranking on both views + cross-view L1 (K4) ----
+    # ---- relative depth: ranking on both views + cross-view L1 (K4).  Issued first: its pair kernel runs for
+    #      milliseconds, during which the host enqueues the many short kernels of the other losses without gaps ----
     w_rank = torch.full((2 * P,), 0.5 * w['intra'] * inv_p, dtype=_F32, device=dev)
     w_l1 = torch.full((P,), w['depth'] * inv_p, dtype=_F32, device=dev)
     lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, C1_), depths, params,
                                               head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
                                               depth_threshold, 0.05, False, w_rank, w_l1, backward)
+
+    # ---- dense cost-volume KL (K1) ----
+    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, batch['t12'], batch['t21'], batch['m1'], batch['m2'], variant,
+                                   grad_scale=w['kl'] * inv_p, want_grad=backward, pairs_per_group=pairs_per_group)
+
+    # ---- Smooth-AP (K2) ----
+    ap, gd1, gd2 = ops.smooth_ap_raw(d1, d2, batch['p3d1'], batch['p3d2'], variant, temp, thr_neg,
+                                     grad_scale=w['ap'] * inv_p, want_grad=backward)
     rank = 0.5 * (lr[0::2] + lr[1::2])
     out.update(kl=kl, ap=ap, rank=rank, l1=l1)
     out['total'] = (w['ap'] * ap + w['depth'] * l1 + w['intra'] * rank + w['kl'] * kl).mean()

