@@ -352,7 +352,8 @@ def run_ours(args):
                     parallelism=f'dp{world} (pairs sharded, no data-path collective)',
                     l2='inputs larger than L2: %.0f MB of teacher volumes + features are read per step' % (in_bytes_dev / 1e6),
                     losses='cost-volume KL + Smooth-AP + depth ranking (2 views) + cross-view L1, fwd+bwd',
-                    launch_mode=graph_note, eager_ms_per_step=round(eager_ms_step, 4)),
+                    launch_mode=graph_note, eager_ms_per_step=round(eager_ms_step, 4),
+                    eager_note='eager launches with a CUDA-event pair around every kernel (source of the per-kernel shares)'),
         clocks=clocks,
         e2e=dict(value=round(world * P / (e2e_ms * 1e-3), 2), unit=UNIT, h2d_bytes_per_step=int(h2d_bytes),
                  d2h_bytes_per_step=int(d2h_bytes), ms_per_step=round(e2e_ms, 3), host_clock_ms_per_step=round(e2e_wall_ms, 3),
