@@ -714,9 +714,12 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 // operand preparation for the GEMMs
 // ------------------------------------------------------------------------------------------
-// epilogue: atomically accumulate alpha * acc into a single fp32 matrix shared by all batches (split-K)
+// epilogue: atomically accumulate acc into a single fp32 matrix shared by all batches (split-K).  The 32 x 32 chunk
+// goes through the per-warp shared tile so that every atomic instruction covers whole row segments: 8 lanes x
+// red.global.add.v4.f32 per row (4 rows per instruction) when the rows are 16-byte aligned, else one row of scalar
+// atomics per instruction.
 struct EpiAtomicAddF32 {
-  static constexpr int kScratchBytes = 0;
+  static constexpr int kScratchBytes = tc::kMaxEpiWarps * tc::kWarpTileBytes;
   struct Params {
     float* C;
     int M, N;
@@ -725,17 +728,37 @@ struct EpiAtomicAddF32 {
   struct Pre {};
   __device__ static void pre(const Params&, const tc::EpiCtx&, Pre&) {}
   __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre&) {
-    const int m = cx.m0 + cx.row;
+    float* t = reinterpret_cast<float*>(cx.scratch) + cx.epi_warp * tc::kWarpTileFloats;
+    const int lane = cx.lane;
+    const int m_warp = cx.m0 + (cx.row & ~31);
+    const int rows = p.M - m_warp;
+    const bool vec = (p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0);
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
       const int n = cx.n0 + c;
       if (n >= p.N) break;
       float v[32];
       tc::tmem_ld32(cx.tmem + c, v);
-      if (m < p.M) {
+      if (rows <= 0) continue;
 #pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (n + q < p.N && v[q] != 0.f) atomicAdd(p.C + (int64_t)m * p.ldc + n + q, v[q]);
+      for (int q = 0; q < 32; ++q) t[lane * 33 + q] = v[q];
+      __syncwarp();
+      float* cslab = p.C + (int64_t)m_warp * p.ldc + n;
+      if (vec && n + 32 <= p.N) {
+        const int sub = lane >> 3, c4 = 4 * (lane & 7);      // 4 rows per instruction, 8 lanes x float4 per row
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) {
+          const int rr = r + sub;
+          const float4 x = make_float4(t[rr * 33 + c4], t[rr * 33 + c4 + 1], t[rr * 33 + c4 + 2], t[rr * 33 + c4 + 3]);
+          if (rr < rows) atomicAdd(reinterpret_cast<float4*>(cslab + (int64_t)rr * p.ldc + c4), x);
+        }
+      } else {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const float x = t[r * 33 + lane];
+          if (r < rows && n + lane < p.N) atomicAdd(cslab + (int64_t)r * p.ldc + lane, x);
+        }
       }
+      __syncwarp();
     }
   }
 };
