@@ -589,7 +589,9 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 template <class OutT>
 struct EpiGradOut {
-  static constexpr int kScratchBytes = tc::kMaxEpiWarps * tc::kWarpTileBytes;
+  static constexpr bool kOut16 = sizeof(OutT) == 2;
+  static constexpr int kWarpBytes = kOut16 ? tc::kWarpTileBytes16 : tc::kWarpTileBytes;
+  static constexpr int kScratchBytes = tc::kMaxEpiWarps * kWarpBytes;
   struct Params {
     int N, C;
     const __nv_bfloat16* X;   // (G, N, ldc) normalised features of the image being differentiated
@@ -624,7 +626,7 @@ struct EpiGradOut {
     }
   }
   __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre& pr) {
-    float* t = reinterpret_cast<float*>(cx.scratch) + cx.epi_warp * tc::kWarpTileFloats;
+    uint8_t* t = cx.scratch + cx.epi_warp * kWarpBytes;
     const int i = cx.m0 + cx.row;
     const bool row_ok = i < p.N;
     const int m_warp = cx.m0 + (cx.row & ~31);
@@ -659,7 +661,10 @@ struct EpiGradOut {
           v[q] = (v[q] - xv * dot) * inv;
         }
       }
-      tc::warp_store_rows<OutT>(t, v, oslab + c0, p.C, rows, p.C - c0, cx.lane);
+      if constexpr (kOut16)
+        tc::warp_store_rows_bf16(reinterpret_cast<uint32_t*>(t), v, oslab + c0, p.C, rows, p.C - c0, cx.lane);
+      else
+        tc::warp_store_rows<OutT>(reinterpret_cast<float*>(t), v, oslab + c0, p.C, rows, p.C - c0, cx.lane);
     }
   }
 };
