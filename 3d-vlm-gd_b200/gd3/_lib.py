@@ -22,6 +22,7 @@ SYMBOLS = {
     'gd3_profile_read': (_sz, [_c.c_char_p, _sz]),
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    'gd3_kp_prepare': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _vp, _vp]),
     'gd3_teacher_volume_workspace': (_sz, [_i64, _i64, _i64]),
     'gd3_teacher_volume': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _sz, _vp]),
     'gd3_semantic_argmax_workspace': (_sz, [_i64, _i64, _i64]),
@@ -159,6 +160,30 @@ def fast_reciprocal_nn(pts1, pts2, seeds, max_iter=10, dist='dot', host_poll=Tru
                                          ptr(ws),
                                          ws.numel(), stream_ptr()))
     return xy1, xy2, conv.bool()
+
+
+def kp_prepare(kp, H, W, patch_size=None, depth=None, window=3):
+    """Patch masks and / or window depths for (P, K, 2) CUDA keypoints in one launch.
+
+    patch_size given -> bool (P, (H // p) * (W // p)) masks; depth given ((H, W) shared or (P, H, W)) -> (P, K) depths."""
+    require_cuda(kp)
+    lib = load()
+    kp = kp.to(torch.float32).contiguous()
+    P, K = kp.shape[0], kp.shape[1]
+    mask = None
+    if patch_size is not None:
+        mask = torch.empty(P, (H // patch_size) * (W // patch_size), dtype=torch.uint8, device=kp.device)
+    kd = None
+    stride = 0
+    if depth is not None:
+        depth = depth.to(torch.float32).contiguous()
+        assert depth.shape[-2:] == (H, W)
+        stride = 0 if depth.dim() == 2 else H * W
+        kd = torch.empty(P, K, dtype=torch.float32, device=kp.device)
+    with torch.cuda.device(kp.device):
+        check(lib.gd3_kp_prepare(ptr(kp), P, K, int(H), int(W), int(patch_size or 1), int(window), ptr(depth), stride,
+                                 ptr(mask), ptr(kd), stream_ptr()))
+    return (mask.bool() if mask is not None else None), kd
 
 
 def teacher_volume(tgt_camap, src_camap=None, temperature=3.0, reciprocity=True, plain_mean=False):

@@ -1,12 +1,13 @@
 """CUDA drop-in for the hot-path subset of the reference's ``utils/functions.py``.
 
-Same names, argument order, defaults and return shapes.  The heavy functions run hand-written
-kernels through lib3dgd.so; tiny index helpers are expressed with device-side torch indexing
-("negligible; ... or leave in torch").
+Same names, argument order, defaults and return shapes.  Sampling, the keypoint patch mask and the keypoint depth run
+hand-written kernels through lib3dgd.so; ``sigmoid`` / ``get_masked_patch_cost`` / ``filter_kp_by_conf`` are kept for
+callers that still hold materialised tensors and are plain device-side torch expressions (SURVEY.md section 8, row
+a7: "negligible; ... or leave in torch").
 """
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from .._lib import require_cuda
 
 
@@ -27,33 +28,21 @@ def interpolate_features(descriptors, pts, h, w, normalize=True, patch_size=14, 
 
 
 def get_patch_mask_from_kp_tensor(kp_xy, H, W, patch_size, device=None):
-    """``utils/functions.py:375-399``: (K, 2) pixel keypoints -> bool (num_patches,)."""
-    if device is None:
-        device = kp_xy.device
-    ph, pw = H // patch_size, W // patch_size
-    mask = torch.zeros(ph * pw, dtype=torch.bool, device=device)
-    x, y = kp_xy[:, 0], kp_xy[:, 1]
-    inside = (x >= 0) & (x < W) & (y >= 0) & (y < H)
-    idx = (y.long() // patch_size) * pw + (x.long() // patch_size)
-    idx = torch.where(inside, idx, torch.zeros_like(idx))
-    # scatter without a host sync: out-of-image keypoints contribute False
-    mask.index_put_((idx.to(device),), inside.to(device), accumulate=True)
-    return mask
+    """``utils/functions.py:375-399``: (K, 2) pixel keypoints -> bool (num_patches,).  One kernel launch, no host sync."""
+    require_cuda(kp_xy)
+    mask, _ = _lib.kp_prepare(kp_xy[None], int(H), int(W), patch_size=int(patch_size))
+    mask = mask[0]
+    return mask if device is None else mask.to(device)
 
 
 def extract_kp_depth(depth_map, kp, window_size=3):
     """``utils/functions.py:348-372``: mean depth in a replicate-padded window at integer keypoints -> (B, K)."""
     if not torch.is_tensor(depth_map):
         depth_map = torch.tensor(depth_map, device=kp.device, dtype=torch.float)
+    require_cuda(depth_map, kp)
     H, W = depth_map.shape[-2:]
-    half = window_size // 2
-    x = kp[..., 0].long()
-    y = kp[..., 1].long()
-    acc = torch.zeros(kp.shape[:2], dtype=depth_map.dtype, device=kp.device)
-    for dy in range(-half, half + 1):
-        for dx in range(-half, half + 1):
-            acc = acc + depth_map[(y + dy).clamp(0, H - 1), (x + dx).clamp(0, W - 1)]
-    return acc / float(window_size * window_size)
+    _, kd = _lib.kp_prepare(kp, int(H), int(W), depth=depth_map, window=int(window_size))
+    return kd.to(depth_map.dtype)
 
 
 def get_masked_patch_cost(cost, mask_patch_1, mask_patch_2=None, eps=1e-8, use_softmax=False, temperature=1.0):

@@ -215,6 +215,19 @@ int gd3_semantic_argmax(const float* kp_desc, int64_t kd_stride_k, int64_t kd_st
                         int64_t* nn_idx, float* nn_val, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Keypoint-side inputs of the losses, batched over P pairs (one launch instead of a dozen torch
+ * ops per pair).  Replaces get_patch_mask_from_kp_tensor (utils/functions.py:375-399) and
+ * extract_kp_depth (utils/functions.py:348-372).
+ *   kp        (P, K, 2) fp32 pixel keypoints (x, y)
+ *   mask      (P, (H / patch) * (W / patch)) uint8 out, or NULL: patches containing >= 1 in-image keypoint
+ *   depth     fp32 depth maps (H, W) per pair (depth_pair_stride elements apart; 0 = one shared map)
+ *   kp_depth  (P, K) fp32 out, or NULL: mean of the replicate-padded window x window neighbourhood
+ *             at the truncated keypoint
+ * ------------------------------------------------------------------------------------------ */
+int gd3_kp_prepare(const float* kp, int64_t P, int64_t K, int64_t H, int64_t W, int patch, int window, const float* depth,
+                   int64_t depth_pair_stride, uint8_t* mask, float* kp_depth, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * MASt3R teacher cost-volume post-processing, fused.  Replaces
  * dust3r/dust3r/model.py:346-366: per decoder layer, head-mean of both branches' pre-softmax
  * cross-attention logits (dust3r/croco/models/blocks.py:163-164), symmetrisation with the

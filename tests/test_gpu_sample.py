@@ -90,3 +90,28 @@ def test_small_helpers_golden(golden):
     np.testing.assert_allclose(fn.get_masked_patch_cost(cost, m1, m2).cpu().numpy(), g['mpc/rownorm_m2'], rtol=1e-6)
     _, idx = fn.filter_kp_by_conf(T(g['conf/kp']).cuda(), T(g['conf/mask']).cuda())
     assert (idx.cpu().numpy() == g['conf/idx']).all()
+
+
+def test_kp_prepare_batched_matches_oracle():
+    """gd3_kp_prepare over several pairs at once against the per-pair oracle helpers, incl. border and outside keypoints."""
+    from gd3 import _lib
+    from oracle import functions as ofn
+    g = torch.Generator().manual_seed(12)
+    P, K, H, W, p = 5, 200, 168, 224, 14
+    kp = torch.stack([torch.randint(-20, W + 20, (P, K), generator=g), torch.randint(-20, H + 20, (P, K), generator=g)], -1).float()
+    kp[0, :4] = torch.tensor([[0., 0.], [W - 1., H - 1.], [W, 5.], [5., H]])
+    depth = torch.rand(P, H, W, generator=g) * 5
+    mask, kd = _lib.kp_prepare(kp.cuda(), H, W, patch_size=p, depth=depth.cuda(), window=3)
+    inside = kp.clone()
+    inside[..., 0].clamp_(0, W - 1)
+    inside[..., 1].clamp_(0, H - 1)
+    _, kd_in = _lib.kp_prepare(inside.cuda(), H, W, depth=depth.cuda(), window=3)
+    for i in range(P):
+        assert (mask[i].cpu() == ofn.get_patch_mask_from_kp_tensor(kp[i], H, W, p)).all(), i
+        want = ofn.extract_kp_depth(depth[i], inside[i:i + 1])
+        assert torch.allclose(kd_in[i:i + 1].cpu(), want, rtol=1e-6, atol=1e-6), i
+    # one depth map shared by all pairs (stride 0) and a 5 x 5 window
+    _, kd5 = _lib.kp_prepare(inside.cuda(), H, W, depth=depth[0].cuda(), window=5)
+    for i in range(P):      # the reference (and the oracle) gather one pair at a time
+        want5 = ofn.extract_kp_depth(depth[0], inside[i:i + 1], window_size=5)
+        assert torch.allclose(kd5[i:i + 1].cpu(), want5, rtol=1e-6, atol=1e-6), i
