@@ -74,6 +74,26 @@ inline int num_sms() {
   return n;
 }
 
+// Opt-in dynamic shared memory of one kernel.  cudaFuncSetAttribute is per device and the size may grow between calls,
+// so remember the largest size configured on each device (one static instance per kernel at the launch site).
+struct SmemOptIn {
+  static constexpr int kMaxDevices = 64;
+  size_t bytes[kMaxDevices] = {};
+  template <class Kernel>
+  cudaError_t ensure(Kernel kernel, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool tracked = dev >= 0 && dev < kMaxDevices;
+    if (tracked && bytes[dev] >= smem) return cudaSuccess;
+    if (smem > 48 * 1024 || !tracked) {
+      const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    if (tracked) bytes[dev] = smem;
+    return cudaSuccess;
+  }
+};
+
 template <class T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 template <class T>

@@ -952,21 +952,15 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 1 + 3);
     dim3 grid((unsigned)w.TA, (unsigned)w.TB, (unsigned)S);
     if (backward) {
-      static bool cfg = false;
-      if (!cfg) {
-        GD3_CHECK_CUDA(cudaFuncSetAttribute(rank_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
-      }
+      static SmemOptIn opt;
+      GD3_CHECK_CUDA(opt.ensure(rank_pairs<true>, smem));
       {
         GD3_PROF("rank_pairs", stream);
         rank_pairs<true><<<grid, WARPS * 32, smem, stream>>>(rp);
       }
     } else {
-      static bool cfg = false;
-      if (!cfg) {
-        GD3_CHECK_CUDA(cudaFuncSetAttribute(rank_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
-      }
+      static SmemOptIn opt;
+      GD3_CHECK_CUDA(opt.ensure(rank_pairs<false>, smem));
       {
         GD3_PROF("rank_pairs", stream);
         rank_pairs<false><<<grid, WARPS * 32, smem, stream>>>(rp);

@@ -183,11 +183,8 @@ int gd3_semantic_argmax(const float* kp_desc, int64_t kd_stride_k, int64_t kd_st
   {
     const size_t smem = sizeof(float) * C * KB;
     GD3_REQUIRE(smem <= 200 * 1024, "gd3_semantic_argmax: C=%lld too large", (long long)C);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(ea_lowres_sim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    static SmemOptIn opt;
+    GD3_CHECK_CUDA(opt.ensure(ea_lowres_sim, smem));
     dim3 grid((unsigned)ceil_div(P, 128), (unsigned)ceil_div<int64_t>(K, KB));
     GD3_PROF("ea_lowres_sim", stream);
     ea_lowres_sim<<<grid, 128, smem, stream>>>(kp_desc, kd_stride_k, kd_stride_c, desc2, (int)K, (int)C, P, w.S);
@@ -197,11 +194,8 @@ int gd3_semantic_argmax(const float* kp_desc, int64_t kd_stride_k, int64_t kd_st
   {
     const size_t smem = sizeof(float) * (P + 4 * img_size);
     GD3_REQUIRE(smem <= 200 * 1024, "gd3_semantic_argmax: patch grid too large");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(ea_upsample_argmax, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    static SmemOptIn opt;
+    GD3_CHECK_CUDA(opt.ensure(ea_upsample_argmax, smem));
     int chunks = (int)ceil_div<int64_t>(4 * num_sms(), K);
     chunks = chunks < 1 ? 1 : chunks;
     dim3 grid((unsigned)chunks, (unsigned)K);

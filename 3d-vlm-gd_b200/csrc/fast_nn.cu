@@ -540,15 +540,11 @@ int nn_search(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t 
   dim3 grid(q_tiles, y);
   const size_t smem = nn_smem_bytes(both);
   {
-    static bool configured = false;
-    if (!configured) {
-      const int big = (int)nn_smem_bytes(true), small = (int)nn_smem_bytes(false);
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, small));
-      configured = true;
-    }
+    static SmemOptIn opt[4];
+    GD3_CHECK_CUDA(opt[0].ensure(nn_tile_kernel<0, true>, nn_smem_bytes(true)));
+    GD3_CHECK_CUDA(opt[1].ensure(nn_tile_kernel<1, true>, nn_smem_bytes(true)));
+    GD3_CHECK_CUDA(opt[2].ensure(nn_tile_kernel<0, false>, nn_smem_bytes(false)));
+    GD3_CHECK_CUDA(opt[3].ensure(nn_tile_kernel<1, false>, nn_smem_bytes(false)));
   }
   {
     GD3_PROF("nn_tile_kernel", stream);
@@ -598,12 +594,9 @@ int nn_query_dev(const float* Q, int nq_lo, int nq_max, const int* nq_dev, const
     y = ceil_div(db_tiles, tiles_per_cta);
     dim3 grid(q_tiles, y);
     const size_t smem = nn_smem_bytes(false);
-    static bool configured = false;
-    if (!configured) {
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      GD3_CHECK_CUDA(cudaFuncSetAttribute(nn_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
+    static SmemOptIn opt[2];
+    GD3_CHECK_CUDA(opt[0].ensure(nn_tile_kernel<0, false>, smem));
+    GD3_CHECK_CUDA(opt[1].ensure(nn_tile_kernel<1, false>, smem));
     GD3_PROF("nn_tile_kernel", stream);
     if (dist == 0)
       nn_tile_kernel<0, false><<<grid, THREADS, smem, stream>>>(Q, 0, DB, (int)ndb, (int)D, tiles_per_cta, keys, nullptr,

@@ -617,11 +617,8 @@ int launch_gemm(const char* name, const CUtensorMap& tmA, const CUtensorMap& tmB
   auto kern = tc_gemm_kernel<BN, EPI_WARPS, Epi, A_MN, B_MN, GROUPED>;
   constexpr int SMEM = smem_bytes(BN, Epi::kScratchBytes);
   static_assert(SMEM <= 227 * 1024, "tc_gemm shared memory budget");
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    GD3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
+  static SmemOptIn opt;   // per instantiation
+  GD3_CHECK_CUDA(opt.ensure(kern, SMEM));
   const int tiles_m = ceil_div(s.M, BM), tiles_n = ceil_div(s.N, BN);
   const long long total = 1LL * tiles_m * tiles_n * s.batch;
   int grid = num_sms();
@@ -646,11 +643,8 @@ int launch_gemm_2sm(const char* name, const CUtensorMap& tmA, const CUtensorMap&
   auto kern = tc_gemm2_kernel<BN, EPI_WARPS, Epi>;
   constexpr int SMEM = smem_bytes_2sm(BN, Epi::kScratchBytes);
   static_assert(SMEM <= 227 * 1024, "tc_gemm2 shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    GD3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
+  static SmemOptIn opt;
+  GD3_CHECK_CUDA(opt.ensure(kern, SMEM));
   const int tiles_m = ceil_div(s.M, 2 * BM), tiles_n = ceil_div(s.N, BN);
   const long long total = 1LL * tiles_m * tiles_n * s.batch;
   int clusters = num_sms() / 2;

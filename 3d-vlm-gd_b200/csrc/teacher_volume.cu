@@ -221,15 +221,11 @@ int gd3_teacher_volume(const float* const* tgt_layers, const float* const* src_l
   const size_t smem = sizeof(float) * rows * ldt;
   GD3_REQUIRE(smem <= 227 * 1024, "gd3_teacher_volume: N=%lld too large for the shared row tile", (long long)N);
   {
-    static size_t configured32 = 0, configured16 = 0;
-    size_t& configured = rows == 32 ? configured32 : configured16;
-    if (smem > 48 * 1024 && smem > configured) {
-      if (rows == 32)
-        GD3_CHECK_CUDA(cudaFuncSetAttribute(tv_layer_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      else
-        GD3_CHECK_CUDA(cudaFuncSetAttribute(tv_layer_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    static SmemOptIn opt32, opt16;
+    if (rows == 32)
+      GD3_CHECK_CUDA(opt32.ensure(tv_layer_rows<32>, smem));
+    else
+      GD3_CHECK_CUDA(opt16.ensure(tv_layer_rows<16>, smem));
     dim3 grid((unsigned)ceil_div<int64_t>(N, rows), (unsigned)L, (unsigned)B);
     GD3_PROF("tv_layer_rows", stream);
     if (rows == 32)

@@ -23,6 +23,8 @@ SYMBOLS = {
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     'gd3_kp_prepare': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _vp, _vp]),
+    'gd3_point_cloud_to_depth_workspace': (_sz, [_i64, _i64, _i64]),
+    'gd3_point_cloud_to_depth': (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     'gd3_teacher_volume_workspace': (_sz, [_i64, _i64, _i64]),
     'gd3_teacher_volume': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _sz, _vp]),
     'gd3_semantic_argmax_workspace': (_sz, [_i64, _i64, _i64]),
@@ -184,6 +186,24 @@ def kp_prepare(kp, H, W, patch_size=None, depth=None, window=3):
         check(lib.gd3_kp_prepare(ptr(kp), P, K, int(H), int(W), int(patch_size or 1), int(window), ptr(depth), stride,
                                  ptr(mask), ptr(kd), stream_ptr()))
     return (mask.bool() if mask is not None else None), kd
+
+
+def point_cloud_to_depth(points, intrinsics, w, h):
+    """(B, M, 3) CUDA camera-frame points + (3, 3) or (B, 3, 3) intrinsics -> (B, h, w) fp32 mean-z depth images."""
+    require_cuda(points, intrinsics)
+    lib = load()
+    points = points.to(torch.float32).contiguous()
+    intrinsics = intrinsics.to(torch.float32).contiguous()
+    B, M = points.shape[0], points.shape[1]
+    assert points.shape[2] == 3 and intrinsics.shape[-2:] == (3, 3)
+    assert intrinsics.dim() == 2 or intrinsics.shape[0] == B
+    depth = torch.empty(B, int(h), int(w), dtype=torch.float32, device=points.device)
+    nbytes = lib.gd3_point_cloud_to_depth_workspace(B, int(h), int(w))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
+    with torch.cuda.device(points.device):
+        check(lib.gd3_point_cloud_to_depth(ptr(points), B, M, ptr(intrinsics), 0 if intrinsics.dim() == 2 else 9,
+                                           int(w), int(h), ptr(depth), ptr(ws), ws.numel(), stream_ptr()))
+    return depth
 
 
 def teacher_volume(tgt_camap, src_camap=None, temperature=3.0, reciprocity=True, plain_mean=False):

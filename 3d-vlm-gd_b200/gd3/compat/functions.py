@@ -1,7 +1,7 @@
 """CUDA drop-in for the hot-path subset of the reference's ``utils/functions.py``.
 
 Same names, argument order, defaults and return shapes.  Sampling, the keypoint patch mask and the keypoint depth run
-hand-written kernels through lib3dgd.so; ``sigmoid`` / ``get_masked_patch_cost`` / ``filter_kp_by_conf`` are kept for
+hand-written kernels through lib3dgd.so, and so does ``point_cloud_to_depth``; ``sigmoid`` / ``get_masked_patch_cost`` / ``filter_kp_by_conf`` are kept for
 callers that still hold materialised tensors and are plain device-side torch expressions (SURVEY.md section 8, row
 a7: "negligible; ... or leave in torch").
 """
@@ -64,3 +64,13 @@ def filter_kp_by_conf(kp, conf_mask):
     valid = conf_mask[xy[:, 1].round().long(), xy[:, 0].round().long()]
     idx = valid.nonzero(as_tuple=False).squeeze(1)
     return kp[:, idx, :], idx
+
+
+def point_cloud_to_depth(points, K, w, h, device):
+    """``utils/functions.py:218-260``: (N, 3) camera-frame points + (3, 3) intrinsics -> (1, 1, h, w) fp32 depth image
+    (mean z per pixel, 0 where no point lands).  A (B, N, 3) batch gives (B, 1, h, w)."""
+    require_cuda(points)
+    batched = points.dim() == 3
+    pts = points if batched else points[None]
+    depth = _lib.point_cloud_to_depth(pts, torch.as_tensor(K, dtype=torch.float32, device=points.device), int(w), int(h))
+    return depth[:, None].to(device)

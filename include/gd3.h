@@ -228,6 +228,20 @@ int gd3_kp_prepare(const float* kp, int64_t P, int64_t K, int64_t H, int64_t W, 
                    int64_t depth_pair_stride, uint8_t* mask, float* kp_depth, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Point map -> depth image, batched.  Replaces point_cloud_to_depth
+ * (utils/functions.py:218-260; called per image at src/finetune_timm_mast3r.py:627-633): points
+ * with z > 0 are projected with the pinhole intrinsics, rounded half-to-even to a pixel, dropped
+ * when outside the image, and every pixel gets the mean z of the points that landed on it (0 if
+ * none).
+ *   points      (B, M, 3) fp32 camera-frame points
+ *   intrinsics  (3, 3) fp32 row-major DEVICE matrices, intr_stride elements apart (0 = one shared)
+ *   depth       (B, h, w) fp32 out
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_point_cloud_to_depth_workspace(int64_t B, int64_t h, int64_t w);
+int gd3_point_cloud_to_depth(const float* points, int64_t B, int64_t M, const float* intrinsics, int64_t intr_stride,
+                             int64_t w, int64_t h, float* depth, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * MASt3R teacher cost-volume post-processing, fused.  Replaces
  * dust3r/dust3r/model.py:346-366: per decoder layer, head-mean of both branches' pre-softmax
  * cross-attention logits (dust3r/croco/models/blocks.py:163-164), symmetrisation with the

@@ -119,3 +119,28 @@ def filter_kp_by_conf(kp, conf_mask):
     yi = xy[:, 1].round().long()
     idx = conf_mask[yi, xi].nonzero(as_tuple=False).squeeze(1)
     return kp[:, idx, :], idx
+
+
+def point_cloud_to_depth(points, K, w, h, device=None):
+    """Pinhole splat of camera-frame points into a (1, 1, h, w) depth image, averaging the depths that land on the
+    same pixel.  Follows ``utils/functions.py:218-260``.
+
+    Only points in front of the camera (z > 0) count; the pixel is round-half-even of (x / z) * fx + cx (three
+    separately rounded fp32 operations, no fused multiply-add), points outside the image are dropped, empty
+    pixels stay 0.
+    """
+    pts = points.to(torch.float32)
+    K = K.to(torch.float32)
+    sums = torch.zeros(h * w, dtype=torch.float32)
+    hits = torch.zeros(h * w, dtype=torch.float32)
+    front = pts[pts[:, 2] > 0]
+    if len(front):
+        z = front[:, 2]
+        col = torch.round((front[:, 0] / z) * K[0, 0] + K[0, 2]).long()
+        row = torch.round((front[:, 1] / z) * K[1, 1] + K[1, 2]).long()
+        inside = (col >= 0) & (col < w) & (row >= 0) & (row < h)
+        pix = (row * w + col)[inside]
+        sums.index_add_(0, pix, z[inside])
+        hits.index_add_(0, pix, torch.ones_like(z[inside]))
+    depth = torch.where(hits > 0, sums / hits.clamp_min(1), torch.zeros(()))
+    return depth.view(1, 1, h, w)

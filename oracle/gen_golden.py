@@ -11,6 +11,7 @@ What is executed from the reference, unmodified:
   utils.model.DepthAwareFeatureFusion
   mast3r.fast_nn.{bruteforce_reciprocal_nns, fast_reciprocal_NNs, merge_corres}
   mast3r.losses.InfoNCE
+  utils.functions.point_cloud_to_depth            (--depth-splat)
 ``utils.functions`` imports kornia at module top (used only by an unrelated depth
 filter); empty stub modules are registered for it.  The LightningModules cannot be
 imported (timm / lightning / hydra absent), so the few lines of glue inside
@@ -358,8 +359,23 @@ def fast_nn_extra():
     np.savez_compressed(os.path.join(OUT, 'fast_nn_extra.npz'), **out)
 
 
+def depth_splat():
+    """``point_cloud_to_depth`` (``utils/functions.py:218-260``) from the live reference -> ``tests/golden/depth_splat.npz``."""
+    from oracle import synth
+    _, RF, _, _ = import_reference()
+    out = {}
+    for name, (pts, K, w, h) in synth.depth_splat_cases().items():
+        ref = RF.point_cloud_to_depth(pts, K, w, h, 'cpu')
+        out[f'{name}/pts'], out[f'{name}/K'], out[f'{name}/wh'] = _np(pts), _np(K), np.array([w, h])
+        out[f'{name}/depth'] = _np(ref)
+        print('point_cloud_to_depth', name, tuple(ref.shape), 'filled', int((ref > 0).sum()))
+    np.savez_compressed(os.path.join(OUT, 'depth_splat.npz'), **out)
+
+
 if __name__ == '__main__':
     if '--fast-nn-extra' in sys.argv:
         fast_nn_extra()
+    elif '--depth-splat' in sys.argv:
+        depth_splat()
     else:
         main()

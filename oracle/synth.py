@@ -205,3 +205,40 @@ def nn_desc_maps(seed, H, W, dim=24, noise=0.15):
     d2 = torch.roll(base, shifts=(3, -5), dims=(0, 1)) + noise * torch.randn(H, W, dim, generator=g)
     d2 = torch.nn.functional.normalize(d2, dim=-1)
     return d1.contiguous(), d2.contiguous()
+
+
+def point_map(seed, h, w, fx, fy, cx, cy, oversample=1.15, noise=0.004, behind=0.02):
+    """A camera-frame point map like the teacher's ``pts3d``: one point per pixel of a slightly denser grid than the
+    target image (so that several points can land on one pixel and some pixels stay empty), smooth depth in
+    [0.8, 4], a little lateral noise, and a fraction of points pushed behind the camera."""
+    g = torch.Generator().manual_seed(seed)
+    hh, ww = int(h * oversample), int(w * oversample)
+    v, u = torch.meshgrid(torch.linspace(-3, h + 2, hh), torch.linspace(-3, w + 2, ww), indexing='ij')
+    z = 2.4 + 1.6 * torch.sin(u / 9.0) * torch.cos(v / 7.0)
+    x = (u - cx) / fx * z + noise * torch.randn(hh, ww, generator=g)
+    y = (v - cy) / fy * z + noise * torch.randn(hh, ww, generator=g)
+    pts = torch.stack([x, y, z], dim=-1).reshape(-1, 3)
+    flip = torch.rand(len(pts), generator=g) < behind
+    pts[flip, 2] = -pts[flip, 2]
+    pts[::97, 2] = 0.0
+    return pts.float().contiguous()
+
+
+def depth_splat_cases():
+    """name -> (points (M, 3), K (3, 3), w, h) for ``point_cloud_to_depth``."""
+    def intr(fx, fy, cx, cy):
+        return torch.tensor([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], dtype=torch.float32)
+
+    cases = {}
+    cases['scene'] = (point_map(71, 48, 64, 60.0, 58.0, 31.5, 23.5), intr(60.0, 58.0, 31.5, 23.5), 64, 48)
+    g = torch.Generator().manual_seed(72)
+    sparse = torch.rand(500, 3, generator=g) * torch.tensor([2.0, 1.5, 3.0]) + torch.tensor([-1.0, -0.75, 0.5])
+    cases['sparse'] = (sparse.float(), intr(40.0, 40.0, 20.0, 15.0), 40, 30)
+    cases['none'] = (torch.cat([sparse[:50, :2], -sparse[:50, 2:]], dim=1).float(), intr(40.0, 40.0, 20.0, 15.0), 40, 30)
+    # projections that fall exactly on k + 0.5 (z = 1, power-of-two focal): round-half-even decides the pixel
+    k = torch.arange(-2, 18, dtype=torch.float32)
+    xs, ys = torch.meshgrid(k / 64.0, k / 64.0, indexing='xy')
+    half = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(xs.numel())], dim=1)
+    half[:, 2] += 0.0
+    cases['halfpix'] = (half.float(), intr(64.0, 64.0, 0.5, 0.5), 16, 16)
+    return cases

@@ -179,3 +179,15 @@ def test_extract_correspondences_nonsym_golden(golden):
                                                                 pixel_tol=tol)
         assert (xy1.numpy() == g[f'{tag}/xy1']).all() and (xy2.numpy() == g[f'{tag}/xy2']).all()
         assert np.array_equal(conf.numpy(), g[f'{tag}/conf'])
+
+
+def test_point_cloud_to_depth_oracle(golden):
+    """Oracle restatement of ``point_cloud_to_depth`` against the live reference's outputs (row f4)."""
+    g = golden('depth_splat.npz')
+    for name in ('scene', 'sparse', 'none', 'halfpix'):
+        w, h = (int(v) for v in g[f'{name}/wh'])
+        out = functions.point_cloud_to_depth(T(g[f'{name}/pts']), T(g[f'{name}/K']), w, h)
+        ref = g[f'{name}/depth']
+        assert out.shape == ref.shape
+        assert ((out.numpy() > 0) == (ref > 0)).all(), name          # same pixels hit: the rounding is bit-exact
+        np.testing.assert_allclose(out.numpy(), ref, rtol=1e-6, atol=0, err_msg=name)
