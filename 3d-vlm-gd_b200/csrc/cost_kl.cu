@@ -420,19 +420,25 @@ struct TeacherView {
   const float *ir12, *ir21;         // 1 / row sum (0 for masked rows), already offset to the pair
   const float *e12, *e21;           // eps of kept rows (0 for masked rows)
 };
+// Four teacher values of one thread.  Aligned rows (VEC): columns col .. col + 3 as one 128-bit load.  Ragged rows
+// (N % 4 != 0, e.g. 37^2): columns col, col + 16, col + 32, col + 48, so that the 16 lanes of a row read 64 contiguous
+// bytes per instruction instead of 16-byte-strided words.
 template <bool VEC>
 __device__ __forceinline__ float4 teacher_ld4(const float* src, int col, int N) {
   if (VEC) return __ldg(reinterpret_cast<const float4*>(src));
   float4 v;
   v.x = __ldg(src);
-  v.y = (col + 1 < N) ? __ldg(src + 1) : 0.f;
-  v.z = (col + 2 < N) ? __ldg(src + 2) : 0.f;
-  v.w = (col + 3 < N) ? __ldg(src + 3) : 0.f;
+  v.y = (col + 16 < N) ? __ldg(src + 16) : 0.f;
+  v.z = (col + 32 < N) ? __ldg(src + 32) : 0.f;
+  v.w = (col + 48 < N) ? __ldg(src + 48) : 0.f;
   return v;
 }
 template <bool VEC>
 __device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& tv, int N, int i0, int j0) {
-  const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
+  const int tr = threadIdx.x >> 4;
+  // tile column of a thread's element q: tc + q * cs
+  const int tc = VEC ? (threadIdx.x & 15) * 4 : (threadIdx.x & 15);
+  constexpr int cs = VEC ? 1 : 16;
   // all eight teacher loads of a thread (and their row factors) are issued before the first use
   float4 v12[4], v21[4];
   float ir12[4], ee12[4], ir21[4], ee21[4];
@@ -455,9 +461,9 @@ __device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& 
     const int r = ps * 16 + tr;
     const float ir = ir12[ps], ee = ee12[ps];
     ws[tc][r] = fmaxf(v12[ps].x * ir, ee);
-    ws[tc + 1][r] = fmaxf(v12[ps].y * ir, ee);
-    ws[tc + 2][r] = fmaxf(v12[ps].z * ir, ee);
-    ws[tc + 3][r] = fmaxf(v12[ps].w * ir, ee);
+    ws[tc + cs][r] = fmaxf(v12[ps].y * ir, ee);
+    ws[tc + 2 * cs][r] = fmaxf(v12[ps].z * ir, ee);
+    ws[tc + 3 * cs][r] = fmaxf(v12[ps].w * ir, ee);
   }
   __syncthreads();
 #pragma unroll
@@ -465,9 +471,9 @@ __device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& 
     const int r = ps * 16 + tr;
     const float ir = ir21[ps], ee = ee21[ps];
     ws[r][tc] += fmaxf(v21[ps].x * ir, ee);
-    ws[r][tc + 1] += fmaxf(v21[ps].y * ir, ee);
-    ws[r][tc + 2] += fmaxf(v21[ps].z * ir, ee);
-    ws[r][tc + 3] += fmaxf(v21[ps].w * ir, ee);
+    ws[r][tc + cs] += fmaxf(v21[ps].y * ir, ee);
+    ws[r][tc + 2 * cs] += fmaxf(v21[ps].z * ir, ee);
+    ws[r][tc + 3 * cs] += fmaxf(v21[ps].w * ir, ee);
   }
   __syncthreads();
 }
