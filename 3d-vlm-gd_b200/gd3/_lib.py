@@ -25,6 +25,9 @@ SYMBOLS = {
     'gd3_kp_prepare': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _vp, _vp]),
     'gd3_point_cloud_to_depth_workspace': (_sz, [_i64, _i64, _i64]),
     'gd3_point_cloud_to_depth': (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    'gd3_vggt_attn_workspace': (_sz, [_i64, _i64, _i64]),
+    'gd3_vggt_attn_accumulate': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _int, _f32, _int, _vp, _vp, _vp, _sz,
+                                        _vp]),
     'gd3_teacher_volume_workspace': (_sz, [_i64, _i64, _i64]),
     'gd3_teacher_volume': (_int, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _int, _vp, _vp, _sz, _vp]),
     'gd3_semantic_argmax_workspace': (_sz, [_i64, _i64, _i64]),
@@ -204,6 +207,39 @@ def point_cloud_to_depth(points, intrinsics, w, h):
         check(lib.gd3_point_cloud_to_depth(ptr(points), B, M, ptr(intrinsics), 0 if intrinsics.dim() == 2 else 9,
                                            int(w), int(h), ptr(depth), ptr(ws), ws.numel(), stream_ptr()))
     return depth
+
+
+def vggt_attn_accumulate(q_scaled, k, temperature=1.0, weight=1.0, out=None, skip=5, round_bf16=True):
+    """One VGGT global block: (B, heads, n_tokens, head_dim) bf16 CUDA q * scale and k -> head-mean cross-view attention
+    maps (attn12, attn21), each (B, n, n) fp32 with n = n_tokens // 2 - skip.  ``out=(attn12, attn21)`` adds
+    ``weight`` x this block to existing maps."""
+    require_cuda(q_scaled, k)
+    lib = load()
+    if q_scaled.dtype != torch.bfloat16 or k.dtype != torch.bfloat16:
+        raise ValueError('vggt_attn_accumulate: q and k must be bfloat16 (the teacher runs under bf16 autocast)')
+    if q_scaled.dim() != 4 or q_scaled.shape != k.shape:
+        raise ValueError(f'vggt_attn_accumulate: q / k must both be (B, heads, tokens, head_dim), got '
+                         f'{tuple(q_scaled.shape)} {tuple(k.shape)}')
+    q_scaled, k = q_scaled.contiguous(), k.contiguous()
+    B, heads, T, dh = q_scaled.shape
+    n = T // 2 - int(skip)
+    if n <= 0:
+        raise ValueError(f'vggt_attn_accumulate: no patch tokens left ({T} tokens, skip {skip})')
+    if out is None:
+        a12 = torch.empty(B, n, n, dtype=torch.float32, device=q_scaled.device)
+        a21 = torch.empty(B, n, n, dtype=torch.float32, device=q_scaled.device)
+        accumulate = 0
+    else:
+        a12, a21 = out
+        assert a12.shape == a21.shape == (B, n, n) and a12.is_contiguous() and a21.is_contiguous()
+        assert a12.dtype == a21.dtype == torch.float32
+        accumulate = 1
+    ws = workspace(lib.gd3_vggt_attn_workspace(B, heads, max(n, 0)), q_scaled.device)
+    with torch.cuda.device(q_scaled.device):
+        check(lib.gd3_vggt_attn_accumulate(ptr(q_scaled), ptr(k), B, heads, T, dh, int(skip), float(temperature),
+                                           int(bool(round_bf16)), float(weight), accumulate, ptr(a12), ptr(a21), ptr(ws),
+                                           ws.numel(), stream_ptr()))
+    return a12, a21
 
 
 def teacher_volume(tgt_camap, src_camap=None, temperature=3.0, reciprocity=True, plain_mean=False):

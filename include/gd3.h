@@ -228,6 +228,28 @@ int gd3_kp_prepare(const float* kp, int64_t P, int64_t K, int64_t H, int64_t W, 
                    int64_t depth_pair_stride, uint8_t* mask, float* kp_depth, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * VGGT teacher cost volumes, one call per global-attention block (VGGT half).
+ * Replaces the return_attn branch of vggt/layers/attention.py:73-84 (cross-view scores of the
+ * patch tokens, softmax(scores / temperature) per head, both directions) together with what the
+ * callers do with the maps: mean over the collected blocks (vggt/models/aggregator.py:259-273) and
+ * mean over heads (src/finetune_timm_vggt.py:390-392).
+ *   q_scaled, k  (B, heads, n_tokens, head_dim) bf16 contiguous; q already multiplied by the
+ *                attention scale (the reference's "q = q * self.scale")
+ *   n_tokens     both views concatenated; each view's first `skip` tokens (camera / register
+ *                tokens, 5 in the reference) are dropped: n = n_tokens / 2 - skip <= 2048
+ *   round_bf16   1: round the scores and scores / temperature to bf16 as the bf16-autocast
+ *                teacher does (src/finetune_timm_vggt.py:359); 0: keep fp32
+ *   attn12/21    (B, n, n) fp32: view-1 queries over view-2 keys / the reverse.
+ *                accumulate = 0: attn = weight * head-mean; 1: attn += weight * head-mean
+ *                (weight = 1 / number of collected blocks gives the reference's cost_1, cost_2)
+ * ------------------------------------------------------------------------------------------ */
+size_t gd3_vggt_attn_workspace(int64_t B, int64_t heads, int64_t n);
+int gd3_vggt_attn_accumulate(const void* q_scaled, const void* k, int64_t B, int64_t heads, int64_t n_tokens,
+                             int64_t head_dim, int64_t skip, float temperature, int round_bf16, float weight,
+                             int accumulate, float* attn12, float* attn21, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Point map -> depth image, batched.  Replaces point_cloud_to_depth
  * (utils/functions.py:218-260; called per image at src/finetune_timm_mast3r.py:627-633): points
  * with z > 0 are projected with the pinhole intrinsics, rounded half-to-even to a pixel, dropped

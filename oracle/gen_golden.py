@@ -12,6 +12,7 @@ What is executed from the reference, unmodified:
   mast3r.fast_nn.{bruteforce_reciprocal_nns, fast_reciprocal_NNs, merge_corres}
   mast3r.losses.InfoNCE
   utils.functions.point_cloud_to_depth            (--depth-splat)
+  vggt.layers.attention.Attention.custom_scaled_dot_product_attention   (--vggt-attn)
 ``utils.functions`` imports kornia at module top (used only by an unrelated depth
 filter); empty stub modules are registered for it.  The LightningModules cannot be
 imported (timm / lightning / hydra absent), so the few lines of glue inside
@@ -372,9 +373,45 @@ def depth_splat():
     np.savez_compressed(os.path.join(OUT, 'depth_splat.npz'), **out)
 
 
+def vggt_attn():
+    """The ``return_attn`` branch of the live ``vggt.layers.attention.Attention`` (``:73-84``) ->
+    ``tests/golden/vggt_attn.npz``.  Two runs per case on the same bf16-representable q / k: fp32 tensors (every op
+    fp32) and bf16 tensors without autocast (bf16 scores, bf16 scores / temperature, softmax evaluated in fp32 and
+    rounded to bf16 on output); CPU autocast is not used because its op lists differ from CUDA's (softmax stays bf16)."""
+    from oracle import synth
+    import_reference()
+    from vggt.layers.attention import Attention
+    out = {}
+    for name, (B, heads, n, temp) in {'small': (1, 3, 37, 1.0), 'ragged_t3': (2, 2, 45, 3.0), 'blocks': (1, 4, 64, 2.0)}.items():
+        att = Attention(dim=64 * heads, num_heads=heads)
+        blocks32 = []
+        for blk in range(3 if name == 'blocks' else 1):
+            q, k = synth.vggt_qk(900 + 10 * len(out) + blk, B, heads, n)
+            v = torch.zeros_like(q)
+            with torch.no_grad():
+                _, a32 = att.custom_scaled_dot_product_attention(q.float(), k.float(), v.float(), return_attn=True,
+                                                                 temperature=temp)
+                _, a16 = att.custom_scaled_dot_product_attention(q, k, v, return_attn=True, temperature=temp)
+            assert a32.dtype == torch.float32 and a16.dtype == torch.bfloat16
+            out[f'{name}/q{blk}'], out[f'{name}/k{blk}'] = _np(q.float()), _np(k.float())
+            out[f'{name}/attn_fp32_{blk}'], out[f'{name}/attn_bf16_{blk}'] = _np(a32), _np(a16.float())
+            blocks32.append(a32)
+        # vggt/models/aggregator.py:273 and src/finetune_timm_vggt.py:390-392 on the live maps
+        attn_mean = torch.mean(torch.stack(blocks32), dim=0)
+        cost_1, cost_2 = attn_mean.chunk(2, dim=0)
+        out[f'{name}/cost_1'], out[f'{name}/cost_2'] = _np(cost_1.mean(dim=1)), _np(cost_2.mean(dim=1))
+        out[f'{name}/meta'] = np.array([B, heads, n, len(blocks32)], dtype=np.int64)
+        out[f'{name}/temperature'] = np.array(temp, dtype=np.float32)
+        out[f'{name}/scale'] = np.array(att.scale, dtype=np.float32)
+        print('vggt attention', name, tuple(a32.shape))
+    np.savez_compressed(os.path.join(OUT, 'vggt_attn.npz'), **out)
+
+
 if __name__ == '__main__':
     if '--fast-nn-extra' in sys.argv:
         fast_nn_extra()
+    elif '--vggt-attn' in sys.argv:
+        vggt_attn()
     elif '--depth-splat' in sys.argv:
         depth_splat()
     else:

@@ -242,3 +242,18 @@ def depth_splat_cases():
     half[:, 2] += 0.0
     cases['halfpix'] = (half.float(), intr(64.0, 64.0, 0.5, 0.5), 16, 16)
     return cases
+
+
+def vggt_qk(seed, B, heads, n, head_dim=64, skip=5, peak=0.6):
+    """bf16 q / k of one VGGT global block for two views of n patch tokens (+ ``skip`` special tokens each): unit-ish
+    Gaussian vectors (q_norm / k_norm are LayerNorms), with the patch tokens of view 2 correlated to a permutation of
+    view 1 so that the attention rows are peaked like a real teacher's."""
+    g = torch.Generator().manual_seed(seed)
+    T = 2 * (n + skip)
+    q = torch.randn(B, heads, T, head_dim, generator=g)
+    k = torch.randn(B, heads, T, head_dim, generator=g)
+    perm = torch.randperm(n, generator=g)
+    half = T // 2
+    k[:, :, half + skip:] += peak * q[:, :, skip:half][:, :, perm]
+    k[:, :, skip:half] += peak * q[:, :, half + skip:][:, :, torch.argsort(perm)]
+    return q.bfloat16(), k.bfloat16()

@@ -191,3 +191,33 @@ def test_point_cloud_to_depth_oracle(golden):
         assert out.shape == ref.shape
         assert ((out.numpy() > 0) == (ref > 0)).all(), name          # same pixels hit: the rounding is bit-exact
         np.testing.assert_allclose(out.numpy(), ref, rtol=1e-6, atol=0, err_msg=name)
+
+
+def _bf16_ulps(a, b):
+    """Distance in bf16 steps between two bf16-representable fp32 arrays of positive numbers."""
+    ia = (a.astype(np.float32).view(np.uint32) >> 16).astype(np.int64)
+    ib = (b.astype(np.float32).view(np.uint32) >> 16).astype(np.int64)
+    return np.abs(ia - ib)
+
+
+def test_vggt_block_attention_oracle(golden):
+    """``oracle.teacher.vggt_block_attention`` against the live ``vggt.layers.attention.Attention`` (row f2, VGGT)."""
+    from oracle import teacher
+    g = golden('vggt_attn.npz')
+    for name in ('small', 'ragged_t3', 'blocks'):
+        B, heads, n, L = (int(v) for v in g[f'{name}/meta'])
+        temp, scale = float(g[f'{name}/temperature']), float(g[f'{name}/scale'])
+        maps = []
+        for blk in range(L):
+            q, k = T(g[f'{name}/q{blk}']), T(g[f'{name}/k{blk}'])
+            a32 = teacher.vggt_block_attention(q, k, scale, temp)
+            np.testing.assert_allclose(a32.numpy(), g[f'{name}/attn_fp32_{blk}'], rtol=2e-6, atol=1e-9)
+            # bf16 tensors: the score roundings are the reference's; its softmax output is rounded to bf16 as well
+            a16 = teacher.vggt_block_attention(q.bfloat16(), k.bfloat16(), scale, temp)
+            assert a16.dtype == torch.float32
+            ulps = _bf16_ulps(a16.bfloat16().float().numpy(), g[f'{name}/attn_bf16_{blk}'])
+            assert ulps.max() <= 1 and (ulps > 0).mean() < 0.01, (name, ulps.max(), (ulps > 0).mean())
+            maps.append(a32)
+        c1, c2 = teacher.vggt_cost_volumes(maps)
+        np.testing.assert_allclose(c1.numpy(), g[f'{name}/cost_1'], rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(c2.numpy(), g[f'{name}/cost_2'], rtol=2e-6, atol=1e-9)
