@@ -11,7 +11,7 @@ used for buffers and the stream only.  The total is the mean over pairs of
 """
 import torch
 
-from . import ops
+from . import _lib, ops
 
 _F32 = torch.float32
 
@@ -32,6 +32,9 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
       t12, t21   (P, N, N)  teacher volumes;  m1, m2 (P, N) bool patch masks
       g1, g2     (P, N, C)  token maps the keypoint descriptors / depth features are sampled from
       kp1, kp2   (P, K, 2)  pixel keypoints;  p3d1, p3d2 (P, K, 3);  dep1, dep2 (P, K) keypoint depths
+      Derived on the device when absent (one ``gd3_kp_prepare`` launch per view): m1 / m2 = patches holding a keypoint
+      (src/finetune_timm_mast3r.py:516-519), dep1 / dep2 = 3 x 3 window depths at the keypoints from ``depth_map1`` /
+      ``depth_map2`` ((P, H, W) or one shared (H, W) map; src/finetune_timm_mast3r.py:482-483).
       head       dict W1, b1, gamma, beta, w2, b2 (+ use_tanh, ln_eps) of the depth-difference head
     Returns dict: kl, ap, rank, l1 (each (P,)), total (0-d) and, if backward, ``grads`` with f1, f2 (feature
     dtype), g1, g2 (fp32) and head (packed [W1 | b1 | gamma | beta | w2 | b2]).
@@ -64,7 +67,19 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     pstr = (2 * K * C1_, C1_, 1)
     ops.sample_fwd_raw(g1, lay1, geom, kp1, False, out=kf[:, 0], out_strides=pstr)
     ops.sample_fwd_raw(g2, lay2, geom, kp2, False, out=kf[:, 1], out_strides=pstr)
-    depths = torch.stack([batch['dep1'].to(_F32), batch['dep2'].to(_F32)], dim=1).reshape(2 * P, K)
+    # patch masks and keypoint depths the caller did not supply
+    prepared = {}
+    for v, kp in (('1', kp1), ('2', kp2)):
+        need_m, need_d = ('m' + v) not in batch, ('dep' + v) not in batch
+        if need_m or need_d:
+            m, d = _lib.kp_prepare(kp, geom[2], geom[3], patch_size=patch_size if need_m else None,
+                                   depth=batch['depth_map' + v] if need_d else None)
+            prepared['m' + v], prepared['dep' + v] = m, d
+    m1 = batch['m1'] if 'm1' in batch else prepared['m1']
+    m2 = batch['m2'] if 'm2' in batch else prepared['m2']
+    dep1 = batch['dep1'] if 'dep1' in batch else prepared['dep1']
+    dep2 = batch['dep2'] if 'dep2' in batch else prepared['dep2']
+    depths = torch.stack([dep1.to(_F32), dep2.to(_F32)], dim=1).reshape(2 * P, K)
 
     # ---- relative depth: ranking on both views + cross-view L1 (K4).  Issued first: its pair kernel runs for
     #      milliseconds, during which the host enqueues the many short kernels of the other losses without gaps ----
@@ -75,7 +90,7 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
                                               depth_threshold, 0.05, False, w_rank, w_l1, backward)
 
     # ---- dense cost-volume KL (K1) ----
-    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, batch['t12'], batch['t21'], batch['m1'], batch['m2'], variant,
+    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, batch['t12'], batch['t21'], m1, m2, variant,
                                    grad_scale=w['kl'] * inv_p, want_grad=backward, pairs_per_group=pairs_per_group)
 
     # ---- Smooth-AP (K2) ----

@@ -66,3 +66,31 @@ def test_graphed_step_matches_eager():
     torch.cuda.synchronize()
     assert torch.allclose(got['kl'], want['kl'], rtol=1e-5) and torch.allclose(got['rank'], want['rank'], rtol=1e-5)
     assert not torch.allclose(got['kl'], eager['kl'], rtol=1e-3)
+
+
+def test_step_derives_masks_and_keypoint_depths():
+    """Without m1 / m2 / dep1 / dep2 the step builds them from the keypoints and depth maps on the device; the result
+    equals the step fed with the oracle helpers' masks (utils/functions.py:375-399) and depths (:348-372)."""
+    from oracle import functions as ofn
+    from gd3 import pipeline
+    cfg = dict(N=256, C=384, K=128, P=3, grid=(16, 16), variant='mast3r')
+    H = W = 16 * 14
+    batch = bench_common.make_batch(cfg, cfg_id=1)
+    g = torch.Generator().manual_seed(5)
+    depth_maps = [torch.rand(cfg['P'], H, W, generator=g) * 4 + 0.5 for _ in range(2)]
+    explicit = dict(batch)
+    for v, dm in (('1', depth_maps[0]), ('2', depth_maps[1])):
+        kp = batch['kp' + v]
+        explicit['m' + v] = torch.stack([ofn.get_patch_mask_from_kp_tensor(kp[p], H, W, 14) for p in range(cfg['P'])])
+        explicit['dep' + v] = torch.cat([ofn.extract_kp_depth(dm[p], kp[p:p + 1]) for p in range(cfg['P'])])
+    derived = {k: v for k, v in batch.items() if k not in ('m1', 'm2', 'dep1', 'dep2')}
+    derived['depth_map1'], derived['depth_map2'] = depth_maps
+    a = pipeline.distillation_step(bench_common.to_device(explicit, 'cuda', feature_dtype=torch.bfloat16),
+                                   variant='mast3r', grid=cfg['grid'])
+    b = pipeline.distillation_step(bench_common.to_device(derived, 'cuda', feature_dtype=torch.bfloat16),
+                                   variant='mast3r', grid=cfg['grid'])
+    torch.cuda.synchronize()
+    for k in ('kl', 'ap', 'rank', 'l1'):
+        assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-7), (k, a[k], b[k])
+    assert not torch.allclose(a['kl'], pipeline.distillation_step(
+        bench_common.to_device(batch, 'cuda', feature_dtype=torch.bfloat16), variant='mast3r', grid=cfg['grid'])['kl'], rtol=1e-4)
