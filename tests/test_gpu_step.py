@@ -94,3 +94,31 @@ def test_step_derives_masks_and_keypoint_depths():
         assert torch.allclose(a[k], b[k], rtol=1e-5, atol=1e-7), (k, a[k], b[k])
     assert not torch.allclose(a['kl'], pipeline.distillation_step(
         bench_common.to_device(batch, 'cuda', feature_dtype=torch.bfloat16), variant='mast3r', grid=cfg['grid'])['kl'], rtol=1e-4)
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_step_random_shapes(seed):
+    """Random ragged shapes (token grid, channels not a multiple of 8, K = 1 ...) of the whole step against the
+    oracle: same bars as the fixed configurations (tools/probe_shapes.py runs longer sweeps)."""
+    import random
+    from gd3 import pipeline
+    rnd = random.Random(1000 + seed)
+    ph, pw = rnd.randint(4, 24), rnd.randint(4, 24)
+    cfg = dict(N=ph * pw, C=rnd.choice([64, 72, 96, 100, 128, 200, 384, 388, 520]),
+               K=rnd.choice([1, 2, 7, 33, 64, 100, 129, 257]), grid=(ph, pw), P=rnd.randint(1, 4),
+               variant=rnd.choice(['mast3r', 'vggt']))
+    dtype = rnd.choice([torch.float32, torch.bfloat16])
+    batch = bench_common.make_batch(cfg, cfg_id=1, pair0=seed)
+    want = bench_common.oracle_step(batch, cfg)
+    out = pipeline.distillation_step(bench_common.to_device(batch, 'cuda', feature_dtype=dtype), variant=cfg['variant'],
+                                     grid=cfg['grid'], pairs_per_group=rnd.choice([0, 1, 2]))
+    torch.cuda.synchronize()
+    for k in ('kl', 'ap', 'rank', 'l1'):
+        got, ref = out[k].float().cpu(), want[k]
+        err = ((got - ref).abs() / ref.abs().clamp_min(1e-6)).max().item()
+        assert err <= 1e-3, (cfg, dtype, k, got, ref)
+    for k in ('f1', 'f2', 'g1', 'g2', 'head'):
+        g, r = out['grads'][k].float().cpu(), want['grads'][k]
+        if float(r.norm()) < 1e-12 and float(g.norm()) < 1e-9:
+            continue
+        assert_grad_close(g, r, name=f'{cfg} {k}', norm_rtol=3e-2)
