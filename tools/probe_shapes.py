@@ -26,9 +26,16 @@ def main():
     rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
     bad = 0
     for case in range(n_cases):
-        ph, pw = rnd.randint(4, 24), rnd.randint(4, 24)
-        cfg = dict(N=ph * pw, C=rnd.choice([64, 72, 96, 100, 128, 200, 384, 388, 520]), K=rnd.choice([1, 2, 7, 33, 64, 100, 129, 257]),
-                   grid=(ph, pw), P=rnd.randint(1, 4), variant=rnd.choice(['mast3r', 'vggt']))
+        if os.environ.get('GD3_PROBE_LARGE'):
+            # larger keypoint counts (Smooth-AP rows beyond one warp's registers, several ranking tiles) and token grids
+            ph, pw = rnd.randint(20, 40), rnd.randint(20, 40)
+            cfg = dict(N=ph * pw, C=rnd.choice([64, 104, 200]), K=rnd.choice([513, 700, 1025, 1100]),
+                       grid=(ph, pw), P=rnd.randint(1, 2), variant=rnd.choice(['mast3r', 'vggt']))
+        else:
+            ph, pw = rnd.randint(4, 24), rnd.randint(4, 24)
+            cfg = dict(N=ph * pw, C=rnd.choice([64, 72, 96, 100, 128, 200, 384, 388, 520]),
+                       K=rnd.choice([1, 2, 7, 33, 64, 100, 129, 257]), grid=(ph, pw), P=rnd.randint(1, 4),
+                       variant=rnd.choice(['mast3r', 'vggt']))
         dtype = rnd.choice([torch.float32, torch.bfloat16])
         tag = f"case {case}: {cfg} {dtype}"
         try:
