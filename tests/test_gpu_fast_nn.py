@@ -220,3 +220,21 @@ def test_extract_correspondences_nonsym_golden(gd3mod, golden):
         assert xy1.is_cuda and conf.is_cuda
         assert (xy1.cpu().numpy() == g[f'{tag}/xy1']).all() and (xy2.cpu().numpy() == g[f'{tag}/xy2']).all()
         assert np.array_equal(conf.cpu().numpy(), g[f'{tag}/conf'])
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_reciprocal_nn_random_sizes(gd3mod, seed):
+    """Random sizes / descriptor widths (incl. 1, odd and > 128) on exactly-representable descriptors: indices equal
+    the oracle's in both directions and for both distances (tools/probe_nn_shapes.py runs longer sweeps)."""
+    import random
+    from gd3.compat import fast_nn
+    rnd = random.Random(500 + seed)
+    na = rnd.choice([1, 2, 31, 64, 65, 127, 129, 500, 1000, 2049, 3000])
+    nb = rnd.choice([1, 3, 33, 128, 130, 777, 1024, 2500, 4097])
+    dim = rnd.choice([1, 2, 3, 5, 8, 24, 25, 64, 100, 128, 130, 256])
+    dist = rnd.choice(['dot', 'l2'])
+    A = synth.nn_exact_set(10 * seed + 1, na, dim=dim, dup=min(8, na // 2))
+    B = synth.nn_exact_set(10 * seed + 2, nb, dim=dim, dup=min(8, nb // 2))
+    a, b = fast_nn.bruteforce_reciprocal_nns(A, B, device='cuda', dist=dist)
+    ra, rb = oracle_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist=dist)
+    assert (a == ra).all() and (b == rb).all(), (na, nb, dim, dist)
