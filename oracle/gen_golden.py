@@ -13,6 +13,7 @@ What is executed from the reference, unmodified:
   mast3r.losses.InfoNCE
   utils.functions.point_cloud_to_depth            (--depth-splat)
   vggt.layers.attention.Attention.custom_scaled_dot_product_attention   (--vggt-attn)
+  dust3r.model.AsymmetricCroCo3DStereo.forward (tgt_attn_map)          (--teacher-volume)
 ``utils.functions`` imports kornia at module top (used only by an unrelated depth
 filter); empty stub modules are registered for it.  The LightningModules cannot be
 imported (timm / lightning / hydra absent), so the few lines of glue inside
@@ -407,9 +408,58 @@ def vggt_attn():
     np.savez_compressed(os.path.join(OUT, 'vggt_attn.npz'), **out)
 
 
+def teacher_volume():
+    """``tgt_attn_map`` of the live MASt3R teacher class (``dust3r/dust3r/model.py:346-363``) ->
+    ``tests/golden/teacher_volume.npz``.  A small random-weight ``AsymmetricCroCo3DStereo`` (3 decoder layers, 3 heads,
+    4 x 6 patches) runs its unmodified ``forward`` on CPU; the per-layer cross-attention logits that ``_decoder``
+    returns are recorded on the way (they are the inputs of the block), with the cross-attention query / key
+    projections scaled up so that the softmax rows are peaked.  ``timm`` is imported by croco's blocks.py but never used:
+    an empty stub module is registered for it."""
+    sys.modules.setdefault('timm', types.ModuleType('timm'))
+    for pth in (REF, os.path.join(REF, 'dust3r')):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    import dust3r.model as dust3r_model
+    out = {}
+    for name, (B, reciprocity, temperature) in {'recip': (2, True, 3.0), 'recip_t1': (1, True, 1.0),
+                                                'plain': (2, False, 3.0)}.items():
+        torch.manual_seed(31 + len(out))
+        net = dust3r_model.AsymmetricCroCo3DStereo(
+            img_size=(64, 96), patch_size=16, enc_embed_dim=64, enc_depth=1, enc_num_heads=2, dec_embed_dim=48,
+            dec_depth=3, dec_num_heads=3, pos_embed='RoPE100', head_type='linear', output_mode='pts3d',
+            landscape_only=False, temperature=temperature)
+        net.eval()
+        net.reciprocity = reciprocity
+        with torch.no_grad():
+            for n_, prm in net.named_parameters():
+                if 'cross_attn.projq.weight' in n_ or 'cross_attn.projk.weight' in n_:
+                    prm.mul_(6.0)
+        seen = {}
+        inner = net._decoder
+
+        def recording_decoder(*a, _inner=inner, _seen=seen, **k):
+            res = _inner(*a, **k)
+            _seen['tgt'], _seen['src'] = [c.clone() for c in res[1]], [c.clone() for c in res[2]]
+            return res
+        net._decoder = recording_decoder
+        views = [dict(img=torch.randn(B, 3, 64, 96), true_shape=torch.tensor([[64, 96]] * B), instance=[str(i)] * B)
+                 for i in range(2)]
+        with torch.no_grad():
+            _, res2 = net(*views)
+        out[f'{name}/tgt'] = _np(torch.stack(seen['tgt']))          # (L, B, heads, N, N)
+        out[f'{name}/src'] = _np(torch.stack(seen['src']))
+        out[f'{name}/tgt_attn_map'] = _np(res2['tgt_attn_map'])
+        out[f'{name}/temperature'] = np.array(temperature, dtype=np.float32)
+        out[f'{name}/reciprocity'] = np.array(int(reciprocity))
+        print('teacher_volume', name, tuple(res2['tgt_attn_map'].shape), 'row max', float(res2['tgt_attn_map'].max(-1).values.mean()))
+    np.savez_compressed(os.path.join(OUT, 'teacher_volume.npz'), **out)
+
+
 if __name__ == '__main__':
     if '--fast-nn-extra' in sys.argv:
         fast_nn_extra()
+    elif '--teacher-volume' in sys.argv:
+        teacher_volume()
     elif '--vggt-attn' in sys.argv:
         vggt_attn()
     elif '--depth-splat' in sys.argv:

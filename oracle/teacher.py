@@ -2,8 +2,9 @@
 
 Test infrastructure only (see ``oracle/__init__.py``).  Plain PyTorch on CPU.
 
-``teacher_volume`` is **parity unpinned**: the block sits inside ``AsymmetricCroCo3DStereo.forward`` and cannot be called without the teacher model and its weights, so no golden vector could be
-produced by the live reference; the restatement re-types those lines around the same torch ops.
+``teacher_volume`` is pinned: ``oracle/gen_golden.py --teacher-volume`` instantiates a small random-weight
+``AsymmetricCroCo3DStereo`` from the reference checkout, runs its unmodified ``forward`` on CPU and records the per-layer
+logits together with the ``tgt_attn_map`` it returns (``tests/golden/teacher_volume.npz``).
 ``vggt_block_attention`` is pinned: the reference's ``Attention`` class imports and runs here on CPU.
 """
 import torch

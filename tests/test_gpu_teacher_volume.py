@@ -54,3 +54,15 @@ def test_vggt_plain_mean_matches_oracle():
     r1, r2 = oracle_teacher.vggt_cost_volumes(maps)
     c1, c2 = teacher.vggt_cost_volumes([m.cuda() for m in maps])
     assert torch.allclose(c1.cpu(), r1, rtol=2e-5, atol=1e-8) and torch.allclose(c2.cpu(), r2, rtol=2e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize('name', ['recip', 'recip_t1', 'plain'])
+def test_teacher_volume_live_reference_golden(golden, name):
+    """The fused kernel against ``tgt_attn_map`` produced by the live MASt3R teacher class on its own logits."""
+    import numpy as np
+    from gd3.compat import teacher
+    g = golden('teacher_volume.npz')
+    tgt = [t.cuda() for t in torch.from_numpy(g[f'{name}/tgt'])]
+    src = [t.cuda() for t in torch.from_numpy(g[f'{name}/src'])]
+    got = teacher.teacher_volume(tgt, src, float(g[f'{name}/temperature']), bool(g[f'{name}/reciprocity']))
+    np.testing.assert_allclose(got.cpu().numpy(), g[f'{name}/tgt_attn_map'], rtol=2e-5, atol=1e-7)

@@ -221,3 +221,14 @@ def test_vggt_block_attention_oracle(golden):
         c1, c2 = teacher.vggt_cost_volumes(maps)
         np.testing.assert_allclose(c1.numpy(), g[f'{name}/cost_1'], rtol=2e-6, atol=1e-9)
         np.testing.assert_allclose(c2.numpy(), g[f'{name}/cost_2'], rtol=2e-6, atol=1e-9)
+
+
+def test_teacher_volume_oracle(golden):
+    """``oracle.teacher.teacher_volume`` against ``tgt_attn_map`` of the live MASt3R teacher class (a small
+    random-weight model run by ``oracle/gen_golden.py --teacher-volume``; row f2)."""
+    from oracle import teacher
+    g = golden('teacher_volume.npz')
+    for name in ('recip', 'recip_t1', 'plain'):
+        tgt, src = list(T(g[f'{name}/tgt'])), list(T(g[f'{name}/src']))
+        out = teacher.teacher_volume(tgt, src, float(g[f'{name}/temperature']), bool(g[f'{name}/reciprocity']))
+        np.testing.assert_allclose(out.numpy(), g[f'{name}/tgt_attn_map'], rtol=1e-6, atol=1e-9, err_msg=name)
