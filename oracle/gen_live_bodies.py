@@ -1,0 +1,176 @@
+"""Golden vectors from the LIVE loss methods of the reference's LightningModules -> ``tests/golden/live_bodies.npz``.
+
+Run in the build container only (``python -m oracle.gen_live_bodies``); needs ``/root/reference``.
+
+``src/finetune_timm_mast3r.py`` and ``src/finetune_timm_vggt.py`` import packages this image does not have (timm,
+pytorch_lightning, hydra, visdom, matplotlib, albumentations, kornia ...).  None of them is touched by the three loss
+methods, so a meta-path finder registers empty stand-in modules for exactly those absent packages (real modules always
+win: the finder is appended), the modules are imported unmodified, and
+
+    FinetuneMASt3RTIMM.calculate_cost_loss / calculate_matching_loss / calculate_depth_loss
+    FinetuneVGGTTIMM.calculate_cost_loss   / calculate_matching_loss / calculate_depth_loss
+
+are called as plain functions on a stand-in ``self`` that supplies what they read from the module: the ViT feature
+getters (returning the given synthetic features instead of running a backbone), ``depth_diff_head`` (the live
+``DepthAwareFeatureFusion``), ``patch_size``, ``thres3d_neg``, ``device``.  Losses and autograd gradients of those live
+bodies are stored next to their inputs; ``tests/test_oracle_golden.py`` pins ``oracle/bodies.py`` to them and the ``-m
+gpu`` tests compare the CUDA ops with them.
+"""
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get('GD3_REFERENCE', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+ABSENT = {'pytorch_lightning', 'timm', 'visdom', 'cv2', 'matplotlib', 'albumentations', 'hydra', 'omegaconf',
+          'huggingface_hub', 'kornia', 'roma', 'trimesh', 'open3d', 'imageio', 'pycocotools', 'h5py', 'wandb',
+          'tensorboard', 'lightning'}
+
+
+def _stand_in_class(name):
+    def call(self, *a, **k):          # usable as a decorator factory (hydra.main) and as a constructor
+        return a[0] if len(a) == 1 and callable(a[0]) and not k else self
+    return type(name, (object,), {'__init__': lambda self, *a, **k: None, '__call__': call,
+                                  '__getattr__': lambda self, n: _stand_in_class(n)()})
+
+
+class _StandInModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        cls = _stand_in_class(name)
+        setattr(self, name, cls)
+        return cls
+
+
+class _AbsentPackages(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split('.')[0] in ABSENT:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _StandInModule(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def import_live_modules():
+    sys.meta_path.append(_AbsentPackages())
+    for p in (REF, os.path.join(REF, 'src'), os.path.join(REF, 'dust3r')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import finetune_timm_mast3r as ft_mast3r
+    import finetune_timm_vggt as ft_vggt
+    import utils.model as ref_model
+    return ft_mast3r, ft_vggt, ref_model
+
+
+def _np(x):
+    return x.detach().cpu().numpy()
+
+
+class _Self:
+    """What the loss methods read from the LightningModule."""
+    device = 'cpu'
+    patch_size = 14
+    resize_patch_size = 14
+    thres3d_neg = 0.1
+
+    def __init__(self, by_image):
+        self.by_image = by_image            # id(rgb tensor) -> dict of the features that image "produces"
+
+    def get_feature_cost(self, rgb, normalize=False, resize=False):
+        return self.by_image[id(rgb)]['cost']
+
+    def get_feature(self, rgb, kp, normalize=True):
+        return self.by_image[id(rgb)]['desc']
+
+    def get_intermediate_feature(self, rgb, n=None, pts=None, reshape=True, return_class_token=False, normalize=True):
+        return self.by_image[id(rgb)]['kp_feat']
+
+
+def main():
+    from oracle import synth
+    ft_mast3r, ft_vggt, ref_model = import_live_modules()
+    out = {}
+    ph, pw, C, K = 8, 10, 64, 40
+    H, W, N = ph * 14, pw * 14, ph * pw
+    for variant, cls in (('mast3r', ft_mast3r.FinetuneMASt3RTIMM), ('vggt', ft_vggt.FinetuneVGGTTIMM)):
+        for case in range(2):
+            tag = f'{variant}{case}'
+            it = synth.pair_inputs(9, 10 * case + (0 if variant == 'mast3r' else 5), N, C, K, (ph, pw), variant)
+            rgb1, rgb2 = torch.zeros(1, 3, H, W), torch.zeros(1, 3, H, W)
+            kp1, kp2 = it.kp1[None], it.kp2[None]
+            leaves = dict(f1=it.f1.clone().requires_grad_(True), f2=it.f2.clone().requires_grad_(True))
+            # descriptors as get_feature(normalize=True) returns them: unit rows, (1, K, C)
+            d1 = torch.nn.functional.normalize(it.g1[:K], dim=-1)[None].clone().requires_grad_(True)
+            d2 = torch.nn.functional.normalize(it.g1[:K] + 0.25 * it.g2[:K], dim=-1)[None].clone().requires_grad_(True)
+            kf1 = it.g1[K:2 * K][None].clone().requires_grad_(True)
+            kf2 = it.g2[K:2 * K][None].clone().requires_grad_(True)
+            me = _Self({id(rgb1): dict(cost=leaves['f1'].view(1, ph, pw, C), desc=d1, kp_feat=kf1),
+                        id(rgb2): dict(cost=leaves['f2'].view(1, ph, pw, C), desc=d2, kp_feat=kf2)})
+            torch.manual_seed(77)
+            me.depth_diff_head = ref_model.DepthAwareFeatureFusion(C)
+            synth.load_head(me.depth_diff_head, synth.head_params(4300 + case, C))
+
+            # ---- cost-volume KL ----
+            if variant == 'mast3r':
+                kl = cls.calculate_cost_loss(me, rgb1, rgb2, kp1, kp2, it.t12, it.t21, 0)
+            elif case == 0:     # keypoint masks
+                kl = cls.calculate_cost_loss(me, rgb1, rgb2, it.t12[None], it.t21[None], kp_1=kp1, kp_2=kp2)
+            else:               # co-visibility pixel masks, reduced to patches by the method itself
+                pix1 = it.m1.view(ph, pw).repeat_interleave(14, 0).repeat_interleave(14, 1)
+                pix2 = it.m2.view(ph, pw).repeat_interleave(14, 0).repeat_interleave(14, 1)
+                out[f'{tag}/pixmask1'], out[f'{tag}/pixmask2'] = _np(pix1), _np(pix2)
+                kl = cls.calculate_cost_loss(me, rgb1, rgb2, it.t12[None], it.t21[None], mask_1=pix1, mask_2=pix2)
+            kl.backward()
+
+            # ---- Smooth-AP ----
+            g = torch.Generator().manual_seed(500 + case)
+            pm1 = torch.rand(H, W, 3, generator=g)
+            pm2 = torch.rand(H, W, 3, generator=g)
+            yx1, yx2 = (kp1[0, :, 1].long(), kp1[0, :, 0].long()), (kp2[0, :, 1].long(), kp2[0, :, 0].long())
+            pm1[yx1] = it.p1
+            pm2[yx2] = it.p2
+            ap = cls.calculate_matching_loss(me, rgb1, rgb2, kp1, kp2, pm1, pm2)
+            ap.backward()
+
+            # ---- depth losses ----
+            dm1 = torch.rand(H, W, generator=g) * 4 + 0.5
+            dm2 = torch.rand(H, W, generator=g) * 4 + 0.5
+            if variant == 'mast3r':
+                l1, rank = cls.calculate_depth_loss(me, dm1, dm2, rgb1, rgb2, kp1, kp2)
+            else:
+                l1, rank = cls.calculate_depth_loss(me, dict(depth_pred_1=dm1, depth_pred_2=dm2), rgb1, rgb2, kp1, kp2)
+            (l1 + rank).backward()
+
+            fl = me.depth_diff_head.fusion_layer
+            head_grads = torch.cat([p.grad.reshape(-1) for p in (fl[0].weight, fl[0].bias, fl[1].weight, fl[1].bias,
+                                                                 fl[3].weight, fl[3].bias)])
+            out.update({f'{tag}/f1': _np(it.f1), f'{tag}/f2': _np(it.f2), f'{tag}/t12': _np(it.t12), f'{tag}/t21': _np(it.t21),
+                        f'{tag}/kp1': _np(kp1), f'{tag}/kp2': _np(kp2), f'{tag}/d1': _np(d1), f'{tag}/d2': _np(d2),
+                        f'{tag}/kf1': _np(kf1), f'{tag}/kf2': _np(kf2), f'{tag}/p3d1': _np(pm1[yx1]), f'{tag}/p3d2': _np(pm2[yx2]),
+                        f'{tag}/dm1': _np(dm1), f'{tag}/dm2': _np(dm2), f'{tag}/head_case': np.array(4300 + case),
+                        f'{tag}/kl': _np(kl), f'{tag}/ap': _np(ap), f'{tag}/l1': _np(l1), f'{tag}/rank': _np(rank),
+                        f'{tag}/grad_f1': _np(leaves['f1'].grad), f'{tag}/grad_f2': _np(leaves['f2'].grad),
+                        f'{tag}/grad_d1': _np(d1.grad), f'{tag}/grad_d2': _np(d2.grad),
+                        f'{tag}/grad_kf1': _np(kf1.grad), f'{tag}/grad_kf2': _np(kf2.grad),
+                        f'{tag}/grad_head': _np(head_grads)})
+            print(tag, 'kl', float(kl), 'ap', float(ap), 'l1', float(l1), 'rank', float(rank))
+    out['meta'] = np.array([ph, pw, C, K])
+    np.savez_compressed(os.path.join(OUT, 'live_bodies.npz'), **out)
+
+
+if __name__ == '__main__':
+    main()

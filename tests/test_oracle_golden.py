@@ -232,3 +232,62 @@ def test_teacher_volume_oracle(golden):
         tgt, src = list(T(g[f'{name}/tgt'])), list(T(g[f'{name}/src']))
         out = teacher.teacher_volume(tgt, src, float(g[f'{name}/temperature']), bool(g[f'{name}/reciprocity']))
         np.testing.assert_allclose(out.numpy(), g[f'{name}/tgt_attn_map'], rtol=1e-6, atol=1e-9, err_msg=name)
+
+
+LIVE_TAGS = ('mast3r0', 'mast3r1', 'vggt0', 'vggt1')
+
+
+def live_case(g, tag):
+    """Inputs of one ``live_bodies.npz`` case as the oracle / ops take them (shared with the GPU test)."""
+    from oracle import synth
+    ph, pw, C, K = (int(v) for v in g['meta'])
+    H, W = ph * 14, pw * 14
+    variant = tag[:-1]
+    c = {k: T(g[f'{tag}/{k}']) for k in ('f1', 'f2', 't12', 't21', 'kp1', 'kp2', 'd1', 'd2', 'kf1', 'kf2', 'p3d1', 'p3d2',
+                                         'dm1', 'dm2')}
+    if g.has(f'{tag}/pixmask1'):      # co-visibility pixel masks -> patches by nearest sampling (finetune_timm_vggt.py:504-508)
+        c['m1'] = T(g[f'{tag}/pixmask1'])[::14, ::14].reshape(-1)
+        c['m2'] = T(g[f'{tag}/pixmask2'])[::14, ::14].reshape(-1)
+    else:
+        c['m1'] = functions.get_patch_mask_from_kp_tensor(c['kp1'][0], H, W, 14)
+        c['m2'] = functions.get_patch_mask_from_kp_tensor(c['kp2'][0], H, W, 14)
+    c['kd1'] = functions.extract_kp_depth(c['dm1'], c['kp1'])
+    c['kd2'] = functions.extract_kp_depth(c['dm2'], c['kp2'])
+    c['head_params'] = synth.head_params(int(g[f'{tag}/head_case']), C)
+    c['variant'], c['C'] = variant, C
+    return c
+
+
+@pytest.mark.parametrize('tag', LIVE_TAGS)
+def test_bodies_against_live_lightning_methods(golden, tag):
+    """``oracle/bodies.py`` against losses and gradients of the reference's own ``calculate_cost_loss`` /
+    ``calculate_matching_loss`` / ``calculate_depth_loss`` methods (``oracle/gen_live_bodies.py``)."""
+    from oracle import bodies, synth
+    g = golden('live_bodies.npz')
+    c = live_case(g, tag)
+    f1, f2 = c['f1'].clone().requires_grad_(True), c['f2'].clone().requires_grad_(True)
+    kl = bodies.cost_volume_kl(f1, f2, c['t12'], c['t21'], c['m1'], c['m2'], c['variant'])
+    kl.backward()
+    assert rel_err(kl, g[f'{tag}/kl']) < 1e-5
+    assert_grad_close(f1.grad, T(g[f'{tag}/grad_f1']), cos_min=0.99999, name='f1', norm_rtol=1e-3)
+    assert_grad_close(f2.grad, T(g[f'{tag}/grad_f2']), cos_min=0.99999, name='f2', norm_rtol=1e-3)
+
+    d1, d2 = c['d1'].clone().requires_grad_(True), c['d2'].clone().requires_grad_(True)
+    ap = bodies.smooth_ap(d1[0], d2[0], c['p3d1'], c['p3d2'], c['variant'])
+    ap.backward()
+    assert rel_err(ap, g[f'{tag}/ap']) < 1e-5
+    assert_grad_close(d1.grad, T(g[f'{tag}/grad_d1']), cos_min=0.99999, name='d1', norm_rtol=1e-3)
+    assert_grad_close(d2.grad, T(g[f'{tag}/grad_d2']), cos_min=0.99999, name='d2', norm_rtol=1e-3)
+
+    head = losses.DepthHead(c['C'])
+    synth.load_head(head, c['head_params'])
+    kf1, kf2 = c['kf1'].clone().requires_grad_(True), c['kf2'].clone().requires_grad_(True)
+    l1, rank = bodies.depth_losses(head, kf1, kf2, c['kd1'], c['kd2'])
+    (l1 + rank).backward()
+    assert rel_err(l1, g[f'{tag}/l1']) < 1e-5 and rel_err(rank, g[f'{tag}/rank']) < 1e-5
+    assert_grad_close(kf1.grad, T(g[f'{tag}/grad_kf1']), cos_min=0.99999, name='kf1', norm_rtol=1e-3)
+    assert_grad_close(kf2.grad, T(g[f'{tag}/grad_kf2']), cos_min=0.99999, name='kf2', norm_rtol=1e-3)
+    fl = head.fusion_layer
+    packed = torch.cat([q.grad.reshape(-1) for q in (fl[0].weight, fl[0].bias, fl[1].weight, fl[1].bias, fl[3].weight,
+                                                     fl[3].bias)])
+    assert_grad_close(packed, T(g[f'{tag}/grad_head']), cos_min=0.99999, name='head', norm_rtol=1e-3)
