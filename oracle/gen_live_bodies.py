@@ -9,6 +9,7 @@ win: the finder is appended), the modules are imported unmodified, and
 
     FinetuneMASt3RTIMM.calculate_cost_loss / calculate_matching_loss / calculate_depth_loss
     FinetuneVGGTTIMM.calculate_cost_loss   / calculate_matching_loss / calculate_depth_loss
+    FinetuneTIMM.training_step             (src/finetune_timm_me.py: the ME baseline's Smooth-AP with 3-D positives)
 
 are called as plain functions on a stand-in ``self`` that supplies what they read from the module: the ViT feature
 getters (returning the given synthetic features instead of running a backbone), ``depth_diff_head`` (the live
@@ -72,8 +73,9 @@ def import_live_modules():
             sys.path.insert(0, p)
     import finetune_timm_mast3r as ft_mast3r
     import finetune_timm_vggt as ft_vggt
+    import finetune_timm_me as ft_me
     import utils.model as ref_model
-    return ft_mast3r, ft_vggt, ref_model
+    return ft_mast3r, ft_vggt, ft_me, ref_model
 
 
 def _np(x):
@@ -102,7 +104,7 @@ class _Self:
 
 def main():
     from oracle import synth
-    ft_mast3r, ft_vggt, ref_model = import_live_modules()
+    ft_mast3r, ft_vggt, ft_me, ref_model = import_live_modules()
     out = {}
     ph, pw, C, K = 8, 10, 64, 40
     H, W, N = ph * 14, pw * 14, ph * pw
@@ -168,6 +170,28 @@ def main():
                         f'{tag}/grad_kf1': _np(kf1.grad), f'{tag}/grad_kf2': _np(kf2.grad),
                         f'{tag}/grad_head': _np(head_grads)})
             print(tag, 'kl', float(kl), 'ap', float(ap), 'l1', float(l1), 'rank', float(rank))
+    # ---- the ME baseline's loss is the body of its training_step (src/finetune_timm_me.py:191-220): positives are all
+    #      (s, t) closer than 5 mm in 3-D, so points are near-duplicated to give rows with several positives ----
+    for case in range(2):
+        tag = f'me{case}'
+        it = synth.pair_inputs(9, 40 + case, N, C, K, (ph, pw), 'mast3r')
+        g = torch.Generator().manual_seed(600 + case)
+        p1 = torch.rand(K, 3, generator=g)
+        p1[K // 2:K // 2 + 6] = p1[:6] + 0.001 * torch.randn(6, 3, generator=g)
+        p2 = p1 + 0.0015 * torch.randn(K, 3, generator=g)
+        d1 = torch.nn.functional.normalize(it.g1[:K], dim=-1)[None].clone().requires_grad_(True)
+        d2 = torch.nn.functional.normalize(it.g1[:K] + 0.25 * it.g2[:K], dim=-1)[None].clone().requires_grad_(True)
+        rgb1, rgb2 = torch.zeros(1, 3, H, W), torch.zeros(1, 3, H, W)
+        me = _Self({id(rgb1): dict(desc=d1), id(rgb2): dict(desc=d2)})
+        me.thresh3d_pos = 5e-3
+        me.log = lambda *a, **k: None
+        batch = dict(rgb_1=rgb1, pts2d_1=it.kp1[None], pts3d_1=p1[None], rgb_2=rgb2, pts2d_2=it.kp2[None], pts3d_2=p2[None])
+        loss = ft_me.FinetuneTIMM.training_step(me, batch, 0)
+        loss.backward()
+        n_pos = int((torch.cdist(p1[None], p2[None]) < 5e-3).sum())
+        out.update({f'{tag}/d1': _np(d1), f'{tag}/d2': _np(d2), f'{tag}/p3d1': _np(p1), f'{tag}/p3d2': _np(p2),
+                    f'{tag}/ap': _np(loss), f'{tag}/grad_d1': _np(d1.grad), f'{tag}/grad_d2': _np(d2.grad)})
+        print(tag, 'ap', float(loss), 'positives', n_pos)
     out['meta'] = np.array([ph, pw, C, K])
     np.savez_compressed(os.path.join(OUT, 'live_bodies.npz'), **out)
 

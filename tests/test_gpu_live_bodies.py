@@ -69,3 +69,16 @@ def test_depth_losses_vs_live_method(golden, tag):
     packed = torch.cat([q.grad.reshape(-1) for q in (fl[0].weight, fl[0].bias, fl[1].weight, fl[1].bias, fl[3].weight,
                                                      fl[3].bias)]).cpu()
     assert_grad_close(packed, T(g[f'{tag}/grad_head']), name='head', norm_rtol=3e-2)
+
+
+@pytest.mark.parametrize('tag', ['me0', 'me1'])
+def test_me_smooth_ap_vs_live_training_step(golden, tag):
+    """'me' variant against the live ``FinetuneTIMM.training_step`` (src/finetune_timm_me.py:191-220)."""
+    from gd3 import ops
+    g = golden('live_bodies.npz')
+    d1, d2 = T(g[f'{tag}/d1']).cuda().requires_grad_(True), T(g[f'{tag}/d2']).cuda().requires_grad_(True)
+    ap = ops.smooth_ap(d1, d2, T(g[f'{tag}/p3d1']).cuda()[None], T(g[f'{tag}/p3d2']).cuda()[None], variant='me')
+    ap.sum().backward()
+    assert rel_err(ap[0].detach().cpu(), g[f'{tag}/ap']) < 1e-3
+    assert_grad_close(d1.grad.cpu(), T(g[f'{tag}/grad_d1']), name='d1', norm_rtol=3e-2)
+    assert_grad_close(d2.grad.cpu(), T(g[f'{tag}/grad_d2']), name='d2', norm_rtol=3e-2)

@@ -291,3 +291,15 @@ def test_bodies_against_live_lightning_methods(golden, tag):
     packed = torch.cat([q.grad.reshape(-1) for q in (fl[0].weight, fl[0].bias, fl[1].weight, fl[1].bias, fl[3].weight,
                                                      fl[3].bias)])
     assert_grad_close(packed, T(g[f'{tag}/grad_head']), cos_min=0.99999, name='head', norm_rtol=1e-3)
+
+
+@pytest.mark.parametrize('tag', ['me0', 'me1'])
+def test_me_smooth_ap_against_live_training_step(golden, tag):
+    """'me' variant (3-D positives, several per row) against the live ``FinetuneTIMM.training_step``."""
+    g = golden('live_bodies.npz')
+    d1, d2 = T(g[f'{tag}/d1']).clone().requires_grad_(True), T(g[f'{tag}/d2']).clone().requires_grad_(True)
+    ap = bodies.smooth_ap(d1[0], d2[0], T(g[f'{tag}/p3d1']), T(g[f'{tag}/p3d2']), 'me')
+    ap.backward()
+    assert rel_err(ap, g[f'{tag}/ap']) < 1e-5
+    assert_grad_close(d1.grad, T(g[f'{tag}/grad_d1']), cos_min=0.99999, name='d1', norm_rtol=1e-3)
+    assert_grad_close(d2.grad, T(g[f'{tag}/grad_d2']), cos_min=0.99999, name='d2', norm_rtol=1e-3)
