@@ -10,6 +10,7 @@ win: the finder is appended), the modules are imported unmodified, and
     FinetuneMASt3RTIMM.calculate_cost_loss / calculate_matching_loss / calculate_depth_loss
     FinetuneVGGTTIMM.calculate_cost_loss   / calculate_matching_loss / calculate_depth_loss
     FinetuneTIMM.training_step             (src/finetune_timm_me.py: the ME baseline's Smooth-AP with 3-D positives)
+    FinetuneMASt3RTIMM.get_intermediate_feature / get_feature   (keypoint sampling glue, stand-in ViT)
 
 are called as plain functions on a stand-in ``self`` that supplies what they read from the module: the ViT feature
 getters (returning the given synthetic features instead of running a backbone), ``depth_diff_head`` (the live
@@ -192,6 +193,48 @@ def main():
         out.update({f'{tag}/d1': _np(d1), f'{tag}/d2': _np(d2), f'{tag}/p3d1': _np(p1), f'{tag}/p3d2': _np(p2),
                     f'{tag}/ap': _np(loss), f'{tag}/grad_d1': _np(d1.grad), f'{tag}/grad_d2': _np(d2.grad)})
         print(tag, 'ap', float(loss), 'positives', n_pos)
+    # ---- keypoint feature getters (src/finetune_timm_mast3r.py:242-313): the live methods with a stand-in ViT that
+    #      returns given token tensors.  get_intermediate_feature samples 4 layers separately and averages them,
+    #      get_feature samples the final features and L2-normalises ----
+    class _ViT:
+        num_prefix_tokens = 1
+        norm = torch.nn.Identity()
+
+        def __init__(self, layers, final):
+            self.layers, self.final = layers, final
+
+        def _intermediate_layers(self, x, n):
+            return [self.layers[i] for i in range(len(n))]
+
+        def forward_features(self, x):
+            return self.final
+
+    for case, (gh, gw) in enumerate([(8, 10), (9, 7)]):
+        tag = f'sample{case}'
+        Hs, Ws = gh * 14, gw * 14
+        g = torch.Generator().manual_seed(700 + case)
+        layers = [torch.randn(1, 1 + gh * gw, C, generator=g).requires_grad_(True) for _ in range(4)]
+        final = torch.randn(1, 1 + gh * gw, C, generator=g).requires_grad_(True)
+        kp = synth.keypoints(710 + case, K, Ws, Hs)[None]
+        me = _Self({})
+        me.model = _ViT(layers, final)
+        me.input_transform = lambda x: x
+        me.refine_conv = torch.nn.Identity()
+        me.target_res = max(Hs, Ws)
+        me.downsample_factor = 14
+        rgb = torch.zeros(1, 3, Hs, Ws)
+        feat = ft_mast3r.FinetuneMASt3RTIMM.get_intermediate_feature(me, rgb, pts=kp, n=[4, 5, 6, 7], reshape=True,
+                                                                     return_class_token=False, normalize=True)
+        desc = ft_mast3r.FinetuneMASt3RTIMM.get_feature(me, rgb, kp, normalize=True)
+        w_f = torch.randn(feat.shape, generator=g)
+        w_d = torch.randn(desc.shape, generator=g)
+        ((feat * w_f).sum() + (desc * w_d).sum()).backward()
+        out.update({f'{tag}/layers': _np(torch.stack([t[0, 1:] for t in layers])), f'{tag}/final': _np(final[0, 1:]),
+                    f'{tag}/kp': _np(kp), f'{tag}/grid': np.array([gh, gw]), f'{tag}/feat': _np(feat), f'{tag}/desc': _np(desc),
+                    f'{tag}/w_feat': _np(w_f), f'{tag}/w_desc': _np(w_d),
+                    f'{tag}/grad_layers': _np(torch.stack([t.grad[0, 1:] for t in layers])),
+                    f'{tag}/grad_final': _np(final.grad[0, 1:])})
+        print(tag, tuple(feat.shape), tuple(desc.shape))
     out['meta'] = np.array([ph, pw, C, K])
     np.savez_compressed(os.path.join(OUT, 'live_bodies.npz'), **out)
 

@@ -82,3 +82,26 @@ def test_me_smooth_ap_vs_live_training_step(golden, tag):
     assert rel_err(ap[0].detach().cpu(), g[f'{tag}/ap']) < 1e-3
     assert_grad_close(d1.grad.cpu(), T(g[f'{tag}/grad_d1']), name='d1', norm_rtol=3e-2)
     assert_grad_close(d2.grad.cpu(), T(g[f'{tag}/grad_d2']), name='d2', norm_rtol=3e-2)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('tag', ['sample0', 'sample1'])
+def test_sample_tokens_vs_live_feature_getters(golden, tag, dtype):
+    """One fused sample of the (4, 1, N, C) layer stack == the live ``get_intermediate_feature`` (4 samples + mean);
+    the normalised sample of the final features == the live ``get_feature``.  Forward and token gradients."""
+    import numpy as np
+    from gd3 import ops
+    g = golden('live_bodies.npz')
+    gh, gw = (int(v) for v in g[f'{tag}/grid'])
+    layers = T(g[f'{tag}/layers']).to(dtype).cuda()[:, None].contiguous().requires_grad_(True)      # (L, P = 1, N, C)
+    final = T(g[f'{tag}/final']).to(dtype).cuda()[None].contiguous().requires_grad_(True)
+    kp = T(g[f'{tag}/kp']).cuda()
+    feat = ops.sample_tokens(layers, (gh, gw), kp, normalize=False)
+    desc = ops.sample_tokens(final, (gh, gw), kp, normalize=True)
+    tol = dict(rtol=1e-5, atol=2e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(feat.detach().float().cpu().numpy(), g[f'{tag}/feat'], **tol)
+    np.testing.assert_allclose(desc.detach().float().cpu().numpy(), g[f'{tag}/desc'], **tol)
+    ((feat * T(g[f'{tag}/w_feat']).cuda()).sum() + (desc * T(g[f'{tag}/w_desc']).cuda()).sum()).backward()
+    cos_min = 0.99999 if dtype == torch.float32 else 0.999
+    assert_grad_close(layers.grad[:, 0].float().cpu(), T(g[f'{tag}/grad_layers']), cos_min=cos_min, name='layers', norm_rtol=3e-2)
+    assert_grad_close(final.grad[0].float().cpu(), T(g[f'{tag}/grad_final']), cos_min=cos_min, name='final', norm_rtol=3e-2)

@@ -303,3 +303,21 @@ def test_me_smooth_ap_against_live_training_step(golden, tag):
     assert rel_err(ap, g[f'{tag}/ap']) < 1e-5
     assert_grad_close(d1.grad, T(g[f'{tag}/grad_d1']), cos_min=0.99999, name='d1', norm_rtol=1e-3)
     assert_grad_close(d2.grad, T(g[f'{tag}/grad_d2']), cos_min=0.99999, name='d2', norm_rtol=1e-3)
+
+
+@pytest.mark.parametrize('tag', ['sample0', 'sample1'])
+def test_sampling_glue_against_live_feature_getters(golden, tag):
+    """``bodies.sample_tokens`` against the live ``get_intermediate_feature`` (4 layers sampled separately, then averaged)
+    and ``get_feature`` (final features, L2-normalised) of ``FinetuneMASt3RTIMM`` run on a stand-in ViT."""
+    g = golden('live_bodies.npz')
+    gh, gw = (int(v) for v in g[f'{tag}/grid'])
+    layers = T(g[f'{tag}/layers']).clone().requires_grad_(True)       # (4, N, C)
+    final = T(g[f'{tag}/final']).clone().requires_grad_(True)
+    kp = T(g[f'{tag}/kp'])
+    feat = torch.stack([bodies.sample_tokens(layers[l][None], gh, gw, kp) for l in range(4)]).mean(dim=0)
+    desc = bodies.sample_tokens(final[None], gh, gw, kp, normalize=True)
+    np.testing.assert_allclose(feat.detach().numpy(), g[f'{tag}/feat'], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(desc.detach().numpy(), g[f'{tag}/desc'], rtol=1e-5, atol=1e-6)
+    ((feat * T(g[f'{tag}/w_feat'])).sum() + (desc * T(g[f'{tag}/w_desc'])).sum()).backward()
+    assert_grad_close(layers.grad, T(g[f'{tag}/grad_layers']), cos_min=0.99999, name='layers', norm_rtol=1e-3)
+    assert_grad_close(final.grad, T(g[f'{tag}/grad_final']), cos_min=0.99999, name='final', norm_rtol=1e-3)
