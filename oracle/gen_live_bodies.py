@@ -11,6 +11,7 @@ win: the finder is appended), the modules are imported unmodified, and
     FinetuneVGGTTIMM.calculate_cost_loss   / calculate_matching_loss / calculate_depth_loss
     FinetuneTIMM.training_step             (src/finetune_timm_me.py: the ME baseline's Smooth-AP with 3-D positives)
     FinetuneMASt3RTIMM.get_intermediate_feature / get_feature   (keypoint sampling glue, stand-in ViT)
+    FinetuneMASt3RTIMM.filter_and_match_keypoints               (teacher-side keypoints: reciprocal NN + filters)
 
 are called as plain functions on a stand-in ``self`` that supplies what they read from the module: the ViT feature
 getters (returning the given synthetic features instead of running a backbone), ``depth_diff_head`` (the live
@@ -235,6 +236,25 @@ def main():
                     f'{tag}/grad_layers': _np(torch.stack([t.grad[0, 1:] for t in layers])),
                     f'{tag}/grad_final': _np(final.grad[0, 1:])})
         print(tag, tuple(feat.shape), tuple(desc.shape))
+    # ---- teacher-side keypoints (src/finetune_timm_mast3r.py:392-469): live fast_reciprocal_NNs + border and confidence
+    #      filters on exactly-representable descriptor maps ----
+    for case, (mh, mw, thr) in enumerate([(64, 96, 10.0), (48, 80, 35.0)]):
+        tag = f'kpmatch{case}'
+        dmap1, dmap2 = synth.nn_desc_maps(800 + case, mh, mw, noise=0.5)
+        dmap2 = torch.roll(dmap2, shifts=(3, -5), dims=(0, 1))          # view 2 is a shifted, noisier copy of view 1
+        dmap1, dmap2 = torch.round(dmap1 * 16) / 8, torch.round(dmap2 * 16) / 8
+        g = torch.Generator().manual_seed(810 + case)
+        conf1, conf2 = torch.rand(mh, mw, generator=g) + 1.0, torch.rand(mh, mw, generator=g) + 1.0
+        me = _Self({})
+        me.min_conf_thr = thr
+        feats = dict(view_1=dict(true_shape=torch.tensor([[mh, mw]])), view_2=dict(true_shape=torch.tensor([[mh, mw]])),
+                     desc_1=dmap1, desc_2=dmap2, conf_1=conf1, conf_2=conf2)
+        rgb = torch.zeros(1, 3, mh, mw)
+        kp_1, kp_2, _, _, w_, h_ = ft_mast3r.FinetuneMASt3RTIMM.filter_and_match_keypoints(me, feats, rgb, rgb)
+        out.update({f'{tag}/desc1_x8': _np(dmap1 * 8).astype(np.int8), f'{tag}/desc2_x8': _np(dmap2 * 8).astype(np.int8), f'{tag}/conf1': _np(conf1), f'{tag}/conf2': _np(conf2),
+                    f'{tag}/min_conf_thr': np.array(thr, dtype=np.float32), f'{tag}/kp1': _np(kp_1), f'{tag}/kp2': _np(kp_2),
+                    f'{tag}/wh': np.array([w_, h_])})
+        print(tag, tuple(kp_1.shape))
     out['meta'] = np.array([ph, pw, C, K])
     np.savez_compressed(os.path.join(OUT, 'live_bodies.npz'), **out)
 

@@ -105,3 +105,17 @@ def test_sample_tokens_vs_live_feature_getters(golden, tag, dtype):
     cos_min = 0.99999 if dtype == torch.float32 else 0.999
     assert_grad_close(layers.grad[:, 0].float().cpu(), T(g[f'{tag}/grad_layers']), cos_min=cos_min, name='layers', norm_rtol=3e-2)
     assert_grad_close(final.grad[0].float().cpu(), T(g[f'{tag}/grad_final']), cos_min=cos_min, name='final', norm_rtol=3e-2)
+
+
+@pytest.mark.parametrize('tag', ['kpmatch0', 'kpmatch1'])
+def test_teacher_keypoints_vs_live_method(golden, tag):
+    """Device-side reciprocal matching + border / confidence filters == the live
+    ``FinetuneMASt3RTIMM.filter_and_match_keypoints`` (src/finetune_timm_mast3r.py:392-469), keypoint for keypoint."""
+    from gd3.compat import keypoints
+    g = golden('live_bodies.npz')
+    feats = dict(desc_1=T(g[f'{tag}/desc1_x8']).float() / 8, desc_2=T(g[f'{tag}/desc2_x8']).float() / 8,
+                 conf_1=T(g[f'{tag}/conf1']), conf_2=T(g[f'{tag}/conf2']))
+    kp1, kp2, w, h = keypoints.filter_and_match_keypoints(feats, float(g[f'{tag}/min_conf_thr']))
+    assert kp1.is_cuda and kp1.dtype == torch.float32
+    assert (w, h) == tuple(int(v) for v in g[f'{tag}/wh'])
+    assert torch.equal(kp1.cpu(), T(g[f'{tag}/kp1'])) and torch.equal(kp2.cpu(), T(g[f'{tag}/kp2']))
