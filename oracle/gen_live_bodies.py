@@ -12,6 +12,7 @@ win: the finder is appended), the modules are imported unmodified, and
     FinetuneTIMM.training_step             (src/finetune_timm_me.py: the ME baseline's Smooth-AP with 3-D positives)
     FinetuneMASt3RTIMM.get_intermediate_feature / get_feature   (keypoint sampling glue, stand-in ViT)
     FinetuneMASt3RTIMM.filter_and_match_keypoints               (teacher-side keypoints: reciprocal NN + filters)
+    FinetuneMASt3RTIMM.training_step                            (the whole step; teacher and ViT are stand-ins)
 
 are called as plain functions on a stand-in ``self`` that supplies what they read from the module: the ViT feature
 getters (returning the given synthetic features instead of running a backbone), ``depth_diff_head`` (the live
@@ -255,6 +256,73 @@ def main():
                     f'{tag}/min_conf_thr': np.array(thr, dtype=np.float32), f'{tag}/kp1': _np(kp_1), f'{tag}/kp2': _np(kp_2),
                     f'{tag}/wh': np.array([w_, h_])})
         print(tag, tuple(kp_1.shape))
+    # ---- one whole training_step of FinetuneMASt3RTIMM (src/finetune_timm_mast3r.py:592-676), live: keypoint
+    #      matching and filtering, the three feature getters, the three losses and their weighted sum.  Stand-ins: the
+    #      teacher (extract_mast3r_features returns fixed maps) and the ViT (returns fixed token tensors per image) ----
+    class _PairViT(_ViT):
+        def __init__(self, per_image):
+            self.per_image = per_image                      # 0 / 1 -> (layers, final)
+
+        def _which(self, x):
+            return int(float(x.mean()) > 0.5)               # image 1 is all zeros, image 2 all ones
+
+        def _intermediate_layers(self, x, n):
+            return list(self.per_image[self._which(x)][0])
+
+        def forward_features(self, x):
+            return self.per_image[self._which(x)][1]
+
+    mh, mw = ph * 14, pw * 14
+    g = torch.Generator().manual_seed(900)
+    # smooth token maps (a common component + per-token detail), view 2 = view 1 + noise: sampled descriptors of matched
+    # keypoints correlate, so the Smooth-AP sigmoids are not all saturated
+    def token_map(base=None):
+        t = torch.randn(1, 1, C, generator=g) + 0.35 * torch.randn(1, 1 + N, C, generator=g) if base is None \
+            else base.detach() + 0.08 * torch.randn(1, 1 + N, C, generator=g)
+        return t.requires_grad_(True)
+    first = ([token_map() for _ in range(4)], token_map())
+    tokens = [first, ([token_map(t) for t in first[0]], token_map(first[1]))]
+    dmap1, dmap2 = synth.nn_desc_maps(901, mh, mw, noise=0.5)
+    dmap1, dmap2 = torch.round(dmap1 * 16) / 8, torch.roll(torch.round(dmap2 * 16) / 8, shifts=(2, -3), dims=(0, 1))
+    conf1, conf2 = torch.rand(mh, mw, generator=g) + 1.0, torch.rand(mh, mw, generator=g) + 1.0
+    (pts1, z1), (pts2, z2) = synth.analytic_scene(mh, mw, 0), synth.analytic_scene(mh, mw, 1)
+    cost1, cost2 = synth.teacher_volume(902, N, 'mast3r'), synth.teacher_volume(903, N, 'mast3r')
+    teacher_out = dict(view_1=dict(true_shape=torch.tensor([[mh, mw]])), view_2=dict(true_shape=torch.tensor([[mh, mw]])),
+                       desc_1=dmap1, desc_2=dmap2, conf_1=conf1, conf_2=conf2, pts3d_1=pts1, pts3d_2_from_1=pts2,
+                       pts3d_2=pts2, cost_1=cost1, cost_2=cost2)
+    cls = ft_mast3r.FinetuneMASt3RTIMM
+    me = _Self({})
+    me.model = _PairViT(tokens)
+    me.input_transform = lambda x: x
+    me.refine_conv = torch.nn.Identity()
+    me.target_res, me.downsample_factor, me.min_conf_thr = max(mh, mw), 14, 10.0
+    me.ap_loss_weight, me.depth_loss_weight, me.intra_depth_loss_weight, me.kl_loss_weight = 1.0, 0.5, 1.0, 2.0
+    torch.manual_seed(78)
+    me.depth_diff_head = ref_model.DepthAwareFeatureFusion(C)
+    synth.load_head(me.depth_diff_head, synth.head_params(4400, C))
+    me.log = lambda *a, **k: None
+    me.extract_mast3r_features = lambda a, b: teacher_out
+    for name in ('filter_and_match_keypoints', 'calculate_depth_loss', 'calculate_cost_loss', 'calculate_matching_loss',
+                 'get_intermediate_feature', 'get_feature', 'get_feature_cost'):
+        setattr(me, name, types.MethodType(getattr(cls, name), me))
+    batch = dict(rgb_1=torch.zeros(1, 3, mh, mw), rgb_2=torch.ones(1, 3, mh, mw), rgb_mast3r_1=None, rgb_mast3r_2=None,
+                 intrinsic=torch.eye(3)[None], depth_1=z1[None], depth_2=z2[None])
+    loss = cls.training_step(me, batch, 0)
+    loss.backward()
+    fl = me.depth_diff_head.fusion_layer
+    out.update({'step/layers': _np(torch.stack([torch.stack([t[0, 1:] for t in tokens[v][0]]) for v in range(2)])),
+                'step/final': _np(torch.stack([tokens[v][1][0, 1:] for v in range(2)])),
+                'step/desc1_x8': _np(dmap1 * 8).astype(np.int8), 'step/desc2_x8': _np(dmap2 * 8).astype(np.int8),
+                'step/conf1': _np(conf1), 'step/conf2': _np(conf2), 'step/cost1': _np(cost1), 'step/cost2': _np(cost2),
+                'step/weights': np.array([1.0, 0.5, 1.0, 2.0], dtype=np.float32), 'step/min_conf_thr': np.array(10.0, dtype=np.float32),
+                'step/loss': _np(loss), 'step/parts': np.array([me.batch_metrics[k][0] for k in
+                                                                ('ap_loss', 'depth_loss', 'intra_depth_loss', 'kl_loss')]),
+                'step/grad_layers': _np(torch.stack([torch.stack([t.grad[0, 1:] for t in tokens[v][0]]) for v in range(2)])),
+                'step/grad_final': _np(torch.stack([tokens[v][1].grad[0, 1:] for v in range(2)])),
+                'step/grad_head': _np(torch.cat([p.grad.reshape(-1) for p in (fl[0].weight, fl[0].bias, fl[1].weight,
+                                                                              fl[1].bias, fl[3].weight, fl[3].bias)]))})
+    print('training_step loss', float(loss), 'parts (ap, depth, intra, kl)', [round(me.batch_metrics[k][0], 5) for k in
+                                                                              ('ap_loss', 'depth_loss', 'intra_depth_loss', 'kl_loss')])
     out['meta'] = np.array([ph, pw, C, K])
     np.savez_compressed(os.path.join(OUT, 'live_bodies.npz'), **out)
 

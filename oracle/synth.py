@@ -257,3 +257,13 @@ def vggt_qk(seed, B, heads, n, head_dim=64, skip=5, peak=0.6):
     k[:, :, half + skip:] += peak * q[:, :, skip:half][:, :, perm]
     k[:, :, skip:half] += peak * q[:, :, half + skip:][:, :, torch.argsort(perm)]
     return q.bfloat16(), k.bfloat16()
+
+
+def analytic_scene(h, w, view):
+    """Smooth per-pixel 3-D points (h, w, 3) and depths (h, w) of ``view`` 0 / 1, computed from pixel coordinates only
+    (no random state), for the end-to-end step fixtures: both the golden generator and the tests evaluate this."""
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
+    u, v = xs / w, ys / h
+    z = 1.5 + 0.8 * torch.sin(3.0 * u + 0.7 * view) * torch.cos(2.0 * v) + 0.05 * view
+    pts = torch.stack([(u - 0.5) * z, (v - 0.5) * z, z], dim=-1)
+    return pts.contiguous(), z.contiguous()
