@@ -2,8 +2,9 @@
 
 Test infrastructure only (see ``oracle/__init__.py``).  Plain PyTorch on CPU.
 
-**Parity unpinned**: the block is inline in the evaluation loop of ``src/evaluate_timm.py`` (which needs timm, the datasets and a checkpoint), so no golden vector could be
-produced by the live reference; the restatement re-types those lines around the same torch ops.
+Pinned: ``oracle/gen_live_bodies.py --eval`` runs the reference's ``semantic_transfer`` unmodified on CPU (dataset
+loader, ViT and ``Tensor.cuda`` replaced by stand-ins) and records the ``nn_idx`` it computes
+(``tests/golden/eval_argmax.npz``).
 """
 import torch
 import torch.nn.functional as F

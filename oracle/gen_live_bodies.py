@@ -13,6 +13,7 @@ win: the finder is appended), the modules are imported unmodified, and
     FinetuneMASt3RTIMM.get_intermediate_feature / get_feature   (keypoint sampling glue, stand-in ViT)
     FinetuneMASt3RTIMM.filter_and_match_keypoints               (teacher-side keypoints: reciprocal NN + filters)
     FinetuneMASt3RTIMM.training_step                            (the whole step; teacher and ViT are stand-ins)
+    evaluate_timm.semantic_transfer                             (--eval -> tests/golden/eval_argmax.npz)
 
 are called as plain functions on a stand-in ``self`` that supplies what they read from the module: the ViT feature
 getters (returning the given synthetic features instead of running a backbone), ``depth_diff_head`` (the live
@@ -327,5 +328,60 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'live_bodies.npz'), **out)
 
 
+def semantic_transfer_golden():
+    """``tests/golden/eval_argmax.npz`` from the LIVE ``semantic_transfer`` (``src/evaluate_timm.py:461-588``).
+
+    The function is run unmodified on CPU for one image pair.  Stand-ins: the dataset loader (two blank images and fixed
+    keypoints), the ViT (fixed token tensors per image) and ``Tensor.cuda`` (identity: there is no GPU here);
+    ``torch.argmax`` is wrapped for the duration of the call to record the similarity maxima and ``nn_idx``, which the
+    function itself only folds into PCK numbers."""
+    from PIL import Image
+    import_live_modules()
+    import evaluate_timm as ev
+    img_size, ph, C, K = 640, 40, 24, 12
+    g = torch.Generator().manual_seed(5)
+    tok = [torch.randn(1, 1 + ph * ph, C, generator=g) for _ in range(2)]
+    # image 2 = shifted, noisy copy of image 1, smoothed like real ViT features
+    shifted = tok[0][:, 1:].reshape(1, ph, ph, C).roll(shifts=(2, -1), dims=(1, 2))
+    tok[1][:, 1:] = (shifted + 0.3 * torch.randn(1, ph, ph, C, generator=g)).reshape(1, -1, C)
+    kps = torch.zeros(2, K, 3)
+    kps[:, :, :2] = torch.randint(20, 620, (2, K, 2), generator=g).float()
+    kps[:, :, 2] = 1
+
+    class _EvalViT:
+        def forward_features(self, x):
+            return tok[int(float(x.mean()) > 0)]          # image 1 is black, image 2 white (after imagenet_norm: < 0 / > 0)
+
+    model = types.SimpleNamespace(model=_EvalViT())
+    blank = {'img_a': Image.fromarray(np.zeros((480, 640, 3), np.uint8)),
+             'img_b': Image.fromarray(np.full((480, 640, 3), 255, np.uint8))}
+    seen = {}
+    real = dict(argmax=torch.argmax, cuda=torch.Tensor.cuda, seed=torch.cuda.manual_seed, load=ev.load_pascal_data,
+                open=ev.Image.open)
+
+    def recording_argmax(x, *a, **k):
+        res = real['argmax'](x, *a, **k)
+        seen['best'], seen['nn_idx'] = x.max(dim=1).values.clone(), res.clone()
+        return res
+    try:
+        torch.argmax = recording_argmax
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.cuda.manual_seed = lambda s: None
+        ev.load_pascal_data = lambda *a, **k: (['img_a', 'img_b'], kps, None)
+        ev.Image.open = lambda fn: blank[fn]
+        ev.semantic_transfer(model, num_cats=1)
+    finally:
+        torch.argmax, torch.Tensor.cuda, torch.cuda.manual_seed = real['argmax'], real['cuda'], real['seed']
+        ev.load_pascal_data, ev.Image.open = real['load'], real['open']
+    out = {'tokens1': _np(tok[0][0, 1:]), 'tokens2': _np(tok[1][0, 1:]), 'kps1': _np(kps[0]),
+           'nn_idx': _np(seen['nn_idx']), 'best': _np(seen['best']),
+           'meta': np.array([img_size, 16, 16, ph, C, K])}
+    np.savez_compressed(os.path.join(OUT, 'eval_argmax.npz'), **out)
+    print('semantic_transfer nn_idx', seen['nn_idx'][:6].tolist())
+
+
 if __name__ == '__main__':
-    main()
+    if '--eval' in sys.argv:
+        semantic_transfer_golden()
+    else:
+        main()

@@ -58,3 +58,24 @@ def test_semantic_argmax_exact_and_ties():
     i1 = _lib.semantic_argmax(kd.cuda(), d2.cuda(), img, patch, stride)
     i2 = _lib.semantic_argmax(kd[0].t().contiguous().cuda(), d2.cuda(), img, patch, stride)
     assert torch.equal(i1, i2)
+
+
+def test_semantic_argmax_vs_live_semantic_transfer(golden):
+    """The CUDA path (``interpolate_features`` + ``semantic_argmax``) against ``nn_idx`` recorded inside the reference's
+    own ``semantic_transfer`` run live (``tests/golden/eval_argmax.npz``)."""
+    import numpy as np
+    from gd3.compat import evaluate
+    from gd3.compat import functions as cfn
+    g = golden('eval_argmax.npz')
+    img, patch, stride, ph, C, K = (int(v) for v in g['meta'])
+    d1 = torch.from_numpy(g['tokens1']).reshape(1, ph, ph, C).permute(0, 3, 1, 2).contiguous().cuda()
+    d2 = torch.from_numpy(g['tokens2']).reshape(1, ph, ph, C).permute(0, 3, 1, 2).contiguous()
+    kps = torch.from_numpy(g['kps1'])[None, :, :2].cuda()
+    kd = cfn.interpolate_features(d1, kps, h=img, w=img, normalize=True)
+    idx, xy = evaluate.semantic_argmax(kd, d2.cuda(), img, patch, stride)
+    idx = idx.cpu().numpy()
+    # a different index is acceptable only as a rounding-level near-tie of the similarity (checked on the oracle's map)
+    _, sim = oracle_eval.semantic_argmax(kd.cpu(), d2, img, patch, stride)
+    at = sim[torch.arange(K), torch.from_numpy(idx)].numpy()
+    assert (np.abs(at - g['best']) <= 2e-6 * np.maximum(1.0, np.abs(g['best']))).all()
+    assert (idx == g['nn_idx']).mean() >= 0.9

@@ -321,3 +321,18 @@ def test_sampling_glue_against_live_feature_getters(golden, tag):
     ((feat * T(g[f'{tag}/w_feat'])).sum() + (desc * T(g[f'{tag}/w_desc'])).sum()).backward()
     assert_grad_close(layers.grad, T(g[f'{tag}/grad_layers']), cos_min=0.99999, name='layers', norm_rtol=1e-3)
     assert_grad_close(final.grad, T(g[f'{tag}/grad_final']), cos_min=0.99999, name='final', norm_rtol=1e-3)
+
+
+def test_semantic_argmax_oracle_against_live_semantic_transfer(golden):
+    """``oracle.evaluate.semantic_argmax`` against ``nn_idx`` recorded inside the live ``semantic_transfer``
+    (``src/evaluate_timm.py:461-588``, run by ``oracle/gen_live_bodies.py --eval``; row f3)."""
+    from oracle import evaluate
+    g = golden('eval_argmax.npz')
+    img, patch, stride, ph, C, K = (int(v) for v in g['meta'])
+    d1 = T(g['tokens1']).reshape(1, ph, ph, C).permute(0, 3, 1, 2)
+    d2 = T(g['tokens2']).reshape(1, ph, ph, C).permute(0, 3, 1, 2)
+    # the live call passes h = w = img_size and leaves patch_size / stride at their defaults (:542)
+    kd = functions.interpolate_features(d1, T(g['kps1'])[None, :, :2], h=img, w=img, normalize=True)
+    idx, sim = evaluate.semantic_argmax(kd, d2, img, patch, stride)
+    assert (idx.numpy() == g['nn_idx']).all()
+    np.testing.assert_allclose(sim.max(dim=1).values.numpy(), g['best'], rtol=1e-6)
