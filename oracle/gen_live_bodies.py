@@ -13,6 +13,7 @@ win: the finder is appended), the modules are imported unmodified, and
     FinetuneMASt3RTIMM.get_intermediate_feature / get_feature   (keypoint sampling glue, stand-in ViT)
     FinetuneMASt3RTIMM.filter_and_match_keypoints               (teacher-side keypoints: reciprocal NN + filters)
     FinetuneMASt3RTIMM.training_step                            (the whole step; teacher and ViT are stand-ins)
+    FinetuneVGGTTIMM.training_step                              (likewise; the teacher's tracker picks the keypoints)
     evaluate_timm.semantic_transfer                             (--eval -> tests/golden/eval_argmax.npz)
 
 are called as plain functions on a stand-in ``self`` that supplies what they read from the module: the ViT feature
@@ -268,7 +269,7 @@ def main():
             return int(float(x.mean()) > 0.5)               # image 1 is all zeros, image 2 all ones
 
         def _intermediate_layers(self, x, n):
-            return list(self.per_image[self._which(x)][0])
+            return [self.per_image[self._which(x)][0][i - 4] for i in n]      # blocks 4..7 are held
 
         def forward_features(self, x):
             return self.per_image[self._which(x)][1]
@@ -324,6 +325,51 @@ def main():
                                                                               fl[1].bias, fl[3].weight, fl[3].bias)]))})
     print('training_step loss', float(loss), 'parts (ap, depth, intra, kl)', [round(me.batch_metrics[k][0], 5) for k in
                                                                               ('ap_loss', 'depth_loss', 'intra_depth_loss', 'kl_loss')])
+    # ---- the same for FinetuneVGGTTIMM.training_step (src/finetune_timm_vggt.py:577-639): KL on block 7 only with
+    #      co-visibility pixel masks, the vggt Smooth-AP variant, all loss weights 1.  Stand-ins: the teacher
+    #      (extract_vggt_features, sample_keypoints -- its tracker picks the keypoints) and the ViT ----
+    g = torch.Generator().manual_seed(950)
+    vtokens = [([t.detach().clone().requires_grad_(True) for t in tokens[v][0]],
+                tokens[v][1].detach().clone().requires_grad_(True)) for v in range(2)]
+    vkp1 = synth.keypoints(951, K, mw, mh)[None]
+    vkp2 = (vkp1 + torch.randint(-4, 5, vkp1.shape, generator=g).float())
+    vkp2[..., 0].clamp_(3, mw - 4)
+    vkp2[..., 1].clamp_(3, mh - 4)
+    pm1 = (torch.rand(ph, pw, generator=g) < 0.6).repeat_interleave(14, 0).repeat_interleave(14, 1)
+    pm2 = (torch.rand(ph, pw, generator=g) < 0.6).repeat_interleave(14, 0).repeat_interleave(14, 1)
+    vcost1, vcost2 = synth.teacher_volume(952, N, 'vggt'), synth.teacher_volume(953, N, 'vggt')
+    vfeat = dict(depth_pred_1=z1, depth_pred_2=z2, cost_1=vcost1[None], cost_2=vcost2[None], point_map_view_1=pts1,
+                 point_map_view_2=pts2, image_shape=(mh, mw))
+    vcls = ft_vggt.FinetuneVGGTTIMM
+    vme = _Self({})
+    vme.model = _PairViT(vtokens)
+    vme.input_transform = lambda x: x
+    vme.refine_conv = torch.nn.Identity()
+    vme.target_res, vme.downsample_factor = max(mh, mw), 14
+    vme.ap_loss_weight, vme.depth_loss_weight, vme.intra_depth_loss_weight, vme.kl_loss_weight = 1.0, 1.0, 1.0, 1.0
+    torch.manual_seed(79)
+    vme.depth_diff_head = ref_model.DepthAwareFeatureFusion(C)
+    synth.load_head(vme.depth_diff_head, synth.head_params(4401, C))
+    vme.log = lambda *a, **k: None
+    vme.extract_vggt_features = lambda rgb, batch_idx=None: vfeat
+    vme.sample_keypoints = lambda feats, num_keypoints=300, min_distance=5: (vkp1, vkp2, None, pm1, pm2)
+    for name in ('calculate_depth_loss', 'calculate_cost_loss', 'calculate_matching_loss', 'get_intermediate_feature',
+                 'get_feature', 'get_feature_cost'):
+        setattr(vme, name, types.MethodType(getattr(vcls, name), vme))
+    vbatch = dict(rgb_1=torch.zeros(1, 3, mh, mw), rgb_2=torch.ones(1, 3, mh, mw), rgb_vggt=None)
+    vloss = vcls.training_step(vme, vbatch, 0)
+    vloss.backward()
+    fl = vme.depth_diff_head.fusion_layer
+    out.update({'vstep/kp1': _np(vkp1), 'vstep/kp2': _np(vkp2), 'vstep/pixmask1': _np(pm1), 'vstep/pixmask2': _np(pm2),
+                'vstep/cost1': _np(vcost1), 'vstep/cost2': _np(vcost2), 'vstep/loss': _np(vloss),
+                'vstep/parts': np.array([vme.batch_metrics[k][0] for k in ('ap_loss', 'depth_loss', 'intra_depth_loss', 'kl_loss')]),
+                'vstep/grad_layers': _np(torch.stack([torch.stack([t.grad[0, 1:] if t.grad is not None else torch.zeros_like(t[0, 1:])
+                                                                   for t in vtokens[v][0]]) for v in range(2)])),
+                'vstep/grad_final': _np(torch.stack([vtokens[v][1].grad[0, 1:] for v in range(2)])),
+                'vstep/grad_head': _np(torch.cat([p.grad.reshape(-1) for p in (fl[0].weight, fl[0].bias, fl[1].weight,
+                                                                               fl[1].bias, fl[3].weight, fl[3].bias)]))})
+    print('vggt training_step loss', float(vloss), 'parts (ap, depth, intra, kl)',
+          [round(vme.batch_metrics[k][0], 5) for k in ('ap_loss', 'depth_loss', 'intra_depth_loss', 'kl_loss')])
     out['meta'] = np.array([ph, pw, C, K])
     np.savez_compressed(os.path.join(OUT, 'live_bodies.npz'), **out)
 
