@@ -336,3 +336,62 @@ def test_semantic_argmax_oracle_against_live_semantic_transfer(golden):
     idx, sim = evaluate.semantic_argmax(kd, d2, img, patch, stride)
     assert (idx.numpy() == g['nn_idx']).all()
     np.testing.assert_allclose(sim.max(dim=1).values.numpy(), g['best'], rtol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['kpmatch0', 'kpmatch1'])
+def test_keypoint_selection_oracle_against_live_method(golden, tag):
+    from oracle import keypoints
+    g = golden('live_bodies.npz')
+    kp1, kp2 = keypoints.filter_and_match_keypoints(T(g[f'{tag}/desc1_x8']).float() / 8, T(g[f'{tag}/desc2_x8']).float() / 8,
+                                                    T(g[f'{tag}/conf1']), T(g[f'{tag}/conf2']),
+                                                    float(g[f'{tag}/min_conf_thr']))
+    assert torch.equal(kp1, T(g[f'{tag}/kp1'])) and torch.equal(kp2, T(g[f'{tag}/kp2']))
+
+
+@pytest.mark.parametrize('which', ['step', 'vstep'])
+def test_oracle_whole_step_against_live_training_step(golden, which):
+    """The oracle pieces chained like the reference's ``training_step`` reproduce the live step (both modules): total,
+    partial losses and the gradients w.r.t. every ViT token and the depth head."""
+    from oracle import keypoints
+    g = golden('live_bodies.npz')
+    ph, pw, C, _ = (int(v) for v in g['meta'])
+    H, W = ph * 14, pw * 14
+    variant = 'mast3r' if which == 'step' else 'vggt'
+    layers = T(g['step/layers']).clone().requires_grad_(True)          # (view, block, N, C)
+    final = T(g['step/final']).clone().requires_grad_(True)
+    (pts1, z1), (pts2, z2) = synth.analytic_scene(H, W, 0), synth.analytic_scene(H, W, 1)
+    head = losses.DepthHead(C)
+    synth.load_head(head, synth.head_params(4400 if which == 'step' else 4401, C))
+    if which == 'step':
+        w_ap, w_depth, w_intra, w_kl = (float(v) for v in g['step/weights'])
+        kp1, kp2 = keypoints.filter_and_match_keypoints(T(g['step/desc1_x8']).float() / 8, T(g['step/desc2_x8']).float() / 8,
+                                                        T(g['step/conf1']), T(g['step/conf2']), float(g['step/min_conf_thr']))
+        m1 = functions.get_patch_mask_from_kp_tensor(kp1[0], H, W, 14)
+        m2 = functions.get_patch_mask_from_kp_tensor(kp2[0], H, W, 14)
+        f1, f2 = layers[0].mean(dim=0), layers[1].mean(dim=0)           # mean of blocks 4..7
+    else:
+        w_ap = w_depth = w_intra = w_kl = 1.0
+        kp1, kp2 = T(g['vstep/kp1']), T(g['vstep/kp2'])
+        m1 = T(g['vstep/pixmask1'])[::14, ::14].reshape(-1)
+        m2 = T(g['vstep/pixmask2'])[::14, ::14].reshape(-1)
+        f1, f2 = layers[0, 3], layers[1, 3]                             # block 7 only
+    kl = bodies.cost_volume_kl(f1, f2, T(g[f'{which}/cost1']), T(g[f'{which}/cost2']), m1, m2, variant)
+    kf1 = torch.stack([bodies.sample_tokens(layers[0, l][None], ph, pw, kp1) for l in range(4)]).mean(dim=0)
+    kf2 = torch.stack([bodies.sample_tokens(layers[1, l][None], ph, pw, kp2) for l in range(4)]).mean(dim=0)
+    l1, rank = bodies.depth_losses(head, kf1, kf2, functions.extract_kp_depth(z1, kp1), functions.extract_kp_depth(z2, kp2))
+    d1 = bodies.sample_tokens(final[0:1], ph, pw, kp1, normalize=True)[0]
+    d2 = bodies.sample_tokens(final[1:2], ph, pw, kp2, normalize=True)[0]
+    p1 = pts1[kp1[0, :, 1].long(), kp1[0, :, 0].long()]
+    p2 = pts2[kp2[0, :, 1].long(), kp2[0, :, 0].long()]
+    ap = bodies.smooth_ap(d1, d2, p1, p2, variant)
+    loss = w_ap * ap + w_depth * l1 + w_intra * rank + w_kl * kl
+    loss.backward()
+    for got, ref in zip((ap, l1, rank, kl), g[f'{which}/parts']):
+        assert rel_err(got, ref) < 1e-5
+    assert rel_err(loss, g[f'{which}/loss']) < 1e-5
+    assert_grad_close(layers.grad, T(g[f'{which}/grad_layers']), cos_min=0.99999, name='block tokens', norm_rtol=1e-3)
+    assert_grad_close(final.grad, T(g[f'{which}/grad_final']), cos_min=0.99999, name='final tokens', norm_rtol=1e-3)
+    fl = head.fusion_layer
+    packed = torch.cat([q.grad.reshape(-1) for q in (fl[0].weight, fl[0].bias, fl[1].weight, fl[1].bias, fl[3].weight,
+                                                     fl[3].bias)])
+    assert_grad_close(packed, T(g[f'{which}/grad_head']), cos_min=0.99999, name='head', norm_rtol=1e-3)
