@@ -726,7 +726,9 @@ int gd3_fast_reciprocal_nn(const float* pts1, int64_t n1, const float* pts2, int
     }
     GD3_CHECK_LAUNCH();
     if (!last && host_poll && it >= 1) {
-      // nothing can converge before the second round; from then on ask the device how many seeds are still live
+      // a seed can converge in round 0 already (its nearest neighbour maps straight back to it), but never all of
+      // them on real data, so the poll is skipped for the first round only to save a synchronisation; from then on
+      // ask the device how many seeds are still live
       // (4 bytes + one stream synchronisation per round) instead of launching rounds that have nothing to do
       int h_live = 0;
       GD3_CHECK_CUDA(cudaMemcpyAsync(&h_live, st.n_live, sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -2,7 +2,7 @@
 //   patch mask   get_patch_mask_from_kp_tensor, utils/functions.py:375-399: patch (y // p) * (W // p) + (x // p) of
 //                every in-image keypoint is marked; out-of-image keypoints are dropped.
 //   keypoint depth   extract_kp_depth, utils/functions.py:348-372: mean of the replicate-padded window x window
-//                neighbourhood of the depth map at the integer keypoint (window sums in row-major order, then / n).
+//                neighbourhood of the depth map at flat index (y * W + x).long() (window sums in row-major order, then / n).
 // One thread per keypoint; the reference does this per pair with a dozen small torch ops.
 #include "../../include/gd3.h"
 #include "common.cuh"
@@ -27,7 +27,16 @@ __global__ void kp_prepare_kernel(const float* __restrict__ kp, int P, int K, in
   }
   if (kp_depth) {
     const float* d = depth + (int64_t)p * depth_pair_stride;
-    const int xi = (int)x, yi = (int)y, r = window / 2;
+    // the reference gathers at the flat index (y * W + x).long() computed in fp32 (utils/functions.py:366-369), which
+    // differs from truncating x and y separately for fractional keypoints; its gather raises for an index outside
+    // the map, here such a keypoint gets NaN (no host round trip inside the step)
+    const float fidx = __fadd_rn(__fmul_rn(y, (float)W), x);
+    const int64_t idx = (int64_t)fidx;       // truncation toward zero like .long()
+    if (!(fidx > -1.f) || idx >= (int64_t)H * W) {
+      kp_depth[e] = __int_as_float(0x7fc00000);
+      return;
+    }
+    const int yi = (int)(idx / W), xi = (int)(idx - (int64_t)yi * W), r = window / 2;
     float acc = 0.f;
     for (int dy = -r; dy <= r; ++dy) {
       const int yy = min(max(yi + dy, 0), H - 1);

@@ -200,14 +200,21 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// loss[p] = acc / Q, scale[p] = 1 / Q  (Q = 0 -> mean of an empty set: NaN like the reference, zero gradient)
+// loss[p] = acc / Q, scale[p] = 1 / Q  (Q = 0 -> mean of an empty set: NaN like the reference, zero gradient).
+// joint (GD3_VARIANT_ME_JOINT): Q is the number of positives of the WHOLE batch, as src/finetune_timm_me.py:202-217
+// takes one mean over the positives of all B pairs; loss[p] is then pair p's share (sum_p loss[p] = the reference
+// loss) and a pair without positives contributes 0 instead of NaN.
 __global__ void ap_finalize(const double* __restrict__ acc, const int* __restrict__ q, float* __restrict__ loss,
-                            float* __restrict__ scale, int P) {
+                            float* __restrict__ scale, int P, int joint) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < P) {
-    const int Q = q[p];
+    long long Q = q[p];
+    if (joint) {
+      Q = 0;
+      for (int k = 0; k < P; ++k) Q += q[k];
+    }
     loss[p] = Q > 0 ? (float)(acc[p] / (double)Q) : __int_as_float(0x7fc00000);
-    scale[p] = Q > 0 ? 1.f / (float)Q : 0.f;
+    scale[p] = Q > 0 ? (float)(1.0 / (double)Q) : 0.f;
   }
 }
 
@@ -371,8 +378,11 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
   GD3_REQUIRE(P > 0 && K >= 0 && C > 0, "gd3_smooth_ap: bad sizes P=%lld K=%lld C=%lld", (long long)P, (long long)K,
               (long long)C);
   GD3_REQUIRE(loss, "gd3_smooth_ap: null loss");
-  GD3_REQUIRE(variant == GD3_VARIANT_MAST3R || variant == GD3_VARIANT_VGGT || variant == GD3_VARIANT_ME,
+  GD3_REQUIRE(variant == GD3_VARIANT_MAST3R || variant == GD3_VARIANT_VGGT || variant == GD3_VARIANT_ME ||
+                  variant == GD3_VARIANT_ME_JOINT,
               "gd3_smooth_ap: unknown variant %d", variant);
+  const int joint = variant == GD3_VARIANT_ME_JOINT;
+  if (joint) variant = GD3_VARIANT_ME;
   GD3_REQUIRE(temp > 0.f, "gd3_smooth_ap: temperature must be positive");
   GD3_REQUIRE((grad_d1 == nullptr) == (grad_d2 == nullptr), "gd3_smooth_ap: pass both gradients or neither");
   GD3_REQUIRE(P <= 65535 && K <= 12000, "gd3_smooth_ap: P <= 65535 and K <= 12000 supported");
@@ -429,7 +439,7 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     GD3_CHECK_LAUNCH();
     {
       GD3_PROF("ap_finalize", stream);
-      ap_finalize<<<(unsigned)ceil_div<int64_t>(P, 128), 128, 0, stream>>>(w.loss_acc, w.qcount, loss, w.scale, (int)P);
+      ap_finalize<<<(unsigned)ceil_div<int64_t>(P, 128), 128, 0, stream>>>(w.loss_acc, w.qcount, loss, w.scale, (int)P, joint);
     }
     GD3_CHECK_LAUNCH();
   }
@@ -511,7 +521,7 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
     // one mean over every valid row of the batch: loss_acc[0] / qcount[0] (ap_finalize with P = 1)
     {
       GD3_PROF("ap_finalize", stream);
-      ap_finalize<<<1, 32, 0, stream>>>(w.loss_acc, w.qcount, loss_mean, w.scale, 1);
+      ap_finalize<<<1, 32, 0, stream>>>(w.loss_acc, w.qcount, loss_mean, w.scale, 1, 0);
     }
     GD3_CHECK_LAUNCH();
   }

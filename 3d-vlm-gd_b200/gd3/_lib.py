@@ -57,7 +57,7 @@ SYMBOLS = {
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 DIST = {'dot': 0, 'l2': 1}
-VARIANT = {'mast3r': 0, 'vggt': 1, 'me': 2}
+VARIANT = {'mast3r': 0, 'vggt': 1, 'me': 2, 'me_joint': 3}
 
 _lib = None
 

@@ -36,7 +36,11 @@ def get_patch_mask_from_kp_tensor(kp_xy, H, W, patch_size, device=None):
 
 
 def extract_kp_depth(depth_map, kp, window_size=3):
-    """``utils/functions.py:348-372``: mean depth in a replicate-padded window at integer keypoints -> (B, K)."""
+    """``utils/functions.py:348-372``: mean depth in a replicate-padded window at flat index ``(y * W + x).long()``
+    (fp32 arithmetic, so fractional keypoints land where the reference's gather lands) -> (B, K).
+
+    Difference: the reference's ``gather`` raises for an index outside the map; raising needs a host sync, so such a
+    keypoint gets NaN here (callers filter keypoints to the image first, src/finetune_timm_mast3r.py:421-426)."""
     if not torch.is_tensor(depth_map):
         depth_map = torch.tensor(depth_map, device=kp.device, dtype=torch.float)
     require_cuda(depth_map, kp)

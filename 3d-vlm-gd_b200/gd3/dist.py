@@ -21,13 +21,32 @@ def shard_range(num_pairs, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def shard_batch(batch, rank, world_size):
-    """Slice every per-pair tensor of a batch dict to this rank's chunk (the head is replicated)."""
+# per-pair entries of a batch dict (leading axis = pair; h1 / h2 / g1 / g2 may carry a layer axis in front of it);
+# anything else (head parameters, a depth map shared by all pairs, scalars) is replicated
+PAIR_KEYS = ('f1', 'f2', 't12', 't21', 'm1', 'm2', 'g1', 'g2', 'h1', 'h2', 'kp1', 'kp2', 'p3d1', 'p3d2', 'dep1', 'dep2',
+             'depth_map1', 'depth_map2')
+
+
+def shard_batch(batch, rank, world_size, pair_keys=PAIR_KEYS):
+    """Slice the per-pair tensors of a batch dict (``pair_keys``) to this rank's chunk; everything else is replicated.
+
+    Sharding goes by key, not by shape: a shared (H, W) depth map whose height happens to equal the number of pairs
+    stays whole (it is 2-D), a per-pair (P, H, W) stack is sliced."""
     P = batch['f1'].shape[0]
     b, e = shard_range(P, rank, world_size)
     out = {}
     for k, v in batch.items():
-        out[k] = v[b:e] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == P else v
+        if k in pair_keys and torch.is_tensor(v):
+            if k in ('depth_map1', 'depth_map2') and v.dim() == 2:
+                out[k] = v
+            elif k in ('g1', 'g2', 'h1', 'h2') and v.dim() == 4:
+                out[k] = v[:, b:e]
+            else:
+                if v.shape[0] != P:
+                    raise ValueError(f'shard_batch: {k} has leading size {v.shape[0]}, expected {P} pairs')
+                out[k] = v[b:e]
+        else:
+            out[k] = v
     return out
 
 
@@ -47,9 +66,17 @@ def gather_pair_losses(local_losses, num_pairs, group=None):
     return torch.cat([p[:e - b] for p, (b, e) in zip(parts, sizes)])
 
 
-def allreduce_mean_(tensor, group=None):
-    """In-place mean over ranks (the DDP gradient semantics for the replicated depth-head parameters)."""
+def allreduce_mean_(tensor, group=None, local_pairs=None, num_pairs=None):
+    """In-place mean over ranks (the DDP gradient semantics for the replicated depth-head parameters).
+
+    With uneven shards pass ``local_pairs`` / ``num_pairs``: ``distillation_step`` scales a rank's gradient by
+    1 / P_local, so the plain mean over ranks would over-weight the pairs of the smaller shards; the weighted form
+    ``sum_r (P_r / P) g_r`` is the gradient of the mean loss over all P pairs."""
     if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
-        tensor /= dist.get_world_size(group)
+        if local_pairs is not None:
+            tensor *= float(local_pairs) / float(num_pairs)
+            dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+            tensor /= dist.get_world_size(group)
     return tensor

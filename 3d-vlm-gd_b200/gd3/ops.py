@@ -155,6 +155,9 @@ def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1
     of ``calculate_matching_loss`` (variant 'mast3r': src/finetune_timm_mast3r.py:557-589, 'vggt':
     src/finetune_timm_vggt.py:543-574) or of src/finetune_timm_me.py:196-217 ('me') for each pair.
     K = 0 gives loss 0 (the callers' early-out, src/finetune_timm_mast3r.py:604-607).
+    'me' returns one mean per pair (a pair without positives is NaN, like a B = 1 reference call).  The reference's ME
+    step with B > 1 takes ONE mean over the positives of the whole batch: use variant 'me_joint', whose ``loss[p]`` is
+    pair p's share of that mean (``loss.sum()`` is the reference loss; pairs without positives contribute 0).
     """
     return _SmoothAP.apply(d1, d2, pts3d_1, pts3d_2, variant, temp, thr_neg, thr_pos, torch.is_grad_enabled())
 

@@ -30,14 +30,15 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     batch (all CUDA tensors):
       f1, f2     (P, N, C)  student patch features for the cost volume (fp32 / bf16)
       t12, t21   (P, N, N)  teacher volumes;  m1, m2 (P, N) bool patch masks
-      g1, g2     (P, N, C)  token maps the keypoint descriptors / depth features are sampled from
+      g1, g2     (P, N, C) or (L, P, N, C)  token maps the matching descriptors are sampled from (L maps: their mean)
+      h1, h2     optional, same shapes: token maps the depth-head features are sampled from (default: g1, g2)
       kp1, kp2   (P, K, 2)  pixel keypoints;  p3d1, p3d2 (P, K, 3);  dep1, dep2 (P, K) keypoint depths
       Derived on the device when absent (one ``gd3_kp_prepare`` launch per view): m1 / m2 = patches holding a keypoint
       (src/finetune_timm_mast3r.py:516-519), dep1 / dep2 = 3 x 3 window depths at the keypoints from ``depth_map1`` /
       ``depth_map2`` ((P, H, W) or one shared (H, W) map; src/finetune_timm_mast3r.py:482-483).
       head       dict W1, b1, gamma, beta, w2, b2 (+ use_tanh, ln_eps) of the depth-difference head
     Returns dict: kl, ap, rank, l1 (each (P,)), total (0-d) and, if backward, ``grads`` with f1, f2 (feature
-    dtype), g1, g2 (fp32) and head (packed [W1 | b1 | gamma | beta | w2 | b2]).
+    dtype), g1, g2 (fp32; h1, h2 too when given) and head (packed [W1 | b1 | gamma | beta | w2 | b2]).
     """
     w = dict(DEFAULT_WEIGHTS[variant])
     if weights:
@@ -53,20 +54,31 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     out = {}
 
     # ---- keypoint descriptors / features from the token maps (K3) ----
+    # g1 / g2: maps the matching descriptors are sampled from (the reference's refine_conv output, normalised);
+    # h1 / h2 (optional, default g1 / g2): maps the depth-head features are sampled from (the reference's mean of
+    # blocks 4..7, src/finetune_timm_mast3r.py:271-277 -- pass the (L, P, N, C) stack, the mean is folded into the sample)
     g1, g2 = batch['g1'], batch['g2']
+    h1, h2 = batch.get('h1', g1), batch.get('h2', g2)
     kp1 = batch['kp1'].to(_F32).contiguous()
     kp2 = batch['kp2'].to(_F32).contiguous()
     K = kp1.shape[1]
-    L1_, P1_, N1_, C1_, str1, gstr1 = ops.token_layout(g1)
-    _, _, _, _, str2, gstr2 = ops.token_layout(g2)
-    lay1, lay2 = (1, P, N, C1_, str1), (1, P, N, C1_, str2)
-    d1, inv1, ostr = ops.sample_fwd_raw(g1, lay1, geom, kp1, True)
-    d2, inv2, _ = ops.sample_fwd_raw(g2, lay2, geom, kp2, True)
+    lays = {}
+    for name, t in (('g1', g1), ('g2', g2), ('h1', h1), ('h2', h2)):
+        L_, P_, N_, C_, st, gst = ops.token_layout(t)
+        if P_ != P or N_ != ph * pw:
+            raise ValueError(f'distillation_step: {name} is {tuple(t.shape)}, expected (..., {P}, {ph * pw}, C) for a '
+                             f'{ph} x {pw} patch grid')
+        lays[name] = (L_, P_, N_, C_, st, gst)
+    if lays['g1'][3] != lays['g2'][3] or lays['h1'][3] != lays['h2'][3]:
+        raise ValueError('distillation_step: the two views must share the channel count of each token map')
+    Cd, Ch = lays['g1'][3], lays['h1'][3]
+    d1, inv1, ostr = ops.sample_fwd_raw(g1, lays['g1'][:5], geom, kp1, True)
+    d2, inv2, _ = ops.sample_fwd_raw(g2, lays['g2'][:5], geom, kp2, True)
     # depth features of both views interleaved as sets (2p, 2p+1) = (view 1, view 2) of pair p
-    kf = torch.empty(P, 2, K, C1_, dtype=_F32, device=dev)
-    pstr = (2 * K * C1_, C1_, 1)
-    ops.sample_fwd_raw(g1, lay1, geom, kp1, False, out=kf[:, 0], out_strides=pstr)
-    ops.sample_fwd_raw(g2, lay2, geom, kp2, False, out=kf[:, 1], out_strides=pstr)
+    kf = torch.empty(P, 2, K, Ch, dtype=_F32, device=dev)
+    pstr = (2 * K * Ch, Ch, 1)
+    ops.sample_fwd_raw(h1, lays['h1'][:5], geom, kp1, False, out=kf[:, 0], out_strides=pstr)
+    ops.sample_fwd_raw(h2, lays['h2'][:5], geom, kp2, False, out=kf[:, 1], out_strides=pstr)
     # patch masks and keypoint depths the caller did not supply
     prepared = {}
     for v, kp in (('1', kp1), ('2', kp2)):
@@ -85,7 +97,7 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     #      milliseconds, during which the host enqueues the many short kernels of the other losses without gaps ----
     w_rank = torch.full((2 * P,), 0.5 * w['intra'] * inv_p, dtype=_F32, device=dev)
     w_l1 = torch.full((P,), w['depth'] * inv_p, dtype=_F32, device=dev)
-    lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, C1_), depths, params,
+    lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, Ch), depths, params,
                                               head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
                                               depth_threshold, 0.05, False, w_rank, w_l1, backward)
 
@@ -102,15 +114,28 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
 
     if backward:
         # scatter the keypoint gradients back into the token maps (K3 backward)
-        gg1 = torch.zeros(P, N, C1_, dtype=_F32, device=dev)
-        gg2 = torch.zeros(P, N, C1_, dtype=_F32, device=dev)
-        dims = (1, P, K, C1_)
-        cont = (K * C1_, C1_, 1)
-        # descriptor gradients (through the normalisation) and depth-feature gradients share one scatter per view
-        gk = gkf.reshape(P, 2, K, C1_)
-        ops.sample_bwd_raw(gd1, cont, d1, ostr, inv1, kp1, dims, geom, True, gg1, gstr1, gk[:, 0], pstr)
-        ops.sample_bwd_raw(gd2, cont, d2, ostr, inv2, kp2, dims, geom, True, gg2, gstr2, gk[:, 1], pstr)
-        out['grads'] = dict(f1=gf1, f2=gf2, g1=gg1, g2=gg2, head=gparams)
+        def zeros_like_tokens(name):
+            L_, P_, N_, C_, _, _ = lays[name]
+            return torch.zeros((L_, P_, N_, C_) if batch_dim4[name] else (P_, N_, C_), dtype=_F32, device=dev)
+        batch_dim4 = {'g1': g1.dim() == 4, 'g2': g2.dim() == 4, 'h1': h1.dim() == 4, 'h2': h2.dim() == 4}
+        gk = gkf.reshape(P, 2, K, Ch)
+        cont = (K * Cd, Cd, 1)
+        gg1, gg2 = zeros_like_tokens('g1'), zeros_like_tokens('g2')
+        shared1, shared2 = h1 is g1, h2 is g2
+        # descriptor gradients (through the normalisation); when the depth features come from the same map their
+        # gradient shares the scatter
+        ops.sample_bwd_raw(gd1, cont, d1, ostr, inv1, kp1, (lays['g1'][0], P, K, Cd), geom, True, gg1, lays['g1'][5],
+                           gk[:, 0] if shared1 else None, pstr if shared1 else (0, 0, 0))
+        ops.sample_bwd_raw(gd2, cont, d2, ostr, inv2, kp2, (lays['g2'][0], P, K, Cd), geom, True, gg2, lays['g2'][5],
+                           gk[:, 1] if shared2 else None, pstr if shared2 else (0, 0, 0))
+        grads_h = {}
+        for name, shared, view, kp in (('h1', shared1, 0, kp1), ('h2', shared2, 1, kp2)):
+            if not shared:
+                gh = zeros_like_tokens(name)
+                ops.sample_bwd_raw(gk[:, view], pstr, None, (0, 0, 0), None, kp, (lays[name][0], P, K, Ch), geom, False,
+                                   gh, lays[name][5])
+                grads_h[name] = gh
+        out['grads'] = dict(f1=gf1, f2=gf2, g1=gg1, g2=gg2, head=gparams, **grads_h)
     return out
 
 

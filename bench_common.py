@@ -46,7 +46,7 @@ def to_device(batch, device, feature_dtype=None, non_blocking=False):
             out[k] = {n: (t.to(device, non_blocking=non_blocking) if torch.is_tensor(t) else t) for n, t in v.items()}
         elif torch.is_tensor(v):
             t = v.to(device, non_blocking=non_blocking)
-            if feature_dtype is not None and k in ('f1', 'f2', 'g1', 'g2'):
+            if feature_dtype is not None and k in ('f1', 'f2', 'g1', 'g2', 'h1', 'h2'):
                 t = t.to(feature_dtype)
             out[k] = t
         else:
@@ -71,8 +71,23 @@ def oracle_step(batch, cfg, backward=True, pairs=None):
     w = WEIGHTS[variant]
     P = batch['f1'].shape[0] if pairs is None else pairs
     C = batch['f1'].shape[2]
-    head = oracle_head(batch, C)
+    head = oracle_head(batch, batch['head']['W1'].shape[1])
     leaves = {k: batch[k][:P].clone().float().requires_grad_(backward) for k in ('f1', 'f2', 'g1', 'g2')}
+    # optional separate maps for the depth-head features, (P, N, C) or an (L, P, N, C) stack of ViT blocks whose
+    # samples are averaged (get_intermediate_feature, src/finetune_timm_mast3r.py:271-277)
+    for k in ('h1', 'h2'):
+        if k in batch:
+            t = batch[k]
+            leaves[k] = (t[:, :P] if t.dim() == 4 else t[:P]).clone().float().requires_grad_(backward)
+
+    def depth_feats(name, fallback, p, kp):
+        if name not in leaves:
+            return bodies.sample_tokens(fallback, ph, pw, kp, normalize=False)
+        t = leaves[name]
+        if t.dim() == 3:
+            return bodies.sample_tokens(t[p:p + 1], ph, pw, kp, normalize=False)
+        return torch.stack([bodies.sample_tokens(t[l, p:p + 1], ph, pw, kp, normalize=False)
+                            for l in range(t.shape[0])]).mean(dim=0)
     res = {k: [] for k in ('kl', 'ap', 'rank', 'l1')}
     total = 0.0
     for p in range(P):
@@ -83,8 +98,8 @@ def oracle_step(batch, cfg, backward=True, pairs=None):
         d1 = bodies.sample_tokens(g1, ph, pw, kp1, normalize=True)[0]
         d2 = bodies.sample_tokens(g2, ph, pw, kp2, normalize=True)[0]
         ap = bodies.smooth_ap(d1, d2, batch['p3d1'][p], batch['p3d2'][p], variant)
-        kf1 = bodies.sample_tokens(g1, ph, pw, kp1, normalize=False)
-        kf2 = bodies.sample_tokens(g2, ph, pw, kp2, normalize=False)
+        kf1 = depth_feats('h1', g1, p, kp1)
+        kf2 = depth_feats('h2', g2, p, kp2)
         l1, rank = bodies.depth_losses(head, kf1, kf2, batch['dep1'][p:p + 1], batch['dep2'][p:p + 1])
         total = total + (w['ap'] * ap + w['depth'] * l1 + w['intra'] * rank + w['kl'] * kl) / P
         for k, v in (('kl', kl), ('ap', ap), ('rank', rank), ('l1', l1)):

@@ -46,7 +46,8 @@ extern "C" {
 /* loss variants: which fine-tune script's body is reproduced */
 #define GD3_VARIANT_MAST3R 0 /* src/finetune_timm_mast3r.py */
 #define GD3_VARIANT_VGGT 1   /* src/finetune_timm_vggt.py   */
-#define GD3_VARIANT_ME 2     /* src/finetune_timm_me.py     */
+#define GD3_VARIANT_ME 2     /* src/finetune_timm_me.py, one mean per pair */
+#define GD3_VARIANT_ME_JOINT 3 /* src/finetune_timm_me.py:202-217 with B > 1: ONE mean over the positives of all pairs (Smooth-AP only) */
 
 int gd3_version(void);
 const char* gd3_last_error(void);
@@ -126,6 +127,8 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
  *   pts3d_1/2   (P, K, 3) fp32 3-D points of the keypoints
  *   temp 0.01, thr_neg 0.1 (thres3d_neg), thr_pos 5e-3 (thresh3d_pos, GD3_VARIANT_ME only)
  *   loss        (P) fp32;  grad_d1/2 (P, K, C) fp32 contiguous (times grad_scale) or NULL, NULL = forward only
+ *   GD3_VARIANT_ME: loss[p] = mean over pair p's positives (NaN without positives, like a B = 1 reference call);
+ *   GD3_VARIANT_ME_JOINT: loss[p] = pair p's share of the single batch-wide mean (sum_p loss[p] = reference loss)
  * ------------------------------------------------------------------------------------------ */
 size_t gd3_smooth_ap_workspace(int64_t P, int64_t K, int64_t C, int with_backward);
 int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const float* pts3d_2, int64_t P, int64_t K,

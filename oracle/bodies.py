@@ -81,6 +81,23 @@ def smooth_ap(d1, d2, pts3d_1, pts3d_2, variant='mast3r', temp=0.01, thr_neg=0.1
     return torch.mean(1.0 - (ap1 + ap2) / 2)
 
 
+def smooth_ap_me_batch(d1, d2, pts3d_1, pts3d_2, temp=0.01, thr_neg=0.1, thr_pos=5e-3):
+    """The ME baseline's loss on a batch of B pairs, ``src/finetune_timm_me.py:199-217`` line for line: the positives
+    of ALL pairs are gathered by one ``nonzero`` and ONE mean is taken over them (so pairs with many positives weigh
+    more, and a pair without positives simply does not count).  d1, d2: (B, K, C); pts3d_*: (B, K, 3)."""
+    dist = torch.cdist(pts3d_1, pts3d_2)
+    sim = torch.bmm(d1, d2.transpose(-1, -2))
+    pos_idxs = torch.nonzero(dist < thr_pos, as_tuple=False)
+    pos_sim = sim[pos_idxs[:, 0], pos_idxs[:, 1], pos_idxs[:, 2]]
+    rpos = sigmoid(pos_sim - 1.0, temp) + 1
+    neg_mask = dist[pos_idxs[:, 0], pos_idxs[:, 1]] > thr_neg
+    sim_rows = sim[pos_idxs[:, 0], pos_idxs[:, 1]]
+    ap1 = rpos / (rpos + torch.sum(sigmoid(sim_rows - 1.0, temp) * neg_mask.float(), -1))
+    rpos = sigmoid(1.0 - pos_sim, temp) + 1
+    ap2 = rpos / (rpos + torch.sum(sigmoid(sim_rows - pos_sim[:, None], temp) * neg_mask.float(), -1))
+    return torch.mean(1.0 - (ap1 + ap2) / 2)
+
+
 def sample_tokens(tokens, ph, pw, kp, patch_size=14, stride=14, normalize=False):
     """Sample token-major features (P, N, C) at pixel keypoints (P, K, 2) -> (P, K, C).
 

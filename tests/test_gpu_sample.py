@@ -115,3 +115,22 @@ def test_kp_prepare_batched_matches_oracle():
     for i in range(P):      # the reference (and the oracle) gather one pair at a time
         want5 = ofn.extract_kp_depth(depth[0], inside[i:i + 1], window_size=5)
         assert torch.allclose(kd5[i:i + 1].cpu(), want5, rtol=1e-6, atol=1e-6), i
+
+
+def test_kp_depth_fractional_and_outside_keypoints():
+    """extract_kp_depth gathers at (y * W + x).long() computed in fp32 (utils/functions.py:366-369): fractional
+    keypoints follow the flat index, not per-axis truncation; an index outside the map (the reference's gather raises)
+    comes back as NaN."""
+    from gd3 import _lib
+    from oracle import functions as ofn
+    g = torch.Generator().manual_seed(13)
+    P, K, H, W = 3, 300, 96, 131
+    kp = torch.stack([torch.rand(P, K, generator=g) * (W - 1), torch.rand(P, K, generator=g) * (H - 2)], -1)
+    depth = torch.rand(P, H, W, generator=g) * 5
+    _, kd = _lib.kp_prepare(kp.cuda(), H, W, depth=depth.cuda(), window=3)
+    for i in range(P):
+        want = ofn.extract_kp_depth(depth[i], kp[i:i + 1])
+        assert torch.equal(kd[i:i + 1].cpu(), want) or torch.allclose(kd[i:i + 1].cpu(), want, rtol=1e-6, atol=1e-6), i
+    out = torch.tensor([[[0., float(H)], [-3., -1.], [5., 5.]]])
+    _, kd_out = _lib.kp_prepare(out.cuda(), H, W, depth=depth[:1].cuda(), window=3)
+    assert torch.isnan(kd_out[0, :2]).all() and torch.isfinite(kd_out[0, 2])

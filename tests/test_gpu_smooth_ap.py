@@ -85,6 +85,33 @@ def test_smooth_ap_full_size_batched(variant, K, C):
         assert_grad_close(D2.grad[p], want[p][2], name=f'd2[{p}]', norm_rtol=3e-2)
 
 
+def test_smooth_ap_me_joint_mean_over_the_batch():
+    """ME baseline with B > 1 (src/finetune_timm_me.py:199-217): one mean over the positives of all pairs.  Pairs get
+    different numbers of positives (one gets none), so the per-pair mean ('me') and the joint mean differ."""
+    from gd3 import ops
+    K, C, B = 96, 64, 3
+    pairs = [make_pair(7300 + 10 * p, K, C) for p in range(B)]
+    D1, D2, P1, P2 = [torch.stack([q[k] for q in pairs]) for k in range(4)]
+    P2 = P1 + 0.2                                   # nothing is a positive ...
+    P2[0, :40] = P1[0, :40] + 1e-3                  # ... except 40 keypoints of pair 0 and 7 of pair 2
+    P2[2, 5:12] = P1[2, 5:12] - 1e-3
+    a = D1.clone().requires_grad_(True)
+    b = D2.clone().requires_grad_(True)
+    want = bodies.smooth_ap_me_batch(a, b, P1, P2)
+    ga, gb = torch.autograd.grad(want, [a, b])
+    x = D1.cuda().requires_grad_(True)
+    y = D2.cuda().requires_grad_(True)
+    loss = ops.smooth_ap(x, y, P1.cuda(), P2.cuda(), variant='me_joint')
+    assert loss.shape == (B,) and float(loss[1]) == 0.0
+    assert rel_err(loss.sum().item(), float(want)) <= 1e-3, (loss.tolist(), float(want))
+    loss.sum().backward()
+    assert_grad_close(x.grad, ga, name='d1', norm_rtol=3e-2)
+    assert_grad_close(y.grad, gb, name='d2', norm_rtol=3e-2)
+    assert float(x.grad[1].abs().max()) == 0.0
+    per_pair = ops.smooth_ap(D1.cuda(), D2.cuda(), P1.cuda(), P2.cuda(), variant='me')
+    assert math.isnan(per_pair[1].item()) and abs(per_pair[0].item() * 40 + per_pair[2].item() * 7 - 47 * float(want)) < 1e-3 * 47
+
+
 def test_smooth_ap_edge_cases():
     from gd3 import ops
     # K = 0: the callers' early-out semantics -> loss 0, no kernel

@@ -34,6 +34,32 @@ def test_distillation_step_vs_oracle(variant, cfg, dtype):
     assert abs(fwd['total'].item() - out['total'].item()) <= 1e-5 * abs(out['total'].item())
 
 
+def test_step_with_separate_depth_feature_maps():
+    """Descriptors from one map, depth-head features from a 4-block stack of other maps (their mean), as the reference's
+    training_step does (refine_conv output vs get_intermediate_feature, src/finetune_timm_mast3r.py:271-277,307-313)."""
+    from gd3 import pipeline
+    cfg = dict(N=12 * 16, C=96, K=65, grid=(12, 16), P=2, variant='vggt')
+    batch = bench_common.make_batch(cfg, cfg_id=1, pair0=3)
+    g = torch.Generator().manual_seed(21)
+    batch['h1'] = 0.5 * torch.randn(4, cfg['P'], cfg['N'], 72, generator=g)
+    batch['h2'] = batch['h1'] + 0.1 * torch.randn(4, cfg['P'], cfg['N'], 72, generator=g)
+    from oracle import synth
+    batch['head'] = dict(synth.head_params(99, 72), use_tanh=True, ln_eps=1e-5)
+    want = bench_common.oracle_step(batch, cfg)
+    out = pipeline.distillation_step(bench_common.to_device(batch, 'cuda'), variant='vggt', grid=cfg['grid'])
+    torch.cuda.synchronize()
+    for k in ('kl', 'ap', 'rank', 'l1'):
+        got, ref = out[k].float().cpu(), want[k]
+        assert ((got - ref).abs() / ref.abs().clamp_min(1e-12)).max().item() <= 1e-3, (k, got, ref)
+    for k in ('g1', 'g2', 'h1', 'h2', 'head'):
+        assert out['grads'][k].shape == want['grads'][k].shape, k
+        assert_grad_close(out['grads'][k], want['grads'][k], name=k, norm_rtol=3e-2)
+    bad = dict(bench_common.to_device(batch, 'cuda'))
+    bad['h1'] = bad['h1'][:, :, :-1]
+    with pytest.raises(ValueError):
+        pipeline.distillation_step(bad, variant='vggt', grid=cfg['grid'])
+
+
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
