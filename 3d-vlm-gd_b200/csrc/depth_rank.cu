@@ -199,14 +199,87 @@ struct RankParams {
   int64_t gparam_off;    // offset of b1 inside gparam (= H * D)
 };
 
-// dynamic smem: va[TILE_A][H] | dua[TILE_A][H] | da[TILE_A] | red[3*H + 1]
+// ---- pair kernel: elementwise part of one ordered pair (a -> b), 8 hidden units per lane as 4 float2 ----------
+// Differences to head_eval (kept for the L1 kernel): the Gaussian density is folded into the exponent
+// (e' = pdf-scaled exp(-y^2/2) = ex2(-ys^2 + log2 kPdf), the erf polynomial is pre-divided by kPdf, so GELU' is one
+// fma), and the LayerNorm-backward mean term m1 is not formed at all: sum_pairs alpha m1 = mean_h(sum_pairs alpha q),
+// so the accumulated gradient rows are centred once in rank_reduce_du instead of once per pair.
+// 22 packed fp32 ops per float2 forward + backward (was 26).  The pair loop is bound by issue slots as much as by the
+// FMA pipe (a packed op holds the pipe 2 cycles but takes one slot), so integer-pipe tricks that trade one packed op
+// for several LOP3 / SEL were measured in SASS and rejected.
+constexpr float kLog2Pdf = -1.0901312512086083f;          // log2(kPdf)
+constexpr float kN1 = -2.f * 0.37046028286393695f;       // -a1 / kPdf   (A&S 7.1.25: a1, a2, a3)
+constexpr float kN2 = 2.f * 0.10206088492966209f;
+constexpr float kN3 = -2.f * 0.7960676214969513f;
+
+struct PairFwd {
+  F2 xh[HP];   // normalised pre-activation
+  F2 g[HP];    // c * GELU(y)
+  F2 gp[HP];   // GELU'(y)
+  float acc;   // partial (this lane) of w2 . GELU
+  float m2;    // partial of sum_h w2 gamma GELU' xh
+};
+
 template <bool GRAD>
+__device__ __forceinline__ void pair_forward(const F2 (&hcv)[HP], float rstd, const HeadConst& hc, PairFwd& o) {
+  const F2 r2 = bc(rstd);
+  F2 acc2 = bc(0.f), m2_2 = bc(0.f);
+#pragma unroll
+  for (int i = 0; i < HP; ++i) {
+    const F2 xh = mul2(hcv[i], r2);
+    const F2 ys = fma2(xh, hc.gs[i], hc.bs[i]);                   // c * y
+    const F2 ti = fma2(bc(kErfP), make_float2(fabsf(ys.x), fabsf(ys.y)), bc(1.f));
+    const F2 t = make_float2(fast_rcp(ti.x), fast_rcp(ti.y));
+    F2 np = fma2(t, bc(kN3), bc(kN2));
+    np = fma2(t, np, bc(kN1));
+    np = mul2(np, t);                                             // -(a1 t + a2 t^2 + a3 t^3) / kPdf
+    const F2 sq = fma2(ys, ys, bc(-kLog2Pdf));
+    const F2 e = make_float2(fast_ex2(-sq.x), fast_ex2(-sq.y));   // kPdf exp(-y^2 / 2)
+    const F2 ea = fma2(np, e, bc(1.f));                           // erf(|y| / sqrt 2)
+    const F2 phi = fma2(bc(0.5f), make_float2(copysignf(ea.x, ys.x), copysignf(ea.y, ys.y)), bc(0.5f));
+    const F2 g = mul2(ys, phi);                                   // c * GELU(y)
+    acc2 = fma2(hc.w2c[i], g, acc2);
+    o.xh[i] = xh;
+    o.g[i] = g;
+    if (GRAD) {
+      const F2 gp = fma2(ys, e, phi);                             // Phi(y) + y pdf(y)
+      o.gp[i] = gp;
+      m2_2 = fma2(hc.w2g[i], mul2(gp, xh), m2_2);
+    }
+  }
+  o.acc = acc2.x + acc2.y;
+  o.m2 = m2_2.x + m2_2.y;
+}
+
+// dynamic smem: va[TILE_A][H] | dua[TILE_A][H] | da[TILE_A] | red[3*H + 1] | prog[WARPS]
+//
+// Synchronisation of the shared a-side gradient tile `dua`.  Warp w walks the ring of 32 row-pair slots starting
+// SPACING (= 4) slots after warp w - 1, so at its step g it touches the slot its successor (w + 1) % WARPS touched
+// at step g - 4 and its predecessor will touch at step g + 4.  Instead of a CTA barrier every 2 steps (which also
+// aligns the phases of all warps: they then compete for the FMA pipe and idle through the MUFU / shuffle
+// latencies together), every warp publishes the number of steps it has completed (`prog`, release) and, right
+// before its read-modify-write, waits until its successor has completed step g - 4 (acquire).  The slowest warp
+// never waits (its successor is ahead), so the ring cannot deadlock; a warp may run up to 3 steps ahead of its
+// successor and arbitrarily far behind it.
+__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// MODE 0 logistic / 1 hinge and the head's tanh are template parameters: the per-pair scalar chain is a third of the
+// issue slots of a step, uniform branches on kernel parameters inside it are not free.
+template <bool GRAD, int MODE, bool TANH>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams p) {
   extern __shared__ __align__(16) float smem[];
   float* va = smem;                       // centred u_a rows of the a tile
   float* dua = va + TILE_A * H;           // accumulated d/d(u_a) (sign applied at reduction)
-  float* da = dua + TILE_A * H;           // depths of the a tile
+  float* da = dua + TILE_A * H;           // depths of the a tile (NaN outside the set: such a pair is never valid)
   float* red = da + TILE_A;                 // cross-warp reduction of parameter gradients
+  int* prog = reinterpret_cast<int*>(red + 3 * H + 4);   // steps completed per warp (ring synchronisation)
   const int set = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
   const int K = p.K;
@@ -222,8 +295,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     m = warp_sum(m) * (1.f / H);
     *reinterpret_cast<float4*>(va + r * H + 4 * lane) = make_float4(m - v.x, m - v.y, m - v.z, m - v.w);
     if (GRAD) *reinterpret_cast<float4*>(dua + r * H + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane == 0) da[r] = (a < K) ? Dp[a] : 0.f;
+    if (lane == 0) da[r] = (a < K) ? Dp[a] : __int_as_float(0x7fc00000);
   }
+  if (threadIdx.x < WARPS) prog[threadIdx.x] = 0;
   HeadConst hc;
   F2 bb[HP];   // b1 - mean(b1)
   {
@@ -243,6 +317,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
 #pragma unroll
   for (int i = 0; i < HP; ++i) dgam[i] = dbet[i] = dw2[i] = bc(0.f);
   float loss_local = 0.f;
+  const int* prog_succ = prog + ((warp + 1) % WARPS);
+  int steps_done = 0;          // ring steps this warp has completed (== its prog entry)
 
   // rstd of one b row against the 64 rows of the a tile: the 16 lanes of a half hold ring slots l16 and l16 + 16
   // (a = 2 * slot + half), i.e. two fully coalesced 128-byte loads per warp and b row
@@ -262,7 +338,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     const int b = tb * TILE_B + bi * WARPS + warp;
     const bool b_ok = b < K;     // warp-uniform
     F2 vb[HP], dub[HP];
-    float d_b = 0.f;
+    float d_b = __int_as_float(0x7fc00000);     // NaN: no pair of a row outside the set is valid
     {
       float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
       if (b_ok) {
@@ -287,7 +363,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     const bool row_flagged = __any_sync(0xffffffffu, rs0 < 0.f || rs1 < 0.f);
     if (bi + 1 < B_PER_WARP) load_rstd(b + WARPS, rs0_next, rs1_next);
     // The walk over the a tile exists twice: the common one trusts the Gram rstd, the rare one (a flagged pair in
-    // this b row) re-derives 1 / sigma from the pair itself where the flag is set.  Same barrier pattern in both.
+    // this b row) re-derives 1 / sigma from the pair itself where the flag is set.
     auto walk_a_tile = [&](auto check_tag) {
     constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll 2
@@ -296,10 +372,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
       const int slot = (t + SPACING * warp) % SLOTS;
       const int r = 2 * slot + half;
       const int a = ta * TILE_A + r;
-      const float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, (lane & 16) | (slot & 15));
-      const float dd = d_b - da[r];
-      bool valid = b_ok && a < K;
-      valid = valid && ((p.mode == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr));
+      float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, (lane & 16) | (slot & 15));
+      const float dd = d_b - da[r];       // NaN when a or b lies outside the set
+      const bool valid = (MODE == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr);
       // both halves run the same instruction stream (98 % of the pairs are valid); an invalid pair is
       // masked out of every accumulation below.  Skip only when neither half has work.
       if (__any_sync(0xffffffffu, valid)) {
@@ -310,60 +385,79 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
         hcv[1] = add2(vb[1], make_float2(a0.z, a0.w));
         hcv[2] = add2(vb[2], make_float2(a1.x, a1.y));
         hcv[3] = add2(vb[3], make_float2(a1.z, a1.w));
-        PairOut o;
-        o.rstd = rs;
         if (CHECK) {
           // flagged by the Gram epilogue (near-duplicate rows): sum of squares of this pair's h_c directly
           F2 ss2 = bc(0.f);
 #pragma unroll
           for (int i = 0; i < HP; ++i) ss2 = fma2(hcv[i], hcv[i], ss2);
           const float ss = half_sum(ss2.x + ss2.y, 0xffffffffu);
-          if (rs < 0.f) o.rstd = rsqrtf(fmaf(ss, 1.f / H, p.ln_eps));
+          if (rs < 0.f) rs = rsqrtf(fmaf(ss, 1.f / H, p.ln_eps));
         }
-        head_eval<GRAD, true>(hcv, hc, p.ln_eps, p.use_tanh, o);
-        const float sg = (dd > 0.f) ? 1.f : ((dd < 0.f) ? -1.f : 0.f);
-        float l, dl;
-        if (p.mode == 0) {
-          const float ex = fast_ex2(-sg * o.s * 1.4426950408889634f);
+        PairFwd o;
+        pair_forward<GRAD>(hcv, rs, hc, o);
+        // the two reductions over the 16 lanes of the pair ride in one float2: packed adds, two shuffles per level
+        F2 am = make_float2(o.acc, o.m2);
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) {
+          F2 other;
+          other.x = __shfl_xor_sync(0xffffffffu, am.x, off);
+          other.y = GRAD ? __shfl_xor_sync(0xffffffffu, am.y, off) : 0.f;
+          am = add2(am, other);
+        }
+        const float acc = am.x + hc.b2;
+        const float sc = TANH ? fast_tanh(acc) : acc;
+        // sign(dd) s without a multiply: flip the sign bit of s where dd < 0 (a valid pair has dd != 0)
+        const float ssc = __uint_as_float(__float_as_uint(sc) ^ (__float_as_uint(dd) & 0x80000000u));
+        float l, dl;      // pair loss and d l / d (sign(dd) s)
+        if (MODE == 0) {
+          const float ex = fast_ex2(ssc * -1.4426950408889634f);
           l = __logf(1.f + ex);
-          dl = -sg * ex * fast_rcp(1.f + ex);
+          dl = -ex * fast_rcp(1.f + ex);
         } else {
-          const float m = p.margin - sg * o.s;
+          const float m = p.margin - ssc;
           l = fmaxf(m, 0.f);
-          dl = (m > 0.f) ? -sg : 0.f;
+          dl = (m > 0.f) ? -1.f : 0.f;
         }
-        loss_local += (valid && l16 == 0) ? l : 0.f;
+        // every lane of the pair adds the same value; the CTA reduction divides by 16
+        loss_local += valid ? l : 0.f;
         if (GRAD) {
           // d total / d (w2.g + b2); zero for a masked pair, which zeroes every contribution below
-          const float dout = valid ? dl * (p.use_tanh ? (1.f - o.s * o.s) : 1.f) * inv_cnt : 0.f;
-          db2 += (l16 == 0) ? dout : 0.f;
-          const F2 dout2 = bc(dout), coef2 = bc(dout * o.rstd), nm1 = bc(-o.m1), nm2 = bc(-o.m2);
-          F2 dh[HP];
+          const float dsg = __uint_as_float(__float_as_uint(dl) ^ (__float_as_uint(dd) & 0x80000000u));   // d l / d s
+          const float dout = valid ? dsg * (TANH ? fmaf(-sc, sc, 1.f) : 1.f) * inv_cnt : 0.f;
+          db2 += dout;
+          // d h = alpha (q - m1 - m2 xh), q = w2 gamma GELU'; the m1 part is the centring done by rank_reduce_du
+          const F2 dout2 = bc(dout), alpha2 = bc(dout * rs), nm2 = bc(am.y * (-1.f / H));
+          F2 tq[HP];
 #pragma unroll
           for (int i = 0; i < HP; ++i) {
             // parameter sums are kept unscaled: d w2 = dw2 / c, d beta = w2 * dbet, d gamma = w2 * dgam
-            const F2 t1 = mul2(dout2, o.gp[i]);
             dw2[i] = fma2(dout2, o.g[i], dw2[i]);
-            dbet[i] = add2(dbet[i], t1);
-            dgam[i] = fma2(t1, o.xh[i], dgam[i]);
-            dh[i] = mul2(coef2, fma2(o.xh[i], nm2, fma2(hc.w2g[i], o.gp[i], nm1)));
-            dub[i] = add2(dub[i], dh[i]);
+            dbet[i] = fma2(dout2, o.gp[i], dbet[i]);
+            dgam[i] = fma2(dout2, mul2(o.gp[i], o.xh[i]), dgam[i]);
+            tq[i] = fma2(nm2, o.xh[i], mul2(hc.w2g[i], o.gp[i]));
+            dub[i] = fma2(alpha2, tq[i], dub[i]);
+          }
+          // ring dependency: the successor warp must have finished the step that touched this slot last
+          {
+            const int need = steps_done - (SPACING - 1);     // successor must have completed its steps 0 .. g - SPACING
+            if (need > 0)
+              while (ld_acquire_cta(prog_succ) < need) {}
           }
           float4* q0 = reinterpret_cast<float4*>(dua + r * H + 4 * l16);
           float4* q1 = reinterpret_cast<float4*>(dua + r * H + 64 + 4 * l16);
           const float4 c0 = *q0, c1 = *q1;
-          const F2 s0 = add2(make_float2(c0.x, c0.y), dh[0]), s1 = add2(make_float2(c0.z, c0.w), dh[1]);
-          const F2 s2 = add2(make_float2(c1.x, c1.y), dh[2]), s3 = add2(make_float2(c1.z, c1.w), dh[3]);
+          const F2 s0 = fma2(alpha2, tq[0], make_float2(c0.x, c0.y)), s1 = fma2(alpha2, tq[1], make_float2(c0.z, c0.w));
+          const F2 s2 = fma2(alpha2, tq[2], make_float2(c1.x, c1.y)), s3 = fma2(alpha2, tq[3], make_float2(c1.z, c1.w));
           *q0 = make_float4(s0.x, s0.y, s1.x, s1.y);
           *q1 = make_float4(s2.x, s2.y, s3.x, s3.y);
         }
       }
-      // Two half warps collide on a row of `dua` only when their step counters differ by a multiple of
-      // SPACING, so a CTA barrier every (SPACING - 1) steps keeps the stagger race-free.
-      // (barrier every 2 steps <= SPACING - 1; the pair of steps in between is unrolled so that their shuffle / MUFU
-      // latencies overlap)
-      static_assert(SPACING - 1 >= 2 && SLOTS % 2 == 0, "barrier period");
-      if (GRAD && (t & 1)) __syncthreads();
+      if (GRAD) {
+        // publish this step (also when it was skipped: the ring position advanced)
+        ++steps_done;
+        __syncwarp();
+        if (lane == 0) st_release_cta(prog + warp, steps_done);
+      }
     }
     };
     if (row_flagged) walk_a_tile(std::true_type{});
@@ -383,7 +477,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     }
   }
   // ---- CTA-level reductions ----
-  loss_local = warp_sum(loss_local);
+  loss_local = warp_sum(loss_local) * (1.f / 16.f);      // all 16 lanes of a pair carried its loss
   if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_sum + set, (double)loss_local);
   if (GRAD) {
     __syncthreads();
@@ -409,7 +503,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
         atomicAdd(red + 2 * H + h, w2v);
       }
     }
-    db2 = warp_sum(db2);
+    db2 = warp_sum(db2) * (1.f / 16.f);
     if (lane == 0) atomicAdd(red + 3 * H, db2);
     __syncthreads();
     float* gp = p.gparam + p.gparam_off;   // [b1 | gamma | beta | w2 | b2]
@@ -673,16 +767,27 @@ __global__ void __launch_bounds__(256)
     const int k = k0 + r;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < K) {
+      // rank_pairs accumulates alpha (q - m2 xh) per pair; the LayerNorm-backward term -alpha m1 = -alpha mean_h(q)
+      // summed over pairs is the mean over h of the accumulated row (mean_h(xh) = 0), removed here once per row
 #pragma unroll 4
       for (int t = 0; t < TA; ++t) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(dub_part + (((int64_t)set * TA + t) * K + k) * H + 4 * lane));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
+      {
+        const float mb = warp_sum((acc.x + acc.y) + (acc.z + acc.w)) * (1.f / H);
+        acc.x -= mb; acc.y -= mb; acc.z -= mb; acc.w -= mb;
+      }
       bsum[0] += acc.x; bsum[1] += acc.y; bsum[2] += acc.z; bsum[3] += acc.w;   // d b1 = sum over pairs of dh
+      float4 aa = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
       for (int t = 0; t < TB; ++t) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(dua_part + (((int64_t)set * TB + t) * K + k) * H + 4 * lane));
-        acc.x -= v.x; acc.y -= v.y; acc.z -= v.z; acc.w -= v.w;
+        aa.x += v.x; aa.y += v.y; aa.z += v.z; aa.w += v.w;
+      }
+      {
+        const float ma = warp_sum((aa.x + aa.y) + (aa.z + aa.w)) * (1.f / H);
+        acc.x -= aa.x - ma; acc.y -= aa.y - ma; acc.z -= aa.z - ma; acc.w -= aa.w - ma;
       }
       if (du_extra) {
         const float4 v = *reinterpret_cast<const float4*>(du_extra + ((int64_t)set * K + k) * H + 4 * lane);
@@ -949,23 +1054,29 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.gparam = grad_params;
   rp.gparam_off = (int64_t)H * D;
   {
-    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 1 + 3);
+    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 4) + sizeof(int) * WARPS;
     dim3 grid((unsigned)w.TA, (unsigned)w.TB, (unsigned)S);
+#define GD3_RANK_LAUNCH(G, M, T)                                            \
+  do {                                                                     \
+    static SmemOptIn opt;                                                  \
+    GD3_CHECK_CUDA(opt.ensure(rank_pairs<G, M, T>, smem));                 \
+    GD3_PROF("rank_pairs", stream);                                        \
+    rank_pairs<G, M, T><<<grid, WARPS * 32, smem, stream>>>(rp);           \
+  } while (0)
+#define GD3_RANK_LAUNCH_T(G, M)                 \
+  do {                                          \
+    if (use_tanh) GD3_RANK_LAUNCH(G, M, true);  \
+    else GD3_RANK_LAUNCH(G, M, false);          \
+  } while (0)
     if (backward) {
-      static SmemOptIn opt;
-      GD3_CHECK_CUDA(opt.ensure(rank_pairs<true>, smem));
-      {
-        GD3_PROF("rank_pairs", stream);
-        rank_pairs<true><<<grid, WARPS * 32, smem, stream>>>(rp);
-      }
+      if (mode == 0) GD3_RANK_LAUNCH_T(true, 0);
+      else GD3_RANK_LAUNCH_T(true, 1);
     } else {
-      static SmemOptIn opt;
-      GD3_CHECK_CUDA(opt.ensure(rank_pairs<false>, smem));
-      {
-        GD3_PROF("rank_pairs", stream);
-        rank_pairs<false><<<grid, WARPS * 32, smem, stream>>>(rp);
-      }
+      if (mode == 0) GD3_RANK_LAUNCH_T(false, 0);
+      else GD3_RANK_LAUNCH_T(false, 1);
     }
+#undef GD3_RANK_LAUNCH_T
+#undef GD3_RANK_LAUNCH
     GD3_CHECK_LAUNCH();
   }
   if (l1) {

@@ -72,6 +72,45 @@ assert torch.equal(full, torch.arange(P, dtype=torch.float32) * 1.5 + 0.25), ful
 g = torch.full((5,), float(rank + 1))
 gdist.allreduce_mean_(g)
 assert torch.allclose(g, torch.full((5,), sum(range(1, world + 1)) / world))
+# uneven shards: rank gradients are means over P_local pairs; the weighted form is the mean over all P pairs
+gw = torch.full((3,), float(sum(range(b, e))) / max(e - b, 1))
+gdist.allreduce_mean_(gw, local_pairs=e - b, num_pairs=P)
+assert torch.allclose(gw, torch.full((3,), sum(range(P)) / P)), gw
+# sharding goes by key: per-pair tensors are sliced, a shared (H, W) depth map with H == P is not
+batch = dict(f1=torch.arange(P * 2.).reshape(P, 2), kp1=torch.zeros(P, 3, 2), depth_map1=torch.ones(P, 5),
+             h1=torch.zeros(4, P, 6, 2), head=dict(W1=torch.zeros(P, 2)), scale=torch.ones(P))
+sh = gdist.shard_batch(batch, rank, world)
+assert sh['f1'].shape[0] == e - b and sh['kp1'].shape[0] == e - b and sh['h1'].shape[:2] == (4, e - b)
+assert sh['depth_map1'].shape == (P, 5) and sh['scale'].shape == (P,) and sh['head']['W1'].shape == (P, 2)
+# bucketed, overlapped gradient all-reduce (the DDP protocol of src/main.py:147-159) against plain averaging
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.Linear(16, 1))
+net[2].weight.requires_grad_(False)                         # a frozen parameter is never bucketed
+unused = torch.nn.Parameter(torch.ones(7))                   # a trainable parameter that gets no gradient
+params = list(net.parameters()) + [unused]
+red = gdist.BucketedGradAllReduce(params, bucket_bytes=100)  # tiny buckets -> several collectives
+assert len(red.buckets) > 2
+for step in range(2):
+    x = torch.randn(4, 6, generator=torch.Generator().manual_seed(10 * step + rank))
+    for q in params:
+        q.grad = None
+    red.reset()
+    (net(x).pow(2).mean() * (rank + 1)).backward()
+    local = [None if q.grad is None else q.grad.clone() for q in params]
+    norm = red.finish(clip_norm=0.05)
+    want = []
+    for q, gl in zip(params, local):
+        if not q.requires_grad:
+            continue
+        t = torch.zeros_like(q) if gl is None else gl.clone()
+        dist.all_reduce(t)
+        want.append((q, t / world))
+    tot = torch.sqrt(sum((t ** 2).sum() for _, t in want))
+    sc = min(1.0, 0.05 / (float(tot) + 1e-6))
+    assert abs(float(norm) - float(tot)) < 1e-5 * float(tot)
+    for q, t in want:
+        assert torch.allclose(q.grad, t * sc, rtol=1e-5, atol=1e-7)
+red.remove()
 dist.barrier()
 if rank == 0:
     print('GLOO_OK')
