@@ -261,13 +261,33 @@ __device__ __forceinline__ void pair_forward(const F2 (&hcv)[HP], float rstd, co
 // before its read-modify-write, waits until its successor has completed step g - 4 (acquire).  The slowest warp
 // never waits (its successor is ahead), so the ring cannot deadlock; a warp may run up to 3 steps ahead of its
 // successor and arbitrarily far behind it.
-__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+__device__ __forceinline__ int ld_acquire_cta(uint32_t saddr) {
   int v;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_cta(int* p, int v) {
-  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_release_cta(uint32_t saddr, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+// The pair loop addresses shared memory through 32-bit shared-window addresses that are made opaque to the compiler
+// once (opaque()): derived from threadIdx they would be rematerialised inside the loop (S2R + shifts, ~25 cycles of
+// exposed latency each) whenever registers get tight.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
 }
 
 // MODE 0 logistic / 1 hinge and the head's tanh are template parameters: the per-pair scalar chain is a third of the
@@ -299,14 +319,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   }
   if (threadIdx.x < WARPS) prog[threadIdx.x] = 0;
   HeadConst hc;
-  F2 bb[HP];   // b1 - mean(b1)
+  float b1_mean;
   {
     float bsum = 0.f;
     for (int h = lane; h < H; h += 32) bsum += p.b1[h];
-    bsum = warp_sum(bsum) * (1.f / H);
-#pragma unroll
-    for (int i = 0; i < HP; ++i)
-      bb[i] = make_float2(p.b1[hidx(l16, 2 * i)] - bsum, p.b1[hidx(l16, 2 * i + 1)] - bsum);
+    b1_mean = warp_sum(bsum) * (1.f / H);
     hc.load(p.gamma, p.beta, p.w2, p.b2, l16);
   }
   const float inv_cnt = p.inv_count[set] * (p.w_rank ? p.w_rank[set] : 1.f);
@@ -317,8 +334,18 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
 #pragma unroll
   for (int i = 0; i < HP; ++i) dgam[i] = dbet[i] = dw2[i] = bc(0.f);
   float loss_local = 0.f;
-  const int* prog_succ = prog + ((warp + 1) % WARPS);
+  // shared-window addresses of this lane's 16-byte column of a ring slot (rows 2 * slot + half), opaque to the compiler
+  constexpr uint32_t kSlotBytes = 2 * H * 4, kRingBytes = SLOTS * kSlotBytes, kDuaOff = TILE_A * H * 4;
+  const uint32_t va_lane = opaque((uint32_t)__cvta_generic_to_shared(va) + (half * H + 4 * l16) * 4);
+  const uint32_t da_lane = opaque((uint32_t)__cvta_generic_to_shared(da) + half * 4);
+  const uint32_t prog_mine = opaque((uint32_t)__cvta_generic_to_shared(prog + warp));
+  const uint32_t prog_succ = opaque((uint32_t)__cvta_generic_to_shared(prog + (warp + 1) % WARPS));
+  const uint32_t lane_half = opaque((uint32_t)(lane & 16));
+  const bool lane0 = opaque((uint32_t)lane) == 0;
+  const uint32_t soff0 = opaque((uint32_t)(SPACING * warp) * kSlotBytes);   // ring offset of this warp's first slot
+  const int a_tile0 = ta * TILE_A;
   int steps_done = 0;          // ring steps this warp has completed (== its prog entry)
+  int succ_seen = 0;           // last value read from the successor's counter (it only grows)
 
   // rstd of one b row against the 64 rows of the a tile: the 16 lanes of a half hold ring slots l16 and l16 + 16
   // (a = 2 * slot + half), i.e. two fully coalesced 128-byte loads per warp and b row
@@ -346,13 +373,15 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
         u1 = *reinterpret_cast<const float4*>(U + (int64_t)b * H + 64 + 4 * l16);
         d_b = Dp[b];
       }
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.b1 + 4 * l16));          // b1 (L1-resident)
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.b1 + 64 + 4 * l16));
       float m = ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w));
       m = half_sum(m, 0xffffffffu) * (1.f / H);
-      const F2 nm = bc(-m);
-      vb[0] = add2(add2(make_float2(u0.x, u0.y), nm), bb[0]);
-      vb[1] = add2(add2(make_float2(u0.z, u0.w), nm), bb[1]);
-      vb[2] = add2(add2(make_float2(u1.x, u1.y), nm), bb[2]);
-      vb[3] = add2(add2(make_float2(u1.z, u1.w), nm), bb[3]);
+      const F2 nm = bc(-(m + b1_mean));      // w_b = (u_b - mean u_b) + (b1 - mean b1)
+      vb[0] = add2(add2(make_float2(u0.x, u0.y), nm), make_float2(c0.x, c0.y));
+      vb[1] = add2(add2(make_float2(u0.z, u0.w), nm), make_float2(c0.z, c0.w));
+      vb[2] = add2(add2(make_float2(u1.x, u1.y), nm), make_float2(c1.x, c1.y));
+      vb[3] = add2(add2(make_float2(u1.z, u1.w), nm), make_float2(c1.z, c1.w));
 #pragma unroll
       for (int i = 0; i < HP; ++i) dub[i] = bc(0.f);
     }
@@ -366,20 +395,24 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     // this b row) re-derives 1 / sigma from the pair itself where the flag is set.
     auto walk_a_tile = [&](auto check_tag) {
     constexpr bool CHECK = decltype(check_tag)::value;
+    uint32_t soff = soff0;                  // byte offset of the current slot inside the ring
+    float da_cur = lds32(da_lane + (soff >> 7));    // depth of row a = 2 * slot + half (slot * 8 bytes)
 #pragma unroll 2
     for (int t = 0; t < SLOTS; ++t) {
       // staggered a index: at any step the half-warps of the CTA work on different rows
-      const int slot = (t + SPACING * warp) % SLOTS;
-      const int r = 2 * slot + half;
-      const int a = ta * TILE_A + r;
-      float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, (lane & 16) | (slot & 15));
-      const float dd = d_b - da[r];       // NaN when a or b lies outside the set
+      const uint32_t slot = soff >> 10;
+      const uint32_t va_addr = va_lane + soff;
+      const uint32_t soff_next = (soff + kSlotBytes) & (kRingBytes - 1);
+      const float dd = d_b - da_cur;       // NaN when a or b lies outside the set
+      da_cur = lds32(da_lane + (soff_next >> 7));     // next step's depth: its latency hides behind this step
+      float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, lane_half | (slot & 15));
       const bool valid = (MODE == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr);
-      // both halves run the same instruction stream (98 % of the pairs are valid); an invalid pair is
-      // masked out of every accumulation below.  Skip only when neither half has work.
-      if (__any_sync(0xffffffffu, valid)) {
-        const float4 a0 = *reinterpret_cast<const float4*>(va + r * H + 4 * l16);
-        const float4 a1 = *reinterpret_cast<const float4*>(va + r * H + 64 + 4 * l16);
+      // both halves run the same instruction stream (98 % of the pairs are valid); an invalid pair is masked out
+      // of every accumulation below.  A slot is skipped only when it lies outside the set for both halves
+      // (warp-uniform test on the indices, no vote on loaded data).
+      if (b_ok && a_tile0 + 2 * (int)slot < K) {
+        const float4 a0 = lds128(va_addr);
+        const float4 a1 = lds128(va_addr + 256);
         F2 hcv[HP];
         hcv[0] = add2(vb[0], make_float2(a0.x, a0.y));
         hcv[1] = add2(vb[1], make_float2(a0.z, a0.w));
@@ -437,26 +470,29 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
             tq[i] = fma2(nm2, o.xh[i], mul2(hc.w2g[i], o.gp[i]));
             dub[i] = fma2(alpha2, tq[i], dub[i]);
           }
-          // ring dependency: the successor warp must have finished the step that touched this slot last
+          // ring dependency: the successor warp must have finished the step that touched this slot last.  Its counter
+          // only grows, so the last value seen is re-read only when it is not enough.
           {
             const int need = steps_done - (SPACING - 1);     // successor must have completed its steps 0 .. g - SPACING
-            if (need > 0)
-              while (ld_acquire_cta(prog_succ) < need) {}
+#ifndef GD3_RANK_NOSYNC_EXPERIMENT
+            while (succ_seen < need) succ_seen = ld_acquire_cta(prog_succ);
+#endif
           }
-          float4* q0 = reinterpret_cast<float4*>(dua + r * H + 4 * l16);
-          float4* q1 = reinterpret_cast<float4*>(dua + r * H + 64 + 4 * l16);
-          const float4 c0 = *q0, c1 = *q1;
+          const float4 c0 = lds128(va_addr + kDuaOff), c1 = lds128(va_addr + kDuaOff + 256);
           const F2 s0 = fma2(alpha2, tq[0], make_float2(c0.x, c0.y)), s1 = fma2(alpha2, tq[1], make_float2(c0.z, c0.w));
           const F2 s2 = fma2(alpha2, tq[2], make_float2(c1.x, c1.y)), s3 = fma2(alpha2, tq[3], make_float2(c1.z, c1.w));
-          *q0 = make_float4(s0.x, s0.y, s1.x, s1.y);
-          *q1 = make_float4(s2.x, s2.y, s3.x, s3.y);
+          sts128(va_addr + kDuaOff, make_float4(s0.x, s0.y, s1.x, s1.y));
+          sts128(va_addr + kDuaOff + 256, make_float4(s2.x, s2.y, s3.x, s3.y));
         }
       }
+      soff = soff_next;
       if (GRAD) {
         // publish this step (also when it was skipped: the ring position advanced)
         ++steps_done;
+#ifndef GD3_RANK_NOSYNC_EXPERIMENT
         __syncwarp();
-        if (lane == 0) st_release_cta(prog + warp, steps_done);
+        if (lane0) st_release_cta(prog_mine, steps_done);
+#endif
       }
     }
     };
