@@ -183,10 +183,25 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------
 // 2. teacher row statistics: one warp per (direction, pair, row)
 // ------------------------------------------------------------------------------------------
+// Teacher element types.  fp32 is the reference's; fp16 is the packed form the teacher-side producers emit
+// (gd3_teacher_pack: values times a power-of-two `scale` so that small probabilities stay normal numbers, plus the
+// row statistics): it halves the bytes of the largest input of the step.  A common scale cancels in the row
+// normalisation c / max(sum c, eps); only the clamp of the row sum has to know it (eps * scale).
+__device__ __forceinline__ float t_load(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float t_load(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ float4 t_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 t_load4(const __half* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <class TT>
 __global__ void __launch_bounds__(256)
-    kl_teacher_stats(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+    kl_teacher_stats(const TT* __restrict__ t12, const TT* __restrict__ t21, int64_t t_pair_stride,
                      int64_t t_row_stride, const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, int pair0,
-                     int G, int N, float eps, float masked_row_const, float* __restrict__ invR /*(2,G,N)*/,
+                     int G, int N, float eps, float eps_sum, float masked_row_const, float* __restrict__ invR /*(2,G,N)*/,
                      float* __restrict__ epsm /*(2,G,N)*/, float* __restrict__ Tsum /*(2,G,N)*/,
                      double* __restrict__ loss_acc /*(G)*/) {
   const int lane = threadIdx.x & 31;
@@ -207,14 +222,14 @@ __global__ void __launch_bounds__(256)
     }
     return;
   }
-  const float* row = (dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride + (int64_t)i * t_row_stride;
+  const TT* row = (dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride + (int64_t)i * t_row_stride;
   float R = 0.f;
-  for (int j = lane; j < N; j += 32) R += __ldg(row + j);
+  for (int j = lane; j < N; j += 32) R += t_load(row + j);
   R = warp_sum(R);
-  const float ir = 1.f / fmaxf(R, eps);
+  const float ir = 1.f / fmaxf(R, eps_sum);
   float T = 0.f, A = 0.f;
   for (int j = lane; j < N; j += 32) {
-    const float tt = fmaxf(__ldg(row + j) * ir, eps);
+    const float tt = fmaxf(t_load(row + j) * ir, eps);
     T += tt;
     A = fmaf(tt, __logf(tt), A);
   }
@@ -231,11 +246,11 @@ __global__ void __launch_bounds__(256)
 // Single-read variant for N <= 128 * NV: the whole row sits in registers (4 NV floats per lane) and all loads of a
 // row are in flight at once.  VEC: N % 4 == 0 and 16-byte aligned rows (128-bit loads); otherwise scalar loads
 // (ragged N such as 37^2, whose rows are not 16-byte aligned).
-template <int NV, bool VEC>
+template <int NV, bool VEC, class TT>
 __global__ void __launch_bounds__(256)
-    kl_teacher_stats_vec(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+    kl_teacher_stats_vec(const TT* __restrict__ t12, const TT* __restrict__ t21, int64_t t_pair_stride,
                          int64_t t_row_stride, const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, int pair0,
-                         int G, int N, float eps, float masked_row_const, float* __restrict__ invR,
+                         int G, int N, float eps, float eps_sum, float masked_row_const, float* __restrict__ invR,
                          float* __restrict__ epsm, float* __restrict__ Tsum, double* __restrict__ loss_acc) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -255,33 +270,37 @@ __global__ void __launch_bounds__(256)
     }
     return;
   }
-  const float* rowp = (dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride + (int64_t)i * t_row_stride;
+  const TT* rowp = (dir == 0 ? t12 : t21) + (int64_t)(pair0 + g) * t_pair_stride + (int64_t)i * t_row_stride;
   float v[4 * NV];       // VEC: element 4 * (lane + 32 k) + q at v[4 k + q]; scalar: element lane + 32 k at v[k]
   if (VEC) {
-    const float4* row = reinterpret_cast<const float4*>(rowp);
-    const int nv = N >> 2;
+    // rows are 4-element aligned and (for ragged N) padded to a multiple of 4: the last vector may reach into the
+    // padding, whose elements are masked below
+    const int nv = (N + 3) >> 2;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int j = lane + 32 * k;
-      const float4 t4 = (j < nv) ? __ldg(row + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t4 = (j < nv) ? t_load4(rowp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * j + 1 >= N) t4.y = 0.f;
+      if (4 * j + 2 >= N) t4.z = 0.f;
+      if (4 * j + 3 >= N) t4.w = 0.f;
       v[4 * k] = t4.x; v[4 * k + 1] = t4.y; v[4 * k + 2] = t4.z; v[4 * k + 3] = t4.w;
     }
   } else {
 #pragma unroll
     for (int k = 0; k < 4 * NV; ++k) {
       const int j = lane + 32 * k;
-      v[k] = (j < N) ? __ldg(rowp + j) : 0.f;
+      v[k] = (j < N) ? t_load(rowp + j) : 0.f;
     }
   }
   float R = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) R += (v[4 * k] + v[4 * k + 1]) + (v[4 * k + 2] + v[4 * k + 3]);
   R = warp_sum(R);
-  const float ir = 1.f / fmaxf(R, eps);
+  const float ir = 1.f / fmaxf(R, eps_sum);
   float T = 0.f, A = 0.f;
 #pragma unroll
   for (int k = 0; k < 4 * NV; ++k) {
-    const bool in_row = VEC ? (4 * (lane + 32 * (k >> 2)) < N) : (lane + 32 * k < N);
+    const bool in_row = VEC ? (4 * (lane + 32 * (k >> 2)) + (k & 3) < N) : (lane + 32 * k < N);
     if (in_row) {
       const float tt = fmaxf(v[k] * ir, eps);
       T += tt;
@@ -296,6 +315,96 @@ __global__ void __launch_bounds__(256)
     epsm[o] = eps;
     Tsum[o] = T;
     loss_add(loss_acc, g, i, scale * (double)A);
+  }
+}
+
+// Row statistics supplied by the teacher-side producer (gd3_teacher_pack): stats (P, 3, N) = [row sum R of the
+// unscaled teacher | T = sum_j t~ | A = sum_j t~ ln t~].  One thread per (direction, pair, row); replaces the pass over
+// the volume above.
+__global__ void kl_stats_from_input(const float* __restrict__ s12, const float* __restrict__ s21,
+                                    const uint8_t* __restrict__ m1, const uint8_t* __restrict__ m2, int pair0, int G, int N,
+                                    float eps, float scale, float masked_row_const, float* __restrict__ invR,
+                                    float* __restrict__ epsm, float* __restrict__ Tsum, double* __restrict__ loss_acc) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)2 * G * N) return;
+  const int dir = (int)(idx / ((int64_t)G * N));
+  const int rem = (int)(idx - (int64_t)dir * G * N);
+  const int g = rem / N, i = rem - g * N;
+  const uint8_t keep = (dir == 0 ? m1 : m2)[(int64_t)(pair0 + g) * N + i];
+  const double lscale = 0.5 / (double)N;
+  if (!keep) {
+    invR[idx] = 0.f;
+    epsm[idx] = 0.f;
+    Tsum[idx] = 0.f;
+    if (masked_row_const != 0.f) loss_add(loss_acc, g, i, lscale * (double)masked_row_const);
+    return;
+  }
+  const float* st = (dir == 0 ? s12 : s21) + (int64_t)(pair0 + g) * 3 * N + i;
+  invR[idx] = 1.f / (fmaxf(st[0], eps) * scale);      // applied to the stored (scaled) values
+  epsm[idx] = eps;
+  Tsum[idx] = st[N];
+  loss_add(loss_acc, g, i, lscale * (double)st[2 * N]);
+}
+
+// Producer-side packing of a teacher volume (fp32 -> fp16 * scale + row statistics), one warp per row, the row read
+// once (kept in registers for N <= 2048, re-read from L1 / L2 otherwise).
+template <int NV>
+__global__ void __launch_bounds__(256)
+    teacher_pack_rows(const float* __restrict__ t, int64_t pair_stride, int64_t row_stride, int64_t rows_total, int N,
+                      float eps, float scale, __half* __restrict__ out, int64_t out_pair_stride, int64_t out_row_stride,
+                      float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= rows_total) return;
+  const int64_t p = wid / N;
+  const int i = (int)(wid - p * N);
+  const float* row = t + p * pair_stride + (int64_t)i * row_stride;
+  __half* orow = out + p * out_pair_stride + (int64_t)i * out_row_stride;
+  float v[NV > 0 ? 4 * NV : 1];
+  float R = 0.f;
+  if (NV > 0) {
+#pragma unroll
+    for (int k = 0; k < 4 * NV; ++k) {
+      const int j = lane + 32 * k;
+      v[k] = (j < N) ? __ldg(row + j) : 0.f;
+      R += v[k];
+    }
+  } else {
+    for (int j = lane; j < N; j += 32) R += __ldg(row + j);
+  }
+  R = warp_sum(R);
+  const float ir = 1.f / fmaxf(R, eps);
+  float T = 0.f, A = 0.f;
+  if (NV > 0) {
+#pragma unroll
+    for (int k = 0; k < 4 * NV; ++k) {
+      const int j = lane + 32 * k;
+      if (j < N) {
+        const float tt = fmaxf(v[k] * ir, eps);
+        T += tt;
+        A = fmaf(tt, __log2f(tt), A);
+        orow[j] = __float2half_rn(v[k] * scale);
+      } else if (j < out_row_stride) {
+        orow[j] = __float2half_rn(0.f);      // row padding (rows are padded to 16 bytes for vector loads)
+      }
+    }
+  } else {
+    for (int j = lane; j < N; j += 32) {
+      const float c = __ldg(row + j);
+      const float tt = fmaxf(c * ir, eps);
+      T += tt;
+      A = fmaf(tt, __log2f(tt), A);
+      orow[j] = __float2half_rn(c * scale);
+    }
+    for (int j = N + lane; j < out_row_stride; j += 32) orow[j] = __float2half_rn(0.f);
+  }
+  T = warp_sum(T);
+  A = warp_sum(A) * 0.69314718055994531f;
+  if (lane == 0) {
+    float* st = stats + p * 3 * N + i;
+    st[0] = R;
+    st[N] = T;
+    st[2 * N] = A;
   }
 }
 
@@ -414,8 +523,9 @@ __global__ void kl_finalize_stats(int G, int N, const float* __restrict__ invR, 
 // direction) and transposed on the way in, t~21 read with lanes along i and added.  256 threads; ends with a barrier.
 // VEC: teacher rows are 16-byte aligned (128-bit loads); otherwise four scalar loads per thread (ragged N such as
 // 37^2: still 256 contiguous bytes per 16 threads).
+template <class TT>
 struct TeacherView {
-  const float *t12, *t21;           // already offset to the pair
+  const TT *t12, *t21;              // already offset to the pair
   int64_t row_stride;
   const float *ir12, *ir21;         // 1 / row sum (0 for masked rows), already offset to the pair
   const float *e12, *e21;           // eps of kept rows (0 for masked rows)
@@ -423,18 +533,18 @@ struct TeacherView {
 // Four teacher values of one thread.  Aligned rows (VEC): columns col .. col + 3 as one 128-bit load.  Ragged rows
 // (N % 4 != 0, e.g. 37^2): columns col, col + 16, col + 32, col + 48, so that the 16 lanes of a row read 64 contiguous
 // bytes per instruction instead of 16-byte-strided words.
-template <bool VEC>
-__device__ __forceinline__ float4 teacher_ld4(const float* src, int col, int N) {
-  if (VEC) return __ldg(reinterpret_cast<const float4*>(src));
+template <bool VEC, class TT>
+__device__ __forceinline__ float4 teacher_ld4(const TT* src, int col, int N) {
+  if (VEC) return t_load4(src);
   float4 v;
-  v.x = __ldg(src);
-  v.y = (col + 16 < N) ? __ldg(src + 16) : 0.f;
-  v.z = (col + 32 < N) ? __ldg(src + 32) : 0.f;
-  v.w = (col + 48 < N) ? __ldg(src + 48) : 0.f;
+  v.x = t_load(src);
+  v.y = (col + 16 < N) ? t_load(src + 16) : 0.f;
+  v.z = (col + 32 < N) ? t_load(src + 32) : 0.f;
+  v.w = (col + 48 < N) ? t_load(src + 48) : 0.f;
   return v;
 }
-template <bool VEC>
-__device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& tv, int N, int i0, int j0) {
+template <bool VEC, class TT>
+__device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView<TT>& tv, int N, int i0, int j0) {
   const int tr = threadIdx.x >> 4;
   // tile column of a thread's element q: tc + q * cs
   const int tc = VEC ? (threadIdx.x & 15) * 4 : (threadIdx.x & 15);
@@ -447,12 +557,12 @@ __device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& 
     const int r = ps * 16 + tr;
     const int i = i0 + r, j = j0 + tc;
     const bool ok12 = i < N && j < N;
-    v12[ps] = ok12 ? teacher_ld4<VEC>(tv.t12 + (int64_t)i * tv.row_stride + j, j, N) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v12[ps] = ok12 ? teacher_ld4<VEC, TT>(tv.t12 + (int64_t)i * tv.row_stride + j, j, N) : make_float4(0.f, 0.f, 0.f, 0.f);
     ir12[ps] = ok12 ? tv.ir12[i] : 0.f;
     ee12[ps] = ok12 ? tv.e12[i] : 0.f;
     const int jj = j0 + r, ii = i0 + tc;
     const bool ok21 = jj < N && ii < N;
-    v21[ps] = ok21 ? teacher_ld4<VEC>(tv.t21 + (int64_t)jj * tv.row_stride + ii, ii, N) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v21[ps] = ok21 ? teacher_ld4<VEC, TT>(tv.t21 + (int64_t)jj * tv.row_stride + ii, ii, N) : make_float4(0.f, 0.f, 0.f, 0.f);
     ir21[ps] = ok21 ? tv.ir21[jj] : 0.f;
     ee21[ps] = ok21 ? tv.e21[jj] : 0.f;
   }
@@ -477,10 +587,11 @@ __device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView& 
   }
   __syncthreads();
 }
-__device__ __forceinline__ TeacherView teacher_view(const float* t12, const float* t21, int64_t t_pair_stride,
-                                                    int64_t t_row_stride, int pair, int g, int G, int N, const float* invR,
-                                                    const float* epsm) {
-  TeacherView tv;
+template <class TT>
+__device__ __forceinline__ TeacherView<TT> teacher_view(const TT* t12, const TT* t21, int64_t t_pair_stride,
+                                                        int64_t t_row_stride, int pair, int g, int G, int N,
+                                                        const float* invR, const float* epsm) {
+  TeacherView<TT> tv;
   tv.t12 = t12 + (int64_t)pair * t_pair_stride;
   tv.t21 = t21 + (int64_t)pair * t_pair_stride;
   tv.row_stride = t_row_stride;
@@ -494,14 +605,14 @@ __device__ __forceinline__ TeacherView teacher_view(const float* t12, const floa
 // Step 3 as a kernel of its own is only needed by forward-only calls (the pass-1 epilogue then reads W^T for the D
 // term); with a backward, kl_dz_fast builds the tile itself and W^T is never written.
 // grid (N/64 i-tiles, N/64 j-tiles, G), block 256.  W^T rows are padded to a multiple of 4 floats: 128-bit stores.
-template <bool VEC>
+template <bool VEC, class TT>
 __global__ void __launch_bounds__(256)
-    kl_build_w_fast(const float* __restrict__ t12, const float* __restrict__ t21, int64_t t_pair_stride,
+    kl_build_w_fast(const TT* __restrict__ t12, const TT* __restrict__ t21, int64_t t_pair_stride,
                     int64_t t_row_stride, int pair0, int G, int N, const float* __restrict__ invR,
                     const float* __restrict__ epsm, float* __restrict__ WT, int ldw) {
   __shared__ float ws[64][65];
   const int g = blockIdx.z, i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
-  load_w_tile<VEC>(ws, teacher_view(t12, t21, t_pair_stride, t_row_stride, pair0 + g, g, G, N, invR, epsm), N, i0, j0);
+  load_w_tile<VEC, TT>(ws, teacher_view<TT>(t12, t21, t_pair_stride, t_row_stride, pair0 + g, g, G, N, invR, epsm), N, i0, j0);
   const int tr = threadIdx.x >> 4, tc = (threadIdx.x & 15) * 4;
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
@@ -514,10 +625,10 @@ __global__ void __launch_bounds__(256)
 
 // grid (N/64 j-tiles, N/64 i-tiles, G), block 256.  The W^T tile comes straight from the teacher volumes (no W^T
 // buffer in the backward path).
-template <bool VEC>
+template <bool VEC, class TT>
 __global__ void __launch_bounds__(256)
-    kl_dz_fast(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const float* __restrict__ t12,
-               const float* __restrict__ t21, int64_t t_pair_stride, int64_t t_row_stride, int pair0,
+    kl_dz_fast(int G, int N, float grad_scale, const __half* __restrict__ Z, int ldz, const TT* __restrict__ t12,
+               const TT* __restrict__ t21, int64_t t_pair_stride, int64_t t_row_stride, int pair0,
                const float* __restrict__ invR, const float* __restrict__ epsm, const float* __restrict__ rc,
                __nv_bfloat16* __restrict__ dZ, int ldd, float* __restrict__ rowdot, float* __restrict__ coldot,
                double* __restrict__ loss_acc) {
@@ -536,7 +647,7 @@ __global__ void __launch_bounds__(256)
     zpre[ps] = (i < N && j0 + jc < N) ? __ldg(reinterpret_cast<const uint4*>(Z + ((int64_t)g * N + i) * ldz + j0 + jc))
                                       : make_uint4(0u, 0u, 0u, 0u);
   }
-  load_w_tile<VEC>(ws, teacher_view(t12, t21, t_pair_stride, t_row_stride, pair0 + g, g, G, N, invR, epsm), N, i0, j0);
+  load_w_tile<VEC, TT>(ws, teacher_view<TT>(t12, t21, t_pair_stride, t_row_stride, pair0 + g, g, G, N, invR, epsm), N, i0, j0);
   const float s = grad_scale * 0.5f / (float)N;
   const float* rr = rc + (int64_t)g * N;
   const float* cc = rc + ((int64_t)G + g) * N;
@@ -731,6 +842,79 @@ int64_t auto_group(int64_t P, int64_t N, int64_t C) {
   return g > P ? P : g;
 }
 
+template <class TT>
+void launch_dz(bool vec_ok, dim3 grid, cudaStream_t stream, int g, int N, float grad_scale, const KLWorkspace& w,
+               const TT* t12, const TT* t21, int64_t t_pair_stride, int64_t t_row_stride, int p0) {
+  if (vec_ok)
+    kl_dz_fast<true, TT><<<grid, 256, 0, stream>>>(g, N, grad_scale, w.Z, w.ldn, t12, t21, t_pair_stride, t_row_stride, p0,
+                                                   w.invR, w.epsm, w.rc, w.dZ, w.ldn, w.rowdot, w.coldot, w.loss_acc);
+  else
+    kl_dz_fast<false, TT><<<grid, 256, 0, stream>>>(g, N, grad_scale, w.Z, w.ldn, t12, t21, t_pair_stride, t_row_stride, p0,
+                                                    w.invR, w.epsm, w.rc, w.dZ, w.ldn, w.rowdot, w.coldot, w.loss_acc);
+}
+
+// teacher row statistics (computed here, or taken from the producer) and, for forward-only calls, the W^T tile
+template <class TT>
+int teacher_stage_t(const TT* t12, const TT* t21, int64_t t_pair_stride, int64_t t_row_stride, const float* tstats12,
+                    const float* tstats21, float scale, const uint8_t* m1, const uint8_t* m2, int p0, int g, int N,
+                    float eps, float masked_const, bool backward, const KLWorkspace& w, bool* vec_ok,
+                    cudaStream_t stream) {
+  const int64_t warps = 2 * (int64_t)g * N;
+  const bool rows_aligned = t_row_stride % 4 == 0 && t_pair_stride % 4 == 0 &&
+                            reinterpret_cast<uintptr_t>(t12) % (4 * sizeof(TT)) == 0 &&
+                            reinterpret_cast<uintptr_t>(t21) % (4 * sizeof(TT)) == 0;
+  if (tstats12) {
+    GD3_PROF("kl_stats_from_input", stream);
+    kl_stats_from_input<<<(unsigned)ceil_div<int64_t>(warps, 256), 256, 0, stream>>>(
+        tstats12, tstats21, m1, m2, p0, g, N, eps, scale, masked_const, w.invR, w.epsm, w.Tsum, w.loss_acc);
+  } else {
+    GD3_PROF("kl_teacher_stats", stream);
+    const unsigned blocks = (unsigned)ceil_div<int64_t>(warps, 8);
+    const float eps_sum = eps * scale;
+#define GD3_TSTATS(NV, VEC)                                                                                            \
+  kl_teacher_stats_vec<NV, VEC, TT><<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, p0, g, N, \
+                                                                eps, eps_sum, masked_const, w.invR, w.epsm, w.Tsum,      \
+                                                                w.loss_acc)
+    // (the scalar-load instantiation of the register-resident kernel measured slower than the two-pass kernel on
+    // unaligned rows -- 345 vs 185 us at N = 37^2 -- so ragged N keeps the two-pass kernel)
+    const bool v4 = rows_aligned && (N % 4 == 0 || t_row_stride >= round_up<int64_t>(N, 4));
+    if (v4 && N <= 512) GD3_TSTATS(4, true);
+    else if (v4 && N <= 1024) GD3_TSTATS(8, true);
+    else if (v4 && N <= 2048) GD3_TSTATS(16, true);
+    else
+      kl_teacher_stats<TT><<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, p0, g, N, eps,
+                                                       eps_sum, masked_const, w.invR, w.epsm, w.Tsum, w.loss_acc);
+#undef GD3_TSTATS
+  }
+  GD3_CHECK_LAUNCH();
+  // 128-bit (fp32) / 64-bit (fp16) teacher loads: rows aligned, and either N % 4 == 0 or rows padded so that the last
+  // vector of a row stays inside it (gd3_teacher_pack pads to a multiple of 8; elements beyond N are masked at use)
+  *vec_ok = rows_aligned && (N % 4 == 0 || t_row_stride >= round_up<int64_t>(N, 4));
+  if (!backward) {
+    // forward only: the pass-1 epilogue needs W^T for the D term
+    dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
+    GD3_PROF("kl_build_w_fast", stream);
+    if (*vec_ok)
+      kl_build_w_fast<true, TT><<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, p0, g, N, w.invR, w.epsm,
+                                                          w.WT, w.ldw);
+    else
+      kl_build_w_fast<false, TT><<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, p0, g, N, w.invR, w.epsm,
+                                                           w.WT, w.ldw);
+    GD3_CHECK_LAUNCH();
+  }
+  return GD3_OK;
+}
+int teacher_stage(bool f16, const void* t12, const void* t21, int64_t t_pair_stride, int64_t t_row_stride,
+                  const float* tstats12, const float* tstats21, float scale, const uint8_t* m1, const uint8_t* m2, int p0,
+                  int g, int N, float eps, float masked_const, bool backward, const KLWorkspace& w, bool* vec_ok,
+                  cudaStream_t stream) {
+  if (f16)
+    return teacher_stage_t(static_cast<const __half*>(t12), static_cast<const __half*>(t21), t_pair_stride, t_row_stride,
+                           tstats12, tstats21, scale, m1, m2, p0, g, N, eps, masked_const, backward, w, vec_ok, stream);
+  return teacher_stage_t(static_cast<const float*>(t12), static_cast<const float*>(t21), t_pair_stride, t_row_stride,
+                         tstats12, tstats21, scale, m1, m2, p0, g, N, eps, masked_const, backward, w, vec_ok, stream);
+}
+
 }  // namespace
 }  // namespace gd3
 
@@ -751,7 +935,8 @@ size_t gd3_cost_kl_workspace(int64_t P, int64_t N, int64_t C, int64_t pairs_per_
 }
 
 int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N, int64_t C, int64_t s1P, int64_t s1N,
-                int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const float* t12, const float* t21,
+                int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const void* t12, const void* t21,
+                int teacher_dtype, float teacher_scale, const float* tstats12, const float* tstats21,
                 int64_t t_pair_stride, int64_t t_row_stride, const uint8_t* m1, const uint8_t* m2, int variant,
                 float eps, float grad_scale, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group,
                 void* workspace, size_t workspace_bytes, void* stream_) {
@@ -765,6 +950,11 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
               variant);
   GD3_REQUIRE((grad_f1 == nullptr) == (grad_f2 == nullptr), "gd3_cost_kl: pass both gradients or neither");
   GD3_REQUIRE(eps > 0.f, "gd3_cost_kl: eps must be positive");
+  GD3_REQUIRE(teacher_dtype == GD3_DTYPE_F32 || teacher_dtype == GD3_DTYPE_F16,
+              "gd3_cost_kl: teacher volumes must be fp32 or fp16 (gd3_teacher_pack), got dtype %d", teacher_dtype);
+  GD3_REQUIRE(teacher_scale > 0.f, "gd3_cost_kl: teacher_scale must be positive");
+  GD3_REQUIRE((tstats12 == nullptr) == (tstats21 == nullptr), "gd3_cost_kl: pass both teacher statistics or neither");
+  const bool t_f16 = teacher_dtype == GD3_DTYPE_F16;
   const bool backward = grad_f1 != nullptr;
   const int64_t G = gd3_cost_kl_group_size(P, N, C, pairs_per_group);
   GD3_REQUIRE(G <= 65535 && ceil_div<int64_t>(N, 32) <= 65535, "gd3_cost_kl: problem too large for one launch grid");
@@ -833,43 +1023,9 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       }
       GD3_CHECK_LAUNCH();
     }
-    {
-      const int64_t warps = 2 * (int64_t)g * N;
-      const bool rows_aligned = t_row_stride % 4 == 0 && t_pair_stride % 4 == 0 &&
-                                reinterpret_cast<uintptr_t>(t12) % 16 == 0 && reinterpret_cast<uintptr_t>(t21) % 16 == 0;
-      {
-        GD3_PROF("kl_teacher_stats", stream);
-        const unsigned blocks = (unsigned)ceil_div<int64_t>(warps, 8);
-#define GD3_TSTATS(NV, VEC)                                                                                          \
-  kl_teacher_stats_vec<NV, VEC><<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, \
-                                                            (int)N, eps, masked_const, w.invR, w.epsm, w.Tsum,          \
-                                                            w.loss_acc)
-        // (the scalar-load instantiation of the register-resident kernel measured slower than the two-pass kernel on
-        // unaligned rows -- 345 vs 185 us at N = 37^2 -- so ragged N keeps the two-pass kernel)
-        const bool v4 = rows_aligned && N % 4 == 0;
-        if (v4 && N <= 512) GD3_TSTATS(4, true);
-        else if (v4 && N <= 1024) GD3_TSTATS(8, true);
-        else if (v4 && N <= 2048) GD3_TSTATS(16, true);
-        else
-          kl_teacher_stats<<<blocks, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, m1, m2, (int)p0, g, (int)N,
-                                                       eps, masked_const, w.invR, w.epsm, w.Tsum, w.loss_acc);
-#undef GD3_TSTATS
-      }
-      GD3_CHECK_LAUNCH();
-      vec_ok = N % 4 == 0 && rows_aligned;
-      if (!backward) {
-        // forward only: the pass-1 epilogue needs W^T for the D term
-        dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
-        GD3_PROF("kl_build_w_fast", stream);
-        if (vec_ok)
-          kl_build_w_fast<true><<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N,
-                                                          w.invR, w.epsm, w.WT, w.ldw);
-        else
-          kl_build_w_fast<false><<<grid, 256, 0, stream>>>(t12, t21, t_pair_stride, t_row_stride, (int)p0, g, (int)N,
-                                                           w.invR, w.epsm, w.WT, w.ldw);
-        GD3_CHECK_LAUNCH();
-      }
-    }
+    if ((rc = teacher_stage(t_f16, t12, t21, t_pair_stride, t_row_stride, tstats12, tstats21, teacher_scale, m1, m2, (int)p0,
+                            g, (int)N, eps, masked_const, backward, w, &vec_ok, stream)))
+      return rc;
     {
       tc::GemmShape s{(int)N, (int)N, (int)C, g};
       if (backward) {
@@ -902,14 +1058,12 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         // workspace rows are padded to a multiple of 8 elements, so the 128-bit kernel also serves ragged N (elements in
         // the padding are masked on read and never consumed: the TMA extents of the gradient GEMMs stop at N)
         GD3_PROF("kl_dz_fast", stream);
-        if (vec_ok)
-          kl_dz_fast<true><<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, t12, t21, t_pair_stride, t_row_stride,
-                                                     (int)p0, w.invR, w.epsm, w.rc, w.dZ, w.ldn, w.rowdot, w.coldot,
-                                                     w.loss_acc);
+        if (t_f16)
+          launch_dz(vec_ok, grid, stream, g, (int)N, grad_scale, w, static_cast<const __half*>(t12),
+                    static_cast<const __half*>(t21), t_pair_stride, t_row_stride, (int)p0);
         else
-          kl_dz_fast<false><<<grid, 256, 0, stream>>>(g, (int)N, grad_scale, w.Z, w.ldn, t12, t21, t_pair_stride, t_row_stride,
-                                                      (int)p0, w.invR, w.epsm, w.rc, w.dZ, w.ldn, w.rowdot, w.coldot,
-                                                      w.loss_acc);
+          launch_dz(vec_ok, grid, stream, g, (int)N, grad_scale, w, static_cast<const float*>(t12),
+                    static_cast<const float*>(t21), t_pair_stride, t_row_stride, (int)p0);
       }
       GD3_CHECK_LAUNCH();
       {
@@ -940,6 +1094,32 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       if (rc) return rc;
     }
   }
+  return GD3_OK;
+}
+
+int gd3_teacher_pack(const float* t, int64_t P, int64_t N, int64_t t_pair_stride, int64_t t_row_stride, float eps,
+                     float scale, void* out_f16, int64_t out_row_stride, float* stats, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (P == 0 || N == 0) return GD3_OK;
+  GD3_REQUIRE(P > 0 && N > 0, "gd3_teacher_pack: bad sizes P=%lld N=%lld", (long long)P, (long long)N);
+  GD3_REQUIRE(t && out_f16 && stats, "gd3_teacher_pack: null pointer");
+  GD3_REQUIRE(eps > 0.f && scale > 0.f, "gd3_teacher_pack: eps and scale must be positive");
+  GD3_REQUIRE(out_row_stride >= N && out_row_stride < N + 32, "gd3_teacher_pack: output row stride %lld must be in [N, N + 32)",
+              (long long)out_row_stride);
+  const int64_t rows = P * N;
+  const unsigned blocks = (unsigned)ceil_div<int64_t>(rows, 8);
+  __half* out = static_cast<__half*>(out_f16);
+  {
+    GD3_PROF("teacher_pack_rows", stream);
+#define GD3_TPACK(NV) \
+  teacher_pack_rows<NV><<<blocks, 256, 0, stream>>>(t, t_pair_stride, t_row_stride, rows, (int)N, eps, scale, out, N * out_row_stride, out_row_stride, stats)
+    if (N <= 512) GD3_TPACK(4);
+    else if (N <= 1024) GD3_TPACK(8);
+    else if (N <= 2048) GD3_TPACK(16);
+    else GD3_TPACK(0);
+#undef GD3_TPACK
+  }
+  GD3_CHECK_LAUNCH();
   return GD3_OK;
 }
 

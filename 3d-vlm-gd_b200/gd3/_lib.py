@@ -36,8 +36,9 @@ SYMBOLS = {
     'gd3_fast_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd3_cost_kl_group_size': (_i64, [_i64, _i64, _i64, _i64]),
     'gd3_cost_kl_workspace': (_sz, [_i64, _i64, _i64, _i64, _int]),
-    'gd3_cost_kl': (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i64,
-                           _vp, _vp, _int, _f32, _f32, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    'gd3_cost_kl': (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _f32,
+                           _vp, _vp, _i64, _i64, _vp, _vp, _int, _f32, _f32, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    'gd3_teacher_pack': (_int, [_vp, _i64, _i64, _i64, _i64, _f32, _f32, _vp, _i64, _vp, _vp]),
     'gd3_smooth_ap_workspace': (_sz, [_i64, _i64, _i64, _int]),
     'gd3_smooth_ap': (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp,
                              _sz, _vp]),
@@ -55,7 +56,7 @@ SYMBOLS = {
     'gd3_debug_gemm_bf16_mn': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _int, _vp]),
 }
 
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 DIST = {'dot': 0, 'l2': 1}
 VARIANT = {'mast3r': 0, 'vggt': 1, 'me': 2, 'me_joint': 3}
 
@@ -120,8 +121,11 @@ def dtype_code(t):
 
 
 # ---------------------------------------------------------------------------------------------
-def reciprocal_nn(A, B, dist='dot', want_A=True, want_B=True):
-    """nn_A, nn_B (int64 CUDA tensors or None) for fp32 CUDA descriptors A (nA, D), B (nB, D)."""
+def reciprocal_nn(A, B, dist='dot', want_A=True, want_B=True, packed=False):
+    """nn_A, nn_B (int64 CUDA tensors or None) for fp32 CUDA descriptors A (nA, D), B (nB, D).
+
+    packed=True (both directions wanted): one (nA + nB,) tensor [nn_A | nn_B], so that a caller that needs the indices
+    on the host issues a single copy."""
     if dist not in DIST:
         raise ValueError(f'Unknown {dist=}')
     require_cuda(A, B)
@@ -131,14 +135,19 @@ def reciprocal_nn(A, B, dist='dot', want_A=True, want_B=True):
     nA, nB = A.shape[0], B.shape[0]
     if A.shape[1] != B.shape[1]:
         raise ValueError('descriptor dimensions differ')
-    nn_A = torch.empty(nA, dtype=torch.int64, device=A.device) if want_A else None
-    nn_B = torch.empty(nB, dtype=torch.int64, device=A.device) if want_B else None
+    both = None
+    if packed and want_A and want_B:
+        both = torch.empty(nA + nB, dtype=torch.int64, device=A.device)
+        nn_A, nn_B = both[:nA], both[nA:]
+    else:
+        nn_A = torch.empty(nA, dtype=torch.int64, device=A.device) if want_A else None
+        nn_B = torch.empty(nB, dtype=torch.int64, device=A.device) if want_B else None
     ws_bytes = lib.gd3_reciprocal_nn_workspace(nA, nB)
     ws = workspace(ws_bytes, A.device)
     with torch.cuda.device(A.device):
         check(lib.gd3_reciprocal_nn(ptr(A), nA, ptr(B), nB, A.shape[1], DIST[dist], ptr(nn_A), ptr(nn_B),
                                     ptr(ws), ws.numel(), stream_ptr()))
-    return nn_A, nn_B
+    return both if both is not None else (nn_A, nn_B)
 
 
 def fast_reciprocal_nn(pts1, pts2, seeds, max_iter=10, dist='dot', host_poll=True):

@@ -56,8 +56,10 @@ def bruteforce_reciprocal_nns(A, B, device='cuda', block_size=None, dist='l2'):
     if dist not in _DISTS:
         raise ValueError(f'Unknown {dist=}')
     _need_gpu(device)
-    nn_A, nn_B = _lib.reciprocal_nn(_on_device(A, device), _on_device(B, device), dist=dist)
-    return nn_A.cpu().numpy(), nn_B.cpu().numpy()
+    A, B = _on_device(A, device), _on_device(B, device)
+    # one device -> host copy (and one synchronisation) for both index arrays ("one D2H + sync at the end")
+    both = _lib.reciprocal_nn(A, B, dist=dist, packed=True).cpu().numpy()
+    return both[:A.shape[0]], both[A.shape[0]:]
 
 
 class cdistMatcher:

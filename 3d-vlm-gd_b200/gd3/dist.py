@@ -23,7 +23,7 @@ def shard_range(num_pairs, rank, world_size):
 
 # per-pair entries of a batch dict (leading axis = pair; h1 / h2 / g1 / g2 may carry a layer axis in front of it);
 # anything else (head parameters, a depth map shared by all pairs, scalars) is replicated
-PAIR_KEYS = ('f1', 'f2', 't12', 't21', 'm1', 'm2', 'g1', 'g2', 'h1', 'h2', 'kp1', 'kp2', 'p3d1', 'p3d2', 'dep1', 'dep2',
+PAIR_KEYS = ('f1', 'f2', 't12', 't21', 'ts12', 'ts21', 'm1', 'm2', 'g1', 'g2', 'h1', 'h2', 'kp1', 'kp2', 'p3d1', 'p3d2', 'dep1', 'dep2',
              'depth_map1', 'depth_map2')
 
 

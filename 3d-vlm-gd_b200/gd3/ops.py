@@ -30,23 +30,82 @@ def _as_mask(m, P, N, device):
 # --------------------------------------------------------------------------------------------
 # dense cost-volume KL
 # --------------------------------------------------------------------------------------------
+TEACHER_SCALE = 1024.0     # default power-of-two scale of packed (fp16) teacher volumes
+
+
+def pack_teacher(teacher, eps=1e-8, scale=TEACHER_SCALE):
+    """Producer-side packing of a teacher cost volume (P, N, N) fp32 -> (fp16 volume * scale, stats (P, 3, N)).
+
+    The statistics are what ``get_masked_patch_cost`` / ``kl_divergence_map`` derive from each row
+    (utils/functions.py:419-420, utils/losses.py:6-9): row sum, sum of the clamped normalised row and its
+    entropy term.  ``cost_kl_raw`` / ``cost_volume_kl`` take the pair as ``(volume, stats)``: half the bytes of
+    the largest input of a step and no statistics pass inside the loss."""
+    require_cuda(teacher)
+    lib = load()
+    if teacher.dim() != 3 or teacher.shape[1] != teacher.shape[2]:
+        raise ValueError(f'pack_teacher: expected (P, N, N), got {tuple(teacher.shape)}')
+    t = teacher.to(_F32)
+    if t.stride(2) != 1:
+        t = t.contiguous()
+    P, N, _ = t.shape
+    ld = (N + 7) // 8 * 8          # rows padded to 16 bytes: vector loads in the loss also for ragged N (37^2)
+    buf = torch.empty(P, N, ld, dtype=torch.float16, device=t.device)
+    stats = torch.empty(P, 3, N, dtype=_F32, device=t.device)
+    if P and N:
+        with torch.cuda.device(t.device):
+            check(lib.gd3_teacher_pack(ptr(t), P, N, t.stride(0), t.stride(1), float(eps), float(scale), ptr(buf), ld,
+                                       ptr(stats), stream_ptr()))
+    return buf[:, :, :N], stats
+
+
+def _teacher_args(teacher, P, N, name):
+    """-> (tensor, dtype code, stats or None) for an fp32 volume, an fp16 volume, or a (fp16 volume, stats) pair."""
+    from ._lib import DTYPE_F16, DTYPE_F32
+    stats = None
+    if isinstance(teacher, (tuple, list)):
+        teacher, stats = teacher
+    if tuple(teacher.shape) != (P, N, N):
+        raise ValueError(f'cost_volume_kl: {name} must be (P, N, N) = {(P, N, N)}, got {tuple(teacher.shape)}')
+    if teacher.dtype == torch.float16:
+        code = DTYPE_F16
+    else:
+        teacher = teacher.to(_F32)
+        code = DTYPE_F32
+    if teacher.stride(2) != 1:       # row / pair strides are free (pack_teacher pads its rows), columns must be contiguous
+        teacher = teacher.contiguous()
+    if stats is not None:
+        if tuple(stats.shape) != (P, 3, N):
+            raise ValueError(f'cost_volume_kl: {name} statistics must be (P, 3, N) = {(P, 3, N)}')
+        stats = stats.to(_F32).contiguous()
+    return teacher, code, stats
+
+
 def cost_kl_raw(f1, f2, teacher12, teacher21, mask1, mask2, variant='mast3r', eps=1e-8, grad_scale=1.0,
-                want_grad=True, pairs_per_group=0):
-    """-> (loss (P,), grad_f1, grad_f2) with gradients of ``grad_scale * loss[p]`` (None if not wanted)."""
-    require_cuda(f1, f2, teacher12, teacher21)
+                want_grad=True, pairs_per_group=0, teacher_scale=None):
+    """-> (loss (P,), grad_f1, grad_f2) with gradients of ``grad_scale * loss[p]`` (None if not wanted).
+
+    teacher12 / teacher21: fp32 volumes (the reference's tensors), or the packed form of ``pack_teacher``: an fp16
+    volume (values times ``teacher_scale``, default 1024) or the pair ``(fp16 volume, stats)``."""
+    require_cuda(f1, f2)
     lib = load()
     if f1.dim() != 3 or f1.shape != f2.shape:
         raise ValueError(f'cost_volume_kl: f1/f2 must both be (P, N, C), got {tuple(f1.shape)} {tuple(f2.shape)}')
     if f1.dtype != f2.dtype:
         raise ValueError('cost_volume_kl: f1 and f2 must share a dtype')
     P, N, C = f1.shape
-    if tuple(teacher12.shape) != (P, N, N) or tuple(teacher21.shape) != (P, N, N):
-        raise ValueError(f'cost_volume_kl: teacher volumes must be (P, N, N) = {(P, N, N)}')
     if variant not in ('mast3r', 'vggt'):
         raise ValueError(f'cost_volume_kl: unknown variant {variant!r}')
     dev = f1.device
-    t12 = teacher12.to(_F32).contiguous()
-    t21 = teacher21.to(_F32).contiguous()
+    t12, code12, st12 = _teacher_args(teacher12, P, N, 'teacher12')
+    t21, code21, st21 = _teacher_args(teacher21, P, N, 'teacher21')
+    require_cuda(t12, t21)
+    if code12 != code21 or (st12 is None) != (st21 is None):
+        raise ValueError('cost_volume_kl: both teacher volumes must come in the same form')
+    if t21.stride() != t12.stride():
+        t21 = t21.contiguous()
+        t12 = t12.contiguous()
+    from ._lib import DTYPE_F16
+    scale = (TEACHER_SCALE if teacher_scale is None else float(teacher_scale)) if code12 == DTYPE_F16 else 1.0
     m1 = _as_mask(mask1, P, N, dev)
     m2 = _as_mask(mask2, P, N, dev)
     loss = torch.empty(P, dtype=_F32, device=dev)
@@ -58,9 +117,9 @@ def cost_kl_raw(f1, f2, teacher12, teacher21, mask1, mask2, variant='mast3r', ep
     with torch.cuda.device(dev):
         check(lib.gd3_cost_kl(ptr(f1), ptr(f2), dtype_code(f1), P, N, C,
                               f1.stride(0), f1.stride(1), f1.stride(2), f2.stride(0), f2.stride(1), f2.stride(2),
-                              ptr(t12), ptr(t21), N * N, N, ptr(m1), ptr(m2), VARIANT[variant], float(eps),
-                              float(grad_scale), ptr(loss), ptr(g1), ptr(g2), int(pairs_per_group), ptr(ws),
-                              ws.numel(), stream_ptr()))
+                              ptr(t12), ptr(t21), code12, scale, ptr(st12), ptr(st21), t12.stride(0), t12.stride(1), ptr(m1), ptr(m2),
+                              VARIANT[variant], float(eps), float(grad_scale), ptr(loss), ptr(g1), ptr(g2),
+                              int(pairs_per_group), ptr(ws), ws.numel(), stream_ptr()))
     return loss, g1, g2
 
 
@@ -69,7 +128,7 @@ class _CostVolumeKL(torch.autograd.Function):
     def forward(ctx, f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, pairs_per_group, grad_mode):
         need_grad = grad_mode and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         loss, g1, g2 = cost_kl_raw(f1, f2, teacher12, teacher21, mask1, mask2, variant, eps, 1.0, need_grad,
-                                   pairs_per_group)
+                                   pairs_per_group)     # teacher*: tensor or (fp16 volume, stats) of pack_teacher
         ctx.save_for_backward(g1, g2)
         return loss
 
@@ -87,7 +146,9 @@ def cost_volume_kl(f1, f2, teacher12, teacher21, mask1=None, mask2=None, variant
     """Dense cost-volume KL loss per pair, ``(P,)``.
 
     f1, f2: (P, N, C) student patch features (fp32 or bf16, any strides); teacher12 / teacher21:
-    (P, N, N) teacher volumes; mask1 / mask2: (P, N) or (N,) bool patch masks (None = keep all).
+    (P, N, N) teacher volumes -- fp32 like the reference's, or the packed form ``pack_teacher`` returns
+    ((fp16 volume, row statistics): half the bytes, no statistics pass); mask1 / mask2: (P, N) or (N,) bool
+    patch masks (None = keep all).
     Equals ``calculate_cost_loss`` of the reference (variant 'mast3r':
     src/finetune_timm_mast3r.py:504-540, 'vggt': src/finetune_timm_vggt.py:488-533) for each pair.
     """

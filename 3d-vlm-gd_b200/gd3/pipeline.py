@@ -29,7 +29,8 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
 
     batch (all CUDA tensors):
       f1, f2     (P, N, C)  student patch features for the cost volume (fp32 / bf16)
-      t12, t21   (P, N, N)  teacher volumes;  m1, m2 (P, N) bool patch masks
+      t12, t21   (P, N, N)  teacher volumes, fp32 -- or fp16 from ``ops.pack_teacher`` together with its row statistics
+                 ts12, ts21 (P, 3, N);  m1, m2 (P, N) bool patch masks
       g1, g2     (P, N, C) or (L, P, N, C)  token maps the matching descriptors are sampled from (L maps: their mean)
       h1, h2     optional, same shapes: token maps the depth-head features are sampled from (default: g1, g2)
       kp1, kp2   (P, K, 2)  pixel keypoints;  p3d1, p3d2 (P, K, 3);  dep1, dep2 (P, K) keypoint depths
@@ -102,7 +103,10 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
                                               depth_threshold, 0.05, False, w_rank, w_l1, backward)
 
     # ---- dense cost-volume KL (K1) ----
-    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, batch['t12'], batch['t21'], m1, m2, variant,
+    # teacher volumes: fp32, or the producers' packed form (fp16 volume t12 / t21 + row statistics ts12 / ts21)
+    t12 = (batch['t12'], batch['ts12']) if 'ts12' in batch else batch['t12']
+    t21 = (batch['t21'], batch['ts21']) if 'ts21' in batch else batch['t21']
+    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, t12, t21, m1, m2, variant,
                                    grad_scale=w['kl'] * inv_p, want_grad=backward, pairs_per_group=pairs_per_group)
 
     # ---- Smooth-AP (K2) ----
@@ -167,14 +171,54 @@ class GraphedStep:
         return self.out
 
 
+class PinnedBatch:
+    """All tensors of one host batch in ONE pinned arena, so that the upload is a single copy.
+
+    ``PinnedBatch(batch)`` lays the (CPU) tensors of ``batch`` out back to back (256-byte aligned) in one pinned
+    uint8 buffer; non-tensor entries (e.g. the head parameters that live on the device) are passed through.
+    ``views(arena)`` re-creates the dict as typed views into any uint8 buffer of the same layout -- the host arena
+    or its device copy.  A data loader fills ``host_views()`` in place for the next step instead of allocating."""
+
+    ALIGN = 256
+
+    def __init__(self, batch):
+        self.meta = []          # (key, dtype, shape, offset, nbytes)
+        self.extra = {}
+        off = 0
+        for k, v in batch.items():
+            if torch.is_tensor(v) and v.device.type == 'cpu':
+                n = v.numel() * v.element_size()
+                self.meta.append((k, v.dtype, tuple(v.shape), off, n))
+                off = (off + n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            else:
+                self.extra[k] = v
+        self.nbytes = off
+        self.arena = torch.empty(max(off, 1), dtype=torch.uint8).pin_memory()
+        hv = self.views(self.arena)
+        for k, v in batch.items():
+            if k not in self.extra:
+                hv[k].copy_(v)
+
+    def views(self, arena):
+        out = dict(self.extra)
+        for k, dtype, shape, off, n in self.meta:
+            out[k] = arena[off:off + n].view(dtype).view(shape)
+        return out
+
+    def host_views(self):
+        return self.views(self.arena)
+
+
 class DevicePrefetcher:
     """Double-buffered host -> device staging for batches that live in pinned host memory.
 
     ``for dev_batch in DevicePrefetcher(batches, device): ...`` uploads batch i+1 on a side stream while
     the caller's stream works on batch i, so a step costs max(copy, compute) instead of their sum.  Every
     tensor of every batch is still copied exactly once (non-tensor entries such as the head parameters
-    are passed through).  The consumer stream waits on the copy event before it touches a batch, and the
-    copy stream waits until the consumer has finished with the buffer it is about to overwrite.
+    are passed through).  A ``PinnedBatch`` goes over as ONE copy into a device arena that is reused every ``depth``
+    steps (no allocation in the steady state); a plain dict of pinned tensors is copied tensor by tensor.  The
+    consumer stream waits on the copy event before it touches a batch, and the copy stream waits until the consumer
+    has finished with the buffer it is about to overwrite.
     """
 
     def __init__(self, batches, device, depth=2):
@@ -182,30 +226,43 @@ class DevicePrefetcher:
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.depth = depth
-        self.queue = []          # [(device batch, ready event)]
-        self.done_events = []    # consumer-side events guarding buffer reuse
+        self.queue = []          # [(device batch, ready event, slot)]
+        self.slot_done = [None] * depth    # consumer-side event of the last batch that used a slot (guards its reuse)
+        self.arenas = []         # device arenas for PinnedBatch uploads, one per slot
+        self.n_enqueued = 0
 
     def _enqueue(self):
         try:
             host = next(self.batches)
         except StopIteration:
             return False
+        slot = self.n_enqueued % self.depth
         with torch.cuda.stream(self.copy_stream):
-            if len(self.done_events) >= self.depth:
-                self.copy_stream.wait_event(self.done_events.pop(0))
-            dev = {}
-            for k, v in host.items():
-                dev[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
+            if self.slot_done[slot] is not None:      # the consumer must be done with the batch that lived in this slot
+                self.copy_stream.wait_event(self.slot_done[slot])
+            if isinstance(host, PinnedBatch):
+                if len(self.arenas) <= slot:
+                    self.arenas.append(torch.empty(max(host.nbytes, 1), dtype=torch.uint8, device=self.device))
+                elif self.arenas[slot].numel() < host.nbytes:
+                    self.arenas[slot] = torch.empty(host.nbytes, dtype=torch.uint8, device=self.device)
+                arena = self.arenas[slot]
+                arena[:host.arena.numel()].copy_(host.arena, non_blocking=True)
+                dev = host.views(arena)
+            else:
+                dev = {}
+                for k, v in host.items():
+                    dev[k] = v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        self.queue.append((dev, ev))
+        self.n_enqueued += 1
+        self.queue.append((dev, ev, slot))
         return True
 
     def __iter__(self):
         for _ in range(self.depth):
             self._enqueue()
         while self.queue:
-            dev, ev = self.queue.pop(0)
+            dev, ev, slot = self.queue.pop(0)
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
             for v in dev.values():
@@ -214,5 +271,5 @@ class DevicePrefetcher:
             yield dev
             done = torch.cuda.Event()
             done.record(cur)
-            self.done_events.append(done)
+            self.slot_done[slot] = done
             self._enqueue()

@@ -9,11 +9,16 @@ N GPUs (launched under torchrun, one rank per GPU) every rank processes its own 
 independent, so there is no data-path collective and the scaling is weak.
 
 Rank 0 prints ONE JSON line (see the contract in the task description):
-  value      pairs/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  value      pairs/s with inputs resident in HBM (device-timed with CUDA events, max over ranks), one CUDA-graph
+             replay per step; `sustained` repeats it for >= 2 s with the clocks sampled
   e2e        pairs/s through gd3.pipeline.distillation_step from PINNED HOST buffers, H2D copies of all
              inputs and a D2H read of the losses inside the timed region
-  roofline   the tensor-core GEMM with the largest share of the step (algorithmic FLOPs / event time / peak)
+  roofline   the kernel with the largest share of the step, against the pipe that bounds it;
+             roofline_tensor: the tensor-core GEMM with the largest share against the burst cuBLAS bf16 peak
   cpu_baseline  the CPU oracle (port of the reference's per-pair flow) timed on a bounded sample, rank 0, N = 1
+  extra      BASELINE.json configs 3 (reciprocal NN, 8192 x 8192 x 24) and 4 (ViT-L/14 518 px, 64 pairs) on the same
+             GPU; with N > 1 also cfg4 strong scaling (64 pairs sharded over the ranks) and cfg5 (a ViT-L/14 training
+             step with the bucketed NCCL gradient all-reduce)
 ``--impl reference`` times that CPU port alone (all host threads), one pair per step.
 """
 import argparse
@@ -21,7 +26,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -89,7 +93,7 @@ class ClockSampler:
 
     def summary(self):
         import datetime
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for ln in self.lines:
             r = [c.strip() for c in ln.split(',')]
@@ -101,6 +105,7 @@ class ClockSampler:
                     continue
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
             except Exception:
                 continue
             for n, v in zip(names, r[4:8]):
@@ -108,7 +113,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), power_w_max=(max(pw) if pw else None))
 
 
 def dist_setup(n_gpus):
@@ -147,7 +152,7 @@ def algorithmic_work(cfg):
                 k1_bytes=2.0 * N * N * 4 + 2.0 * N * C * 2 + 2.0 * N * C * 2)
 
 
-# per-launch algorithmic FLOPs of the tensor-core GEMMs, keyed by the library's profile names
+# per-step algorithmic FLOPs of the tensor-core GEMMs, keyed by the library's profile names
 def gemm_flops_per_step(cfg, P):
     N, C, K = cfg['N'], cfg['C'], cfg['K']
     return {
@@ -161,7 +166,7 @@ def gemm_flops_per_step(cfg, P):
     }
 
 
-# fp32 operations of the restated math per ordered keypoint pair and hidden unit, forward + backward (DESIGN.md, K4):
+# fp32 operations of the restated math per ordered keypoint pair and hidden unit, forward + backward (DESIGN.md 4.3):
 # LayerNorm scale/affine 4, erf (A&S 7.1.25) + Phi + GELU 15, w2 dot 2, GELU' 3, LayerNorm backward means 4,
 # parameter gradients 6, d h 5, the two u-gradient accumulations 2.  MUFU (rcp, ex2) counted as 1 each.
 RANK_FLOPS_PER_UNIT = 41
@@ -173,13 +178,33 @@ def ncu_traffic(kernel, workload):
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
             t = json.load(f)
-        return t.get(workload, {}).get(kernel, {}).get('dram_bytes_per_launch')
+        e = t.get(workload, {}).get(kernel, {})
+        return e.get('dram_bytes_per_launch'), e.get('source')
     except (OSError, ValueError):
-        return None
+        return None, None
+
+
+def timed_replays(fn, steps, world, local, sample_clocks=True):
+    """K calls of ``fn`` bracketed by barrier + synchronize, CUDA events on the current stream, max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk = ClockSampler(local) if sample_clocks else None
+    if clk:
+        clk.__enter__()
+    barrier(world)
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    barrier(world)
+    if clk:
+        clk.__exit__()
+    ms = max_over_ranks(e0.elapsed_time(e1), world) / steps
+    return ms, (clk.summary() if clk else None), out
 
 
 def run_ours(args):
-    from gd3 import _lib, pipeline
+    from gd3 import _lib, ops, pipeline
     import bench_common
     rank, world, local = dist_setup(args.gpus)
     cfg = dict(WORKLOADS[args.workload])
@@ -187,24 +212,35 @@ def run_ours(args):
         cfg['P'] = args.pairs
     P = cfg['P']
     dev = torch.device('cuda', local)
-    lib = _lib.load()
+    _lib.load()
     peaks = load_peaks()
-
+    import bench_extras
+    # every rank pulls its inputs through PCIe from pinned host memory: keep the process (and the pages it pins) on the
+    # NUMA node of its GPU, and with several ranks share the cores instead of oversubscribing them
+    all_cpus = sorted(os.sched_getaffinity(0))
+    affinity = bench_extras.bind_to_gpu_numa_node(local)
     if world > 1:
-        # every rank builds its own batch on the host: share the cores instead of oversubscribing them
-        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // 2))
     # ---- synthetic inputs: every rank gets its own seeded batch (pair indices rank*P ...) ----
     host = bench_common.make_batch(cfg, cfg_id=cfg['cfg_id'], pair0=rank * P)
     host = bench_common.to_device(host, 'cpu', feature_dtype=torch.bfloat16)
-    pinned = {}
-    for k, v in host.items():
-        if torch.is_tensor(v):
-            pinned[k] = v.contiguous().pin_memory()
     head_dev = {n: (t.to(dev) if torch.is_tensor(t) else t) for n, t in host['head'].items()}
+    # Two forms of the teacher volumes: fp32 as the reference holds them, and the form the teacher-side producers
+    # (gd3_teacher_volume / gd3_vggt_attn_accumulate + gd3_teacher_pack) emit: fp16 * 1024 plus per-row statistics.
+    # The packed form is the headline input format (half the bytes of the largest input, no statistics pass); the
+    # fp32 form is measured next to it.  Both meet the BASELINE parity bars against the fp32 reference
+    # (tests/test_gpu_cost_kl.py::test_cost_kl_packed_teacher_full_size).
+    pinned32 = {k: v.contiguous().pin_memory() for k, v in host.items() if torch.is_tensor(v)}
+    pinned = dict(pinned32)
+    for d in ('12', '21'):
+        vol, st = ops.pack_teacher(pinned32['t' + d].to(dev))
+        pinned['t' + d] = vol.cpu().pin_memory()
+        pinned['ts' + d] = st.cpu().pin_memory()
+    del vol, st
     resident = {k: v.to(dev) for k, v in pinned.items()}
     resident['head'] = head_dev
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
-    in_bytes_dev = h2d_bytes
+    h2d_bytes32 = sum(v.numel() * v.element_size() for v in pinned32.values())
 
     def step(batch):
         return pipeline.distillation_step(batch, variant=cfg['variant'], grid=cfg['grid'], backward=True,
@@ -215,125 +251,162 @@ def run_ours(args):
         out = step(resident)
     barrier(world)
 
-    # ---- timed region 1: inputs resident in HBM; per-kernel CUDA events on the launching stream ----
+    # ---- timed region 1: eager launches with a CUDA-event pair around every kernel (per-kernel breakdown) ----
     launches0 = _lib.launch_count()
     _lib.profile_enable(True)
     _lib.profile_read()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier(world)
-        e0.record()
-        for _ in range(args.steps):
-            out = step(resident)
-        e1.record()
-        barrier(world)
-    ms_total = max_over_ranks(e0.elapsed_time(e1), world)
+    eager_ms_step, clocks, out = timed_replays(lambda: step(resident), args.steps, world, local)
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     launches = _lib.launch_count() - launches0
-    ms_step = ms_total / args.steps
+    ms_step = eager_ms_step
     value = world * P / (ms_step * 1e-3)
-    clocks = clk.summary()
 
     # ---- timed region 1b: the same K steps as one CUDA-graph replay per step (no per-launch gaps); this is the
     #      device-resident figure reported as `value`, region 1 supplies the per-kernel breakdown ----
-    eager_ms_step = ms_step
     graph_note = 'eager launches'
+    gstep = None
+    sustained = None
     if not args.no_graph:
         try:
             gstep = pipeline.GraphedStep(resident, variant=cfg['variant'], grid=cfg['grid'], backward=True,
                                          pairs_per_group=args.pairs_per_group)
             for _ in range(max(3, args.warmup)):
                 gstep()
-            launches_g0 = _lib.launch_count()
-            with ClockSampler(local) as clk_g:
-                barrier(world)
-                e0.record()
-                for _ in range(args.steps):
-                    out = gstep()
-                e1.record()
-                barrier(world)
-            ms_step = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+            ms_step, clk_g, out = timed_replays(gstep, args.steps, world, local)
             value = world * P / (ms_step * 1e-3)
-            clocks = clk_g.summary() or clocks
+            clocks = clk_g or clocks
             graph_note = 'one CUDA-graph replay per step (the graph holds the %d kernel launches of a step)' % (
                 launches // args.steps)
+            # ---- sustained leg: >= 2 s of back-to-back replays, clocks and power sampled throughout ----
+            n_sus = max(args.steps, int(args.sustained_s * 1e3 / ms_step) + 1)
+            sus_ms, sus_clk, _ = timed_replays(gstep, n_sus, world, local)
+            sustained = dict(ms_per_step=round(sus_ms, 4), value=round(world * P / (sus_ms * 1e-3), 2), steps=n_sus,
+                             seconds=round(sus_ms * n_sus * 1e-3, 2), clocks=sus_clk)
         except Exception as exc:      # stay loud: the eager figure is reported and the reason is printed
             print(f'[bench] CUDA-graph capture failed, reporting eager launches: {exc!r}', file=sys.stderr)
             ms_step = eager_ms_step
 
+    # ---- the same step on the reference's fp32 teacher volumes (device-resident, graph replay) ----
+    fp32_teacher = None
+    if not args.no_graph and not args.quick:
+        res32 = {k: (resident[k] if k not in ('t12', 't21') else pinned32[k].to(dev)) for k in pinned32}
+        res32['head'] = head_dev
+        try:
+            g32 = pipeline.GraphedStep(res32, variant=cfg['variant'], grid=cfg['grid'], backward=True,
+                                       pairs_per_group=args.pairs_per_group)
+            for _ in range(3):
+                g32()
+            ms32, _, _ = timed_replays(g32, args.steps, world, local, sample_clocks=False)
+            fp32_teacher = dict(ms_per_step=round(ms32, 4), value=round(world * P / (ms32 * 1e-3), 2))
+            del g32
+        except Exception as exc:
+            print(f'[bench] fp32-teacher leg failed: {exc!r}', file=sys.stderr)
+        del res32
+
     # ---- timed region 2 (e2e): every step uploads ALL of its inputs from pinned host memory and reads its
     #      losses back; uploads of step i+1 overlap the kernels of step i (gd3.pipeline.DevicePrefetcher) ----
     e2e_steps = max(5, min(args.steps, 20))
-
-    def host_batches(n):
-        for _ in range(n):
-            hb = dict(pinned)
-            hb['head'] = head_dev
-            yield hb
     res_host = torch.empty(4, P, dtype=torch.float32).pin_memory()
 
-    def e2e_run(n):
-        last = None
-        for b in pipeline.DevicePrefetcher(host_batches(n), dev):
-            o = step(b)
-            res_host.copy_(torch.stack([o['kl'], o['ap'], o['rank'], o['l1']]), non_blocking=True)   # D2H of the step's result
-            last = o
+    def h2d_probe(nbytes=256 << 20, reps=6):
+        """Plain pinned -> device copy bandwidth of this box (the ceiling of the e2e leg), GB/s."""
+        h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        d.copy_(h, non_blocking=True)
         torch.cuda.synchronize()
-        return last
-    e2e_run(3)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        torch.cuda.synchronize()
+        return nbytes * reps / (time.perf_counter() - t0) / 1e9
+
+    def e2e_measure(host_tensors):
+        # the whole host batch lives in one pinned arena: one H2D copy per step (gd3.pipeline.PinnedBatch)
+        hb = dict(host_tensors)
+        hb['head'] = head_dev
+        packed_host = pipeline.PinnedBatch(hb)
+
+        def host_batches(n):
+            for _ in range(n):
+                yield packed_host
+
+        def e2e_run(n):
+            for b in pipeline.DevicePrefetcher(host_batches(n), dev):
+                o = step(b)
+                res_host.copy_(torch.stack([o['kl'], o['ap'], o['rank'], o['l1']]), non_blocking=True)   # D2H of the step's result
+            torch.cuda.synchronize()
+        e2e_run(3)
+        barrier(world)
+        # device-timed on the compute stream (uploads run on the prefetcher's stream, but every step's kernels wait for
+        # their batch and the result D2H is on the compute stream); the host clock is kept next to it as a cross-check
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        g0.record()
+        e2e_run(e2e_steps)
+        g1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        barrier(world)
+        return max_over_ranks(g0.elapsed_time(g1), world) / e2e_steps, wall
     barrier(world)
-    # device-timed on the compute stream (uploads run on the prefetcher's stream, but every step's kernels wait for
-    # their batch and the result D2H is on the compute stream); the host clock is kept next to it as a cross-check
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    g0.record()
-    e2e_run(e2e_steps)
-    g1.record()
-    torch.cuda.synchronize()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    barrier(world)
-    e2e_ms = max_over_ranks(g0.elapsed_time(g1), world) / e2e_steps
+    h2d_gbs = h2d_probe()            # all ranks copy at the same time, like in the e2e leg
+    e2e_ms, e2e_wall_ms = e2e_measure(pinned)
+    e2e32_ms = None
+    if not args.quick:
+        e2e32_ms, _ = e2e_measure(pinned32)
     d2h_bytes = res_host.numel() * res_host.element_size()
+
+    # ---- extras: BASELINE configs 3 and 4 on this GPU; strong scaling and the cfg5 training step with N > 1 ----
+    extra = {}
+    if not args.no_extras:
+        import bench_extras
+        try:
+            extra = bench_extras.run(args, rank, world, local, dev, peaks)
+        except Exception as exc:
+            print(f'[bench] extras failed: {exc!r}', file=sys.stderr)
+            extra = dict(error=repr(exc))
 
     if rank != 0:
         return
-    # ---- roofline of the dominant tensor-core kernel ----
+    # ---- rooflines ----
     flops = gemm_flops_per_step(cfg, P)
     tot_prof_ms = sum(ms for _, ms in prof.values()) or 1.0
     shares = {k: dict(launches=c, ms_per_step=ms / args.steps, share=ms / tot_prof_ms) for k, (c, ms) in prof.items()}
-    gemms = {k: v for k, v in prof.items() if k in flops}
-    top = max(gemms, key=lambda k: gemms[k][1]) if gemms else None
-    roofline = None
-    if top:
-        cnt, ms = gemms[top]
+    sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+    peak32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    K = cfg['K']
+
+    def roofline_of(name):
+        """Roofline entry of one kernel timed in isolation (CUDA events around each launch, eager region)."""
+        cnt, ms = prof[name]
         per_launch_ms = ms / cnt
-        per_launch_flops = flops[top] * args.steps / cnt
-        achieved = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
-        peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
-        roofline = dict(kernel=top, bound='tensor', achieved=round(achieved, 2), peak=peak, unit='TFLOP/s',
-                        frac=round(achieved / peak, 4), traffic=ncu_traffic(top, args.workload),
-                        peak_source=peaks['source'] + ' (sustained cuBLAS bf16)',
-                        share_of_step=round(ms / tot_prof_ms, 4), launches=cnt,
-                        us_per_launch=round(per_launch_ms * 1e3, 2))
-    # ---- the kernel with the largest share of the step is the pair kernel of the depth-ranking loss: fp32 SIMT
-    #      work (LayerNorm / GELU / logistic per hidden unit of every ordered keypoint pair), neither HBM- nor
-    #      tensor-bound, so it is reported against the fp32 FMA peak at the measured SM clock ----
-    simt = None
-    if 'rank_pairs' in prof:
-        cnt, ms = prof['rank_pairs']
-        K = cfg['K']
-        flops_launch = RANK_FLOPS_PER_UNIT * 128.0 * K * K * (2 * P) * args.steps / cnt
-        sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
-        peak32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        ach = flops_launch / (ms / cnt * 1e-3) / 1e12
-        simt = dict(kernel='rank_pairs', bound='fp32 FMA pipe', achieved=round(ach, 2), peak=round(peak32, 1),
-                    unit='TFLOP/s', frac=round(ach / peak32, 4), share_of_step=round(ms / tot_prof_ms, 4),
-                    us_per_launch=round(ms / cnt * 1e3, 1),
-                    flops_per_pair_and_hidden_unit=RANK_FLOPS_PER_UNIT,
-                    traffic=ncu_traffic('rank_pairs', args.workload),
-                    note='algorithmic fp32 flops (DESIGN.md, K4) per ordered pair and hidden unit, fwd+bwd; '
-                         'peak = 148 SMs x 128 lanes x 2 flop x SM clock')
+        traffic, tsrc = ncu_traffic(name, args.workload)
+        common = dict(kernel=name, share_of_step=round(ms / tot_prof_ms, 4), launches_per_step=cnt // args.steps,
+                      us_per_launch=round(per_launch_ms * 1e3, 2), traffic=traffic,
+                      traffic_source=tsrc or 'no ncu capture of this kernel / workload committed')
+        if name in flops:
+            per_launch = flops[name] * args.steps / cnt
+            ach = per_launch / (per_launch_ms * 1e-3) / 1e12
+            peak = peaks['bf16_tflops'] or peaks['bf16_tflops_sustained']
+            return dict(common, bound='tensor', achieved=round(ach, 2), peak=peak, unit='TFLOP/s', frac=round(ach / peak, 4),
+                        peak_source=peaks['source'] + ' cuBLAS bf16 burst figure (the kernel is timed alone)',
+                        flops_per_launch=per_launch)
+        if name == 'rank_pairs':
+            per_launch = RANK_FLOPS_PER_UNIT * 128.0 * K * K * (2 * P) * args.steps / cnt
+            ach = per_launch / (per_launch_ms * 1e-3) / 1e12
+            return dict(common, bound='fp32 FMA pipe', achieved=round(ach, 2), peak=round(peak32, 1), unit='TFLOP/s',
+                        frac=round(ach / peak32, 4), flops_per_launch=per_launch,
+                        flops_per_pair_and_hidden_unit=RANK_FLOPS_PER_UNIT,
+                        peak_source='148 SMs x 128 fp32 lanes x 2 flop x %.0f MHz (SM clock sampled during the run); '
+                                    'not in MEASURED_PEAKS.json: the kernel is neither HBM- nor tensor-bound '
+                                    '(K^2 x 128 LayerNorm/GELU/logistic evaluations, DESIGN.md 4.3)' % sm_mhz)
+        return dict(common, bound='hbm', achieved=None, peak=peaks['hbm_gbs'], unit='GB/s', frac=None)
+    top = max(prof, key=lambda k: prof[k][1]) if prof else None
+    roofline = roofline_of(top) if top else None
+    gemms = [k for k in prof if k in flops]
+    top_gemm = max(gemms, key=lambda k: prof[k][1]) if gemms else None
+    roofline_tensor = roofline_of(top_gemm) if top_gemm else None
     work = algorithmic_work(cfg)
     step_tflops = (work['k1_flops'] + work['k2_flops']) * P / (ms_step * 1e-3) / 1e12
     peak_s = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
@@ -341,7 +414,11 @@ def run_ours(args):
     # ---- CPU baseline (oracle port of the reference's per-pair flow), bounded sample ----
     cpu = None
     if world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)          # the CPU arm may use every host core again
         cpu = cpu_baseline(cfg, host, sample_pairs=args.cpu_pairs)
+        if not args.no_extras and isinstance(extra.get('cfg3'), dict):
+            import bench_extras
+            extra['cfg3'].update(bench_extras.cfg3_cpu_check())
 
     line = dict(
         metric=METRIC, value=round(value, 2), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -350,22 +427,37 @@ def run_ours(args):
         config=dict(workload=f"{args.workload}: {cfg['desc']}, {P} synthetic pairs per GPU",
                     pairs_per_gpu=P, tokens=cfg['N'], channels=cfg['C'], keypoints=cfg['K'], variant=cfg['variant'],
                     parallelism=f'dp{world} (pairs sharded, no data-path collective)',
-                    l2='inputs larger than L2: %.0f MB of teacher volumes + features are read per step' % (in_bytes_dev / 1e6),
+                    l2='inputs larger than L2: %.0f MB of teacher volumes + features are read per step' % (h2d_bytes / 1e6),
                     losses='cost-volume KL + Smooth-AP + depth ranking (2 views) + cross-view L1, fwd+bwd',
+                    teacher_format='fp16 x 1024 + row statistics as emitted by the teacher-side producer '
+                                   '(gd3_teacher_pack); the fp32-teacher figures are in fp32_teacher / e2e.fp32_teacher',
                     launch_mode=graph_note, eager_ms_per_step=round(eager_ms_step, 4),
-                    eager_note='eager launches with a CUDA-event pair around every kernel (source of the per-kernel shares)'),
+                    eager_note='eager launches with a CUDA-event pair around every kernel (source of the per-kernel shares)',
+                    cpu_affinity=affinity),
         clocks=clocks,
+        sustained=sustained,
+        fp32_teacher=fp32_teacher,
         e2e=dict(value=round(world * P / (e2e_ms * 1e-3), 2), unit=UNIT, h2d_bytes_per_step=int(h2d_bytes),
                  d2h_bytes_per_step=int(d2h_bytes), ms_per_step=round(e2e_ms, 3), host_clock_ms_per_step=round(e2e_wall_ms, 3),
-                 steps=e2e_steps, bound='PCIe: every input of the step is uploaded from pinned host memory'),
+                 steps=e2e_steps, h2d_gbs_per_gpu=round(h2d_bytes / (e2e_ms * 1e-3) / 1e9, 2),
+                 h2d_gbs_aggregate=round(world * h2d_bytes / (e2e_ms * 1e-3) / 1e9, 2),
+                 h2d_probe_gbs_per_gpu=round(h2d_gbs, 2),
+                 bound='PCIe: every input of the step is uploaded from pinned host memory (one copy of a pinned arena per '
+                       'step, overlapped with the previous step); h2d_probe_gbs_per_gpu is the plain pinned-copy '
+                       'bandwidth of this box measured on all ranks at once just before',
+                 fp32_teacher=(None if e2e32_ms is None else dict(
+                     value=round(world * P / (e2e32_ms * 1e-3), 2), ms_per_step=round(e2e32_ms, 3),
+                     h2d_bytes_per_step=int(h2d_bytes32)))),
         gpu_launches=int(launches),
         roofline=roofline,
-        roofline_simt=simt,
+        roofline_tensor=roofline_tensor,
         step_tensor_fraction=dict(algorithmic_tflops=round(step_tflops, 2), peak=peak_s,
                                   frac=round(step_tflops / peak_s, 4),
-                                  note='(K1 + K2 algorithmic FLOPs of SURVEY 8-d) / whole-step time'),
+                                  note='(K1 + K2 algorithmic FLOPs of SURVEY 8-d) / whole-step time, against the '
+                                       'sustained cuBLAS bf16 figure'),
         kernels={k: dict(launches=v['launches'], us_per_step=round(v['ms_per_step'] * 1e3, 1), share=round(v['share'], 4))
                  for k, v in sorted(shares.items(), key=lambda kv: -kv[1]['share'])},
+        extra=extra,
         cpu_baseline=cpu,
     )
     print(json.dumps(line))
@@ -387,7 +479,9 @@ def cpu_baseline(cfg, host, sample_pairs=10):
     dt = time.perf_counter() - t0
     return dict(value=round(sample_pairs / dt, 4), unit=UNIT, cores=torch.get_num_threads(), kind='port',
                 sample=f'{sample_pairs} pairs of the same workload through the CPU oracle (port of the reference '
-                       f'PyTorch flow, fp32, one pair per call), {dt:.1f} s')
+                       f'PyTorch flow, fp32, one pair per call), {dt:.1f} s',
+                note='the reference is Python and /root/reference does not exist on the GPU box, so its live functions '
+                     'cannot be timed here; the port is pinned to them by tests/golden (DESIGN.md 2)')
 
 
 def run_reference(args):
@@ -436,8 +530,12 @@ def main():
     ap.add_argument('--pairs', type=int, default=0, help='pairs per GPU (default: the workload\'s)')
     ap.add_argument('--pairs-per-group', type=int, default=0)
     ap.add_argument('--cpu-pairs', type=int, default=10)
+    ap.add_argument('--sustained-s', type=float, default=2.0, help='length of the sustained graph-replay leg')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
+    ap.add_argument('--no-extras', action='store_true', help='skip the cfg3 / cfg4 / cfg5 blocks')
+    ap.add_argument('--quick', action='store_true', help='skip the fp32-teacher legs (profiling runs)')
+    ap.add_argument('--cfg5', action='store_true', help='run the cfg5 training-step block also at N = 1')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -38,6 +38,7 @@ extern "C" {
 /* element types of feature tensors */
 #define GD3_DTYPE_F32 0
 #define GD3_DTYPE_BF16 1
+#define GD3_DTYPE_F16 2 /* packed teacher volumes only (gd3_teacher_pack) */
 
 /* distances of the reciprocal-NN matcher (mast3r/fast_nn.py:26-37) */
 #define GD3_DIST_DOT 0
@@ -99,8 +100,12 @@ int gd3_fast_reciprocal_nn(const float* pts1, int64_t n1, const float* pts2, int
  * kl_divergence_map (utils/losses.py:5-15).
  *   f1, f2   (P, N, C) student patch features, dtype f32 or bf16, arbitrary element strides
  *            (sP, sN, sC) -- the MASt3R path hands over a channel-major view (sN = 1, sC = N)
- *   t12, t21 (P, N, N) fp32 teacher volumes, rows of t12 = patches of view 1, rows of t21 =
- *            patches of view 2; t_row_stride / t_pair_stride in elements
+ *   t12, t21 (P, N, N) teacher volumes, rows of t12 = patches of view 1, rows of t21 = patches of view 2;
+ *            t_row_stride / t_pair_stride in elements.  teacher_dtype GD3_DTYPE_F32 (the reference's
+ *            tensors, teacher_scale 1) or GD3_DTYPE_F16: the packed form of gd3_teacher_pack, values
+ *            times teacher_scale -- half the bytes of the largest input of the step.
+ *   tstats12/21 (P, 3, N) fp32 row statistics [sum_j c | sum_j t~ | sum_j t~ ln t~] from
+ *            gd3_teacher_pack, or NULL, NULL: computed here with one more pass over the volumes
  *   m1, m2   (P, N) uint8 patch masks (mask_patch_1 of each direction; mask_patch_2 is always
  *            None in the reference's callers)
  *   loss     (P) fp32, one value per pair = (KL_12 + KL_21) / 2
@@ -113,10 +118,26 @@ int gd3_fast_reciprocal_nn(const float* pts1, int64_t n1, const float* pts2, int
 int64_t gd3_cost_kl_group_size(int64_t P, int64_t N, int64_t C, int64_t pairs_per_group);
 size_t gd3_cost_kl_workspace(int64_t P, int64_t N, int64_t C, int64_t pairs_per_group, int with_backward);
 int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N, int64_t C, int64_t s1P, int64_t s1N,
-                int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const float* t12, const float* t21,
+                int64_t s1C, int64_t s2P, int64_t s2N, int64_t s2C, const void* t12, const void* t21,
+                int teacher_dtype, float teacher_scale, const float* tstats12, const float* tstats21,
                 int64_t t_pair_stride, int64_t t_row_stride, const uint8_t* m1, const uint8_t* m2, int variant,
                 float eps, float grad_scale, float* loss, void* grad_f1, void* grad_f2, int64_t pairs_per_group,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Teacher-side packing of a cost volume for gd3_cost_kl: the last step of a teacher producer
+ * (dust3r/dust3r/model.py:346-366 -> res2['tgt_attn_map'], vggt/models/aggregator.py:259-273 followed by
+ * src/finetune_timm_vggt.py:390-392).  Every row is read once: out = fp16(c * scale) and the statistics
+ * get_masked_patch_cost / kl_divergence_map derive from the row (utils/functions.py:419-420,
+ * utils/losses.py:6-9): R = sum_j c, T = sum_j t~, A = sum_j t~ ln t~ with t~ = max(c / max(R, eps), eps).
+ *   t      (P, N, N) fp32, pair / row strides in elements
+ *   out    (P, N, out_row_stride) fp16, out_row_stride >= N elements (a multiple of 8 keeps rows 16-byte aligned for
+ *          gd3_cost_kl's vector loads when N is ragged, e.g. 37^2; the padding is zero-filled)
+ *   stats  (P, 3, N) fp32 [R | T | A]
+ * scale: a power of two (1024 keeps probabilities down to 6e-8 normal fp16 numbers).
+ * ------------------------------------------------------------------------------------------ */
+int gd3_teacher_pack(const float* t, int64_t P, int64_t N, int64_t t_pair_stride, int64_t t_row_stride, float eps,
+                     float scale, void* out_f16, int64_t out_row_stride, float* stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Smooth-AP sparse-correspondence loss, forward + backward, batched over P pairs.

@@ -132,3 +132,63 @@ def test_cost_kl_properties_at_batch_size(ops):
     assert_grad_close(g2[3], g1[0], cos_min=0.9999, name='swap', norm_rtol=1e-2)
     radial = (g1[0] * f1).sum(-1).abs().max() / (g1[0].norm(dim=-1).max() * f1.norm(dim=-1).max())
     assert radial < 2e-2
+
+
+@pytest.mark.parametrize('cfg', ['cfg2', 'cfg4'])
+@pytest.mark.parametrize('with_stats', [True, False])
+def test_cost_kl_packed_teacher_full_size(ops, cfg, with_stats):
+    """Teacher volumes in the producers' packed form (fp16 * 1024 + row statistics, gd3_teacher_pack) against the CPU
+    oracle on the ORIGINAL fp32 volumes at the BASELINE.json sizes: same bars as the fp32 path."""
+    c = synth.CONFIGS[cfg]
+    N, C, variant = c['N'], c['C'], c['variant']
+    f1, f2 = synth.features(5100, N, C)
+    t12, t21 = synth.teacher_volume(5101, N, variant, heads=4), synth.teacher_volume(5102, N, variant, heads=4)
+    m1, m2 = synth.patch_mask(5103, N), synth.patch_mask(5104, N)
+    want, ga, gb = oracle_pair(f1, f2, t12, t21, m1, m2, variant)
+    p12, s12 = ops.pack_teacher(t12.cuda()[None])
+    p21, s21 = ops.pack_teacher(t21.cuda()[None])
+    assert p12.dtype == torch.float16 and s12.shape == (1, 3, N)
+    # the statistics are those of the fp32 rows
+    R = t12.double().sum(-1)
+    tt = (t12.double() / R.clamp_min(1e-8)[:, None]).clamp_min(1e-8)
+    assert torch.allclose(s12[0, 0].double().cpu(), R, rtol=1e-5)
+    assert torch.allclose(s12[0, 1].double().cpu(), tt.sum(-1), rtol=1e-5)
+    assert torch.allclose(s12[0, 2].double().cpu(), (tt * tt.log()).sum(-1), rtol=1e-4, atol=1e-6)
+    F1 = f1.cuda().to(torch.bfloat16)[None].requires_grad_(True)
+    F2 = f2.cuda().to(torch.bfloat16)[None].requires_grad_(True)
+    a12, a21 = ((p12, s12), (p21, s21)) if with_stats else (p12, p21)
+    loss = ops.cost_volume_kl(F1, F2, a12, a21, m1.cuda()[None], m2.cuda()[None], variant=variant)
+    loss.sum().backward()
+    assert rel_err(loss[0].item(), want) <= LOSS_RTOL, (loss[0].item(), want)
+    assert_grad_close(F1.grad[0].float().cpu(), ga, name='g1', norm_rtol=3e-2)
+    assert_grad_close(F2.grad[0].float().cpu(), gb, name='g2', norm_rtol=3e-2)
+    with torch.no_grad():
+        fwd = ops.cost_volume_kl(F1, F2, a12, a21, m1.cuda()[None], m2.cuda()[None], variant=variant)
+    assert rel_err(fwd[0].item(), want) <= LOSS_RTOL
+
+
+def test_cost_kl_packed_teacher_ragged_batched(ops):
+    """Packed teachers on a ragged size (N = 15 * 13, rows not 8-byte aligned -> scalar loads), 3 pairs, both variants,
+    all-masked and all-kept rows; mixing forms is rejected."""
+    N, C, P = 195, 72, 3
+    for variant in ('mast3r', 'vggt'):
+        pairs = []
+        for p in range(P):
+            f1, f2 = synth.features(5200 + p, N, C)
+            mode = ['bernoulli', 'all', 'none'][p]
+            pairs.append((f1, f2, synth.teacher_volume(5210 + p, N, variant), synth.teacher_volume(5220 + p, N, variant),
+                          synth.patch_mask(5230 + p, N, mode=mode), synth.patch_mask(5240 + p, N, mode=mode)))
+        want = [oracle_pair(*q, variant) for q in pairs]
+        st = [torch.stack([q[k] for q in pairs]).cuda() for k in range(6)]
+        t12 = ops.pack_teacher(st[2])
+        t21 = ops.pack_teacher(st[3])
+        F1, F2 = st[0].requires_grad_(True), st[1].requires_grad_(True)
+        loss = ops.cost_volume_kl(F1, F2, t12, t21, st[4], st[5], variant=variant, pairs_per_group=2)
+        loss.sum().backward()
+        for p in range(P):
+            assert abs(float(loss[p]) - want[p][0]) <= LOSS_RTOL * abs(want[p][0]) + 1e-7, (variant, p, float(loss[p]), want[p][0])
+            if float(want[p][1].norm()) > 0:
+                assert_grad_close(F1.grad[p].cpu(), want[p][1], name=f'g1[{p}]', norm_rtol=3e-2)
+                assert_grad_close(F2.grad[p].cpu(), want[p][2], name=f'g2[{p}]', norm_rtol=3e-2)
+    with pytest.raises(ValueError):
+        ops.cost_volume_kl(F1, F2, t12, st[3], st[4], st[5], variant='vggt')

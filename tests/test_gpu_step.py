@@ -148,3 +148,32 @@ def test_step_random_shapes(seed):
         if float(r.norm()) < 1e-12 and float(g.norm()) < 1e-9:
             continue
         assert_grad_close(g, r, name=f'{cfg} {k}', norm_rtol=3e-2)
+
+
+def test_pinned_batch_prefetcher_delivers_every_batch_intact():
+    """PinnedBatch (one pinned arena per host batch, one H2D copy) through the double-buffered DevicePrefetcher: every
+    step sees exactly its own batch although the two device arenas are reused and the consumer is slow."""
+    from gd3 import pipeline
+    g = torch.Generator().manual_seed(3)
+    steps = 7
+    src = [dict(a=torch.randn(1000, 33, generator=g), m=torch.rand(257, generator=g) < 0.5,
+                h=torch.randn(64, 8, generator=g).to(torch.float16), k=torch.randint(0, 99, (5, 2), generator=g),
+                head=dict(tag=i)) for i in range(steps)]
+    packed = [pipeline.PinnedBatch(b) for b in src]
+    assert packed[0].arena.is_pinned() and packed[0].nbytes % 256 == 0
+    hv = packed[2].host_views()
+    assert torch.equal(hv['a'], src[2]['a']) and torch.equal(hv['m'], src[2]['m']) and hv['head']['tag'] == 2
+    big = torch.randn(4096, 4096, device='cuda')
+    seen = 0
+    for i, dev in enumerate(pipeline.DevicePrefetcher(iter(packed), 'cuda')):
+        for _ in range(3):
+            big = big @ big * 1e-4          # keep the consumer stream busy while the next upload runs
+        for k in ('a', 'm', 'h', 'k'):
+            assert dev[k].is_cuda and torch.equal(dev[k].cpu(), src[i][k]), (i, k)
+        assert dev['head']['tag'] == i
+        seen += 1
+    assert seen == steps
+    # plain dicts of pinned tensors still work (tensor-by-tensor copies)
+    plain = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in src[:3]]
+    for i, dev in enumerate(pipeline.DevicePrefetcher(iter(plain), 'cuda')):
+        assert torch.equal(dev['a'].cpu(), src[i]['a'])
