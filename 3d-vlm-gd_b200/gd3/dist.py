@@ -96,10 +96,16 @@ class BucketedGradAllReduce:
     handling), divides by the world size, copies the means back into ``p.grad`` and optionally clips the global norm
     (Lightning ``gradient_clip_val=1.0``, src/main.py:158).
 
+    Bucket size: DDP's 25 MB default is sized for PCIe / InfiniBand rings.  Over NVLink 5 / NVSwitch a 1.2 GB all-reduce
+    takes 2 ms, so what shows up in the step is the fixed cost per collective (launch, stream hand-over, SMs taken
+    from the backward kernels): measured on 2 x B200 with a ViT-L/14 full fine-tune step (tools/cfg5_probe.py), the
+    exposed communication is 8.4 ms with 49 buckets of 25 MB, 3.5 ms with 12 x 100 MB and 0.76 ms with 3 x 400 MB.
+    The default is therefore 256 MB.
+
     Works with any backend; with ``gloo`` (CPU tests) everything runs synchronously on the host.
     """
 
-    def __init__(self, params, bucket_bytes=25 * 1024 * 1024, group=None):
+    def __init__(self, params, bucket_bytes=256 * 1024 * 1024, group=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1

@@ -240,7 +240,7 @@ def allreduce_bench(nbytes, world, dev, iters=10):
                 bus_gbs=round(2.0 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9, 1))
 
 
-def cfg5_block(args, rank, world, local, dev, pairs=4, K=128, steps=6, warmup=3):
+def cfg5_block(args, rank, world, local, dev, pairs=4, K=128, steps=6, warmup=3, bucket_mb=256):
     from transformers import CLIPVisionConfig, CLIPVisionModel
     from bench import barrier, max_over_ranks
     from gd3 import dist as gdist, ops
@@ -295,11 +295,11 @@ def cfg5_block(args, rank, world, local, dev, pairs=4, K=128, steps=6, warmup=3)
         barrier(world)
         return max_over_ranks(e0.elapsed_time(e1), world) / n, float(loss), float(norm)
 
-    red = gdist.BucketedGradAllReduce(params, bucket_bytes=25 * 1024 * 1024)
+    red = gdist.BucketedGradAllReduce(params, bucket_bytes=bucket_mb * 1024 * 1024)
     ms_full, loss, norm = timed(red, steps)
     red.remove()
     # the same step with the collective switched off (every rank keeps its local gradients): exposed communication
-    red_local = gdist.BucketedGradAllReduce(params, bucket_bytes=25 * 1024 * 1024)
+    red_local = gdist.BucketedGradAllReduce(params, bucket_bytes=bucket_mb * 1024 * 1024)
     red_local.world = 1
     ms_local, _, _ = timed(red_local, steps)
     red_local.remove()
@@ -309,6 +309,7 @@ def cfg5_block(args, rank, world, local, dev, pairs=4, K=128, steps=6, warmup=3)
                n_gpus=world, pairs_per_gpu=P, step_ms=round(ms_full, 3), step_ms_without_allreduce=round(ms_local, 3),
                exposed_allreduce_ms=round(ms_full - ms_local, 3), value=round(world * P / (ms_full * 1e-3), 2),
                unit='pairs/s', gradient_payload_mb=round(red.payload_bytes / 1e6, 1), buckets=len(red.buckets),
+               bucket_mb=bucket_mb,
                loss=round(loss, 5), grad_norm=round(norm, 5), steps=steps)
     if world > 1:
         blk['allreduce_full_finetune'] = allreduce_bench(red.payload_bytes, world, dev)
