@@ -28,6 +28,8 @@
 // Forward-only calls have no step 5: kl_build_w materialises W^T and the pass-1 epilogue accumulates D from it.
 // The fp32 N x N cost volume never exists in memory; only fp16 z / bf16 dz are staged for the gradient GEMMs (see
 // DESIGN.md for the TMEM budget argument against a single kernel).
+#include <type_traits>
+
 #include "../../include/gd3.h"
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -543,8 +545,60 @@ __device__ __forceinline__ float4 teacher_ld4(const TT* src, int col, int N) {
   v.w = (col + 48 < N) ? t_load(src + 48) : 0.f;
   return v;
 }
+// fp16 teacher, aligned rows: 8 halves (one 128-bit load) per thread and pass, two passes of 32 rows -- the same bytes
+// per load instruction as the fp32 path, so the tile stays latency-hidden at half the traffic.
+__device__ __forceinline__ void h8_to_float(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+    f[2 * k] = p.x;
+    f[2 * k + 1] = p.y;
+  }
+}
+__device__ __forceinline__ void load_w_tile_h8(float (*ws)[65], const TeacherView<__half>& tv, int N, int i0, int j0) {
+  const int tr = threadIdx.x >> 3, tc = (threadIdx.x & 7) * 8;
+  uint4 v12[2], v21[2];
+  float ir12[2], ee12[2], ir21[2], ee21[2];
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int r = ps * 32 + tr;
+    const int i = i0 + r, j = j0 + tc;
+    const bool ok12 = i < N && j < N;
+    v12[ps] = ok12 ? __ldg(reinterpret_cast<const uint4*>(tv.t12 + (int64_t)i * tv.row_stride + j)) : make_uint4(0u, 0u, 0u, 0u);
+    ir12[ps] = ok12 ? tv.ir12[i] : 0.f;
+    ee12[ps] = ok12 ? tv.e12[i] : 0.f;
+    const int jj = j0 + r, ii = i0 + tc;
+    const bool ok21 = jj < N && ii < N;
+    v21[ps] = ok21 ? __ldg(reinterpret_cast<const uint4*>(tv.t21 + (int64_t)jj * tv.row_stride + ii)) : make_uint4(0u, 0u, 0u, 0u);
+    ir21[ps] = ok21 ? tv.ir21[jj] : 0.f;
+    ee21[ps] = ok21 ? tv.e21[jj] : 0.f;
+  }
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int r = ps * 32 + tr;
+    float f[8];
+    h8_to_float(v12[ps], f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ws[tc + q][r] = fmaxf(f[q] * ir12[ps], ee12[ps]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int r = ps * 32 + tr;
+    float f[8];
+    h8_to_float(v21[ps], f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ws[r][tc + q] += fmaxf(f[q] * ir21[ps], ee21[ps]);
+  }
+  __syncthreads();
+}
 template <bool VEC, class TT>
 __device__ __forceinline__ void load_w_tile(float (*ws)[65], const TeacherView<TT>& tv, int N, int i0, int j0) {
+  if constexpr (VEC && std::is_same<TT, __half>::value) {
+    load_w_tile_h8(ws, tv, N, i0, j0);
+    return;
+  }
   const int tr = threadIdx.x >> 4;
   // tile column of a thread's element q: tc + q * cs
   const int tc = VEC ? (threadIdx.x & 15) * 4 : (threadIdx.x & 15);
@@ -860,9 +914,10 @@ int teacher_stage_t(const TT* t12, const TT* t21, int64_t t_pair_stride, int64_t
                     float eps, float masked_const, bool backward, const KLWorkspace& w, bool* vec_ok,
                     cudaStream_t stream) {
   const int64_t warps = 2 * (int64_t)g * N;
-  const bool rows_aligned = t_row_stride % 4 == 0 && t_pair_stride % 4 == 0 &&
-                            reinterpret_cast<uintptr_t>(t12) % (4 * sizeof(TT)) == 0 &&
-                            reinterpret_cast<uintptr_t>(t21) % (4 * sizeof(TT)) == 0;
+  // vector width of the teacher loads: 4 fp32 or 8 fp16 elements (16 bytes either way)
+  constexpr int VW = 16 / (int)sizeof(TT);
+  const bool rows_aligned = t_row_stride % VW == 0 && t_pair_stride % VW == 0 &&
+                            reinterpret_cast<uintptr_t>(t12) % 16 == 0 && reinterpret_cast<uintptr_t>(t21) % 16 == 0;
   if (tstats12) {
     GD3_PROF("kl_stats_from_input", stream);
     kl_stats_from_input<<<(unsigned)ceil_div<int64_t>(warps, 256), 256, 0, stream>>>(
@@ -877,7 +932,7 @@ int teacher_stage_t(const TT* t12, const TT* t21, int64_t t_pair_stride, int64_t
                                                                 w.loss_acc)
     // (the scalar-load instantiation of the register-resident kernel measured slower than the two-pass kernel on
     // unaligned rows -- 345 vs 185 us at N = 37^2 -- so ragged N keeps the two-pass kernel)
-    const bool v4 = rows_aligned && (N % 4 == 0 || t_row_stride >= round_up<int64_t>(N, 4));
+    const bool v4 = rows_aligned && (N % 4 == 0 || t_row_stride >= round_up<int64_t>(N, 4));     // (the statistics kernel loads 4 elements per lane)
     if (v4 && N <= 512) GD3_TSTATS(4, true);
     else if (v4 && N <= 1024) GD3_TSTATS(8, true);
     else if (v4 && N <= 2048) GD3_TSTATS(16, true);
@@ -889,7 +944,7 @@ int teacher_stage_t(const TT* t12, const TT* t21, int64_t t_pair_stride, int64_t
   GD3_CHECK_LAUNCH();
   // 128-bit (fp32) / 64-bit (fp16) teacher loads: rows aligned, and either N % 4 == 0 or rows padded so that the last
   // vector of a row stays inside it (gd3_teacher_pack pads to a multiple of 8; elements beyond N are masked at use)
-  *vec_ok = rows_aligned && (N % 4 == 0 || t_row_stride >= round_up<int64_t>(N, 4));
+  *vec_ok = rows_aligned && (N % VW == 0 || t_row_stride >= round_up<int64_t>(N, VW));
   if (!backward) {
     // forward only: the pass-1 epilogue needs W^T for the D term
     dim3 grid((unsigned)ceil_div<int64_t>(N, 64), (unsigned)ceil_div<int64_t>(N, 64), (unsigned)g);
