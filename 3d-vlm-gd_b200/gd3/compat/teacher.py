@@ -7,9 +7,16 @@ from .. import _lib
 
 
 @torch.no_grad()
-def teacher_volume(tgt_camap, src_camap, temperature=3.0, reciprocity=True):
-    """Lists of per-layer logits (B, heads, N, N) -> tgt_attn_map (B, N, N), every logit read once."""
-    return _lib.teacher_volume(tgt_camap, src_camap, temperature=temperature, reciprocity=reciprocity)
+def teacher_volume(tgt_camap, src_camap, temperature=3.0, reciprocity=True, packed=False, eps=1e-8):
+    """Lists of per-layer logits (B, heads, N, N) -> tgt_attn_map (B, N, N), every logit read once.
+
+    packed=True hands the volume over in the form ``gd3.ops.cost_volume_kl`` reads fastest: ``(fp16 volume * 1024,
+    row statistics (B, 3, N))`` (``gd3.ops.pack_teacher``: half the bytes, no statistics pass in the loss)."""
+    out = _lib.teacher_volume(tgt_camap, src_camap, temperature=temperature, reciprocity=reciprocity)
+    if packed:
+        from .. import ops
+        return ops.pack_teacher(out, eps=eps)
+    return out
 
 
 @torch.no_grad()
@@ -48,7 +55,12 @@ class VggtCostVolumes:
                                               skip=self.skip, round_bf16=self.round_bf16)
         self.blocks += 1
 
-    def result(self):
+    def result(self, packed=False, eps=1e-8):
+        """(cost_1, cost_2), each (B, n, n) fp32 -- or, with packed=True, each as the ``(fp16 volume, row statistics)``
+        pair of ``gd3.ops.pack_teacher`` for ``gd3.ops.cost_volume_kl``."""
         if self.maps is None:
             raise _lib.Gd3Error('VggtCostVolumes.result() before any add_block()')
+        if packed:
+            from .. import ops
+            return tuple(ops.pack_teacher(m, eps=eps) for m in self.maps)
         return self.maps

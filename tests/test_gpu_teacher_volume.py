@@ -45,6 +45,14 @@ def test_teacher_volume_feeds_cost_kl():
     m = torch.ones(1, N, dtype=torch.bool).cuda()
     loss = ops.cost_volume_kl(f1, f2, t12, t21, m, m, variant='mast3r')
     assert torch.isfinite(loss).all() and (loss > 0).all()
+    # the same producer handing the volume over in the packed form (fp16 * 1024 + row statistics): same loss
+    p12 = teacher.teacher_volume([t.cuda() for t in tgt], [s.cuda() for s in src], 3.0, True, packed=True)
+    p21 = teacher.teacher_volume([s.cuda() for s in src], [t.cuda() for t in tgt], 3.0, True, packed=True)
+    assert p12[0].dtype == torch.float16 and p12[1].shape == (1, 3, N)
+    assert torch.allclose(p12[0].float() / 1024.0, t12, rtol=1e-3, atol=1e-7)
+    assert torch.allclose(p12[1][:, 0], t12.sum(-1), rtol=1e-5)
+    lp = ops.cost_volume_kl(f1, f2, p12, p21, m, m, variant='mast3r')
+    assert abs(lp.item() - loss.item()) <= 1e-3 * abs(loss.item())
 
 
 def test_vggt_plain_mean_matches_oracle():
