@@ -40,9 +40,10 @@ constexpr int B_PER_WARP = 16;
 constexpr int TILE_B = WARPS * B_PER_WARP;          // 128
 constexpr int CTAS_PER_SM = 2;
 #ifndef GD3_RANK_UNROLL
-#define GD3_RANK_UNROLL 2
+#define GD3_RANK_UNROLL 4
 #endif
 constexpr int kRankUnroll = GD3_RANK_UNROLL;      // steps of the a-tile walk per loop iteration (build knob for experiments)
+constexpr int kBarrierPeriod = 4;                 // CTA barrier every this many steps of the walk (see rank_pairs)
 constexpr int SLOTS = TILE_A / 2;                    // ring of row pairs a warp walks through
 constexpr int SPACING = SLOTS / WARPS;               // ring distance between consecutive warps
 static_assert(SLOTS % WARPS == 0 && SPACING >= 2, "stagger needs at least 2 ring slots between warps");
@@ -256,24 +257,15 @@ __device__ __forceinline__ void pair_forward(const F2 (&hcv)[HP], float rstd, co
   o.m2 = m2_2.x + m2_2.y;
 }
 
-// dynamic smem: va[TILE_A][H] | dua[TILE_A][H] | da[TILE_A] | red[3*H + 1] | prog[WARPS]
+// dynamic smem: va[TILE_A][H] | dua[TILE_A][H] | da[TILE_A] | red[3*H + 1]
 //
 // Synchronisation of the shared a-side gradient tile `dua`.  Warp w walks the ring of 32 row-pair slots starting
-// SPACING (= 4) slots after warp w - 1, so at its step g it touches the slot its successor (w + 1) % WARPS touched
-// at step g - 4 and its predecessor will touch at step g + 4.  Instead of a CTA barrier every 2 steps (which also
-// aligns the phases of all warps: they then compete for the FMA pipe and idle through the MUFU / shuffle
-// latencies together), every warp publishes the number of steps it has completed (`prog`, release) and, right
-// before its read-modify-write, waits until its successor has completed step g - 4 (acquire).  The slowest warp
-// never waits (its successor is ahead), so the ring cannot deadlock; a warp may run up to 3 steps ahead of its
-// successor and arbitrarily far behind it.
-__device__ __forceinline__ int ld_acquire_cta(uint32_t saddr) {
-  int v;
-  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_cta(uint32_t saddr, int v) {
-  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
+// SPACING (= 4) slots after warp w - 1, so two warps touch the same slot only when their step counters differ by a
+// multiple of SPACING.  A CTA barrier every kBarrierPeriod = SPACING steps bounds the drift between any two warps to
+// SPACING - 1 steps, which keeps the read-modify-writes race-free; the steps between two barriers are unrolled.
+// Measured alternatives at cfg2 (tools/time_rank.py): barrier every 2 steps 2.98 ms, every 4 steps unrolled 2.90 ms, a
+// barrier-free release / acquire flag ring between neighbouring warps 3.05 ms (the flag traffic costs more than the
+// barrier it removes), no synchronisation at all (wrong results, lower bound) 2.81 ms.
 // The pair loop addresses shared memory through 32-bit shared-window addresses that are made opaque to the compiler
 // once (opaque()): derived from threadIdx they would be rematerialised inside the loop (S2R + shifts, ~25 cycles of
 // exposed latency each) whenever registers get tight.
@@ -304,7 +296,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   float* dua = va + TILE_A * H;           // accumulated d/d(u_a) (sign applied at reduction)
   float* da = dua + TILE_A * H;           // depths of the a tile (NaN outside the set: such a pair is never valid)
   float* red = da + TILE_A;                 // cross-warp reduction of parameter gradients
-  int* prog = reinterpret_cast<int*>(red + 3 * H + 4);   // steps completed per warp (ring synchronisation)
   const int set = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
   const int K = p.K;
@@ -322,7 +313,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     if (GRAD) *reinterpret_cast<float4*>(dua + r * H + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane == 0) da[r] = (a < K) ? Dp[a] : __int_as_float(0x7fc00000);
   }
-  if (threadIdx.x < WARPS) prog[threadIdx.x] = 0;
   HeadConst hc;
   float b1_mean;
   {
@@ -343,14 +333,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   constexpr uint32_t kSlotBytes = 2 * H * 4, kRingBytes = SLOTS * kSlotBytes, kDuaOff = TILE_A * H * 4;
   const uint32_t va_lane = opaque((uint32_t)__cvta_generic_to_shared(va) + (half * H + 4 * l16) * 4);
   const uint32_t da_lane = opaque((uint32_t)__cvta_generic_to_shared(da) + half * 4);
-  const uint32_t prog_mine = opaque((uint32_t)__cvta_generic_to_shared(prog + warp));
-  const uint32_t prog_succ = opaque((uint32_t)__cvta_generic_to_shared(prog + (warp + 1) % WARPS));
   const uint32_t lane_half = opaque((uint32_t)(lane & 16));
-  const bool lane0 = opaque((uint32_t)lane) == 0;
   const uint32_t soff0 = opaque((uint32_t)(SPACING * warp) * kSlotBytes);   // ring offset of this warp's first slot
   const int a_tile0 = ta * TILE_A;
-  int steps_done = 0;          // ring steps this warp has completed (== its prog entry)
-  int succ_seen = 0;           // last value read from the successor's counter (it only grows)
 
   // rstd of one b row against the 64 rows of the a tile: the 16 lanes of a half hold ring slots l16 and l16 + 16
   // (a = 2 * slot + half), i.e. two fully coalesced 128-byte loads per warp and b row
@@ -475,14 +460,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
             tq[i] = fma2(nm2, o.xh[i], mul2(hc.w2g[i], o.gp[i]));
             dub[i] = fma2(alpha2, tq[i], dub[i]);
           }
-          // ring dependency: the successor warp must have finished the step that touched this slot last.  Its counter
-          // only grows, so the last value seen is re-read only when it is not enough.
-          {
-            const int need = steps_done - (SPACING - 1);     // successor must have completed its steps 0 .. g - SPACING
-#ifndef GD3_RANK_NOSYNC_EXPERIMENT
-            while (succ_seen < need) succ_seen = ld_acquire_cta(prog_succ);
-#endif
-          }
           const float4 c0 = lds128(va_addr + kDuaOff), c1 = lds128(va_addr + kDuaOff + 256);
           const F2 s0 = fma2(alpha2, tq[0], make_float2(c0.x, c0.y)), s1 = fma2(alpha2, tq[1], make_float2(c0.z, c0.w));
           const F2 s2 = fma2(alpha2, tq[2], make_float2(c1.x, c1.y)), s3 = fma2(alpha2, tq[3], make_float2(c1.z, c1.w));
@@ -491,14 +468,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
         }
       }
       soff = soff_next;
-      if (GRAD) {
-        // publish this step (also when it was skipped: the ring position advanced)
-        ++steps_done;
-#ifndef GD3_RANK_NOSYNC_EXPERIMENT
-        __syncwarp();
-        if (lane0) st_release_cta(prog_mine, steps_done);
-#endif
-      }
+      // every warp of the CTA runs the same number of steps (the row break above is CTA-uniform), so the barrier is safe
+      static_assert(kBarrierPeriod <= SPACING && SLOTS % kBarrierPeriod == 0 && (kBarrierPeriod & (kBarrierPeriod - 1)) == 0,
+                    "barrier period");
+      if (GRAD && (t & (kBarrierPeriod - 1)) == kBarrierPeriod - 1) __syncthreads();
     }
     };
     if (row_flagged) walk_a_tile(std::true_type{});
@@ -1095,7 +1068,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.gparam = grad_params;
   rp.gparam_off = (int64_t)H * D;
   {
-    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 4) + sizeof(int) * WARPS;
+    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 4);
     dim3 grid((unsigned)w.TA, (unsigned)w.TB, (unsigned)S);
 #define GD3_RANK_LAUNCH(G, M, T)                                            \
   do {                                                                     \

@@ -2,9 +2,6 @@
 # compute-sanitizer passes over the small parity tests of every kernel family (run on a GPU box through gpurun):
 #   tools/sanitize.sh [memcheck|racecheck|synccheck|initcheck ...]      default: memcheck racecheck
 # Writes gpurun_out/sanitize_<tool>.log; the summaries kept in the repo are profiles/r2_sanitize_<tool>.txt.
-# racecheck only understands barriers: rank_pairs orders its shared gradient tile through release / acquire flags
-# between warps, so its hazard reports for that kernel's `dua` tile are expected false positives;
-# the ring protocol is exercised by tests/test_gpu_depth_rank.py against the CPU oracle instead.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
