@@ -333,8 +333,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   constexpr uint32_t kSlotBytes = 2 * H * 4, kRingBytes = SLOTS * kSlotBytes, kDuaOff = TILE_A * H * 4;
   const uint32_t va_lane = opaque((uint32_t)__cvta_generic_to_shared(va) + (half * H + 4 * l16) * 4);
   const uint32_t da_lane = opaque((uint32_t)__cvta_generic_to_shared(da) + half * 4);
-  const uint32_t lane_half = opaque((uint32_t)(lane & 16));
-  const uint32_t soff0 = opaque((uint32_t)(SPACING * warp) * kSlotBytes);   // ring offset of this warp's first slot
+  // ring position of this warp (byte offset of its current slot): starts SPACING * warp slots into the ring and comes
+  // back to the same slot after every full walk of SLOTS steps, so it simply persists from one b row to the next
+  uint32_t soff = opaque((uint32_t)(SPACING * warp) * kSlotBytes);
   const int a_tile0 = ta * TILE_A;
 
   // rstd of one b row against the 64 rows of the a tile: the 16 lanes of a half hold ring slots l16 and l16 + 16
@@ -350,6 +351,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   // b rows are dealt round-robin to the warps (row bi * WARPS + warp of the tile), so that a partial last tile
   // (K = 300: 44 of 128 rows) still keeps all 8 warps busy and the CTA stops as soon as the rows run out
   load_rstd(tb * TILE_B + warp, rs0_next, rs1_next);
+  // depth of row a = 2 * slot + half of the current slot (slot * 8 bytes into `da`); always loaded one step ahead
+  float da_cur = lds32(da_lane + (soff >> 7));
   for (int bi = 0; bi < B_PER_WARP; ++bi) {
     if (tb * TILE_B + bi * WARPS >= K) break;       // CTA-uniform: no row left for any warp
     const int b = tb * TILE_B + bi * WARPS + warp;
@@ -385,8 +388,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     // this b row) re-derives 1 / sigma from the pair itself where the flag is set.
     auto walk_a_tile = [&](auto check_tag) {
     constexpr bool CHECK = decltype(check_tag)::value;
-    uint32_t soff = soff0;                  // byte offset of the current slot inside the ring
-    float da_cur = lds32(da_lane + (soff >> 7));    // depth of row a = 2 * slot + half (slot * 8 bytes)
 #pragma unroll kRankUnroll
     for (int t = 0; t < SLOTS; ++t) {
       // staggered a index: at any step the half-warps of the CTA work on different rows
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
       const uint32_t soff_next = (soff + kSlotBytes) & (kRingBytes - 1);
       const float dd = d_b - da_cur;       // NaN when a or b lies outside the set
       da_cur = lds32(da_lane + (soff_next >> 7));     // next step's depth: its latency hides behind this step
-      float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, lane_half | (slot & 15));
+      float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, slot & 15, 16);     // within each 16-lane half
       const bool valid = (MODE == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr);
       // both halves run the same instruction stream (98 % of the pairs are valid); an invalid pair is masked out
       // of every accumulation below.  A slot is skipped only when it lies outside the set for both halves
