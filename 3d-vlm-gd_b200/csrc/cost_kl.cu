@@ -419,8 +419,10 @@ __global__ void __launch_bounds__(256)
 // reads W and z anyway and takes the term over, so this epilogue issues no global loads at all.
 template <bool WITH_D>
 struct EpiKLStats {
-  static constexpr int kScratchBytes = 0;
+  // the fp16 copy of z leaves through TMA stores (one 32 x 32 box per warp and chunk, see EpiGradOutTMA)
+  static constexpr int kScratchBytes = tc::kMaxEpiWarps * tc::kStoreSlabBytes;
   struct Params {
+    alignas(64) CUtensorMap tm_z;   // (ldz, N, g) fp16 view of the z staging buffer (valid when Z != nullptr)
     int N;
     const float* WT;   // (G, N, ldw)
     int ldw;
@@ -442,13 +444,21 @@ struct EpiKLStats {
       if (j0 >= p.N) break;                       // warp-uniform: the rest of the tile is padding
       float v[32];
       tc::tmem_ld32(cx.tmem + c, v);
-      if (p.Z && row_ok) {
-        uint4* zrow = reinterpret_cast<uint4*>(p.Z + ((int64_t)cx.b * p.N + i) * p.ldz + j0);
+      if (p.Z && cx.m0 + (cx.row & ~31) < p.N) {          // warp-uniform: some row of this warp lies inside the tensor
+        uint8_t* slab = cx.scratch + cx.epi_warp * tc::kStoreSlabBytes;
+        if (cx.lane == 0) tc::tma_store_wait_read();        // the previous box has been read out of the slab
+        __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (j0 + 8 * q < p.ldz)
-            zrow[q] = make_uint4(pack_f16x2(v[8 * q], v[8 * q + 1]), pack_f16x2(v[8 * q + 2], v[8 * q + 3]),
-                                 pack_f16x2(v[8 * q + 4], v[8 * q + 5]), pack_f16x2(v[8 * q + 6], v[8 * q + 7]));
+          *reinterpret_cast<uint4*>(slab + tc::store_slab_offset(cx.lane, q)) =
+              make_uint4(pack_f16x2(v[8 * q], v[8 * q + 1]), pack_f16x2(v[8 * q + 2], v[8 * q + 3]),
+                         pack_f16x2(v[8 * q + 4], v[8 * q + 5]), pack_f16x2(v[8 * q + 6], v[8 * q + 7]));
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (cx.lane == 0) {
+          tc::tma_store_3d(&p.tm_z, slab, j0, cx.m0 + (cx.row & ~31), cx.b);     // columns >= ldz / rows >= N are clipped
+          tc::tma_store_commit();
+        }
       }
       float e[32];
 #pragma unroll
@@ -476,6 +486,10 @@ struct EpiKLStats {
       if (j0 + cx.lane < p.N) atomicAdd(p.Lcol + (int64_t)cx.b * p.N + j0 + cx.lane, e[0]);
     }
     if (row_ok) atomicAdd(p.Lrow + (int64_t)cx.b * p.N + i, rowsum);
+    if (p.Z) {
+      if (cx.lane == 0) tc::tma_store_wait_read();
+      __syncwarp();
+    }
     if (WITH_D) {
       dsum = warp_sum(dsum);
       if (cx.lane == 0 && dsum != 0.f) loss_add(p.loss_acc, cx.b, (unsigned)i >> 5, -(0.5 / (double)p.N) * (double)dsum);
@@ -840,6 +854,92 @@ struct EpiGradOut {
   }
 };
 
+// The same epilogue for bf16 gradients with 16-byte aligned rows, leaving through TMA: a warp packs its 32 x 32 chunk
+// into a 64-byte-swizzled shared slab (4 STS.128 per thread, conflict-free) and one elected lane issues a TMA store of
+// the box; rows / columns outside the tensor are clipped by the tensor map.  Replaces the shared-memory transposition
+// + 16 two-row global stores per chunk of warp_store_rows_bf16: the gradient GEMM at cfg2 is bound by its epilogue
+// (MMA 3.3 us per tile at peak, epilogue ~8), so the store path is what its time consists of.
+struct EpiGradOutTMA {
+  static constexpr int kScratchBytes = tc::kMaxEpiWarps * tc::kStoreSlabBytes;      // 8 x 2 KB, each slab 1024-aligned
+  struct Params {
+    alignas(64) CUtensorMap tm_out;   // (C, N, g) bf16 view of this group's gradient tensor
+    int N, C;
+    const __nv_bfloat16* X;   // (G, N, ldc) normalised features of the image being differentiated
+    int ldc;
+    const float* dot;         // (G, N)
+    const float* inv;         // (G, N)
+  };
+  struct Pre {
+    uint4 x[4];
+    float dot, inv;
+  };
+  __device__ static __forceinline__ void load_x(const Params& p, const tc::EpiCtx& cx, int i, int c0, uint4 (&x)[4]) {
+    const __nv_bfloat16* xr = p.X + ((int64_t)cx.b * p.N + i) * p.ldc + c0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = __ldg(reinterpret_cast<const uint4*>(xr + 8 * q));
+  }
+  __device__ static void pre(const Params& p, const tc::EpiCtx& cx, Pre& pr) {
+    const int i = cx.m0 + cx.row;
+    pr.dot = 0.f;
+    pr.inv = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pr.x[q] = make_uint4(0, 0, 0, 0);
+    if (i < p.N) {
+      pr.dot = p.dot[(int64_t)cx.b * p.N + i];
+      pr.inv = p.inv[(int64_t)cx.b * p.N + i];
+      const int c0 = cx.n0 + cx.col_begin;
+      if (c0 + 32 <= p.C) load_x(p, cx, i, c0, pr.x);
+    }
+  }
+  __device__ static void run(const Params& p, const tc::EpiCtx& cx, const Pre& pr) {
+    uint8_t* slab = cx.scratch + cx.epi_warp * tc::kStoreSlabBytes;
+    const int i = cx.m0 + cx.row;
+    const bool row_ok = i < p.N;
+    const int m_warp = cx.m0 + (cx.row & ~31);
+    const float dot = pr.dot, inv = pr.inv;
+    const __nv_bfloat16* x = p.X + ((int64_t)cx.b * p.N + i) * p.ldc;
+    uint4 xn[4] = {pr.x[0], pr.x[1], pr.x[2], pr.x[3]};
+    for (int c = cx.col_begin; c < cx.col_end; c += 32) {
+      const int c0 = cx.n0 + c;
+      if (c0 >= p.C) break;
+      uint4 xc[4] = {xn[0], xn[1], xn[2], xn[3]};
+      const bool full = c0 + 32 <= p.C;          // (C % 8 == 0: a partial chunk still has whole 16-byte pieces)
+      if (row_ok && c + 32 < cx.col_end && c0 + 64 <= p.C) load_x(p, cx, i, c0 + 32, xn);   // next chunk
+      float v[32];
+      tc::tmem_ld32(cx.tmem + c, v);
+      if (m_warp >= p.N) continue;               // warp-uniform: the whole 32-row slab lies outside the tensor
+      if (!full) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          xc[q] = (row_ok && c0 + 8 * q < p.C) ? __ldg(reinterpret_cast<const uint4*>(x + c0 + 8 * q)) : make_uint4(0, 0, 0, 0);
+      }
+      // the previous TMA store must have finished reading the slab before it is overwritten
+      if (cx.lane == 0) tc::tma_store_wait_read();
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t xs[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float lo = (v[8 * q + 2 * h] - bf16_bits_to_float(xs[h] & 0xFFFFu) * dot) * inv;
+          const float hi = (v[8 * q + 2 * h + 1] - bf16_bits_to_float(xs[h] >> 16) * dot) * inv;
+          o[h] = pack_bf16x2(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(slab + tc::store_slab_offset(cx.lane, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (cx.lane == 0) {
+        tc::tma_store_3d(&p.tm_out, slab, c0, m_warp, cx.b);
+        tc::tma_store_commit();
+      }
+    }
+    if (cx.lane == 0) tc::tma_store_wait_read();     // the slab is free again (and stays valid until it has been read)
+    __syncwarp();
+  }
+};
+
 __global__ void kl_write_loss(const double* __restrict__ acc, float* __restrict__ loss, int G) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < G) {
@@ -1085,10 +1185,15 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
       tc::GemmShape s{(int)N, (int)N, (int)C, g};
       if (backward) {
         // the D term is taken over by kl_dz, which reads W and z anyway
-        EpiKLStats<false>::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, w.Z, w.ldn};
+        EpiKLStats<false>::Params ep{};
+        if ((rc = tc::make_tmap_store16(&ep.tm_z, w.Z, w.ldn, N, g, w.ldn, N * (int64_t)w.ldn, true))) return rc;
+        ep.N = (int)N; ep.WT = w.WT; ep.ldw = w.ldw; ep.Lrow = w.Lrow; ep.Lcol = w.Lcol; ep.loss_acc = w.loss_acc;
+        ep.Z = w.Z; ep.ldz = w.ldn;
         rc = tc::launch_gemm<256, 8, EpiKLStats<false>>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream);
       } else {
-        EpiKLStats<true>::Params ep{(int)N, w.WT, w.ldw, w.Lrow, w.Lcol, w.loss_acc, nullptr, w.ldn};
+        EpiKLStats<true>::Params ep{};
+        ep.N = (int)N; ep.WT = w.WT; ep.ldw = w.ldw; ep.Lrow = w.Lrow; ep.Lcol = w.Lcol; ep.loss_acc = w.loss_acc;
+        ep.Z = nullptr; ep.ldz = w.ldn;
         rc = tc::launch_gemm<256, 8, EpiKLStats<true>>("kl_pass1_gemm", tm_a, tm_b, s, ep, stream);
       }
       if (rc) return rc;
@@ -1144,9 +1249,36 @@ int gd3_cost_kl(const void* f1, const void* f2, int dtype, int64_t P, int64_t N,
         GD3_KL_GRAD(128);
 #undef GD3_KL_GRAD
       };
-      if (dtype == GD3_DTYPE_F32) rc = run_grad(float{});
-      else rc = run_grad(__nv_bfloat16{});
-      if (rc) return rc;
+      // bf16 gradients with 16-byte aligned rows leave through TMA stores (EpiGradOutTMA)
+      const bool tma_out = dtype == GD3_DTYPE_BF16 && C % 8 == 0 && reinterpret_cast<uintptr_t>(grad_f1) % 16 == 0 &&
+                           reinterpret_cast<uintptr_t>(grad_f2) % 16 == 0;
+      if (tma_out) {
+        using E = EpiGradOutTMA;
+        E::Params e1{}, e2{};
+        __nv_bfloat16* o1 = static_cast<__nv_bfloat16*>(grad_f1) + p0 * N * C;
+        __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(grad_f2) + p0 * N * C;
+        if ((rc = tc::make_tmap_store16(&e1.tm_out, o1, C, N, g, C, N * C, false))) return rc;
+        if ((rc = tc::make_tmap_store16(&e2.tm_out, o2, C, N, g, C, N * C, false))) return rc;
+        e1.N = e2.N = (int)N;
+        e1.C = e2.C = (int)C;
+        e1.X = w.a; e2.X = w.b;
+        e1.ldc = e2.ldc = w.ldc;
+        e1.dot = w.rowdot; e2.dot = w.coldot;
+        e1.inv = w.inv1; e2.inv = w.inv2;
+#define GD3_KL_GRAD_TMA(BN)                                                                                        \
+  do {                                                                                                             \
+    if ((rc = tc::launch_gemm<BN, 8, E, false, true>("kl_grad_gemm", tm_dz, tm_b_mn, s, e1, stream))) return rc;  \
+    if ((rc = tc::launch_gemm<BN, 8, E, true, true>("kl_grad_gemm", tm_dz_mn, tm_a_mn, s, e2, stream))) return rc; \
+  } while (0)
+        if (bn == 256) GD3_KL_GRAD_TMA(256);
+        else if (bn == 192) GD3_KL_GRAD_TMA(192);
+        else GD3_KL_GRAD_TMA(128);
+#undef GD3_KL_GRAD_TMA
+      } else {
+        if (dtype == GD3_DTYPE_F32) rc = run_grad(float{});
+        else rc = run_grad(__nv_bfloat16{});
+        if (rc) return rc;
+      }
     }
   }
   return GD3_OK;

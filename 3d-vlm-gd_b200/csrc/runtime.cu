@@ -123,6 +123,33 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t k_extent, int64_t
   return GD3_OK;
 }
 
+int make_tmap_store16(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t batch,
+                      int64_t row_stride_elems, int64_t batch_stride_elems, bool fp16) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return GD3_ERR_CUDA;
+  }
+  GD3_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA store base pointer must be 16-byte aligned");
+  GD3_REQUIRE(row_stride_elems % 8 == 0 && (batch <= 1 || batch_stride_elems % 8 == 0),
+              "TMA store strides must be multiples of 16 bytes (row stride %lld, batch stride %lld elements)",
+              (long long)row_stride_elems, (long long)batch_stride_elems);
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_elems * 2,
+                           (cuuint64_t)(batch > 1 ? batch_stride_elems : row_stride_elems * rows) * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (store map) failed with CUresult %d (cols=%lld rows=%lld batch=%lld ld=%lld)", (int)r,
+              (long long)cols, (long long)rows, (long long)batch, (long long)row_stride_elems);
+    return GD3_ERR_CUDA;
+  }
+  return GD3_OK;
+}
+
 }  // namespace tc
 }  // namespace gd3
 

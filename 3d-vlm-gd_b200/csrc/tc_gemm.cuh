@@ -93,6 +93,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// TMA store of a shared-memory box (written by the generic proxy: fence_proxy_async_smem + a warp sync come first)
+// into a 3-D tensor map; bulk-group completion.  wait_read: the shared-memory source may be overwritten again.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)
@@ -202,7 +213,7 @@ struct EpiCtx {
 template <int BN, int EPI_WARPS, class Epi, bool A_MN = false, bool B_MN = false, bool GROUPED = false>
 __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int tiles_m,
-                   int tiles_n, int batch, int k_blocks, typename Epi::Params ep, GroupedK gk) {
+                   int tiles_n, int batch, int k_blocks, const __grid_constant__ typename Epi::Params ep, GroupedK gk) {
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(!GROUPED || (A_MN && B_MN), "the grouped contraction reads both operands MN-major");
   static_assert(!B_MN || BN % 64 == 0, "MN-major B needs BN to be a multiple of 64");
@@ -372,6 +383,14 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
 // 128-byte swizzle, out-of-bounds elements read as zero (this is what pads ragged N / K).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t k_extent, int64_t rows, int64_t batch,
                    int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows);
+// Tensor map for epilogue TMA STORES of 16-bit outputs: dims (cols, rows, batch), box (32 cols = 64 bytes, 32 rows, 1),
+// 64-byte swizzle (the staging slab of a warp is [32 rows][64 B], 16-byte chunk index xor ((row >> 1) & 3)); elements
+// outside the tensor are clipped, which is what handles ragged M / N.  fp16 = true for __half outputs, else bf16.
+int make_tmap_store16(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t batch,
+                      int64_t row_stride_elems, int64_t batch_stride_elems, bool fp16);
+// byte offset of 16-byte chunk `c16` (0..3) of row `r` (0..31) inside such a slab
+__host__ __device__ constexpr int store_slab_offset(int r, int c16) { return r * 64 + ((c16 ^ ((r >> 1) & 3)) << 4); }
+constexpr int kStoreSlabBytes = 32 * 64;          // one 32 x 32 chunk of 16-bit values; slabs are 1024-byte aligned
 
 struct GemmShape {
   int M, N, K, batch;
