@@ -32,12 +32,11 @@ namespace {
 
 constexpr int H = 128;           // hidden width of fusion_layer (utils/model.py:88)
 constexpr int HPL = 8;           // hidden units per lane
-// CTA tile of the pair kernel: TILE_A rows on the shared (a) side, WARPS * B_PER_WARP rows on the register (b)
+// CTA tile of the pair kernel: TILE_A rows on the shared (a) side, WARPS * b_per_warp rows on the register (b)
 // side.  Two 8-warp CTAs per SM (independent barrier domains) hide latency better than one 16-warp CTA.
 constexpr int TILE_A = 64;
 constexpr int WARPS = 8;
-constexpr int B_PER_WARP = 16;
-constexpr int TILE_B = WARPS * B_PER_WARP;          // 128
+constexpr int B_PER_WARP_MAX = 16;                   // b rows a warp walks per CTA: 16, 8, 4 or 2, chosen per problem (rank_b_per_warp)
 constexpr int CTAS_PER_SM = 2;
 #ifndef GD3_RANK_UNROLL
 #define GD3_RANK_UNROLL 4
@@ -194,6 +193,7 @@ struct RankParams {
   const float* inv_count;  // (S)   1 / #valid pairs (joint or per set), 0 if none
   const float* w_rank;     // (S) or nullptr
   int K, S;
+  int b_per_warp;        // b rows per warp and CTA (the b tile is WARPS * b_per_warp rows)
   int mode;              // 0 logistic, 1 hinge
   int use_tanh;
   float thr, margin, ln_eps;
@@ -350,12 +350,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   float rs0_next, rs1_next;
   // b rows are dealt round-robin to the warps (row bi * WARPS + warp of the tile), so that a partial last tile
   // (K = 300: 44 of 128 rows) still keeps all 8 warps busy and the CTA stops as soon as the rows run out
-  load_rstd(tb * TILE_B + warp, rs0_next, rs1_next);
+  const int tile_b = WARPS * p.b_per_warp;
+  load_rstd(tb * tile_b + warp, rs0_next, rs1_next);
   // depth of row a = 2 * slot + half of the current slot (slot * 8 bytes into `da`); always loaded one step ahead
   float da_cur = lds32(da_lane + (soff >> 7));
-  for (int bi = 0; bi < B_PER_WARP; ++bi) {
-    if (tb * TILE_B + bi * WARPS >= K) break;       // CTA-uniform: no row left for any warp
-    const int b = tb * TILE_B + bi * WARPS + warp;
+  for (int bi = 0; bi < p.b_per_warp; ++bi) {
+    if (tb * tile_b + bi * WARPS >= K) break;       // CTA-uniform: no row left for any warp
+    const int b = tb * tile_b + bi * WARPS + warp;
     const bool b_ok = b < K;     // warp-uniform
     F2 vb[HP], dub[HP];
     float d_b = __int_as_float(0x7fc00000);     // NaN: no pair of a row outside the set is valid
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     const float rs0 = rs0_next, rs1 = rs1_next;
     // does any pair of this b row carry the "recompute directly" flag of the Gram epilogue?  (warp-uniform, rare)
     const bool row_flagged = __any_sync(0xffffffffu, rs0 < 0.f || rs1 < 0.f);
-    if (bi + 1 < B_PER_WARP) load_rstd(b + WARPS, rs0_next, rs1_next);
+    if (bi + 1 < p.b_per_warp) load_rstd(b + WARPS, rs0_next, rs1_next);
     // The walk over the a tile exists twice: the common one trusts the Gram rstd, the rare one (a flagged pair in
     // this b row) re-derives 1 / sigma from the pair itself where the flag is set.
     auto walk_a_tile = [&](auto check_tag) {
@@ -898,9 +899,29 @@ struct RankWorkspace {
   double *loss_sum, *l1_sum;
   int* count;
   size_t total;
-  int ldd, TA, TB, groups;
+  int ldd, TA, TB, groups, bpw;
   int gs;        // sets per split-K group of the d W1 contraction
 };
+
+// b rows per warp of a rank_pairs CTA.  A CTA is the unit of scheduling, two fit on an SM: the kernel takes
+// ceil(CTAs / (2 SMs)) waves of (b_per_warp + 1) row walks (the +1 stands for loading the a tile and flushing its
+// gradient), so few sets (strong scaling: 8 pairs per GPU) or a ragged K want smaller b tiles, while large problems keep
+// 16 rows per warp, which writes the fewest a-side partial tiles.  Deterministic in (S, K): the workspace depends on it.
+int rank_b_per_warp(int64_t S, int64_t K) {
+  const int64_t slots = 2 * (int64_t)num_sms();
+  const int64_t ta = ceil_div<int64_t>(K, TILE_A);
+  int best = B_PER_WARP_MAX;
+  double best_cost = 1e30;
+  for (int bpw = B_PER_WARP_MAX; bpw >= 2; bpw /= 2) {
+    const int64_t ctas = ta * ceil_div<int64_t>(K, (int64_t)WARPS * bpw) * S;
+    const double cost = (double)ceil_div<int64_t>(ctas, slots) * (bpw + 1);
+    if (cost < 0.97 * best_cost) {      // a smaller tile has to win by 3 %: it multiplies the partial-tile traffic
+      best_cost = cost;
+      best = bpw;
+    }
+  }
+  return best;
+}
 
 RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backward, bool l1) {
   RankWorkspace w{};
@@ -913,7 +934,8 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.gs = (int)ceil_div<int64_t>(S, w.groups);
   w.groups = (int)ceil_div<int64_t>(S, w.gs);
   w.TA = (int)ceil_div<int64_t>(K, TILE_A);
-  w.TB = (int)ceil_div<int64_t>(K, TILE_B);
+  w.bpw = rank_b_per_warp(S, K);
+  w.TB = (int)ceil_div<int64_t>(K, (int64_t)WARPS * w.bpw);
   w.F3 = c.take<__nv_bfloat16>(R * 3 * w.ldd);
   w.W3 = c.take<__nv_bfloat16>((int64_t)H * 3 * w.ldd);
   w.u = c.take<float>(R * H);
@@ -1058,6 +1080,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.w_rank = w_rank;
   rp.K = (int)K;
   rp.S = (int)S;
+  rp.b_per_warp = w.bpw;
   rp.mode = mode;
   rp.use_tanh = use_tanh;
   rp.thr = thr;
