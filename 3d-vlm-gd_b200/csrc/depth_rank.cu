@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
         pair_forward<GRAD>(hcv, rs, hc, o);
         // the two reductions over the 16 lanes of the pair ride in one float2: packed adds, two shuffles per level
         F2 am = make_float2(o.acc, o.m2);
+        // (a fixed-point REDUX over the 16 lanes instead of the shuffle butterfly was measured: 3.47 vs 2.91 ms)
 #pragma unroll
         for (int off = 8; off > 0; off >>= 1) {
           F2 other;
