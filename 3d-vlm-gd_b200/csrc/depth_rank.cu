@@ -1030,6 +1030,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     if ((rc = tc::make_tmap_bf16(&ta, w.F3, 3 * (int64_t)w.ldd, R, 1, 3 * (int64_t)w.ldd, 0, tc::BM))) return rc;
     if ((rc = tc::make_tmap_bf16(&tb, w.W3, 3 * (int64_t)w.ldd, H, 1, 3 * (int64_t)w.ldd, 0, 128))) return rc;
     tc::EpiStoreF32::Params ep{w.u, (int)R, H, H, 0, 1.0f, nullptr};
+    if ((rc = tc::enable_tma_store(ep, 1))) return rc;
     tc::GemmShape s{(int)R, H, 3 * w.ldd, 1};
     if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>("rank_u_gemm", ta, tb, s, ep, stream))) return rc;
   }
@@ -1156,6 +1157,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     if ((rc = tc::make_tmap_bf16(&t_du, w.du2, H, R, 1, 2 * H, 0, tc::BM))) return rc;
     if ((rc = tc::make_tmap_bf16(&t_w1, w.W3, D, H, 1, 3 * (int64_t)w.ldd, 0, 64))) return rc;
     tc::EpiStoreF32::Params e1{grad_feats, (int)R, (int)D, D, 0, 1.0f, nullptr};
+    if ((rc = tc::enable_tma_store(e1, 1))) return rc;
     tc::GemmShape s1{(int)R, (int)D, H, 1};
     if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, false, true>("rank_df_gemm", t_du, t_w1, s1, e1, stream))) return rc;
     // d W1 (H x D) = sum over sets of du_s^T f_s with the 3-term bf16 split  hi^T hi + lo^T hi + hi^T lo: a grouped

@@ -150,6 +150,33 @@ int make_tmap_store16(CUtensorMap* out, const void* base, int64_t cols, int64_t 
   return GD3_OK;
 }
 
+int make_tmap_store32(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t batch,
+                      int64_t row_stride_elems, int64_t batch_stride_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return GD3_ERR_CUDA;
+  }
+  GD3_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA store base pointer must be 16-byte aligned");
+  GD3_REQUIRE(row_stride_elems % 4 == 0 && (batch <= 1 || batch_stride_elems % 4 == 0),
+              "TMA store strides must be multiples of 16 bytes (row stride %lld, batch stride %lld fp32 elements)",
+              (long long)row_stride_elems, (long long)batch_stride_elems);
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_elems * 4,
+                           (cuuint64_t)(batch > 1 ? batch_stride_elems : row_stride_elems * rows) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32 store map) failed with CUresult %d (cols=%lld rows=%lld batch=%lld ld=%lld)",
+              (int)r, (long long)cols, (long long)rows, (long long)batch, (long long)row_stride_elems);
+    return GD3_ERR_CUDA;
+  }
+  return GD3_OK;
+}
+
 }  // namespace tc
 }  // namespace gd3
 
@@ -207,6 +234,7 @@ int gd3_debug_gemm_bf16(const void* A, const void* B, float* C, int64_t M, int64
   int rc;
   tc::EpiStoreF32::Params ep{C, (int)M, (int)N, ldc, M * ldc, 1.0f, nullptr};
   tc::GemmShape s{(int)M, (int)N, (int)K, (int)batch};
+  if (tile_n > 0 && (rc = tc::enable_tma_store(ep, (int)batch))) return rc;
   if ((rc = tc::make_tmap_bf16(&ta, A, K, M, batch, lda, M * lda, tc::BM))) return rc;
   if (tile_n < 0) {
     // 2-CTA (cta_group::2) kernel: 256 x bn tiles, each CTA loads half of the B tile

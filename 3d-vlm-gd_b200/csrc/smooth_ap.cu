@@ -415,6 +415,7 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     if ((rc = tc::make_tmap_bf16(&tb, w.B3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 128)))
       return rc;
     tc::EpiStoreF32::Params ep{w.sim, (int)K, (int)K, w.lds, K * (int64_t)w.lds, 1.0f, nullptr};
+    if ((rc = tc::enable_tma_store(ep, (int)P))) return rc;
     tc::GemmShape s{(int)K, (int)K, 3 * w.ldc, (int)P};
     if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>("ap_sim_gemm", ta, tb, s, ep, stream))) return rc;
   }
@@ -454,6 +455,7 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     tc::GemmShape s{(int)K, (int)C, (int)K, (int)P};
     tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, w.scale};
     tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, w.scale};
+    if ((rc = tc::enable_tma_store(e1, (int)P)) || (rc = tc::enable_tma_store(e2, (int)P))) return rc;
     if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, false, true>("ap_grad_gemm", t_ds, t_d2_mn, s, e1, stream))) return rc;
     if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, true, true>("ap_grad_gemm", t_ds_mn, t_d1_mn, s, e2, stream))) return rc;
   }
@@ -495,6 +497,7 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
     if ((rc = tc::make_tmap_bf16(&tb, w.B3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 128)))
       return rc;
     tc::EpiStoreF32::Params ep{w.sim, (int)K, (int)K, w.lds, K * (int64_t)w.lds, 1.0f, nullptr};
+    if ((rc = tc::enable_tma_store(ep, (int)P))) return rc;
     tc::GemmShape s{(int)K, (int)K, 3 * w.ldc, (int)P};
     if ((rc = tc::launch_gemm<128, 8, tc::EpiStoreF32>("nce_sim_gemm", ta, tb, s, ep, stream))) return rc;
   }
@@ -537,6 +540,7 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
     // every batch entry is scaled by the same 1 / n_valid (scale[0]); stride-0 read via a per-batch pointer of 1 entry
     tc::EpiStoreF32::Params e1{grad_d1, (int)K, (int)C, C, K * C, grad_scale, nullptr};
     tc::EpiStoreF32::Params e2{grad_d2, (int)K, (int)C, C, K * C, grad_scale, nullptr};
+    if ((rc = tc::enable_tma_store(e1, (int)P)) || (rc = tc::enable_tma_store(e2, (int)P))) return rc;
     e1.batch_scale = w.scale;
     e2.batch_scale = w.scale;
     e1.batch_scale_stride0 = 1;

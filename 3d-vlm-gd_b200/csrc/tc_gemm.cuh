@@ -552,8 +552,16 @@ __device__ __forceinline__ void warp_load_rows_finish(float* t, const uint32_t (
 
 // ------------------------------------------------------------------ a plain epilogue: store fp32
 // C[b][m][n] = alpha * acc   (row-major, leading dimension ldc, batch stride in elements)
+// Tensor map for TMA stores of fp32 outputs: dims (cols, rows, batch), box (32 cols = 128 bytes, 32 rows, 1), 128-byte
+// swizzle (staging slab [32 rows][128 B], 16-byte chunk index xor (row & 7)).
+int make_tmap_store32(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t batch,
+                      int64_t row_stride_elems, int64_t batch_stride_elems);
+__host__ __device__ constexpr int store_slab32_offset(int r, int c16) { return r * 128 + ((c16 ^ (r & 7)) << 4); }
+constexpr int kStoreSlab32Bytes = 32 * 128;
+
 struct EpiStoreF32 {
   static constexpr int kScratchBytes = kMaxEpiWarps * kWarpTileBytes;
+  static_assert(kWarpTileBytes >= kStoreSlab32Bytes, "the TMA slab reuses the transposition scratch");
   struct Params {
     float* C;
     int M, N;
@@ -561,14 +569,42 @@ struct EpiStoreF32 {
     float alpha;
     const float* batch_scale;   // optional per-batch factor read from device memory (nullptr = 1)
     int batch_scale_stride0 = 0;   // 1: every batch entry uses batch_scale[0]
+    int use_tma = 0;            // set by enable_tma_store(): rows are 16-byte aligned and the map below is valid
+    alignas(64) CUtensorMap tm_out = {};
   };
   struct Pre {};
   __device__ static void pre(const Params&, const EpiCtx&, Pre&) {}
   __device__ static void run(const Params& p, const EpiCtx& cx, const Pre&) {
     const float alpha = p.batch_scale ? p.alpha * __ldg(p.batch_scale + (p.batch_scale_stride0 ? 0 : cx.b)) : p.alpha;
-    float* t = reinterpret_cast<float*>(cx.scratch) + cx.epi_warp * kWarpTileFloats;
     const int m_warp = cx.m0 + (cx.row & ~31);            // first row of this warp's 32-row slab
     const int rows = p.M - m_warp;                         // valid rows in the slab (may be <= 0)
+    if (p.use_tma) {
+      // fp32 tile out through TMA: 8 conflict-free STS.128 per thread into a 128-byte-swizzled slab, one box store per chunk
+      uint8_t* slab = cx.scratch + cx.epi_warp * kStoreSlab32Bytes;
+      for (int c = cx.col_begin; c < cx.col_end; c += 32) {
+        const int n = cx.n0 + c;
+        if (n >= p.N) break;
+        float v[32];
+        tmem_ld32(cx.tmem + c, v);
+        if (rows <= 0) continue;
+        if (cx.lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(slab + store_slab32_offset(cx.lane, q)) =
+              make_float4(v[4 * q] * alpha, v[4 * q + 1] * alpha, v[4 * q + 2] * alpha, v[4 * q + 3] * alpha);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (cx.lane == 0) {
+          tma_store_3d(&p.tm_out, slab, n, m_warp, cx.b);
+          tma_store_commit();
+        }
+      }
+      if (cx.lane == 0) tma_store_wait_read();
+      __syncwarp();
+      return;
+    }
+    float* t = reinterpret_cast<float*>(cx.scratch) + cx.epi_warp * kWarpTileFloats;
     float* cslab = p.C + cx.b * p.batch_stride + static_cast<int64_t>(m_warp) * p.ldc;
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
       const int n = cx.n0 + c;
@@ -582,6 +618,18 @@ struct EpiStoreF32 {
     }
   }
 };
+
+// Switch an EpiStoreF32 output to TMA stores when its layout allows it (16-byte aligned base and strides); otherwise the
+// parameters are left as they are and the shared-memory transposition path runs.  Returns GD3_OK or an error code.
+inline int enable_tma_store(EpiStoreF32::Params& p, int batch) {
+  const bool ok = (reinterpret_cast<uintptr_t>(p.C) % 16 == 0) && p.ldc % 4 == 0 && (batch <= 1 || p.batch_stride % 4 == 0) &&
+                  p.N >= 1 && p.M >= 1;
+  if (!ok) return GD3_OK;
+  const int rc = make_tmap_store32(&p.tm_out, p.C, p.N, p.M, batch, p.ldc, batch > 1 ? p.batch_stride : p.ldc * p.M);
+  if (rc) return rc;
+  p.use_tma = 1;
+  return GD3_OK;
+}
 
 }  // namespace tc
 }  // namespace gd3
