@@ -617,6 +617,8 @@ struct EpiRstd {
     const float* nb;     // (S, K)
     const float* na;     // (S, K)
     float eps;
+    int use_tma = 0;     // K % 4 == 0 and an aligned buffer: rows leave through TMA stores (tc::EpiStoreF32 has the details)
+    alignas(64) CUtensorMap tm_out = {};
   };
   struct Pre {
     float nb;
@@ -647,7 +649,27 @@ struct EpiRstd {
         // |w| |v|): flag such pairs (negative value) and let the pair kernel sum the squares directly
         v[q] = (ss < kGramMinRatio * nsum) ? -1.f : rsqrtf(fmaf(ss, 1.f / H, p.eps));
       }
-      tc::warp_store_rows<float>(t, v, oslab + n, p.K, rows, p.K - n, cx.lane);
+      if (p.use_tma) {
+        uint8_t* slab = cx.scratch + cx.epi_warp * tc::kStoreSlab32Bytes;
+        if (cx.lane == 0) tc::tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(slab + tc::store_slab32_offset(cx.lane, q)) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (cx.lane == 0) {
+          tc::tma_store_3d(&p.tm_out, slab, n, m_warp, cx.b);
+          tc::tma_store_commit();
+        }
+      } else {
+        tc::warp_store_rows<float>(t, v, oslab + n, p.K, rows, p.K - n, cx.lane);
+      }
+    }
+    if (p.use_tma) {
+      if (cx.lane == 0) tc::tma_store_wait_read();
+      __syncwarp();
     }
   }
 };
@@ -1047,6 +1069,10 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     if ((rc = tc::make_tmap_bf16(&ta, w.Wb3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, tc::BM))) return rc;
     if ((rc = tc::make_tmap_bf16(&tb, w.Va3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, bn))) return rc;
     EpiRstd::Params ep{w.rstd, (int)K, w.nb, w.na, ln_eps};
+    if (K % 4 == 0 && reinterpret_cast<uintptr_t>(w.rstd) % 16 == 0) {
+      if ((rc = tc::make_tmap_store32(&ep.tm_out, w.rstd, K, K, S, K, K * K))) return rc;
+      ep.use_tma = 1;
+    }
     if (bn == 256) rc = tc::launch_gemm<256, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
     else if (bn == 192) rc = tc::launch_gemm<192, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
     else rc = tc::launch_gemm<128, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
