@@ -130,27 +130,42 @@ __global__ void __launch_bounds__(256)
                  int K, int variant, float inv_tau, float thr_neg, __nv_bfloat16* __restrict__ dS, int ldk,
                  double* __restrict__ loss_acc, int* __restrict__ qcount) {
   __shared__ float s_loss[8];
+  // the pair's K points of view 2, staged once per block: every row tests all of them (coalesced load here, stride-3
+  // shared reads below are conflict-free) instead of 3 K strided global loads per row
+  __shared__ float sP2[3 * 32 * NE];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int s = blockIdx.x * 8 + wid, p = blockIdx.y;
   const bool row_ok = s < K;
   float loss_row = 0.f;
+  {
+    const float* gP2 = p2 + (int64_t)p * K * 3;
+    for (int e = threadIdx.x; e < 3 * K; e += blockDim.x) sP2[e] = __ldg(gP2 + e);
+  }
+  // the row's similarities are requested before the barrier so that their latency overlaps the staging
+  float sj[NE];
+  if (row_ok) {
+    const float* srow0 = sim + ((int64_t)p * K + s) * lds;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const int j = lane + 32 * e;
+      sj[e] = (j < K) ? __ldg(srow0 + j) : 0.f;
+    }
+  }
+  __syncthreads();
   if (row_ok) {
     const float* srow = sim + ((int64_t)p * K + s) * lds;
     const float* a = p1 + ((int64_t)p * K + s) * 3;
-    const float* P2 = p2 + (int64_t)p * K * 3;
+    const float* P2 = sP2;
     const float ax = a[0], ay = a[1], az = a[2];
     const float pos = srow[s];
     float g1[NE], g2[NE];
     float S1 = 0.f, S2 = 0.f, G2 = 0.f;
-    // all loads of the row first (independent, coalesced), then the arithmetic: the negative mask lives in a bit field
-    float sj[NE];
+    // the negative mask lives in a bit field
     unsigned negmask = 0u;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const int j = lane + 32 * e;
-      sj[e] = 0.f;
       if (j < K) {
-        sj[e] = srow[j];
         const float dx = ax - P2[3 * j], dy = ay - P2[3 * j + 1], dz = az - P2[3 * j + 2];
         if ((sqrtf(dx * dx + dy * dy + dz * dz) > thr_neg) && (j != s)) negmask |= 1u << e;
       }
