@@ -23,8 +23,19 @@ DEFAULT_WEIGHTS = {
 }
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(dev, n=2):
+    """Two long-lived side streams per device for the independent loss branches of a step."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+    return _SIDE_STREAMS[key]
+
+
 def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backward=True, weights=None,
-                      pairs_per_group=0, depth_threshold=0.05, thr_neg=0.1, temp=0.01):
+                      pairs_per_group=0, depth_threshold=0.05, thr_neg=0.1, temp=0.01, parallel_branches=False):
     """Run the three distillation losses (+ L1) forward and backward for a batch of pairs.
 
     batch (all CUDA tensors):
@@ -38,6 +49,11 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
       (src/finetune_timm_mast3r.py:516-519), dep1 / dep2 = 3 x 3 window depths at the keypoints from ``depth_map1`` /
       ``depth_map2`` ((P, H, W) or one shared (H, W) map; src/finetune_timm_mast3r.py:482-483).
       head       dict W1, b1, gamma, beta, w2, b2 (+ use_tanh, ln_eps) of the depth-difference head
+    parallel_branches: the three losses are independent until the final scatter; with True the KL and Smooth-AP
+      pipelines are enqueued on two side streams while the caller's stream runs the depth-ranking pipeline (under
+      CUDA-graph capture they become parallel branches of the graph).  Off by default: measured on B200 at cfg2 it does
+      not pay (3.92 ms per step against 3.88 ms on one stream) -- the pair kernel fills every SM with CTAs that own all
+      registers, so the other kernels only interleave with it and the total SM time is conserved.
     Returns dict: kl, ap, rank, l1 (each (P,)), total (0-d) and, if backward, ``grads`` with f1, f2 (feature
     dtype), g1, g2 (fp32; h1, h2 too when given) and head (packed [W1 | b1 | gamma | beta | w2 | b2]).
     """
@@ -94,24 +110,42 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     dep2 = batch['dep2'] if 'dep2' in batch else prepared['dep2']
     depths = torch.stack([dep1.to(_F32), dep2.to(_F32)], dim=1).reshape(2 * P, K)
 
-    # ---- relative depth: ranking on both views + cross-view L1 (K4).  Issued first: its pair kernel runs for
-    #      milliseconds, during which the host enqueues the many short kernels of the other losses without gaps ----
-    w_rank = torch.full((2 * P,), 0.5 * w['intra'] * inv_p, dtype=_F32, device=dev)
-    w_l1 = torch.full((P,), w['depth'] * inv_p, dtype=_F32, device=dev)
-    lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, Ch), depths, params,
-                                              head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
-                                              depth_threshold, 0.05, False, w_rank, w_l1, backward)
-
-    # ---- dense cost-volume KL (K1) ----
     # teacher volumes: fp32, or the producers' packed form (fp16 volume t12 / t21 + row statistics ts12 / ts21)
     t12 = (batch['t12'], batch['ts12']) if 'ts12' in batch else batch['t12']
     t21 = (batch['t21'], batch['ts21']) if 'ts21' in batch else batch['t21']
-    kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, t12, t21, m1, m2, variant,
-                                   grad_scale=w['kl'] * inv_p, want_grad=backward, pairs_per_group=pairs_per_group)
+    w_rank = torch.full((2 * P,), 0.5 * w['intra'] * inv_p, dtype=_F32, device=dev)
+    w_l1 = torch.full((P,), w['depth'] * inv_p, dtype=_F32, device=dev)
+    main = torch.cuda.current_stream(dev)
+    if parallel_branches:
+        s_kl, s_ap = _side_streams(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        s_kl.wait_event(fork)
+        s_ap.wait_event(fork)
+    else:
+        s_kl = s_ap = main
 
-    # ---- Smooth-AP (K2) ----
-    ap, gd1, gd2 = ops.smooth_ap_raw(d1, d2, batch['p3d1'], batch['p3d2'], variant, temp, thr_neg,
-                                     grad_scale=w['ap'] * inv_p, want_grad=backward)
+    # ---- dense cost-volume KL (K1), side stream ----
+    with torch.cuda.stream(s_kl):
+        kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, t12, t21, m1, m2, variant, grad_scale=w['kl'] * inv_p,
+                                       want_grad=backward, pairs_per_group=pairs_per_group)
+    # ---- Smooth-AP (K2), side stream ----
+    with torch.cuda.stream(s_ap):
+        ap, gd1, gd2 = ops.smooth_ap_raw(d1, d2, batch['p3d1'], batch['p3d2'], variant, temp, thr_neg,
+                                         grad_scale=w['ap'] * inv_p, want_grad=backward)
+    # ---- relative depth: ranking on both views + cross-view L1 (K4), on the caller's stream ----
+    lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, Ch), depths, params,
+                                              head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
+                                              depth_threshold, 0.05, False, w_rank, w_l1, backward)
+    if parallel_branches:
+        for side, outs in ((s_kl, (kl, gf1, gf2)), (s_ap, (ap, gd1, gd2))):
+            join = torch.cuda.Event()
+            join.record(side)
+            main.wait_event(join)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in outs:       # produced on a side stream, consumed (and later freed) on the caller's
+                    if t is not None:
+                        t.record_stream(main)
     rank = 0.5 * (lr[0::2] + lr[1::2])
     out.update(kl=kl, ap=ap, rank=rank, l1=l1)
     out['total'] = (w['ap'] * ap + w['depth'] * l1 + w['intra'] * rank + w['kl'] * kl).mean()

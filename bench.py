@@ -242,9 +242,9 @@ def run_ours(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
     h2d_bytes32 = sum(v.numel() * v.element_size() for v in pinned32.values())
 
-    def step(batch):
+    def step(batch, parallel=False):
         return pipeline.distillation_step(batch, variant=cfg['variant'], grid=cfg['grid'], backward=True,
-                                          pairs_per_group=args.pairs_per_group)
+                                          pairs_per_group=args.pairs_per_group, parallel_branches=parallel)
 
     # ---- warm-up ----
     for _ in range(args.warmup):
@@ -255,7 +255,8 @@ def run_ours(args):
     launches0 = _lib.launch_count()
     _lib.profile_enable(True)
     _lib.profile_read()
-    eager_ms_step, clocks, out = timed_replays(lambda: step(resident), args.steps, world, local)
+    # (branches serialised here so that every kernel's event pair times that kernel alone)
+    eager_ms_step, clocks, out = timed_replays(lambda: step(resident, parallel=False), args.steps, world, local)
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     launches = _lib.launch_count() - launches0

@@ -94,6 +94,22 @@ def test_graphed_step_matches_eager():
     assert not torch.allclose(got['kl'], eager['kl'], rtol=1e-3)
 
 
+def test_parallel_branches_match_serial():
+    """The KL / Smooth-AP pipelines on side streams (parallel_branches=True) give the same step as everything on one stream."""
+    from gd3 import pipeline
+    cfg = dict(N=256, C=384, K=128, P=4, grid=(16, 16), variant='vggt')
+    batch = bench_common.to_device(bench_common.make_batch(cfg, cfg_id=1, pair0=11), 'cuda', feature_dtype=torch.bfloat16)
+    for _ in range(3):
+        a = pipeline.distillation_step(batch, variant='vggt', grid=cfg['grid'], parallel_branches=True)
+        b = pipeline.distillation_step(batch, variant='vggt', grid=cfg['grid'], parallel_branches=False)
+        torch.cuda.synchronize()
+        for k in ('kl', 'ap', 'rank', 'l1'):
+            assert torch.allclose(a[k], b[k], rtol=1e-6, atol=1e-8), k
+        for k in ('f1', 'f2', 'g1', 'head'):
+            x, y = a['grads'][k].float().flatten().double(), b['grads'][k].float().flatten().double()
+            assert float(torch.dot(x, y) / (x.norm() * y.norm())) > 1 - 1e-6, k
+
+
 def test_step_derives_masks_and_keypoint_depths():
     """Without m1 / m2 / dep1 / dep2 the step builds them from the keypoints and depth maps on the device; the result
     equals the step fed with the oracle helpers' masks (utils/functions.py:375-399) and depths (:348-372)."""
