@@ -192,3 +192,28 @@ def test_cost_kl_packed_teacher_ragged_batched(ops):
                 assert_grad_close(F2.grad[p].cpu(), want[p][2], name=f'g2[{p}]', norm_rtol=3e-2)
     with pytest.raises(ValueError):
         ops.cost_volume_kl(F1, F2, t12, st[3], st[4], st[5], variant='vggt')
+
+
+@pytest.mark.parametrize('N,C', [(130, 72), (257, 200), (64, 8), (333, 136)])
+def test_cost_kl_tma_store_partial_chunks(ops, N, C):
+    """bf16 gradients leave through TMA stores in 32-column boxes: channel counts that end inside a box (C = 72, 200, 8,
+    136), token counts that end inside a 32-row box, packed and fp32 teachers, against the CPU oracle."""
+    P = 2
+    pairs = []
+    for p in range(P):
+        f1, f2 = synth.features(5300 + p + N, N, C)
+        pairs.append((f1, f2, synth.teacher_volume(5310 + p, N, 'vggt'), synth.teacher_volume(5320 + p, N, 'vggt'),
+                      synth.patch_mask(5330 + p, N), synth.patch_mask(5340 + p, N)))
+    want = [oracle_pair(*q, 'vggt') for q in pairs]
+    st = [torch.stack([q[k] for q in pairs]).cuda() for k in range(6)]
+    for packed in (False, True):
+        F1 = st[0].to(torch.bfloat16).requires_grad_(True)
+        F2 = st[1].to(torch.bfloat16).requires_grad_(True)
+        t12, t21 = (ops.pack_teacher(st[2]), ops.pack_teacher(st[3])) if packed else (st[2], st[3])
+        loss = ops.cost_volume_kl(F1, F2, t12, t21, st[4], st[5], variant='vggt')
+        loss.sum().backward()
+        for p in range(P):
+            assert rel_err(loss[p].item(), want[p][0]) <= LOSS_RTOL, (N, C, packed, p, loss[p].item(), want[p][0])
+            assert torch.isfinite(F1.grad[p].float()).all() and torch.isfinite(F2.grad[p].float()).all()
+            assert_grad_close(F1.grad[p].float().cpu(), want[p][1], name=f'g1[{p}]', norm_rtol=3e-2)
+            assert_grad_close(F2.grad[p].float().cpu(), want[p][2], name=f'g2[{p}]', norm_rtol=3e-2)
