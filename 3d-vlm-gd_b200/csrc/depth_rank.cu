@@ -16,10 +16,11 @@
 //   loss = mean over valid pairs (0 without gradient if none)
 // L1 term: pairs keypoint k of set 2p+1 (a) with keypoint k of set 2p (b): mean_k |s - tanh(d_b - d_a)|.
 //
-// Layout of the pair kernel: 16 lanes own one pair, each lane 8 of the 128 hidden units, so LayerNorm / dot
-// reductions are 4 xor-shuffles and a warp works on two pairs at a time.  A CTA owns a 128 x 128 tile of
-// (a, b): every warp keeps the gradient of its b rows in registers and accumulates the a side into a shared
-// tile; the a index is staggered per warp so no two warps touch the same row in the same step.
+// Layout of the pair kernel (rank_pairs): a warp owns one b row and evaluates 4 pairs per step, every lane 4 of the
+// 128 hidden units of each; the per-pair sums are 32-lane shuffle reductions arranged so that one scalar chain per
+// lane serves 4 pairs, and the loop is software-pipelined (forward of step t + 1 under the chain of step t).  A CTA
+// owns a 64 x (4 b_per_warp) tile of (a, b): every warp keeps the gradient of its b row in registers and accumulates
+// the a side into a shared tile; the a index is staggered per warp so no two warps touch the same row in the same step.
 #include <type_traits>
 
 #include "../../include/gd3.h"
@@ -33,19 +34,11 @@ namespace {
 constexpr int H = 128;           // hidden width of fusion_layer (utils/model.py:88)
 constexpr int HPL = 8;           // hidden units per lane
 // CTA tile of the pair kernel: TILE_A rows on the shared (a) side, WARPS * b_per_warp rows on the register (b)
-// side.  Two 8-warp CTAs per SM (independent barrier domains) hide latency better than one 16-warp CTA.
+// side.  Two 4-warp CTAs per SM: the pipelined kernel holds two steps of forward state and wants ~224 registers.
 constexpr int TILE_A = 64;
-constexpr int WARPS = 8;
-constexpr int B_PER_WARP_MAX = 16;                   // b rows a warp walks per CTA: 16, 8, 4 or 2, chosen per problem (rank_b_per_warp)
+constexpr int WARPS = 4;
+constexpr int B_PER_WARP_MAX = 32;                   // b rows a warp walks per CTA: 32, 16, 8, 4 or 2, chosen per problem (rank_b_per_warp)
 constexpr int CTAS_PER_SM = 2;
-#ifndef GD3_RANK_UNROLL
-#define GD3_RANK_UNROLL 4
-#endif
-constexpr int kRankUnroll = GD3_RANK_UNROLL;      // steps of the a-tile walk per loop iteration (build knob for experiments)
-constexpr int kBarrierPeriod = 4;                 // CTA barrier every this many steps of the walk (see rank_pairs)
-constexpr int SLOTS = TILE_A / 2;                    // ring of row pairs a warp walks through
-constexpr int SPACING = SLOTS / WARPS;               // ring distance between consecutive warps
-static_assert(SLOTS % WARPS == 0 && SPACING >= 2, "stagger needs at least 2 ring slots between warps");
 
 // sum over the 16 lanes of a half warp (xor offsets < 16 never cross the halves)
 __device__ __forceinline__ float half_sum(float v, unsigned mask) {
@@ -204,68 +197,17 @@ struct RankParams {
   int64_t gparam_off;    // offset of b1 inside gparam (= H * D)
 };
 
-// ---- pair kernel: elementwise part of one ordered pair (a -> b), 8 hidden units per lane as 4 float2 ----------
+// ---- pair kernel: elementwise part of one ordered pair (a -> b) --------------------------------------------------
 // Differences to head_eval (kept for the L1 kernel): the Gaussian density is folded into the exponent
 // (e' = pdf-scaled exp(-y^2/2) = ex2(-ys^2 + log2 kPdf), the erf polynomial is pre-divided by kPdf, so GELU' is one
 // fma), and the LayerNorm-backward mean term m1 is not formed at all: sum_pairs alpha m1 = mean_h(sum_pairs alpha q),
 // so the accumulated gradient rows are centred once in rank_reduce_du instead of once per pair.
-// 22 packed fp32 ops per float2 forward + backward (was 26).  The pair loop is bound by issue slots as much as by the
-// FMA pipe (a packed op holds the pipe 2 cycles but takes one slot), so integer-pipe tricks that trade one packed op
-// for several LOP3 / SEL were measured in SASS and rejected.
+// 22 packed fp32 ops per float2 forward + backward.
 constexpr float kLog2Pdf = -1.0901312512086083f;          // log2(kPdf)
 constexpr float kN1 = -2.f * 0.37046028286393695f;       // -a1 / kPdf   (A&S 7.1.25: a1, a2, a3)
 constexpr float kN2 = 2.f * 0.10206088492966209f;
 constexpr float kN3 = -2.f * 0.7960676214969513f;
 
-struct PairFwd {
-  F2 xh[HP];   // normalised pre-activation
-  F2 g[HP];    // c * GELU(y)
-  F2 gp[HP];   // GELU'(y)
-  float acc;   // partial (this lane) of w2 . GELU
-  float m2;    // partial of sum_h w2 gamma GELU' xh
-};
-
-template <bool GRAD>
-__device__ __forceinline__ void pair_forward(const F2 (&hcv)[HP], float rstd, const HeadConst& hc, PairFwd& o) {
-  const F2 r2 = bc(rstd);
-  F2 acc2 = bc(0.f), m2_2 = bc(0.f);
-#pragma unroll
-  for (int i = 0; i < HP; ++i) {
-    const F2 xh = mul2(hcv[i], r2);
-    const F2 ys = fma2(xh, hc.gs[i], hc.bs[i]);                   // c * y
-    const F2 ti = fma2(bc(kErfP), make_float2(fabsf(ys.x), fabsf(ys.y)), bc(1.f));
-    // (one reciprocal per float2 via 1 / a = b / (a b) was measured: -8 MUFU, +12 FMA-pipe cycles per step, 2 % slower)
-    const F2 t = make_float2(fast_rcp(ti.x), fast_rcp(ti.y));
-    F2 np = fma2(t, bc(kN3), bc(kN2));
-    np = fma2(t, np, bc(kN1));
-    np = mul2(np, t);                                             // -(a1 t + a2 t^2 + a3 t^3) / kPdf
-    const F2 sq = fma2(ys, ys, bc(-kLog2Pdf));
-    const F2 e = make_float2(fast_ex2(-sq.x), fast_ex2(-sq.y));   // kPdf exp(-y^2 / 2)
-    const F2 ea = fma2(np, e, bc(1.f));                           // erf(|y| / sqrt 2)
-    const F2 phi = fma2(bc(0.5f), make_float2(copysignf(ea.x, ys.x), copysignf(ea.y, ys.y)), bc(0.5f));
-    const F2 g = mul2(ys, phi);                                   // c * GELU(y)
-    acc2 = fma2(hc.w2c[i], g, acc2);
-    o.xh[i] = xh;
-    o.g[i] = g;
-    if (GRAD) {
-      const F2 gp = fma2(ys, e, phi);                             // Phi(y) + y pdf(y)
-      o.gp[i] = gp;
-      m2_2 = fma2(hc.w2g[i], mul2(gp, xh), m2_2);
-    }
-  }
-  o.acc = acc2.x + acc2.y;
-  o.m2 = m2_2.x + m2_2.y;
-}
-
-// dynamic smem: va[TILE_A][H] | dua[TILE_A][H] | da[TILE_A] | red[3*H + 1]
-//
-// Synchronisation of the shared a-side gradient tile `dua`.  Warp w walks the ring of 32 row-pair slots starting
-// SPACING (= 4) slots after warp w - 1, so two warps touch the same slot only when their step counters differ by a
-// multiple of SPACING.  A CTA barrier every kBarrierPeriod = SPACING steps bounds the drift between any two warps to
-// SPACING - 1 steps, which keeps the read-modify-writes race-free; the steps between two barriers are unrolled.
-// Measured alternatives at cfg2 (tools/time_rank.py): barrier every 2 steps 2.98 ms, every 4 steps unrolled 2.90 ms, a
-// barrier-free release / acquire flag ring between neighbouring warps 3.05 ms (the flag traffic costs more than the
-// barrier it removes), no synchronisation at all (wrong results, lower bound) 2.81 ms.
 // The pair loop addresses shared memory through 32-bit shared-window addresses that are made opaque to the compiler
 // once (opaque()): derived from threadIdx they would be rematerialised inside the loop (S2R + shifts, ~25 cycles of
 // exposed latency each) whenever registers get tight.
@@ -287,214 +229,318 @@ __device__ __forceinline__ uint32_t opaque(uint32_t x) {
   return x;
 }
 
-// MODE 0 logistic / 1 hinge and the head's tanh are template parameters: the per-pair scalar chain is a third of the
-// issue slots of a step, uniform branches on kernel parameters inside it are not free.
+// ---- pair kernel: whole warp per pair, four a rows per lane and step, software-pipelined ---------------------------
+// Measured history at cfg2 (64 sets x 512 keypoints; tools/time_rank.py), all with identical results:
+//   16 lanes per pair, 8 hidden units per lane, 1 pair per lane, 16 warps x 128 registers          2.91 ms  (round 2 start)
+//   same, 2 pairs per lane and one shared scalar chain ("quad step"), 12 warps x 168 registers      2.64 ms
+//   32 lanes per pair, 4 hidden units per lane, 4 pairs per lane (this layout), 12 warps x 168      2.63 ms
+//   this layout, software-pipelined, 8 warps x 224 registers                                       2.44 ms
+// The register budget decides the layout.  Per lane, the state that lives across the scalar chain is 3 values
+// (xh, GELU, GELU') per (pair, hidden unit) = 12 x pairs-per-warp-step registers whatever the layout, while the
+// per-hidden-unit constants and accumulators (gamma, beta, w2 (x2), d gamma, d beta, d w2, v_b, d u_b: 9 values) scale
+// with the hidden units a lane owns.  So a lane owns 4 hidden units (36 persistent registers instead of 72), a pair is
+// spread over all 32 lanes, and a step covers a QUAD slot (4 rows of the a tile, one b row): 8 independent packed
+// chains per lane in the forward.  Lane l names the rows of the slot X_j = row (j ^ p), p = bits 4..3 of l, so the
+// first two levels of the 32-lane reduction are "keep X0 (X1), send X2 (X3)" and "keep X0, send X1" for every lane (no
+// selects); three butterfly levels finish all four pairs at once: 12 shuffles for 4 pairs.  Each lane then runs the
+// scalar chain (tanh, logistic / hinge, validity, loss) for ITS X0 pair only -- one chain per 4 pairs -- and fetches
+// (d out, m2) of X1..X3 from lanes l ^ 8, l ^ 16, l ^ 24.
+// Timing experiments with parts removed (results wrong, 12 warps): no barrier -2 %, no a-side read-modify-write -5 %, no
+// parameter sums (-17 % of the FMA work) -5 %, no MUFU in the forward -2 %, forward arithmetic removed altogether
+// 1.82 ms, and forward + barrier + RMW + parameter sums removed still 1.42 ms (1.22 ms with 16 warps): the skeleton --
+// operand loads, 22 shuffles, the scalar chain and the d u accumulation -- is a dependent chain of ~1200 cycles per
+// step, which is why hiding it (pipelining) pays and removing arithmetic does not.
+constexpr int HPW = 4;                               // hidden units per lane
+constexpr int NPW = HPW / 2;                         // ... as float2
+constexpr int QSLOTS = TILE_A / 4;                   // ring of quad slots
+constexpr int SPACING_W = QSLOTS / WARPS;            // ring distance between consecutive warps
+static_assert(QSLOTS % WARPS == 0 && SPACING_W >= 2, "stagger needs at least 2 quad slots between warps");
+static_assert((QSLOTS & (QSLOTS - 1)) == 0, "the ring offset wraps with a mask");
+
+struct HeadConstW {
+  F2 gs[NPW], bs[NPW], w2c[NPW], w2g[NPW];      // as HeadConst, hidden units 4 lane .. 4 lane + 3
+  float b2;
+  __device__ __forceinline__ void load(const float* gamma, const float* beta, const float* w2, const float* b2p, int lane) {
+#pragma unroll
+    for (int i = 0; i < NPW; ++i) {
+      const int h0 = 4 * lane + 2 * i, h1 = h0 + 1;
+      gs[i] = make_float2(gamma[h0] * kC, gamma[h1] * kC);
+      bs[i] = make_float2(beta[h0] * kC, beta[h1] * kC);
+      w2c[i] = make_float2(w2[h0] * (1.f / kC), w2[h1] * (1.f / kC));
+      w2g[i] = make_float2(w2[h0] * gamma[h0], w2[h1] * gamma[h1]);
+    }
+    b2 = b2p[0];
+  }
+};
+struct PairFwdW {
+  F2 xh[NPW], g[NPW], gp[NPW];
+  float acc, m2;
+};
+// pair_forward for NPW float2 per lane (same arithmetic, same constants)
+template <bool GRAD>
+__device__ __forceinline__ void pair_forward_w(const F2 (&hcv)[NPW], float rstd, const HeadConstW& hc, PairFwdW& o) {
+  const F2 r2 = bc(rstd);
+  F2 acc2 = bc(0.f), m2_2 = bc(0.f);
+#pragma unroll
+  for (int i = 0; i < NPW; ++i) {
+    const F2 xh = mul2(hcv[i], r2);
+    const F2 ys = fma2(xh, hc.gs[i], hc.bs[i]);
+    const F2 ti = fma2(bc(kErfP), make_float2(fabsf(ys.x), fabsf(ys.y)), bc(1.f));
+    // (one reciprocal per float2 via 1 / a = b / (a b) was measured: -8 MUFU, +12 FMA-pipe cycles per step, 2 % slower)
+    const F2 t = make_float2(fast_rcp(ti.x), fast_rcp(ti.y));
+    F2 np = fma2(t, bc(kN3), bc(kN2));
+    np = fma2(t, np, bc(kN1));
+    np = mul2(np, t);
+    const F2 sq = fma2(ys, ys, bc(-kLog2Pdf));
+    const F2 e = make_float2(fast_ex2(-sq.x), fast_ex2(-sq.y));   // kPdf exp(-y^2 / 2)
+    const F2 ea = fma2(np, e, bc(1.f));
+    const F2 phi = fma2(bc(0.5f), make_float2(copysignf(ea.x, ys.x), copysignf(ea.y, ys.y)), bc(0.5f));
+    const F2 g = mul2(ys, phi);
+    acc2 = fma2(hc.w2c[i], g, acc2);
+    o.xh[i] = xh;
+    o.g[i] = g;
+    if (GRAD) {
+      const F2 gp = fma2(ys, e, phi);
+      o.gp[i] = gp;
+      m2_2 = fma2(hc.w2g[i], mul2(gp, xh), m2_2);
+    }
+  }
+  o.acc = acc2.x + acc2.y;
+  o.m2 = m2_2.x + m2_2.y;
+}
+
+// ---- software pipeline: the reduction + scalar chain of slot t overlap the forward of slot t + 1 ----
+// Per step a warp has ~280 instructions of independent packed arithmetic (forward, backward) and a serial section of
+// ~55 instructions (5 shuffle levels, 4 dependent MUFU levels: ~330 cycles of latency).  With 3-4 warps per scheduler
+// the serial sections are not hidden (the unpipelined kernel: FMA pipe 56 % busy).  Here the loop body is
+//     R(t) | F(t + 1) | B(t)
+// in ONE basic block: the forward of the next quad slot has no dependence on the chain of the current one, so the
+// scheduler fills the chain's latency with it.  Two stages of forward state (2 x 54 registers) are live, so the kernel
+// runs 8 warps per SM with up to 255 registers.  Control flow inside the walk depends on blockIdx / loop counters only
+// (a b row beyond the set is clamped and made invalid through a NaN depth; a quad slot beyond the set is evaluated on
+// zero rows with NaN depths): the compiler emits no divergence checks (BRA.DIV) around the shuffles, which would split
+// the block.  Near-duplicate pairs (negative rstd from the Gram epilogue) are repaired by rank_fix_rstd beforehand.
+constexpr int kTripP = 2;      // slots per trip of rank_pairs (= its barrier period; 4 measured equal)
+static_assert(kTripP % 2 == 0 && kTripP <= SPACING_W && QSLOTS % kTripP == 0, "trip length");
+struct StageW {
+  PairFwdW o[4];
+  float rs[4];
+  float dd;
+  uint32_t ad0;
+};
+struct ScalW {
+  float d[4], al[4], nn[4];
+};
+
 template <bool GRAD, int MODE, bool TANH>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams p) {
-  extern __shared__ __align__(16) float smem[];
-  float* va = smem;                       // centred u_a rows of the a tile
-  float* dua = va + TILE_A * H;           // accumulated d/d(u_a) (sign applied at reduction)
-  float* da = dua + TILE_A * H;           // depths of the a tile (NaN outside the set: such a pair is never valid)
-  float* red = da + TILE_A;                 // cross-warp reduction of parameter gradients
+  extern __shared__ __align__(16) float smem_raw[];
+  const uint32_t s_raw = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  float* va = smem_raw + (((2048u - (s_raw & 2047u)) & 2047u) >> 2);
+  float* dua = va + TILE_A * H;
+  float* da = dua + TILE_A * H;
+  float* red = da + TILE_A;
   const int set = blockIdx.z, ta = blockIdx.x, tb = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pq = (lane >> 3) & 3;
   const int K = p.K;
   const float* U = p.u + (int64_t)set * K * H;
   const float* Dp = p.depth + (int64_t)set * K;
 
-  // ---- load and centre the a tile; it is stored NEGATED so that hc = vb + va is a plain packed add ----
   for (int r = warp; r < TILE_A; r += WARPS) {
     const int a = ta * TILE_A + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < K) v = *reinterpret_cast<const float4*>(U + (int64_t)a * H + 4 * lane);
     float m = (v.x + v.y) + (v.z + v.w);
     m = warp_sum(m) * (1.f / H);
-    *reinterpret_cast<float4*>(va + r * H + 4 * lane) = make_float4(m - v.x, m - v.y, m - v.z, m - v.w);
+    *reinterpret_cast<float4*>(va + r * H + 4 * lane) = make_float4(m - v.x, m - v.y, m - v.z, m - v.w);   // negated
     if (GRAD) *reinterpret_cast<float4*>(dua + r * H + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane == 0) da[r] = (a < K) ? Dp[a] : __int_as_float(0x7fc00000);
   }
-  HeadConst hc;
-  float b1_mean;
+  HeadConstW hc;
+  float4 b1v;
   {
-    float bsum = 0.f;
-    for (int h = lane; h < H; h += 32) bsum += p.b1[h];
-    b1_mean = warp_sum(bsum) * (1.f / H);
-    hc.load(p.gamma, p.beta, p.w2, p.b2, l16);
+    b1v = make_float4(p.b1[4 * lane], p.b1[4 * lane + 1], p.b1[4 * lane + 2], p.b1[4 * lane + 3]);
+    const float b1_mean = warp_sum((b1v.x + b1v.y) + (b1v.z + b1v.w)) * (1.f / H);
+    b1v.x -= b1_mean; b1v.y -= b1_mean; b1v.z -= b1_mean; b1v.w -= b1_mean;
+    hc.load(p.gamma, p.beta, p.w2, p.b2, lane);
   }
   const float inv_cnt = p.inv_count[set] * (p.w_rank ? p.w_rank[set] : 1.f);
   __syncthreads();
 
-  F2 dgam[HP], dbet[HP], dw2[HP];
+  F2 dgam[NPW], dbet[NPW], dw2[NPW];
   float db2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HP; ++i) dgam[i] = dbet[i] = dw2[i] = bc(0.f);
+  for (int i = 0; i < NPW; ++i) dgam[i] = dbet[i] = dw2[i] = bc(0.f);
   float loss_local = 0.f;
-  // shared-window addresses of this lane's 16-byte column of a ring slot (rows 2 * slot + half), opaque to the compiler
-  constexpr uint32_t kSlotBytes = 2 * H * 4, kRingBytes = SLOTS * kSlotBytes, kDuaOff = TILE_A * H * 4;
-  const uint32_t va_lane = opaque((uint32_t)__cvta_generic_to_shared(va) + (half * H + 4 * l16) * 4);
-  const uint32_t da_lane = opaque((uint32_t)__cvta_generic_to_shared(da) + half * 4);
-  // ring position of this warp (byte offset of its current slot): starts SPACING * warp slots into the ring and comes
-  // back to the same slot after every full walk of SLOTS steps, so it simply persists from one b row to the next
-  uint32_t soff = opaque((uint32_t)(SPACING * warp) * kSlotBytes);
+  constexpr uint32_t kRowBytes = H * 4, kQslotBytes = 4 * kRowBytes, kRingBytes = QSLOTS * kQslotBytes, kDuaOff = TILE_A * H * 4;
+  const uint32_t va_x0 = opaque((uint32_t)__cvta_generic_to_shared(va) + pq * kRowBytes + lane * 16);
+  const uint32_t da_x0 = opaque((uint32_t)__cvta_generic_to_shared(da) + pq * 4);
+  uint32_t soff = opaque((uint32_t)(SPACING_W * warp) * kQslotBytes);
   const int a_tile0 = ta * TILE_A;
 
-  // rstd of one b row against the 64 rows of the a tile: the 16 lanes of a half hold ring slots l16 and l16 + 16
-  // (a = 2 * slot + half), i.e. two fully coalesced 128-byte loads per warp and b row
-  static_assert(SLOTS == 32, "rstd registers cover 2 x 16 ring slots");
   auto load_rstd = [&](int b_, float& x0, float& x1) {
-    const float* rrow = p.rstd + ((int64_t)set * K + b_) * K + ta * TILE_A + half;
-    const int a0 = ta * TILE_A + 2 * l16 + half, a1 = a0 + 32;
-    x0 = (b_ < K && a0 < K) ? __ldg(rrow + 2 * l16) : 1.f;
-    x1 = (b_ < K && a1 < K) ? __ldg(rrow + 2 * l16 + 32) : 1.f;
+    const float* rrow = p.rstd + ((int64_t)set * K + b_) * K + a_tile0;
+    x0 = (b_ < K && a_tile0 + lane < K) ? __ldg(rrow + lane) : 1.f;
+    x1 = (b_ < K && a_tile0 + lane + 32 < K) ? __ldg(rrow + lane + 32) : 1.f;
   };
   float rs0_next, rs1_next;
-  // b rows are dealt round-robin to the warps (row bi * WARPS + warp of the tile), so that a partial last tile
-  // (K = 300: 44 of 128 rows) still keeps all 8 warps busy and the CTA stops as soon as the rows run out
   const int tile_b = WARPS * p.b_per_warp;
   load_rstd(tb * tile_b + warp, rs0_next, rs1_next);
-  // depth of row a = 2 * slot + half of the current slot (slot * 8 bytes into `da`); always loaded one step ahead
-  float da_cur = lds32(da_lane + (soff >> 7));
   for (int bi = 0; bi < p.b_per_warp; ++bi) {
-    if (tb * tile_b + bi * WARPS >= K) break;       // CTA-uniform: no row left for any warp
+    if (tb * tile_b + bi * WARPS >= K) break;       // CTA-uniform
     const int b = tb * tile_b + bi * WARPS + warp;
-    const bool b_ok = b < K;     // warp-uniform
-    F2 vb[HP], dub[HP];
-    float d_b = __int_as_float(0x7fc00000);     // NaN: no pair of a row outside the set is valid
+    const bool b_ok = b < K;
+    const int b_ld = b_ok ? b : K - 1;              // a row beyond the set: evaluated on a valid row, every pair invalid
+    F2 vb[NPW], dub[NPW];
+    float d_b;
     {
-      float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
-      if (b_ok) {
-        u0 = *reinterpret_cast<const float4*>(U + (int64_t)b * H + 4 * l16);
-        u1 = *reinterpret_cast<const float4*>(U + (int64_t)b * H + 64 + 4 * l16);
-        d_b = Dp[b];
-      }
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.b1 + 4 * l16));          // b1 (L1-resident)
-      const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.b1 + 64 + 4 * l16));
-      float m = ((u0.x + u0.y) + (u0.z + u0.w)) + ((u1.x + u1.y) + (u1.z + u1.w));
-      m = half_sum(m, 0xffffffffu) * (1.f / H);
-      const F2 nm = bc(-(m + b1_mean));      // w_b = (u_b - mean u_b) + (b1 - mean b1)
-      vb[0] = add2(add2(make_float2(u0.x, u0.y), nm), make_float2(c0.x, c0.y));
-      vb[1] = add2(add2(make_float2(u0.z, u0.w), nm), make_float2(c0.z, c0.w));
-      vb[2] = add2(add2(make_float2(u1.x, u1.y), nm), make_float2(c1.x, c1.y));
-      vb[3] = add2(add2(make_float2(u1.z, u1.w), nm), make_float2(c1.z, c1.w));
-#pragma unroll
-      for (int i = 0; i < HP; ++i) dub[i] = bc(0.f);
+      const float4 u0 = *reinterpret_cast<const float4*>(U + (int64_t)b_ld * H + 4 * lane);
+      d_b = b_ok ? Dp[b_ld] : __int_as_float(0x7fc00000);
+      const float m = warp_sum((u0.x + u0.y) + (u0.z + u0.w)) * (1.f / H);
+      vb[0] = make_float2((u0.x - m) + b1v.x, (u0.y - m) + b1v.y);
+      vb[1] = make_float2((u0.z - m) + b1v.z, (u0.w - m) + b1v.w);
+      dub[0] = dub[1] = bc(0.f);
     }
-    // 1 / sigma of this b row's pairs: taken from the registers loaded during the previous row, and the next
-    // row's values are requested now
     const float rs0 = rs0_next, rs1 = rs1_next;
-    // does any pair of this b row carry the "recompute directly" flag of the Gram epilogue?  (warp-uniform, rare)
-    const bool row_flagged = __any_sync(0xffffffffu, rs0 < 0.f || rs1 < 0.f);
     if (bi + 1 < p.b_per_warp) load_rstd(b + WARPS, rs0_next, rs1_next);
-    // The walk over the a tile exists twice: the common one trusts the Gram rstd, the rare one (a flagged pair in
-    // this b row) re-derives 1 / sigma from the pair itself where the flag is set.
-    auto walk_a_tile = [&](auto check_tag) {
-    constexpr bool CHECK = decltype(check_tag)::value;
-#pragma unroll kRankUnroll
-    for (int t = 0; t < SLOTS; ++t) {
-      // staggered a index: at any step the half-warps of the CTA work on different rows
-      const uint32_t slot = soff >> 10;
-      const uint32_t va_addr = va_lane + soff;
-      const uint32_t soff_next = (soff + kSlotBytes) & (kRingBytes - 1);
-      const float dd = d_b - da_cur;       // NaN when a or b lies outside the set
-      da_cur = lds32(da_lane + (soff_next >> 7));     // next step's depth: its latency hides behind this step
-      float rs = __shfl_sync(0xffffffffu, (slot < 16) ? rs0 : rs1, slot & 15, 16);     // within each 16-lane half
-      const bool valid = (MODE == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr);
-      // both halves run the same instruction stream (98 % of the pairs are valid); an invalid pair is masked out
-      // of every accumulation below.  A slot is skipped only when it lies outside the set for both halves
-      // (warp-uniform test on the indices, no vote on loaded data).
-      if (b_ok && a_tile0 + 2 * (int)slot < K) {
-        const float4 a0 = lds128(va_addr);
-        const float4 a1 = lds128(va_addr + 256);
-        F2 hcv[HP];
-        hcv[0] = add2(vb[0], make_float2(a0.x, a0.y));
-        hcv[1] = add2(vb[1], make_float2(a0.z, a0.w));
-        hcv[2] = add2(vb[2], make_float2(a1.x, a1.y));
-        hcv[3] = add2(vb[3], make_float2(a1.z, a1.w));
-        if (CHECK) {
-          // flagged by the Gram epilogue (near-duplicate rows): sum of squares of this pair's h_c directly
-          F2 ss2 = bc(0.f);
+
+    // F: forward of the quad slot at ring offset so
+    auto fwd = [&](StageW& st, uint32_t so) {
+      const uint32_t row0 = (so >> 9) + pq;
+      st.dd = d_b - lds32(da_x0 + (so >> 7));
+      const float rsel = (so < 32 * kRowBytes) ? rs0 : rs1;
 #pragma unroll
-          for (int i = 0; i < HP; ++i) ss2 = fma2(hcv[i], hcv[i], ss2);
-          const float ss = half_sum(ss2.x + ss2.y, 0xffffffffu);
-          if (rs < 0.f) rs = rsqrtf(fmaf(ss, 1.f / H, p.ln_eps));
-        }
-        PairFwd o;
-        pair_forward<GRAD>(hcv, rs, hc, o);
-        // the two reductions over the 16 lanes of the pair ride in one float2: packed adds, two shuffles per level
-        F2 am = make_float2(o.acc, o.m2);
-        // (a fixed-point REDUX over the 16 lanes instead of the shuffle butterfly was measured: 3.47 vs 2.91 ms)
+      for (int j = 0; j < 4; ++j) st.rs[j] = __shfl_sync(0xffffffffu, rsel, row0 ^ j);
+      st.ad0 = va_x0 + so;
 #pragma unroll
-        for (int off = 8; off > 0; off >>= 1) {
-          F2 other;
-          other.x = __shfl_xor_sync(0xffffffffu, am.x, off);
-          other.y = GRAD ? __shfl_xor_sync(0xffffffffu, am.y, off) : 0.f;
-          am = add2(am, other);
-        }
-        const float acc = am.x + hc.b2;
-        const float sc = TANH ? fast_tanh(acc) : acc;
-        // sign(dd) s without a multiply: flip the sign bit of s where dd < 0 (a valid pair has dd != 0)
-        const float ssc = __uint_as_float(__float_as_uint(sc) ^ (__float_as_uint(dd) & 0x80000000u));
-        float l, dl;      // pair loss and d l / d (sign(dd) s)
-        if (MODE == 0) {
-          const float ex = fast_ex2(ssc * -1.4426950408889634f);
-          l = __logf(1.f + ex);
-          dl = -ex * fast_rcp(1.f + ex);
-        } else {
-          const float m = p.margin - ssc;
-          l = fmaxf(m, 0.f);
-          dl = (m > 0.f) ? -1.f : 0.f;
-        }
-        // every lane of the pair adds the same value; the CTA reduction divides by 16
-        loss_local += valid ? l : 0.f;
-        if (GRAD) {
-          // d total / d (w2.g + b2); zero for a masked pair, which zeroes every contribution below
-          const float dsg = __uint_as_float(__float_as_uint(dl) ^ (__float_as_uint(dd) & 0x80000000u));   // d l / d s
-          const float dout = valid ? dsg * (TANH ? fmaf(-sc, sc, 1.f) : 1.f) * inv_cnt : 0.f;
-          db2 += dout;
-          // d h = alpha (q - m1 - m2 xh), q = w2 gamma GELU'; the m1 part is the centring done by rank_reduce_du
-          const F2 dout2 = bc(dout), alpha2 = bc(dout * rs), nm2 = bc(am.y * (-1.f / H));
-          F2 tq[HP];
-#pragma unroll
-          for (int i = 0; i < HP; ++i) {
-            // parameter sums are kept unscaled: d w2 = dw2 / c, d beta = w2 * dbet, d gamma = w2 * dgam
-            dw2[i] = fma2(dout2, o.g[i], dw2[i]);
-            dbet[i] = fma2(dout2, o.gp[i], dbet[i]);
-            dgam[i] = fma2(dout2, mul2(o.gp[i], o.xh[i]), dgam[i]);
-            tq[i] = fma2(nm2, o.xh[i], mul2(hc.w2g[i], o.gp[i]));
-            dub[i] = fma2(alpha2, tq[i], dub[i]);
-          }
-          const float4 c0 = lds128(va_addr + kDuaOff), c1 = lds128(va_addr + kDuaOff + 256);
-          const F2 s0 = fma2(alpha2, tq[0], make_float2(c0.x, c0.y)), s1 = fma2(alpha2, tq[1], make_float2(c0.z, c0.w));
-          const F2 s2 = fma2(alpha2, tq[2], make_float2(c1.x, c1.y)), s3 = fma2(alpha2, tq[3], make_float2(c1.z, c1.w));
-          sts128(va_addr + kDuaOff, make_float4(s0.x, s0.y, s1.x, s1.y));
-          sts128(va_addr + kDuaOff + 256, make_float4(s2.x, s2.y, s3.x, s3.y));
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float4 x = lds128(st.ad0 ^ (j * kRowBytes));
+        F2 h[NPW];
+        h[0] = add2(vb[0], make_float2(x.x, x.y));
+        h[1] = add2(vb[1], make_float2(x.z, x.w));
+        pair_forward_w<GRAD>(h, st.rs[j], hc, st.o[j]);
       }
-      soff = soff_next;
-      // every warp of the CTA runs the same number of steps (the row break above is CTA-uniform), so the barrier is safe
-      static_assert(kBarrierPeriod <= SPACING && SLOTS % kBarrierPeriod == 0 && (kBarrierPeriod & (kBarrierPeriod - 1)) == 0,
-                    "barrier period");
-      if (GRAD && (t & (kBarrierPeriod - 1)) == kBarrierPeriod - 1) __syncthreads();
-    }
     };
-    if (row_flagged) walk_a_tile(std::true_type{});
-    else walk_a_tile(std::false_type{});
-    if (GRAD) {
-      // combine the two half warps and store this b row's partial (over the a tile) gradient
+    // R: 32-lane sums, scalar chain of this lane's X0 pair, exchange of (d out, m2)
+    auto chain = [&](const StageW& st, ScalW& sc_) {
+      F2 am0 = make_float2(st.o[0].acc, st.o[0].m2), am1 = make_float2(st.o[1].acc, st.o[1].m2);
+      {
+        F2 r0, r1;
+        r0.x = __shfl_xor_sync(0xffffffffu, st.o[2].acc, 16);
+        r1.x = __shfl_xor_sync(0xffffffffu, st.o[3].acc, 16);
+        r0.y = GRAD ? __shfl_xor_sync(0xffffffffu, st.o[2].m2, 16) : 0.f;
+        r1.y = GRAD ? __shfl_xor_sync(0xffffffffu, st.o[3].m2, 16) : 0.f;
+        am0 = add2(am0, r0);
+        am1 = add2(am1, r1);
+        r0.x = __shfl_xor_sync(0xffffffffu, am1.x, 8);
+        r0.y = GRAD ? __shfl_xor_sync(0xffffffffu, am1.y, 8) : 0.f;
+        am0 = add2(am0, r0);
+      }
 #pragma unroll
-      for (int i = 0; i < HP; ++i) {
-        dub[i].x += __shfl_xor_sync(0xffffffffu, dub[i].x, 16);
-        dub[i].y += __shfl_xor_sync(0xffffffffu, dub[i].y, 16);
+      for (int off = 4; off > 0; off >>= 1) {
+        F2 other;
+        other.x = __shfl_xor_sync(0xffffffffu, am0.x, off);
+        other.y = GRAD ? __shfl_xor_sync(0xffffffffu, am0.y, off) : 0.f;
+        am0 = add2(am0, other);
       }
-      if (b_ok && half == 0) {
-        float* dst = p.dub_part + (((int64_t)set * gridDim.x + ta) * K + b) * H;
-        *reinterpret_cast<float4*>(dst + 4 * l16) = make_float4(dub[0].x, dub[0].y, dub[1].x, dub[1].y);
-        *reinterpret_cast<float4*>(dst + 64 + 4 * l16) = make_float4(dub[2].x, dub[2].y, dub[3].x, dub[3].y);
+      const float dd = st.dd;
+      const bool valid = (MODE == 0) ? (fabsf(dd) > p.thr) : (fabsf(tanhf(dd)) > p.thr);
+      const float acc = am0.x + hc.b2;
+      const float sc = TANH ? fast_tanh(acc) : acc;
+      const float ssc = __uint_as_float(__float_as_uint(sc) ^ (__float_as_uint(dd) & 0x80000000u));
+      float l, dl;
+      if (MODE == 0) {
+        const float ex = fast_ex2(ssc * -1.4426950408889634f);
+        l = __logf(1.f + ex);
+        dl = -ex * fast_rcp(1.f + ex);
+      } else {
+        const float m = p.margin - ssc;
+        l = fmaxf(m, 0.f);
+        dl = (m > 0.f) ? -1.f : 0.f;
       }
+      loss_local += valid ? l : 0.f;
+      if (GRAD) {
+        const float dsg = __uint_as_float(__float_as_uint(dl) ^ (__float_as_uint(dd) & 0x80000000u));
+        const float dout0 = valid ? dsg * (TANH ? fmaf(-sc, sc, 1.f) : 1.f) * inv_cnt : 0.f;
+        db2 += dout0;
+        sc_.d[0] = dout0;
+        sc_.al[0] = dout0 * st.rs[0];
+        sc_.nn[0] = am0.y * (-1.f / H);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+          const float dj = __shfl_xor_sync(0xffffffffu, dout0, 8 * j);
+          const float mj = __shfl_xor_sync(0xffffffffu, am0.y, 8 * j);
+          sc_.d[j] = dj;
+          sc_.al[j] = dj * st.rs[j];
+          sc_.nn[j] = mj * (-1.f / H);
+        }
+      }
+    };
+    // B: parameter sums, d u_b, read-modify-write of the a-side rows
+    auto bwd = [&](const StageW& st, const ScalW& sc_) {
+      F2 tq[4][NPW];
+#pragma unroll
+      for (int i = 0; i < NPW; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const F2 dj = bc(sc_.d[j]);
+          dw2[i] = fma2(dj, st.o[j].g[i], dw2[i]);
+          dbet[i] = fma2(dj, st.o[j].gp[i], dbet[i]);
+          dgam[i] = fma2(dj, mul2(st.o[j].gp[i], st.o[j].xh[i]), dgam[i]);
+          tq[j][i] = fma2(bc(sc_.nn[j]), st.o[j].xh[i], mul2(hc.w2g[i], st.o[j].gp[i]));
+          dub[i] = fma2(bc(sc_.al[j]), tq[j][i], dub[i]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t ad = (st.ad0 ^ (j * kRowBytes)) + kDuaOff;
+        const float4 c = lds128(ad);
+        const F2 s0 = fma2(bc(sc_.al[j]), tq[j][0], make_float2(c.x, c.y));
+        const F2 s1 = fma2(bc(sc_.al[j]), tq[j][1], make_float2(c.z, c.w));
+        sts128(ad, make_float4(s0.x, s0.y, s1.x, s1.y));
+      }
+    };
+
+    // One trip = kTripP slots between two CTA barriers (kTripP <= ring spacing of the warps).  Inside a trip nothing
+    // separates the stages, so the chain of slot t + 1 (which needs the forward of t + 1 only) also overlaps the
+    // backward of slot t.  The last trip of a row has no next slot to forward: it is a second copy of the body.
+    StageW sA, sB;
+    fwd(sA, soff);
+    soff = (soff + kQslotBytes) & (kRingBytes - 1);
+    auto trip = [&](auto last_tag) {
+      constexpr bool LAST = decltype(last_tag)::value;
+#pragma unroll
+      for (int k = 0; k < kTripP; k += 2) {
+        {
+          ScalW sc_;
+          chain(sA, sc_);
+          fwd(sB, soff);
+          soff = (soff + kQslotBytes) & (kRingBytes - 1);
+          if (GRAD) bwd(sA, sc_);
+        }
+        {
+          ScalW sc_;
+          chain(sB, sc_);
+          if (!(LAST && k + 2 == kTripP)) {
+            fwd(sA, soff);
+            soff = (soff + kQslotBytes) & (kRingBytes - 1);
+          }
+          if (GRAD) bwd(sB, sc_);
+        }
+      }
+      if (GRAD) __syncthreads();
+    };
+#pragma unroll 1
+    for (int tt = 0; tt < QSLOTS / kTripP - 1; ++tt) trip(std::false_type{});
+    trip(std::true_type{});
+    if (GRAD && b_ok) {
+      float* dst = p.dub_part + (((int64_t)set * gridDim.x + ta) * K + b) * H;
+      *reinterpret_cast<float4*>(dst + 4 * lane) = make_float4(dub[0].x, dub[0].y, dub[1].x, dub[1].y);
     }
   }
   // ---- CTA-level reductions ----
-  loss_local = warp_sum(loss_local) * (1.f / 16.f);      // all 16 lanes of a pair carried its loss
+  loss_local = warp_sum(loss_local) * (1.f / 8.f);
   if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_sum + set, (double)loss_local);
   if (GRAD) {
     __syncthreads();
@@ -505,25 +551,19 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) red[e] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < HPL; ++j) {
+    for (int j = 0; j < HPW; ++j) {
       const int i = j >> 1;
       const bool hi = j & 1;
       const float w2h = (hi ? hc.w2c[i].y : hc.w2c[i].x) * kC;
-      const float vg = hi ? dgam[i].y : dgam[i].x, vb_ = hi ? dbet[i].y : dbet[i].x, vw = hi ? dw2[i].y : dw2[i].x;
-      const float g2 = (vg + __shfl_xor_sync(0xffffffffu, vg, 16)) * w2h;
-      const float b2v = (vb_ + __shfl_xor_sync(0xffffffffu, vb_, 16)) * w2h;
-      const float w2v = (vw + __shfl_xor_sync(0xffffffffu, vw, 16)) * (1.f / kC);
-      if (half == 0) {
-        const int h = hidx(l16, j);
-        atomicAdd(red + h, g2);
-        atomicAdd(red + H + h, b2v);
-        atomicAdd(red + 2 * H + h, w2v);
-      }
+      const int h = 4 * lane + j;
+      atomicAdd(red + h, (hi ? dgam[i].y : dgam[i].x) * w2h);
+      atomicAdd(red + H + h, (hi ? dbet[i].y : dbet[i].x) * w2h);
+      atomicAdd(red + 2 * H + h, (hi ? dw2[i].y : dw2[i].x) * (1.f / kC));
     }
-    db2 = warp_sum(db2) * (1.f / 16.f);
+    db2 = warp_sum(db2) * (1.f / 8.f);
     if (lane == 0) atomicAdd(red + 3 * H, db2);
     __syncthreads();
-    float* gp = p.gparam + p.gparam_off;   // [b1 | gamma | beta | w2 | b2]
+    float* gp = p.gparam + p.gparam_off;
     for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x)
       if (red[e] != 0.f) atomicAdd(gp + H + e, red[e]);
   }
@@ -617,6 +657,7 @@ struct EpiRstd {
     const float* nb;     // (S, K)
     const float* na;     // (S, K)
     float eps;
+    int* rowflag;        // (S, K): set to 1 for a b row that holds a flagged pair (rank_fix_rstd repairs those rows)
     int use_tma = 0;     // K % 4 == 0 and an aligned buffer: rows leave through TMA stores (tc::EpiStoreF32 has the details)
     alignas(64) CUtensorMap tm_out = {};
   };
@@ -633,6 +674,7 @@ struct EpiRstd {
     const int rows = p.K - m_warp;
     float* oslab = p.out + ((int64_t)cx.b * p.K + m_warp) * p.K;
     const float* na = p.na + (int64_t)cx.b * p.K;
+    bool flagged = false;
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
       const int n = cx.n0 + c;
       if (n >= p.K) break;
@@ -647,7 +689,10 @@ struct EpiRstd {
         const float ss = fmaxf(fmaf(-2.f, v[q], nsum), 0.f);
         // the difference of nearly identical rows cancels in |w|^2 + |v|^2 - 2 w.v (split-bf16 products carry ~2^-16 of
         // |w| |v|): flag such pairs (negative value) and let the pair kernel sum the squares directly
-        v[q] = (ss < kGramMinRatio * nsum) ? -1.f : rsqrtf(fmaf(ss, 1.f / H, p.eps));
+        // the diagonal (a == b: h_c = centred b1 only) always cancels and is never a valid pair (D = 0): not flagged
+        const bool bad = ss < kGramMinRatio * nsum && (n + q != cx.m0 + cx.row);
+        flagged |= bad && (n + q < p.K);
+        v[q] = bad ? -1.f : rsqrtf(fmaf(ss, 1.f / H, p.eps));
       }
       if (p.use_tma) {
         uint8_t* slab = cx.scratch + cx.epi_warp * tc::kStoreSlab32Bytes;
@@ -671,8 +716,44 @@ struct EpiRstd {
       if (cx.lane == 0) tc::tma_store_wait_read();
       __syncwarp();
     }
+    if (flagged && cx.m0 + cx.row < p.K) p.rowflag[(int64_t)cx.b * p.K + cx.m0 + cx.row] = 1;
   }
 };
+
+// Repairs the pairs the Gram epilogue flagged (rstd < 0: near-duplicate rows, where |w|^2 + |v|^2 - 2 w.v cancels): the
+// sum of squares of h_c = w_b - v_a is taken directly from the fp32 rows.  One warp per b row; rows without a flag
+// return at once, so the kernel costs a launch when nothing is flagged (the usual case).  This keeps every branch out
+// of the pair loop of rank_pairs.
+__global__ void __launch_bounds__(256) rank_fix_rstd(const float* __restrict__ u, const float* __restrict__ b1,
+                                                     const int* __restrict__ rowflag, int64_t R, int K, float eps,
+                                                     float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R || !rowflag[r]) return;      // warp-uniform
+  const int64_t set = r / K;
+  float4 w = *reinterpret_cast<const float4*>(u + r * H + 4 * lane);
+  {
+    const float4 bv = make_float4(b1[4 * lane], b1[4 * lane + 1], b1[4 * lane + 2], b1[4 * lane + 3]);
+    const float m = warp_sum((w.x + w.y) + (w.z + w.w)) * (1.f / H);
+    const float bm = warp_sum((bv.x + bv.y) + (bv.z + bv.w)) * (1.f / H);
+    w = make_float4((w.x - m) + (bv.x - bm), (w.y - m) + (bv.y - bm), (w.z - m) + (bv.z - bm), (w.w - m) + (bv.w - bm));
+  }
+  float* row = rstd + r * K;
+  for (int a0 = 0; a0 < K; a0 += 32) {
+    float v = (a0 + lane < K) ? row[a0 + lane] : 1.f;
+    unsigned mask = __ballot_sync(0xffffffffu, v < 0.f);
+    if (!mask) continue;
+    for (unsigned mk = mask; mk; mk &= mk - 1) {
+      const int bit = __ffs(mk) - 1;
+      const float4 ua = *reinterpret_cast<const float4*>(u + (set * K + a0 + bit) * H + 4 * lane);
+      const float ma = warp_sum((ua.x + ua.y) + (ua.z + ua.w)) * (1.f / H);
+      const float hx = w.x - (ua.x - ma), hy = w.y - (ua.y - ma), hz = w.z - (ua.z - ma), hw = w.w - (ua.w - ma);
+      const float ss = warp_sum(fmaf(hx, hx, fmaf(hy, hy, fmaf(hz, hz, hw * hw))));
+      if (lane == bit) v = rsqrtf(fmaf(ss, 1.f / H, eps));
+    }
+    if ((mask >> lane) & 1u) row[a0 + lane] = v;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // number of valid pairs per set -> inv_count (per set, or shared when joint_mean)
@@ -921,6 +1002,7 @@ struct RankWorkspace {
   float *u, *inv_count, *dub_part, *dua_part, *du_extra, *nb, *na, *rstd, *mu;
   double *loss_sum, *l1_sum;
   int* count;
+  int* rowflag;
   size_t total;
   int ldd, TA, TB, groups, bpw;
   int gs;        // sets per split-K group of the d W1 contraction
@@ -931,7 +1013,7 @@ struct RankWorkspace {
 // gradient), so few sets (strong scaling: 8 pairs per GPU) or a ragged K want smaller b tiles, while large problems keep
 // 16 rows per warp, which writes the fewest a-side partial tiles.  Deterministic in (S, K): the workspace depends on it.
 int rank_b_per_warp(int64_t S, int64_t K) {
-  const int64_t slots = 2 * (int64_t)num_sms();
+  const int64_t slots = CTAS_PER_SM * (int64_t)num_sms();
   const int64_t ta = ceil_div<int64_t>(K, TILE_A);
   int best = B_PER_WARP_MAX;
   double best_cost = 1e30;
@@ -969,6 +1051,7 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.na = c.take<float>(R);
   w.rstd = c.take<float>(R * K);
   w.count = c.take<int>(S);
+  w.rowflag = c.take<int>(R);
   w.inv_count = c.take<float>(S);
   w.loss_sum = c.take<double>(S);
   w.l1_sum = c.take<double>(S);
@@ -1007,6 +1090,7 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   GD3_REQUIRE(hidden == H, "gd3_depth_head_loss: hidden width %lld not supported (fusion_layer uses %d)",
               (long long)hidden, H);
   GD3_REQUIRE(mode == 0 || mode == 1, "gd3_depth_head_loss: mode must be 0 (logistic) or 1 (hinge)");
+  GD3_REQUIRE(thr >= 0.f, "gd3_depth_head_loss: thr must be >= 0 (a pair of equal depths is never valid)");
   GD3_REQUIRE(loss_rank, "gd3_depth_head_loss: null loss output");
   GD3_REQUIRE((grad_feats == nullptr) == (grad_params == nullptr),
               "gd3_depth_head_loss: pass both gradient buffers or neither");
@@ -1068,7 +1152,8 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     CUtensorMap ta, tb;
     if ((rc = tc::make_tmap_bf16(&ta, w.Wb3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, tc::BM))) return rc;
     if ((rc = tc::make_tmap_bf16(&tb, w.Va3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, bn))) return rc;
-    EpiRstd::Params ep{w.rstd, (int)K, w.nb, w.na, ln_eps};
+    GD3_CHECK_CUDA(cudaMemsetAsync(w.rowflag, 0, sizeof(int) * R, stream));
+    EpiRstd::Params ep{w.rstd, (int)K, w.nb, w.na, ln_eps, w.rowflag};
     if (K % 4 == 0 && reinterpret_cast<uintptr_t>(w.rstd) % 16 == 0) {
       if ((rc = tc::make_tmap_store32(&ep.tm_out, w.rstd, K, K, S, K, K * K))) return rc;
       ep.use_tma = 1;
@@ -1077,6 +1162,11 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     else if (bn == 192) rc = tc::launch_gemm<192, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
     else rc = tc::launch_gemm<128, 8, EpiRstd>("rank_rstd_gemm", ta, tb, s, ep, stream);
     if (rc) return rc;
+    {
+      GD3_PROF("rank_fix_rstd", stream);
+      rank_fix_rstd<<<(unsigned)ceil_div<int64_t>(R, 8), 256, 0, stream>>>(w.u, b1, w.rowflag, R, (int)K, ln_eps, w.rstd);
+    }
+    GD3_CHECK_LAUNCH();
   }
   // ---- valid-pair counts ----
   GD3_CHECK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * S, stream));
@@ -1120,14 +1210,14 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.gparam = grad_params;
   rp.gparam_off = (int64_t)H * D;
   {
-    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 4);
+    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 4) + 2048;      // + alignment slack of rank_pairs_w
     dim3 grid((unsigned)w.TA, (unsigned)w.TB, (unsigned)S);
 #define GD3_RANK_LAUNCH(G, M, T)                                            \
   do {                                                                     \
     static SmemOptIn opt;                                                  \
-    GD3_CHECK_CUDA(opt.ensure(rank_pairs<G, M, T>, smem));                 \
+    GD3_CHECK_CUDA(opt.ensure(rank_pairs<G, M, T>, smem));            \
     GD3_PROF("rank_pairs", stream);                                        \
-    rank_pairs<G, M, T><<<grid, WARPS * 32, smem, stream>>>(rp);           \
+    rank_pairs<G, M, T><<<grid, WARPS * 32, smem, stream>>>(rp);      \
   } while (0)
 #define GD3_RANK_LAUNCH_T(G, M)                 \
   do {                                          \

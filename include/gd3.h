@@ -180,7 +180,7 @@ int gd3_infonce(const float* d1, const float* d2, const uint8_t* valid, int64_t 
  * (src/finetune_timm_mast3r.py:489-494).
  *   feats   (S, K, D) fp32 contiguous keypoint features;  depths (S, K) fp32
  *   head    W1 (hidden, D), b1, gamma, beta, w2 (hidden), b2 (1), hidden = 128; use_tanh; ln_eps
- *   thr     depth threshold (0.05 in the callers);  margin: hinge base margin (mode 1)
+ *   thr     depth threshold, >= 0 (0.05 in the callers; a pair of equal depths is never valid);  margin: hinge base margin (mode 1)
  *   joint_mean != 0: one mean over the valid pairs of all sets (the reference's B > 1 semantics)
  *   w_rank  (S) weights with which each set's loss enters the differentiated total (NULL = 1)
  *   w_l1    (S/2) weights of the L1 term coupling set 2p (view 1) with set 2p+1 (view 2); NULL = no L1
