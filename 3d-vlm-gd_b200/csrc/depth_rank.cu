@@ -21,6 +21,7 @@
 // lane serves 4 pairs, and the loop is software-pipelined (forward of step t + 1 under the chain of step t).  A CTA
 // owns a 64 x (4 b_per_warp) tile of (a, b): every warp keeps the gradient of its b row in registers and accumulates
 // the a side into a shared tile; the a index is staggered per warp so no two warps touch the same row in the same step.
+#include <algorithm>
 #include <type_traits>
 
 #include "../../include/gd3.h"
@@ -191,8 +192,7 @@ struct RankParams {
   int use_tanh;
   float thr, margin, ln_eps;
   double* loss_sum;      // (S) sum of pair losses (unnormalised)
-  float* dub_part;       // (S, TA, K, H) partial gradient of u on the b side, per a tile
-  float* dua_part;       // (S, TB, K, H) partial (positive) gradient flowing to -u_a, per b tile
+  float* du;             // (S, K, H), zero on entry: d u_b rows and -(d u_a) tiles are added with vector reductions
   float* gparam;         // packed parameter gradients: [W1 (H*D) | b1 | gamma | beta | w2 | b2]
   int64_t gparam_off;    // offset of b1 inside gparam (= H * D)
 };
@@ -535,8 +535,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
     for (int tt = 0; tt < QSLOTS / kTripP - 1; ++tt) trip(std::false_type{});
     trip(std::true_type{});
     if (GRAD && b_ok) {
-      float* dst = p.dub_part + (((int64_t)set * gridDim.x + ta) * K + b) * H;
-      *reinterpret_cast<float4*>(dst + 4 * lane) = make_float4(dub[0].x, dub[0].y, dub[1].x, dub[1].y);
+      // this b row's gradient over the a tile goes straight into du (red.global.add.v4.f32: one 512-byte row per warp)
+      atomicAdd(reinterpret_cast<float4*>(p.du + ((int64_t)set * K + b) * H + 4 * lane),
+                make_float4(dub[0].x, dub[0].y, dub[1].x, dub[1].y));
     }
   }
   // ---- CTA-level reductions ----
@@ -544,11 +545,30 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
   if (lane == 0 && loss_local != 0.f) atomicAdd(p.loss_sum + set, (double)loss_local);
   if (GRAD) {
     __syncthreads();
-    for (int e = threadIdx.x; e < TILE_A * H; e += blockDim.x) {
-      const int r = e / H, a = ta * TILE_A + r;
-      if (a < K) p.dua_part[(((int64_t)set * gridDim.y + tb) * K + a) * H + (e - r * H)] = dua[e];
+    // the a tile's accumulated gradient flows to -u_a
+    for (int e = threadIdx.x; e < TILE_A * (H / 4); e += blockDim.x) {
+      const int r = e / (H / 4), a = ta * TILE_A + r;
+      if (a < K) {
+        const float4 v = *reinterpret_cast<const float4*>(dua + 4 * e);
+        atomicAdd(reinterpret_cast<float4*>(p.du + ((int64_t)set * K + a) * H + 4 * (e - r * (H / 4))),
+                  make_float4(-v.x, -v.y, -v.z, -v.w));
+      }
     }
-    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) red[e] = 0.f;
+    // red: [b1 | gamma | beta | w2 | b2], the layout of the parameter gradient behind W1.
+    // d b1 = sum over pairs of the centred d h = column sums of the a tile (the same pairs as the b rows), centred over
+    // h: sum_pairs alpha m1 is the h-mean of the accumulated rows (rank_reduce_du), and centring is linear
+    static_assert(WARPS * 32 == H, "one thread per hidden unit for the b1 column sums");
+    {
+      float c = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < TILE_A; ++r) c += dua[r * H + threadIdx.x];
+      const float cm = warp_sum(c);
+      if (lane == 0) red[4 * H + 1 + warp] = cm;
+      __syncthreads();
+      const float mean = ((red[4 * H + 1] + red[4 * H + 2]) + (red[4 * H + 3] + red[4 * H + 4])) * (1.f / H);
+      red[threadIdx.x] = c - mean;
+    }
+    for (int e = H + threadIdx.x; e < 4 * H + 1; e += blockDim.x) red[e] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < HPW; ++j) {
@@ -556,16 +576,16 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
       const bool hi = j & 1;
       const float w2h = (hi ? hc.w2c[i].y : hc.w2c[i].x) * kC;
       const int h = 4 * lane + j;
-      atomicAdd(red + h, (hi ? dgam[i].y : dgam[i].x) * w2h);
-      atomicAdd(red + H + h, (hi ? dbet[i].y : dbet[i].x) * w2h);
-      atomicAdd(red + 2 * H + h, (hi ? dw2[i].y : dw2[i].x) * (1.f / kC));
+      atomicAdd(red + H + h, (hi ? dgam[i].y : dgam[i].x) * w2h);
+      atomicAdd(red + 2 * H + h, (hi ? dbet[i].y : dbet[i].x) * w2h);
+      atomicAdd(red + 3 * H + h, (hi ? dw2[i].y : dw2[i].x) * (1.f / kC));
     }
     db2 = warp_sum(db2) * (1.f / 8.f);
-    if (lane == 0) atomicAdd(red + 3 * H, db2);
+    if (lane == 0) atomicAdd(red + 4 * H, db2);
     __syncthreads();
     float* gp = p.gparam + p.gparam_off;
-    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x)
-      if (red[e] != 0.f) atomicAdd(gp + H + e, red[e]);
+    for (int e = threadIdx.x; e < 4 * H + 1; e += blockDim.x)
+      if (red[e] != 0.f) atomicAdd(gp + e, red[e]);
   }
 }
 
@@ -603,6 +623,44 @@ __global__ void __launch_bounds__(1024) rank_group_mean(const float* __restrict_
 #pragma unroll
     for (int k = 0; k < 16; ++k) t += part[k][cl];
     mu[(int64_t)g * D + c] = t / (float)rows;
+  }
+}
+
+// the same for D % 4 == 0 and 16-byte aligned rows: a thread owns 4 channels (one 128-bit load per row) and keeps 4 row
+// loads in flight -- 37 -> ~20 us at cfg2 (100 MB).  grid (groups, ceil(D / 64)), block 256 = 16 row slices x 16 quads
+__global__ void __launch_bounds__(256) rank_group_mean_v4(const float* __restrict__ f, int rows, int D, float* __restrict__ mu) {
+  __shared__ float4 part[16][16];
+  const int g = blockIdx.x, ql = threadIdx.x & 15, c = blockIdx.y * 64 + 4 * ql, slice = threadIdx.x >> 4;
+  float4 s[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < D) {
+    const float* col = f + (int64_t)g * rows * D + c;
+    int r = slice;
+    for (; r + 48 < rows; r += 64) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(col + (int64_t)(r + 16 * i) * D));
+        s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+      }
+    }
+    for (; r < rows; r += 16) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(col + (int64_t)r * D));
+      s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+    }
+  }
+  part[slice][ql] = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
+                                (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
+  __syncthreads();
+  if (slice == 0 && c < D) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 v = part[k][ql];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    const float inv = 1.f / (float)rows;
+    *reinterpret_cast<float4*>(mu + (int64_t)g * D + c) = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
   }
 }
 
@@ -657,7 +715,7 @@ struct EpiRstd {
     const float* nb;     // (S, K)
     const float* na;     // (S, K)
     float eps;
-    int* rowflag;        // (S, K): set to 1 for a b row that holds a flagged pair (rank_fix_rstd repairs those rows)
+    int* rowflag;        // (S, K), zero on entry: number of flagged pairs of every b row (rank_fix_rstd repairs those rows)
     int use_tma = 0;     // K % 4 == 0 and an aligned buffer: rows leave through TMA stores (tc::EpiStoreF32 has the details)
     alignas(64) CUtensorMap tm_out = {};
   };
@@ -674,7 +732,7 @@ struct EpiRstd {
     const int rows = p.K - m_warp;
     float* oslab = p.out + ((int64_t)cx.b * p.K + m_warp) * p.K;
     const float* na = p.na + (int64_t)cx.b * p.K;
-    bool flagged = false;
+    int nbad = 0;      // flagged pairs of this thread's row (a column past K reads as zero and is never flagged)
     for (int c = cx.col_begin; c < cx.col_end; c += 32) {
       const int n = cx.n0 + c;
       if (n >= p.K) break;
@@ -689,9 +747,8 @@ struct EpiRstd {
         const float ss = fmaxf(fmaf(-2.f, v[q], nsum), 0.f);
         // the difference of nearly identical rows cancels in |w|^2 + |v|^2 - 2 w.v (split-bf16 products carry ~2^-16 of
         // |w| |v|): flag such pairs (negative value) and let the pair kernel sum the squares directly
-        // the diagonal (a == b: h_c = centred b1 only) always cancels and is never a valid pair (D = 0): not flagged
-        const bool bad = ss < kGramMinRatio * nsum && (n + q != cx.m0 + cx.row);
-        flagged |= bad && (n + q < p.K);
+        const bool bad = ss < kGramMinRatio * nsum;
+        nbad += bad ? 1 : 0;
         v[q] = bad ? -1.f : rsqrtf(fmaf(ss, 1.f / H, p.eps));
       }
       if (p.use_tma) {
@@ -716,21 +773,27 @@ struct EpiRstd {
       if (cx.lane == 0) tc::tma_store_wait_read();
       __syncwarp();
     }
-    if (flagged && cx.m0 + cx.row < p.K) p.rowflag[(int64_t)cx.b * p.K + cx.m0 + cx.row] = 1;
+    if (nbad && cx.m0 + cx.row < p.K) atomicAdd(p.rowflag + (int64_t)cx.b * p.K + cx.m0 + cx.row, nbad);
   }
 };
 
 // Repairs the pairs the Gram epilogue flagged (rstd < 0: near-duplicate rows, where |w|^2 + |v|^2 - 2 w.v cancels): the
-// sum of squares of h_c = w_b - v_a is taken directly from the fp32 rows.  One warp per b row; rows without a flag
-// return at once, so the kernel costs a launch when nothing is flagged (the usual case).  This keeps every branch out
-// of the pair loop of rank_pairs.
+// sum of squares of h_c = w_b - v_a is taken directly from the fp32 rows.  One warp per b row.  The diagonal pair
+// (a == b: h_c is the centred b1 alone) is flagged in nearly every row but never valid (D = 0; rank_pairs multiplies its
+// rstd by a zero weight), so a row whose only flag is its diagonal returns at once: the kernel costs a launch and one
+// pass over the row flags when nothing else is flagged (the usual case).  This keeps every branch out of the pair loop.
 __global__ void __launch_bounds__(256) rank_fix_rstd(const float* __restrict__ u, const float* __restrict__ b1,
                                                      const int* __restrict__ rowflag, int64_t R, int K, float eps,
                                                      float* __restrict__ rstd) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= R || !rowflag[r]) return;      // warp-uniform
+  if (r >= R) return;
   const int64_t set = r / K;
+  {
+    const int nflag = rowflag[r];
+    if (nflag == 0) return;      // warp-uniform
+    if (nflag == 1 && rstd[r * K + (r - set * K)] < 0.f) return;      // only the diagonal
+  }
   float4 w = *reinterpret_cast<const float4*>(u + r * H + 4 * lane);
   {
     const float4 bv = make_float4(b1[4 * lane], b1[4 * lane + 1], b1[4 * lane + 2], b1[4 * lane + 3]);
@@ -801,7 +864,6 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
   __shared__ float red[3 * H + 1];
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
-  const int k = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + half;
   const int K = p.K;
   const int sb = 2 * pair, sa = 2 * pair + 1;
   HeadConst hc;
@@ -809,6 +871,10 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
   float dgam[HPL], dbet[HPL], dw2[HPL], db2 = 0.f, loss_local = 0.f;
 #pragma unroll
   for (int i = 0; i < HPL; ++i) dgam[i] = dbet[i] = dw2[i] = 0.f;
+  // a CTA walks keypoints blockIdx.x * 16 + [0, 16), + 16 gridDim.x, ...: few CTAs per pair keep the number of global
+  // parameter-gradient atomics (385 per CTA, all CTAs on the same addresses) small
+  for (int k0 = blockIdx.x * 16; k0 < K; k0 += 16 * gridDim.x) {      // CTA-uniform bounds: both halves of a warp stay together
+  const int k = k0 + (threadIdx.x >> 5) * 2 + half;
   const bool ok = k < K;
   float hs[HPL];
   float m = 0.f;
@@ -827,11 +893,11 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
   if (ok) {
     const float tgt = tanhf(p.depth[(int64_t)sb * K + k] - p.depth[(int64_t)sa * K + k]);
     const float diff = o.s - tgt;
-    if (l16 == 0) loss_local = fabsf(diff);
+    if (l16 == 0) loss_local += fabsf(diff);
     if (GRAD) {
       const float sg = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
       const float dout = sg * (p.use_tanh ? (1.f - o.s * o.s) : 1.f) * w_l1[pair] / (float)K;
-      db2 = (l16 == 0) ? dout : 0.f;
+      db2 += (l16 == 0) ? dout : 0.f;
       const float coef = dout * o.rstd;
 #pragma unroll
       for (int j = 0; j < HPL; ++j) {
@@ -841,14 +907,15 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
         const float gp = hi ? o.gp[i].y : o.gp[i].x, gg = hi ? o.g[i].y : o.g[i].x, xh = hi ? o.xh[i].y : o.xh[i].x;
         const float w2h = (hi ? hc.w2c[i].y : hc.w2c[i].x) * kC, w2g = hi ? hc.w2g[i].y : hc.w2g[i].x;
         const float pg = w2h * gp;
-        dw2[j] = dout * gg * (1.f / kC);
-        dbet[j] = dout * pg;
-        dgam[j] = dout * pg * xh;
+        dw2[j] += dout * gg * (1.f / kC);
+        dbet[j] += dout * pg;
+        dgam[j] += dout * pg * xh;
         const float dh = coef * (w2g * gp - o.m1 - xh * o.m2);
         du_extra[((int64_t)sb * K + k) * H + h] = dh;
         du_extra[((int64_t)sa * K + k) * H + h] = -dh;
       }
     }
+  }
   }
   loss_local = warp_sum(loss_local);
   if (lane == 0 && loss_local != 0.f) atomicAdd(l1_sum + pair, (double)loss_local);
@@ -872,12 +939,12 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// du = sum_ta dub_part - sum_tb dua_part (+ L1 part); emits the bf16 hi / lo panels of du and the b1 gradient
+// du = accumulated pair gradient (rank_pairs) + L1 part, every row centred over h; emits the bf16 hi / lo panels of du
+// and the L1 term's share of the b1 gradient (the pair term's share comes from rank_pairs itself).
 // grid (ceil(K/32), S), block 256 (8 warps x 32 lanes: lane -> 4 h, warp -> rows)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    rank_reduce_du(const float* __restrict__ dub_part, const float* __restrict__ dua_part,
-                   const float* __restrict__ du_extra, int S, int K, int TA, int TB,
+    rank_reduce_du(const float* __restrict__ du, const float* __restrict__ du_extra, int S, int K,
                    __nv_bfloat16* __restrict__ du2 /* (S K, 2 H): [hi | lo] */, float* __restrict__ gb1) {
   __shared__ float colsum[8][H];
   const int set = blockIdx.y, k0 = blockIdx.x * 32;
@@ -885,30 +952,12 @@ __global__ void __launch_bounds__(256)
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int r = w; r < 32; r += 8) {
     const int k = k0 + r;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < K) {
       // rank_pairs accumulates alpha (q - m2 xh) per pair; the LayerNorm-backward term -alpha m1 = -alpha mean_h(q)
       // summed over pairs is the mean over h of the accumulated row (mean_h(xh) = 0), removed here once per row
-#pragma unroll 4
-      for (int t = 0; t < TA; ++t) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dub_part + (((int64_t)set * TA + t) * K + k) * H + 4 * lane));
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      {
-        const float mb = warp_sum((acc.x + acc.y) + (acc.z + acc.w)) * (1.f / H);
-        acc.x -= mb; acc.y -= mb; acc.z -= mb; acc.w -= mb;
-      }
-      bsum[0] += acc.x; bsum[1] += acc.y; bsum[2] += acc.z; bsum[3] += acc.w;   // d b1 = sum over pairs of dh
-      float4 aa = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int t = 0; t < TB; ++t) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(dua_part + (((int64_t)set * TB + t) * K + k) * H + 4 * lane));
-        aa.x += v.x; aa.y += v.y; aa.z += v.z; aa.w += v.w;
-      }
-      {
-        const float ma = warp_sum((aa.x + aa.y) + (aa.z + aa.w)) * (1.f / H);
-        acc.x -= aa.x - ma; acc.y -= aa.y - ma; acc.z -= aa.z - ma; acc.w -= aa.w - ma;
-      }
+      float4 acc = __ldg(reinterpret_cast<const float4*>(du + ((int64_t)set * K + k) * H + 4 * lane));
+      const float mb = warp_sum((acc.x + acc.y) + (acc.z + acc.w)) * (1.f / H);
+      acc.x -= mb; acc.y -= mb; acc.z -= mb; acc.w -= mb;
       if (du_extra) {
         const float4 v = *reinterpret_cast<const float4*>(du_extra + ((int64_t)set * K + k) * H + 4 * lane);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -925,6 +974,7 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<uint2*>(row + H) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
     }
   }
+  if (!du_extra) return;      // CTA-uniform
 #pragma unroll
   for (int i = 0; i < 4; ++i) colsum[w][4 * lane + i] = bsum[i];
   __syncthreads();
@@ -999,7 +1049,7 @@ __global__ void rank_finalize(const double* __restrict__ loss_sum, const float* 
 struct RankWorkspace {
   __nv_bfloat16 *F3, *W3, *du2;
   __nv_bfloat16 *Wb3, *Va3;
-  float *u, *inv_count, *dub_part, *dua_part, *du_extra, *nb, *na, *rstd, *mu;
+  float *u, *inv_count, *du, *du_extra, *nb, *na, *rstd, *mu;
   double *loss_sum, *l1_sum;
   int* count;
   int* rowflag;
@@ -1057,8 +1107,7 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.l1_sum = c.take<double>(S);
   if (backward) {
     w.du2 = c.take<__nv_bfloat16>(R * 2 * H);
-    w.dub_part = c.take<float>(S * w.TA * K * H);
-    w.dua_part = c.take<float>(S * w.TB * K * H);
+    w.du = c.take<float>(R * H);
     if (l1) w.du_extra = c.take<float>(R * H);
   }
   w.total = c.total();
@@ -1124,7 +1173,10 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     {
       dim3 grid((unsigned)(R / group_rows), (unsigned)ceil_div<int64_t>(D, 64));
       GD3_PROF("rank_group_mean", stream);
-      rank_group_mean<<<grid, 1024, 0, stream>>>(feats, group_rows, (int)D, w.mu);
+      if (D % 4 == 0 && reinterpret_cast<uintptr_t>(feats) % 16 == 0 && reinterpret_cast<uintptr_t>(w.mu) % 16 == 0)
+        rank_group_mean_v4<<<grid, 256, 0, stream>>>(feats, group_rows, (int)D, w.mu);
+      else
+        rank_group_mean<<<grid, 1024, 0, stream>>>(feats, group_rows, (int)D, w.mu);
     }
     GD3_CHECK_LAUNCH();
     if ((rc = launch_split3("split3_feats", feats, R, (int)D, w.ldd, 2, w.F3, stream, w.mu, group_rows)))
@@ -1205,12 +1257,12 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.margin = margin;
   rp.ln_eps = ln_eps;
   rp.loss_sum = w.loss_sum;
-  rp.dub_part = w.dub_part;
-  rp.dua_part = w.dua_part;
+  rp.du = w.du;
+  if (backward) GD3_CHECK_CUDA(cudaMemsetAsync(w.du, 0, sizeof(float) * R * H, stream));
   rp.gparam = grad_params;
   rp.gparam_off = (int64_t)H * D;
   {
-    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 3 * H + 4) + 2048;      // + alignment slack of rank_pairs_w
+    const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 4 * H + 8) + 2048;      // + alignment slack of rank_pairs_w
     dim3 grid((unsigned)w.TA, (unsigned)w.TB, (unsigned)S);
 #define GD3_RANK_LAUNCH(G, M, T)                                            \
   do {                                                                     \
@@ -1237,7 +1289,10 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   }
   if (l1) {
     if (backward) GD3_CHECK_CUDA(cudaMemsetAsync(w.du_extra, 0, sizeof(float) * R * H, stream));
-    dim3 grid((unsigned)ceil_div<int64_t>(K, 16), (unsigned)(S / 2));
+    // about one wave of CTAs (2 per SM): a CTA walks several blocks of 16 keypoints
+    const int64_t gx_max = ceil_div<int64_t>(2 * (int64_t)num_sms(), S / 2);
+    const int64_t gx = std::min<int64_t>(ceil_div<int64_t>(K, 16), std::max<int64_t>(gx_max, 1));
+    dim3 grid((unsigned)gx, (unsigned)(S / 2));
     if (backward)
       {
         GD3_PROF("rank_l1", stream);
@@ -1262,8 +1317,8 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     dim3 grid((unsigned)ceil_div<int64_t>(K, 32), (unsigned)S);
     {
       GD3_PROF("rank_reduce_du", stream);
-      rank_reduce_du<<<grid, 256, 0, stream>>>(w.dub_part, w.dua_part, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.TA,
-                                             w.TB, w.du2, grad_params + (int64_t)H * D);
+      rank_reduce_du<<<grid, 256, 0, stream>>>(w.du, l1 ? w.du_extra : nullptr, (int)S, (int)K, w.du2,
+                                             grad_params + (int64_t)H * D);
     }
     GD3_CHECK_LAUNCH();
   }

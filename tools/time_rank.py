@@ -49,7 +49,7 @@ prof = _lib.profile_read()
 _lib.profile_enable(False)
 tot = sum(ms for _, ms in prof.values())
 print(f'[{a.tag}] S={S} K={K} D={D}: pipeline {tot / a.iters * 1e3:.1f} us; ' +
-      ', '.join(f'{k} {ms / a.iters * 1e3:.1f}' for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:6]))
+      ', '.join(f'{k} {ms / a.iters * 1e3:.1f}' for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:16]))
 lr, l1, gf, gp = out
 sig = dict(loss=float(lr.double().mean()), l1=float(l1.double().mean()), gf=float(gf.double().norm()), gp=float(gp.double().norm()))
-print('  ', sig)
+print("  ", sig, flush=True)
