@@ -123,6 +123,36 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t k_extent, int64_t
   return GD3_OK;
 }
 
+// the same view with 32-element (64-byte) boxes and the 64-byte swizzle: half-size pipeline stages for kernels whose
+// shared memory only fits two 64-element stages (ap_fused_kernel)
+int make_tmap_bf16_k32(CUtensorMap* out, const void* base, int64_t k_extent, int64_t rows, int64_t batch,
+                       int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return GD3_ERR_CUDA;
+  }
+  GD3_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  GD3_REQUIRE(row_stride_elems % 8 == 0 && (batch <= 1 || batch_stride_elems % 8 == 0),
+              "TMA strides must be multiples of 16 bytes (row stride %lld, batch stride %lld elements)",
+              (long long)row_stride_elems, (long long)batch_stride_elems);
+  GD3_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+  cuuint64_t dims[3] = {(cuuint64_t)k_extent, (cuuint64_t)rows, (cuuint64_t)(batch < 1 ? 1 : batch)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_elems * 2,
+                           (cuuint64_t)(batch > 1 ? batch_stride_elems : row_stride_elems * rows) * 2};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (k32) failed with CUresult %d (k=%lld rows=%lld batch=%lld ld=%lld)", (int)r,
+              (long long)k_extent, (long long)rows, (long long)batch, (long long)row_stride_elems);
+    return GD3_ERR_CUDA;
+  }
+  return GD3_OK;
+}
+
 int make_tmap_store16(CUtensorMap* out, const void* base, int64_t cols, int64_t rows, int64_t batch,
                       int64_t row_stride_elems, int64_t batch_stride_elems, bool fp16) {
   EncodeTiledFn fn = get_encode_fn();

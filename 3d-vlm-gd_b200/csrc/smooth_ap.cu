@@ -20,6 +20,8 @@
 //   3 ap_rows          SIMT  one block per row: S1, S2, loss, d loss / d sim (bf16, unnormalised)
 //   4 tc_gemm<Store> x2      d d1 = dsim d2 / Q,  d d2 = dsim^T d1 / Q   (Q = number of positives); dsim and the
 //                            descriptors are read in place through MN-major operand descriptors (no transposes)
+#include <cstdlib>
+
 #include "../../include/gd3.h"
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -27,6 +29,12 @@
 
 namespace gd3 {
 namespace {
+
+// build-independent A/B switch for timing and parity runs (GD3_AP_UNFUSED=1 selects the unfused Smooth-AP pipeline)
+bool getenv_flag(const char* name) {
+  const char* v = std::getenv(name);
+  return v && v[0] && v[0] != '0';
+}
 
 // ------------------------------------------------------------------------------------------
 // 3. per-row statistics and d loss / d sim.  grid (K, P), block 128, dynamic smem K floats
@@ -121,6 +129,20 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// The warp-per-row kernel's sigmoid: the temperature and log2(e) are folded into one factor (k = log2(e) / tau), the clamp
+// acts on the exponent, and the derivative is s (1 - s) / tau without the range test of sig_both: where the reference's
+// clamp is active (|u / tau| > 50) s (1 - s) / tau < 2e-20, which no fp32 sum of the loss can see.
+__device__ __forceinline__ SigT sig_fast(float u, float k, float inv_tau) {
+  const float ec = fminf(fmaxf(-u * k, -50.f * 1.4426950408889634f), 50.f * 1.4426950408889634f);
+  float ex, s;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(ec));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.f + ex));
+  SigT r;
+  r.s = s;
+  r.ds = s * (1.f - s) * inv_tau;
+  return r;
+}
+
 // One warp per row for the single-positive variants (mast3r / vggt: the positive of row s is column s) and
 // K <= 32 * NE: the row, its negative mask and both sigmoid derivatives stay in registers, one pass over the row,
 // shuffle reductions only, one loss atomic per block of 8 rows.  Same formulas as ap_rows.
@@ -160,19 +182,22 @@ __global__ void __launch_bounds__(256)
     const float pos = srow[s];
     float g1[NE], g2[NE];
     float S1 = 0.f, S2 = 0.f, G2 = 0.f;
-    // the negative mask lives in a bit field
+    // the negative mask lives in a bit field.  dist > thr  <=>  dist^2 > thr^2 for thr >= 0 (a negative threshold makes
+    // every pair a negative: thr2 = -1), which saves the square root
+    const float thr2 = thr_neg >= 0.f ? thr_neg * thr_neg : -1.f;
+    const float kexp = inv_tau * 1.4426950408889634f;
     unsigned negmask = 0u;
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       const int j = lane + 32 * e;
       if (j < K) {
         const float dx = ax - P2[3 * j], dy = ay - P2[3 * j + 1], dz = az - P2[3 * j + 2];
-        if ((sqrtf(dx * dx + dy * dy + dz * dz) > thr_neg) && (j != s)) negmask |= 1u << e;
+        if ((fmaf(dx, dx, fmaf(dy, dy, dz * dz)) > thr2) && (j != s)) negmask |= 1u << e;
       }
     }
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-      const SigT q1 = sig_both(sj[e] - 1.f, inv_tau), q2 = sig_both(sj[e] - pos, inv_tau);
+      const SigT q1 = sig_fast(sj[e] - 1.f, kexp, inv_tau), q2 = sig_fast(sj[e] - pos, kexp, inv_tau);
       const bool neg = (negmask >> e) & 1u;
       S1 += neg ? q1.s : 0.f;
       S2 += neg ? q2.s : 0.f;
@@ -214,6 +239,332 @@ __global__ void __launch_bounds__(256)
     atomicAdd(qcount + p, n);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Fused similarity GEMM + row statistics + d loss / d sim for the single-positive variants and K <= 512.
+// One CTA per (pair, 128-row tile): the 128 x K similarity tile lives in ALL 512 TMEM columns (two N <= 256 UMMAs per
+// k step), so a CTA owns whole rows and the K x K similarity never goes to memory.
+//   warp 0    TMA producer (A: 128 x 64 box of the [hi|hi|lo] panels, B: 512 x 64 of [hi|lo|hi]; 2 stages of 80 KB).  The
+//             m-tiles of a pair form a thread-block CLUSTER and share the B tile: CTA r loads rows [128 r, 128 r + 128)
+//             of it and multicasts them into the same shared-memory slot of every CTA of the cluster, so the L2 -> SM
+//             traffic per CTA is A + one B slice instead of A + the whole B (369 -> 147 MB for the batch at cfg2).  A slot
+//             is refilled when the MMAs of ALL CTAs have released it (multicast tcgen05.commit onto every CTA's empty
+//             barrier).  Measured at cfg2: the multicast alone changed nothing (66 vs 68 us), 4 stages of 32 k elements
+//             instead of 2 of 64 gave 68 -> 64 us; of those ~33 us are the MMAs (38.6 GFLOP with the 3-term split on the
+//             128 busy SMs, the practical tensor rate) and ~27 us launch, set-up, sweep 1 (MUFU-bound at 8 us) and sweep 2.
+//   warp 1    MMA issuer, TMEM owner
+//   warps 2-9 epilogue, two warps per TMEM lane quadrant taking alternate 32-column chunks of their 32 rows:
+//     sweep 1  sigmoids of every element (4 MUFU each: the sweep is MUFU-bound), partial S1 / S2 / G2 in registers, and the
+//              two sigmoids written BACK into the accumulator's columns as packed halves (tcgen05.st), zero where the
+//              element is not a negative
+//     exchange of the partial sums of the two warps of a row through shared memory; row scalars (c1, c2, d pos, loss)
+//     sweep 2  d sim = (c1 s1 (1 - s1) + c2 s2 (1 - s2)) / (2 tau) from the stored halves (no MUFU), bf16, out through
+//              TMA stores -- the gradient only sees the fp16 rounding of s (the loss and G2 use the fp32 values)
+// Replaces ap_sim_gemm + ap_rows: 64 us instead of 57 + 39 us at cfg2.
+// ------------------------------------------------------------------------------------------
+namespace apf {
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (tc::PRODUCER_WARPS + EPI_WARPS) * 32;
+// 32 k elements per stage (64-byte rows, 64-byte swizzle): 4 stages of 40 KB.  With 64-element stages only two fit next
+// to the 512-row B tile and the loop ran at the TMA round-trip time per stage (1.14 us per 80 KB, 41 us for the GEMM part
+// with or without the multicast).
+constexpr int BKF = 32;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = tc::BM * BKF * 2;               // 8 KB
+constexpr int B_SLICE_BYTES = 128 * BKF * 2;            // 8 KB: the rows of B one CTA of the cluster delivers
+constexpr int B_HALF_BYTES = 256 * BKF * 2;             // 16 KB
+constexpr int STAGE_BYTES = A_BYTES + 2 * B_HALF_BYTES; // 40 KB
+constexpr int KMAX = 512;
+constexpr int OFF_SLABS = STAGES * STAGE_BYTES;
+constexpr int OFF_P2 = OFF_SLABS + EPI_WARPS * tc::kStoreSlabBytes;      // KMAX x float4
+constexpr int OFF_POS = OFF_P2 + KMAX * 16;                              // 128 floats
+constexpr int OFF_PART = OFF_POS + 128 * 4;                              // [2][128] float4
+constexpr int OFF_MASK = OFF_PART + 2 * 128 * 16;                        // [KMAX / 32][128] uint32 negative masks
+constexpr int OFF_BARS = OFF_MASK + (KMAX / 32) * 128 * 4;
+constexpr int SMEM_BYTES = 1024 + OFF_BARS + 128;
+
+struct Params {
+  alignas(64) CUtensorMap tm_ds;     // (K, K, P) bf16 view of d sim (valid when want_grad)
+  const float* p1;                   // (P, K, 3)
+  const float* p2;
+  int K, variant, want_grad, k_blocks;
+  float inv_tau, thr2;
+  double* loss_acc;                  // (P)
+  int* qcount;                       // (P): every row has one positive
+};
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) of every CTA in mask
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                               int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "h"(mask)
+      : "memory");
+}
+// arrives on `bar` of every CTA in mask once this CTA's MMAs issued so far have retired
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(tc::smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+    ap_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ Params p) {
+  extern __shared__ uint8_t apf_smem_raw[];
+  uint8_t* smem = apf_smem_raw + ((1024u - (tc::smem_u32(apf_smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = smem;
+  uint8_t* slabs = smem + OFF_SLABS;
+  float4* p2s = reinterpret_cast<float4*>(smem + OFF_P2);
+  float* pos_s = reinterpret_cast<float*>(smem + OFF_POS);
+  float4* part = reinterpret_cast<float4*>(smem + OFF_PART);
+  uint32_t* nmask_s = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;   // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, m0 = blockIdx.x * tc::BM;
+  const int K = p.K;
+  // UMMA N of the two column halves (multiples of 16)
+  const int kp = (K + 15) & ~15;
+  const int n_lo = kp < 256 ? kp : 256, n_hi = kp - n_lo;
+  // the cluster = the m-tiles of this pair (gridDim.x = cluster size <= 4, so blockIdx.x is the rank)
+  const uint32_t csize = gridDim.x, crank = cluster_ctarank();
+  const uint16_t cmask = static_cast<uint16_t>((1u << csize) - 1u);
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    if (p.want_grad) tc::prefetch_tmap(&p.tm_ds);
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(&full_bar[s], 1);
+      tc::mbar_init(&empty_bar[s], csize);      // one multicast commit per CTA of the cluster
+    }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // the barriers of every CTA are initialised before any remote copy / arrive
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      // this CTA receives its own A box and one B slice from every CTA of the cluster (128 csize >= K rows in total)
+      const uint32_t bytes = A_BYTES + csize * B_SLICE_BYTES;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);      // every CTA of the cluster has released the slot
+        uint8_t* sa = ring + stage * STAGE_BYTES;
+        tc::mbar_expect_tx(&full_bar[stage], bytes);
+        tc::tma_load_3d(sa, &tmA, &full_bar[stage], kb * BKF, m0, b);
+        tma_load_3d_mc(sa + A_BYTES + crank * B_SLICE_BYTES, &tmB, &full_bar[stage], kb * BKF, 128 * (int)crank, b, cmask);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_lo = tc::make_idesc_bf16(tc::BM, n_lo), idesc_hi = tc::make_idesc_bf16(tc::BM, n_hi ? n_hi : 16);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(ring + stage * STAGE_BYTES);
+        const uint64_t da = tc::make_smem_desc_k64(sa);
+        const uint64_t db0 = tc::make_smem_desc_k64(sa + A_BYTES), db1 = tc::make_smem_desc_k64(sa + A_BYTES + B_HALF_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKF / tc::UMMA_K; ++k) {
+          const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+          tc::umma_bf16(tmem_base, da + 2 * k, db0 + 2 * k, idesc_lo, accum);
+          if (n_hi) tc::umma_bf16(tmem_base + 256, da + 2 * k, db1 + 2 * k, idesc_hi, accum);
+        }
+        tc_commit_mc(&empty_bar[stage], cmask);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc::tc_commit(tmem_full);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - tc::PRODUCER_WARPS;          // 0..7
+    const int quad = warp & 3, hpart = ew >> 2;        // TMEM lane quadrant; which of the alternate 32-column chunks
+    const int row = quad * 32 + lane, rowg = m0 + row;
+    const bool row_ok = rowg < K;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int et = threadIdx.x - tc::PRODUCER_WARPS * 32;      // 0..255
+    {
+      const float* gp2 = p.p2 + (int64_t)b * K * 3;
+      for (int j = et; j < K; j += EPI_WARPS * 32) p2s[j] = make_float4(__ldg(gp2 + 3 * j), __ldg(gp2 + 3 * j + 1), __ldg(gp2 + 3 * j + 2), 0.f);
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (row_ok) {
+      const float* a = p.p1 + ((int64_t)b * K + rowg) * 3;
+      ax = a[0]; ay = a[1]; az = a[2];
+    }
+    const float inv_tau = p.inv_tau, kexp = p.inv_tau * 1.4426950408889634f, thr2 = p.thr2;
+    epi_barrier();       // p2s is complete
+    // negative masks of this thread's row for its chunks: they do not depend on the similarity, so they are built
+    // while the MMAs run and parked in shared memory (the chunk loops stay rolled: unrolled, the kernel was 120 KB of
+    // straight-line code that missed the instruction cache all the way)
+#pragma unroll 1
+    for (int c32 = hpart; 32 * c32 < K; c32 += 2) {
+      const int n0 = 32 * c32;
+      uint32_t m = 0u;
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) {
+        const int col = n0 + q;
+        const float4 pj = p2s[col < K ? col : 0];
+        const float dx = ax - pj.x, dy = ay - pj.y, dz = az - pj.z;
+        const bool neg = (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) > thr2) && (col != rowg) && (col < K);
+        m |= neg ? (1u << q) : 0u;
+      }
+      nmask_s[c32 * 128 + row] = m;
+    }
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    // the positive of row r is column m0 + r: chunk (m0 >> 5) + quad, element `lane` of it
+    const int dchunk = (m0 >> 5) + quad;
+    if ((dchunk & 1) == hpart) {
+      float v[32];
+      tc::tmem_ld32(trow + 32 * dchunk, v);
+      float pv = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) pv = (q == lane) ? v[q] : pv;
+      pos_s[row] = pv;
+    }
+    epi_barrier();       // pos_s is complete
+    const float pos = pos_s[row];
+    // sigmoid(u / tau) = 1 / (1 + 2^(-u k)), k = log2(e) / tau, without the reference's clamp of the exponent to +-50:
+    // beyond it the sigmoid differs from 0 / 1 by < 2e-22 (an overflowing 2^x gives exactly 0).  G2 accumulates
+    // s2 (1 - s2); the 1 / tau is applied once.
+    const float e1c = kexp, e2c = pos * kexp;      // -u k = v (-k) + {1, pos} k
+    float S1 = 0.f, S2 = 0.f, G2 = 0.f;
+#pragma unroll 1
+    for (int c32 = hpart; 32 * c32 < K; c32 += 2) {
+      const int n0 = 32 * c32;
+      float v[32];
+      tc::tmem_ld32(trow + n0, v);
+      const uint32_t m = nmask_s[c32 * 128 + row];
+      uint32_t pk[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        float x1, x2, s1, s2;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x1) : "f"(fmaf(v[q], -kexp, e1c)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x2) : "f"(fmaf(v[q], -kexp, e2c)));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(1.f + x1));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s2) : "f"(1.f + x2));
+        const float mf = ((m >> q) & 1u) ? 1.f : 0.f;
+        S1 = fmaf(s1, mf, S1);
+        S2 = fmaf(s2, mf, S2);
+        G2 = fmaf(fmaf(-s2, s2, s2), mf, G2);
+        const __half2 h = __floats2half2_rn(s1, s2);
+        pk[q] = ((m >> q) & 1u) ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
+      }
+      if (p.want_grad) tmem_st32(trow + n0, pk);
+    }
+    G2 *= inv_tau;
+    if (p.want_grad) tmem_wait_st();
+    part[hpart * 128 + row] = make_float4(S1, S2, G2, 0.f);
+    epi_barrier();
+    {
+      const float4 o = part[(hpart ^ 1) * 128 + row];
+      S1 += o.x; S2 += o.y; G2 += o.z;
+    }
+    const float inv_tau_ = inv_tau;
+    const SigT q1 = (p.variant == GD3_VARIANT_VGGT) ? sig_both(1.f - pos, inv_tau_) : sig_both(pos - 1.f, inv_tau_);
+    const SigT q2 = sig_both(1.f - pos, inv_tau_);
+    const float r1 = 1.f + q1.s, r2 = 1.f + q2.s;
+    const float den1 = r1 + S1, den2 = r2 + S2;
+    if (hpart == 0) {
+      float lr = row_ok ? 1.f - 0.5f * (r1 / den1 + r2 / den2) : 0.f;
+      lr = warp_sum(lr);
+      if (lane == 0 && m0 + quad * 32 < K) atomicAdd(p.loss_acc + b, (double)lr);
+      if (blockIdx.x == 0 && ew == 0 && lane == 0) p.qcount[b] = K;
+    }
+    if (p.want_grad) {
+      // d sim = c1 s1 (1 - s1) + c2 s2 (1 - s2): s (1 - s) for both sigmoids is one half2 fma, the result is rounded
+      // to bf16 anyway
+      const float c1 = 0.5f * inv_tau * r1 / (den1 * den1), c2 = 0.5f * inv_tau * r2 / (den2 * den2);
+      const float dr1 = (p.variant == GD3_VARIANT_VGGT) ? -q1.ds : q1.ds;
+      const float dpos = -0.5f * (S1 / (den1 * den1) * dr1 - S2 / (den2 * den2) * q2.ds + r2 / (den2 * den2) * G2);
+      uint8_t* slab = slabs + ew * tc::kStoreSlabBytes;
+      const int m_warp = m0 + quad * 32;
+#pragma unroll 1
+      for (int c32 = hpart; 32 * c32 < K; c32 += 2) {
+        const int n0 = 32 * c32;
+        float v[32];
+        tc::tmem_ld32(trow + n0, v);
+        if (m_warp >= K) continue;      // warp-uniform: the slab lies outside the tensor
+        if (lane == 0) tc::tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t o[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float g[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int q = 8 * q4 + 2 * h + e;
+              const uint32_t bits = __float_as_uint(v[q]);
+              const __half2 hs = *reinterpret_cast<const __half2*>(&bits);
+              const float2 tt = __half22float2(__hfma2(__hneg2(hs), hs, hs));      // s (1 - s), both sigmoids
+              const float gg = fmaf(c1, tt.x, c2 * tt.y);
+              g[e] = (n0 + q == rowg) ? dpos : gg;
+            }
+            o[h] = pack_bf16x2(g[0], g[1]);
+          }
+          *reinterpret_cast<uint4*>(slab + tc::store_slab_offset(lane, q4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tc::tma_store_3d(&p.tm_ds, slab, n0, m_warp, b);
+          tc::tma_store_commit();
+        }
+      }
+      if (lane == 0) tc::tma_store_wait_read();
+      __syncwarp();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // nobody leaves while a peer may still copy into its shared memory or arrive on its barriers
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+}  // namespace apf
 
 // loss[p] = acc / Q, scale[p] = 1 / Q  (Q = 0 -> mean of an empty set: NaN like the reference, zero gradient).
 // joint (GD3_VARIANT_ME_JOINT): Q is the number of positives of the WHOLE batch, as src/finetune_timm_me.py:202-217
@@ -422,6 +773,60 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     if ((rc = launch_split3("ap_prepare", d1, P * K, (int)C, w.ldc, 2, w.A3, stream))) return rc;
     if ((rc = launch_split3("ap_prepare", d2, P * K, (int)C, w.ldc, 1, w.B3, stream))) return rc;
   }
+  // the fused kernel runs one 128-row tile per CTA and one CTA per SM: it wins when the tiles fill their waves (cfg2: 128
+  // tiles on 148 SMs, 64 us against 57 + 39 us); a poorly filled last wave costs a whole tile time (cfg4: 192 tiles, 115
+  // against 72 + 37 us).  GD3_AP_FUSED=1 / GD3_AP_UNFUSED=1 force either path (parity and timing runs).
+  bool fused = variant != GD3_VARIANT_ME && K <= apf::KMAX && !getenv_flag("GD3_AP_UNFUSED");
+  if (fused && !getenv_flag("GD3_AP_FUSED")) {
+    const int64_t tiles = ceil_div<int64_t>(K, tc::BM) * P, sms = num_sms();
+    fused = (double)tiles / (double)(ceil_div<int64_t>(tiles, sms) * sms) >= 0.8;
+  }
+  if (fused) {
+    // similarity GEMM + row statistics + d sim in one kernel (the K x K similarity stays in TMEM)
+    CUtensorMap ta, tb;
+    if ((rc = tc::make_tmap_bf16_k32(&ta, w.A3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc,
+                                     tc::BM)))
+      return rc;
+    if ((rc = tc::make_tmap_bf16_k32(&tb, w.B3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc, 128)))
+      return rc;
+    apf::Params ap{};
+    if (backward && (rc = tc::make_tmap_store16(&ap.tm_ds, w.dS, K, K, P, w.ldk, K * (int64_t)w.ldk, false))) return rc;
+    ap.p1 = pts3d_1;
+    ap.p2 = pts3d_2;
+    ap.K = (int)K;
+    ap.variant = variant;
+    ap.want_grad = backward ? 1 : 0;
+    ap.k_blocks = (int)ceil_div<int64_t>(3 * (int64_t)w.ldc, apf::BKF);
+    ap.inv_tau = 1.f / temp;
+    ap.thr2 = thr_neg >= 0.f ? thr_neg * thr_neg : -1.f;
+    ap.loss_acc = w.loss_acc;
+    ap.qcount = w.qcount;
+    static SmemOptIn opt;
+    GD3_CHECK_CUDA(opt.ensure(apf::ap_fused_kernel, apf::SMEM_BYTES));
+    // one cluster per pair: its m-tiles share the B tile
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ceil_div<int64_t>(K, tc::BM), (unsigned)P);
+    cfg.blockDim = dim3(apf::THREADS);
+    cfg.dynamicSmemBytes = apf::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cfg.gridDim.x;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    {
+      GD3_PROF("ap_fused", stream);
+      GD3_CHECK_CUDA(cudaLaunchKernelEx(&cfg, apf::ap_fused_kernel, ta, tb, ap));
+    }
+    GD3_CHECK_LAUNCH();
+    {
+      GD3_PROF("ap_finalize", stream);
+      ap_finalize<<<(unsigned)ceil_div<int64_t>(P, 128), 128, 0, stream>>>(w.loss_acc, w.qcount, loss, w.scale, (int)P, joint);
+    }
+    GD3_CHECK_LAUNCH();
+  } else {
   {
     CUtensorMap ta, tb;
     if ((rc = tc::make_tmap_bf16(&ta, w.A3, 3 * (int64_t)w.ldc, K, P, 3 * (int64_t)w.ldc, K * 3 * (int64_t)w.ldc,
@@ -458,6 +863,7 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
       ap_finalize<<<(unsigned)ceil_div<int64_t>(P, 128), 128, 0, stream>>>(w.loss_acc, w.qcount, loss, w.scale, (int)P, joint);
     }
     GD3_CHECK_LAUNCH();
+  }
   }
   if (backward) {
     // d D1 = dS D2 and d D2 = dS^T D1: dS is read K-major for the first and MN-major for the second product, the

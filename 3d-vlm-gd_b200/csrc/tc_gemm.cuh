@@ -162,6 +162,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// K-major, 64B-swizzled operand (32 bf16 per row, boxes from make_tmap_bf16_k32): 8 rows x 64 B = 512 B between row groups
+__device__ __forceinline__ uint64_t make_smem_desc_k64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
 // MN-major, 128B-swizzled operand: the tile sits in shared memory as [k rows][64 MN elements] blocks (128-byte rows,
 // exactly how TMA delivers a box of a matrix whose MN dimension is the contiguous one), one 8 KB block per 64 MN
 // elements.  Canonical layout ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units: LBO = distance between 64-element MN
@@ -383,6 +393,8 @@ __global__ void __launch_bounds__((PRODUCER_WARPS + EPI_WARPS) * 32, 1)
 // 128-byte swizzle, out-of-bounds elements read as zero (this is what pads ragged N / K).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t k_extent, int64_t rows, int64_t batch,
                    int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows);
+int make_tmap_bf16_k32(CUtensorMap* out, const void* base, int64_t k_extent, int64_t rows, int64_t batch,
+                       int64_t row_stride_elems, int64_t batch_stride_elems, int box_rows);
 // Tensor map for epilogue TMA STORES of 16-bit outputs: dims (cols, rows, batch), box (32 cols = 64 bytes, 32 rows, 1),
 // 64-byte swizzle (the staging slab of a warp is [32 rows][64 B], 16-byte chunk index xor ((row >> 1) & 3)); elements
 // outside the tensor are clipped, which is what handles ragged M / N.  fp16 = true for __half outputs, else bf16.

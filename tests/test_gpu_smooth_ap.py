@@ -85,6 +85,45 @@ def test_smooth_ap_full_size_batched(variant, K, C):
         assert_grad_close(D2.grad[p], want[p][2], name=f'd2[{p}]', norm_rtol=3e-2)
 
 
+@pytest.mark.parametrize('variant,K,C,P', [('mast3r', 512, 768, 3), ('vggt', 300, 1024, 3), ('mast3r', 77, 64, 2),
+                                           ('vggt', 130, 128, 2), ('mast3r', 257, 96, 2), ('vggt', 5, 64, 1)])
+def test_smooth_ap_fused_kernel_forced(monkeypatch, variant, K, C, P):
+    """The one-kernel path (similarity tile in TMEM, cluster-shared B tile) is chosen by a wave-fill heuristic that small
+    batches never meet: force it (GD3_AP_FUSED=1) at the BASELINE sizes and at ragged K (1, 2, 3 and 4 CTAs per
+    cluster, K not a multiple of 16 / 32) against the CPU oracle, and check that it equals the unfused path."""
+    from gd3 import ops
+    pairs = [make_pair(7600 + 10 * p, K, C) for p in range(P)]
+    want = []
+    for d1, d2, p1, p2 in pairs:
+        a = d1.clone().requires_grad_(True)
+        b = d2.clone().requires_grad_(True)
+        loss = bodies.smooth_ap(a, b, p1, p2, variant)
+        ga, gb = torch.autograd.grad(loss, [a, b])
+        want.append((float(loss), ga, gb))
+    D1, D2, P1, P2 = [torch.stack([q[k] for q in pairs]).cuda() for k in range(4)]
+    got = {}
+    for path in ('GD3_AP_FUSED', 'GD3_AP_UNFUSED'):
+        monkeypatch.delenv('GD3_AP_FUSED', raising=False)
+        monkeypatch.delenv('GD3_AP_UNFUSED', raising=False)
+        monkeypatch.setenv(path, '1')
+        x = D1.clone().requires_grad_(True)
+        y = D2.clone().requires_grad_(True)
+        loss = ops.smooth_ap(x, y, P1, P2, variant=variant)
+        loss.sum().backward()
+        got[path] = (loss.detach(), x.grad, y.grad)
+        for p in range(P):
+            assert rel_err(loss[p].item(), want[p][0]) <= 1e-3, (path, p, loss[p].item(), want[p][0])
+            assert_grad_close(x.grad[p], want[p][1], name=f'{path} d1[{p}]', norm_rtol=3e-2)
+            assert_grad_close(y.grad[p], want[p][2], name=f'{path} d2[{p}]', norm_rtol=3e-2)
+    # forward-only call through the fused path (no d sim sweep)
+    monkeypatch.delenv('GD3_AP_UNFUSED', raising=False)
+    monkeypatch.setenv('GD3_AP_FUSED', '1')
+    with torch.no_grad():
+        l0 = ops.smooth_ap(D1, D2, P1, P2, variant=variant)
+    assert torch.allclose(l0, got['GD3_AP_FUSED'][0], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(got['GD3_AP_FUSED'][0], got['GD3_AP_UNFUSED'][0], rtol=2e-4, atol=1e-6)
+
+
 def test_smooth_ap_me_joint_mean_over_the_batch():
     """ME baseline with B > 1 (src/finetune_timm_me.py:199-217): one mean over the positives of all pairs.  Pairs get
     different numbers of positives (one gets none), so the per-pair mean ('me') and the joint mean differ."""
