@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) rank_pairs(RankParams
       if (lane == 0) red[4 * H + 1 + warp] = cm;
       __syncthreads();
       const float mean = ((red[4 * H + 1] + red[4 * H + 2]) + (red[4 * H + 3] + red[4 * H + 4])) * (1.f / H);
+      __syncthreads();      // every thread has read the warp sums before `red` is rewritten
       red[threadIdx.x] = c - mean;
     }
     for (int e = H + threadIdx.x; e < 4 * H + 1; e += blockDim.x) red[e] = 0.f;
