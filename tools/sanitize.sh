@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 TOOLS=${@:-memcheck racecheck}
 # one small, fast test per kernel family (the full-size tests take minutes under the sanitizer)
 TESTS="tests/test_gpu_cost_kl.py::test_cost_kl_golden tests/test_gpu_cost_kl.py::test_cost_kl_packed_teacher_ragged_batched \
-tests/test_gpu_smooth_ap.py::test_smooth_ap_golden tests/test_gpu_smooth_ap.py::test_smooth_ap_me_joint_mean_over_the_batch \
+tests/test_gpu_smooth_ap.py::test_smooth_ap_golden tests/test_gpu_smooth_ap.py::test_smooth_ap_me_joint_mean_over_the_batch tests/test_gpu_smooth_ap.py::test_smooth_ap_fused_kernel_forced \
 tests/test_gpu_depth_rank.py::test_fused_depth_losses_golden tests/test_gpu_depth_rank.py::test_depth_losses_edge_cases tests/test_gpu_sample.py tests/test_gpu_fast_nn.py::test_reciprocal_nn_golden tests/test_gpu_fast_nn.py::test_fast_reciprocal_nns_golden \
 tests/test_gpu_teacher_volume.py tests/test_gpu_depth_splat.py tests/test_gpu_eval_argmax.py"
 for tool in $TOOLS; do
