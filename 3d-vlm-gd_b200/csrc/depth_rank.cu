@@ -235,6 +235,8 @@ __device__ __forceinline__ uint32_t opaque(uint32_t x) {
 //   same, 2 pairs per lane and one shared scalar chain ("quad step"), 12 warps x 168 registers      2.64 ms
 //   32 lanes per pair, 4 hidden units per lane, 4 pairs per lane (this layout), 12 warps x 168      2.63 ms
 //   this layout, software-pipelined, 8 warps x 224 registers                                       2.44 ms
+//   the same with the d u flush below                                                             2.39 ms
+//   software-pipelined with 2 pairs per lane and step (half the stage state), 12 warps x 168      2.60 ms
 // The register budget decides the layout.  Per lane, the state that lives across the scalar chain is 3 values
 // (xh, GELU, GELU') per (pair, hidden unit) = 12 x pairs-per-warp-step registers whatever the layout, while the
 // per-hidden-unit constants and accumulators (gamma, beta, w2 (x2), d gamma, d beta, d w2, v_b, d u_b: 9 values) scale
