@@ -864,7 +864,7 @@ __global__ void rank_inv_count(const int* __restrict__ count, int S, int joint, 
 template <bool GRAD>
 __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __restrict__ w_l1, double* __restrict__ l1_sum,
                                               float* __restrict__ du_extra /* (S, K, H) zero-initialised */) {
-  __shared__ float red[3 * H + 1];
+  __shared__ float part[16][3 * H + 1];      // per half warp: [gamma | beta | w2 | b2] partial sums
   const int pair = blockIdx.y;
   const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
   const int K = p.K;
@@ -923,21 +923,28 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
   loss_local = warp_sum(loss_local);
   if (lane == 0 && loss_local != 0.f) atomicAdd(l1_sum + pair, (double)loss_local);
   if (GRAD) {
-    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) red[e] = 0.f;
-    __syncthreads();
+    // parameter sums of the CTA without atomics: every half warp (16 of them, each covering all 128 hidden units) writes
+    // its 3 x 128 partial sums to shared memory, then one thread per entry adds the 16 rows.  (Shared float atomics are
+    // compare-and-swap loops; 16 half warps hitting the same 384 addresses made this tail most of the kernel.)
+    const int hw = threadIdx.x >> 4;      // 0..15
 #pragma unroll
     for (int i = 0; i < HPL; ++i) {
       const int h = hidx(l16, i);
-      atomicAdd(red + h, dgam[i]);
-      atomicAdd(red + H + h, dbet[i]);
-      atomicAdd(red + 2 * H + h, dw2[i]);
+      part[hw][h] = dgam[i];
+      part[hw][H + h] = dbet[i];
+      part[hw][2 * H + h] = dw2[i];
     }
     db2 = warp_sum(db2);
-    if (lane == 0) atomicAdd(red + 3 * H, db2);
+    if (lane == 0) part[hw][3 * H] = db2;      // one entry per warp (its even half-warp row); the odd rows hold 0
+    else if (l16 == 0) part[hw][3 * H] = 0.f;
     __syncthreads();
     float* gp = p.gparam + p.gparam_off;
-    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x)
-      if (red[e] != 0.f) atomicAdd(gp + H + e, red[e]);
+    for (int e = threadIdx.x; e < 3 * H + 1; e += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += part[k][e];
+      if (t != 0.f) atomicAdd(gp + H + e, t);
+    }
   }
 }
 
