@@ -167,3 +167,39 @@ def test_ranking_correlated_keypoint_features(spread):
     got.backward()
     assert rel_err(got.item(), want.item()) <= 1e-3, (spread, got.item(), want.item())
     assert_grad_close(x.grad, ref_in.grad, name=f'feats/spread={spread}', norm_rtol=3e-2)
+
+
+def test_ranking_exact_duplicate_keypoints():
+    """Many keypoints with EXACTLY the same feature (several keypoints on one token): their pair differences are the
+    bias alone, the Gram form of the LayerNorm statistics cancels completely, and every such pair goes through the
+    direct recomputation (rank_fix_rstd; rows with many flags, K not a multiple of 32)."""
+    from gd3.compat import losses
+    torch.manual_seed(13)
+    K, D = 77, 64
+    head = olosses.DepthHead(D)
+    feats = torch.randn(2, K, D)
+    feats[0, 10:30] = feats[0, 10]                 # 20 identical rows in set 0
+    feats[1, 0::7] = feats[1, 0]                   # every 7th row identical in set 1
+    depths = torch.rand(2, K) * 4.5 + 0.5
+    ref_in = feats.clone().requires_grad_(True)
+    want = olosses.pairwise_logistic_ranking_loss(head, ref_in, depths, depth_threshold=0.05)
+    want.backward()
+    h = cuda_head(head)
+    x = feats.cuda().requires_grad_(True)
+    got = losses.pairwise_logistic_ranking_loss(h, x, depths.cuda(), depth_threshold=0.05)
+    got.backward()
+    assert torch.isfinite(x.grad).all()
+    assert rel_err(got.item(), want.item()) <= 1e-3, (got.item(), want.item())
+    assert_grad_close(x.grad, ref_in.grad, name='feats with duplicates', norm_rtol=3e-2)
+    for i, (p_ref, p_got) in enumerate(zip(head_grads(head), head_grads(h))):
+        assert_grad_close(p_got.cpu().reshape(-1), p_ref.reshape(-1), name=f'head[{i}]', norm_rtol=3e-2)
+
+
+def test_depth_head_loss_rejects_negative_threshold():
+    """thr >= 0 is part of the contract (a pair of equal depths is never valid): the library says so instead of
+    silently counting the diagonal."""
+    from gd3 import _lib
+    from gd3.compat import losses
+    head = cuda_head(olosses.DepthHead(32))
+    with pytest.raises((ValueError, _lib.Gd3Error), match='thr must be >= 0'):
+        losses.pairwise_logistic_ranking_loss(head, torch.randn(1, 8, 32).cuda(), torch.rand(1, 8).cuda(), -0.1)
