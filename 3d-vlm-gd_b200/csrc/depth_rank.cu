@@ -22,6 +22,7 @@
 // owns a 64 x (4 b_per_warp) tile of (a, b): every warp keeps the gradient of its b row in registers and accumulates
 // the a side into a shared tile; the a index is staggered per warp so no two warps touch the same row in the same step.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "../../include/gd3.h"
@@ -955,7 +956,7 @@ __global__ void __launch_bounds__(256) rank_l1(RankParams p, const float* __rest
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     rank_reduce_du(const float* __restrict__ du, const float* __restrict__ du_extra, int S, int K,
-                   __nv_bfloat16* __restrict__ du2 /* (S K, 2 H): [hi | lo] */, float* __restrict__ gb1) {
+                   __nv_bfloat16* __restrict__ du2 /* (S K, H) bf16 */, float* __restrict__ gb1) {
   __shared__ float colsum[8][H];
   const int set = blockIdx.y, k0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -973,15 +974,10 @@ __global__ void __launch_bounds__(256)
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         if ((set & 1) == 0) { bsum[0] += v.x; bsum[1] += v.y; bsum[2] += v.z; bsum[3] += v.w; }   // b side of the L1 pair
       }
-      // bf16 hi / lo split of du, row-major: the d feats GEMM reads the hi panel K-major, the d W1 GEMM reads both
-      // panels MN-major (tc_gemm.cuh), so no transposed copy is written
-      const float v[4] = {acc.x, acc.y, acc.z, acc.w};
-      uint16_t hi[4], lo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split_detail::hi_lo(v[i], hi[i], lo[i]);
-      __nv_bfloat16* row = du2 + ((int64_t)set * K + k) * 2 * H + 4 * lane;
-      *reinterpret_cast<uint2*>(row) = make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2] | ((uint32_t)hi[3] << 16));
-      *reinterpret_cast<uint2*>(row + H) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2] | ((uint32_t)lo[3] << 16));
+      // du in bf16, row-major: the d feats GEMM reads it K-major, the d W1 GEMM MN-major (tc_gemm.cuh), so no
+      // transposed copy is written
+      __nv_bfloat16* row = du2 + ((int64_t)set * K + k) * H + 4 * lane;
+      *reinterpret_cast<uint2*>(row) = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
     }
   }
   if (!du_extra) return;      // CTA-uniform
@@ -1116,7 +1112,7 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.loss_sum = c.take<double>(S);
   w.l1_sum = c.take<double>(S);
   if (backward) {
-    w.du2 = c.take<__nv_bfloat16>(R * 2 * H);
+    w.du2 = c.take<__nv_bfloat16>(R * H);
     w.du = c.take<float>(R * H);
     if (l1) w.du_extra = c.take<float>(R * H);
   }
@@ -1333,27 +1329,26 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     GD3_CHECK_LAUNCH();
   }
   {
-    // d feats = du W1: A = du hi panel (K-major, row stride 2 H), B = W1 hi panel of W3 read MN-major ([k = h][mn = d])
+    // d feats = du W1: A = du (K-major), B = W1 hi panel of W3 read MN-major ([k = h][mn = d])
     CUtensorMap t_du, t_w1;
-    if ((rc = tc::make_tmap_bf16(&t_du, w.du2, H, R, 1, 2 * H, 0, tc::BM))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_du, w.du2, H, R, 1, H, 0, tc::BM))) return rc;
     if ((rc = tc::make_tmap_bf16(&t_w1, w.W3, D, H, 1, 3 * (int64_t)w.ldd, 0, 64))) return rc;
     tc::EpiStoreF32::Params e1{grad_feats, (int)R, (int)D, D, 0, 1.0f, nullptr};
     if ((rc = tc::enable_tma_store(e1, 1))) return rc;
     tc::GemmShape s1{(int)R, (int)D, H, 1};
     if ((rc = tc::launch_gemm<256, 8, tc::EpiStoreF32, false, true>("rank_df_gemm", t_du, t_w1, s1, e1, stream))) return rc;
-    // d W1 (H x D) = sum over sets of du_s^T f_s with the 3-term bf16 split  hi^T hi + lo^T hi + hi^T lo: a grouped
-    // contraction over (term, set of the group, 64-keypoint block), both operands read MN-major from their row-major
-    // panels (du2 = [hi | lo], F3 = [hi | hi | lo]); one GEMM batch entry per group, fp32 atomic accumulation
+    // d W1 (H x D) = sum over sets of du_s^T f_s: a grouped contraction over (set of the group, 64-keypoint block), both
+    // operands read MN-major from their row-major buffers (du2, the hi panel of F3); one GEMM batch entry per group, fp32
+    // atomic accumulation.  Plain bf16 operands: the sum runs over all S K keypoints with incoherent terms, so the 2^-9
+    // operand rounding averages out (the three-term split of round 1 changed |d W1| by 3e-5 and cost 44 instead of 25 us).
     CUtensorMap t_dum, t_fm;
-    if ((rc = tc::make_tmap_bf16(&t_dum, w.du2, 2 * H, K, S, 2 * H, K * 2 * (int64_t)H, 64))) return rc;
+    if ((rc = tc::make_tmap_bf16(&t_dum, w.du2, H, K, S, H, K * (int64_t)H, 64))) return rc;
     if ((rc = tc::make_tmap_bf16(&t_fm, w.F3, 3 * (int64_t)w.ldd, K, S, 3 * (int64_t)w.ldd, K * 3 * (int64_t)w.ldd, 64)))
       return rc;
     tc::GroupedK gk;
-    gk.panels = 3;
+    gk.panels = 1;
     gk.sets_per_group = w.gs;
     gk.row_blocks = (int)ceil_div<int64_t>(K, tc::BK);
-    gk.a_off[0] = 0; gk.a_off[1] = H; gk.a_off[2] = 0;
-    gk.b_off[0] = 0; gk.b_off[1] = 0; gk.b_off[2] = 2 * w.ldd;
     EpiAtomicAddF32::Params e2{grad_params, H, (int)D, D};
     tc::GemmShape s2{H, (int)D, gk.panels * gk.sets_per_group * gk.row_blocks * tc::BK, w.groups};
     if ((rc = tc::launch_gemm<256, 8, EpiAtomicAddF32, true, true, true>("rank_dw1_gemm", t_dum, t_fm, s2, e2, stream, 0, gk)))
