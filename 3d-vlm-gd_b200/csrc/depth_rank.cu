@@ -825,37 +825,46 @@ __global__ void __launch_bounds__(256) rank_fix_rstd(const float* __restrict__ u
 // ------------------------------------------------------------------------------------------
 // number of valid pairs per set -> inv_count (per set, or shared when joint_mean)
 // ------------------------------------------------------------------------------------------
-// grid (ceil(K / 256), S), block 256: thread = one a, loop over all b with the set's depths in shared memory
-__global__ void __launch_bounds__(256) rank_count(const float* __restrict__ depth, int K, int mode, float thr,
-                                                  int* __restrict__ count) {
+// grid (ceil(K / 256), S, splits of the b range), block 256: thread = one a, loop over its slice of b with the set's
+// depths in shared memory.  The last CTA to finish (ticket counter count[S]) turns the counts into 1 / count.
+__global__ void __launch_bounds__(256) rank_count(const float* __restrict__ depth, int K, int S, int mode, float thr,
+                                                  int joint, int* __restrict__ count /* S + 1, zero on entry */,
+                                                  float* __restrict__ inv) {
   extern __shared__ float sdep[];     // K depths of this set
   __shared__ int red[32];
+  __shared__ int s_last;
   const int set = blockIdx.y;
   const float* d = depth + (int64_t)set * K;
   for (int k = threadIdx.x; k < K; k += blockDim.x) sdep[k] = d[k];
   __syncthreads();
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = (K + gridDim.z - 1) / gridDim.z, b0 = blockIdx.z * chunk, b1 = min(K, b0 + chunk);
   int c = 0;
   if (a < K) {
     const float da = sdep[a];
     if (mode == 0) {
-      for (int b = 0; b < K; ++b) c += (fabsf(sdep[b] - da) > thr) ? 1 : 0;
+      for (int b = b0; b < b1; ++b) c += (fabsf(sdep[b] - da) > thr) ? 1 : 0;
     } else {
-      for (int b = 0; b < K; ++b) c += (fabsf(tanhf(sdep[b] - da)) > thr) ? 1 : 0;
+      for (int b = b0; b < b1; ++b) c += (fabsf(tanhf(sdep[b] - da)) > thr) ? 1 : 0;
     }
   }
   c = block_sum(c, red);
-  if (threadIdx.x == 0 && c) atomicAdd(count + set, c);
-}
-__global__ void rank_inv_count(const int* __restrict__ count, int S, int joint, float* __restrict__ inv) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= S) return;
-  long long n = count[s];
-  if (joint) {
-    n = 0;
-    for (int k = 0; k < S; ++k) n += count[k];
+  if (threadIdx.x == 0) {
+    if (c) atomicAdd(count + set, c);
+    __threadfence();
+    const int ticket = atomicAdd(count + S, 1);
+    s_last = ticket == (int)(gridDim.x * gridDim.y * gridDim.z) - 1;
   }
-  inv[s] = n > 0 ? (float)(1.0 / (double)n) : 0.f;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  long long total = 0;
+  if (joint)
+    for (int k = 0; k < S; ++k) total += __ldcg(count + k);
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const long long n = joint ? total : (long long)__ldcg(count + s);
+    inv[s] = n > 0 ? (float)(1.0 / (double)n) : 0.f;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1059,6 +1068,8 @@ struct RankWorkspace {
   double *loss_sum, *l1_sum;
   int* count;
   int* rowflag;
+  uint8_t* zero_a;
+  size_t zero_a_bytes, zero_b_bytes;
   size_t total;
   int ldd, TA, TB, groups, bpw;
   int gs;        // sets per split-K group of the d W1 contraction
@@ -1106,15 +1117,23 @@ RankWorkspace carve_rank(void* base, int64_t S, int64_t K, int64_t D, bool backw
   w.nb = c.take<float>(R);
   w.na = c.take<float>(R);
   w.rstd = c.take<float>(R * K);
-  w.count = c.take<int>(S);
-  w.rowflag = c.take<int>(R);
   w.inv_count = c.take<float>(S);
+  // zero-initialised accumulators, contiguous: one memset each for [loss_sum | l1_sum | count + ticket | rowflag] and
+  // [du | du_extra]
   w.loss_sum = c.take<double>(S);
   w.l1_sum = c.take<double>(S);
+  w.count = c.take<int>(S + 1);
+  w.rowflag = c.take<int>(R);
+  w.zero_a = reinterpret_cast<uint8_t*>(w.loss_sum);
+  w.zero_a_bytes = (size_t)(reinterpret_cast<uint8_t*>(w.rowflag + R) - w.zero_a);
   if (backward) {
     w.du2 = c.take<__nv_bfloat16>(R * H);
     w.du = c.take<float>(R * H);
-    if (l1) w.du_extra = c.take<float>(R * H);
+    w.zero_b_bytes = sizeof(float) * R * H;
+    if (l1) {
+      w.du_extra = c.take<float>(R * H);
+      w.zero_b_bytes = (size_t)(reinterpret_cast<uint8_t*>(w.du_extra + R * H) - reinterpret_cast<uint8_t*>(w.du));
+    }
   }
   w.total = c.total();
   return w;
@@ -1154,8 +1173,10 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   GD3_REQUIRE(S <= 65535, "gd3_depth_head_loss: at most 65535 sets per call");
   GD3_REQUIRE(K <= 12288, "gd3_depth_head_loss: at most 12288 keypoints per set (K^2 pairs are evaluated)");
   const bool backward = grad_feats != nullptr;
-  GD3_CHECK_CUDA(cudaMemsetAsync(loss_rank, 0, sizeof(float) * S, stream));
-  if (l1) GD3_CHECK_CUDA(cudaMemsetAsync(loss_l1, 0, sizeof(float) * (S / 2), stream));
+  if (K == 0) {      // every other case writes all the losses (rank_finalize)
+    GD3_CHECK_CUDA(cudaMemsetAsync(loss_rank, 0, sizeof(float) * S, stream));
+    if (l1) GD3_CHECK_CUDA(cudaMemsetAsync(loss_l1, 0, sizeof(float) * (S / 2), stream));
+  }
   const int64_t nparam = (int64_t)H * D + 4 * H + 1;
   if (backward) {
     GD3_CHECK_CUDA(cudaMemsetAsync(grad_params, 0, sizeof(float) * nparam, stream));
@@ -1171,6 +1192,9 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   }
   const int64_t R = S * K;
   int rc;
+  // every zero-initialised accumulator of the call in two memsets
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.zero_a, 0, w.zero_a_bytes, stream));
+  if (backward) GD3_CHECK_CUDA(cudaMemsetAsync(w.du, 0, w.zero_b_bytes, stream));
   // ---- u = f W1^T on the tensor cores (split bf16, 3 K-concatenated panels) ----
   {
     // operands of u = f W1^T; the backward GEMMs read the same panels MN-major (no transposed copies)
@@ -1210,7 +1234,6 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     CUtensorMap ta, tb;
     if ((rc = tc::make_tmap_bf16(&ta, w.Wb3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, tc::BM))) return rc;
     if ((rc = tc::make_tmap_bf16(&tb, w.Va3, 3 * H, K, S, 3 * H, K * 3 * (int64_t)H, bn))) return rc;
-    GD3_CHECK_CUDA(cudaMemsetAsync(w.rowflag, 0, sizeof(int) * R, stream));
     EpiRstd::Params ep{w.rstd, (int)K, w.nb, w.na, ln_eps, w.rowflag};
     if (K % 4 == 0 && reinterpret_cast<uintptr_t>(w.rstd) % 16 == 0) {
       if ((rc = tc::make_tmap_store32(&ep.tm_out, w.rstd, K, K, S, K, K * K))) return rc;
@@ -1227,19 +1250,16 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     GD3_CHECK_LAUNCH();
   }
   // ---- valid-pair counts ----
-  GD3_CHECK_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int) * S, stream));
-  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_sum, 0, sizeof(double) * S, stream));
-  GD3_CHECK_CUDA(cudaMemsetAsync(w.l1_sum, 0, sizeof(double) * S, stream));
   {
-    dim3 grid((unsigned)ceil_div<int64_t>(K, 256), (unsigned)S);
+    // ~2 CTAs per SM: the b range of a set is split when there are few sets
+    const int64_t xy = ceil_div<int64_t>(K, 256) * S;
+    int64_t split = ceil_div<int64_t>(2 * (int64_t)num_sms(), xy);
+    split = std::max<int64_t>(1, std::min<int64_t>(split, ceil_div<int64_t>(K, 64)));
+    dim3 grid((unsigned)ceil_div<int64_t>(K, 256), (unsigned)S, (unsigned)split);
     {
       GD3_PROF("rank_count", stream);
-      rank_count<<<grid, 256, sizeof(float) * K, stream>>>(depths, (int)K, mode, thr, w.count);
-    }
-    GD3_CHECK_LAUNCH();
-    {
-      GD3_PROF("rank_inv_count", stream);
-      rank_inv_count<<<(unsigned)ceil_div<int64_t>(S, 128), 128, 0, stream>>>(w.count, (int)S, joint_mean, w.inv_count);
+      rank_count<<<grid, 256, sizeof(float) * K, stream>>>(depths, (int)K, (int)S, mode, thr, joint_mean, w.count,
+                                                          w.inv_count);
     }
     GD3_CHECK_LAUNCH();
   }
@@ -1264,7 +1284,6 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.ln_eps = ln_eps;
   rp.loss_sum = w.loss_sum;
   rp.du = w.du;
-  if (backward) GD3_CHECK_CUDA(cudaMemsetAsync(w.du, 0, sizeof(float) * R * H, stream));
   rp.gparam = grad_params;
   rp.gparam_off = (int64_t)H * D;
   {
@@ -1294,7 +1313,6 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     GD3_CHECK_LAUNCH();
   }
   if (l1) {
-    if (backward) GD3_CHECK_CUDA(cudaMemsetAsync(w.du_extra, 0, sizeof(float) * R * H, stream));
     // about one wave of CTAs (2 per SM): a CTA walks several blocks of 16 keypoints
     const int64_t gx_max = ceil_div<int64_t>(2 * (int64_t)num_sms(), S / 2);
     const int64_t gx = std::min<int64_t>(ceil_div<int64_t>(K, 16), std::max<int64_t>(gx_max, 1));

@@ -764,8 +764,8 @@ int gd3_smooth_ap(const float* d1, const float* d2, const float* pts3d_1, const 
     set_error("gd3_smooth_ap: workspace too small (%zu < %zu)", workspace_bytes, w.total);
     return GD3_ERR_WORKSPACE;
   }
-  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, sizeof(double) * P, stream));
-  GD3_CHECK_CUDA(cudaMemsetAsync(w.qcount, 0, sizeof(int) * P, stream));
+  // loss_acc | tot | qcount are carved back to back: one memset
+  GD3_CHECK_CUDA(cudaMemsetAsync(w.loss_acc, 0, (size_t)(reinterpret_cast<uint8_t*>(w.qcount + P) - reinterpret_cast<uint8_t*>(w.loss_acc)), stream));
   int rc;
   {
     // [hi | hi | lo] x [hi | lo | hi] panels for the similarity GEMM; the gradient GEMMs read the hi panels (panel 0 of

@@ -113,8 +113,8 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     # teacher volumes: fp32, or the producers' packed form (fp16 volume t12 / t21 + row statistics ts12 / ts21)
     t12 = (batch['t12'], batch['ts12']) if 'ts12' in batch else batch['t12']
     t21 = (batch['t21'], batch['ts21']) if 'ts21' in batch else batch['t21']
-    w_rank = torch.full((2 * P,), 0.5 * w['intra'] * inv_p, dtype=_F32, device=dev)
-    w_l1 = torch.full((P,), w['depth'] * inv_p, dtype=_F32, device=dev)
+    w_rank = _const_vector(2 * P, 0.5 * w['intra'] * inv_p, dev)
+    w_l1 = _const_vector(P, w['depth'] * inv_p, dev)
     main = torch.cuda.current_stream(dev)
     if parallel_branches:
         s_kl, s_ap = _side_streams(dev)
@@ -146,9 +146,11 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
                 for t in outs:       # produced on a side stream, consumed (and later freed) on the caller's
                     if t is not None:
                         t.record_stream(main)
-    rank = 0.5 * (lr[0::2] + lr[1::2])
+    rank = lr.view(P, 2).mean(dim=1)
     out.update(kl=kl, ap=ap, rank=rank, l1=l1)
-    out['total'] = (w['ap'] * ap + w['depth'] * l1 + w['intra'] * rank + w['kl'] * kl).mean()
+    # weighted sum of the four per-pair losses, mean over the pairs: one small product instead of eight elementwise kernels
+    wvec = _weight_vector((w['ap'], w['depth'], w['intra'], w['kl']), inv_p, dev)
+    out['total'] = (torch.stack((ap, l1, rank, kl)) * wvec).sum()
 
     if backward:
         # scatter the keypoint gradients back into the token maps (K3 backward)
@@ -175,6 +177,31 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
                 grads_h[name] = gh
         out['grads'] = dict(f1=gf1, f2=gf2, g1=gg1, g2=gg2, head=gparams, **grads_h)
     return out
+
+
+_CONSTS = {}
+
+
+def _const_vector(n, value, dev):
+    """Cached constant fp32 vector (the per-set loss weights): no fill kernel per step, and none inside a captured graph."""
+    key = ('full', int(n), float(value), str(dev))
+    t = _CONSTS.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            return torch.full((n,), value, dtype=_F32, device=dev)      # never cache graph-pool memory
+        t = _CONSTS[key] = torch.full((n,), value, dtype=_F32, device=dev)
+    return t
+
+
+def _weight_vector(weights, scale, dev):
+    key = ('w', tuple(float(x) for x in weights), float(scale), str(dev))
+    t = _CONSTS.get(key)
+    if t is None:
+        vals = [float(x) * float(scale) for x in weights]
+        if torch.cuda.is_current_stream_capturing():      # no host -> device copy inside a capture: device-side fills
+            return torch.cat([torch.full((1, 1), v, dtype=_F32, device=dev) for v in vals])
+        t = _CONSTS[key] = torch.tensor(vals, dtype=_F32, device=dev)[:, None]
+    return t
 
 
 class GraphedStep:
