@@ -51,9 +51,11 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
       head       dict W1, b1, gamma, beta, w2, b2 (+ use_tanh, ln_eps) of the depth-difference head
     parallel_branches: the three losses are independent until the final scatter; with True the KL and Smooth-AP
       pipelines are enqueued on two side streams while the caller's stream runs the depth-ranking pipeline (under
-      CUDA-graph capture they become parallel branches of the graph).  Off by default: measured on B200 at cfg2 it does
-      not pay (3.92 ms per step against 3.88 ms on one stream) -- the pair kernel fills every SM with CTAs that own all
-      registers, so the other kernels only interleave with it and the total SM time is conserved.
+      CUDA-graph capture they become parallel branches of the graph).  With the round-2 pair kernel (2 CTAs x 4 warps
+      per SM: 57 K registers, 136 KB of shared memory) the other pipelines find room next to it and in its tail: 3.24
+      instead of 3.32 ms per step at cfg2; the earlier pair kernel owned every register of the SM and the
+      branches gained nothing (3.92 against 3.88 ms).  The default stays False for eager callers (the side streams cost
+      event traffic per call); ``GraphedStep`` and the benchmark turn it on.
     Returns dict: kl, ap, rank, l1 (each (P,)), total (0-d) and, if backward, ``grads`` with f1, f2 (feature
     dtype), g1, g2 (fp32; h1, h2 too when given) and head (packed [W1 | b1 | gamma | beta | w2 | b2]).
     """
@@ -216,6 +218,7 @@ class GraphedStep:
 
     def __init__(self, batch, **step_kwargs):
         self.batch = batch
+        step_kwargs.setdefault('parallel_branches', True)      # parallel graph branches: 3.32 -> 3.24 ms at cfg2
         self.kwargs = step_kwargs
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -271,14 +271,14 @@ def run_ours(args):
     if not args.no_graph:
         try:
             gstep = pipeline.GraphedStep(resident, variant=cfg['variant'], grid=cfg['grid'], backward=True,
-                                         pairs_per_group=args.pairs_per_group)
+                                         pairs_per_group=args.pairs_per_group, parallel_branches=not args.serial_branches)
             for _ in range(max(3, args.warmup)):
                 gstep()
             ms_step, clk_g, out = timed_replays(gstep, args.steps, world, local)
             value = world * P / (ms_step * 1e-3)
             clocks = clk_g or clocks
-            graph_note = 'one CUDA-graph replay per step (the graph holds the %d kernel launches of a step)' % (
-                launches // args.steps)
+            graph_note = 'one CUDA-graph replay per step (the graph holds the %d kernel launches of a step%s)' % (
+                launches // args.steps, '' if args.serial_branches else '; KL, Smooth-AP and ranking pipelines as parallel branches')
             # ---- sustained leg: >= 2 s of back-to-back replays, clocks and power sampled throughout ----
             n_sus = max(args.steps, int(args.sustained_s * 1e3 / ms_step) + 1)
             sus_ms, sus_clk, _ = timed_replays(gstep, n_sus, world, local)
@@ -534,6 +534,8 @@ def main():
     ap.add_argument('--sustained-s', type=float, default=2.0, help='length of the sustained graph-replay leg')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of CUDA-graph replays')
+    ap.add_argument('--serial-branches', action='store_true',
+                    help='capture the step on one stream instead of three parallel graph branches (KL | Smooth-AP | ranking)')
     ap.add_argument('--no-extras', action='store_true', help='skip the cfg3 / cfg4 / cfg5 blocks')
     ap.add_argument('--quick', action='store_true', help='skip the fp32-teacher legs (profiling runs)')
     ap.add_argument('--cfg5', action='store_true', help='run the cfg5 training-step block also at N = 1')
