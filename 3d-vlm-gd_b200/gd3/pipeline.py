@@ -26,11 +26,14 @@ DEFAULT_WEIGHTS = {
 _SIDE_STREAMS = {}
 
 
-def _side_streams(dev, n=2):
-    """Two long-lived side streams per device for the independent loss branches of a step."""
+def _side_streams(dev):
+    """Three long-lived side streams per device for the independent loss branches of a step: KL, Smooth-AP, and a
+    HIGH-priority one for the depth-ranking pipeline -- its pair kernel is 70 % of the step, so its CTAs should never
+    queue behind the other branches' (3.24 -> 3.21 ms per step at cfg2)."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev),
+                              torch.cuda.Stream(device=dev, priority=-1)]
     return _SIDE_STREAMS[key]
 
 
@@ -49,9 +52,9 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
       (src/finetune_timm_mast3r.py:516-519), dep1 / dep2 = 3 x 3 window depths at the keypoints from ``depth_map1`` /
       ``depth_map2`` ((P, H, W) or one shared (H, W) map; src/finetune_timm_mast3r.py:482-483).
       head       dict W1, b1, gamma, beta, w2, b2 (+ use_tanh, ln_eps) of the depth-difference head
-    parallel_branches: the three losses are independent until the final scatter; with True the KL and Smooth-AP
-      pipelines are enqueued on two side streams while the caller's stream runs the depth-ranking pipeline (under
-      CUDA-graph capture they become parallel branches of the graph).  With the round-2 pair kernel (2 CTAs x 4 warps
+    parallel_branches: the three losses are independent until the final scatter; with True the KL, Smooth-AP and
+      depth-ranking pipelines are enqueued on three side streams (the ranking one with high priority; under CUDA-graph
+      capture they become parallel branches of the graph).  With the round-2 pair kernel (2 CTAs x 4 warps
       per SM: 57 K registers, 136 KB of shared memory) the other pipelines find room next to it and in its tail: 3.24
       instead of 3.32 ms per step at cfg2; the earlier pair kernel owned every register of the SM and the
       branches gained nothing (3.92 against 3.88 ms).  The default stays False for eager callers (the side streams cost
@@ -119,13 +122,13 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     w_l1 = _const_vector(P, w['depth'] * inv_p, dev)
     main = torch.cuda.current_stream(dev)
     if parallel_branches:
-        s_kl, s_ap = _side_streams(dev)
+        s_kl, s_ap, s_rank = _side_streams(dev)
         fork = torch.cuda.Event()
         fork.record(main)
-        s_kl.wait_event(fork)
-        s_ap.wait_event(fork)
+        for side in (s_kl, s_ap, s_rank):
+            side.wait_event(fork)
     else:
-        s_kl = s_ap = main
+        s_kl = s_ap = s_rank = main
 
     # ---- dense cost-volume KL (K1), side stream ----
     with torch.cuda.stream(s_kl):
@@ -135,12 +138,13 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     with torch.cuda.stream(s_ap):
         ap, gd1, gd2 = ops.smooth_ap_raw(d1, d2, batch['p3d1'], batch['p3d2'], variant, temp, thr_neg,
                                          grad_scale=w['ap'] * inv_p, want_grad=backward)
-    # ---- relative depth: ranking on both views + cross-view L1 (K4), on the caller's stream ----
-    lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, Ch), depths, params,
-                                              head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
-                                              depth_threshold, 0.05, False, w_rank, w_l1, backward)
+    # ---- relative depth: ranking on both views + cross-view L1 (K4): the caller's stream, or the high-priority side stream ----
+    with torch.cuda.stream(s_rank):
+        lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, Ch), depths, params,
+                                                  head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
+                                                  depth_threshold, 0.05, False, w_rank, w_l1, backward)
     if parallel_branches:
-        for side, outs in ((s_kl, (kl, gf1, gf2)), (s_ap, (ap, gd1, gd2))):
+        for side, outs in ((s_kl, (kl, gf1, gf2)), (s_ap, (ap, gd1, gd2)), (s_rank, (lr, l1, gkf, gparams))):
             join = torch.cuda.Event()
             join.record(side)
             main.wait_event(join)
