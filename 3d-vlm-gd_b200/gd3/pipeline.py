@@ -94,13 +94,7 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
     if lays['g1'][3] != lays['g2'][3] or lays['h1'][3] != lays['h2'][3]:
         raise ValueError('distillation_step: the two views must share the channel count of each token map')
     Cd, Ch = lays['g1'][3], lays['h1'][3]
-    d1, inv1, ostr = ops.sample_fwd_raw(g1, lays['g1'][:5], geom, kp1, True)
-    d2, inv2, _ = ops.sample_fwd_raw(g2, lays['g2'][:5], geom, kp2, True)
-    # depth features of both views interleaved as sets (2p, 2p+1) = (view 1, view 2) of pair p
-    kf = torch.empty(P, 2, K, Ch, dtype=_F32, device=dev)
     pstr = (2 * K * Ch, Ch, 1)
-    ops.sample_fwd_raw(h1, lays['h1'][:5], geom, kp1, False, out=kf[:, 0], out_strides=pstr)
-    ops.sample_fwd_raw(h2, lays['h2'][:5], geom, kp2, False, out=kf[:, 1], out_strides=pstr)
     # patch masks and keypoint depths the caller did not supply
     prepared = {}
     for v, kp in (('1', kp1), ('2', kp2)):
@@ -129,22 +123,38 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
             side.wait_event(fork)
     else:
         s_kl = s_ap = s_rank = main
+    # the zero-initialised token-gradient maps of the backward scatter: filled on the caller's stream, which has nothing
+    # else to do until the branches join
+    shared1, shared2 = h1 is g1, h2 is g2
+    gmaps = {}
+    if backward:
+        for name, t, wanted in (('g1', g1, True), ('g2', g2, True), ('h1', h1, not shared1), ('h2', h2, not shared2)):
+            if wanted:
+                L_, P_, N_, C_, _, _ = lays[name]
+                gmaps[name] = torch.zeros((L_, P_, N_, C_) if t.dim() == 4 else (P_, N_, C_), dtype=_F32, device=dev)
 
     # ---- dense cost-volume KL (K1), side stream ----
     with torch.cuda.stream(s_kl):
         kl, gf1, gf2 = ops.cost_kl_raw(f1, f2, t12, t21, m1, m2, variant, grad_scale=w['kl'] * inv_p,
                                        want_grad=backward, pairs_per_group=pairs_per_group)
-    # ---- Smooth-AP (K2), side stream ----
+    # ---- Smooth-AP (K2), side stream: samples its own (normalised) descriptors ----
     with torch.cuda.stream(s_ap):
+        d1, inv1, ostr = ops.sample_fwd_raw(g1, lays['g1'][:5], geom, kp1, True)
+        d2, inv2, _ = ops.sample_fwd_raw(g2, lays['g2'][:5], geom, kp2, True)
         ap, gd1, gd2 = ops.smooth_ap_raw(d1, d2, batch['p3d1'], batch['p3d2'], variant, temp, thr_neg,
                                          grad_scale=w['ap'] * inv_p, want_grad=backward)
     # ---- relative depth: ranking on both views + cross-view L1 (K4): the caller's stream, or the high-priority side stream ----
     with torch.cuda.stream(s_rank):
+        # depth features of both views interleaved as sets (2p, 2p+1) = (view 1, view 2) of pair p
+        kf = torch.empty(P, 2, K, Ch, dtype=_F32, device=dev)
+        ops.sample_fwd_raw(h1, lays['h1'][:5], geom, kp1, False, out=kf[:, 0], out_strides=pstr)
+        ops.sample_fwd_raw(h2, lays['h2'][:5], geom, kp2, False, out=kf[:, 1], out_strides=pstr)
         lr, l1, gkf, gparams = ops.depth_head_raw(kf.reshape(2 * P, K, Ch), depths, params,
                                                   head.get('use_tanh', True), head.get('ln_eps', 1e-5), 0,
                                                   depth_threshold, 0.05, False, w_rank, w_l1, backward)
     if parallel_branches:
-        for side, outs in ((s_kl, (kl, gf1, gf2)), (s_ap, (ap, gd1, gd2)), (s_rank, (lr, l1, gkf, gparams))):
+        for side, outs in ((s_kl, (kl, gf1, gf2)), (s_ap, (ap, gd1, gd2, d1, d2, inv1, inv2)),
+                           (s_rank, (lr, l1, gkf, gparams, kf))):
             join = torch.cuda.Event()
             join.record(side)
             main.wait_event(join)
@@ -160,14 +170,9 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
 
     if backward:
         # scatter the keypoint gradients back into the token maps (K3 backward)
-        def zeros_like_tokens(name):
-            L_, P_, N_, C_, _, _ = lays[name]
-            return torch.zeros((L_, P_, N_, C_) if batch_dim4[name] else (P_, N_, C_), dtype=_F32, device=dev)
-        batch_dim4 = {'g1': g1.dim() == 4, 'g2': g2.dim() == 4, 'h1': h1.dim() == 4, 'h2': h2.dim() == 4}
         gk = gkf.reshape(P, 2, K, Ch)
         cont = (K * Cd, Cd, 1)
-        gg1, gg2 = zeros_like_tokens('g1'), zeros_like_tokens('g2')
-        shared1, shared2 = h1 is g1, h2 is g2
+        gg1, gg2 = gmaps['g1'], gmaps['g2']
         # descriptor gradients (through the normalisation); when the depth features come from the same map their
         # gradient shares the scatter
         ops.sample_bwd_raw(gd1, cont, d1, ostr, inv1, kp1, (lays['g1'][0], P, K, Cd), geom, True, gg1, lays['g1'][5],
@@ -177,7 +182,7 @@ def distillation_step(batch, variant='mast3r', grid=None, patch_size=14, backwar
         grads_h = {}
         for name, shared, view, kp in (('h1', shared1, 0, kp1), ('h2', shared2, 1, kp2)):
             if not shared:
-                gh = zeros_like_tokens(name)
+                gh = gmaps[name]
                 ops.sample_bwd_raw(gk[:, view], pstr, None, (0, 0, 0), None, kp, (lays[name][0], P, K, Ch), geom, False,
                                    gh, lays[name][5])
                 grads_h[name] = gh
