@@ -1286,6 +1286,25 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
   rp.du = w.du;
   rp.gparam = grad_params;
   rp.gparam_off = (int64_t)H * D;
+  // the cross-view L1 term first: it needs u only, and ahead of the pair kernel it overlaps the other branches of a step
+  // instead of sitting in the tail behind rank_pairs
+  if (l1) {
+    // about one wave of CTAs (2 per SM): a CTA walks several blocks of 16 keypoints
+    const int64_t gx_max = ceil_div<int64_t>(2 * (int64_t)num_sms(), S / 2);
+    const int64_t gx = std::min<int64_t>(ceil_div<int64_t>(K, 16), std::max<int64_t>(gx_max, 1));
+    dim3 grid((unsigned)gx, (unsigned)(S / 2));
+    if (backward)
+      {
+        GD3_PROF("rank_l1", stream);
+        rank_l1<true><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, w.du_extra);
+      }
+    else
+      {
+        GD3_PROF("rank_l1", stream);
+        rank_l1<false><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, nullptr);
+      }
+    GD3_CHECK_LAUNCH();
+  }
   {
     const size_t smem = sizeof(float) * (2 * TILE_A * H + TILE_A + 4 * H + 8) + 2048;      // + alignment slack of rank_pairs_w
     dim3 grid((unsigned)w.TA, (unsigned)w.TB, (unsigned)S);
@@ -1310,23 +1329,6 @@ int gd3_depth_head_loss(const float* feats, const float* depths, int64_t S, int6
     }
 #undef GD3_RANK_LAUNCH_T
 #undef GD3_RANK_LAUNCH
-    GD3_CHECK_LAUNCH();
-  }
-  if (l1) {
-    // about one wave of CTAs (2 per SM): a CTA walks several blocks of 16 keypoints
-    const int64_t gx_max = ceil_div<int64_t>(2 * (int64_t)num_sms(), S / 2);
-    const int64_t gx = std::min<int64_t>(ceil_div<int64_t>(K, 16), std::max<int64_t>(gx_max, 1));
-    dim3 grid((unsigned)gx, (unsigned)(S / 2));
-    if (backward)
-      {
-        GD3_PROF("rank_l1", stream);
-        rank_l1<true><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, w.du_extra);
-      }
-    else
-      {
-        GD3_PROF("rank_l1", stream);
-        rank_l1<false><<<grid, 256, 0, stream>>>(rp, w_l1, w.l1_sum, nullptr);
-      }
     GD3_CHECK_LAUNCH();
   }
   {
