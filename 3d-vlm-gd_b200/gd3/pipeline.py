@@ -219,7 +219,8 @@ class GraphedStep:
     """CUDA-graph replay of ``distillation_step`` for a batch that lives in fixed device buffers.
 
     The step is ~35 kernel launches and a dozen small torch fills / memsets; captured once, a replay issues them as
-    one graph launch (no per-launch gaps, no Python between kernels).  ``step = GraphedStep(batch, variant=...,
+    one graph launch (no per-launch gaps, no Python between kernels), with the KL, Smooth-AP and depth-ranking pipelines
+    as parallel branches (``parallel_branches=True`` unless the caller says otherwise).  ``step = GraphedStep(batch, variant=...,
     grid=...)``, then refresh the contents of ``batch``'s tensors in place and call ``step()``: it returns the same
     dict of (static) output tensors every time.  Capture allocates the outputs and workspaces from the graph's
     private pool, so the addresses baked into the TMA descriptors stay valid for every replay.
