@@ -19,13 +19,16 @@ constexpr int TILE = 128;      // rows of Q and rows of DB per tile
 constexpr int KC = 24;         // k-chunk held in shared memory (MASt3R descriptors are 24-d: one chunk)
 constexpr int THREADS = 256;   // 16 x 16 threads, 8 x 8 scores each
 // Shared-memory panels (no [k][row] transposition: that made every 4-byte cp.async a 32-way bank conflict):
-//   Q  panel  sq[row][k]              row stride KSQ = 28 floats: the 8 lanes of an LDS.128 wavefront that read
-//                                     different rows fall into disjoint groups of 4 banks
-//   DB panel  sd[row / 2][2 k + row % 2]   two adjacent DB rows interleaved, so that one LDS.128 yields the (k, k+1)
-//                                     values of a COLUMN PAIR as two register pairs -> FFMA2 on two scores at once;
-//                                     pair-row stride KSD = 52 floats (same bank argument)
-constexpr int KSQ = KC + 4;
-constexpr int KSD = 2 * KC + 4;
+//   DB panel  sd[row][k]               row-major, row stride KSD = 28 floats: a DB tile arrives as 16-byte cp.async copies
+//                                      (3 per thread and tile for 24-d descriptors)
+//   Q  panel  sq[row / 2][2 k + row % 2]   two adjacent query rows interleaved, so that one LDS.128 yields the (k, k+1)
+//                                      values of a ROW PAIR as two register pairs -> FFMA2 on two scores at once with
+//                                      the DB value as the broadcast scalar operand; pair-row stride KSQ = 52 floats.
+//                                      The query tile is resident for the whole CTA, so the 4-byte interleaving copies
+//                                      are paid once per CTA, not once per tile (round 1 interleaved the DB panel: the
+//                                      index arithmetic of its loader cost as many instructions as the FFMA work).
+constexpr int KSD = KC + 4;
+constexpr int KSQ = 2 * KC + 4;
 
 __device__ __forceinline__ unsigned long long pack_key(float score, uint32_t idx) {
   score = score + 0.0f;        // -0 -> +0 so that signed zeros tie like torch.max
@@ -47,18 +50,26 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Q panel: rows [row0, row0 + TILE) x columns [k0, k0 + kc) -> sq[row][k]; rows past n and columns up to the next
-// multiple of 4 are zero.  16-byte copies when the rows are 16-byte aligned (vec).
-__device__ __forceinline__ void load_q_async(float (*dst)[KSQ], const float* __restrict__ X, int n, int row0, int D, int k0,
-                                             int kc, bool vec) {
+// DB panel: rows [row0, row0 + TILE) x columns [k0, k0 + kc) -> sd[row][k]; rows past n and columns up to the next
+// multiple of 4 are zero.  16-byte copies when the rows are 16-byte aligned (vec); KC4 > 0 fixes the number of
+// 16-byte pieces per row at compile time (no integer division in the per-tile path).
+template <int KC4>
+__device__ __forceinline__ void load_db_vec(float (*dst)[KSD], const float* __restrict__ X, int n, int row0, int D, int k0,
+                                            int kc4_rt) {
+  const int kc4 = KC4 > 0 ? KC4 : kc4_rt;
+  for (int e = threadIdx.x; e < TILE * kc4; e += THREADS) {
+    const int row = e / kc4, j = e - row * kc4;
+    const int g = row0 + row;
+    if (g < n) cp_async16(&dst[row][4 * j], X + (size_t)g * D + k0 + 4 * j);
+    else *reinterpret_cast<float4*>(&dst[row][4 * j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void load_db_async(float (*dst)[KSD], const float* __restrict__ X, int n, int row0, int D, int k0,
+                                              int kc, bool vec) {
   const int kc4 = (kc + 3) >> 2;
   if (vec) {
-    for (int e = threadIdx.x; e < TILE * kc4; e += THREADS) {
-      const int row = e / kc4, j = e - row * kc4;
-      const int g = row0 + row;
-      if (g < n) cp_async16(&dst[row][4 * j], X + (size_t)g * D + k0 + 4 * j);
-      else *reinterpret_cast<float4*>(&dst[row][4 * j]) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    if (kc4 == KC / 4) load_db_vec<KC / 4>(dst, X, n, row0, D, k0, kc4);
+    else load_db_vec<0>(dst, X, n, row0, D, k0, kc4);
   } else {
     for (int e = threadIdx.x; e < TILE * 4 * kc4; e += THREADS) {
       const int row = e / (4 * kc4), k = e - row * (4 * kc4);
@@ -68,9 +79,9 @@ __device__ __forceinline__ void load_q_async(float (*dst)[KSQ], const float* __r
     }
   }
 }
-// DB panel, interleaved by row pairs: element (row, k) -> sd[row / 2][2 k + row % 2]
-__device__ __forceinline__ void load_db_async(float (*dst)[KSD], const float* __restrict__ X, int n, int row0, int D,
-                                              int k0, int kc) {
+// Q panel, interleaved by row pairs: element (row, k) -> sq[row / 2][2 k + row % 2]
+__device__ __forceinline__ void load_q_async(float (*dst)[KSQ], const float* __restrict__ X, int n, int row0, int D,
+                                             int k0, int kc) {
   const int kp = ((kc + 3) >> 2) << 2;
   for (int e = threadIdx.x; e < TILE * kp; e += THREADS) {
     const int row = e / kp, k = e - row * kp;
@@ -83,14 +94,14 @@ __device__ __forceinline__ void load_db_async(float (*dst)[KSD], const float* __
 
 // dynamic shared memory: sq | sd0 | sd1 | nq2 | nd2 | colbest[8][TILE] (BOTH only)
 inline size_t nn_smem_bytes(bool both) {
-  return sizeof(float) * (TILE * KSQ + 2 * (TILE / 2) * KSD + 2 * TILE) + (both ? sizeof(unsigned long long) * 8 * TILE : 0);
+  return sizeof(float) * ((TILE / 2) * KSQ + 2 * TILE * KSD + 2 * TILE) + (both ? sizeof(unsigned long long) * 8 * TILE : 0);
 }
 
 // Q: (nq, D) queries, DB: (ndb, D).  Each CTA: one 128-row query tile x `tiles_per_cta` DB tiles.
 // MODE 0: score = q.d ; MODE 1: score = -sqrt(max(|q|^2 + |d|^2 - 2 q.d, 0))
 // BOTH: also reduce every tile over its rows -> arg-best query for each DB row (the nn_B direction), from the
 // very same accumulators, so both directions see bit-identical scores in a single pass.
-// Thread (ty, tx) owns query rows ty * 8 + [0, 8) and the four DB column pairs 2 * (cp * 16 + tx) + {0, 1}.
+// Thread (ty, tx) owns the four query row pairs ty * 8 + 2 rp + {0, 1} and the eight DB columns c * 16 + tx.
 template <int MODE, bool BOTH>
 __global__ void __launch_bounds__(THREADS, 2)
     nn_tile_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, int ndb, int D, int tiles_per_cta,
@@ -104,18 +115,22 @@ __global__ void __launch_bounds__(THREADS, 2)
     if (nq < nq_min || (int)(blockIdx.x * TILE) >= nq) return;
   }
   float (*sq)[KSQ] = reinterpret_cast<float (*)[KSQ]>(nn_smem);
-  float (*sd0)[KSD] = reinterpret_cast<float (*)[KSD]>(sq + TILE);
-  float (*sd1)[KSD] = sd0 + TILE / 2;
-  float* nq2 = reinterpret_cast<float*>(sd1 + TILE / 2);
+  float (*sd0)[KSD] = reinterpret_cast<float (*)[KSD]>(sq + TILE / 2);
+  float (*sd1)[KSD] = sd0 + TILE;
+  float* nq2 = reinterpret_cast<float*>(sd1 + TILE);
   float* nd2 = nq2 + TILE;
   unsigned long long (*colbest)[TILE] = reinterpret_cast<unsigned long long (*)[TILE]>(nd2 + TILE);   // [8][TILE] if BOTH
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // lane -> (ty, tx): the 16 lanes an LDS.64 serves together hold 8 different tx (and both ty of the warp), so the
+  // DB reads, 8 rows of stride 28 floats x 2 floats, fall into disjoint banks; tx and tx + 8 would collide
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tx = (lane & 7) | ((lane >> 4) << 3);
+  const int ty = 2 * warp + ((lane >> 3) & 1);
   const int q0 = blockIdx.x * TILE;
   const int ndb_tiles = ceil_div(ndb, TILE);
   const int t_begin = blockIdx.y * tiles_per_cta;
   const int t_end = min(t_begin + tiles_per_cta, ndb_tiles);
   const bool one_chunk = D <= KC;      // whole descriptor in one chunk: Q stays resident, DB tiles are double-buffered
-  const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(Q) % 16 == 0);
+  const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(DB) % 16 == 0);
 
   // running per-row best as (value, index): a thread visits its columns in increasing index order, so a strict
   // '>' keeps the lowest index on ties; keys are only packed for the cross-thread reductions
@@ -138,19 +153,19 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
   }
   if (one_chunk && t_begin < t_end) {
-    load_q_async(sq, Q, nq, q0, D, 0, D, vec);
-    load_db_async(sd0, DB, ndb, t_begin * TILE, D, 0, D);
+    load_q_async(sq, Q, nq, q0, D, 0, D);
+    load_db_async(sd0, DB, ndb, t_begin * TILE, D, 0, D, vec);
     cp_async_commit();
   }
 
   for (int t = t_begin; t < t_end; ++t) {
     const int d0 = t * TILE;
     const int buf = one_chunk ? ((t - t_begin) & 1) : 0;
-    float2 acc[8][4];            // [query row][column pair]
+    float2 acc[4][8];            // [query row pair][column]
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
+      for (int c = 0; c < 8; ++c) acc[r][c] = make_float2(0.f, 0.f);
 
     if (MODE == 1) {
       __syncthreads();
@@ -167,14 +182,14 @@ __global__ void __launch_bounds__(THREADS, 2)
       const int kc = min(KC, D - k0);
       if (one_chunk) {
         // prefetch the next DB tile into the other buffer, then wait for the current one
-        if (t + 1 < t_end) load_db_async(buf ? sd0 : sd1, DB, ndb, (t + 1) * TILE, D, 0, D);
+        if (t + 1 < t_end) load_db_async(buf ? sd0 : sd1, DB, ndb, (t + 1) * TILE, D, 0, D, vec);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
       } else {
         __syncthreads();
-        load_q_async(sq, Q, nq, q0, D, k0, kc, vec);
-        load_db_async(sd0, DB, ndb, d0, D, k0, kc);
+        load_q_async(sq, Q, nq, q0, D, k0, kc);
+        load_db_async(sd0, DB, ndb, d0, D, k0, kc, vec);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
@@ -182,19 +197,19 @@ __global__ void __launch_bounds__(THREADS, 2)
       float (*sdb)[KSD] = buf ? sd1 : sd0;
       // 2 k at a time (columns past kc are zero: fma(0, 0, acc) leaves acc unchanged).  Per score the FFMA chain runs
       // over k in increasing order, so the result does not depend on the tiling; FFMA2 works on the two scores of
-      // a column pair with the query value broadcast.
+      // a row pair with the DB value broadcast.
       for (int k = 0; k < kc; k += 2) {
-        float2 a[8];
+        float4 a[4];             // (r0 k, r1 k, r0 k+1, r1 k+1)
 #pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float2*>(&sq[ty * 8 + r][k]);
+        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(&sq[ty * 4 + r][2 * k]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 b = *reinterpret_cast<const float4*>(&sdb[c * 16 + tx][2 * k]);   // (c0 k, c1 k, c0 k+1, c1 k+1)
+        for (int c = 0; c < 8; ++c) {
+          const float2 b = *reinterpret_cast<const float2*>(&sdb[c * 16 + tx][k]);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
+          for (int r = 0; r < 4; ++r) {
             float2 v = acc[r][c];
-            v = __ffma2_rn(make_float2(a[r].x, a[r].x), make_float2(b.x, b.y), v);
-            v = __ffma2_rn(make_float2(a[r].y, a[r].y), make_float2(b.z, b.w), v);
+            v = __ffma2_rn(make_float2(b.x, b.x), make_float2(a[r].x, a[r].y), v);
+            v = __ffma2_rn(make_float2(b.y, b.y), make_float2(a[r].z, a[r].w), v);
             acc[r][c] = v;
           }
         }
@@ -202,17 +217,17 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
     // ---- fold this tile into the running per-row best and, for BOTH, into the per-column best of this tile ----
     // Two stages per row / column: the maximum VALUE first (one FMNMX per score), then the lowest index that
-    // attains it (compare + select per score, under a branch for the rows: the running best rarely improves).
+    // attains it (compare + select per score, under ONE branch for the rows: the running best rarely improves).
     // This replaced a (value, index) update per score, which cost twice the FFMA work of a 24-d descriptor.
-    float sc[8][8];              // [query row][column c8]; column inside the tile: lc(c8) = 2 * ((c8 >> 1) * 16 + tx) + (c8 & 1)
+    float sc[8][8];              // [query row][column c]; column inside the tile: c * 16 + tx
     const bool partial = (d0 + TILE > ndb) || (q0 + TILE > nq);      // CTA-uniform
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float v = (c & 1) ? acc[r][c >> 1].y : acc[r][c >> 1].x;
+        float v = (r & 1) ? acc[r >> 1][c].y : acc[r >> 1][c].x;
         if (MODE == 1) {
-          const float d2 = (nq2[ty * 8 + r] + nd2[2 * ((c >> 1) * 16 + tx) + (c & 1)]) - 2.0f * v;
+          const float d2 = (nq2[ty * 8 + r] + nd2[c * 16 + tx]) - 2.0f * v;
           v = -sqrtf(fmaxf(d2, 0.f));
         }
         sc[r][c] = v;
@@ -223,13 +238,13 @@ __global__ void __launch_bounds__(THREADS, 2)
       for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const bool ok = (d0 + 2 * ((c >> 1) * 16 + tx) + (c & 1) < ndb) && (q0 + ty * 8 + r < nq);
+          const bool ok = (d0 + c * 16 + tx < ndb) && (q0 + ty * 8 + r < nq);
           sc[r][c] = ok ? sc[r][c] : -INFINITY;
         }
     }
     if (t == t_begin) {
       // first candidate of every row: with it in place a strict '>' implements "first maximum" even for -inf scores
-      const int d = d0 + 2 * tx;
+      const int d = d0 + tx;
 #pragma unroll
       for (int r = 0; r < 8; ++r)
         if (d < ndb) {
@@ -237,21 +252,30 @@ __global__ void __launch_bounds__(THREADS, 2)
           besti[r] = (uint32_t)d;
         }
     }
+    float rm[8];
+    bool improved = false;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       float m = sc[r][0];
 #pragma unroll
       for (int c = 1; c < 8; ++c) m = fmaxf(m, sc[r][c]);
-      if (m > bestv[r]) {
+      rm[r] = m;
+      improved |= m > bestv[r];
+    }
+    if (improved) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float m = rm[r];
         int ci = 7;
 #pragma unroll
         for (int c = 6; c >= 0; --c) ci = (sc[r][c] == m) ? c : ci;
-        bestv[r] = m;
-        besti[r] = (uint32_t)(d0 + 2 * ((ci >> 1) * 16 + tx) + (ci & 1));
+        const bool up = m > bestv[r];
+        besti[r] = up ? (uint32_t)(d0 + ci * 16 + tx) : besti[r];
+        bestv[r] = up ? m : bestv[r];
       }
     }
-    unsigned long long cb[8];
     if (BOTH) {
+      unsigned long long cb[8];
       const bool rows_ok = q0 + ty * 8 < nq;       // valid rows are a prefix of the thread's 8 rows
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -262,20 +286,17 @@ __global__ void __launch_bounds__(THREADS, 2)
 #pragma unroll
         for (int r = 7; r >= 1; --r) ri = (sc[r][c] == m) ? r : ri;
         ri = (sc[0][c] == m) ? 0 : ri;
-        const bool col_ok = d0 + 2 * ((c >> 1) * 16 + tx) + (c & 1) < ndb;
+        const bool col_ok = d0 + c * 16 + tx < ndb;
         cb[c] = (rows_ok && col_ok) ? pack_key(m, (uint32_t)(q0 + ty * 8 + ri)) : 0ull;
       }
-    }
-    if (BOTH) {
-      // the two ty groups of a warp first, then the 8 warps through shared memory, then one atomic per DB row
+      // the two ty groups of a warp first (lane bit 3), then the 8 warps through shared memory, then one atomic per DB row
 #pragma unroll
-      for (int c = 0; c < 8; ++c) cb[c] = kmax(cb[c], __shfl_xor_sync(0xffffffffu, cb[c], 16));
-      const int warp = threadIdx.x >> 5;
-      if ((threadIdx.x & 16) == 0) {
+      for (int c = 0; c < 8; ++c) cb[c] = kmax(cb[c], __shfl_xor_sync(0xffffffffu, cb[c], 8));
+      if ((lane & 8) == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) colbest[warp][2 * ((c >> 1) * 16 + tx) + (c & 1)] = cb[c];
+        for (int c = 0; c < 8; ++c) colbest[warp][c * 16 + tx] = cb[c];
       }
-      __syncthreads();
+      __syncthreads();           // also: every warp is done with this DB buffer before the next prefetch overwrites it
       if (threadIdx.x < TILE) {
         unsigned long long k = colbest[0][threadIdx.x];
 #pragma unroll
@@ -283,16 +304,19 @@ __global__ void __launch_bounds__(THREADS, 2)
         const int d = d0 + threadIdx.x;
         if (d < ndb && k != 0ull) atomicMax(&keysDB[d], k);
       }
+      // colbest is rewritten only after the barrier that follows the next tile's cp.async wait
+    } else if (one_chunk) {
+      __syncthreads();           // everyone is done with this DB buffer before the next prefetch overwrites it
     }
-    if (one_chunk) __syncthreads();   // everyone is done with this DB buffer before the next prefetch overwrites it
   }
   cp_async_wait<0>();
-  // reduce across the 16 threads that share a row group (same ty -> a half warp), then one atomic per row
+  // reduce across the 16 threads that share a row group (same ty: lane bits 4, 2, 1, 0), then one atomic per row
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     unsigned long long k = (besti[r] != 0xFFFFFFFFu) ? pack_key(bestv[r], besti[r]) : 0ull;
+    k = kmax(k, __shfl_xor_sync(0xffffffffu, k, 16));
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) k = kmax(k, __shfl_xor_sync(0xffffffffu, k, o));
+    for (int o = 4; o > 0; o >>= 1) k = kmax(k, __shfl_xor_sync(0xffffffffu, k, o));
     const int q = q0 + ty * 8 + r;
     if (tx == 0 && q < nq && k != 0ull) atomicMax(&keysQ[q], k);
   }
