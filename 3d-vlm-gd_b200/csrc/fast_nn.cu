@@ -15,9 +15,15 @@
 namespace gd3 {
 namespace {
 
-constexpr int TILE = 128;      // rows of Q and rows of DB per tile
+#ifndef NN_THREADS
+#define NN_THREADS 256
+#endif
+constexpr int TILE = 128;      // rows of DB per tile
 constexpr int KC = 24;         // k-chunk held in shared memory (MASt3R descriptors are 24-d: one chunk)
-constexpr int THREADS = 256;   // 16 x 16 threads, 8 x 8 scores each
+constexpr int THREADS = NN_THREADS;   // (THREADS / 16) x 16 threads, 8 x 8 scores each
+constexpr int TQ = THREADS / 2;       // rows of Q per CTA
+constexpr int NWARP = THREADS / 32;
+static_assert(THREADS >= TILE && THREADS % 32 == 0, "the per-tile column stages use one thread per DB row");
 // Shared-memory panels (no [k][row] transposition: that made every 4-byte cp.async a 32-way bank conflict):
 //   DB panel  sd[row][k]               row-major, row stride KSD = 28 floats: a DB tile arrives as 16-byte cp.async copies
 //                                      (3 per thread and tile for 24-d descriptors)
@@ -81,9 +87,23 @@ __device__ __forceinline__ void load_db_async(float (*dst)[KSD], const float* __
 }
 // Q panel, interleaved by row pairs: element (row, k) -> sq[row / 2][2 k + row % 2]
 __device__ __forceinline__ void load_q_async(float (*dst)[KSQ], const float* __restrict__ X, int n, int row0, int D,
-                                             int k0, int kc) {
+                                             int k0, int kc, bool vec) {
   const int kp = ((kc + 3) >> 2) << 2;
-  for (int e = threadIdx.x; e < TILE * kp; e += THREADS) {
+  if (vec && kp == kc) {
+    // 16-byte loads of both rows of a pair, interleaved in registers (synchronous: once per CTA for 24-d descriptors)
+    const int kc4 = kc >> 2;
+    for (int u = threadIdx.x; u < (TQ / 2) * kc4; u += THREADS) {
+      const int p = u / kc4, j = u - p * kc4;
+      const int g = row0 + 2 * p;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (g < n) v0 = __ldg(reinterpret_cast<const float4*>(X + (size_t)g * D + k0 + 4 * j));
+      if (g + 1 < n) v1 = __ldg(reinterpret_cast<const float4*>(X + (size_t)(g + 1) * D + k0 + 4 * j));
+      *reinterpret_cast<float4*>(&dst[p][8 * j]) = make_float4(v0.x, v1.x, v0.y, v1.y);
+      *reinterpret_cast<float4*>(&dst[p][8 * j + 4]) = make_float4(v0.z, v1.z, v0.w, v1.w);
+    }
+    return;
+  }
+  for (int e = threadIdx.x; e < TQ * kp; e += THREADS) {
     const int row = e / kp, k = e - row * kp;
     const int g = row0 + row;
     float* d = &dst[row >> 1][2 * k + (row & 1)];
@@ -92,18 +112,19 @@ __device__ __forceinline__ void load_q_async(float (*dst)[KSQ], const float* __r
   }
 }
 
-// dynamic shared memory: sq | sd0 | sd1 | nq2 | nd2 | colbest[8][TILE] (BOTH only)
+// dynamic shared memory: sq | sd0 | sd1 | nq2 | nd2 | colbest[NWARP][TILE] (BOTH only)
 inline size_t nn_smem_bytes(bool both) {
-  return sizeof(float) * ((TILE / 2) * KSQ + 2 * TILE * KSD + 2 * TILE) + (both ? sizeof(unsigned long long) * 8 * TILE : 0);
+  return sizeof(float) * ((TQ / 2) * KSQ + 2 * TILE * KSD + TQ + TILE) +
+         (both ? sizeof(unsigned long long) * NWARP * TILE : 0);
 }
 
-// Q: (nq, D) queries, DB: (ndb, D).  Each CTA: one 128-row query tile x `tiles_per_cta` DB tiles.
+// Q: (nq, D) queries, DB: (ndb, D).  Each CTA: one TQ-row query tile x `tiles_per_cta` DB tiles of 128 rows.
 // MODE 0: score = q.d ; MODE 1: score = -sqrt(max(|q|^2 + |d|^2 - 2 q.d, 0))
 // BOTH: also reduce every tile over its rows -> arg-best query for each DB row (the nn_B direction), from the
 // very same accumulators, so both directions see bit-identical scores in a single pass.
 // Thread (ty, tx) owns the four query row pairs ty * 8 + 2 rp + {0, 1} and the eight DB columns c * 16 + tx.
 template <int MODE, bool BOTH>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
     nn_tile_kernel(const float* __restrict__ Q, int nq, const float* __restrict__ DB, int ndb, int D, int tiles_per_cta,
                    unsigned long long* __restrict__ keysQ, unsigned long long* __restrict__ keysDB,
                    const int* __restrict__ nq_dev = nullptr, int nq_min = 0) {
@@ -112,25 +133,26 @@ __global__ void __launch_bounds__(THREADS, 2)
     // device-resident loops (gd3_fast_reciprocal_nn): the number of live queries is only known on the device; the
     // grid is sized for the maximum and surplus CTAs leave.  Below nq_min the streaming kernel takes the query.
     nq = *nq_dev;
-    if (nq < nq_min || (int)(blockIdx.x * TILE) >= nq) return;
+    if (nq < nq_min || (int)(blockIdx.x * TQ) >= nq) return;
   }
   float (*sq)[KSQ] = reinterpret_cast<float (*)[KSQ]>(nn_smem);
-  float (*sd0)[KSD] = reinterpret_cast<float (*)[KSD]>(sq + TILE / 2);
+  float (*sd0)[KSD] = reinterpret_cast<float (*)[KSD]>(sq + TQ / 2);
   float (*sd1)[KSD] = sd0 + TILE;
   float* nq2 = reinterpret_cast<float*>(sd1 + TILE);
-  float* nd2 = nq2 + TILE;
-  unsigned long long (*colbest)[TILE] = reinterpret_cast<unsigned long long (*)[TILE]>(nd2 + TILE);   // [8][TILE] if BOTH
+  float* nd2 = nq2 + TQ;
+  unsigned long long (*colbest)[TILE] = reinterpret_cast<unsigned long long (*)[TILE]>(nd2 + TILE);   // [NWARP][TILE] if BOTH
   // lane -> (ty, tx): the 16 lanes an LDS.64 serves together hold 8 different tx (and both ty of the warp), so the
   // DB reads, 8 rows of stride 28 floats x 2 floats, fall into disjoint banks; tx and tx + 8 would collide
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tx = (lane & 7) | ((lane >> 4) << 3);
   const int ty = 2 * warp + ((lane >> 3) & 1);
-  const int q0 = blockIdx.x * TILE;
+  const int q0 = blockIdx.x * TQ;
   const int ndb_tiles = ceil_div(ndb, TILE);
   const int t_begin = blockIdx.y * tiles_per_cta;
   const int t_end = min(t_begin + tiles_per_cta, ndb_tiles);
   const bool one_chunk = D <= KC;      // whole descriptor in one chunk: Q stays resident, DB tiles are double-buffered
   const bool vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(DB) % 16 == 0);
+  const bool vecq = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(Q) % 16 == 0);
 
   // running per-row best as (value, index): a thread visits its columns in increasing index order, so a strict
   // '>' keeps the lowest index on ties; keys are only packed for the cross-thread reductions
@@ -144,7 +166,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 
   if (MODE == 1) {
     // squared norms of this CTA's query rows (sequential k order, one thread per row)
-    if (threadIdx.x < TILE) {
+    if (threadIdx.x < TQ) {
       const int q = q0 + threadIdx.x;
       float s = 0.f;
       if (q < nq)
@@ -153,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
   }
   if (one_chunk && t_begin < t_end) {
-    load_q_async(sq, Q, nq, q0, D, 0, D);
+    load_q_async(sq, Q, nq, q0, D, 0, D, vecq);
     load_db_async(sd0, DB, ndb, t_begin * TILE, D, 0, D, vec);
     cp_async_commit();
   }
@@ -188,7 +210,7 @@ __global__ void __launch_bounds__(THREADS, 2)
         __syncthreads();
       } else {
         __syncthreads();
-        load_q_async(sq, Q, nq, q0, D, k0, kc);
+        load_q_async(sq, Q, nq, q0, D, k0, kc, vecq);
         load_db_async(sd0, DB, ndb, d0, D, k0, kc, vec);
         cp_async_commit();
         cp_async_wait<0>();
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 2)
       // 2 k at a time (columns past kc are zero: fma(0, 0, acc) leaves acc unchanged).  Per score the FFMA chain runs
       // over k in increasing order, so the result does not depend on the tiling; FFMA2 works on the two scores of
       // a row pair with the DB value broadcast.
-      for (int k = 0; k < kc; k += 2) {
+      auto step = [&](int k) {
         float4 a[4];             // (r0 k, r1 k, r0 k+1, r1 k+1)
 #pragma unroll
         for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(&sq[ty * 4 + r][2 * k]);
@@ -213,14 +235,15 @@ __global__ void __launch_bounds__(THREADS, 2)
             acc[r][c] = v;
           }
         }
-      }
+      };
+      for (int k = 0; k < kc; k += 2) step(k);
     }
     // ---- fold this tile into the running per-row best and, for BOTH, into the per-column best of this tile ----
     // Two stages per row / column: the maximum VALUE first (one FMNMX per score), then the lowest index that
     // attains it (compare + select per score, under ONE branch for the rows: the running best rarely improves).
     // This replaced a (value, index) update per score, which cost twice the FFMA work of a 24-d descriptor.
     float sc[8][8];              // [query row][column c]; column inside the tile: c * 16 + tx
-    const bool partial = (d0 + TILE > ndb) || (q0 + TILE > nq);      // CTA-uniform
+    const bool partial = (d0 + TILE > ndb) || (q0 + TQ > nq);      // CTA-uniform
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -300,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 2)
       if (threadIdx.x < TILE) {
         unsigned long long k = colbest[0][threadIdx.x];
 #pragma unroll
-        for (int w2 = 1; w2 < 8; ++w2) k = kmax(k, colbest[w2][threadIdx.x]);
+        for (int w2 = 1; w2 < NWARP; ++w2) k = kmax(k, colbest[w2][threadIdx.x]);
         const int d = d0 + threadIdx.x;
         if (d < ndb && k != 0ull) atomicMax(&keysDB[d], k);
       }
@@ -554,10 +577,10 @@ int nn_search(const float* Q, int64_t nq, const float* DB, int64_t ndb, int64_t 
     return GD3_OK;
   }
   if (both) GD3_CHECK_CUDA(cudaMemsetAsync(keysDB, 0, sizeof(unsigned long long) * ndb, stream));
-  const int q_tiles = (int)ceil_div<int64_t>(nq, TILE);
+  const int q_tiles = (int)ceil_div<int64_t>(nq, TQ);
   const int db_tiles = (int)ceil_div<int64_t>(ndb, TILE);
-  // aim at ~4 CTAs per SM over the whole grid so that short query sets still fill the chip
-  int y = (int)ceil_div<int64_t>(4 * num_sms(), q_tiles);
+  // aim at ~4 CTAs of 256 threads per SM over the whole grid so that short query sets still fill the chip
+  int y = (int)ceil_div<int64_t>(4 * (256 / THREADS) * num_sms(), q_tiles);
   y = y < 1 ? 1 : (y > db_tiles ? db_tiles : y);
   const int tiles_per_cta = ceil_div(db_tiles, y);
   y = ceil_div(db_tiles, tiles_per_cta);
@@ -610,9 +633,9 @@ int nn_query_dev(const float* Q, int nq_lo, int nq_max, const int* nq_dev, const
     }
   }
   if (nq_max >= tile_min) {
-    const int q_tiles = ceil_div(nq_max, TILE);
+    const int q_tiles = ceil_div(nq_max, TQ);
     const int db_tiles = (int)ceil_div<int64_t>(ndb, TILE);
-    int y = (int)ceil_div<int64_t>(4 * num_sms(), q_tiles);
+    int y = (int)ceil_div<int64_t>(4 * (256 / THREADS) * num_sms(), q_tiles);
     y = y < 1 ? 1 : (y > db_tiles ? db_tiles : y);
     const int tiles_per_cta = ceil_div(db_tiles, y);
     y = ceil_div(db_tiles, tiles_per_cta);
