@@ -23,6 +23,10 @@
 // the a side into a shared tile; the a index is staggered per warp so no two warps touch the same row in the same step.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include <type_traits>
 
 #include "../../include/gd3.h"
@@ -39,7 +43,7 @@ constexpr int HPL = 8;           // hidden units per lane
 // side.  Two 4-warp CTAs per SM: the pipelined kernel holds two steps of forward state and wants ~224 registers.
 constexpr int TILE_A = 64;
 constexpr int WARPS = 4;
-constexpr int B_PER_WARP_MAX = 32;                   // b rows a warp walks per CTA: 32, 16, 8, 4 or 2, chosen per problem (rank_b_per_warp)
+constexpr int B_PER_WARP_MAX = 32;                   // b rows a warp walks per CTA: 2 .. 32, chosen per problem (rank_b_per_warp)
 constexpr int CTAS_PER_SM = 2;
 
 // sum over the 16 lanes of a half warp (xor offsets < 16 never cross the halves)
@@ -1075,23 +1079,51 @@ struct RankWorkspace {
   int gs;        // sets per split-K group of the d W1 contraction
 };
 
-// b rows per warp of a rank_pairs CTA.  A CTA is the unit of scheduling, two fit on an SM: the kernel takes
-// ceil(CTAs / (2 SMs)) waves of (b_per_warp + 1) row walks (the +1 stands for loading the a tile and flushing its
-// gradient), so few sets (strong scaling: 8 pairs per GPU) or a ragged K want smaller b tiles, while large problems keep
-// 16 rows per warp, which writes the fewest a-side partial tiles.  Deterministic in (S, K): the workspace depends on it.
+// b rows per warp of a rank_pairs CTA.  A CTA is the unit of scheduling, two fit on an SM, and a CTA costs
+// (b rows it walks per warp + 1) row walks (the +1 stands for loading the a tile and flushing its gradient).  Large
+// problems keep 16 rows per warp, which issues the fewest a-side reductions; few sets (strong scaling: 8 pairs per GPU)
+// or a ragged K leave the last wave of such CTAs mostly empty, so every b_per_warp in [2, 32] is tried on a model of
+// the launch -- CTAs handed to the 2 x SMs slots in launch order (a tile fastest, then b tile, then set), the ragged
+// last b tile at its real length -- and a different tile has to beat 16 rows by 3 %.  cfg4 with 8 pairs per GPU:
+// 8 rows per warp were 3 waves x 9 walks, 7 rows are 2.97 waves x 8.  Deterministic in (S, K): the grid depends on it.
+double rank_launch_cost(int64_t S, int64_t K, int bpw, int64_t slots) {
+  const int64_t ta = ceil_div<int64_t>(K, TILE_A), tile_b = (int64_t)WARPS * bpw, tb = ceil_div<int64_t>(K, tile_b);
+  const int64_t last_rows = K - (tb - 1) * tile_b;
+  const int cost_full = bpw + 1, cost_last = (int)ceil_div<int64_t>(last_rows, WARPS) + 1;
+  const int64_t ctas = ta * tb * S;
+  const double work = (double)S * ta * ((tb - 1) * cost_full + cost_last);
+  if (ctas > 64 * slots) return work / slots;        // many waves: the tail does not matter
+  std::vector<int> finish((size_t)slots, 0);           // min-heap of the slots' finishing times
+  auto later = [](int x, int y) { return x > y; };
+  int end = 0;
+  for (int64_t z = 0; z < S; ++z)
+    for (int64_t y = 0; y < tb; ++y)
+      for (int64_t x = 0; x < ta; ++x) {
+        std::pop_heap(finish.begin(), finish.end(), later);
+        finish.back() += (y == tb - 1) ? cost_last : cost_full;
+        end = std::max(end, finish.back());
+        std::push_heap(finish.begin(), finish.end(), later);
+      }
+  return (double)end;
+}
 int rank_b_per_warp(int64_t S, int64_t K) {
+  static std::mutex mu;
+  static std::map<std::pair<int64_t, int64_t>, int> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({S, K});
+  if (it != cache.end()) return it->second;
   const int64_t slots = CTAS_PER_SM * (int64_t)num_sms();
-  const int64_t ta = ceil_div<int64_t>(K, TILE_A);
-  int best = B_PER_WARP_MAX;
-  double best_cost = 1e30;
-  for (int bpw = B_PER_WARP_MAX; bpw >= 2; bpw /= 2) {
-    const int64_t ctas = ta * ceil_div<int64_t>(K, (int64_t)WARPS * bpw) * S;
-    const double cost = (double)ceil_div<int64_t>(ctas, slots) * (bpw + 1);
-    if (cost < 0.97 * best_cost) {      // a smaller tile has to win by 3 %: it multiplies the partial-tile traffic
+  int best = 16;
+  double best_cost = 0.97 * rank_launch_cost(S, K, 16, slots);      // another tile has to win by 3 %
+  for (int bpw = B_PER_WARP_MAX; bpw >= 2; --bpw) {
+    if (bpw == 16) continue;
+    const double cost = rank_launch_cost(S, K, bpw, slots);
+    if (cost < best_cost) {
       best_cost = cost;
       best = bpw;
     }
   }
+  cache[{S, K}] = best;
   return best;
 }
 
