@@ -1084,8 +1084,8 @@ struct RankWorkspace {
 // problems keep 16 rows per warp, which issues the fewest a-side reductions; few sets (strong scaling: 8 pairs per GPU)
 // or a ragged K leave the last wave of such CTAs mostly empty, so every b_per_warp in [2, 32] is tried on a model of
 // the launch -- CTAs handed to the 2 x SMs slots in launch order (a tile fastest, then b tile, then set), the ragged
-// last b tile at its real length -- and a different tile has to beat 16 rows by 5 % (the model overstates the gain:
-// at cfg2 it prefers 32 rows by 3 %, which measures 1 % slower).  cfg4 with 8 pairs per GPU: 8 rows per warp were
+// last b tile at its real length -- and a different tile has to beat 16 rows by 5 % (the model overstates small
+// gains: at cfg2 it prefers 32 rows by 3 %, which measures the same, 2.412 against 2.413 ms).  cfg4 with 8 pairs per GPU: 8 rows per warp were
 // 3 waves x 9 walks, 7 rows are 2.97 waves x 8 (283 -> 263 us).  Deterministic in (S, K): the grid depends on it.
 double rank_launch_cost(int64_t S, int64_t K, int bpw, int64_t slots) {
   const int64_t ta = ceil_div<int64_t>(K, TILE_A), tile_b = (int64_t)WARPS * bpw, tb = ceil_div<int64_t>(K, tile_b);
