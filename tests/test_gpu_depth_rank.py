@@ -115,6 +115,38 @@ def test_depth_losses_full_size(K, D):
         assert_grad_close(got, want, name=n_, norm_rtol=3e-2)
 
 
+def test_depth_losses_batch_split_invariance():
+    """Size-independent property at the strong-scaling shard size of cfg4 (8 pairs per GPU, K = 300, D = 1024): the
+    per-set losses and the feature gradients of a batch equal those of its halves evaluated separately.  The pair
+    kernel picks a different b tile for every (sets, K) -- 7 rows per warp for 16 sets, another for 8 -- so this also
+    pins the launch-shape model of rank_b_per_warp."""
+    from gd3 import ops
+    P, K, D = 8, 300, 1024
+    head = olosses.DepthHead(D)
+    synth.load_head(head, synth.head_params(83, D))
+    h = cuda_head(head)
+    gen = synth._gen(84)
+    feats = (0.5 * torch.randn(2 * P, K, D, generator=gen)).cuda()
+    depths = torch.stack([synth.depths(120 + s, K) for s in range(2 * P)]).cuda()
+
+    def run(lo, hi):
+        x = feats[2 * lo:2 * hi].clone().requires_grad_(True)
+        n = hi - lo
+        total, lr, l1 = ops.depth_head_loss(h, x, depths[2 * lo:2 * hi], w_rank=torch.full((2 * n,), 0.5, device='cuda'),
+                                            w_l1=torch.full((n,), 0.7, device='cuda'))
+        total.backward()
+        return lr.detach(), l1.detach(), x.grad
+
+    lr, l1, g = run(0, P)
+    lr_a, l1_a, g_a = run(0, P // 2)
+    lr_b, l1_b, g_b = run(P // 2, P)
+    assert torch.allclose(lr, torch.cat([lr_a, lr_b]), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(l1, torch.cat([l1_a, l1_b]), rtol=1e-5, atol=1e-7)
+    g_split = torch.cat([g_a, g_b])
+    assert_grad_close(g, g_split, name='feats (whole batch vs halves)', norm_rtol=1e-3)
+    assert float((g - g_split).abs().max()) <= 1e-3 * float(g.abs().max())
+
+
 def test_depth_losses_edge_cases():
     from gd3 import ops
     from gd3.compat import losses

@@ -238,3 +238,23 @@ def test_reciprocal_nn_random_sizes(gd3mod, seed):
     a, b = fast_nn.bruteforce_reciprocal_nns(A, B, device='cuda', dist=dist)
     ra, rb = oracle_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist=dist)
     assert (a == ra).all() and (b == rb).all(), (na, nb, dim, dist)
+
+
+@pytest.mark.parametrize('shift_a,shift_b', [(1, 0), (0, 1), (3, 2)])
+def test_reciprocal_nn_misaligned_rows(gd3mod, shift_a, shift_b):
+    """24-d descriptors whose base pointers are not 16-byte aligned (views into a larger buffer at an odd float offset):
+    the tile kernel's loaders fall back from 16-byte to 4-byte copies; indices stay identical to the aligned call."""
+    from gd3 import _lib
+    A = synth.nn_exact_set(71, 700)
+    B = synth.nn_exact_set(72, 900)
+    ra, rb = oracle_nn.bruteforce_reciprocal_nns(A, B, device='cpu', dist='dot')
+
+    def shifted(x, s):
+        buf = torch.zeros(x.numel() + 8, device='cuda')
+        v = buf[s:s + x.numel()].view(x.shape)
+        v.copy_(x)
+        assert v.data_ptr() % 16 == (4 * s) % 16
+        return v
+
+    a, b = _lib.reciprocal_nn(shifted(A, shift_a), shifted(B, shift_b), dist='dot')
+    assert (a.cpu().numpy() == ra).all() and (b.cpu().numpy() == rb).all()
