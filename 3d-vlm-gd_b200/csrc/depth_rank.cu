@@ -1093,18 +1093,25 @@ double rank_launch_cost(int64_t S, int64_t K, int bpw, int64_t slots) {
   const int cost_full = bpw + 1, cost_last = (int)ceil_div<int64_t>(last_rows, WARPS) + 1;
   const int64_t ctas = ta * tb * S;
   const double work = (double)S * ta * ((tb - 1) * cost_full + cost_last);
-  if (ctas > 64 * slots) return work / slots;        // many waves: the tail does not matter
-  std::vector<int> finish((size_t)slots, 0);           // min-heap of the slots' finishing times
-  auto later = [](int x, int y) { return x > y; };
+  if (ctas > 16 * slots) return work / slots;        // many waves: the tail does not matter
+  // list scheduling in launch order with small integer costs: free_at[t] = slots that become free at time t
+  // (O(CTAs + makespan); K changes from step to step in training, so a new (S, K) must cost microseconds, not ms)
+  const int64_t horizon = (ceil_div<int64_t>(ctas, slots) + 2) * cost_full + 2;
+  std::vector<int> free_at((size_t)horizon, 0);
+  free_at[0] = (int)slots;
+  int64_t issued = 0, x = 0, y = 0;
   int end = 0;
-  for (int64_t z = 0; z < S; ++z)
-    for (int64_t y = 0; y < tb; ++y)
-      for (int64_t x = 0; x < ta; ++x) {
-        std::pop_heap(finish.begin(), finish.end(), later);
-        finish.back() += (y == tb - 1) ? cost_last : cost_full;
-        end = std::max(end, finish.back());
-        std::push_heap(finish.begin(), finish.end(), later);
+  for (int t = 0; issued < ctas && t < horizon - cost_full - 1; ++t)
+    for (int nfree = free_at[t]; nfree > 0 && issued < ctas; --nfree) {
+      const int done = t + ((y == tb - 1) ? cost_last : cost_full);
+      ++free_at[done];
+      end = std::max(end, done);
+      ++issued;
+      if (++x == ta) {
+        x = 0;
+        if (++y == tb) y = 0;
       }
+    }
   return (double)end;
 }
 int rank_b_per_warp(int64_t S, int64_t K) {
