@@ -23,6 +23,10 @@ SYMBOLS = {
     'gd3_reciprocal_nn_workspace': (_sz, [_i64, _i64]),
     'gd3_reciprocal_nn': (_int, [_vp, _i64, _vp, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
     'gd3_kp_prepare': (_int, [_vp, _i64, _i64, _i64, _i64, _int, _int, _vp, _i64, _vp, _vp, _vp]),
+    'gd3_masked_patch_cost': (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _int, _f32, _f32, _vp, _vp, _vp]),
+    'gd3_masked_patch_cost_backward': (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _int, _f32, _f32, _vp, _vp]),
+    'gd3_kl_divergence_map_workspace': (_sz, [_i64]),
+    'gd3_kl_divergence_map': (_int, [_vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
     'gd3_point_cloud_to_depth_workspace': (_sz, [_i64, _i64, _i64]),
     'gd3_point_cloud_to_depth': (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     'gd3_vggt_attn_workspace': (_sz, [_i64, _i64, _i64]),
@@ -121,6 +125,57 @@ def dtype_code(t):
 
 
 # ---------------------------------------------------------------------------------------------
+def masked_patch_cost(cost, mask1, mask2, use_softmax, eps, temperature, want_row_sum=True):
+    """out (B, hw, hw2) fp32 and the per-row sums (B * hw,) of ``get_masked_patch_cost`` for a CUDA volume."""
+    require_cuda(cost, mask1, mask2)
+    lib = load()
+    cost = cost.contiguous().float()
+    B, hw, hw2 = cost.shape
+    m1 = mask1.to(torch.bool).contiguous()
+    m2 = None if mask2 is None else mask2.to(torch.bool).contiguous()
+    if m1.numel() != hw or (m2 is not None and m2.numel() != hw2):
+        raise ValueError('get_masked_patch_cost: mask sizes do not match the volume')
+    out = torch.empty_like(cost)
+    row_sum = torch.empty(B * hw, dtype=torch.float32, device=cost.device) if want_row_sum else None
+    with torch.cuda.device(cost.device):
+        check(lib.gd3_masked_patch_cost(ptr(cost), B, hw, hw2, ptr(m1), ptr(m2), int(bool(use_softmax)), float(eps),
+                                        float(temperature), ptr(out), ptr(row_sum), stream_ptr()))
+    return out, row_sum, m1, m2
+
+
+def masked_patch_cost_backward(grad_out, out, row_sum, m1, m2, use_softmax, eps, temperature):
+    lib = load()
+    grad_out = grad_out.contiguous().float()
+    B, hw, hw2 = out.shape
+    grad_cost = torch.empty_like(out)
+    with torch.cuda.device(out.device):
+        check(lib.gd3_masked_patch_cost_backward(ptr(grad_out), ptr(out), ptr(row_sum), B, hw, hw2, ptr(m1), ptr(m2),
+                                                 int(bool(use_softmax)), float(eps), float(temperature), ptr(grad_cost),
+                                                 stream_ptr()))
+    return grad_cost
+
+
+def kl_divergence_map(teacher, student, eps, want_grad_student, want_grad_teacher):
+    """loss (0-d fp32) of ``kl_divergence_map`` for CUDA volumes of equal shape (..., n), and the two gradients (or None)."""
+    require_cuda(teacher, student)
+    if teacher.shape != student.shape:
+        raise ValueError(f'kl_divergence_map: shapes differ ({tuple(teacher.shape)} vs {tuple(student.shape)})')
+    lib = load()
+    t = teacher.contiguous().float()
+    s = student.contiguous().float()
+    n = t.shape[-1]
+    rows = t.numel() // max(n, 1)
+    loss = torch.empty((), dtype=torch.float32, device=t.device)
+    gs = torch.empty_like(s) if want_grad_student else None
+    gt = torch.empty_like(t) if want_grad_teacher else None
+    ws_bytes = lib.gd3_kl_divergence_map_workspace(rows)
+    ws = workspace(ws_bytes, t.device)
+    with torch.cuda.device(t.device):
+        check(lib.gd3_kl_divergence_map(ptr(t), ptr(s), rows, n, float(eps), ptr(loss), ptr(gs), ptr(gt), ptr(ws),
+                                        ws.numel(), stream_ptr()))
+    return loss, gs, gt
+
+
 def reciprocal_nn(A, B, dist='dot', want_A=True, want_B=True, packed=False):
     """nn_A, nn_B (int64 CUDA tensors or None) for fp32 CUDA descriptors A (nA, D), B (nB, D).
 

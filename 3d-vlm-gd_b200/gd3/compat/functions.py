@@ -1,9 +1,9 @@
 """CUDA drop-in for the hot-path subset of the reference's ``utils/functions.py``.
 
 Same names, argument order, defaults and return shapes.  Sampling, the keypoint patch mask and the keypoint depth run
-hand-written kernels through lib3dgd.so, and so does ``point_cloud_to_depth``; ``sigmoid`` / ``get_masked_patch_cost`` / ``filter_kp_by_conf`` are kept for
-callers that still hold materialised tensors and are plain device-side torch expressions (SURVEY.md section 8, row
-a7: "negligible; ... or leave in torch").
+hand-written kernels through lib3dgd.so, and so do ``point_cloud_to_depth`` and ``get_masked_patch_cost`` (forward and
+backward); ``sigmoid`` / ``filter_kp_by_conf`` are plain device-side torch expressions (SURVEY.md section 8, row a7:
+"negligible; ... or leave in torch").
 """
 import torch
 
@@ -49,17 +49,37 @@ def extract_kp_depth(depth_map, kp, window_size=3):
     return kd.to(depth_map.dtype)
 
 
-def get_masked_patch_cost(cost, mask_patch_1, mask_patch_2=None, eps=1e-8, use_softmax=False, temperature=1.0):
-    """``utils/functions.py:402-422`` on an already materialised (B, N, N2) volume.
+class _MaskedPatchCost(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cost, mask1, mask2, eps, use_softmax, temperature):
+        out, row_sum, m1, m2 = _lib.masked_patch_cost(cost, mask1, mask2, use_softmax, eps, temperature,
+                                                      want_row_sum=ctx.needs_input_grad[0])
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(out, row_sum, m1, *(() if m2 is None else (m2,)))
+            ctx.cfg = (bool(use_softmax), float(eps), float(temperature), cost.dtype)
+        return out if (use_softmax or cost.dtype == torch.float32) else out.to(cost.dtype)
 
-    Kept for callers that hold a volume; the fused path (``ops.cost_volume_kl``) never builds one.
+    @staticmethod
+    def backward(ctx, grad_out):
+        out, row_sum, m1, *rest = ctx.saved_tensors
+        use_softmax, eps, temperature, dtype = ctx.cfg
+        g = _lib.masked_patch_cost_backward(grad_out, out, row_sum, m1, rest[0] if rest else None, use_softmax, eps,
+                                            temperature)
+        return g.to(dtype), None, None, None, None, None
+
+
+def get_masked_patch_cost(cost, mask_patch_1, mask_patch_2=None, eps=1e-8, use_softmax=False, temperature=1.0):
+    """``utils/functions.py:402-422`` on an already materialised (B, N, N2) volume: rows of ``mask_patch_1 == False``
+    (and columns of ``mask_patch_2 == False``) are overwritten with 0, then every row is divided by its clamped sum or
+    goes through ``softmax(x / temperature)`` in fp32.
+
+    One CUDA kernel forward (``gd3_masked_patch_cost``) and one backward instead of clone + masked fill + softmax /
+    sum / clamp / divide.  Kept for callers that hold a volume; the fused path (``ops.cost_volume_kl``) never builds one.
     """
-    B, n1, n2 = cost.shape
-    keep = mask_patch_1[:, None] if mask_patch_2 is None else (mask_patch_1[:, None] & mask_patch_2[None, :])
-    out = torch.where(keep[None].expand(B, n1, n2), cost, cost.new_zeros(()))
-    if use_softmax:
-        return torch.softmax(out / temperature, dim=-1, dtype=torch.float32)
-    return out / out.sum(dim=-1, keepdim=True).clamp_min(eps)
+    require_cuda(cost, mask_patch_1, mask_patch_2)
+    if cost.dim() != 3:
+        raise ValueError(f'get_masked_patch_cost: expected a (B, hw, hw2) volume, got {tuple(cost.shape)}')
+    return _MaskedPatchCost.apply(cost, mask_patch_1, mask_patch_2, float(eps), bool(use_softmax), float(temperature))
 
 
 def filter_kp_by_conf(kp, conf_mask):

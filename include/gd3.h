@@ -252,6 +252,35 @@ int gd3_kp_prepare(const float* kp, int64_t P, int64_t K, int64_t H, int64_t W, 
                    int64_t depth_pair_stride, uint8_t* mask, float* kp_depth, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Volume-level helpers of the cost-volume loss for callers that already hold (B, hw, hw2) fp32
+ * volumes (the minimal drop-in of INTEGRATION.md section 2; gd3_cost_kl never builds a volume).
+ *
+ * gd3_masked_patch_cost replaces get_masked_patch_cost (utils/functions.py:402-422):
+ *   xm = cost with the rows of mask1 == 0 (and, when mask2 is given, the columns of mask2 == 0)
+ *   overwritten by 0;  use_softmax == 0: out = xm / clamp_min(sum_j xm, eps);
+ *   use_softmax != 0: out = softmax(xm / temperature) in fp32 (a masked row becomes uniform).
+ *   mask1 (hw) / mask2 (hw2 or NULL): bool bytes shared by the B volumes.  row_sum (B * hw) out:
+ *   the row's sum (or sum of exponentials), which the backward needs; may be NULL without one.
+ * gd3_masked_patch_cost_backward: grad_cost from grad_out and the saved out / row_sum
+ *   (softmax: y (dy - <dy, y>) / T;  row-normalisation: (dy - [sum >= eps] <dy, y>) / max(sum, eps);
+ *   0 at the overwritten entries).
+ *
+ * gd3_kl_divergence_map replaces kl_divergence_map (utils/losses.py:5-15) on (rows, n) volumes:
+ *   loss[0] = mean over the rows of sum_j t~ log(t~ / s~), t~ = clamp_min(teacher, eps), s~ likewise;
+ *   grad_student / grad_teacher (rows, n; either may be NULL) = d loss / d student, d loss / d teacher
+ *   from the same pass: -(t~ / s~) [s >= eps] / rows and (log(t~ / s~) + 1) [t >= eps] / rows.
+ *   The row sums go through the workspace and are added in a fixed order (deterministic).
+ * ------------------------------------------------------------------------------------------ */
+int gd3_masked_patch_cost(const float* cost, int64_t B, int64_t hw, int64_t hw2, const uint8_t* mask1, const uint8_t* mask2,
+                          int use_softmax, float eps, float temperature, float* out, float* row_sum, void* stream);
+int gd3_masked_patch_cost_backward(const float* grad_out, const float* out, const float* row_sum, int64_t B, int64_t hw,
+                                   int64_t hw2, const uint8_t* mask1, const uint8_t* mask2, int use_softmax, float eps,
+                                   float temperature, float* grad_cost, void* stream);
+size_t gd3_kl_divergence_map_workspace(int64_t rows);
+int gd3_kl_divergence_map(const float* teacher, const float* student, int64_t rows, int64_t n, float eps, float* loss,
+                          float* grad_student, float* grad_teacher, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * VGGT teacher cost volumes, one call per global-attention block (VGGT half).
  * Replaces the return_attn branch of vggt/layers/attention.py:73-84 (cross-view scores of the
  * patch tokens, softmax(scores / temperature) per head, both directions) together with what the
