@@ -17,7 +17,8 @@ def _volume(seed, B, n1, n2, scale=1.0):
     return scale * torch.randn(B, n1, n2, generator=g)
 
 
-@pytest.mark.parametrize('B,n1,n2', [(1, 64, 64), (2, 37, 50), (2, 1369, 1369), (1, 5, 3)])
+# row lengths: register-resident kernels (<= 1024, <= 2048, 16-byte rows), streaming vector kernel (> 2048), scalar (ragged)
+@pytest.mark.parametrize('B,n1,n2', [(1, 64, 64), (2, 37, 50), (2, 1369, 1369), (1, 5, 3), (2, 40, 1368), (1, 8, 2052)])
 @pytest.mark.parametrize('mode', ['rownorm', 'softmax', 'softmax_t', 'rownorm_m2', 'softmax_m2'])
 def test_masked_patch_cost_forward_backward(B, n1, n2, mode):
     from gd3.compat import functions as fn
