@@ -48,6 +48,7 @@ def test_version_and_error_channel():
     assert lib.gd3_reciprocal_nn_workspace(8192, 8192) >= 2 * 8192 * 8
     assert lib.gd3_smooth_ap_workspace(4, 512, 768, 1) > lib.gd3_smooth_ap_workspace(4, 512, 768, 0)
     assert lib.gd3_depth_head_loss_workspace(8, 300, 1024, 1, 1) > 0
+    assert lib.gd3_kl_divergence_map_workspace(32 * 1024) >= 32 * 1024 * 4
     assert lib.gd3_cost_kl_group_size(32, 1024, 768, 5) == 5
     assert 1 <= lib.gd3_cost_kl_group_size(32, 1024, 768, 0) <= 32
 
@@ -74,6 +75,10 @@ def test_no_cpu_fallback():
     from oracle.losses import DepthHead
     with pytest.raises(_lib.Gd3Error):
         losses.pairwise_logistic_ranking_loss(DepthHead(8), f, torch.rand(1, 16))
+    with pytest.raises(_lib.Gd3Error):
+        losses.kl_divergence_map(t, t)
+    with pytest.raises(_lib.Gd3Error):
+        functions.get_masked_patch_cost(t, torch.ones(16, dtype=torch.bool))
 
 
 def test_product_code_never_imports_the_oracle():
